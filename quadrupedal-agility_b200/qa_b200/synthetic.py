@@ -1,0 +1,217 @@
+"""Synthetic / recorded-state generator for the BBC go2_locomotion hot path.
+
+IsaacGym (the physics backend) is not installable outside its own python-3.8 binary
+distribution, so tests and `bench.py` drive the env with *synthetic state snapshots*
+whose distributions follow SURVEY.md section 8(d).  One snapshot = the simulator-owned
+tensors (`root_states`, `dof_state`, `rigid_body_state`, `contact_forces`) plus the env's
+persistent buffers, named exactly like the reference attributes
+(bbc/legged_gym/envs/base/legged_robot.py:743-859).
+
+All draws come from a seeded CPU `torch.Generator`, so the CPU oracle and the CUDA path
+see bit-identical inputs.
+"""
+import math
+from typing import Dict, Optional
+
+import torch
+
+from . import config as C
+from .config import BbcEnvConfig
+
+
+def _rand(gen, *shape):
+    return torch.rand(*shape, generator=gen, dtype=torch.float32)
+
+
+def _randn(gen, *shape):
+    return torch.randn(*shape, generator=gen, dtype=torch.float32)
+
+
+def make_static(cfg: BbcEnvConfig, seed: int = 1234, terrain_cells: int = 1600) -> Dict[str, torch.Tensor]:
+    """Per-env constants created once at env construction (legged_robot.py:796-859, 1051-1076)."""
+    gen = torch.Generator().manual_seed(seed * 7919 + 1)
+    N = cfg.num_envs
+    st = {}
+    # EASI motor strength (legged_robot.py:861-888, go2_locomotion_config.py:90-95)
+    easi_mean = [1.270984856442925803e+00, 1.269402596100474012e+00, 8.637638584658215990e-01,
+                 8.973783516018792872e-01, 7.804512147922660903e-01, 1.069519100829913416e+00]
+    easi_var = [9.087216265313172864e-03, 6.342416661098186637e-03, 1.376369951477590226e-05,
+                4.598280851616735464e-05, 5.266858327126125377e-06, 8.413655048485571975e-05]
+    mean_p = torch.tensor([easi_mean[0], easi_mean[2], easi_mean[4]] * 4)
+    mean_d = torch.tensor([easi_mean[1], easi_mean[3], easi_mean[5]] * 4)
+    std_p = torch.tensor([easi_var[0], easi_var[2], easi_var[4]] * 4)
+    std_d = torch.tensor([easi_var[1], easi_var[3], easi_var[5]] * 4)
+    ms_p = mean_p + std_p * _randn(gen, N, 12)
+    ms_d = mean_d + std_d * _randn(gen, N, 12)
+    st["motor_strength"] = torch.stack([ms_p, ms_d], dim=0).contiguous()            # (2,N,12)
+    mass = torch.empty(N, 4)
+    mass[:, 0] = 1.5 * _rand(gen, N)
+    mass[:, 1:] = 0.2 * _rand(gen, N, 3) - 0.1
+    st["mass_params_tensor"] = mass
+    st["friction_coeffs_tensor"] = (0.6 + 1.4 * _rand(gen, N, 1))
+    origins = torch.zeros(N, 3)
+    origins[:, :2] = torch.floor(_rand(gen, N, 2) * 10.0) * 10.0 + 5.0              # terrain tile centres
+    st["env_origins"] = origins
+    st["height_samples"] = torch.randint(-10, 11, (terrain_cells, terrain_cells), generator=gen,
+                                         dtype=torch.int16)
+    gx, gy = torch.meshgrid(torch.tensor(cfg.measured_points_x), torch.tensor(cfg.measured_points_y),
+                            indexing="ij")
+    pts = torch.zeros(cfg.num_height_points, 3)
+    pts[:, 0] = gx.flatten()
+    pts[:, 1] = gy.flatten()
+    st["height_points"] = pts                                                       # (187,3), same for every env
+    st["default_dof_pos"] = torch.tensor(cfg.default_dof_pos, dtype=torch.float32).unsqueeze(0)
+    st["p_gains"] = torch.full((12,), cfg.stiffness, dtype=torch.float32)
+    st["d_gains"] = torch.full((12,), cfg.damping, dtype=torch.float32)
+    st["torque_limits"] = torch.tensor(cfg.torque_limits, dtype=torch.float32)
+    st["dof_vel_limits"] = torch.tensor(cfg.dof_vel_limits, dtype=torch.float32)
+    st["dof_pos_limits"] = cfg.soft_dof_pos_limits()
+    st["noise_scale_vec"] = cfg.noise_scale_vec()
+    st["prior_parameters"] = torch.ones(C.DIM_C) * (1.0 / C.DIM_C)
+    return st
+
+
+def _center_cell_margin(cfg, root_states):
+    """Distance (in cells, float64) of the centre height-scan point to the nearest cell boundary."""
+    q = root_states[:, 3:7].double()
+    yaw_q = q.clone()
+    yaw_q[:, :2] = 0
+    yaw_q = yaw_q / yaw_q.norm(dim=-1, keepdim=True)
+    idx = cfg.center_height_index
+    ny = len(cfg.measured_points_y)
+    px = cfg.measured_points_x[idx // ny]
+    py = cfg.measured_points_y[idx % ny]
+    ang = 2.0 * torch.atan2(yaw_q[:, 2], yaw_q[:, 3])
+    wx = math.cos(0) * 0 + (torch.cos(ang) * px - torch.sin(ang) * py) + root_states[:, 0].double()
+    wy = (torch.sin(ang) * px + torch.cos(ang) * py) + root_states[:, 1].double()
+    fx = (wx + cfg.border_size) / cfg.horizontal_scale
+    fy = (wy + cfg.border_size) / cfg.horizontal_scale
+    mx = torch.minimum(fx - torch.floor(fx), torch.ceil(fx) - fx)
+    my = torch.minimum(fy - torch.floor(fy), torch.ceil(fy) - fy)
+    return torch.minimum(mx, my)
+
+
+def make_snapshot(cfg: BbcEnvConfig, seed: int = 1234, step: int = 0,
+                  reset_frac: float = 0.015, plant_frac: float = 0.003) -> Dict[str, torch.Tensor]:
+    """One post-physics state snapshot (what IsaacGym's refresh_* calls would expose) plus
+    the env's carried buffers.  Distributions: SURVEY.md section 8(d)."""
+    gen = torch.Generator().manual_seed(seed * 1000003 + step * 101 + 17)
+    N, B = cfg.num_envs, cfg.num_bodies
+    s = {}
+    root = torch.zeros(N, 13)
+    root[:, 0:2] = -2.0 + 104.0 * _rand(gen, N, 2)
+    root[:, 2] = 0.22 + 0.23 * _rand(gen, N)
+    yaw = (2 * _rand(gen, N) - 1) * math.pi
+    roll = 0.15 * _randn(gen, N)
+    pitch = 0.15 * _randn(gen, N)
+    cy, sy = torch.cos(yaw * 0.5), torch.sin(yaw * 0.5)
+    cr, sr = torch.cos(roll * 0.5), torch.sin(roll * 0.5)
+    cp, sp = torch.cos(pitch * 0.5), torch.sin(pitch * 0.5)
+    quat = torch.stack([cy * sr * cp - sy * cr * sp, cy * cr * sp + sy * sr * cp,
+                        sy * cr * cp - cy * sr * sp, cy * cr * cp + sy * sr * sp], dim=-1)
+    root[:, 3:7] = quat / quat.norm(dim=-1, keepdim=True)
+    root[:, 7:10] = 0.6 * _randn(gen, N, 3)
+    root[:, 10:13] = 0.8 * _randn(gen, N, 3)
+    # keep the centre height-scan sample away from knife-edge cell boundaries: torch-CPU and
+    # torch-CUDA themselves disagree there by one ulp (-> a different int16 cell).
+    for _ in range(8):
+        bad = _center_cell_margin(cfg, root) < 2e-3
+        if not bool(bad.any()):
+            break
+        root[bad, 0:2] += 0.013
+    s["root_states"] = root
+
+    q0 = torch.tensor(cfg.default_dof_pos)
+    dof = torch.zeros(N, 12, 2)
+    dof[..., 0] = q0 + 0.25 * _randn(gen, N, 12)
+    dof[..., 1] = 3.0 * _randn(gen, N, 12)
+    s["dof_state"] = dof.reshape(N * 12, 2).contiguous()
+
+    rb = torch.zeros(N, B, 13)
+    rb[:, :, 0:3] = root[:, None, 0:3] + 0.2 * _randn(gen, N, B, 3)
+    rb[:, :, 2] = rb[:, :, 2].clamp(min=0.0)
+    rb[:, :, 6] = 1.0
+    s["rigid_body_state"] = rb.reshape(N * B, 13).contiguous()
+
+    cf = torch.zeros(N, B, 3)
+    feet = torch.tensor(cfg.feet_indices)
+    fz = torch.relu(40.0 + 40.0 * _randn(gen, N, 4)) * (_rand(gen, N, 4) > 0.5).float()
+    fxy = 5.0 * _randn(gen, N, 4, 2) * (fz > 0).float().unsqueeze(-1)
+    cf[:, feet, 2] = fz
+    cf[:, feet, 0:2] = fxy
+    nonfoot = torch.tensor([i for i in range(B) if i not in cfg.feet_indices])
+    hit = _rand(gen, N, len(nonfoot)) < (reset_frac / 5.0)
+    mag = 1.0 + 49.0 * _rand(gen, N, len(nonfoot))
+    dirv = _randn(gen, N, len(nonfoot), 3)
+    dirv = dirv / dirv.norm(dim=-1, keepdim=True)
+    cf[:, nonfoot] = dirv * (mag * hit.float()).unsqueeze(-1)
+    s["contact_forces"] = cf
+
+    s["actions"] = _randn(gen, N, 12)
+    s["last_actions"] = s["actions"] + 0.3 * _randn(gen, N, 12)
+    s["torques_org"] = 8.0 * _randn(gen, N, 12)
+    s["last_torques_org"] = 8.0 * _randn(gen, N, 12)
+    s["last_dof_vel"] = dof[..., 1] + 0.5 * _randn(gen, N, 12)
+    s["last_root_vel"] = torch.zeros(N, 6)
+    ah = _randn(gen, N, C.ACTION_BUF_LEN, 12)
+    s["action_history_buf"] = ah
+    ep = torch.randint(0, 1000, (N,), generator=gen, dtype=torch.int64)
+    planted = _rand(gen, N)
+    pf = plant_frac
+    ep = torch.where(planted < pf, torch.full_like(ep, 1000), ep)                   # -> time-out after += 1
+    ep = torch.where((planted >= pf) & (planted < 2 * pf), torch.full_like(ep, 299), ep)     # -> resample
+    ep = torch.where((planted >= 2 * pf) & (planted < 3 * pf), torch.full_like(ep, 0), ep)   # -> ep_len == 1 (history fill)
+    root[(planted >= 3 * pf) & (planted < 3.3 * pf), 2] = -7.0                      # fell off the world (:174)
+    s["episode_length_buf"] = ep
+    s["last_contacts"] = _rand(gen, N, 4) > 0.5
+
+    c_idx = torch.randint(0, C.DIM_C, (N,), generator=gen)
+    s["latent_c"] = torch.nn.functional.one_hot(c_idx, C.DIM_C).float()
+    s["latent_eps"] = 2 * _rand(gen, N, 1) - 1
+    cmd = torch.zeros(N, 5)
+    lx = torch.tensor(cfg.lin_vel_x)[c_idx]
+    ly = torch.tensor(cfg.lin_vel_y)[c_idx]
+    lw = torch.tensor(cfg.ang_vel_yaw)[c_idx]
+    cmd[:, 0] = lx[:, 0] + (lx[:, 1] - lx[:, 0]) * _rand(gen, N)
+    cmd[:, 1] = ly[:, 0] + (ly[:, 1] - ly[:, 0]) * _rand(gen, N)
+    cmd[:, 2] = lw[:, 0] + (lw[:, 1] - lw[:, 0]) * _rand(gen, N)
+    jump = (c_idx == C.DIM_C - 1).float()
+    cmd[:, 3] = (cfg.jump_height[0] + (cfg.jump_height[1] - cfg.jump_height[0]) * _rand(gen, N)) * jump
+    cmd[:, 4] = (cfg.locomotion_height[0] + (cfg.locomotion_height[1] - cfg.locomotion_height[0]) * _rand(gen, N)) * (1 - jump)
+    s["commands"] = cmd
+    # 60 % of the envs roughly track their command (so that most clipped rewards are > 0)
+    track = _rand(gen, N) < 0.6
+    v_body = torch.stack([cmd[:, 0], cmd[:, 1], torch.zeros(N)], dim=-1) + 0.2 * _randn(gen, N, 3)
+    qv, qw = root[:, 3:6], root[:, 6:7]
+    tt = 2.0 * torch.cross(qv, v_body, dim=-1)
+    v_world = v_body + qw * tt + torch.cross(qv, tt, dim=-1)
+    root[track, 7:10] = v_world[track]
+    root[track, 12] = (cmd[:, 2] + 0.2 * _randn(gen, N))[track]
+
+    s["obs_history_buf"] = 0.5 * _randn(gen, N, C.HISTORY_LEN, C.NUM_PROP)
+    s["obs_disc_buf"] = 0.5 * _randn(gen, N, C.NUM_OBS_DISC)
+    s["episode_sums"] = 0.1 * _randn(gen, C.NUM_REWARDS, N)
+    s["feet_air_time"] = _rand(gen, N, 4)
+    return s
+
+
+def make_rng_draws(cfg: BbcEnvConfig, seed: int = 1234, step: int = 0,
+                   num_clips_per_mode: Optional[list] = None) -> Dict[str, torch.Tensor]:
+    """Dense per-env pre-drawn randoms for *parity mode* (SURVEY.md section 7 "RNG parity").
+
+    The reference draws on variable-length index sets from three RNG sources (torch, numpy,
+    multinomial; legged_robot.py:504-540, motion_loader.py:311-341).  In parity mode every env
+    gets its own pre-drawn value; the kernels and the oracle consume only the entries of envs
+    that actually resample / reset."""
+    gen = torch.Generator().manual_seed(seed * 2000003 + step * 211 + 5)
+    N = cfg.num_envs
+    d = {}
+    d["noise_u"] = _rand(gen, N, C.OBS_WIDTH)
+    for tag in ("rs", "rt"):                       # rs: periodic resample site, rt: reset site
+        d[f"{tag}_eps_u"] = torch.rand(N, generator=gen, dtype=torch.float64)
+        d[f"{tag}_c_idx"] = torch.randint(0, C.DIM_C, (N,), generator=gen, dtype=torch.int32)
+        d[f"{tag}_cmd_u"] = _rand(gen, N, 5)
+    d["push_u"] = _rand(gen, N, 2)
+    d["mocap_clip_u"] = torch.rand(N, generator=gen, dtype=torch.float64)   # -> clip within the env's mode
+    d["mocap_time_u"] = torch.rand(N, generator=gen, dtype=torch.float64)   # np.random.uniform (float64)
+    return d
