@@ -1,0 +1,270 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/sec of the BBC go2_locomotion hot path on N B200s (BASELINE.json metric).
+
+One "step" = one training iteration of the reference loop (on_policy_runner.py:156-225) over synthetic
+recorded state: T=24 env steps of 4096 envs per GPU (policy act -> action push -> 4x PD torques -> fused
+post-physics -> disc reward -> storage) followed by GAE and the PPO update, IsaacGym excluded
+(SURVEY.md 8d).  value = T*N*n_gpus / seconds_per_iteration, exactly `Perf/total_fps`
+(on_policy_runner.py:256) without the physics time.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+`--impl reference` times the reference algorithm's CPU path (the oracle port, all host threads) on a
+bounded sample of the same workload; it is the only place besides `cpu_baseline` where `oracle/` runs.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "quadrupedal-agility_b200"))
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+METRIC = "env_steps_per_sec"
+UNIT = "env-steps/s"
+T_STEPS = 24
+ENVS_PER_GPU = 4096
+K2_BYTES_PER_ENV = 11158          # algorithmic bytes of the fused obs/reward kernel per env-step
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.proc, self.gpu = None, gpu_index
+        self.path = f"/tmp/qa_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_workload(rank, device, n_envs=ENVS_PER_GPU, steps=T_STEPS):
+    """Synthetic recorded rollout for this rank: T state snapshots + static per-env constants (seed 1234+rank)."""
+    from qa_b200 import synthetic
+    from qa_b200.config import BbcEnvConfig
+    from qa_b200.mocap import MocapTable
+    cfg = BbcEnvConfig(num_envs=n_envs)
+    seed = 1234 + rank
+    static = synthetic.make_static(cfg, seed=seed)
+    snaps = [synthetic.make_snapshot(cfg, seed=seed, step=t) for t in range(steps)]
+    table = MocapTable.from_npz(os.path.join(ROOT, "tests", "golden", "mocap_lb_table.npz"))
+    return cfg, static, snaps, table
+
+
+SIM_KEYS = ("root_states", "dof_state", "rigid_body_state", "contact_forces")
+
+
+def run_ours(args):
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+    from qa_b200.pipeline import BbcIteration
+    cfg, static, snaps, table = build_workload(rank, dev)
+    it = BbcIteration(cfg, static, snaps, table, device=dev, seed=1234 + rank, world_size=world)
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ("value") ----------------------------------------------------------
+    for _ in range(args.warmup):
+        it.run_resident()
+    it.reset_counters()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    total_ms = 0.0
+    for _ in range(args.steps):
+        flush.fill_(1)                                                 # L2 flush between timed iterations (untimed)
+        torch.cuda.synchronize()
+        ev0.record()
+        it.run_resident(profile_k2=True)
+        ev1.record()
+        ev1.synchronize()
+        total_ms += ev0.elapsed_time(ev1)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    k2_ms, k2_launches = it.k2_time_ms()
+    launches = it.launch_count
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    value = T_STEPS * cfg.num_envs * world / (ms_per_step * 1e-3)
+
+    # ---- end-to-end timing through the public API with HOST buffers ("e2e") ---------------------------
+    for _ in range(max(1, args.warmup // 2)):
+        it.run_host()
+    barrier()
+    e2e_ms = 0.0
+    for _ in range(args.steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        ev0.record()
+        it.run_host()
+        ev1.record()
+        ev1.synchronize()
+        e2e_ms += ev0.elapsed_time(ev1)
+    barrier()
+    t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = T_STEPS * cfg.num_envs * world / (float(t.item()) / args.steps * 1e-3)
+
+    if rank == 0:
+        pk, pk_src = peaks()
+        k2_avg_s = (k2_ms / max(k2_launches, 1)) * 1e-3
+        achieved = K2_BYTES_PER_ENV * cfg.num_envs / k2_avg_s / 1e9 if k2_launches else None
+        cpu = cpu_baseline_sample() if world == 1 and not args.no_cpu_baseline else None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": it.dtype_name, "data": "synthetic",
+            "config": {"workload": it.workload_name, "envs_per_gpu": cfg.num_envs, "steps_per_env": T_STEPS,
+                       "stages": it.stage_names, "rng": "in-kernel Philox4x32-10",
+                       "l2": "256 MiB flush between timed iterations; per-step working set 46 MB < 126 MB L2",
+                       "parallelism": f"env-sharded dp{world}"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": it.h2d_bytes_per_iteration,
+                    "d2h_bytes_per_step": it.d2h_bytes_per_iteration},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": "k_post_physics_bbc", "achieved": achieved,
+                         "peak": pk["hbm_gbs"], "peak_source": pk_src, "unit": "GB/s",
+                         "frac": (achieved / pk["hbm_gbs"]) if achieved else None,
+                         "us_per_launch": k2_avg_s * 1e6, "launches_timed": k2_launches,
+                         "algorithmic_bytes_per_launch": K2_BYTES_PER_ENV * cfg.num_envs, "traffic": it.k2_traffic_bytes},
+            "clocks": clocks,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_reference_iteration(n_envs, steps, threads):
+    """The reference algorithm's CPU path (oracle port) over `steps` env steps + GAE.  Returns seconds."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import bbc_env as O
+    import trainer as OT
+    from qa_b200 import synthetic
+    torch.set_num_threads(threads)
+    cfg, static, snaps, table = build_workload(0, "cpu", n_envs=n_envs, steps=steps)
+    draws = [synthetic.make_rng_draws(cfg, seed=1234, step=t) for t in range(steps)]
+    for d in draws:
+        d["mocap_clip_idx"] = table.sample_clip(d["rt_c_idx"], d["mocap_clip_u"])
+    from qa_b200 import pipeline
+    return pipeline.cpu_oracle_iteration(O, OT, cfg, static, snaps, draws, table)
+
+
+def cpu_baseline_sample():
+    threads = os.cpu_count() or 1
+    steps = 6                                                   # bounded sample: 6 of the 24 env steps, full 4096 envs
+    cpu_reference_iteration(ENVS_PER_GPU, 2, threads)          # warm-up
+    t0 = time.perf_counter()
+    sec, stages = cpu_reference_iteration(ENVS_PER_GPU, steps, threads)
+    _ = time.perf_counter() - t0
+    return {"value": steps * ENVS_PER_GPU / sec, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{steps} env steps x {ENVS_PER_GPU} envs + GAE through oracle/ (torch {torch.__version__} CPU, "
+                      f"{threads} threads); stages: {stages}"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    steps_per_sample = 6
+    for _ in range(min(args.warmup, 2)):
+        cpu_reference_iteration(ENVS_PER_GPU, 2, threads)
+    secs = []
+    for _ in range(args.steps):
+        sec, stages = cpu_reference_iteration(ENVS_PER_GPU, steps_per_sample, threads)
+        secs.append(sec)
+    sec = sum(secs) / len(secs)
+    value = steps_per_sample * ENVS_PER_GPU / sec
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3 * (T_STEPS / steps_per_sample), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "bbc_go2_locomotion_4096x24 (CPU sample)", "envs_per_gpu": ENVS_PER_GPU,
+                       "steps_per_env": T_STEPS, "stages": stages},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"{steps_per_sample} env steps x {ENVS_PER_GPU} envs + GAE per timed step, "
+                                       f"oracle/ port of the reference on torch {torch.__version__} CPU"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,318 @@
+/*
+ * qa_b200.h -- C ABI of libqa_b200.so, the B200-native (sm_100a) hot path of
+ * NJU-RLC/quadrupedal-agility.
+ *
+ * The reference has no FFI of its own (it is pure Python over PyTorch eager ops); the
+ * drop-in boundary is the Python class API.  This header is the C
+ * ABI that sits directly under those classes: every entry point replaces one reference
+ * method (cited as file:line under /root/reference), takes a POD struct of raw DEVICE
+ * pointers + sizes + scalar config, enqueues its kernel(s) on the caller's CUDA stream and
+ * returns without synchronising.
+ *
+ * Conventions
+ *   - PyTorch (or any caller) owns every buffer; the library never allocates or frees
+ *     device memory and keeps no global state.
+ *   - return value: 0 on success, a positive cudaError_t if a launch failed, a negative
+ *     QA_E* code if argument validation failed.  The Python wrappers raise RuntimeError.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ *   - float = IEEE fp32; masks are uint8 (torch.bool / torch.uint8 storage); all arrays
+ *     are contiguous unless a pitch/stride argument says otherwise.
+ *   - one host thread per process / GPU (matches the reference's single-threaded loop).
+ */
+#ifndef QA_B200_H_
+#define QA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QA_ABI_VERSION 1
+
+#define QA_EINVAL (-1)   /* null pointer / bad size */
+#define QA_ERANGE (-2)   /* dimension outside the compiled limits */
+
+#define QA_NUM_DOF 12
+#define QA_NUM_PROP 57
+#define QA_OBS_WIDTH 671       /* 57+4+29+570+11, go2_locomotion_config.py:12-17 */
+#define QA_HIST_LEN 10
+#define QA_NUM_OBS_DISC 49
+#define QA_DIM_C 5
+#define QA_NUM_COMMANDS 5
+#define QA_NUM_REWARDS 14
+#define QA_EPSUM_PITCH 16
+#define QA_ACT_HIST_LEN 8
+#define QA_MOCAP_W 49
+#define QA_MAX_BODIES 32
+
+int qa_version(void);
+/* human readable build string ("sm_100a, nvcc 12.9, ...") */
+const char* qa_build_info(void);
+/* sizeof() of argument struct number `which` (order of declaration in this header, QaActionPushArgs
+ * = 0 ... QaGaeArgs = 9; -1 if unknown): a layout handshake for FFI mirrors of these structs */
+int qa_struct_size(int which);
+
+/* ------------------------------------------------------------------------------------------
+ * K0  action history push + delayed-action select + clip
+ *     replaces bbc/legged_gym/envs/base/legged_robot.py:84-98 (LeggedRobot.step, front half)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct QaActionPushArgs {
+    int32_t num_envs;
+    int32_t delay;                  /* self.delay, 0..7 */
+    float clip;                     /* clip_actions / action_scale */
+    const float* actions_in;        /* (N,12) policy output */
+    float* action_history_buf;      /* (N,8,12) in/out, shifted in place */
+    float* actions_out;             /* (N,12) delayed + clipped action  (self.actions) */
+} QaActionPushArgs;
+int qa_action_push(const QaActionPushArgs* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K1  PD torques  -- replaces LeggedRobot._compute_torques, legged_robot.py:547-579
+ *     (control_type 'P', randomize_motor=True).  Called `decimation` (4) times per env step.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct QaTorqueArgs {
+    int32_t num_envs;
+    float action_scale;             /* 0.25 */
+    float hip_scale_reduction;      /* 0.5, applied to DOF 0,3,6,9 */
+    const float* actions;           /* (N,12) */
+    const float* dof_state;         /* (N,12,2) interleaved pos,vel (IsaacGym layout) */
+    const float* motor_strength;    /* (2,N,12) */
+    const float* p_gains;           /* (12) */
+    const float* d_gains;           /* (12) */
+    const float* default_dof_pos;   /* (12) */
+    const float* torque_limits;     /* (12) */
+    float* torques;                 /* (N,12) clipped, goes to set_dof_actuation_force_tensor */
+    float* torques_org;             /* (N,12) un-clipped (self.torques_org) */
+} QaTorqueArgs;
+int qa_pd_torques(const QaTorqueArgs* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K3  terrain height scan -- replaces LeggedRobot._get_heights, legged_robot.py:1190-1228
+ * ------------------------------------------------------------------------------------------ */
+typedef struct QaTerrain {
+    const int16_t* height_samples;  /* (rows, cols) */
+    int32_t rows, cols;
+    float border_size;              /* 30 */
+    float horizontal_scale;         /* 0.1 */
+    float vertical_scale;           /* 0.005 */
+} QaTerrain;
+
+typedef struct QaHeightScanArgs {
+    int32_t num_envs;
+    int32_t num_points;             /* 187 */
+    const float* root_states;       /* (N,13) */
+    const float* height_points;     /* (P,3) base-frame sample points (identical for all envs) */
+    QaTerrain terrain;
+    float* measured_heights;        /* (N,P) */
+} QaHeightScanArgs;
+int qa_height_scan(const QaHeightScanArgs* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Mocap clip table (reference-state initialisation at reset)
+ *   MotionLoader.get_full_frame_batch -> traj_time_sample_batch -> get_full_frame_at_time_batch,
+ *   bbc/rsl_rl/datasets/motion_loader.py:461-474, 333-341, 410-447; quaternion_slerp,
+ *   bbc/rsl_rl/utils/utils.py:126-159
+ * ------------------------------------------------------------------------------------------ */
+typedef struct QaMocapTable {
+    const float* frames;            /* (F,49) */
+    const int32_t* clip_start;      /* (K) */
+    const double* clip_nframes;     /* (K) */
+    const double* clip_len_s;       /* (K) */
+    const double* clip_frame_dur;   /* (K) */
+    const int32_t* mode_offset;     /* (DIM_C+1) CSR of clips per behaviour mode */
+    const int32_t* mode_clips;      /* (K) */
+    const double* mode_cdf;         /* (K) inclusive CDF of the within-mode clip weights */
+    int32_t num_clips;
+    int32_t num_frames;
+} QaMocapTable;
+
+/* K4 standalone blend (also used inside K2's reset path) */
+typedef struct QaMocapBlendArgs {
+    int32_t num;                    /* rows to produce */
+    QaMocapTable table;
+    const int32_t* clip_idx;        /* (num) */
+    const double* time_u;           /* (num) uniform draws in [0,1) */
+    double time_between_frames;     /* env.dt */
+    int32_t disc_obs_len;           /* 2 */
+    float* frames_out;              /* (num,49) */
+} QaMocapBlendArgs;
+int qa_mocap_blend(const QaMocapBlendArgs* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K2  fused post-physics step: counters, base-frame quantities, contact filter, periodic
+ *     command/latent resampling, centre terrain height, push, termination, 14 reward terms,
+ *     reset (resample + mocap frame blend + state write), observations (671 / 49 / history),
+ *     last_* carries, reset statistics.
+ *     replaces LeggedRobot.post_physics_step and everything it calls:
+ *       post_physics_step :124-166, _post_physics_step_callback :449-472, _resample_* :474-540,
+ *       _push_robots :682-687, check_termination :168-176, compute_reward :242-259 with the
+ *       active _reward_* :1248-1335, reset_idx :178-240 (+ _reset_dofs_mocap :598-612,
+ *       _reset_root_states_mocap :660-680), compute_observations :261-331,
+ *       compute_flat_key_pos :1377-1396.
+ *     One warp per env; see DESIGN.md for the data layout and the byte budget.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct QaBbcConst {
+    /* body roles */
+    int32_t num_bodies;
+    int32_t feet_indices[4];
+    uint32_t termination_body_mask;     /* bit b set: body b terminates the episode on contact */
+    uint32_t penalised_body_mask;       /* bit b set: body b counts for _reward_collision */
+    /* per-DOF constants */
+    float default_dof_pos[12];
+    float dof_pos_lower[12];            /* soft limits */
+    float dof_pos_upper[12];
+    float dof_vel_limits[12];
+    float torque_limits[12];
+    uint32_t hip_dof_mask;              /* bit d set: DOF d is a hip joint (0,3,6,9) */
+    /* reward scales (already multiplied by dt), dir() order, legged_robot.py:922-946 */
+    float reward_scale[QA_NUM_REWARDS];
+    float dt;                           /* 0.02 */
+    float tracking_sigma;
+    float soft_dof_vel_limit;
+    float soft_torque_limit;
+    float jump_goal;                    /* 10 */
+    float jump_height_lo;               /* command_ranges["jump_height"][0] = 0.45 */
+    int32_t only_positive_rewards;
+    /* episode bookkeeping */
+    float max_episode_length;           /* 1000 */
+    int32_t resample_period;            /* 300 */
+    float episode_length_s;             /* 20 */
+    /* command ranges per mode */
+    float lin_vel_x[QA_DIM_C][2];
+    float lin_vel_y[QA_DIM_C][2];
+    float ang_vel_yaw[QA_DIM_C][2];
+    float jump_h_lo, jump_h_span;       /* lo and (float)(hi-lo) with hi-lo evaluated in double */
+    float loco_h_lo, loco_h_span;
+    float lin_vel_x_clip, lin_vel_y_clip, ang_vel_yaw_clip;
+    float prior_cdf[QA_DIM_C];          /* softmax(prior/T) inclusive CDF, used in Philox mode */
+    /* observation scales */
+    float s_lin_vel, s_ang_vel, s_dof_pos, s_dof_vel, s_key_pos, s_foot_contact;
+    float s_lin_vel_dist, s_ang_vel_dist;
+    float clip_obs;
+    int32_t add_noise;
+    int32_t root_height_obs;
+    int32_t measure_heights;
+    /* centre height sample point (base frame), legged_robot.py:266 */
+    float center_px, center_py;
+    float max_push_vel_xy;
+    double time_between_frames;         /* env.dt as double (mocap time sampling) */
+    int32_t disc_obs_len;
+} QaBbcConst;
+
+#define QA_K2_BULK_STORE 1u   /* obs/priv rows leave through TMA bulk stores (needs pitch 671, N % 4 == 0) */
+
+typedef struct QaBbcStepArgs {
+    int32_t num_envs;
+    int32_t do_push;                    /* common_step_counter % push_interval == 0 */
+    int32_t obs_pitch;                  /* floats between obs rows (>= 671) */
+    int32_t contact_ring_head;          /* slot of the contact rings written this step */
+    int32_t contact_ring_len;           /* 100 */
+    uint32_t flags;                     /* QA_K2_* */
+    uint64_t rng_seed;                  /* Philox key   (perf mode) */
+    uint64_t rng_step;                  /* Philox counter high word: global step index */
+
+    /* simulator-owned state (IsaacGym tensors), updated in place on reset / push */
+    float* root_states;                 /* (N,13) */
+    float* dof_state;                   /* (N,12,2) */
+    const float* rigid_body_state;      /* (N,B,13) */
+    const float* contact_forces;        /* (N,B,3) */
+
+    /* per-env constants */
+    const float* motor_strength;        /* (2,N,12) */
+    const float* mass_params;           /* (N,4) */
+    const float* friction_coeffs;       /* (N,1) */
+    const float* env_origins;           /* (N,3) */
+    const float* noise_scale_vec;       /* (671) */
+    QaTerrain terrain;
+    QaMocapTable mocap;
+
+    /* carried env buffers, in/out */
+    int64_t* episode_length_buf;        /* (N) */
+    uint8_t* last_contacts;             /* (N,4) */
+    float* commands;                    /* (N,5) */
+    float* latent_eps;                  /* (N,1) */
+    float* latent_c;                    /* (N,5) */
+    const float* actions;               /* (N,12) */
+    float* last_actions;                /* (N,12) */
+    const float* torques_org;           /* (N,12) */
+    float* last_torques_org;            /* (N,12) */
+    float* last_dof_vel;                /* (N,12) */
+    float* last_root_vel;               /* (N,6) */
+    float* action_history_buf;          /* (N,8,12) */
+    float* obs_history_buf;             /* (N,10,57) */
+    float* episode_sums;                /* (N,16) env-major, first 14 used */
+    float* feet_air_time;               /* (N,4) */
+    float* contact_buf;                 /* (N,L,4) ring, may be NULL */
+    float* contact_force_buf;           /* (N,L,4) ring, may be NULL */
+
+    /* step outputs */
+    float* obs_buf;                     /* (N,pitch) */
+    float* privileged_obs_buf;          /* (N,pitch); may alias obs_buf (byte-identical content) */
+    float* obs_disc_buf;                /* (N,49) this step's; the previous one stays intact for terminal states */
+    float* rew_buf;                     /* (N) */
+    uint8_t* reset_buf;                 /* (N) */
+    uint8_t* time_out_buf;              /* (N) */
+    float* base_lin_vel;                /* (N,3) */
+    float* base_ang_vel;                /* (N,3) */
+    float* projected_gravity;           /* (N,3) */
+    float* rpy;                         /* (N,3) roll,pitch,yaw */
+    float* feet_forces;                 /* (N,4) */
+    uint8_t* contact_filt;              /* (N,4) */
+    float* root_h;                      /* (N) z - centre terrain height, pre-reset (rewards) */
+
+    /* reset statistics, written by the last CTA to finish */
+    float* episode_rew_means;           /* (14) mean over reset envs / episode_length_s; untouched if no reset */
+    uint8_t* time_outs_latched;         /* (N) extras["time_outs"]: refreshed only on steps with >=1 reset (:239-240) */
+    int32_t* num_resets;                /* (1) */
+    void* workspace;                    /* >= 128 bytes, zero-initialised once by the caller */
+
+    /* parity-mode random draws (dense, one per env).  ALL NULL => in-kernel Philox4x32-10 */
+    const float* noise_u;               /* (N,671) */
+    const double* rs_eps_u;             /* (N) periodic-resample site */
+    const int32_t* rs_c_idx;            /* (N) */
+    const float* rs_cmd_u;              /* (N,5) */
+    const double* rt_eps_u;             /* (N) reset site */
+    const int32_t* rt_c_idx;            /* (N) */
+    const float* rt_cmd_u;              /* (N,5) */
+    const float* push_u;                /* (N,2) */
+    const int32_t* mocap_clip_idx;      /* (N) */
+    const double* mocap_time_u;         /* (N) */
+} QaBbcStepArgs;
+int qa_post_physics_bbc(const QaBbcConst* c, const QaBbcStepArgs* a, void* stream);
+
+/* sorted compaction of the reset mask (+ gather of the terminal discriminator states)
+ * replaces `reset_buf.nonzero()` / `obs_disc_buf[env_ids]`, legged_robot.py:153-154 */
+typedef struct QaCompactArgs {
+    int32_t num_envs;
+    const uint8_t* reset_buf;           /* (N) */
+    const float* prev_obs_disc_buf;     /* (N,49) may be NULL */
+    int64_t* reset_env_ids;             /* (N) first *count entries valid, ascending */
+    int32_t* reset_env_ids_i32;         /* (N) same, int32 for gym.set_*_indexed; may be NULL */
+    float* terminal_disc_states;        /* (N,49) first *count rows valid; may be NULL */
+    int32_t* count;                     /* (1) */
+} QaCompactArgs;
+int qa_compact_resets(const QaCompactArgs* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K5  GAE -- replaces RolloutStorage.compute_returns, bbc/rsl_rl/storage/rollout_storage.py:97-111
+ *     (identical in tsc/rsl_rl/storage/rollout_storage.py:102-116)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct QaGaeArgs {
+    int32_t num_steps;                  /* T = 24 (<= 32: one warp scans the horizon) */
+    int32_t num_envs;
+    float gamma, lam;
+    const float* rewards;               /* (T,N) */
+    const float* values;                /* (T,N) */
+    const uint8_t* dones;               /* (T,N) */
+    const float* last_values;           /* (N) */
+    float* returns;                     /* (T,N) */
+    float* advantages;                  /* (T,N) normalised: (A-mean)/(std_unbiased+1e-8) */
+    double* workspace;                  /* >= 64 bytes, zero-initialised once by the caller */
+} QaGaeArgs;
+int qa_gae(const QaGaeArgs* a, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QA_B200_H_ */

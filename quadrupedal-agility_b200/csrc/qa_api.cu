@@ -1,0 +1,30 @@
+// Library identification for libqa_b200.so.
+#include "qa_b200.h"
+
+extern "C" int qa_version(void) { return QA_ABI_VERSION; }
+
+extern "C" const char* qa_build_info(void) {
+    return "libqa_b200 abi " 
+#define QA_STR2(x) #x
+#define QA_STR(x) QA_STR2(x)
+        QA_STR(QA_ABI_VERSION) ", sm_100a, nvcc " QA_STR(__CUDACC_VER_MAJOR__) "." QA_STR(__CUDACC_VER_MINOR__)
+        ", built " __DATE__;
+}
+
+// Layout handshake for FFI bindings: sizeof() of every argument struct, so that a ctypes / cgo /
+// JNI mirror can assert it agrees with this build before passing pointers.
+extern "C" int qa_struct_size(int which) {
+    switch (which) {
+        case 0: return (int)sizeof(QaActionPushArgs);
+        case 1: return (int)sizeof(QaTorqueArgs);
+        case 2: return (int)sizeof(QaTerrain);
+        case 3: return (int)sizeof(QaHeightScanArgs);
+        case 4: return (int)sizeof(QaMocapTable);
+        case 5: return (int)sizeof(QaMocapBlendArgs);
+        case 6: return (int)sizeof(QaBbcConst);
+        case 7: return (int)sizeof(QaBbcStepArgs);
+        case 8: return (int)sizeof(QaCompactArgs);
+        case 9: return (int)sizeof(QaGaeArgs);
+        default: return -1;
+    }
+}

@@ -1,0 +1,162 @@
+"""ctypes mirror of `include/qa_b200.h` and the loader of `libqa_b200.so`.
+
+The library is the product: there is NO fallback.  `load()` raises if the shared object
+has not been built (run `python -c "import __graft_entry__ as g; g.build()"` or
+`make -C quadrupedal-agility_b200`), and every op wrapper raises `RuntimeError` on a
+non-zero return code.
+"""
+import ctypes as C
+import os
+
+QA_ABI_VERSION = 1
+NUM_DOF, DIM_C, NUM_REWARDS = 12, 5, 14
+QA_K2_BULK_STORE = 1
+
+f32p = C.POINTER(C.c_float)
+vp = C.c_void_p   # every device pointer travels as a plain address
+
+
+class QaActionPushArgs(C.Structure):
+    _fields_ = [("num_envs", C.c_int32), ("delay", C.c_int32), ("clip", C.c_float),
+                ("actions_in", vp), ("action_history_buf", vp), ("actions_out", vp)]
+
+
+class QaTorqueArgs(C.Structure):
+    _fields_ = [("num_envs", C.c_int32), ("action_scale", C.c_float), ("hip_scale_reduction", C.c_float),
+                ("actions", vp), ("dof_state", vp), ("motor_strength", vp), ("p_gains", vp), ("d_gains", vp),
+                ("default_dof_pos", vp), ("torque_limits", vp), ("torques", vp), ("torques_org", vp)]
+
+
+class QaTerrain(C.Structure):
+    _fields_ = [("height_samples", vp), ("rows", C.c_int32), ("cols", C.c_int32), ("border_size", C.c_float),
+                ("horizontal_scale", C.c_float), ("vertical_scale", C.c_float)]
+
+
+class QaHeightScanArgs(C.Structure):
+    _fields_ = [("num_envs", C.c_int32), ("num_points", C.c_int32), ("root_states", vp), ("height_points", vp),
+                ("terrain", QaTerrain), ("measured_heights", vp)]
+
+
+class QaMocapTable(C.Structure):
+    _fields_ = [("frames", vp), ("clip_start", vp), ("clip_nframes", vp), ("clip_len_s", vp),
+                ("clip_frame_dur", vp), ("mode_offset", vp), ("mode_clips", vp), ("mode_cdf", vp),
+                ("num_clips", C.c_int32), ("num_frames", C.c_int32)]
+
+
+class QaMocapBlendArgs(C.Structure):
+    _fields_ = [("num", C.c_int32), ("table", QaMocapTable), ("clip_idx", vp), ("time_u", vp),
+                ("time_between_frames", C.c_double), ("disc_obs_len", C.c_int32), ("frames_out", vp)]
+
+
+class QaBbcConst(C.Structure):
+    _fields_ = [
+        ("num_bodies", C.c_int32), ("feet_indices", C.c_int32 * 4),
+        ("termination_body_mask", C.c_uint32), ("penalised_body_mask", C.c_uint32),
+        ("default_dof_pos", C.c_float * 12), ("dof_pos_lower", C.c_float * 12), ("dof_pos_upper", C.c_float * 12),
+        ("dof_vel_limits", C.c_float * 12), ("torque_limits", C.c_float * 12), ("hip_dof_mask", C.c_uint32),
+        ("reward_scale", C.c_float * NUM_REWARDS), ("dt", C.c_float), ("tracking_sigma", C.c_float),
+        ("soft_dof_vel_limit", C.c_float), ("soft_torque_limit", C.c_float), ("jump_goal", C.c_float),
+        ("jump_height_lo", C.c_float), ("only_positive_rewards", C.c_int32),
+        ("max_episode_length", C.c_float), ("resample_period", C.c_int32), ("episode_length_s", C.c_float),
+        ("lin_vel_x", (C.c_float * 2) * DIM_C), ("lin_vel_y", (C.c_float * 2) * DIM_C),
+        ("ang_vel_yaw", (C.c_float * 2) * DIM_C),
+        ("jump_h_lo", C.c_float), ("jump_h_span", C.c_float), ("loco_h_lo", C.c_float), ("loco_h_span", C.c_float),
+        ("lin_vel_x_clip", C.c_float), ("lin_vel_y_clip", C.c_float), ("ang_vel_yaw_clip", C.c_float),
+        ("prior_cdf", C.c_float * DIM_C),
+        ("s_lin_vel", C.c_float), ("s_ang_vel", C.c_float), ("s_dof_pos", C.c_float), ("s_dof_vel", C.c_float),
+        ("s_key_pos", C.c_float), ("s_foot_contact", C.c_float), ("s_lin_vel_dist", C.c_float),
+        ("s_ang_vel_dist", C.c_float), ("clip_obs", C.c_float), ("add_noise", C.c_int32),
+        ("root_height_obs", C.c_int32), ("measure_heights", C.c_int32),
+        ("center_px", C.c_float), ("center_py", C.c_float), ("max_push_vel_xy", C.c_float),
+        ("time_between_frames", C.c_double), ("disc_obs_len", C.c_int32),
+    ]
+
+
+class QaBbcStepArgs(C.Structure):
+    _fields_ = [
+        ("num_envs", C.c_int32), ("do_push", C.c_int32), ("obs_pitch", C.c_int32),
+        ("contact_ring_head", C.c_int32), ("contact_ring_len", C.c_int32), ("flags", C.c_uint32),
+        ("rng_seed", C.c_uint64), ("rng_step", C.c_uint64),
+        ("root_states", vp), ("dof_state", vp), ("rigid_body_state", vp), ("contact_forces", vp),
+        ("motor_strength", vp), ("mass_params", vp), ("friction_coeffs", vp), ("env_origins", vp),
+        ("noise_scale_vec", vp), ("terrain", QaTerrain), ("mocap", QaMocapTable),
+        ("episode_length_buf", vp), ("last_contacts", vp), ("commands", vp), ("latent_eps", vp),
+        ("latent_c", vp), ("actions", vp), ("last_actions", vp), ("torques_org", vp),
+        ("last_torques_org", vp), ("last_dof_vel", vp), ("last_root_vel", vp), ("action_history_buf", vp),
+        ("obs_history_buf", vp), ("episode_sums", vp), ("feet_air_time", vp), ("contact_buf", vp),
+        ("contact_force_buf", vp),
+        ("obs_buf", vp), ("privileged_obs_buf", vp), ("obs_disc_buf", vp), ("rew_buf", vp), ("reset_buf", vp),
+        ("time_out_buf", vp), ("base_lin_vel", vp), ("base_ang_vel", vp), ("projected_gravity", vp), ("rpy", vp),
+        ("feet_forces", vp), ("contact_filt", vp), ("root_h", vp),
+        ("episode_rew_means", vp), ("time_outs_latched", vp), ("num_resets", vp), ("workspace", vp),
+        ("noise_u", vp), ("rs_eps_u", vp), ("rs_c_idx", vp), ("rs_cmd_u", vp), ("rt_eps_u", vp),
+        ("rt_c_idx", vp), ("rt_cmd_u", vp), ("push_u", vp), ("mocap_clip_idx", vp), ("mocap_time_u", vp),
+    ]
+
+
+class QaCompactArgs(C.Structure):
+    _fields_ = [("num_envs", C.c_int32), ("reset_buf", vp), ("prev_obs_disc_buf", vp), ("reset_env_ids", vp),
+                ("reset_env_ids_i32", vp), ("terminal_disc_states", vp), ("count", vp)]
+
+
+class QaGaeArgs(C.Structure):
+    _fields_ = [("num_steps", C.c_int32), ("num_envs", C.c_int32), ("gamma", C.c_float), ("lam", C.c_float),
+                ("rewards", vp), ("values", vp), ("dones", vp), ("last_values", vp), ("returns", vp),
+                ("advantages", vp), ("workspace", vp)]
+
+
+# every symbol `include/qa_b200.h` declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "qa_version": (C.c_int, []),
+    "qa_build_info": (C.c_char_p, []),
+    "qa_struct_size": (C.c_int, [C.c_int]),
+    "qa_action_push": (C.c_int, [C.POINTER(QaActionPushArgs), vp]),
+    "qa_pd_torques": (C.c_int, [C.POINTER(QaTorqueArgs), vp]),
+    "qa_height_scan": (C.c_int, [C.POINTER(QaHeightScanArgs), vp]),
+    "qa_mocap_blend": (C.c_int, [C.POINTER(QaMocapBlendArgs), vp]),
+    "qa_post_physics_bbc": (C.c_int, [C.POINTER(QaBbcConst), C.POINTER(QaBbcStepArgs), vp]),
+    "qa_compact_resets": (C.c_int, [C.POINTER(QaCompactArgs), vp]),
+    "qa_gae": (C.c_int, [C.POINTER(QaGaeArgs), vp]),
+}
+
+STRUCT_ORDER = [QaActionPushArgs, QaTorqueArgs, QaTerrain, QaHeightScanArgs, QaMocapTable, QaMocapBlendArgs,
+                QaBbcConst, QaBbcStepArgs, QaCompactArgs, QaGaeArgs]
+
+_LIB = None
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libqa_b200.so")
+
+
+def load():
+    """dlopen libqa_b200.so, bind every declared symbol, check the ABI version.  Raises loudly."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.isfile(LIB_PATH):
+        raise RuntimeError(
+            f"qa_b200: {LIB_PATH} is missing -- the CUDA library is the product and there is no fallback. "
+            "Build it with `python -c 'import __graft_entry__ as g; g.build()'` from the repo root.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)          # AttributeError if the .so does not export it
+        fn.restype = res
+        fn.argtypes = args
+    ver = lib.qa_version()
+    if ver != QA_ABI_VERSION:
+        raise RuntimeError(f"qa_b200: ABI mismatch, library reports {ver}, bindings expect {QA_ABI_VERSION}")
+    for which, st in enumerate(STRUCT_ORDER):
+        want = lib.qa_struct_size(which)
+        if want != C.sizeof(st):
+            raise RuntimeError(f"qa_b200: struct layout mismatch for {st.__name__}: library {want} B, "
+                               f"bindings {C.sizeof(st)} B")
+    _LIB = lib
+    return lib
+
+
+def check(code: int, what: str) -> None:
+    if code == 0:
+        return
+    if code < 0:
+        kind = {-1: "QA_EINVAL (null pointer / bad size)", -2: "QA_ERANGE (dimension outside compiled limits)"}.get(
+            code, "argument error")
+        raise RuntimeError(f"{what}: {kind} [{code}]")
+    raise RuntimeError(f"{what}: CUDA error {code}")

@@ -1,0 +1,216 @@
+"""Thin torch-tensor wrappers over the C ABI of `libqa_b200.so` (include/qa_b200.h).
+
+Each function checks dtype / contiguity / device, passes `tensor.data_ptr()` and the current CUDA
+stream, and raises `RuntimeError` on a non-zero return code.  No function here computes anything
+in torch: if the library is missing, `_abi.load()` raises.
+"""
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _abi
+from . import config as K
+
+
+# number of libqa_b200 kernels launched through this module (bench.py reports it as `gpu_launches`)
+launches = 0
+
+
+def _count(n: int) -> None:
+    global launches
+    launches += n
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor], dtype=None, name="tensor") -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError(f"qa_b200: {name} must be a CUDA tensor (no CPU fallback exists)")
+    if not t.is_contiguous():
+        raise RuntimeError(f"qa_b200: {name} must be contiguous")
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError(f"qa_b200: {name} must be {dtype}, got {t.dtype}")
+    return t.data_ptr()
+
+
+def _bytep(t, name):
+    if t.dtype not in (torch.bool, torch.uint8):
+        raise RuntimeError(f"qa_b200: {name} must be bool/uint8")
+    return _p(t, None, name)
+
+
+# ---- K0 ---------------------------------------------------------------------------------------
+def action_push(actions_in, action_history_buf, actions_out, delay: int, clip: float) -> None:
+    """LeggedRobot.step front half, legged_robot.py:84-98 (history shifted IN PLACE)."""
+    lib = _abi.load()
+    n = actions_in.shape[0]
+    a = _abi.QaActionPushArgs(n, int(delay), float(clip), _p(actions_in, torch.float32, "actions"),
+                              _p(action_history_buf, torch.float32, "action_history_buf"),
+                              _p(actions_out, torch.float32, "actions_out"))
+    _abi.check(lib.qa_action_push(C.byref(a), _stream()), "qa_action_push")
+    _count(1)
+
+
+# ---- K1 ---------------------------------------------------------------------------------------
+def pd_torques(actions, dof_state, motor_strength, p_gains, d_gains, default_dof_pos, torque_limits,
+               torques, torques_org, action_scale: float, hip_scale_reduction: float) -> None:
+    """LeggedRobot._compute_torques, legged_robot.py:547-579."""
+    lib = _abi.load()
+    f = torch.float32
+    a = _abi.QaTorqueArgs(actions.shape[0], float(action_scale), float(hip_scale_reduction),
+                          _p(actions, f, "actions"), _p(dof_state, f, "dof_state"),
+                          _p(motor_strength, f, "motor_strength"), _p(p_gains, f, "p_gains"),
+                          _p(d_gains, f, "d_gains"), _p(default_dof_pos, f, "default_dof_pos"),
+                          _p(torque_limits, f, "torque_limits"), _p(torques, f, "torques"),
+                          _p(torques_org, f, "torques_org"))
+    _abi.check(lib.qa_pd_torques(C.byref(a), _stream()), "qa_pd_torques")
+    _count(1)
+
+
+def terrain_struct(height_samples, border_size, horizontal_scale, vertical_scale) -> _abi.QaTerrain:
+    return _abi.QaTerrain(_p(height_samples, torch.int16, "height_samples"), height_samples.shape[0],
+                          height_samples.shape[1], float(border_size), float(horizontal_scale),
+                          float(vertical_scale))
+
+
+# ---- K3 ---------------------------------------------------------------------------------------
+def height_scan(root_states, height_points, height_samples, border_size, horizontal_scale, vertical_scale,
+                measured_heights) -> None:
+    """LeggedRobot._get_heights, legged_robot.py:1190-1228."""
+    lib = _abi.load()
+    f = torch.float32
+    a = _abi.QaHeightScanArgs(root_states.shape[0], height_points.shape[0], _p(root_states, f, "root_states"),
+                              _p(height_points, f, "height_points"),
+                              terrain_struct(height_samples, border_size, horizontal_scale, vertical_scale),
+                              _p(measured_heights, f, "measured_heights"))
+    _abi.check(lib.qa_height_scan(C.byref(a), _stream()), "qa_height_scan")
+    _count(1)
+
+
+def mocap_struct(table) -> _abi.QaMocapTable:
+    """`table`: qa_b200.mocap.MocapTable whose tensors already live on the GPU."""
+    return _abi.QaMocapTable(
+        _p(table.frames, torch.float32, "mocap.frames"), _p(table.clip_start, torch.int32, "mocap.clip_start"),
+        _p(table.clip_nframes, torch.float64, "mocap.clip_nframes"),
+        _p(table.clip_len_s, torch.float64, "mocap.clip_len_s"),
+        _p(table.clip_frame_dur, torch.float64, "mocap.clip_frame_dur"),
+        _p(table.mode_offset, torch.int32, "mocap.mode_offset"), _p(table.mode_clips, torch.int32, "mocap.mode_clips"),
+        _p(table.mode_cdf, torch.float64, "mocap.mode_cdf"), table.num_clips, int(table.frames.shape[0]))
+
+
+# ---- K4 ---------------------------------------------------------------------------------------
+def mocap_blend(table, clip_idx, time_u, time_between_frames: float, disc_obs_len: int, frames_out) -> None:
+    """MotionLoader.get_full_frame_at_time_batch(traj_time_sample_batch(...)), motion_loader.py:333-341, 410-447."""
+    lib = _abi.load()
+    a = _abi.QaMocapBlendArgs(clip_idx.shape[0], mocap_struct(table), _p(clip_idx, torch.int32, "clip_idx"),
+                              _p(time_u, torch.float64, "time_u"), float(time_between_frames), int(disc_obs_len),
+                              _p(frames_out, torch.float32, "frames_out"))
+    _abi.check(lib.qa_mocap_blend(C.byref(a), _stream()), "qa_mocap_blend")
+    _count(1)
+
+
+# ---- reset compaction ---------------------------------------------------------------------------
+def compact_resets(reset_buf, prev_obs_disc_buf, reset_env_ids, reset_env_ids_i32, terminal_disc_states,
+                   count) -> None:
+    """`reset_buf.nonzero()` + `obs_disc_buf[env_ids]`, legged_robot.py:153-154, without a host sync."""
+    lib = _abi.load()
+    a = _abi.QaCompactArgs(reset_buf.shape[0], _bytep(reset_buf, "reset_buf"),
+                           _p(prev_obs_disc_buf, torch.float32, "prev_obs_disc_buf"),
+                           _p(reset_env_ids, torch.int64, "reset_env_ids"),
+                           _p(reset_env_ids_i32, torch.int32, "reset_env_ids_i32"),
+                           _p(terminal_disc_states, torch.float32, "terminal_disc_states"),
+                           _p(count, torch.int32, "count"))
+    _abi.check(lib.qa_compact_resets(C.byref(a), _stream()), "qa_compact_resets")
+    _count(1)
+
+
+# ---- K5 ---------------------------------------------------------------------------------------
+def gae(rewards, values, dones, last_values, returns, advantages, workspace, gamma: float, lam: float) -> None:
+    """RolloutStorage.compute_returns, rollout_storage.py:97-111.  Tensors are (T,N[,1])."""
+    lib = _abi.load()
+    f = torch.float32
+    T, N = rewards.shape[0], rewards.shape[1]
+    a = _abi.QaGaeArgs(T, N, float(gamma), float(lam), _p(rewards, f, "rewards"), _p(values, f, "values"),
+                       _bytep(dones, "dones"), _p(last_values, f, "last_values"), _p(returns, f, "returns"),
+                       _p(advantages, f, "advantages"), _p(workspace, torch.float64, "workspace"))
+    _abi.check(lib.qa_gae(C.byref(a), _stream()), "qa_gae")
+    _count(2)
+
+
+# ---- K2 constants ---------------------------------------------------------------------------------
+def bbc_const(cfg: "K.BbcEnvConfig", prior_parameters=None) -> _abi.QaBbcConst:
+    """Flattens the task configuration into the POD the fused kernel takes by value."""
+    import math
+    c = _abi.QaBbcConst()
+    c.num_bodies = cfg.num_bodies
+    for j in range(4):
+        c.feet_indices[j] = cfg.feet_indices[j]
+    c.termination_body_mask = sum(1 << b for b in cfg.termination_contact_indices)
+    c.penalised_body_mask = sum(1 << b for b in cfg.penalised_contact_indices)
+    soft = cfg.soft_dof_pos_limits()
+    for d in range(12):
+        c.default_dof_pos[d] = cfg.default_dof_pos[d]
+        c.dof_pos_lower[d] = float(soft[d, 0])
+        c.dof_pos_upper[d] = float(soft[d, 1])
+        c.dof_vel_limits[d] = cfg.dof_vel_limits[d]
+        c.torque_limits[d] = cfg.torque_limits[d]
+    c.hip_dof_mask = sum(1 << d for d in cfg.hip_indices)
+    for k, s in enumerate(cfg.reward_scales_dt()):
+        c.reward_scale[k] = s
+    c.dt = cfg.dt
+    c.tracking_sigma = cfg.tracking_sigma
+    c.soft_dof_vel_limit = cfg.soft_dof_vel_limit
+    c.soft_torque_limit = cfg.soft_torque_limit
+    c.jump_goal = cfg.jump_goal
+    c.jump_height_lo = cfg.jump_height[0]
+    c.only_positive_rewards = int(cfg.only_positive_rewards)
+    c.max_episode_length = cfg.max_episode_length
+    c.resample_period = cfg.resample_period
+    c.episode_length_s = cfg.episode_length_s
+    for m in range(K.DIM_C):
+        for j in range(2):
+            c.lin_vel_x[m][j] = cfg.lin_vel_x[m][j]
+            c.lin_vel_y[m][j] = cfg.lin_vel_y[m][j]
+            c.ang_vel_yaw[m][j] = cfg.ang_vel_yaw[m][j]
+    c.jump_h_lo = cfg.jump_height[0]
+    c.jump_h_span = cfg.jump_height[1] - cfg.jump_height[0]          # (hi-lo) in double, then fp32
+    c.loco_h_lo = cfg.locomotion_height[0]
+    c.loco_h_span = cfg.locomotion_height[1] - cfg.locomotion_height[0]
+    c.lin_vel_x_clip = cfg.lin_vel_x_clip
+    c.lin_vel_y_clip = cfg.lin_vel_y_clip
+    c.ang_vel_yaw_clip = cfg.ang_vel_yaw_clip
+    prior = [1.0 / K.DIM_C] * K.DIM_C if prior_parameters is None else [float(x) for x in prior_parameters]
+    z = [p / cfg.latent_c_temperature for p in prior]                # legged_robot.py:536-538
+    mx = max(z)
+    ez = [math.exp(v - mx) for v in z]
+    tot, acc = sum(ez), 0.0
+    for k in range(K.DIM_C):
+        acc += ez[k] / tot
+        c.prior_cdf[k] = acc
+    c.s_lin_vel, c.s_ang_vel, c.s_dof_pos, c.s_dof_vel = cfg.s_lin_vel, cfg.s_ang_vel, cfg.s_dof_pos, cfg.s_dof_vel
+    c.s_key_pos, c.s_foot_contact = cfg.s_key_pos, cfg.s_foot_contact
+    c.s_lin_vel_dist, c.s_ang_vel_dist = cfg.s_lin_vel_dist, cfg.s_ang_vel_dist
+    c.clip_obs = cfg.clip_observations
+    c.add_noise = int(cfg.add_noise)
+    c.root_height_obs = int(cfg.root_height_obs)
+    c.measure_heights = int(cfg.measure_heights)
+    ci = cfg.center_height_index
+    ny = len(cfg.measured_points_y)
+    c.center_px = cfg.measured_points_x[ci // ny]
+    c.center_py = cfg.measured_points_y[ci % ny]
+    c.max_push_vel_xy = cfg.max_push_vel_xy
+    c.time_between_frames = cfg.dt
+    c.disc_obs_len = K.DISC_OBS_LEN
+    return c
+
+
+def post_physics_bbc(const: _abi.QaBbcConst, args: _abi.QaBbcStepArgs) -> None:
+    """One fused post-physics step (K2).  `args` is a pre-built, reusable struct of device pointers."""
+    lib = _abi.load()
+    _abi.check(lib.qa_post_physics_bbc(C.byref(const), C.byref(args), _stream()), "qa_post_physics_bbc")
+    _count(1)
