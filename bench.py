@@ -111,7 +111,8 @@ def run_ours(args):
     dev = torch.device(f"cuda:{local_rank}")
     from qa_b200.pipeline import BbcIteration
     cfg, static, snaps, table = build_workload(rank, dev)
-    it = BbcIteration(cfg, static, snaps, table, device=dev, seed=1234 + rank, world_size=world)
+    it = BbcIteration(cfg, static, snaps, table, device=dev, seed=1234 + rank, world_size=world,
+                      bulk_store=bool(args.k2_bulk))
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
@@ -197,31 +198,37 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def cpu_reference_iteration(n_envs, steps, threads):
-    """The reference algorithm's CPU path (oracle port) over `steps` env steps + GAE.  Returns seconds."""
+def cpu_reference_sample(n_envs, rollout_steps, minibatch_steps, threads):
+    """The reference algorithm's CPU path (oracle port): `rollout_steps` of the 24 env steps, GAE, and
+    `minibatch_steps` of the 20 PPO minibatch steps.  Returns (extrapolated seconds per full iteration, detail)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import bbc_env as O
     import trainer as OT
-    from qa_b200 import synthetic
+    from qa_b200 import pipeline, synthetic
     torch.set_num_threads(threads)
-    cfg, static, snaps, table = build_workload(0, "cpu", n_envs=n_envs, steps=steps)
-    draws = [synthetic.make_rng_draws(cfg, seed=1234, step=t) for t in range(steps)]
+    cfg, static, snaps, table = build_workload(0, "cpu", n_envs=n_envs, steps=T_STEPS)
+    draws = [synthetic.make_rng_draws(cfg, seed=1234, step=t) for t in range(rollout_steps)]
     for d in draws:
         d["mocap_clip_idx"] = table.sample_clip(d["rt_c_idx"], d["mocap_clip_u"])
-    from qa_b200 import pipeline
-    return pipeline.cpu_oracle_iteration(O, OT, cfg, static, snaps, draws, table)
+    r = pipeline.cpu_oracle_iteration(O, OT, cfg, static, snaps, draws, table, synthetic.make_weights(1),
+                                      rollout_steps=rollout_steps, minibatch_steps=minibatch_steps)
+    full = r["t_rollout"] * (T_STEPS / rollout_steps) + r["t_gae"] + r["t_update"] * (20 / minibatch_steps)
+    return full, r
+
+
+def _cpu_line(threads, rollout_steps, minibatch_steps, full, r):
+    return {"value": T_STEPS * ENVS_PER_GPU / full, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": (f"oracle/ port of the reference on torch {torch.__version__} CPU, {threads} threads, {ENVS_PER_GPU} envs: "
+                       f"{rollout_steps}/24 rollout steps ({r['t_rollout']:.2f} s), GAE ({r['t_gae']:.3f} s), "
+                       f"{minibatch_steps}/20 PPO minibatch steps of 24576 ({r['t_update']:.2f} s), "
+                       f"extrapolated to one full iteration = {full:.2f} s")}
 
 
 def cpu_baseline_sample():
     threads = os.cpu_count() or 1
-    steps = 6                                                   # bounded sample: 6 of the 24 env steps, full 4096 envs
-    cpu_reference_iteration(ENVS_PER_GPU, 2, threads)          # warm-up
-    t0 = time.perf_counter()
-    sec, stages = cpu_reference_iteration(ENVS_PER_GPU, steps, threads)
-    _ = time.perf_counter() - t0
-    return {"value": steps * ENVS_PER_GPU / sec, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{steps} env steps x {ENVS_PER_GPU} envs + GAE through oracle/ (torch {torch.__version__} CPU, "
-                      f"{threads} threads); stages: {stages}"}
+    rs, ms = 12, 6                                   # ~10-20 s of CPU work
+    full, r = cpu_reference_sample(ENVS_PER_GPU, rs, ms, threads)
+    return _cpu_line(threads, rs, ms, full, r)
 
 
 def run_reference(args):
@@ -229,24 +236,22 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    steps_per_sample = 6
-    for _ in range(min(args.warmup, 2)):
-        cpu_reference_iteration(ENVS_PER_GPU, 2, threads)
-    secs = []
+    rs, ms = 6, 2
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference_sample(ENVS_PER_GPU, 2, 1, threads)
+    fulls = []
     for _ in range(args.steps):
-        sec, stages = cpu_reference_iteration(ENVS_PER_GPU, steps_per_sample, threads)
-        secs.append(sec)
-    sec = sum(secs) / len(secs)
-    value = steps_per_sample * ENVS_PER_GPU / sec
+        full, r = cpu_reference_sample(ENVS_PER_GPU, rs, ms, threads)
+        fulls.append(full)
+    full = sum(fulls) / len(fulls)
+    value = T_STEPS * ENVS_PER_GPU / full
     world = int(os.environ.get("WORLD_SIZE", 1))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": sec * 1e3 * (T_STEPS / steps_per_sample), "higher_is_better": True,
+            "warmup": args.warmup, "ms_per_step": full * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "bbc_go2_locomotion_4096x24 (CPU sample)", "envs_per_gpu": ENVS_PER_GPU,
-                       "steps_per_env": T_STEPS, "stages": stages},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": f"{steps_per_sample} env steps x {ENVS_PER_GPU} envs + GAE per timed step, "
-                                       f"oracle/ port of the reference on torch {torch.__version__} CPU"},
+            "config": {"workload": "bbc_go2_locomotion_4096x24: rollout + GAE + PPO update (CPU, bounded sample per step)",
+                       "envs_per_gpu": ENVS_PER_GPU, "steps_per_env": T_STEPS},
+            "cpu_baseline": _cpu_line(threads, rs, ms, full, r),
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -254,10 +259,11 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--k2-bulk", type=int, default=1, help="1: TMA bulk stores for the obs rows (default), 0: warp stores")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

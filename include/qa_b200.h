@@ -50,7 +50,7 @@ int qa_version(void);
 /* human readable build string ("sm_100a, nvcc 12.9, ...") */
 const char* qa_build_info(void);
 /* sizeof() of argument struct number `which` (order of declaration in this header, QaActionPushArgs
- * = 0 ... QaGaeArgs = 9; -1 if unknown): a layout handshake for FFI mirrors of these structs */
+ * = 0 ... QaGaeArgs = 9, QaGatherArgs = 10, QaClipAdamArgs = 11; -1 if unknown): a layout handshake for FFI mirrors of these structs */
 int qa_struct_size(int which);
 
 /* ------------------------------------------------------------------------------------------
@@ -311,6 +311,45 @@ typedef struct QaGaeArgs {
     double* workspace;                  /* >= 64 bytes, zero-initialised once by the caller */
 } QaGaeArgs;
 int qa_gae(const QaGaeArgs* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K6  minibatch gather -- replaces the 9 index ops per minibatch of RolloutStorage.mini_batch_generator,
+ *     bbc/rsl_rl/storage/rollout_storage.py:147-155: dst[t][j,:] = src[t][indices[j],:] for every tensor t
+ * ------------------------------------------------------------------------------------------ */
+#define QA_GATHER_MAX_TENSORS 12
+typedef struct QaGatherArgs {
+    int64_t num_rows;                   /* minibatch size (24 576) */
+    int32_t num_tensors;
+    const int64_t* indices;             /* (num_rows) rows of the flattened (T*N) storage */
+    const float* src[QA_GATHER_MAX_TENSORS];   /* (T*N, width[t]) */
+    float* dst[QA_GATHER_MAX_TENSORS];         /* (num_rows, width[t]) */
+    int32_t width[QA_GATHER_MAX_TENSORS];
+} QaGatherArgs;
+int qa_gather_minibatch(const QaGatherArgs* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K8  fused gradient clipping + Adam on one flat fp32 parameter buffer -- replaces
+ *     nn.utils.clip_grad_norm_(params, max_grad_norm) + optimizer.step(),
+ *     bbc/rsl_rl/algorithms/gail.py:409-412 (actor-critic) and :361-365 (estimator).
+ *     grads are first multiplied by grad_scale (1/world_size after an NCCL all-reduce(SUM)); the learning
+ *     rate and the step counter live on the device so that the adaptive-KL schedule (:368-379) needs no
+ *     host round trip.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct QaClipAdamArgs {
+    int64_t numel;
+    float* params;                      /* (numel) in/out */
+    const float* grads;                 /* (numel) */
+    float* exp_avg;                     /* (numel) in/out */
+    float* exp_avg_sq;                  /* (numel) in/out */
+    const float* lr;                    /* (1) device scalar */
+    int32_t* step;                      /* (1) device scalar, incremented by the call */
+    float beta1, beta2, eps;
+    float max_grad_norm;                /* <= 0: no clipping */
+    float grad_scale;
+    float* grad_norm_out;               /* (1) total norm before clipping, may be NULL */
+    double* workspace;                  /* >= 16 bytes */
+} QaClipAdamArgs;
+int qa_clip_adam(const QaClipAdamArgs* a, void* stream);
 
 #ifdef __cplusplus
 }

@@ -25,6 +25,8 @@ extern "C" int qa_struct_size(int which) {
         case 7: return (int)sizeof(QaBbcStepArgs);
         case 8: return (int)sizeof(QaCompactArgs);
         case 9: return (int)sizeof(QaGaeArgs);
+        case 10: return (int)sizeof(QaGatherArgs);
+        case 11: return (int)sizeof(QaClipAdamArgs);
         default: return -1;
     }
 }

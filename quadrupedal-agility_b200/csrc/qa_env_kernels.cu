@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(256) k_action_push(QaActionPushArgs a) {
 
 extern "C" int qa_action_push(const QaActionPushArgs* a, void* stream) {
     QA_CHECK_PTR(a);
+    if (a->num_envs == 0) return 0;          // empty input: nothing to do (pointers may be null)
     QA_CHECK_PTR(a->actions_in);
     QA_CHECK_PTR(a->action_history_buf);
     QA_CHECK_PTR(a->actions_out);
@@ -65,6 +66,7 @@ __global__ void __launch_bounds__(256) k_pd_torques(QaTorqueArgs a) {
 
 extern "C" int qa_pd_torques(const QaTorqueArgs* a, void* stream) {
     QA_CHECK_PTR(a);
+    if (a->num_envs == 0) return 0;
     QA_CHECK_PTR(a->actions);
     QA_CHECK_PTR(a->dof_state);
     QA_CHECK_PTR(a->motor_strength);
@@ -117,6 +119,7 @@ __global__ void __launch_bounds__(256) k_height_scan(QaHeightScanArgs a) {
 
 extern "C" int qa_height_scan(const QaHeightScanArgs* a, void* stream) {
     QA_CHECK_PTR(a);
+    if (a->num_envs == 0) return 0;
     QA_CHECK_PTR(a->root_states);
     QA_CHECK_PTR(a->height_points);
     QA_CHECK_PTR(a->terrain.height_samples);
@@ -155,6 +158,7 @@ __global__ void __launch_bounds__(128) k_mocap_blend(QaMocapBlendArgs a) {
 
 extern "C" int qa_mocap_blend(const QaMocapBlendArgs* a, void* stream) {
     QA_CHECK_PTR(a);
+    if (a->num == 0) return 0;
     QA_CHECK_PTR(a->table.frames);
     QA_CHECK_PTR(a->table.clip_start);
     QA_CHECK_PTR(a->table.clip_nframes);

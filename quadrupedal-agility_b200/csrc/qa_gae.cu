@@ -124,6 +124,7 @@ __global__ void __launch_bounds__(256) k_gae_normalise(QaGaeArgs g) {
 
 extern "C" int qa_gae(const QaGaeArgs* g, void* stream) {
     QA_CHECK_PTR(g);
+    if (g->num_envs == 0 && g->num_steps > 0) return 0;
     QA_CHECK_PTR(g->rewards);
     QA_CHECK_PTR(g->values);
     QA_CHECK_PTR(g->dones);

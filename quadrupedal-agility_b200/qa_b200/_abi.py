@@ -105,6 +105,20 @@ class QaGaeArgs(C.Structure):
                 ("advantages", vp), ("workspace", vp)]
 
 
+GATHER_MAX = 12
+
+
+class QaGatherArgs(C.Structure):
+    _fields_ = [("num_rows", C.c_int64), ("num_tensors", C.c_int32), ("indices", vp), ("src", vp * GATHER_MAX),
+                ("dst", vp * GATHER_MAX), ("width", C.c_int32 * GATHER_MAX)]
+
+
+class QaClipAdamArgs(C.Structure):
+    _fields_ = [("numel", C.c_int64), ("params", vp), ("grads", vp), ("exp_avg", vp), ("exp_avg_sq", vp),
+                ("lr", vp), ("step", vp), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+                ("max_grad_norm", C.c_float), ("grad_scale", C.c_float), ("grad_norm_out", vp), ("workspace", vp)]
+
+
 # every symbol `include/qa_b200.h` declares: name -> (restype, argtypes)
 SYMBOLS = {
     "qa_version": (C.c_int, []),
@@ -117,10 +131,12 @@ SYMBOLS = {
     "qa_post_physics_bbc": (C.c_int, [C.POINTER(QaBbcConst), C.POINTER(QaBbcStepArgs), vp]),
     "qa_compact_resets": (C.c_int, [C.POINTER(QaCompactArgs), vp]),
     "qa_gae": (C.c_int, [C.POINTER(QaGaeArgs), vp]),
+    "qa_gather_minibatch": (C.c_int, [C.POINTER(QaGatherArgs), vp]),
+    "qa_clip_adam": (C.c_int, [C.POINTER(QaClipAdamArgs), vp]),
 }
 
 STRUCT_ORDER = [QaActionPushArgs, QaTorqueArgs, QaTerrain, QaHeightScanArgs, QaMocapTable, QaMocapBlendArgs,
-                QaBbcConst, QaBbcStepArgs, QaCompactArgs, QaGaeArgs]
+                QaBbcConst, QaBbcStepArgs, QaCompactArgs, QaGaeArgs, QaGatherArgs, QaClipAdamArgs]
 
 _LIB = None
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libqa_b200.so")

@@ -197,3 +197,29 @@ class BbcEnvConfig:
         v[17:29] = self.n_dof_vel * self.noise_level * self.s_dof_vel
         v[58:61] = self.n_lin_vel * self.noise_level * self.s_lin_vel
         return v
+
+
+def bbc_train_cfg() -> dict:
+    """`class_to_dict(Go2LocomotionCfgAlgo())` of the reference (go2_locomotion_config.py:184-244 over
+    legged_robot_config.py:196-233): the dict `OnPolicyRunner(env, train_cfg, ...)` takes."""
+    return {
+        "seed": 1,
+        "runner_class_name": "OnPolicyRunner",
+        "policy": dict(init_noise_std=1.0, actor_hidden_dims=[512, 256, 128], critic_hidden_dims=[512, 256, 128],
+                       priv_encoder_dims=[64], activation="elu", train_with_estimated_latent=True),
+        "algorithm": dict(value_loss_coef=5.0, use_clipped_value_loss=True, clip_param=0.2, entropy_coef=0.01,
+                          num_learning_epochs=5, num_mini_batches=4, schedule="adaptive", gamma=0.99, lam=0.95,
+                          desired_kl=0.01, max_grad_norm=1.0, lr_ac=1e-3, lr_disc=5e-4, lr_q=1e-3,
+                          surrogate_loss_coef=2.0, bounds_loss_coef=0.0, disc_coef=1.0, disc_logit_reg=0.05,
+                          disc_grad_penalty=0.1, disc_weight_decay=0.0001, disc_replay_buffer_size=1000000,
+                          us_coef=1.0, ss_coef=1.0, prior_soft_coef=1e-3, info_max_coef=1.0, begin_rim=200,
+                          disc_loss_function="MSELoss", priv_reg_coef_schedual=[0, 0.1, 1000, 2000],
+                          priv_reg_coef_schedual_resume=[0, 0.1, 0, 1]),
+        "estimator": dict(train_with_estimated_explicit=True, learning_rate=1.0e-4, hidden_dims=[128, 64]),
+        "runner": dict(policy_class_name="ActorCritic", algorithm_class_name="SSInfoGAIL", num_steps_per_env=24,
+                       max_iterations=500000, save_interval=100, experiment_name="go2_locomotion", run_name="",
+                       dagger_update_freq=20, motion_files_lb=[], motion_files_ulb=[], num_preload_transitions=200000,
+                       reward_i_coef=1.0, reward_us_coef=0.01, reward_ss_coef=0.2, reward_t_coef=0.2,
+                       disc_hidden_units=[512, 256], min_normalized_std=[0.05, 0.02, 0.05] * 4,
+                       resume=False, load_run=-1, checkpoint=-1, resume_path=None),
+    }

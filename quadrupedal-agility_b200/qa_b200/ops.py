@@ -142,6 +142,40 @@ def gae(rewards, values, dones, last_values, returns, advantages, workspace, gam
     _count(2)
 
 
+# ---- K6 ---------------------------------------------------------------------------------------
+def gather_minibatch(indices, srcs, dsts) -> None:
+    """dst[t][j] = src[t][indices[j]] for every (src, dst) pair (2-D float32, same width), one launch.
+    Replaces the per-tensor advanced indexing of mini_batch_generator, rollout_storage.py:147-155."""
+    lib = _abi.load()
+    a = _abi.QaGatherArgs()
+    a.num_rows, a.num_tensors = indices.shape[0], len(srcs)
+    if len(srcs) > _abi.GATHER_MAX:
+        raise RuntimeError("qa_gather_minibatch: too many tensors")
+    a.indices = _p(indices, torch.int64, "indices")
+    for t, (s, d) in enumerate(zip(srcs, dsts)):
+        if s.shape[1:] != d.shape[1:] or d.shape[0] != indices.shape[0]:
+            raise RuntimeError("qa_gather_minibatch: shape mismatch")
+        a.src[t], a.dst[t] = _p(s, torch.float32, "src"), _p(d, torch.float32, "dst")
+        a.width[t] = int(s[0].numel())
+    _abi.check(lib.qa_gather_minibatch(C.byref(a), _stream()), "qa_gather_minibatch")
+    _count(1)
+
+
+# ---- K8 ---------------------------------------------------------------------------------------
+def clip_adam(params, grads, exp_avg, exp_avg_sq, lr, step, workspace, beta1=0.9, beta2=0.999, eps=1e-8,
+              max_grad_norm=1.0, grad_scale=1.0, grad_norm_out=None) -> None:
+    """clip_grad_norm_ + Adam.step on a flat fp32 buffer (gail.py:409-412); `lr` (f32) and `step` (i32) are
+    1-element device tensors."""
+    lib = _abi.load()
+    f = torch.float32
+    a = _abi.QaClipAdamArgs(params.numel(), _p(params, f, "params"), _p(grads, f, "grads"), _p(exp_avg, f, "exp_avg"),
+                            _p(exp_avg_sq, f, "exp_avg_sq"), _p(lr, f, "lr"), _p(step, torch.int32, "step"),
+                            float(beta1), float(beta2), float(eps), float(max_grad_norm), float(grad_scale),
+                            _p(grad_norm_out, f, "grad_norm_out"), _p(workspace, torch.float64, "workspace"))
+    _abi.check(lib.qa_clip_adam(C.byref(a), _stream()), "qa_clip_adam")
+    _count(2)
+
+
 # ---- K2 constants ---------------------------------------------------------------------------------
 def bbc_const(cfg: "K.BbcEnvConfig", prior_parameters=None) -> _abi.QaBbcConst:
     """Flattens the task configuration into the POD the fused kernel takes by value."""

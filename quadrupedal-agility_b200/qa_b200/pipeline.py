@@ -27,9 +27,15 @@ CARRIED = ("last_actions", "last_torques_org", "last_dof_vel", "last_root_vel", 
 
 class BbcIteration:
     dtype_name = "f32"
+    workload_name = "bbc_go2_locomotion_4096x24: rollout (act, env step, disc reward, storage) + GAE + PPO update"
+    stage_names = ["act (estimator+actor+critic)", "action_push", "pd_torques x4",
+                   "post_physics_bbc (fused obs/reward/termination/reset)", "compact_resets", "predict_disc_reward",
+                   "process_env_step", "gae", "PPO update: 5 epochs x 4 minibatches (gather, fwd/bwd graph, clip+Adam)"]
 
     def __init__(self, cfg, static, snaps: List[Dict[str, torch.Tensor]], table, device, seed=1234, world_size=1,
-                 gamma=0.99, lam=0.95):
+                 bulk_store=True, use_cuda_graph=True):
+        from .config import bbc_train_cfg
+        from .rsl_rl.runner import OnPolicyRunner
         self.cfg, self.device, self.T = cfg, torch.device(device), len(snaps)
         dev, N, T = self.device, cfg.num_envs, len(snaps)
         # pinned host copies of the simulator tensors (run_host) and device-resident snapshots (run_resident)
@@ -38,30 +44,23 @@ class BbcIteration:
         self.staging = {k: torch.empty_like(self.dev_snaps[0][k]) for k in SIM_KEYS}
         self.phys_resident = RecordedPhysics(self.dev_snaps)
         self.phys_staged = RecordedPhysics([self.staging])
-        self.env = LeggedRobot(cfg, self.phys_resident, static, table, device=dev, seed=seed)
-        self.env.load_state({k: v.to(dev) for k, v in snaps[0].items() if k in CARRIED})
+        self.env = LeggedRobot(cfg, self.phys_resident, static, table, device=dev, seed=seed, bulk_store=bulk_store)
         self.env.global_counter = 1
-        g = torch.Generator().manual_seed(seed + 99)
-        self.actions = [torch.randn(N, K.NUM_ACTIONS, generator=g).to(dev) for _ in range(T)]
-        self.gamma, self.lam = gamma, lam
-        f = dict(device=dev, dtype=torch.float32)
-        self.rewards = torch.zeros(T, N, 1, **f)
-        self.values = torch.zeros(T, N, 1, **f)
-        self.dones = torch.zeros(T, N, 1, device=dev, dtype=torch.uint8)
-        self.last_values = torch.zeros(N, 1, **f)
-        self.returns = torch.zeros(T, N, 1, **f)
-        self.advantages = torch.zeros(T, N, 1, **f)
-        self.gae_ws = torch.zeros(8, device=dev, dtype=torch.float64)
-        self.mean_reward_host = torch.zeros(1).pin_memory()
+        torch.manual_seed(seed)
+        train_cfg = bbc_train_cfg()
+        train_cfg["algorithm"]["use_cuda_graph"] = use_cuda_graph
+        self.runner = OnPolicyRunner(self.env, train_cfg, log_dir=None, device=dev)
+        self.env.load_state({k: v.to(dev) for k, v in snaps[0].items() if k in CARRIED})
+        self.phys_resident.cursor = -1
+        self.obs, self.critic_obs = self.env.get_observations(), self.env.get_privileged_observations()
+        self.runner._disc_hist = torch.stack([self.env.get_disc_observations()] * 2, dim=1)
+        self.result_host = torch.zeros(8).pin_memory()
         self.k2_traffic_bytes = None
         self.h2d_bytes_per_iteration = T * sum(self.staging[k].numel() * self.staging[k].element_size() for k in SIM_KEYS)
-        self.d2h_bytes_per_iteration = 4
+        self.d2h_bytes_per_iteration = 4 * 8
         self._launch0 = ops.launches
         self._iters = 0
-
-    workload_name = "bbc_go2_locomotion_4096x24_env_gae (trainer stages pending)"
-    stage_names = ["action_push", "pd_torques x4", "post_physics_bbc (fused obs/reward/termination/reset)",
-                   "compact_resets", "gae"]
+        self._k2_pairs = []
 
     # ---- bookkeeping ---------------------------------------------------------------------------------
     def reset_counters(self):
@@ -76,68 +75,116 @@ class BbcIteration:
         return (ops.launches - self._launch0) // max(self._iters, 1)
 
     def k2_time_ms(self):
-        pairs = getattr(self, "_k2_pairs", [])
-        return sum(a.elapsed_time(b) for a, b in pairs), len(pairs)
+        return sum(a.elapsed_time(b) for a, b in self._k2_pairs), len(self._k2_pairs)
 
-    # ---- the iteration -----------------------------------------------------------------------------------
-    def _collect_step(self, t):
-        env = self.env
-        obs, priv, rew, reset, ids, count, term = env.step_device(self.actions[t])
-        self.rewards[t, :, 0].copy_(rew)
-        self.dones[t, :, 0].copy_(reset)
-
+    # ---- the iteration (on_policy_runner.py:152-225) -----------------------------------------------------
     def _learn(self):
-        ops.gae(self.rewards, self.values, self.dones, self.last_values, self.returns, self.advantages, self.gae_ws,
-                self.gamma, self.lam)
+        alg = self.runner.alg
+        with torch.no_grad():
+            alg.compute_returns(self.critic_obs)
+        return alg.update()
 
     def run_resident(self, profile_k2=False):
-        env = self.env
+        env, runner = self.env, self.runner
         env.physics = self.phys_resident
         env.k2_events = [] if profile_k2 else None
-        for t in range(self.T):
-            self._collect_step(t)
-        self._learn()
+        with torch.no_grad():
+            for _ in range(self.T):
+                self.obs, self.critic_obs = runner.rollout_step(self.obs, self.critic_obs)
+        stats = self._learn()
         if profile_k2:
-            self._k2_pairs = getattr(self, "_k2_pairs", []) + env.k2_events
+            self._k2_pairs += env.k2_events
             env.k2_events = None
         self._iters += 1
+        return stats
 
     def run_host(self):
-        env = self.env
+        env, runner = self.env, self.runner
         env.physics = self.phys_staged
-        for t in range(self.T):
-            for k in SIM_KEYS:                                   # the physics backend's hand-over: pinned host -> HBM
-                self.staging[k].copy_(self.host_snaps[t][k], non_blocking=True)
-            self._collect_step(t)
-        self._learn()
-        self.mean_reward_host.copy_(self.rewards.mean().reshape(1), non_blocking=True)
+        with torch.no_grad():
+            for t in range(self.T):
+                for k in SIM_KEYS:                               # the physics backend's hand-over: pinned host -> HBM
+                    self.staging[k].copy_(self.host_snaps[t][k], non_blocking=True)
+                self.obs, self.critic_obs = runner.rollout_step(self.obs, self.critic_obs)
+            mean_rew = runner.alg.storage.rewards.mean()
+        stats = self._learn()                                    # reads the loss statistics back (one D2H)
+        self.result_host[0:1].copy_(mean_rew.reshape(1), non_blocking=True)
         torch.cuda.current_stream().synchronize()
         self._iters += 1
-        return float(self.mean_reward_host[0])
+        return float(self.result_host[0]), stats
 
 
-def cpu_oracle_iteration(O, OT, cfg, static, snaps, draws, table, gamma=0.99, lam=0.95):
-    """The same iteration through the CPU oracle (test infrastructure; called only by bench.py's
-    cpu_baseline / --impl reference legs).  Returns (seconds, stage description)."""
+def cpu_oracle_iteration(O, OT, cfg, static, snaps, draws, table, weights, rollout_steps=None, minibatch_steps=20,
+                         gamma=0.99, lam=0.95, num_mini_batches=4):
+    """The same iteration through the CPU oracle (test infrastructure; called only by bench.py's cpu_baseline /
+    --impl reference legs).  `rollout_steps` <= T env steps and `minibatch_steps` <= 20 PPO minibatch steps are
+    executed (a bounded sample); returns dict(t_rollout, t_gae, t_update, rollout_steps, minibatch_steps)."""
     T, N = len(snaps), cfg.num_envs
+    R = T if rollout_steps is None else min(rollout_steps, T)
     g = torch.Generator().manual_seed(7)
     carried = {k: snaps[0][k].clone() for k in CARRIED}
-    rewards, dones = torch.zeros(T, N, 1), torch.zeros(T, N, 1, dtype=torch.uint8)
-    values, last_values = torch.zeros(T, N, 1), torch.zeros(N, 1)
+    sd_ac = {k: v.clone().requires_grad_(True) for k, v in weights["ac"].items()}
+    sd_est = {k: v.clone().requires_grad_(True) for k, v in weights["est"].items()}
+    opt_a = torch.optim.Adam(list(sd_ac.values()), lr=1e-3)
+    opt_e = torch.optim.Adam(list(sd_est.values()), lr=1e-4)
+    W = 671
+    st = dict(obs=torch.zeros(T, N, W), actions=torch.zeros(T, N, 12), rewards=torch.zeros(T, N, 1),
+              dones=torch.zeros(T, N, 1, dtype=torch.uint8), values=torch.zeros(T, N, 1), logp=torch.zeros(T, N, 1),
+              mu=torch.zeros(T, N, 12), sigma=torch.ones(T, N, 12))
+    obs = torch.zeros(N, W)
+    disc_hist = torch.stack([carried["obs_disc_buf"]] * 2, dim=1)
+    time_outs = torch.zeros(N, dtype=torch.bool)
     t0 = time.perf_counter()
-    for t in range(T):
-        actions = torch.randn(N, 12, generator=g)
-        hist, act = O.action_push(cfg, carried["action_history_buf"], actions, delay=0)
-        s = dict(snaps[t])
-        s.update({k: carried[k] for k in CARRIED})
-        s["action_history_buf"], s["actions"] = hist, act
-        for _ in range(cfg.decimation):
-            _, s["torques_org"] = O.compute_torques(cfg, {**static, "dof_state": s["dof_state"]}, act.clone())
-        out = O.post_physics_step(cfg, static, s, draws[t], table, t + 1)
-        rewards[t, :, 0] = out["rew_buf"]
-        dones[t, :, 0] = out["reset_buf"]
-        for k in CARRIED:
-            carried[k] = out[k]
-    OT.compute_returns(rewards, values, dones, last_values, gamma, lam)
-    sec = time.perf_counter() - t0
-    return sec, "action_push, compute_torques x4, post_physics_step, compute_returns"
+    with torch.no_grad():
+        for t in range(R):
+            a = OT.act(sd_ac, sd_est, obs, obs, torch.randn(N, 12, generator=g))
+            hist, act = O.action_push(cfg, carried["action_history_buf"], a["actions"], delay=0)
+            s = dict(snaps[t])
+            s.update({k: carried[k] for k in CARRIED})
+            s["action_history_buf"], s["actions"] = hist, act
+            for _ in range(cfg.decimation):
+                _, s["torques_org"] = O.compute_torques(cfg, {**static, "dof_state": s["dof_state"]}, act.clone())
+            out = O.post_physics_step(cfg, static, s, draws[t], table, t + 1)
+            done = out["reset_buf"]
+            with_term = torch.where(done[:, None], carried["obs_disc_buf"], out["obs_disc_buf"])
+            disc_hist = torch.stack([disc_hist[:, 1], with_term], dim=1)
+            rew = OT.predict_disc_reward(weights["disc"], out["rew_buf"].unsqueeze(1), obs, disc_hist,
+                                         weights["norm_mean"], weights["norm_var"], cfg.dt, 1.0)[0]
+            if bool(done.any()):
+                time_outs = out["time_out_buf"]
+            rew = rew + gamma * torch.squeeze(a["values"] * time_outs.unsqueeze(1), 1)       # gail.py:203-205
+            st["obs"][t], st["actions"][t], st["rewards"][t, :, 0] = obs, a["actions"], rew.float()
+            st["dones"][t, :, 0], st["values"][t], st["logp"][t, :, 0] = done, a["values"], a["actions_log_prob"]
+            st["mu"][t], st["sigma"][t] = a["action_mean"], a["action_sigma"]
+            disc_hist = torch.where(done[:, None, None], out["obs_disc_buf"].unsqueeze(1).expand(-1, 2, -1), disc_hist)
+            obs = out["obs_buf"]
+            for k in CARRIED:
+                carried[k] = out[k]
+    t1 = time.perf_counter()
+    with torch.no_grad():
+        last_values = OT.critic_value(sd_ac, obs)
+        returns, adv = OT.compute_returns(st["rewards"], st["values"], st["dones"], last_values, gamma, lam)
+    t2 = time.perf_counter()
+    flat = lambda x: x.flatten(0, 1)                                                        # noqa: E731
+    idx = torch.randperm(T * N, generator=g)
+    mb = (T * N) // num_mini_batches
+    lr = 1e-3
+    for k in range(minibatch_steps):
+        i = idx[(k % num_mini_batches) * mb:((k % num_mini_batches) + 1) * mb]
+        batch = dict(obs=flat(st["obs"])[i], critic_obs=flat(st["obs"])[i], actions=flat(st["actions"])[i],
+                     target_values=flat(st["values"])[i], advantages=flat(adv)[i], returns=flat(returns)[i],
+                     old_actions_log_prob=flat(st["logp"])[i], old_mu=flat(st["mu"])[i], old_sigma=flat(st["sigma"])[i])
+        L = OT.ppo_losses(sd_ac, sd_est, batch)
+        opt_e.zero_grad()
+        L["estimator_loss"].backward()
+        torch.nn.utils.clip_grad_norm_(list(sd_est.values()), 1.0)
+        opt_e.step()
+        lr = OT.adaptive_lr(lr, float(L["kl_mean"]))
+        for pg in opt_a.param_groups:
+            pg["lr"] = lr
+        opt_a.zero_grad()
+        L["ppo_loss"].backward()
+        torch.nn.utils.clip_grad_norm_(list(sd_ac.values()), 1.0)
+        opt_a.step()
+    t3 = time.perf_counter()
+    return dict(t_rollout=t1 - t0, t_gae=t2 - t1, t_update=t3 - t2, rollout_steps=R, minibatch_steps=minibatch_steps)

@@ -1,0 +1,327 @@
+"""`SSInfoGAIL` -- the PPO half of the reference algorithm (bbc/rsl_rl/algorithms/gail.py:12-413) re-designed
+for one B200 per process:
+
+  * `act` / `process_env_step` / `compute_returns` keep the reference's signatures (:176-217);
+  * `update()` runs the 20 PPO minibatch steps of `update_actor_critic` (:328-413) with NO host round trip:
+    minibatches are gathered by one kernel (K6) into static buffers, the forward/backward of the whole step
+    is a replayed CUDA graph, the adaptive-KL learning rate (:368-379) lives in a device scalar, gradient
+    clipping + Adam are one fused pass over the flat parameter buffer (K8), and the per-minibatch loss
+    statistics are accumulated on the device and read back once per update (the reference calls `.item()`
+    six times per minibatch, :277-282);
+  * multi-GPU: envs are sharded one shard per rank; the only collectives are an in-place NCCL all-reduce of
+    the flat gradient buffers and of the scalar KL, both before the fused optimiser pass.
+
+The semi-supervised InfoGAIL discriminator update (`update_ss_info_gail`, :415-541) and DAgger
+(`update_dagger`, :543-575) are SURVEY.md 8(f) "next" rows and are not part of this path yet.
+"""
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from .. import ops
+from .storage import RolloutStorage
+
+
+class ReplayBuffer:
+    """Fixed-size ring of discriminator observations (storage/replay_buffer.py:6-48); filled every env step
+    by `process_env_step` (gail.py:207-208), consumed by the discriminator update."""
+
+    def __init__(self, obs_dim, dim_c, history_len, buffer_size, device):
+        self.states = torch.zeros(buffer_size, history_len * obs_dim, device=device)
+        self.latent_eps = torch.zeros(buffer_size, 1, device=device)
+        self.latent_c = torch.zeros(buffer_size, dim_c, device=device)
+        self.buffer_size, self.device = buffer_size, device
+        self.step = 0
+        self.num_samples = 0
+
+    def insert(self, states, latent_eps, latent_c):
+        n = states.shape[0]
+        first = min(n, self.buffer_size - self.step)
+        for dst, src in ((self.states, states), (self.latent_eps, latent_eps), (self.latent_c, latent_c)):
+            dst[self.step:self.step + first].copy_(src[:first])
+            if first < n:
+                dst[:n - first].copy_(src[first:])
+        self.num_samples = min(self.buffer_size, max(self.step + n, self.num_samples))
+        self.step = (self.step + n) % self.buffer_size
+
+
+class FlatAdam:
+    """Adam state for one flat parameter buffer; `step()` = clip_grad_norm_ + Adam.step through K8."""
+
+    def __init__(self, flat, lr: float, max_grad_norm: float, betas=(0.9, 0.999), eps=1e-8):
+        dev = flat.data.device
+        self.flat = flat
+        self.exp_avg = torch.zeros_like(flat.data)
+        self.exp_avg_sq = torch.zeros_like(flat.data)
+        self.lr = torch.full((1,), lr, device=dev, dtype=torch.float32)
+        self.step_count = torch.zeros(1, device=dev, dtype=torch.int32)
+        self.grad_norm = torch.zeros(1, device=dev, dtype=torch.float32)
+        self.ws = torch.zeros(2, device=dev, dtype=torch.float64)
+        self.betas, self.eps, self.max_grad_norm = betas, eps, max_grad_norm
+
+    def step(self, grad_scale: float = 1.0):
+        ops.clip_adam(self.flat.data, self.flat.grad, self.exp_avg, self.exp_avg_sq, self.lr, self.step_count, self.ws,
+                      self.betas[0], self.betas[1], self.eps, self.max_grad_norm, grad_scale, self.grad_norm)
+
+    # torch.optim-compatible state for checkpoints
+    def state_dict(self):
+        return {"exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "lr": self.lr, "step": self.step_count}
+
+    def load_state_dict(self, sd):
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        self.lr.copy_(sd["lr"])
+        self.step_count.copy_(sd["step"])
+
+
+STAT_NAMES = ("surrogate_loss", "value_loss", "b_loss", "entropy", "priv_reg_loss", "estimator_loss", "kl_mean")
+
+
+class SSInfoGAIL:
+    def __init__(self, env, actor_critic, discriminator, estimator, estimator_paras, motion_loader, disc_normalizer,
+                 disc_history_len, disc_obs_len, num_disc_obs, obs_disc_weight_step, disc_loss_function=None,
+                 num_learning_epochs=1, num_mini_batches=1, clip_param=0.2, gamma=0.998, lam=0.95,
+                 surrogate_loss_coef=1., value_loss_coef=5., entropy_coef=0., bounds_loss_coef=10., disc_coef=5.,
+                 disc_logit_reg=0.05, disc_grad_penalty=0.2, disc_weight_decay=0.0001, lr_ac=1e-3, lr_disc=1e-3,
+                 lr_q=1e-3, max_grad_norm=1.0, use_clipped_value_loss=False, schedule="fixed", desired_kl=0.01,
+                 device='cpu', disc_replay_buffer_size=100000, min_std=None, us_coef=1.0, ss_coef=4.0,
+                 prior_soft_coef=1e-3, info_max_coef=2.0, begin_rim=100, priv_reg_coef_schedual=[0, 0.1, 0, 1],
+                 priv_reg_coef_schedual_resume=[0, 0.1, 0, 1], use_cuda_graph=True):
+        self.device, self.env = device, env
+        self.desired_kl, self.schedule = desired_kl, schedule
+        self.lr_disc, self.lr_q, self.min_std = lr_disc, lr_q, min_std
+        self.dim_c = env.dim_c
+        self.disc_loss_function = disc_loss_function
+        self.disc_history_len, self.disc_obs_len, self.num_disc_obs = disc_history_len, disc_obs_len, num_disc_obs
+        self.obs_disc_weight_step = obs_disc_weight_step
+        self.disc = discriminator.to(device) if discriminator is not None else None
+        self.disc_storage = ReplayBuffer(env.num_obs_disc, self.dim_c, disc_obs_len, disc_replay_buffer_size, device)
+        self.motion_loader, self.disc_normalizer = motion_loader, disc_normalizer
+        cfg_env = env.cfg.env if hasattr(env.cfg, "env") else None
+        g = (lambda k, d: getattr(cfg_env, k, d)) if cfg_env is not None else (lambda k, d: d)
+        self.num_prop, self.num_explicit = g("num_prop", 57), g("num_explicit", 4)
+        self.num_latent, self.num_hist, self.num_command = g("num_latent", 29), g("history_len", 10), g("num_command", 11)
+
+        self.actor_critic = actor_critic.to(device)
+        self.estimator = estimator.to(device)
+        self.ac_flat = self.actor_critic.flatten_parameters()
+        self.est_flat = self.estimator.flatten_parameters()
+        self.optim_ac = FlatAdam(self.ac_flat, lr_ac, max_grad_norm)
+        self.optim_estimator = FlatAdam(self.est_flat, estimator_paras["learning_rate"], max_grad_norm)
+        self.train_with_estimated_explicit = estimator_paras["train_with_estimated_explicit"]
+        self.priv_reg_coef_schedual = priv_reg_coef_schedual
+        self.priv_reg_counter = 0
+        self.transition: Optional[RolloutStorage.Transition] = None
+        self.storage: Optional[RolloutStorage] = None
+
+        self.clip_param, self.num_learning_epochs, self.num_mini_batches = clip_param, num_learning_epochs, num_mini_batches
+        self.surrogate_loss_coef, self.value_loss_coef = surrogate_loss_coef, value_loss_coef
+        self.entropy_coef, self.bounds_loss_coef = entropy_coef, bounds_loss_coef
+        self.gamma, self.lam, self.max_grad_norm = gamma, lam, max_grad_norm
+        self.use_clipped_value_loss = use_clipped_value_loss
+        self.learning_steps = 0
+        self.world_size = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.use_cuda_graph = use_cuda_graph and torch.device(device).type == "cuda"
+        self._graphs = None
+        self._priv_reg_coef = torch.zeros((), device=device)
+        self._stats = torch.zeros(len(STAT_NAMES), device=device)
+        self.last_stats = {}
+
+    # ---- reference API --------------------------------------------------------------------------------
+    @property
+    def lr_ac(self) -> float:
+        return float(self.optim_ac.lr.item())
+
+    def init_storage(self, num_envs, num_transitions_per_env, actor_obs_shape, critic_obs_shape, action_shape):
+        self.transition = RolloutStorage.Transition(num_envs, actor_obs_shape, critic_obs_shape, action_shape, self.device)
+        self.storage = RolloutStorage(num_envs, num_transitions_per_env, actor_obs_shape, critic_obs_shape,
+                                      action_shape, self.device)
+
+    def test_mode(self):
+        self.actor_critic.eval()
+
+    def train_mode(self):
+        self.actor_critic.train()
+
+    @torch.no_grad()
+    def act(self, obs, critic_obs, hist_encoding=False, normal_draw=None):
+        """gail.py:176-197: estimator overwrite of the explicit privileged lanes, policy sample, value."""
+        tr, ac = self.transition, self.actor_critic
+        if self.train_with_estimated_explicit:
+            obs_est = obs.clone()
+            obs_est[:, self.num_prop:self.num_prop + self.num_explicit] = self.estimator(obs_est[:, :self.num_prop])
+            tr.actions = ac.act(obs_est, hist_encoding, normal_draw=normal_draw)
+        else:
+            tr.actions = ac.act(obs, hist_encoding, normal_draw=normal_draw)
+        tr.values = ac.evaluate(critic_obs)
+        tr.actions_log_prob = ac.get_actions_log_prob(tr.actions)
+        tr.action_mean, tr.action_sigma = ac.action_mean, ac.action_std
+        tr.observations, tr.critic_observations = obs, critic_obs
+        return tr.actions
+
+    @torch.no_grad()
+    def process_env_step(self, rewards, dones, infos, obs_disc_history_buf=None):
+        """gail.py:199-212 (time-out bootstrap happens in the dtype of `rewards`, float64 when they come from
+        predict_disc_reward; the storage copy rounds to fp32)."""
+        tr = self.transition
+        tr.rewards = rewards.clone()
+        tr.dones = dones
+        if 'time_outs' in infos:
+            tr.rewards += self.gamma * torch.squeeze(tr.values * infos['time_outs'].unsqueeze(1).to(self.device), 1)
+        if obs_disc_history_buf is not None:
+            self.disc_storage.insert(obs_disc_history_buf.view(obs_disc_history_buf.shape[0], -1), self.env.latent_eps,
+                                     self.env.latent_c)
+        self.storage.add_transitions(tr)
+        self.actor_critic.reset(dones)
+
+    @torch.no_grad()
+    def compute_returns(self, last_critic_obs):
+        last_values = self.actor_critic.evaluate(last_critic_obs)
+        self.storage.compute_returns(last_values, self.gamma, self.lam)
+
+    # ---- PPO minibatch step ------------------------------------------------------------------------------
+    def _alloc_minibatch(self, mb_size):
+        st, dev = self.storage, self.device
+        z = lambda w: torch.zeros(mb_size, w, device=dev)                       # noqa: E731
+        W, A = st.observations.shape[-1], st.actions.shape[-1]
+        Wc = st.privileged_observations.shape[-1] if st.privileged_observations is not None else W
+        self._mb = dict(obs=z(W), critic_obs=z(Wc), actions=z(A), values=z(1), returns=z(1),
+                        old_actions_log_prob=z(1), advantages=z(1), old_mu=z(A), old_sigma=z(A))
+        self._mb_keys = list(self._mb.keys())
+
+    def _gather(self, idx):
+        v = self.storage.flat_views()
+        ops.gather_minibatch(idx, [v[k] for k in self._mb_keys], [self._mb[k] for k in self._mb_keys])
+
+    def _forward_backward(self):
+        """Forward + both backward passes of one minibatch (gail.py:328-408) on the static minibatch buffers.
+        Leaves gradients in the flat buffers, kl_mean in `self._kl`, and adds the loss statistics."""
+        mb, ac, est = self._mb, self.actor_critic, self.estimator
+        obs = mb["obs"]
+        p, e, l, h = self.num_prop, self.num_explicit, self.num_latent, self.num_hist * self.num_prop
+        ac.update_distribution(obs, False)
+        mu, sigma = ac.action_mean, ac.action_std
+        logp = ac.get_actions_log_prob(mb["actions"])
+        value = ac.evaluate(mb["critic_obs"])
+        entropy = ac.entropy
+        priv_latent = ac.infer_priv_latent(obs[:, p + e:p + e + l])
+        with torch.no_grad():
+            hist_latent = ac.infer_hist_latent(obs[:, p + e + l:p + e + l + h])
+        priv_reg_loss = (priv_latent - hist_latent).norm(p=2, dim=1).mean()
+        # estimator (:359-365)
+        est_loss = (est(obs[:, :p]) - obs[:, p:p + e]).pow(2).mean()
+        self.est_flat.zero_grad()
+        est_loss.backward()
+        # KL for the adaptive schedule (:367-373)
+        with torch.no_grad():
+            osg, omu = mb["old_sigma"], mb["old_mu"]
+            kl = torch.sum(torch.log(sigma / osg + 1.e-5) + (torch.square(osg) + torch.square(omu - mu)) /
+                           (2.0 * torch.square(sigma)) - 0.5, dim=-1)
+            self._kl.copy_(kl.mean())
+        adv = mb["advantages"].squeeze(1)
+        ratio = torch.exp(logp - mb["old_actions_log_prob"].squeeze(1))
+        surrogate = -adv * ratio
+        surrogate_clipped = -adv * torch.clamp(ratio, 1.0 - self.clip_param, 1.0 + self.clip_param)
+        surrogate_loss = torch.max(surrogate, surrogate_clipped).mean()
+        if self.use_clipped_value_loss:
+            tv = mb["values"]
+            value_clipped = tv + (value - tv).clamp(-self.clip_param, self.clip_param)
+            value_loss = torch.max((value - mb["returns"]).pow(2), (value_clipped - mb["returns"]).pow(2)).mean()
+        else:
+            value_loss = (mb["returns"] - value).pow(2).mean()
+        b_loss = (torch.clamp(mu + 1.0, max=0.) ** 2 + torch.clamp(mu - 1.0, min=0.) ** 2).sum(dim=-1).mean()
+        ent = entropy.mean()
+        loss = (self.surrogate_loss_coef * surrogate_loss + self.value_loss_coef * value_loss +
+                self.bounds_loss_coef * b_loss - self.entropy_coef * ent + self._priv_reg_coef * priv_reg_loss)
+        self.ac_flat.zero_grad()
+        loss.backward()
+        with torch.no_grad():
+            self._stats += torch.stack([surrogate_loss.detach(), value_loss.detach(), b_loss.detach(), ent.detach(),
+                                        priv_reg_loss.detach(), est_loss.detach(), self._kl])
+
+    def _apply(self):
+        """All-reduce (multi-GPU), adaptive LR on the device (:374-379), fused clip + Adam (:361-365, :409-412)."""
+        scale = 1.0
+        if self.world_size > 1:
+            dist.all_reduce(self.ac_flat.grad)
+            dist.all_reduce(self.est_flat.grad)
+            dist.all_reduce(self._kl)
+            self._kl /= self.world_size
+            scale = 1.0 / self.world_size
+        self.optim_estimator.step(scale)
+        if self.desired_kl is not None and self.schedule == 'adaptive':
+            lr, kl = self.optim_ac.lr, self._kl
+            hi = kl > self.desired_kl * 2.0
+            lo = (kl < self.desired_kl / 2.0) & (kl > 0.0)
+            lr.copy_(torch.where(hi, torch.clamp(lr / 1.5, min=1e-5), torch.where(lo, torch.clamp(lr * 1.5, max=1e-2), lr)))
+        self.optim_ac.step(scale)
+
+    def _minibatch_step(self):
+        self._forward_backward()
+        self._apply()
+
+    def _capture(self):
+        """Warm up on a side stream, then capture the minibatch step (one graph when single-GPU; the
+        forward/backward graph and the apply graph are split around the eager NCCL all-reduce otherwise)."""
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        snap = [t.clone() for t in (self.ac_flat.data, self.est_flat.data, self.optim_ac.exp_avg, self.optim_ac.exp_avg_sq,
+                                    self.optim_estimator.exp_avg, self.optim_estimator.exp_avg_sq, self.optim_ac.lr,
+                                    self.optim_ac.step_count, self.optim_estimator.step_count, self._stats)]
+        with torch.cuda.stream(s):
+            for _ in range(3):
+                self._minibatch_step()
+        torch.cuda.current_stream().wait_stream(s)
+        if self.world_size == 1:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._minibatch_step()
+            self._graphs = (g,)
+        else:
+            g1 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1):
+                self._forward_backward()
+            self._graphs = (g1,)
+        # undo the warm-up / capture side effects on the trainable state
+        for t, v in zip((self.ac_flat.data, self.est_flat.data, self.optim_ac.exp_avg, self.optim_ac.exp_avg_sq,
+                         self.optim_estimator.exp_avg, self.optim_estimator.exp_avg_sq, self.optim_ac.lr,
+                         self.optim_ac.step_count, self.optim_estimator.step_count, self._stats), snap):
+            t.copy_(v)
+
+    def update(self, indices: Optional[torch.Tensor] = None):
+        """PPO part of SSInfoGAIL.update (:231-326): num_learning_epochs x num_mini_batches minibatch steps over
+        ONE permutation.  Returns the reference's first six means (surrogate, value, bound, entropy, priv_reg,
+        estimator); the discriminator statistics are not produced (next row)."""
+        st = self.storage
+        batch = st.num_envs * st.num_transitions_per_env
+        mb_size = batch // self.num_mini_batches
+        if getattr(self, "_mb", None) is None or self._mb["obs"].shape[0] != mb_size:
+            self._alloc_minibatch(mb_size)
+            self._kl = torch.zeros((), device=self.device)
+            self._graphs = None
+        self.learning_steps += 1
+        sch = self.priv_reg_coef_schedual
+        stage = min(max((self.priv_reg_counter - sch[2]), 0) / sch[3], 1)
+        self._priv_reg_coef.fill_(stage * (sch[1] - sch[0]) + sch[0])
+        if indices is None:
+            indices = torch.randperm(self.num_mini_batches * mb_size, device=self.device)
+        if self.use_cuda_graph and self._graphs is None:
+            self._gather(indices[:mb_size])
+            self._capture()
+        self._stats.zero_()
+        for _ in range(self.num_learning_epochs):
+            for i in range(self.num_mini_batches):
+                self._gather(indices[i * mb_size:(i + 1) * mb_size])
+                if self.use_cuda_graph:
+                    self._graphs[0].replay()
+                    if self.world_size > 1:
+                        self._apply()
+                else:
+                    self._minibatch_step()
+        n = self.num_learning_epochs * self.num_mini_batches
+        vals = (self._stats / n).tolist()                      # the one host sync of the update
+        self.last_stats = dict(zip(STAT_NAMES, vals))
+        st.clear()
+        self.priv_reg_counter += 1
+        return tuple(vals[:6])

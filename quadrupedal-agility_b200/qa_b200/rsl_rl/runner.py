@@ -1,0 +1,140 @@
+"""`OnPolicyRunner` -- rollout / learn loop with the reference's constructor, `learn`, `save`, `load` and
+`get_inference_policy` (bbc/rsl_rl/runners/on_policy_runner.py:18-351).
+
+Loop order per step is the reference's (:156-181): act -> env.step -> disc-history update with the terminal
+states patched in -> predict_disc_reward -> process_env_step -> reset rows of the disc history.  The
+variable-length `reset_env_ids` indexing of the reference is replaced by dense masked selects on the reset
+mask (same values, no host sync); TensorBoard bookkeeping (:183-206, :238-304) is SURVEY 8(f) "next" and only
+the throughput numbers the reference logs as Perf/* are kept.
+"""
+import os
+import time
+
+import torch
+
+from .. import config as K
+from .algorithm import SSInfoGAIL
+from .modules import ActorCritic, Estimator, Discriminator
+from .utils import Normalizer, install_pickle_alias
+
+
+class OnPolicyRunner:
+    def __init__(self, env, train_cfg, log_dir=None, device='cpu', motion_loader=None):
+        self.device, self.env = device, env
+        self.cfg, self.alg_cfg = train_cfg["runner"], dict(train_cfg["algorithm"])
+        self.policy_cfg, self.estimator_cfg = train_cfg["policy"], train_cfg["estimator"]
+        self.disc_loss_function = self.alg_cfg["disc_loss_function"]
+        r = self.cfg
+        self.disc_history_len, self.disc_obs_len, self.obs_disc_weight_step = 2, K.DISC_OBS_LEN, 0.0
+        num_prop, num_hist, num_explicit = K.NUM_PROP, K.HISTORY_LEN, K.NUM_EXPLICIT
+        num_latent, num_command = K.NUM_LATENT, K.NUM_COMMAND
+        num_actor_obs = env.num_obs
+        num_critic_obs = env.num_obs + num_hist * num_prop
+        num_disc_obs = env.num_obs_disc
+        actor_critic = ActorCritic(num_actor_obs, num_critic_obs, env.num_actions, num_prop, num_hist, num_explicit,
+                                   num_latent, num_command, **self.policy_cfg).to(device)
+        estimator = Estimator(input_dim=num_prop, output_dim=num_explicit,
+                              hidden_dims=self.estimator_cfg["hidden_dims"]).to(device)
+        disc_normalizer = Normalizer(num_disc_obs * self.disc_obs_len)
+        discriminator = Discriminator(env, num_disc_obs * self.disc_obs_len, num_disc_obs, len(env.mocap_category),
+                                      env.dt, self.disc_loss_function, None, r["reward_i_coef"], r["reward_us_coef"],
+                                      r["reward_ss_coef"], r["reward_t_coef"], self.disc_history_len, self.disc_obs_len,
+                                      self.obs_disc_weight_step, r["disc_hidden_units"], device).to(device)
+        min_std = (torch.tensor(r["min_normalized_std"], device=device) *
+                   torch.abs(env.dof_pos_limits[:, 1] - env.dof_pos_limits[:, 0]))
+        self.alg = SSInfoGAIL(env, actor_critic, discriminator, estimator, self.estimator_cfg, motion_loader,
+                              disc_normalizer, self.disc_history_len, self.disc_obs_len, num_disc_obs,
+                              self.obs_disc_weight_step, device=device, min_std=min_std, **self.alg_cfg)
+        self.num_steps_per_env = r["num_steps_per_env"]
+        self.save_interval = r["save_interval"]
+        self.dagger_update_freq = r["dagger_update_freq"]
+        self.alg.init_storage(env.num_envs, self.num_steps_per_env, [num_actor_obs + num_hist * num_prop],
+                              [env.num_privileged_obs + num_hist * num_prop], [env.num_actions])
+        self.log_dir = log_dir
+        self.tot_timesteps, self.tot_time, self.current_learning_iteration = 0, 0.0, 0
+        self.perf = {}
+        self._disc_hist = None
+        env.reset()
+
+    # ---- one rollout step (:156-181) ----------------------------------------------------------------------
+    def rollout_step(self, obs, critic_obs, hist_encoding=False):
+        env, alg = self.env, self.alg
+        actions = alg.act(obs, critic_obs, hist_encoding)
+        prev_disc = env.get_disc_observations()
+        next_obs, next_priv, rewards, dones, _ids, _cnt, _term = env.step_device(actions)
+        next_disc = env.get_disc_observations()
+        done_col = dones.unsqueeze(1)
+        # terminal disc state of a reset env == its disc obs of the previous step (:153-154, :166-167)
+        with_term = torch.where(done_col, prev_disc, next_disc)
+        hist = torch.stack([self._disc_hist[:, 1], with_term], dim=1)
+        rew, r_i, r_us, r_ss, r_t = alg.disc.predict_disc_reward(rewards.unsqueeze(1), obs, hist,
+                                                                 normalizer=alg.disc_normalizer)
+        infos = {"time_outs": env._time_outs_latched} if env.cfg.send_timeouts else {}
+        alg.process_env_step(rew, dones, infos, hist)
+        # fresh episodes restart their discriminator history (:180-181)
+        self._disc_hist = torch.where(done_col.unsqueeze(2), next_disc.unsqueeze(1).expand(-1, self.disc_obs_len, -1), hist)
+        return next_obs, next_priv
+
+    def learn(self, num_learning_iterations, init_at_random_ep_len=False):
+        env, alg = self.env, self.alg
+        if init_at_random_ep_len:
+            env.episode_length_buf.copy_(torch.randint_like(env.episode_length_buf, high=int(env.max_episode_length)))
+        obs, critic_obs = env.get_observations(), env.get_privileged_observations()
+        self._disc_hist = torch.stack([env.get_disc_observations()] * self.disc_obs_len, dim=1)
+        alg.actor_critic.train()
+        for it in range(self.current_learning_iteration, self.current_learning_iteration + num_learning_iterations):
+            start = time.time()
+            hist_encoding = it % self.dagger_update_freq == 0
+            with torch.inference_mode(False), torch.no_grad():
+                for _ in range(self.num_steps_per_env):
+                    obs, critic_obs = self.rollout_step(obs, critic_obs, hist_encoding)
+                torch.cuda.synchronize() if torch.device(self.device).type == "cuda" else None
+                stop = time.time()
+                collection_time = stop - start
+                start = stop
+                alg.compute_returns(critic_obs)
+            stats = alg.update()
+            if env.task_obs_weight_decay_steps:
+                env.task_obs_weight = max(0, env.task_obs_weight - 1.0 / env.task_obs_weight_decay_steps)
+            learn_time = time.time() - start
+            self.tot_timesteps += self.num_steps_per_env * env.num_envs
+            self.tot_time += collection_time + learn_time
+            self.perf = {"total_fps": int(self.num_steps_per_env * env.num_envs / (collection_time + learn_time)),
+                         "collection_time": collection_time, "learning_time": learn_time, "stats": stats}
+            if self.log_dir is not None and (it + 1) % self.save_interval == 0:
+                self.save(os.path.join(self.log_dir, 'model.pt'))
+        self.current_learning_iteration += num_learning_iterations
+        if self.log_dir is not None:
+            self.save(os.path.join(self.log_dir, 'model.pt'))
+
+    # ---- checkpoints (:306-339): same top-level keys; flat Adam state replaces the torch.optim dicts ----------
+    def save(self, path, infos=None):
+        os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+        torch.save({'actor_critic': self.alg.actor_critic.state_dict(), 'estimator': self.alg.estimator.state_dict(),
+                    'disc': self.alg.disc.state_dict(), 'optim_ac': self.alg.optim_ac.state_dict(),
+                    'optim_estimator': self.alg.optim_estimator.state_dict(),
+                    'disc_normalizer': self.alg.disc_normalizer, 'reward_i_normalizer': None,
+                    'iter': self.current_learning_iteration, 'infos': infos}, path)
+
+    def load(self, path, load_optimizer=True):
+        install_pickle_alias()
+        d = torch.load(path, map_location=self.device, weights_only=False)
+        self.alg.actor_critic.load_state_dict(d['actor_critic'])
+        self.alg.estimator.load_state_dict(d['estimator'])
+        self.alg.disc.load_state_dict(d['disc'])
+        n = d['disc_normalizer']
+        if n is not None:
+            mine = Normalizer(n.mean.shape[0], epsilon=n.epsilon, clip_obs=n.clip_obs)
+            mine.mean, mine.var, mine.count = n.mean, n.var, n.count
+            self.alg.disc_normalizer = mine
+        if load_optimizer and isinstance(d.get('optim_ac'), dict) and 'exp_avg' in d['optim_ac']:
+            self.alg.optim_ac.load_state_dict(d['optim_ac'])
+            self.alg.optim_estimator.load_state_dict(d['optim_estimator'])
+        self.current_learning_iteration = d.get('iter', 0)
+        return d.get('infos')
+
+    def get_inference_policy(self, device=None):
+        self.alg.actor_critic.eval()
+        if device is not None:
+            self.alg.actor_critic.to(device)
+        return self.alg.actor_critic.act_inference

@@ -215,3 +215,52 @@ def make_rng_draws(cfg: BbcEnvConfig, seed: int = 1234, step: int = 0,
     d["mocap_clip_u"] = torch.rand(N, generator=gen, dtype=torch.float64)   # -> clip within the env's mode
     d["mocap_time_u"] = torch.rand(N, generator=gen, dtype=torch.float64)   # np.random.uniform (float64)
     return d
+
+
+# ------------------------------------------------------------------------------------------
+# Seeded network weights with the reference's state_dict names / shapes (tsc/weights/bbc/model.pt layout).
+# The GPU box has neither the reference nor its checkpoint; tests regenerate these from the seed.
+# ------------------------------------------------------------------------------------------
+AC_SHAPES = [("std", (12,)), ("priv_encoder.0.weight", (64, 29)), ("priv_encoder.0.bias", (64,)),
+             ("priv_encoder.2.weight", (29, 64)), ("priv_encoder.2.bias", (29,)),
+             ("history_encoder.encoder.0.weight", (30, 57)), ("history_encoder.encoder.0.bias", (30,)),
+             ("history_encoder.conv_layers.0.weight", (20, 30, 4)), ("history_encoder.conv_layers.0.bias", (20,)),
+             ("history_encoder.conv_layers.2.weight", (10, 20, 2)), ("history_encoder.conv_layers.2.bias", (10,)),
+             ("history_encoder.linear_output.0.weight", (29, 30)), ("history_encoder.linear_output.0.bias", (29,)),
+             ("actor_trunk.0.weight", (512, 101)), ("actor_trunk.0.bias", (512,)),
+             ("actor_trunk.2.weight", (256, 512)), ("actor_trunk.2.bias", (256,)),
+             ("actor_trunk.4.weight", (128, 256)), ("actor_trunk.4.bias", (128,)),
+             ("actor_head.weight", (12, 128)), ("actor_head.bias", (12,)),
+             ("critic_trunk.0.weight", (512, 671)), ("critic_trunk.0.bias", (512,)),
+             ("critic_trunk.2.weight", (256, 512)), ("critic_trunk.2.bias", (256,)),
+             ("critic_trunk.4.weight", (128, 256)), ("critic_trunk.4.bias", (128,)),
+             ("critic_head.weight", (1, 128)), ("critic_head.bias", (1,))]
+EST_SHAPES = [("estimator.0.weight", (128, 57)), ("estimator.0.bias", (128,)), ("estimator.2.weight", (64, 128)),
+              ("estimator.2.bias", (64,)), ("estimator.4.weight", (4, 64)), ("estimator.4.bias", (4,))]
+DISC_SHAPES = [("trunk.0.weight", (512, 98)), ("trunk.0.bias", (512,)), ("trunk.2.weight", (256, 512)),
+               ("trunk.2.bias", (256,)), ("linear.weight", (1, 256)), ("linear.bias", (1,)),
+               ("classifier.weight", (5, 256)), ("classifier.bias", (5,)), ("encoder_eps.weight", (1, 256)),
+               ("encoder_eps.bias", (1,))]
+
+
+def _make_sd(shapes, gen):
+    sd = {}
+    for name, shape in shapes:
+        if name == "std":
+            sd[name] = 0.6 + 0.4 * torch.rand(shape, generator=gen)
+        elif name.endswith("bias"):
+            sd[name] = 0.05 * torch.randn(shape, generator=gen)
+        else:
+            fan_in = 1
+            for d in shape[1:]:
+                fan_in *= d
+            sd[name] = (2 * torch.rand(shape, generator=gen) - 1) * (1.7 / math.sqrt(fan_in))
+    return sd
+
+
+def make_weights(seed: int = 0):
+    """Returns dict(ac=..., est=..., disc=..., norm_mean (98,) f64, norm_var (98,) f64)."""
+    gen = torch.Generator().manual_seed(seed * 31337 + 11)
+    return dict(ac=_make_sd(AC_SHAPES, gen), est=_make_sd(EST_SHAPES, gen), disc=_make_sd(DISC_SHAPES, gen),
+                norm_mean=0.2 * torch.randn(98, generator=gen, dtype=torch.float64),
+                norm_var=0.2 + torch.rand(98, generator=gen, dtype=torch.float64))

@@ -54,3 +54,28 @@ def test_gae_oracle_matches_reference_golden(name):
 
 def test_reward_order_is_alphabetical():
     assert list(C.REWARD_NAMES) == sorted(C.REWARD_NAMES) and len(C.REWARD_NAMES) == 14
+
+
+def test_policy_oracle_matches_reference_golden():
+    """oracle/trainer.py act / predict_disc_reward / ppo_losses vs the reference's recorded outputs."""
+    from qa_b200 import synthetic
+    torch.set_num_threads(1)
+    z = np.load(f"{GOLD}/trainer_policy_seed3.npz")
+    g = {k: torch.from_numpy(z[k]) for k in z.files}
+    w = synthetic.make_weights(int(g["in.weights_seed"]))
+    for he in (False, True):
+        o = OT.act(w["ac"], w["est"], g["in.obs"], g["in.obs"], g["in.draw"], hist_encoding=he)
+        for k in ("actions", "values", "actions_log_prob", "action_mean", "action_sigma"):
+            assert torch.allclose(o[k], g[f"act{int(he)}.{k}"], rtol=1e-6, atol=1e-6), k
+    r = OT.predict_disc_reward(w["disc"], g["in.rew_t"], g["in.obs"], g["in.disc_hist"], w["norm_mean"], w["norm_var"],
+                               0.02, float(g["in.task_obs_weight"]))
+    for k, v in zip(("rewards", "reward_i", "reward_us", "reward_ss", "reward_t"), r):
+        assert v.dtype == g[f"disc.{k}"].dtype and torch.allclose(v, g[f"disc.{k}"], rtol=1e-6, atol=1e-7), k
+    batch = dict(obs=g["in.obs"], critic_obs=g["in.obs"], actions=g["in.batch.actions"],
+                 target_values=g["in.batch.target_values"], advantages=g["in.batch.advantages"],
+                 returns=g["in.batch.returns"], old_actions_log_prob=g["in.batch.old_actions_log_prob"],
+                 old_mu=g["in.batch.old_mu"], old_sigma=g["in.batch.old_sigma"])
+    L = OT.ppo_losses(w["ac"], w["est"], batch, priv_reg_coef=OT.priv_reg_coef(int(g["in.priv_reg_counter"])))
+    for k in ("surrogate_loss", "value_loss", "b_loss", "entropy", "priv_reg_loss", "estimator_loss"):
+        assert torch.allclose(L[k], g[f"ppo.{k}"], rtol=1e-5, atol=1e-7), k
+    assert abs(OT.adaptive_lr(1e-3, float(L["kl_mean"])) - float(g["ppo.lr_new"])) < 1e-12

@@ -1,0 +1,154 @@
+"""GPU parity of the trainer half (policy act, discriminator reward, gather, fused clip+Adam, one PPO
+minibatch step) against golden vectors produced by the UNMODIFIED reference classes
+(oracle/gen_golden_policy.py) and against the CPU oracle.
+
+Tolerances: the dense layers run through cuBLAS/tensor cores in fp32 here (TF32 is NOT enabled), so the
+comparison with the reference's CPU fp32 results uses rtol 1e-4 on network outputs (different summation order
+over K up to 671) and 1e-5 on everything element-wise."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import trainer as OT
+from helpers import GOLD, assert_close
+from qa_b200 import ops, synthetic
+from qa_b200.config import bbc_train_cfg
+from qa_b200.rsl_rl import ActorCritic, Estimator, Discriminator, Normalizer, RolloutStorage, SSInfoGAIL
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+NET_RTOL, NET_ATOL = 1e-4, 2e-5
+
+
+def load_golden():
+    z = np.load(f"{GOLD}/trainer_policy_seed3.npz")
+    return {k: torch.from_numpy(z[k]) for k in z.files}
+
+
+def build(w, n_envs=64):
+    cfg = bbc_train_cfg()
+    ac = ActorCritic(101, 671, 12, 57, 10, 4, 29, 11, **cfg["policy"])
+    ac.load_state_dict(w["ac"])
+    est = Estimator(57, 4, hidden_dims=[128, 64])
+    est.load_state_dict(w["est"])
+    env = types.SimpleNamespace(task_obs_weight_decay=True, task_obs_weight=0.7, dim_c=5, num_obs_disc=49,
+                                cfg=types.SimpleNamespace(), latent_eps=None, latent_c=None)
+    disc = Discriminator(env, 98, 49, 5, 0.02, "MSELoss", None, 1.0, 0.01, 0.2, 0.2, 2, 2, 0.0, [512, 256], DEV)
+    disc.load_state_dict(w["disc"])
+    norm = Normalizer(98)
+    norm.mean, norm.var = w["norm_mean"].numpy().copy(), w["norm_var"].numpy().copy()
+    alg = SSInfoGAIL(env, ac, disc, est, cfg["estimator"], None, norm, 2, 2, 49, 0.0, device=DEV,
+                     use_cuda_graph=False, disc_replay_buffer_size=1024, **cfg["algorithm"])
+    alg.init_storage(n_envs, 24, [671], [671], [12])
+    return alg, env, norm
+
+
+def test_act_and_disc_reward_match_reference_golden():
+    g = load_golden()
+    alg, env, norm = build(synthetic.make_weights(3))
+    obs, draw = g["in.obs"].to(DEV), g["in.draw"].to(DEV)
+    for he in (False, True):
+        a = alg.act(obs.clone(), obs.clone(), hist_encoding=he, normal_draw=draw)
+        tr = alg.transition
+        for k, v in (("actions", a), ("values", tr.values), ("actions_log_prob", tr.actions_log_prob),
+                     ("action_mean", tr.action_mean), ("action_sigma", tr.action_sigma)):
+            assert_close(f"act{int(he)}.{k}", v, g[f"act{int(he)}.{k}"], rtol=NET_RTOL, atol=NET_ATOL)
+    out = alg.disc.predict_disc_reward(g["in.rew_t"].to(DEV), obs, g["in.disc_hist"].to(DEV), normalizer=norm)
+    for k, v in zip(("rewards", "reward_i", "reward_us", "reward_ss", "reward_t"), out):
+        assert v.dtype == g[f"disc.{k}"].dtype, k                       # float64 quirk preserved
+        assert_close(f"disc.{k}", v, g[f"disc.{k}"], rtol=NET_RTOL, atol=NET_ATOL)
+
+
+def test_ppo_minibatch_step_matches_reference_golden():
+    g = load_golden()
+    alg, env, norm = build(synthetic.make_weights(3))
+    alg.priv_reg_counter = int(g["in.priv_reg_counter"])
+    alg._alloc_minibatch(64)
+    alg._kl = torch.zeros((), device=DEV)
+    mb = alg._mb
+    mb["obs"].copy_(g["in.obs"])
+    mb["critic_obs"].copy_(g["in.obs"])
+    for k_mb, k_g in (("actions", "actions"), ("values", "target_values"), ("returns", "returns"),
+                      ("old_actions_log_prob", "old_actions_log_prob"), ("advantages", "advantages"),
+                      ("old_mu", "old_mu"), ("old_sigma", "old_sigma")):
+        mb[k_mb].copy_(g["in.batch." + k_g])
+    alg._priv_reg_coef.fill_(OT.priv_reg_coef(1500))
+    alg._stats.zero_()
+    alg._minibatch_step()
+    torch.cuda.synchronize()
+    stats = alg._stats.cpu()
+    for i, k in enumerate(("surrogate_loss", "value_loss", "b_loss", "entropy", "priv_reg_loss", "estimator_loss")):
+        assert_close(f"ppo.{k}", stats[i], g[f"ppo.{k}"], rtol=NET_RTOL, atol=NET_ATOL)
+    assert_close("kl_mean", stats[6], g["ppo.kl_mean"], rtol=1e-3, atol=1e-5)
+    assert abs(alg.lr_ac - float(g["ppo.lr_new"])) < 1e-9
+    stride = int(g["in.param_stride"])
+    # post-step parameters: Adam's first step moves every weight by ~lr * sign(g); compare sampled entries
+    ac_flat = torch.cat([v.reshape(-1) for v in alg.actor_critic.state_dict().values()])[::stride]
+    est_flat = torch.cat([v.reshape(-1) for v in alg.estimator.state_dict().values()])[::stride]
+    assert_close("ac params after step", ac_flat, g["ppo.ac_params_sampled"], rtol=1e-4, atol=2e-5)
+    assert_close("est params after step", est_flat, g["ppo.est_params_sampled"], rtol=1e-4, atol=2e-6)
+
+
+def test_gather_minibatch_matches_indexing():
+    g = torch.Generator().manual_seed(0)
+    R = 24 * 512
+    srcs = [torch.randn(R, w, generator=g).to(DEV) for w in (671, 671, 12, 1, 1, 1, 1, 12, 12)]
+    idx = torch.randperm(R, generator=g)[:3000].to(DEV)
+    dsts = [torch.empty(3000, s.shape[1], device=DEV) for s in srcs]
+    ops.gather_minibatch(idx, srcs, dsts)
+    for s, d in zip(srcs, dsts):
+        assert torch.equal(d, s[idx])
+    ops.gather_minibatch(idx[:0], srcs, [d[:0] for d in dsts])         # empty minibatch
+
+
+def test_clip_adam_matches_torch():
+    g = torch.Generator().manual_seed(1)
+    n = 735699
+    p0 = torch.randn(n, generator=g)
+    for max_norm, scale in ((1.0, 1.0), (1e9, 0.5)):
+        p_ref = p0.clone().requires_grad_(True)
+        opt = torch.optim.Adam([p_ref], lr=3e-4)
+        p, m, v = p0.clone().to(DEV), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+        lr, step = torch.full((1,), 3e-4, device=DEV), torch.zeros(1, dtype=torch.int32, device=DEV)
+        ws, gn = torch.zeros(2, dtype=torch.float64, device=DEV), torch.zeros(1, device=DEV)
+        for it in range(3):
+            grad = torch.randn(n, generator=g) * (0.01 if it else 1.0)
+            p_ref.grad = (grad * scale).clone()
+            tn = torch.nn.utils.clip_grad_norm_([p_ref], max_norm)
+            opt.step()
+            ops.clip_adam(p, grad.to(DEV), m, v, lr, step, ws, max_grad_norm=max_norm, grad_scale=scale, grad_norm_out=gn)
+            assert_close("grad norm", gn[0], tn, rtol=1e-5)
+        assert int(step.item()) == 3
+        assert_close("params", p, p_ref.detach(), rtol=1e-5, atol=1e-6)
+
+
+def test_update_runs_with_and_without_cuda_graph_identically():
+    """The captured-graph path of SSInfoGAIL.update is the same computation as the eager path."""
+    outs = []
+    for graph in (False, True):
+        torch.manual_seed(0)
+        alg, env, norm = build(synthetic.make_weights(4), n_envs=64)
+        alg.use_cuda_graph = graph
+        st = alg.storage
+        g = torch.Generator().manual_seed(2)
+        st.observations.copy_(torch.randn(24, 64, 671, generator=g))
+        st.privileged_observations.copy_(st.observations)
+        with torch.no_grad():
+            for t in range(24):
+                o = st.observations[t]
+                alg.act(o, o, normal_draw=torch.randn(64, 12, generator=g).to(DEV))
+                tr = alg.transition
+                st.actions[t], st.values[t] = tr.actions, tr.values
+                st.actions_log_prob[t, :, 0], st.mu[t], st.sigma[t] = tr.actions_log_prob, tr.action_mean, tr.action_sigma
+        st.rewards.copy_(0.05 * torch.rand(24, 64, 1, generator=g))
+        st.dones.copy_((torch.rand(24, 64, 1, generator=g) < 0.02).byte())
+        st.compute_returns(torch.zeros(64, 1, device=DEV), 0.99, 0.95)
+        idx = torch.randperm(24 * 64, generator=g).to(DEV)
+        stats = alg.update(indices=idx)
+        outs.append((stats, alg.ac_flat.data.clone(), alg.lr_ac))
+    for a, b in zip(outs[0][0], outs[1][0]):
+        assert abs(a - b) <= 1e-4 * max(1.0, abs(a)), (outs[0][0], outs[1][0])
+    assert_close("params eager vs graph", outs[1][1], outs[0][1], rtol=1e-4, atol=1e-5)
+    assert outs[0][2] == outs[1][2]
