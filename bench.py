@@ -112,7 +112,7 @@ def run_ours(args):
     from qa_b200.pipeline import BbcIteration
     cfg, static, snaps, table = build_workload(rank, dev)
     it = BbcIteration(cfg, static, snaps, table, device=dev, seed=1234 + rank, world_size=world,
-                      bulk_store=bool(args.k2_bulk))
+                      bulk_store=bool(args.k2_bulk), tiled=(args.k2_bulk == 2))
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
@@ -142,6 +142,7 @@ def run_ours(args):
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     k2_ms, k2_launches = it.k2_time_ms()
+    collect_ms, learn_ms = it.phase_ms()
     launches = it.launch_count
     t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -175,7 +176,8 @@ def run_ours(args):
         cpu = cpu_baseline_sample() if world == 1 and not args.no_cpu_baseline else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "collection_ms": collect_ms, "learning_ms": learn_ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": it.dtype_name, "data": "synthetic",
             "config": {"workload": it.workload_name, "envs_per_gpu": cfg.num_envs, "steps_per_env": T_STEPS,
                        "stages": it.stage_names, "rng": "in-kernel Philox4x32-10",
@@ -263,7 +265,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--k2-bulk", type=int, default=1, help="1: TMA bulk stores for the obs rows (default), 0: warp stores")
+    ap.add_argument("--k2-bulk", type=int, default=2,
+                    help="K2 variant: 2 = 8-env TMA tiles (default), 1 = warp-per-env + TMA row stores, 0 = warp stores")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

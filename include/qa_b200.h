@@ -45,6 +45,7 @@ extern "C" {
 #define QA_ACT_HIST_LEN 8
 #define QA_MOCAP_W 49
 #define QA_MAX_BODIES 32
+#define QA_MAX_NOISE_LANES 64
 
 int qa_version(void);
 /* human readable build string ("sm_100a, nvcc 12.9, ...") */
@@ -198,9 +199,16 @@ typedef struct QaBbcConst {
     float max_push_vel_xy;
     double time_between_frames;         /* env.dt as double (mocap time sampling) */
     int32_t disc_obs_len;
+    /* compact form of noise_scale_vec (legged_robot.py:721-740): the lanes of the 671-row with a non-zero
+     * scale (32 in the shipped config), so that noise costs one pass over <= 64 lanes, not 671 */
+    int32_t num_noise;
+    int32_t noise_idx[QA_MAX_NOISE_LANES];
+    float noise_scale[QA_MAX_NOISE_LANES];
 } QaBbcConst;
 
 #define QA_K2_BULK_STORE 1u   /* obs/priv rows leave through TMA bulk stores (needs pitch 671, N % 4 == 0) */
+#define QA_K2_TILED 2u        /* 8-env CTA tiles, every per-env array staged by TMA bulk copies (needs N % 8 == 0,
+                               * 16 B aligned bases, pitch 671); falls back to the warp-per-env kernel otherwise */
 
 typedef struct QaBbcStepArgs {
     int32_t num_envs;

@@ -1,0 +1,569 @@
+// K2 "tiled" variant: the fused BBC post-physics step with 8-env CTA tiles staged entirely by TMA.
+//
+// Same function as k_post_physics_bbc (qa_post_physics_bbc.cu; reference lines cited there), restructured after
+// the round-1 profile showed the warp-per-env kernel to be instruction/latency bound (3150 warp-instructions per
+// env, 32x redundant scalar math, serialised global->shared copies), not HBM bound:
+//
+//   P0  one thread issues ~22 TMA bulk loads (cp.async.bulk + mbarrier complete_tx) for EVERY per-env array of
+//       the CTA's 8 envs -- each array's 8-env slice is contiguous and 16 B aligned -- while the other threads
+//       fetch the two strided inputs (feet positions, last action);
+//   P1  warp-per-env, lanes = DOFs / bodies: the nine 12-wide reward sums (warp-shuffle butterflies) and the
+//       contact-force norms (ballots) -> per-env scalars in shared memory;
+//   P2  thread-per-env (8 lanes of warp 0): the scalar program -- base-frame quantities, euler angles, centre
+//       terrain height, periodic resampling, push, termination, reward total, episode sums, reset decision;
+//       SIMD across envs instead of 32x redundant;
+//   P3  warp-per-env: reset envs blend their mocap frame (lanes = frame columns) and rewrite simulator state;
+//       then key-body positions, the 671-float row, history shift, noise on the <= 64 noisy lanes, clip, disc obs;
+//   P4  one thread issues the TMA bulk stores of every output tile (obs, privileged obs, history, disc obs,
+//       last_*, episode sums, commands ...); reset statistics are finalised by the last CTA as in the other kernel.
+//
+// Per env this is ~1100 warp-instructions, and all global traffic is full-line bulk copies.
+#include "qa_k2_common.cuh"
+
+#define T2_ENVS 8
+#define T2_THREADS (T2_ENVS * 32)
+
+// per-env scalar slots (floats) exchanged between the phases
+enum {
+    SC_SUM0 = 0,        // 9 DOF sums: action_rate, delta_torques, dof_acc, dof_error, dof_pos_limits, dof_vel_limits,
+                        //             hip_pos, torque_limits, torques
+    SC_NCOL = 9,
+    SC_TERM = 10,
+    SC_FF = 11,         // 4 feet force norms
+    SC_RESET = 15,
+    SC_CH = 16,         // centre terrain height
+    SC_MODE = 17,       // behaviour mode drawn at reset (int bits)
+    SC_N = 32
+};
+
+struct __align__(16) T2Smem {
+    float obs[T2_ENVS * ROW];
+    float hist[T2_ENVS * HIST_W];
+    float root[T2_ENVS * 13];
+    float dof[T2_ENVS * 24];
+    float cf[T2_ENVS * QA_MAX_BODIES * 3];
+    float act[T2_ENVS * 12], lact[T2_ENVS * 12], tq[T2_ENVS * 12], ltq[T2_ENVS * 12], ldv[T2_ENVS * 12];
+    float msp[T2_ENVS * 12], msd[T2_ENVS * 12];
+    float cmd[T2_ENVS * 5], eps[T2_ENVS], lc[T2_ENVS * 5];
+    float mass[T2_ENVS * 4], fric[T2_ENVS];
+    float epsum[T2_ENVS * QA_EPSUM_PITCH];
+    long long ep[T2_ENVS];
+    uint8_t lcont[T2_ENVS * 4];
+    float key[T2_ENVS * 12], alast[T2_ENVS * 12];
+    float disc[T2_ENVS * QA_NUM_OBS_DISC];
+    float dv_out[T2_ENVS * 12];
+    float lrv[T2_ENVS * 6];
+    float rew[T2_ENVS], rooth[T2_ENVS];
+    float blv[T2_ENVS * 3], bav[T2_ENVS * 3], pg[T2_ENVS * 3], rpy[T2_ENVS * 3];
+    float ff[T2_ENVS * 4];
+    uint8_t cont_out[T2_ENVS * 4], cfilt_out[T2_ENVS * 4];
+    float scal[T2_ENVS][SC_N];
+    uint64_t bar;
+    int last;
+};
+
+// thread-level resampler (same arithmetic as resample_env)
+__device__ __forceinline__ void resample_thread(const QaBbcConst& c, const K2Draw& d, float* cmd, float* eps, float* lc) {
+    const int m = d.c_idx;
+    float n0 = (c.lin_vel_x[m][1] - c.lin_vel_x[m][0]) * d.cmd_u[0] + c.lin_vel_x[m][0];
+    float n1 = (c.lin_vel_y[m][1] - c.lin_vel_y[m][0]) * d.cmd_u[1] + c.lin_vel_y[m][0];
+    float n2 = (c.ang_vel_yaw[m][1] - c.ang_vel_yaw[m][0]) * d.cmd_u[2] + c.ang_vel_yaw[m][0];
+    const float jump = (m == QA_DIM_C - 1) ? 1.f : 0.f;
+    cmd[3] = (c.jump_h_span * d.cmd_u[3] + c.jump_h_lo) * jump;
+    cmd[4] = (c.loco_h_span * d.cmd_u[4] + c.loco_h_lo) * (1.f - jump);
+    n0 *= (fabsf(n0) > c.lin_vel_x_clip) ? 1.f : 0.f;
+    n1 *= (fabsf(n1) > c.lin_vel_y_clip) ? 1.f : 0.f;
+    n2 *= (fabsf(n2) > c.ang_vel_yaw_clip) ? 1.f : 0.f;
+    cmd[0] = n0;
+    cmd[1] = n1;
+    cmd[2] = n2;
+    eps[0] = (float)(d.eps_u * 2. - 1.);
+#pragma unroll
+    for (int k = 0; k < QA_DIM_C; ++k) lc[k] = (k == m) ? 1.f : 0.f;
+}
+
+__global__ void __launch_bounds__(T2_THREADS)
+k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_constant__ QaBbcStepArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    T2Smem& S = *reinterpret_cast<T2Smem*>(smem_raw);
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int e0 = blockIdx.x * T2_ENVS;
+    const int B = c.num_bodies;
+    const size_t nd = (size_t)a.num_envs * QA_NUM_DOF;
+
+    // ---------------- P0: stage every per-env array of this tile ------------------------------------------
+    if (tid == 0) {
+        mbar_init(&S.bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned n12 = T2_ENVS * 12 * 4;
+        const unsigned cf_bytes = (unsigned)(T2_ENVS * B * 3 * 4);
+        const unsigned total = T2_ENVS * HIST_W * 4 + T2_ENVS * 13 * 4 + T2_ENVS * 24 * 4 + cf_bytes + 7 * n12 +
+                               T2_ENVS * 5 * 4 * 2 + T2_ENVS * 4 + T2_ENVS * 4 * 4 + T2_ENVS * 4 +
+                               T2_ENVS * QA_EPSUM_PITCH * 4 + T2_ENVS * 8 + T2_ENVS * 4;
+        mbar_expect_tx(&S.bar, total);
+        bulk_load_tile(S.hist, a.obs_history_buf + (size_t)e0 * HIST_W, T2_ENVS * HIST_W * 4, &S.bar);
+        bulk_load_tile(S.root, a.root_states + (size_t)e0 * 13, T2_ENVS * 13 * 4, &S.bar);
+        bulk_load_tile(S.dof, a.dof_state + (size_t)e0 * 24, T2_ENVS * 24 * 4, &S.bar);
+        bulk_load_tile(S.cf, a.contact_forces + (size_t)e0 * B * 3, cf_bytes, &S.bar);
+        bulk_load_tile(S.act, a.actions + (size_t)e0 * 12, n12, &S.bar);
+        bulk_load_tile(S.lact, a.last_actions + (size_t)e0 * 12, n12, &S.bar);
+        bulk_load_tile(S.tq, a.torques_org + (size_t)e0 * 12, n12, &S.bar);
+        bulk_load_tile(S.ltq, a.last_torques_org + (size_t)e0 * 12, n12, &S.bar);
+        bulk_load_tile(S.ldv, a.last_dof_vel + (size_t)e0 * 12, n12, &S.bar);
+        bulk_load_tile(S.msp, a.motor_strength + (size_t)e0 * 12, n12, &S.bar);
+        bulk_load_tile(S.msd, a.motor_strength + nd + (size_t)e0 * 12, n12, &S.bar);
+        bulk_load_tile(S.cmd, a.commands + (size_t)e0 * 5, T2_ENVS * 5 * 4, &S.bar);
+        bulk_load_tile(S.lc, a.latent_c + (size_t)e0 * 5, T2_ENVS * 5 * 4, &S.bar);
+        bulk_load_tile(S.eps, a.latent_eps + e0, T2_ENVS * 4, &S.bar);
+        bulk_load_tile(S.mass, a.mass_params + (size_t)e0 * 4, T2_ENVS * 4 * 4, &S.bar);
+        bulk_load_tile(S.fric, a.friction_coeffs + e0, T2_ENVS * 4, &S.bar);
+        bulk_load_tile(S.epsum, a.episode_sums + (size_t)e0 * QA_EPSUM_PITCH, T2_ENVS * QA_EPSUM_PITCH * 4, &S.bar);
+        bulk_load_tile(S.ep, a.episode_length_buf + e0, T2_ENVS * 8, &S.bar);
+        bulk_load_tile(S.lcont, a.last_contacts + (size_t)e0 * 4, T2_ENVS * 4, &S.bar);
+    }
+    if (tid < T2_ENVS * 12) {                      // the two strided inputs, straight to shared memory
+        const int el = tid / 12, k = tid - el * 12;
+        const int j = k / 3, x = k - j * 3;
+        S.key[tid] = a.rigid_body_state[((size_t)(e0 + el) * B + c.feet_indices[j]) * 13 + x];
+        S.alast[tid] = a.action_history_buf[(size_t)(e0 + el) * QA_ACT_HIST_LEN * QA_NUM_DOF +
+                                            (QA_ACT_HIST_LEN - 1) * QA_NUM_DOF + k];
+    }
+    mbar_wait(&S.bar, 0);
+
+    // ---------------- P1: warp-per-env DOF sums and contact-force norms ------------------------------------
+    {
+        const int el = wid;
+        const bool dl = lane < QA_NUM_DOF;
+        const int d_ = dl ? lane : 0;
+        const float dof_pos = S.dof[el * 24 + 2 * d_], dof_vel = S.dof[el * 24 + 2 * d_ + 1];
+        const float act = S.act[el * 12 + d_], lact = S.lact[el * 12 + d_];
+        const float tq = S.tq[el * 12 + d_], ltq = S.ltq[el * 12 + d_], ldv = S.ldv[el * 12 + d_];
+        float v, s[9];
+        v = lact - act;
+        s[0] = warp_sum(dl ? v * v : 0.f);                                         // action_rate
+        v = tq - ltq;
+        s[1] = warp_sum(dl ? v * v : 0.f);                                         // delta_torques
+        v = (ldv - dof_vel) / c.dt;
+        s[2] = warp_sum(dl ? v * v : 0.f);                                         // dof_acc
+        const float dq0 = dof_pos - c.default_dof_pos[d_];
+        s[3] = warp_sum(dl ? dq0 * dq0 : 0.f);                                     // dof_error
+        v = -fminf(dof_pos - c.dof_pos_lower[d_], 0.f);
+        v = v + fmaxf(dof_pos - c.dof_pos_upper[d_], 0.f);
+        s[4] = warp_sum(dl ? v : 0.f);                                             // dof_pos_limits
+        v = clampf(fabsf(dof_vel) - c.dof_vel_limits[d_] * c.soft_dof_vel_limit, 0.f, 1.f);
+        s[5] = warp_sum(dl ? v : 0.f);                                             // dof_vel_limits
+        s[6] = warp_sum((dl && ((c.hip_dof_mask >> d_) & 1u)) ? dq0 * dq0 : 0.f);  // hip_pos
+        v = fmaxf(fabsf(tq) - c.torque_limits[d_] * c.soft_torque_limit, 0.f);
+        s[7] = warp_sum(dl ? v : 0.f);                                             // torque_limits
+        s[8] = warp_sum(dl ? tq * tq : 0.f);                                       // torques
+        float nrm = 0.f;
+        if (lane < B) {
+            const float* f = S.cf + (el * B + lane) * 3;
+            nrm = sqrtf(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]);
+        }
+        const unsigned hit_term = __ballot_sync(QA_FULL, nrm > 1.f) & c.termination_body_mask;
+        const unsigned hit_col = __ballot_sync(QA_FULL, nrm > 0.1f) & c.penalised_body_mask;
+        float ff[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ff[j] = __shfl_sync(QA_FULL, nrm, c.feet_indices[j]);
+        float out = 0.f;
+#pragma unroll
+        for (int k = 0; k < 9; ++k)
+            if (lane == k) out = s[k];
+        if (lane == SC_NCOL) out = (float)__popc(hit_col);
+        if (lane == SC_TERM) out = hit_term ? 1.f : 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (lane == SC_FF + j) out = ff[j];
+        if (lane < SC_RESET) S.scal[el][lane] = out;
+    }
+    __syncthreads();
+
+    // ---------------- P2: thread-per-env scalar program -------------------------------------------------------
+    bool any_state_write = a.do_push != 0;
+    if (tid < T2_ENVS) {
+        const int el = tid, e = e0 + el;
+        float* R = S.root + el * 13;
+        float* sc = S.scal[el];
+        float* cmd = S.cmd + el * 5;
+        const Quat q = {R[3], R[4], R[5], R[6]};
+        long long ep = S.ep[el] + 1;                                               // :133
+        float center_h = 0.f;
+        if (c.measure_heights) center_h = terrain_center_height(a.terrain, yaw_quat(q), R[0], R[1], c.center_px, c.center_py);
+        const Vec3 blv = quat_rotate_sgn(q, Vec3{R[7], R[8], R[9]}, -1.f);        // :138-140
+        const Vec3 bav = quat_rotate_sgn(q, Vec3{R[10], R[11], R[12]}, -1.f);
+        const Vec3 pg = quat_rotate_sgn(q, Vec3{0.f, 0.f, -1.f}, -1.f);
+        float roll, pitch, yaw;
+        {
+            const float t0 = 2.0f * (q.w * q.x + q.y * q.z);
+            const float t1 = 1.0f - 2.0f * (q.x * q.x + q.y * q.y);
+            roll = atan2f(t0, t1);
+            float t2 = 2.0f * (q.w * q.y - q.z * q.x);
+            t2 = clampf(t2, -1.f, 1.f);
+            pitch = asinf(t2);
+            const float t3 = 2.0f * (q.w * q.z + q.x * q.y);
+            const float t4 = 1.0f - 2.0f * (q.y * q.y + q.z * q.z);
+            yaw = atan2f(t3, t4);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {                                              // :143-146
+            const float f = sc[SC_FF + j];
+            const bool ct = f > 2.f;
+            S.ff[el * 4 + j] = f;
+            S.cont_out[el * 4 + j] = ct ? 1 : 0;
+            S.cfilt_out[el * 4 + j] = (ct || S.lcont[el * 4 + j] != 0) ? 1 : 0;
+        }
+        if (ep % (long long)c.resample_period == 0) {                              // :454-462
+            const K2Draw d = draw_site(c, a, e, SITE_RS0, a.rs_eps_u, a.rs_c_idx, a.rs_cmd_u);
+            resample_thread(c, d, cmd, S.eps + el, S.lc + el * 5);
+        }
+        if (a.do_push) {                                                           // :682-687
+            float u0, u1;
+            if (a.push_u != nullptr) {
+                u0 = a.push_u[e * 2 + 0];
+                u1 = a.push_u[e * 2 + 1];
+            } else {
+                Philox4 r = philox4x32_10((uint32_t)e, SITE_PUSH, (uint32_t)a.rng_step, (uint32_t)(a.rng_step >> 32),
+                                          (uint32_t)a.rng_seed, (uint32_t)(a.rng_seed >> 32));
+                u0 = u32_to_unit_f32(r.v[0]);
+                u1 = u32_to_unit_f32(r.v[1]);
+            }
+            const float span = c.max_push_vel_xy - (-c.max_push_vel_xy);
+            R[7] = span * u0 + (-c.max_push_vel_xy);
+            R[8] = span * u1 + (-c.max_push_vel_xy);
+        }
+        const float root_z_pre = R[2];
+        const bool time_out = ((float)ep > c.max_episode_length) || (root_z_pre < -6.0f);   // :168-176
+        const bool is_reset = (sc[SC_TERM] != 0.f) || time_out;
+        const float root_h_pre = root_z_pre - center_h;
+        float rt[QA_NUM_REWARDS];                                                  // :1248-1335, dir() order
+        rt[0] = sc[SC_SUM0 + 0];
+        rt[1] = sc[SC_NCOL];
+        rt[2] = sc[SC_SUM0 + 1];
+        rt[3] = sc[SC_SUM0 + 2];
+        rt[4] = sc[SC_SUM0 + 3];
+        rt[5] = sc[SC_SUM0 + 4];
+        rt[6] = sc[SC_SUM0 + 5];
+        rt[7] = sc[SC_SUM0 + 6];
+        {
+            const float err = sqrtf((cmd[3] - root_h_pre) * (cmd[3] - root_h_pre));
+            rt[8] = ((err < 0.05f) && (cmd[3] >= c.jump_height_lo)) ? c.jump_goal : 0.f;
+        }
+        {
+            const float err = sqrtf((cmd[4] - root_h_pre) * (cmd[4] - root_h_pre));
+            const float rl = expf(-10.0f * (err * err) / c.tracking_sigma);
+            rt[9] = (!(cmd[3] > c.jump_height_lo)) ? rl : 0.f;
+        }
+        rt[10] = sc[SC_SUM0 + 7];
+        rt[11] = sc[SC_SUM0 + 8];
+        {
+            const float dw = cmd[2] - bav.z;
+            rt[12] = expf(-(dw * dw) / c.tracking_sigma);
+            const float dx = cmd[0] - blv.x, dy = cmd[1] - blv.y;
+            rt[13] = expf(-(dx * dx + dy * dy) / c.tracking_sigma);
+        }
+        float rew = 0.f;
+        float* es = S.epsum + el * QA_EPSUM_PITCH;
+#pragma unroll
+        for (int k = 0; k < QA_NUM_REWARDS; ++k) {
+            const float t = rt[k] * c.reward_scale[k];
+            rew = rew + t;
+            es[k] = es[k] + t;
+        }
+        if (c.only_positive_rewards) rew = fmaxf(rew, 0.f);
+        int mode = 0;
+        if (is_reset) {                                                            // :178-240 (scalar half)
+            K2Workspace* ws = reinterpret_cast<K2Workspace*>(a.workspace);
+#pragma unroll
+            for (int k = 0; k < QA_NUM_REWARDS; ++k) {
+                atomicAdd(&ws->sums[k], (double)es[k]);
+                es[k] = 0.f;
+            }
+            atomicAdd(&ws->reset_count, 1u);
+            const K2Draw d = draw_site(c, a, e, SITE_RT0, a.rt_eps_u, a.rt_c_idx, a.rt_cmd_u);
+            resample_thread(c, d, cmd, S.eps + el, S.lc + el * 5);
+            mode = d.c_idx;
+            ep = 0;
+        }
+        S.ep[el] = ep;
+        S.rew[el] = rew;
+        S.rooth[el] = root_h_pre;
+        S.blv[el * 3 + 0] = blv.x, S.blv[el * 3 + 1] = blv.y, S.blv[el * 3 + 2] = blv.z;
+        S.bav[el * 3 + 0] = bav.x, S.bav[el * 3 + 1] = bav.y, S.bav[el * 3 + 2] = bav.z;
+        S.pg[el * 3 + 0] = pg.x, S.pg[el * 3 + 1] = pg.y, S.pg[el * 3 + 2] = pg.z;
+        S.rpy[el * 3 + 0] = roll, S.rpy[el * 3 + 1] = pitch, S.rpy[el * 3 + 2] = yaw;
+        sc[SC_RESET] = is_reset ? 1.f : 0.f;
+        sc[SC_CH] = center_h;
+        sc[SC_MODE] = __int_as_float(mode);
+        a.reset_buf[e] = is_reset ? 1 : 0;
+        a.time_out_buf[e] = time_out ? 1 : 0;
+        any_state_write = any_state_write || is_reset;
+    }
+    any_state_write = __syncthreads_or(any_state_write ? 1 : 0) != 0;
+
+    // ---------------- P3: warp-per-env reset write, row assembly ---------------------------------------------
+    {
+        const int el = wid, e = e0 + el;
+        float* sc = S.scal[el];
+        float* R = S.root + el * 13;
+        float* row = S.obs + el * ROW;
+        const bool is_reset = sc[SC_RESET] != 0.f;
+        const bool dl = lane < QA_NUM_DOF;
+        const int d_ = dl ? lane : 0;
+        float dof_pos = S.dof[el * 24 + 2 * d_], dof_vel = S.dof[el * 24 + 2 * d_ + 1];
+        float hla = S.alast[el * 12 + d_];
+        if (is_reset) {
+            int clip;
+            double time_u;
+            if (a.mocap_clip_idx != nullptr) {
+                clip = a.mocap_clip_idx[e];
+                time_u = a.mocap_time_u[e];
+            } else {
+                Philox4 r = philox4x32_10((uint32_t)e, SITE_MOCAP, (uint32_t)a.rng_step, (uint32_t)(a.rng_step >> 32),
+                                          (uint32_t)a.rng_seed, (uint32_t)(a.rng_seed >> 32));
+                const double cu = u64_to_unit_f64(r.v[0], r.v[1]);
+                time_u = u64_to_unit_f64(r.v[2], r.v[3]);
+                const int m = __float_as_int(sc[SC_MODE]);
+                const int lo = a.mocap.mode_offset[m], hi = a.mocap.mode_offset[m + 1];
+                int j = lo;
+                while (j < hi - 1 && a.mocap.mode_cdf[j] <= cu) ++j;
+                clip = a.mocap.mode_clips[j];
+            }
+            clip = min(max(clip, 0), a.mocap.num_clips - 1);
+            const MocapBlendIdx bi = mocap_blend_index(a.mocap, clip, time_u, c.time_between_frames, c.disc_obs_len);
+            const float* f0 = a.mocap.frames + (size_t)bi.row_lo * QA_MOCAP_W;
+            const float* f1 = a.mocap.frames + (size_t)bi.row_hi * QA_MOCAP_W;
+            const float bl = bi.blend;
+            const Quat qs = slerp_ref(Quat{f0[3], f0[4], f0[5], f0[6]}, Quat{f1[3], f1[4], f1[5], f1[6]}, bl);
+            if (dl) {
+                dof_pos = mocap_lerp(f0[7 + lane], f1[7 + lane], bl);
+                dof_vel = mocap_lerp(f0[37 + lane], f1[37 + lane], bl);
+                S.dof[el * 24 + 2 * lane] = dof_pos;
+                S.dof[el * 24 + 2 * lane + 1] = dof_vel;
+            }
+            const Vec3 lin = quat_rotate_sgn(
+                qs, Vec3{mocap_lerp(f0[31], f1[31], bl), mocap_lerp(f0[32], f1[32], bl), mocap_lerp(f0[33], f1[33], bl)}, 1.f);
+            const Vec3 ang = quat_rotate_sgn(
+                qs, Vec3{mocap_lerp(f0[34], f1[34], bl), mocap_lerp(f0[35], f1[35], bl), mocap_lerp(f0[36], f1[36], bl)}, 1.f);
+            __syncwarp();
+            if (lane == 0) {
+                R[0] = mocap_lerp(f0[0], f1[0], bl) + a.env_origins[e * 3 + 0];
+                R[1] = mocap_lerp(f0[1], f1[1], bl) + a.env_origins[e * 3 + 1];
+                R[2] = mocap_lerp(f0[2], f1[2], bl) + a.env_origins[e * 3 + 2];
+                R[3] = qs.x, R[4] = qs.y, R[5] = qs.z, R[6] = qs.w;
+                R[7] = lin.x, R[8] = lin.y, R[9] = lin.z;
+                R[10] = ang.x, R[11] = ang.y, R[12] = ang.z;
+            }
+            hla = 0.f;
+            float* gah = a.action_history_buf + (size_t)e * QA_ACT_HIST_LEN * QA_NUM_DOF;
+            for (int i = lane; i < QA_ACT_HIST_LEN * QA_NUM_DOF; i += 32) gah[i] = 0.f;
+            if (lane < 4) a.feet_air_time[e * 4 + lane] = 0.f;
+            __syncwarp();
+        }
+        // observations (:261-331) on post-reset root / dof, pre-reset base velocities / angles / contacts
+        const float root_h = R[2] - sc[SC_CH];
+        float* disc = S.disc + el * QA_NUM_OBS_DISC;
+        if (lane < 4) {                                                            // compute_flat_key_pos :1377-1396
+            const Quat hq = heading_quat_inv(Quat{R[3], R[4], R[5], R[6]});
+            const Vec3 local = {S.key[el * 12 + lane * 3 + 0] - R[0], S.key[el * 12 + lane * 3 + 1] - R[1],
+                                S.key[el * 12 + lane * 3 + 2] - R[2]};
+            const Vec3 o = quat_rotate_sgn(hq, local, 1.f);
+            disc[33 + lane * 3 + 0] = o.x * c.s_key_pos;
+            disc[33 + lane * 3 + 1] = o.y * c.s_key_pos;
+            disc[33 + lane * 3 + 2] = o.z * c.s_key_pos;
+            const float cf_ = S.cfilt_out[el * 4 + lane] ? 1.f : 0.f;
+            row[41 + lane] = cf_ - 0.5f;
+            row[61 + lane] = S.mass[el * 4 + lane];
+            disc[45 + lane] = cf_ * c.s_foot_contact;
+        }
+        if (dl) {
+            const float dq = (dof_pos - c.default_dof_pos[lane]) * c.s_dof_pos;
+            const float dv = dof_vel * c.s_dof_vel;
+            row[5 + lane] = dq;
+            row[17 + lane] = dv;
+            row[29 + lane] = hla;
+            row[45 + lane] = 0.f;
+            row[66 + lane] = S.msp[el * 12 + lane] - 1.f;
+            row[78 + lane] = S.msd[el * 12 + lane] - 1.f;
+            disc[9 + lane] = dq;
+            disc[21 + lane] = dv;
+            S.dv_out[el * 12 + lane] = dof_vel;
+        }
+        if (lane < 6) S.lrv[el * 6 + lane] = R[7 + lane];
+        if (lane >= 16 && lane < 19) {
+            const int k = lane - 16;
+            const float lv = S.blv[el * 3 + k], av = S.bav[el * 3 + k];
+            row[2 + k] = av * c.s_ang_vel;
+            row[58 + k] = lv * c.s_lin_vel;
+            disc[3 + k] = lv * c.s_lin_vel_dist;
+            disc[6 + k] = av * c.s_ang_vel_dist;
+        }
+        if (lane == 19) {
+            const float roll = S.rpy[el * 3 + 0], pitch = S.rpy[el * 3 + 1];
+            row[0] = roll;
+            row[1] = pitch;
+            row[57] = c.root_height_obs ? root_h : 0.f;
+            row[65] = S.fric[el];
+            disc[0] = roll;
+            disc[1] = pitch;
+            disc[2] = root_h;
+        }
+        if (lane >= 20 && lane < 31) {
+            const int k = lane - 20;
+            row[CMD_OFF + k] = k < 5 ? S.cmd[el * 5 + k] : (k == 5 ? S.eps[el] : S.lc[el * 5 + k - 6]);
+        }
+        __syncwarp();
+        // history (:302-312): staged through registers so that the in-place shift of the tile is hazard free
+        {
+            const bool fill = S.ep[el] <= 1;
+            float* h = S.hist + el * HIST_W;
+            float hv[(HIST_W + 31) / 32];
+#pragma unroll
+            for (int k = 0; k < (HIST_W + 31) / 32; ++k) {
+                const int i = k * 32 + lane;
+                float v = 0.f;
+                if (i < HIST_W) {
+                    if (fill) v = row[i % QA_NUM_PROP];
+                    else v = (i < HIST_W - QA_NUM_PROP) ? h[i + QA_NUM_PROP] : row[i - (HIST_W - QA_NUM_PROP)];
+                }
+                hv[k] = v;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < (HIST_W + 31) / 32; ++k) {
+                const int i = k * 32 + lane;
+                if (i < HIST_W) {
+                    row[HIST_OFF + i] = hv[k];
+                    h[i] = clampf(hv[k], -c.clip_obs, c.clip_obs);
+                }
+            }
+        }
+        __syncwarp();
+        // noise on the noisy lanes only (:318-319), then clip (:326-328)
+        for (int k = lane; k < c.num_noise; k += 32) {
+            const int i = c.noise_idx[k];
+            float u;
+            if (a.noise_u != nullptr) {
+                u = a.noise_u[(size_t)e * ROW + i];
+            } else {
+                Philox4 r = philox4x32_10((uint32_t)e, SITE_NOISE0 + (i >> 2), (uint32_t)a.rng_step,
+                                          (uint32_t)(a.rng_step >> 32), (uint32_t)a.rng_seed, (uint32_t)(a.rng_seed >> 32));
+                u = u32_to_unit_f32(r.v[i & 3]);
+            }
+            row[i] = row[i] + (2.f * u - 1.f) * c.noise_scale[k];
+        }
+        __syncwarp();
+        for (int i = lane; i < ROW; i += 32) row[i] = clampf(row[i], -c.clip_obs, c.clip_obs);
+        if (lane < 4) {
+            if (a.contact_buf)
+                a.contact_buf[((size_t)e * a.contact_ring_len + a.contact_ring_head) * 4 + lane] =
+                    S.cfilt_out[el * 4 + lane] ? 1.f : 0.f;
+            if (a.contact_force_buf)
+                a.contact_force_buf[((size_t)e * a.contact_ring_len + a.contact_ring_head) * 4 + lane] =
+                    clampf(S.ff[el * 4 + lane], -c.clip_obs, c.clip_obs);
+        }
+    }
+
+    // ---------------- P4: every output tile leaves through the TMA engine --------------------------------------
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned n12 = T2_ENVS * 12 * 4;
+        bulk_store_bytes(a.obs_buf + (size_t)e0 * ROW, S.obs, T2_ENVS * ROW * 4);
+        if (a.privileged_obs_buf != a.obs_buf) bulk_store_bytes(a.privileged_obs_buf + (size_t)e0 * ROW, S.obs, T2_ENVS * ROW * 4);
+        bulk_store_bytes(a.obs_history_buf + (size_t)e0 * HIST_W, S.hist, T2_ENVS * HIST_W * 4);
+        bulk_store_bytes(a.obs_disc_buf + (size_t)e0 * QA_NUM_OBS_DISC, S.disc, T2_ENVS * QA_NUM_OBS_DISC * 4);
+        bulk_store_bytes(a.last_actions + (size_t)e0 * 12, S.act, n12);                       // :158
+        bulk_store_bytes(a.last_dof_vel + (size_t)e0 * 12, S.dv_out, n12);                    // :159
+        bulk_store_bytes(a.last_root_vel + (size_t)e0 * 6, S.lrv, T2_ENVS * 6 * 4);           // :160
+        bulk_store_bytes(a.last_torques_org + (size_t)e0 * 12, S.tq, n12);                    // :161
+        bulk_store_bytes(a.episode_sums + (size_t)e0 * QA_EPSUM_PITCH, S.epsum, T2_ENVS * QA_EPSUM_PITCH * 4);
+        bulk_store_bytes(a.commands + (size_t)e0 * 5, S.cmd, T2_ENVS * 5 * 4);
+        bulk_store_bytes(a.latent_c + (size_t)e0 * 5, S.lc, T2_ENVS * 5 * 4);
+        bulk_store_bytes(a.latent_eps + e0, S.eps, T2_ENVS * 4);
+        bulk_store_bytes(a.episode_length_buf + e0, S.ep, T2_ENVS * 8);
+        bulk_store_bytes(a.last_contacts + (size_t)e0 * 4, S.cont_out, T2_ENVS * 4);
+        bulk_store_bytes(a.contact_filt + (size_t)e0 * 4, S.cfilt_out, T2_ENVS * 4);
+        bulk_store_bytes(a.feet_forces + (size_t)e0 * 4, S.ff, T2_ENVS * 4 * 4);
+        bulk_store_bytes(a.rew_buf + e0, S.rew, T2_ENVS * 4);
+        bulk_store_bytes(a.root_h + e0, S.rooth, T2_ENVS * 4);
+        bulk_store_bytes(a.base_lin_vel + (size_t)e0 * 3, S.blv, T2_ENVS * 3 * 4);
+        bulk_store_bytes(a.base_ang_vel + (size_t)e0 * 3, S.bav, T2_ENVS * 3 * 4);
+        bulk_store_bytes(a.projected_gravity + (size_t)e0 * 3, S.pg, T2_ENVS * 3 * 4);
+        bulk_store_bytes(a.rpy + (size_t)e0 * 3, S.rpy, T2_ENVS * 3 * 4);
+        if (any_state_write) {                          // simulator memory is only written on reset / push
+            bulk_store_bytes(a.root_states + (size_t)e0 * 13, S.root, T2_ENVS * 13 * 4);
+            bulk_store_bytes(a.dof_state + (size_t)e0 * 24, S.dof, T2_ENVS * 24 * 4);
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        // complete (not only read) before the ticket: the last CTA reads time_out_buf written by direct stores, but
+        // a following kernel must see these tiles, which stream order guarantees at kernel end
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+
+    // ---------------- epilogue: reset statistics, last CTA finalises (as in k_post_physics_bbc) ------------------
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        K2Workspace* ws = reinterpret_cast<K2Workspace*>(a.workspace);
+        const unsigned t = atomicAdd(&ws->ticket, 1u);
+        S.last = (t == gridDim.x - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (S.last) {
+        __threadfence();
+        K2Workspace* ws = reinterpret_cast<K2Workspace*>(a.workspace);
+        const unsigned cnt = *reinterpret_cast<volatile unsigned*>(&ws->reset_count);
+        if (cnt > 0) {
+            if (tid < QA_NUM_REWARDS) {
+                const double s = *reinterpret_cast<volatile double*>(&ws->sums[tid]);
+                const float mean = (float)(s / (double)cnt);
+                a.episode_rew_means[tid] = mean / c.episode_length_s;
+            }
+            const volatile uint8_t* src = a.time_out_buf;
+            for (int i = tid; i < a.num_envs; i += T2_THREADS) a.time_outs_latched[i] = src[i];
+        }
+        __syncthreads();
+        if (tid == 0) {
+            *a.num_resets = (int)cnt;
+            ws->reset_count = 0u;
+            ws->ticket = 0u;
+        }
+        if (tid < QA_NUM_REWARDS) ws->sums[tid] = 0.0;
+    }
+}
+
+static bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
+
+// Returns 1 if the tiled kernel was launched, 0 if the arguments do not qualify (caller falls back), <0 / >0 error.
+int qa_k2_try_launch_tiled(const QaBbcConst* c, const QaBbcStepArgs* a, cudaStream_t stream, int* launched) {
+    *launched = 0;
+    if (!(a->flags & QA_K2_TILED)) return 0;
+    if (a->num_envs % T2_ENVS != 0 || a->obs_pitch != QA_OBS_WIDTH || c->num_bodies > 32) return 0;
+    if (c->num_noise < 0 || c->num_noise > QA_MAX_NOISE_LANES) return QA_ERANGE;
+    const void* ptrs[] = {a->obs_buf, a->privileged_obs_buf, a->obs_history_buf, a->obs_disc_buf, a->root_states,
+                          a->dof_state, a->contact_forces, a->actions, a->last_actions, a->torques_org,
+                          a->last_torques_org, a->last_dof_vel, a->last_root_vel, a->motor_strength, a->commands,
+                          a->latent_c, a->latent_eps, a->mass_params, a->friction_coeffs, a->episode_sums,
+                          a->episode_length_buf, a->last_contacts, a->contact_filt, a->feet_forces, a->rew_buf,
+                          a->root_h, a->base_lin_vel, a->base_ang_vel, a->projected_gravity, a->rpy};
+    for (const void* p : ptrs)
+        if (!aligned16(p)) return 0;
+    if ((((size_t)a->num_envs * QA_NUM_DOF * 4) & 15u) != 0) return 0;       // second motor_strength plane
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_post_physics_bbc_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)sizeof(T2Smem));
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    k_post_physics_bbc_tiled<<<a->num_envs / T2_ENVS, T2_THREADS, sizeof(T2Smem), stream>>>(*c, *a);
+    *launched = 1;
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : (int)e;
+}

@@ -11,6 +11,8 @@ import os
 QA_ABI_VERSION = 1
 NUM_DOF, DIM_C, NUM_REWARDS = 12, 5, 14
 QA_K2_BULK_STORE = 1
+QA_K2_TILED = 2
+MAX_NOISE_LANES = 64
 
 f32p = C.POINTER(C.c_float)
 vp = C.c_void_p   # every device pointer travels as a plain address
@@ -69,6 +71,7 @@ class QaBbcConst(C.Structure):
         ("root_height_obs", C.c_int32), ("measure_heights", C.c_int32),
         ("center_px", C.c_float), ("center_py", C.c_float), ("max_push_vel_xy", C.c_float),
         ("time_between_frames", C.c_double), ("disc_obs_len", C.c_int32),
+        ("num_noise", C.c_int32), ("noise_idx", C.c_int32 * MAX_NOISE_LANES), ("noise_scale", C.c_float * MAX_NOISE_LANES),
     ]
 
 

@@ -80,7 +80,7 @@ class LeggedRobot:
 
     def __init__(self, cfg: BbcEnvConfig, physics: PhysicsBackend, static: Dict[str, torch.Tensor],
                  mocap: MocapTable, device="cuda:0", seed: int = 1, bulk_store: bool = True,
-                 keep_contact_rings: bool = True):
+                 keep_contact_rings: bool = True, tiled: bool = True):
         _abi.load()                                        # fail loudly if the CUDA library is missing
         self.cfg, self.physics, self.device = cfg, physics, torch.device(device)
         dev, N = self.device, cfg.num_envs
@@ -168,7 +168,8 @@ class LeggedRobot:
         self._measured_heights = z(N, cfg.num_height_points)
 
         self._const = ops.bbc_const(cfg, self.prior_parameters.tolist())
-        self._flags = _abi.QA_K2_BULK_STORE if (bulk_store and N % 4 == 0) else 0
+        # kernel variant request; the library falls back to the warp-per-env kernel when a tile constraint fails
+        self._flags = (_abi.QA_K2_BULK_STORE if (bulk_store and N % 4 == 0) else 0) | (_abi.QA_K2_TILED if tiled else 0)
         self._draws = None
         self.k2_events = None
         self._args = self._build_args()

@@ -240,6 +240,14 @@ def bbc_const(cfg: "K.BbcEnvConfig", prior_parameters=None) -> _abi.QaBbcConst:
     c.max_push_vel_xy = cfg.max_push_vel_xy
     c.time_between_frames = cfg.dt
     c.disc_obs_len = K.DISC_OBS_LEN
+    ns = cfg.noise_scale_vec() if cfg.add_noise else None
+    lanes = [] if ns is None else [i for i in range(K.OBS_WIDTH) if float(ns[i]) != 0.0]
+    if len(lanes) > _abi.MAX_NOISE_LANES:
+        raise RuntimeError(f"qa_b200: {len(lanes)} noisy observation lanes exceed QA_MAX_NOISE_LANES")
+    c.num_noise = len(lanes)
+    for k, i in enumerate(lanes):
+        c.noise_idx[k] = i
+        c.noise_scale[k] = float(ns[i])
     return c
 
 

@@ -33,7 +33,7 @@ class BbcIteration:
                    "process_env_step", "gae", "PPO update: 5 epochs x 4 minibatches (gather, fwd/bwd graph, clip+Adam)"]
 
     def __init__(self, cfg, static, snaps: List[Dict[str, torch.Tensor]], table, device, seed=1234, world_size=1,
-                 bulk_store=True, use_cuda_graph=True):
+                 bulk_store=True, use_cuda_graph=True, tiled=True):
         from .config import bbc_train_cfg
         from .rsl_rl.runner import OnPolicyRunner
         self.cfg, self.device, self.T = cfg, torch.device(device), len(snaps)
@@ -44,7 +44,7 @@ class BbcIteration:
         self.staging = {k: torch.empty_like(self.dev_snaps[0][k]) for k in SIM_KEYS}
         self.phys_resident = RecordedPhysics(self.dev_snaps)
         self.phys_staged = RecordedPhysics([self.staging])
-        self.env = LeggedRobot(cfg, self.phys_resident, static, table, device=dev, seed=seed, bulk_store=bulk_store)
+        self.env = LeggedRobot(cfg, self.phys_resident, static, table, device=dev, seed=seed, bulk_store=bulk_store, tiled=tiled)
         self.env.global_counter = 1
         torch.manual_seed(seed)
         train_cfg = bbc_train_cfg()
@@ -61,6 +61,7 @@ class BbcIteration:
         self._launch0 = ops.launches
         self._iters = 0
         self._k2_pairs = []
+        self._phase_events = []
 
     # ---- bookkeeping ---------------------------------------------------------------------------------
     def reset_counters(self):
@@ -68,6 +69,14 @@ class BbcIteration:
         self._iters = 0
         self.env.k2_events = None
         self._k2_pairs = []
+        self._phase_events = []
+
+    def phase_ms(self):
+        """(collection, learning) device milliseconds per iteration -- the reference's Perf/collection time and
+        Perf/learning_time split (on_policy_runner.py:208-228)."""
+        n = max(len(self._phase_events), 1)
+        return (sum(e[0].elapsed_time(e[1]) for e in self._phase_events) / n,
+                sum(e[1].elapsed_time(e[2]) for e in self._phase_events) / n)
 
     @property
     def launch_count(self):
@@ -88,10 +97,18 @@ class BbcIteration:
         env, runner = self.env, self.runner
         env.physics = self.phys_resident
         env.k2_events = [] if profile_k2 else None
+        if profile_k2:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            ev[0].record()
         with torch.no_grad():
             for _ in range(self.T):
                 self.obs, self.critic_obs = runner.rollout_step(self.obs, self.critic_obs)
+        if profile_k2:
+            ev[1].record()
         stats = self._learn()
+        if profile_k2:
+            ev[2].record()
+            self._phase_events.append(ev)
         if profile_k2:
             self._k2_pairs += env.k2_events
             env.k2_events = None

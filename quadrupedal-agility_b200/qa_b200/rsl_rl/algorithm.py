@@ -273,6 +273,7 @@ class SSInfoGAIL:
             for _ in range(3):
                 self._minibatch_step()
         torch.cuda.current_stream().wait_stream(s)
+        before = ops.launches
         if self.world_size == 1:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
@@ -283,6 +284,7 @@ class SSInfoGAIL:
             with torch.cuda.graph(g1):
                 self._forward_backward()
             self._graphs = (g1,)
+        self._graph_launches = ops.launches - before         # libqa_b200 kernels inside one replay
         # undo the warm-up / capture side effects on the trainable state
         for t, v in zip((self.ac_flat.data, self.est_flat.data, self.optim_ac.exp_avg, self.optim_ac.exp_avg_sq,
                          self.optim_estimator.exp_avg, self.optim_estimator.exp_avg_sq, self.optim_ac.lr,
@@ -315,6 +317,7 @@ class SSInfoGAIL:
                 self._gather(indices[i * mb_size:(i + 1) * mb_size])
                 if self.use_cuda_graph:
                     self._graphs[0].replay()
+                    ops._count(self._graph_launches)
                     if self.world_size > 1:
                         self._apply()
                 else:

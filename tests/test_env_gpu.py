@@ -28,11 +28,16 @@ STATE_KEYS = ["rew_buf", "obs_buf", "privileged_obs_buf", "obs_disc_buf", "obs_h
 EXACT_KEYS = ["reset_buf", "time_out_buf", "episode_length_buf", "contact_filt", "last_contacts"]
 
 
-def make_env(cfg, static, snap, draws, counter_before, bulk=True, table=None):
+VARIANTS = ["warp", "bulk", "tiled"]      # K2 kernel variants (warp stores / TMA row stores / 8-env TMA tiles)
+
+
+def make_env(cfg, static, snap, draws, counter_before, bulk="tiled", table=None):
     table = table or mocap_table()
     s = to_dev({k: v.clone() for k, v in snap.items()}, DEV)
     phys = RecordedPhysics([s])
-    env = LeggedRobot(cfg, phys, static, table, device=DEV, seed=7, bulk_store=bulk)
+    variant = {False: "warp", True: "bulk"}.get(bulk, bulk)
+    env = LeggedRobot(cfg, phys, static, table, device=DEV, seed=7, bulk_store=(variant != "warp"),
+                      tiled=(variant == "tiled"))
     env.load_state(s)
     env.common_step_counter = counter_before
     if draws is not None:
@@ -67,7 +72,7 @@ def check_against(env, want, n_reset_ids, terminal, label):
 
 
 @pytest.mark.parametrize("name", ["n64a", "n64b_push"])
-@pytest.mark.parametrize("bulk", [False, True])
+@pytest.mark.parametrize("bulk", VARIANTS)
 def test_post_physics_matches_reference_golden(name, bulk):
     cfg, static, snap, draws, ref, meta = load_env_golden(name)
     env = make_env(cfg, static, snap, draws, int(meta["counter_before"]), bulk=bulk)
@@ -120,7 +125,7 @@ def test_mocap_blend_matches_oracle():
     ops.mocap_blend(table.to(DEV), clip[:0].to(DEV), tu[:0].to(DEV), 0.02, 2, out[:0])      # empty input
 
 
-@pytest.mark.parametrize("bulk", [False, True])
+@pytest.mark.parametrize("bulk", VARIANTS)
 def test_post_physics_matches_oracle_at_4096(bulk):
     cfg = BbcEnvConfig(num_envs=4096)
     static = synthetic.make_static(cfg, seed=1234)
@@ -144,13 +149,14 @@ def test_bulk_store_variant_is_bit_identical():
     snap = synthetic.make_snapshot(cfg, seed=5, step=0)
     draws = synthetic.make_rng_draws(cfg, seed=5, step=0)
     outs = []
-    for bulk in (False, True):
+    for bulk in VARIANTS:
         env = make_env(cfg, static, snap, draws, 10, bulk=bulk)
         env.post_physics_step()
         torch.cuda.synchronize()
         outs.append((env.obs_buf.clone(), env.privileged_obs_buf.clone(), env.obs_history_buf.clone()))
-    for a, b in zip(*outs):
-        assert torch.equal(a, b)
+    for other in outs[1:]:
+        for a, b in zip(outs[0], other):
+            assert torch.equal(a, b)
 
 
 def test_ragged_env_counts():
@@ -187,12 +193,20 @@ def test_philox_mode_properties():
         return env
 
     e1, e2, e3 = run(3), run(3), run(4)
+    # the Philox stream is a function of (seed, step, env, site) only: every kernel variant draws the same numbers
+    for variant in ("warp", "bulk"):
+        ev = make_env(cfg, static, snap, None, 3, bulk=variant, table=table)
+        ev.post_physics_step()
+        torch.cuda.synchronize()
+        for k in ("obs_buf", "commands", "latent_eps", "latent_c", "root_states", "dof_state", "obs_history_buf"):
+            assert torch.equal(getattr(ev, k), getattr(e1, k)), (variant, k)
     assert torch.equal(e1.obs_buf, e2.obs_buf) and torch.equal(e1.commands, e2.commands)
     assert not torch.equal(e1.obs_buf, e3.obs_buf)
     for k in EXACT_KEYS:
         assert_close(k, getattr(e1, k), want[k])
-    assert_close("rew_buf", e1.rew_buf, want["rew_buf"])           # rewards use pre-reset state, no noise
     keep = ~(want["reset_buf"] | (want["episode_length_buf"] % cfg.resample_period == 0))
+    # rewards use the pre-reset state and no noise, but the commands of envs resampled in the callback differ
+    assert_close("rew_buf", e1.rew_buf.cpu()[keep], want["rew_buf"][keep])
     ns = static["noise_scale_vec"]
     quiet = (ns == 0)
     got, ref_obs = e1.obs_buf.cpu(), want["obs_buf"]

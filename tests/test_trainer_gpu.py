@@ -39,8 +39,8 @@ def build(w, n_envs=64):
     disc.load_state_dict(w["disc"])
     norm = Normalizer(98)
     norm.mean, norm.var = w["norm_mean"].numpy().copy(), w["norm_var"].numpy().copy()
-    alg = SSInfoGAIL(env, ac, disc, est, cfg["estimator"], None, norm, 2, 2, 49, 0.0, device=DEV,
-                     use_cuda_graph=False, disc_replay_buffer_size=1024, **cfg["algorithm"])
+    alg_cfg = dict(cfg["algorithm"], disc_replay_buffer_size=1024, use_cuda_graph=False)
+    alg = SSInfoGAIL(env, ac, disc, est, cfg["estimator"], None, norm, 2, 2, 49, 0.0, device=DEV, **alg_cfg)
     alg.init_storage(n_envs, 24, [671], [671], [12])
     return alg, env, norm
 
