@@ -274,6 +274,12 @@ typedef struct QaBbcStepArgs {
     uint8_t* time_outs_latched;         /* (N) extras["time_outs"]: refreshed only on steps with >=1 reset (:239-240) */
     int32_t* num_resets;                /* (1) */
     void* workspace;                    /* >= 128 bytes, zero-initialised once by the caller */
+    /* optional device-resident step counter (CUDA-graph replay): when non-NULL, step_state[0] is
+     * common_step_counter BEFORE this step; the kernel derives rng_step = counter + 1, do_push =
+     * (push_interval > 0 && (counter + 1) % push_interval == 0), contact_ring_head = counter % ring_len
+     * from it (the scalar fields above are ignored) and its last CTA stores counter + 1 back */
+    int64_t* step_state;
+    int32_t push_interval;              /* ceil(push_interval_s / dt) = 400, or 0 when push_robots is off */
 
     /* parity-mode random draws (dense, one per env).  ALL NULL => in-kernel Philox4x32-10 */
     const float* noise_u;               /* (N,671) */

@@ -28,6 +28,20 @@
 #define SITE_MOCAP 13
 #define SITE_NOISE0 16                  // + element/4
 
+// Step arguments with the per-step scalars resolved: either the host-supplied fields or, under CUDA-graph
+// replay, values derived from the device-resident step counter (see QaBbcStepArgs::step_state).
+struct K2Step : QaBbcStepArgs {
+    __device__ __forceinline__ explicit K2Step(const QaBbcStepArgs& in) : QaBbcStepArgs(in) {
+        if (in.step_state != nullptr) {
+            const long long before = *reinterpret_cast<const volatile long long*>(in.step_state);
+            const long long cnt = before + 1;
+            rng_step = (uint64_t)cnt;
+            do_push = (in.push_interval > 0 && (cnt % in.push_interval) == 0) ? 1 : 0;
+            contact_ring_head = in.contact_ring_len > 0 ? (int)(before % in.contact_ring_len) : 0;
+        }
+    }
+};
+
 struct K2Draw {
     double eps_u;
     int c_idx;

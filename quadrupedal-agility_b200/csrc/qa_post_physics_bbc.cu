@@ -29,7 +29,8 @@
 
 template <bool BULK>
 __global__ void __launch_bounds__(K2_THREADS)
-k_post_physics_bbc(const __grid_constant__ QaBbcConst c, const __grid_constant__ QaBbcStepArgs a) {
+k_post_physics_bbc(const __grid_constant__ QaBbcConst c, const __grid_constant__ QaBbcStepArgs a_in) {
+    const K2Step a(a_in);
     __shared__ __align__(16) float s_tile[K2_ENVS * ROW];          // obs rows of this CTA, contiguous
     __shared__ __align__(16) float s_stage[K2_ENVS][S_TOTAL];
     __shared__ float s_noise[ROW];
@@ -482,6 +483,7 @@ k_post_physics_bbc(const __grid_constant__ QaBbcConst c, const __grid_constant__
         __syncthreads();
         if (threadIdx.x == 0) {
             *a.num_resets = (int)cnt;
+            if (a.step_state != nullptr) a.step_state[0] = (long long)a.rng_step;
             ws->reset_count = 0u;
             ws->ticket = 0u;
         }

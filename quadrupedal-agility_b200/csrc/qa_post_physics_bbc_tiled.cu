@@ -83,7 +83,8 @@ __device__ __forceinline__ void resample_thread(const QaBbcConst& c, const K2Dra
 }
 
 __global__ void __launch_bounds__(T2_THREADS)
-k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_constant__ QaBbcStepArgs a) {
+k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_constant__ QaBbcStepArgs a_in) {
+    const K2Step a(a_in);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     T2Smem& S = *reinterpret_cast<T2Smem*>(smem_raw);
 
@@ -501,9 +502,8 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
             bulk_store_bytes(a.dof_state + (size_t)e0 * 24, S.dof, T2_ENVS * 24 * 4);
         }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        // complete (not only read) before the ticket: the last CTA reads time_out_buf written by direct stores, but
-        // a following kernel must see these tiles, which stream order guarantees at kernel end
-        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        // not waited for here: the last CTA only reads time_out_buf (direct stores above); the tiles become visible
+        // to the next kernel at kernel end.  The shared-memory source is released by the .read wait at the end.
     }
 
     // ---------------- epilogue: reset statistics, last CTA finalises (as in k_post_physics_bbc) ------------------
@@ -531,11 +531,13 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
         __syncthreads();
         if (tid == 0) {
             *a.num_resets = (int)cnt;
+            if (a.step_state != nullptr) a.step_state[0] = (long long)a.rng_step;
             ws->reset_count = 0u;
             ws->ticket = 0u;
         }
         if (tid < QA_NUM_REWARDS) ws->sums[tid] = 0.0;
     }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 static bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }

@@ -92,6 +92,7 @@ class QaBbcStepArgs(C.Structure):
         ("time_out_buf", vp), ("base_lin_vel", vp), ("base_ang_vel", vp), ("projected_gravity", vp), ("rpy", vp),
         ("feet_forces", vp), ("contact_filt", vp), ("root_h", vp),
         ("episode_rew_means", vp), ("time_outs_latched", vp), ("num_resets", vp), ("workspace", vp),
+        ("step_state", vp), ("push_interval", C.c_int32),
         ("noise_u", vp), ("rs_eps_u", vp), ("rs_c_idx", vp), ("rs_cmd_u", vp), ("rt_eps_u", vp),
         ("rt_c_idx", vp), ("rt_cmd_u", vp), ("push_u", vp), ("mocap_clip_idx", vp), ("mocap_time_u", vp),
     ]

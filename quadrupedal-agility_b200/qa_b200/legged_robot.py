@@ -171,6 +171,10 @@ class LeggedRobot:
         # kernel variant request; the library falls back to the warp-per-env kernel when a tile constraint fails
         self._flags = (_abi.QA_K2_BULK_STORE if (bulk_store and N % 4 == 0) else 0) | (_abi.QA_K2_TILED if tiled else 0)
         self._draws = None
+        # device-resident step counter: lets a captured CUDA graph of post_physics_step be replayed (the Philox
+        # counter, the push schedule and the contact-ring head advance on the device)
+        self._step_state = torch.zeros(2, device=dev, dtype=torch.int64)
+        self.device_step_counter = False
         self.k2_events = None
         self._args = self._build_args()
 
@@ -267,6 +271,7 @@ class LeggedRobot:
         a.time_outs_latched = self._time_outs_latched.data_ptr()
         a.num_resets = p(self._num_resets, i32)
         a.workspace = p(self._workspace, f64)
+        a.push_interval = int(cfg.push_interval) if cfg.push_robots else 0
         return a
 
     def set_parity_draws(self, draws: Optional[Dict[str, torch.Tensor]]) -> None:
@@ -302,6 +307,20 @@ class LeggedRobot:
             self._episode_sums[:, :K.NUM_REWARDS].copy_(snap["episode_sums"].to(dev).t())
         if "obs_disc_buf" in snap:
             self.obs_disc_buf.copy_(snap["obs_disc_buf"].to(dev))
+
+    def use_device_step_counter(self, on: bool = True) -> None:
+        """Switch the per-step scalars (Philox counter, push flag, ring head) to the device-resident counter, synced
+        from the host's `common_step_counter`.  Required before capturing `post_physics_step` in a CUDA graph; the
+        host counters keep advancing in Python but are only authoritative again after `sync_step_counter()`."""
+        self.device_step_counter = on
+        if on:
+            self._step_state[0] = self.common_step_counter
+
+    def sync_step_counter(self) -> None:
+        """Host counters := device counter (one 8-byte D2H)."""
+        self.common_step_counter = int(self._step_state[0].item())
+        if self._ring_len:
+            self._ring_head = (self.common_step_counter - 1) % self._ring_len
 
     def set_prior_parameters(self, prior: torch.Tensor) -> None:
         """The trainer updates `env.prior_parameters` (gail.py:463-464); refresh the in-kernel CDF."""
@@ -347,6 +366,7 @@ class LeggedRobot:
         a.do_push = int(do_push)
         a.contact_ring_head = max(self._ring_head, 0)
         a.rng_step = self.common_step_counter
+        a.step_state = self._step_state.data_ptr() if self.device_step_counter else None
         a.root_states, a.dof_state = ph.root_states.data_ptr(), ph.dof_state.data_ptr()
         a.rigid_body_state, a.contact_forces = ph.rigid_body_state.data_ptr(), ph.contact_forces.data_ptr()
         a.obs_buf, a.privileged_obs_buf = self.obs_buf.data_ptr(), self.privileged_obs_buf.data_ptr()
@@ -364,6 +384,20 @@ class LeggedRobot:
         ph.set_states_indexed(self._reset_ids_i32, self._reset_count)
         if do_push:
             ph.set_root_states_all()
+
+    def _k2_only_step(self) -> None:
+        """The fused post-physics launch alone (bench roofline leg)."""
+        ph, a = self.physics, self._args
+        ph.refresh()
+        self._pp ^= 1
+        self.obs_buf, self.privileged_obs_buf = self._obs[self._pp], self._priv[self._pp]
+        self.obs_disc_buf = self._disc[self._pp]
+        a.step_state = self._step_state.data_ptr() if self.device_step_counter else None
+        a.root_states, a.dof_state = ph.root_states.data_ptr(), ph.dof_state.data_ptr()
+        a.rigid_body_state, a.contact_forces = ph.rigid_body_state.data_ptr(), ph.contact_forces.data_ptr()
+        a.obs_buf, a.privileged_obs_buf = self.obs_buf.data_ptr(), self.privileged_obs_buf.data_ptr()
+        a.obs_disc_buf = self.obs_disc_buf.data_ptr()
+        ops.post_physics_bbc(self._const, a)
 
     def step_device(self, actions: torch.Tensor):
         """Sync-free step.  Returns (obs, priv_obs, rew, reset, reset_ids_padded, count, terminal_padded);

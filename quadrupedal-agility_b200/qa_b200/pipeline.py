@@ -62,6 +62,8 @@ class BbcIteration:
         self._iters = 0
         self._k2_pairs = []
         self._phase_events = []
+        self.graph_rollout = use_cuda_graph
+        self._rollout_graphs = {}
 
     # ---- bookkeeping ---------------------------------------------------------------------------------
     def reset_counters(self):
@@ -93,36 +95,110 @@ class BbcIteration:
             alg.compute_returns(self.critic_obs)
         return alg.update()
 
-    def run_resident(self, profile_k2=False):
+    # ---- CUDA-graph rollouts ---------------------------------------------------------------------------------
+    def _rollout_eager(self, host: bool):
         env, runner = self.env, self.runner
-        env.physics = self.phys_resident
-        env.k2_events = [] if profile_k2 else None
-        if profile_k2:
+        env.physics = self.phys_staged if host else self.phys_resident
+        with torch.no_grad():
+            for t in range(self.T):
+                if host:
+                    for k in SIM_KEYS:                           # the physics backend's hand-over: pinned host -> HBM
+                        self.staging[k].copy_(self.host_snaps[t][k], non_blocking=True)
+                self.obs, self.critic_obs = runner.rollout_step(self.obs, self.critic_obs)
+
+    def _capture_rollout(self, host: bool):
+        """Captures the whole T-step rollout (every torch op and libqa_b200 launch of `rollout_step`, and in host
+        mode the T x 4 pinned-host -> HBM copies) as ONE CUDA graph.  Python-side state that the steps advance
+        (ping-pong parity, snapshot cursor, storage.step) is periodic in T; what is not periodic -- the step counter
+        that drives Philox, the push schedule and the contact rings -- lives on the device (K2 step_state)."""
+        env, runner, alg = self.env, self.runner, self.runner.alg
+        assert self.T % 2 == 0
+        env.use_device_step_counter(True)
+        if alg._disc_stage is None:
+            alg.stage_disc_inserts(True)
+        hist0 = runner._disc_hist.clone()
+        runner._disc_hist = hist0
+        obs0, crit0 = self.obs, self.critic_obs
+        alg.storage.clear()
+        self.phys_resident.cursor = -1
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):                               # warm-up on a side stream (allocator, cuBLAS handles)
+            self._rollout_eager(host)
+            alg.storage.clear()
+            runner._disc_hist = hist0.copy_(runner._disc_hist)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        before = ops.launches
+        g = torch.cuda.CUDAGraph()
+        self.obs, self.critic_obs = obs0, crit0
+        with torch.cuda.graph(g):
+            self._rollout_eager(host)
+            hist0.copy_(runner._disc_hist)
+        runner._disc_hist = hist0
+        assert self.obs.data_ptr() == obs0.data_ptr()
+        alg.storage.clear()
+        return g, ops.launches - before
+
+    def _rollout(self, host: bool):
+        if not self.graph_rollout:
+            self._rollout_eager(host)
+            return
+        key = "host" if host else "resident"
+        if key not in self._rollout_graphs:
+            self._rollout_graphs[key] = self._capture_rollout(host)
+        g, n = self._rollout_graphs[key]
+        g.replay()
+        ops._count(n)
+        self.runner.alg.flush_disc_stage()
+
+    def run_resident(self, profile_phases=False):
+        if profile_phases:
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
             ev[0].record()
-        with torch.no_grad():
-            for _ in range(self.T):
-                self.obs, self.critic_obs = runner.rollout_step(self.obs, self.critic_obs)
-        if profile_k2:
+        self._rollout(host=False)
+        if profile_phases:
             ev[1].record()
         stats = self._learn()
-        if profile_k2:
+        if profile_phases:
             ev[2].record()
             self._phase_events.append(ev)
-        if profile_k2:
-            self._k2_pairs += env.k2_events
-            env.k2_events = None
         self._iters += 1
         return stats
 
+    def time_k2_only(self, reps=20):
+        """Roofline leg: the T fused post-physics launches of one rollout (T different state snapshots), alone in a
+        CUDA graph, timed with CUDA events around each replay.  Returns (total ms, launches)."""
+        env = self.env
+        env.physics = self.phys_resident
+        env.use_device_step_counter(True)
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            env.post_physics_step()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.phys_resident.cursor = -1
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(self.T):
+                env._k2_only_step()
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        total = 0.0
+        for _ in range(reps):
+            flush.fill_(1)
+            e0.record()
+            g.replay()
+            e1.record()
+            e1.synchronize()
+            total += e0.elapsed_time(e1)
+        return total, reps * self.T
+
     def run_host(self):
-        env, runner = self.env, self.runner
-        env.physics = self.phys_staged
+        runner = self.runner
+        self._rollout(host=True)
         with torch.no_grad():
-            for t in range(self.T):
-                for k in SIM_KEYS:                               # the physics backend's hand-over: pinned host -> HBM
-                    self.staging[k].copy_(self.host_snaps[t][k], non_blocking=True)
-                self.obs, self.critic_obs = runner.rollout_step(self.obs, self.critic_obs)
             mean_rew = runner.alg.storage.rewards.mean()
         stats = self._learn()                                    # reads the loss statistics back (one D2H)
         self.result_host[0:1].copy_(mean_rew.reshape(1), non_blocking=True)

@@ -127,6 +127,23 @@ class SSInfoGAIL:
         self._priv_reg_coef = torch.zeros((), device=device)
         self._stats = torch.zeros(len(STAT_NAMES), device=device)
         self.last_stats = {}
+        self._disc_stage = None
+
+    def stage_disc_inserts(self, on: bool = True):
+        """Replay-buffer inserts of a rollout go to a (T,N,.) staging area at fixed addresses (so that the rollout can
+        be a replayed CUDA graph) and are appended to the ring by `flush_disc_stage()` after the rollout."""
+        if not on:
+            self._disc_stage = None
+            return
+        st, ds = self.storage, self.disc_storage
+        T, N = st.num_transitions_per_env, st.num_envs
+        z = lambda w: torch.zeros(T, N, w, device=self.device)                  # noqa: E731
+        self._disc_stage = (z(ds.states.shape[1]), z(1), z(ds.latent_c.shape[1]))
+
+    def flush_disc_stage(self):
+        if self._disc_stage is not None:
+            s, e, c = self._disc_stage
+            self.disc_storage.insert(s.flatten(0, 1), e.flatten(0, 1), c.flatten(0, 1))
 
     # ---- reference API --------------------------------------------------------------------------------
     @property
@@ -170,8 +187,14 @@ class SSInfoGAIL:
         if 'time_outs' in infos:
             tr.rewards += self.gamma * torch.squeeze(tr.values * infos['time_outs'].unsqueeze(1).to(self.device), 1)
         if obs_disc_history_buf is not None:
-            self.disc_storage.insert(obs_disc_history_buf.view(obs_disc_history_buf.shape[0], -1), self.env.latent_eps,
-                                     self.env.latent_c)
+            flat_hist = obs_disc_history_buf.reshape(obs_disc_history_buf.shape[0], -1)
+            if self._disc_stage is not None:          # CUDA-graph rollouts: fixed-address staging, flushed per iteration
+                t = self.storage.step
+                self._disc_stage[0][t].copy_(flat_hist)
+                self._disc_stage[1][t].copy_(self.env.latent_eps)
+                self._disc_stage[2][t].copy_(self.env.latent_c)
+            else:
+                self.disc_storage.insert(flat_hist, self.env.latent_eps, self.env.latent_c)
         self.storage.add_transitions(tr)
         self.actor_critic.reset(dones)
 
