@@ -115,6 +115,8 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device(f"cuda:{local_rank}")
     from qa_b200.pipeline import BbcIteration
+    from qa_b200.rsl_rl import linear
+    linear.set_mode("tc" if args.linear == "tc" else "fp32")
     cfg, static, snaps, table = build_workload(rank, dev)
     it = BbcIteration(cfg, static, snaps, table, device=dev, seed=1234 + rank, world_size=world,
                       bulk_store=bool(args.k2_bulk), tiled=(args.k2_bulk == 2))
@@ -272,6 +274,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--linear", default="tc", choices=["tc", "cublas"],
+                    help="dense layers: tc = hand-written tcgen05 TF32 forward (default), cublas = library TF32 GEMMs")
     ap.add_argument("--k2-bulk", type=int, default=2,
                     help="K2 variant: 2 = 8-env TMA tiles (default), 1 = warp-per-env + TMA row stores, 0 = warp stores")
     args = ap.parse_args()

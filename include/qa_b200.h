@@ -51,7 +51,7 @@ int qa_version(void);
 /* human readable build string ("sm_100a, nvcc 12.9, ...") */
 const char* qa_build_info(void);
 /* sizeof() of argument struct number `which` (order of declaration in this header, QaActionPushArgs
- * = 0 ... QaGaeArgs = 9, QaGatherArgs = 10, QaClipAdamArgs = 11; -1 if unknown): a layout handshake for FFI mirrors of these structs */
+ * = 0 ... QaGaeArgs = 9, QaGatherArgs = 10, QaClipAdamArgs = 11, QaLinearArgs = 12; -1 if unknown): a layout handshake for FFI mirrors of these structs */
 int qa_struct_size(int which);
 
 /* ------------------------------------------------------------------------------------------
@@ -364,6 +364,25 @@ typedef struct QaClipAdamArgs {
     double* workspace;                  /* >= 16 bytes */
 } QaClipAdamArgs;
 int qa_clip_adam(const QaClipAdamArgs* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K7  Y = act(X W^T + b) on the tcgen05 tensor cores (TF32 operands, fp32 accumulate in TMEM) -- replaces every
+ *     nn.Linear (+ the ELU / ReLU that follows it) of ActorCritic, Estimator and Discriminator:
+ *     bbc/rsl_rl/modules/actor_critic.py:96-129, modules/estimator.py:24-33, algorithms/discriminator.py:36-46.
+ *     x and w are read by TMA: bases 16 B aligned, pitches multiples of 4 floats; M, N, K are arbitrary.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct QaLinearArgs {
+    int32_t M, N, K;
+    int32_t act;                        /* 0 none, 1 ELU(alpha=1), 2 ReLU */
+    const float* x;                     /* (M,K) row-major */
+    int64_t x_pitch;                    /* floats between rows of x */
+    const float* w;                     /* (N,K) row-major: PyTorch Linear.weight */
+    int64_t w_pitch;
+    const float* bias;                  /* (N) or NULL */
+    float* y;                           /* (M,N) */
+    int64_t y_pitch;
+} QaLinearArgs;
+int qa_linear_fwd(const QaLinearArgs* a, void* stream);
 
 #ifdef __cplusplus
 }

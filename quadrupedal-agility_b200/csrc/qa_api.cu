@@ -27,6 +27,7 @@ extern "C" int qa_struct_size(int which) {
         case 9: return (int)sizeof(QaGaeArgs);
         case 10: return (int)sizeof(QaGatherArgs);
         case 11: return (int)sizeof(QaClipAdamArgs);
+        case 12: return (int)sizeof(QaLinearArgs);
         default: return -1;
     }
 }

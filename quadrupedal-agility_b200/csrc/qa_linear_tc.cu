@@ -1,0 +1,291 @@
+// K7: Y = act(X W^T + b) on the 5th-generation tensor cores (tcgen05, sm_100a).
+//
+// The one dense-contraction site of the hot path: every nn.Linear of ActorCritic / Estimator / Discriminator
+// (bbc/rsl_rl/modules/actor_critic.py:96-129, modules/estimator.py:24-33, algorithms/discriminator.py:36-46, 64-69),
+// with the bias add and the ELU / ReLU that follow each of them in the reference fused into the epilogue.
+//
+// Operands stay fp32 in HBM and are consumed as TF32 (kind::tf32: fp32 bit patterns, 10-bit mantissa used, fp32
+// accumulate in TMEM) -- no conversion pass.  X is (M,K) row-major and W is (N,K) row-major (PyTorch's Linear layout),
+// i.e. both are K-major UMMA operands.
+//
+// One CTA computes a 128 x BN tile of Y:
+//   warp 0      TMA producer: cp.async.bulk.tensor 2-D loads of the 128x32 (A) and BNx32 (B) fp32 boxes, 128-byte
+//               swizzle, into a STAGES-deep shared-memory ring; full/empty mbarriers.  Out-of-bounds rows / K columns
+//               are zero-filled by TMA, so M, N, K need no padding (only 16-byte row pitches).
+//   warp 1      allocates TMEM (BN fp32 columns) and issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=BN, K=8) from
+//               one elected lane, 4 MMAs per 32-float K block; tcgen05.commit releases ring slots and finally signals
+//               the epilogue.
+//   warps 2..5  epilogue: tcgen05.ld 32x32b (lane = output row) -> bias + activation in registers -> 16-byte global
+//               stores of the row segment.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "qa_b200.h"
+#include "qa_common.cuh"
+#include "qa_k2_common.cuh"   // mbarrier helpers
+
+#define TC_BM 128
+#define TC_BK 32              // floats per K block = 128 bytes = one swizzle span
+#define TC_STAGES 4
+#define TC_THREADS 192
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) { mbar_expect_tx(bar, bytes); }
+
+__device__ __forceinline__ void tma_load_2d(void* sdst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            (unsigned)__cvta_generic_to_shared(sdst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"((unsigned)__cvta_generic_to_shared(bar))
+        : "memory");
+}
+
+// UMMA shared-memory descriptor, K-major operand, 128-byte swizzle: rows at 128 B pitch, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(const void* smem) {
+    const uint32_t addr = (uint32_t)__cvta_generic_to_shared(smem);
+    uint64_t d = 0;
+    d |= (uint64_t)((addr & 0x3FFFF) >> 4);          // start address, bits [0,14)
+    d |= (uint64_t)0 << 16;                          // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset: 8 rows x 128 B, bits [32,46)
+    d |= (uint64_t)1 << 46;                          // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                          // layout type SWIZZLE_128B
+    return d;
+}
+
+// instruction descriptor: D = f32, A = B = tf32, both K-major, M = 128, N = BN
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32"
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, "
+        "%24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32"
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+
+template <int BN>
+struct TcSmem {
+    float a[TC_STAGES][TC_BM * TC_BK];      // 16 KB per stage, 1024 B aligned
+    float b[TC_STAGES][BN * TC_BK];
+    uint64_t full[TC_STAGES];
+    uint64_t empty[TC_STAGES];
+    uint64_t tmem_full;
+    uint32_t tmem_base;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_linear_tf32(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+              const __grid_constant__ QaLinearArgs g) {
+    extern __shared__ unsigned char smem_raw[];
+    // 1024 B alignment for the 128 B swizzle atoms
+    TcSmem<BN>& S = *reinterpret_cast<TcSmem<BN>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * BN;
+    const int num_kb = (g.K + TC_BK - 1) / TC_BK;
+    constexpr unsigned TMEM_COLS = BN < 32 ? 32 : BN;
+    constexpr unsigned STAGE_BYTES = (TC_BM + BN) * TC_BK * 4;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) {
+            mbar_init(&S.full[s], 1);
+            mbar_init(&S.empty[s], 1);
+        }
+        mbar_init(&S.tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {                       // TMEM allocation is a warp-wide instruction
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         (unsigned)__cvta_generic_to_shared(&S.tmem_base)),
+                     "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = S.tmem_base;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % TC_STAGES;
+                const unsigned ph = (kb / TC_STAGES) & 1;
+                mbar_wait(&S.empty[s], ph ^ 1);                      // slot free (passes immediately the first time)
+                mbar_arrive_expect_tx(&S.full[s], STAGE_BYTES);
+                tma_load_2d(S.a[s], &map_x, kb * TC_BK, m0, &S.full[s]);
+                tma_load_2d(S.b[s], &map_w, kb * TC_BK, n0, &S.full[s]);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_tf32(BN);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % TC_STAGES;
+                const unsigned ph = (kb / TC_STAGES) & 1;
+                mbar_wait(&S.full[s], ph);                           // TMA bytes have landed
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint64_t adesc = umma_desc_kmajor_sw128(S.a[s]);
+                const uint64_t bdesc = umma_desc_kmajor_sw128(S.b[s]);
+#pragma unroll
+                for (int k = 0; k < TC_BK / 8; ++k)                  // UMMA_K = 8 tf32 = 32 bytes -> +2 in the address field
+                    umma_tf32(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                umma_commit(&S.empty[s]);                            // frees the slot when these MMAs retire
+            }
+            umma_commit(&S.tmem_full);                               // accumulator complete
+        }
+    } else {
+        // ===== epilogue: warps 2..5 own TMEM lane quadrants (warp % 4) =====
+        const int q = warp & 3;
+        const int row = m0 + q * 32 + lane;
+        mbar_wait(&S.tmem_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const bool vec_ok = ((g.y_pitch & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.y) & 15u) == 0);
+        constexpr int CH = BN >= 32 ? 32 : 16;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += CH) {
+            uint32_t r[32];
+            const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+            if (CH == 32) tmem_ld32(taddr, r);
+            else tmem_ld16(taddr, r);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (row < g.M) {
+                float* yrow = g.y + (size_t)row * g.y_pitch;
+#pragma unroll
+                for (int j = 0; j < CH; j += 4) {
+                    const int col = n0 + c0 + j;
+                    float v[4];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        float x = __uint_as_float(r[j + t]);
+                        const int cc = col + t;
+                        if (g.bias != nullptr && cc < g.N) x += __ldg(g.bias + cc);
+                        if (g.act == 1) x = x > 0.f ? x : expm1f(x);            // ELU(alpha = 1)
+                        else if (g.act == 2) x = fmaxf(x, 0.f);                 // ReLU
+                        v[t] = x;
+                    }
+                    if (vec_ok && col + 3 < g.N) {
+                        *reinterpret_cast<float4*>(yrow + col) = make_float4(v[0], v[1], v[2], v[3]);
+                    } else {
+#pragma unroll
+                        for (int t = 0; t < 4; ++t)
+                            if (col + t < g.N) yrow[col + t] = v[t];
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---- host side -------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+
+// 2-D fp32 tensor (rows, cols) with `pitch` floats per row; box = (box_rows, 32 floats), 128 B swizzle, zero OOB fill
+static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t pitch, int box_rows) {
+    PFN_encodeTiled enc = get_encode();
+    if (enc == nullptr) return QA_EINVAL;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)pitch * 4};
+    cuuint32_t box[2] = {TC_BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : QA_EINVAL;
+}
+
+template <int BN>
+static int launch_linear(const QaLinearArgs* g, cudaStream_t stream) {
+    CUtensorMap mx, mw;
+    int rc = make_map(&mx, g->x, g->M, g->K, g->x_pitch, TC_BM);
+    if (rc) return rc;
+    rc = make_map(&mw, g->w, g->N, g->K, g->w_pitch, BN);
+    if (rc) return rc;
+    const size_t smem = sizeof(TcSmem<BN>) + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_linear_tf32<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    dim3 grid((g->M + TC_BM - 1) / TC_BM, (g->N + BN - 1) / BN);
+    k_linear_tf32<BN><<<grid, TC_THREADS, smem, stream>>>(mx, mw, *g);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : (int)e;
+}
+
+extern "C" int qa_linear_fwd(const QaLinearArgs* g, void* stream) {
+    QA_CHECK_PTR(g);
+    if (g->M == 0) return 0;
+    QA_CHECK_PTR(g->x);
+    QA_CHECK_PTR(g->w);
+    QA_CHECK_PTR(g->y);
+    if (g->M < 0 || g->N <= 0 || g->K <= 0) return QA_EINVAL;
+    if (g->act < 0 || g->act > 2) return QA_EINVAL;
+    // TMA constraints: 16 B aligned bases and row pitches
+    if ((g->x_pitch & 3) || (g->w_pitch & 3) || (reinterpret_cast<uintptr_t>(g->x) & 15u) ||
+        (reinterpret_cast<uintptr_t>(g->w) & 15u) || g->x_pitch < g->K || g->w_pitch < g->K || g->y_pitch < g->N)
+        return QA_EINVAL;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int n = g->N;
+    if (n <= 16) return launch_linear<16>(g, s);
+    if (n <= 32) return launch_linear<32>(g, s);
+    if (n <= 64) return launch_linear<64>(g, s);
+    if (n <= 128 || g->M < 8192) return launch_linear<128>(g, s);
+    return launch_linear<256>(g, s);
+}

@@ -123,6 +123,12 @@ class QaClipAdamArgs(C.Structure):
                 ("max_grad_norm", C.c_float), ("grad_scale", C.c_float), ("grad_norm_out", vp), ("workspace", vp)]
 
 
+class QaLinearArgs(C.Structure):
+    _fields_ = [("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("act", C.c_int32), ("x", vp),
+                ("x_pitch", C.c_int64), ("w", vp), ("w_pitch", C.c_int64), ("bias", vp), ("y", vp),
+                ("y_pitch", C.c_int64)]
+
+
 # every symbol `include/qa_b200.h` declares: name -> (restype, argtypes)
 SYMBOLS = {
     "qa_version": (C.c_int, []),
@@ -137,10 +143,11 @@ SYMBOLS = {
     "qa_gae": (C.c_int, [C.POINTER(QaGaeArgs), vp]),
     "qa_gather_minibatch": (C.c_int, [C.POINTER(QaGatherArgs), vp]),
     "qa_clip_adam": (C.c_int, [C.POINTER(QaClipAdamArgs), vp]),
+    "qa_linear_fwd": (C.c_int, [C.POINTER(QaLinearArgs), vp]),
 }
 
 STRUCT_ORDER = [QaActionPushArgs, QaTorqueArgs, QaTerrain, QaHeightScanArgs, QaMocapTable, QaMocapBlendArgs,
-                QaBbcConst, QaBbcStepArgs, QaCompactArgs, QaGaeArgs, QaGatherArgs, QaClipAdamArgs]
+                QaBbcConst, QaBbcStepArgs, QaCompactArgs, QaGaeArgs, QaGatherArgs, QaClipAdamArgs, QaLinearArgs]
 
 _LIB = None
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libqa_b200.so")

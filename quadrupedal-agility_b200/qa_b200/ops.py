@@ -176,6 +176,30 @@ def clip_adam(params, grads, exp_avg, exp_avg_sq, lr, step, workspace, beta1=0.9
     _count(2)
 
 
+# ---- K7 ---------------------------------------------------------------------------------------
+ACT_ID = {None: 0, "none": 0, "elu": 1, "relu": 2}
+
+
+def linear_tc_ok(x, weight) -> bool:
+    """TMA constraints of qa_linear_fwd: fp32 CUDA, unit inner stride, 16 B aligned bases and row pitches."""
+    return (x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32 and x.dim() == 2 and
+            x.stride(1) == 1 and weight.stride(1) == 1 and x.stride(0) % 4 == 0 and weight.stride(0) % 4 == 0 and
+            x.data_ptr() % 16 == 0 and weight.data_ptr() % 16 == 0 and x.shape[0] > 0)
+
+
+def linear_fwd(x, weight, bias, y, act) -> None:
+    """y = act(x @ weight.T + bias) on the tcgen05 tensor cores (TF32 operands, fp32 accumulate)."""
+    lib = _abi.load()
+    M, K = x.shape
+    N = weight.shape[0]
+    if y.stride(1) != 1 or y.dtype != torch.float32 or not y.is_cuda:
+        raise RuntimeError("qa_linear_fwd: bad output tensor")
+    a = _abi.QaLinearArgs(M, N, K, ACT_ID[act], x.data_ptr(), x.stride(0), weight.data_ptr(), weight.stride(0),
+                          None if bias is None else _p(bias, torch.float32, "bias"), y.data_ptr(), y.stride(0))
+    _abi.check(lib.qa_linear_fwd(C.byref(a), _stream()), "qa_linear_fwd")
+    _count(1)
+
+
 # ---- K2 constants ---------------------------------------------------------------------------------
 def bbc_const(cfg: "K.BbcEnvConfig", prior_parameters=None) -> _abi.QaBbcConst:
     """Flattens the task configuration into the POD the fused kernel takes by value."""

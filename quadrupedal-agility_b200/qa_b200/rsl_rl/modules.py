@@ -59,21 +59,38 @@ class FlatParams:
     `module.state_dict()` / `load_state_dict()` keep working: the Parameters are views."""
 
     def __init__(self, module: nn.Module):
+        """Every tensor starts on a 16-byte boundary and the rows of 2-D weights are padded to a multiple of 4
+        floats (the padding stays zero: zero gradient, zero Adam update), so that the tcgen05 GEMM can read the
+        weights straight out of the flat buffer through TMA.  The Parameters are (possibly strided) views."""
         params = [p for p in module.parameters()]
-        self.numel = sum(p.numel() for p in params)
+        names = {id(p): n for n, p in module.named_parameters()}
         dev = params[0].device
+        plan, off = [], 0
+        for p in params:
+            if p.dim() == 2:
+                rows, k = p.shape
+                kp = (k + 3) // 4 * 4
+                n = rows * kp
+            else:
+                n = (p.numel() + 3) // 4 * 4
+            plan.append((p, off, n))
+            off += n
+        self.numel = off
         self.data = torch.zeros(self.numel, device=dev, dtype=torch.float32)
         self.grad = torch.zeros(self.numel, device=dev, dtype=torch.float32)
-        off = 0
         self.slices = {}
-        names = {id(p): n for n, p in module.named_parameters()}
-        for p in params:
-            n = p.numel()
-            self.data[off:off + n].copy_(p.data.reshape(-1))
-            p.data = self.data[off:off + n].view_as(p)
-            p.grad = self.grad[off:off + n].view_as(p)
-            self.slices[names[id(p)]] = (off, n)
-            off += n
+
+        def view(buf, p, o, n):
+            if p.dim() == 2:
+                rows, k = p.shape
+                return buf[o:o + n].view(rows, n // rows)[:, :k]
+            return buf[o:o + p.numel()].view(p.shape)
+
+        for p, o, n in plan:
+            view(self.data, p, o, n).copy_(p.data)
+            p.data = view(self.data, p, o, n)
+            p.grad = view(self.grad, p, o, n)
+            self.slices[names[id(p)]] = (o, n)
 
     def zero_grad(self):
         self.grad.zero_()
@@ -180,7 +197,15 @@ class ActorCritic(nn.Module):
         obs_prop, obs_explicit, obs_latent, obs_hist, obs_command = self._split(observations)
         if self.train_with_estimated_latent:
             obs_latent = self.infer_hist_latent(obs_hist) if hist_encoding else self.infer_priv_latent(obs_latent)
-        x = torch.cat([obs_prop, obs_explicit, obs_latent, obs_command], dim=-1)
+        # [prop | explicit | latent | command] assembled in a buffer whose rows are 16-byte aligned (TMA operand)
+        n_in = self.num_actor_obs
+        buf = torch.empty(observations.shape[0], (n_in + 3) // 4 * 4, device=observations.device, dtype=observations.dtype)
+        x = buf[:, :n_in]
+        p, e, l = self.num_prop, self.num_explicit, self.num_latent
+        x[:, :p] = obs_prop
+        x[:, p:p + e] = obs_explicit
+        x[:, p + e:p + e + l] = obs_latent
+        x[:, p + e + l:] = obs_command
         return linear_act(run_mlp(self.actor_trunk, x), self.actor_head.weight, self.actor_head.bias, None)
 
     def update_distribution(self, observations, hist_encoding: bool):

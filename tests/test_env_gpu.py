@@ -279,3 +279,37 @@ def test_multi_step_rollout_matches_oracle_chain():
                   "feet_air_time", "obs_disc_buf", "action_history_buf"):
             carried[k] = want[k]
         prev_out = want
+
+
+def test_device_step_counter_matches_host_counters():
+    """CUDA-graph mode: the Philox counter, push schedule and contact-ring head derived on the device from
+    step_state are the ones the host path passes as scalars (5 steps across a push at counter 400)."""
+    N = 512
+    cfg = BbcEnvConfig(num_envs=N)
+    static = synthetic.make_static(cfg, seed=41)
+    table = mocap_table()
+    snaps = [synthetic.make_snapshot(cfg, seed=41, step=t, reset_frac=0.1, plant_frac=0.02) for t in range(5)]
+    envs = []
+    for dev_counter in (False, True):
+        phys = RecordedPhysics([to_dev({k: v.clone() for k, v in s.items()}, DEV) for s in snaps])
+        env = LeggedRobot(cfg, phys, static, table, device=DEV, seed=5)
+        env.load_state(to_dev(snaps[0], DEV))
+        env.common_step_counter = 397
+        env._ring_head = 396 % 100
+        if dev_counter:
+            env.use_device_step_counter(True)
+        envs.append(env)
+    pushed = False
+    for t in range(5):
+        for env in envs:
+            env.post_physics_step()
+        torch.cuda.synchronize()
+        a, b = envs
+        for k in ("obs_buf", "commands", "root_states", "rew_buf", "reset_buf", "obs_history_buf"):
+            assert torch.equal(getattr(a, k), getattr(b, k)), (t, k)
+        assert torch.equal(a._contact_ring, b._contact_ring), t
+        pushed = pushed or (a.common_step_counter % 400 == 0)
+    assert pushed
+    envs[1].common_step_counter = -1
+    envs[1].sync_step_counter()
+    assert envs[1].common_step_counter == envs[0].common_step_counter == 402

@@ -1,0 +1,83 @@
+"""GPU numerics of K7 (tcgen05 TF32 GEMM + fused bias/activation epilogue) against a plain PyTorch fp32
+reference of the same op.  TF32 keeps 10 mantissa bits of each operand (fp32 accumulate), so the tolerance is
+2e-3 relative to the row's scale -- stated here, not the 1e-5 bar of the env/GAE kernels."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from qa_b200 import ops, synthetic
+from qa_b200.config import bbc_train_cfg
+from qa_b200.rsl_rl import ActorCritic, linear
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+torch.backends.cuda.matmul.allow_tf32 = False
+torch.backends.cudnn.allow_tf32 = False
+
+SHAPES = [  # (M, N, K, x_pitch, w_pitch)
+    (24576, 512, 671, 672, 672), (4096, 512, 101, 104, 104), (4096, 256, 512, 512, 512), (4096, 128, 256, 256, 256),
+    (4096, 12, 128, 128, 128), (4096, 1, 128, 128, 128), (300, 64, 57, 672, 60), (128, 29, 64, 64, 64),
+    (1, 16, 32, 32, 32), (1000, 512, 98, 100, 100), (129, 5, 256, 256, 256), (4096, 4, 64, 64, 64),
+]
+
+
+def ref(x, w, b, act):
+    y = F.linear(x.double(), w.double(), None if b is None else b.double())
+    if act == "elu":
+        y = F.elu(y)
+    elif act == "relu":
+        y = F.relu(y)
+    return y
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("act", [None, "elu", "relu"])
+def test_linear_fwd_matches_fp32_reference(shape, act):
+    M, N, K, xp, wp = shape
+    g = torch.Generator().manual_seed(M + 7 * N + 13 * K)
+    xbuf = torch.randn(M, xp, generator=g).to(DEV)
+    wbuf = (torch.randn(N, wp, generator=g) / K ** 0.5).to(DEV)
+    b = (0.1 * torch.randn(N, generator=g)).to(DEV)
+    x, w = xbuf[:, :K], wbuf[:, :K]
+    assert ops.linear_tc_ok(x, w)
+    y = torch.full((M, N), float("nan"), device=DEV)
+    ops.linear_fwd(x, w, b, y, act)
+    torch.cuda.synchronize()
+    want = ref(x, w, b, act)
+    scale = (x.double().abs() @ w.double().abs().t() + b.double().abs()).clamp(min=1e-6)
+    err = ((y.double() - want).abs() / scale).max().item()
+    assert torch.isfinite(y).all()
+    assert err < 2e-3, f"{shape} act={act}: max scaled err {err:.3e}"
+    # without bias
+    ops.linear_fwd(x, w, None, y, act)
+    err = ((y.double() - ref(x, w, None, act)).abs() / scale).max().item()
+    assert err < 2e-3
+
+
+def test_linear_rejects_unaligned_operands():
+    x = torch.randn(64, 101, device=DEV)            # pitch 101 floats: not a 16-byte multiple
+    w = torch.randn(32, 101, device=DEV)
+    assert not ops.linear_tc_ok(x, w)
+    with pytest.raises(RuntimeError, match="QA_EINVAL"):
+        ops.linear_fwd(x, w, None, torch.empty(64, 32, device=DEV), None)
+
+
+def test_actor_critic_tc_mode_matches_fp32_mode_and_grads():
+    w = synthetic.make_weights(3)
+    ac = ActorCritic(101, 671, 12, 57, 10, 4, 29, 11, **bbc_train_cfg()["policy"]).to(DEV)
+    ac.load_state_dict(w["ac"])
+    flat = ac.flatten_parameters()
+    g = torch.Generator().manual_seed(0)
+    obs = torch.randn(2048, 672, generator=g).to(DEV)[:, :671]
+    outs = {}
+    for mode in ("fp32", "tc"):
+        linear.set_mode(mode)
+        flat.zero_grad()
+        mean = ac.act_inference(obs, hist_encoding=False)
+        val = ac.evaluate(obs)
+        (mean.square().mean() + val.square().mean()).backward()
+        outs[mode] = (mean.detach().clone(), val.detach().clone(), flat.grad.clone())
+    linear.set_mode("fp32")
+    for a, b, name in zip(outs["tc"], outs["fp32"], ("mean", "value", "grad")):
+        denom = b.abs().max().item()
+        assert (a - b).abs().max().item() < 5e-3 * denom, name

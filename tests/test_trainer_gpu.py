@@ -19,6 +19,8 @@ from qa_b200.rsl_rl import ActorCritic, Estimator, Discriminator, Normalizer, Ro
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
+torch.backends.cuda.matmul.allow_tf32 = False     # parity path: full fp32 contractions
+torch.backends.cudnn.allow_tf32 = False
 NET_RTOL, NET_ATOL = 1e-4, 2e-5
 
 
