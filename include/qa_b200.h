@@ -51,7 +51,7 @@ int qa_version(void);
 /* human readable build string ("sm_100a, nvcc 12.9, ...") */
 const char* qa_build_info(void);
 /* sizeof() of argument struct number `which` (order of declaration in this header, QaActionPushArgs
- * = 0 ... QaGaeArgs = 9, QaGatherArgs = 10, QaClipAdamArgs = 11, QaLinearArgs = 12; -1 if unknown): a layout handshake for FFI mirrors of these structs */
+ * = 0 ... QaGaeArgs = 9, QaGatherArgs = 10, QaClipAdamArgs = 11, QaLinearArgs = 12, QaActBwdArgs = 13, QaPpoLossArgs = 14; -1 if unknown): a layout handshake for FFI mirrors of these structs */
 int qa_struct_size(int which);
 
 /* ------------------------------------------------------------------------------------------
@@ -383,6 +383,50 @@ typedef struct QaLinearArgs {
     int64_t y_pitch;
 } QaLinearArgs;
 int qa_linear_fwd(const QaLinearArgs* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K9  gz = gy * act'(y), db = column sums of gz -- the element-wise half of Linear+ELU/ReLU backward
+ *     (autograd of bbc/rsl_rl/modules/actor_critic.py:113-129).  y is the layer OUTPUT saved by the forward.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct QaActBwdArgs {
+    int64_t M;
+    int32_t N;
+    int32_t act;                        /* 0 none, 1 ELU, 2 ReLU */
+    const float* gy; int64_t gy_pitch;  /* (M,N) upstream gradient */
+    const float* y;  int64_t y_pitch;   /* (M,N) forward output (unused when act == 0) */
+    float* gz;       int64_t gz_pitch;  /* (M,N) out, may alias gy, may be NULL (bias gradient only) */
+    float* db;                          /* (N) out, may be NULL */
+    int32_t zero_db;                    /* 1: db is zeroed first, 0: accumulate */
+} QaActBwdArgs;
+int qa_act_bwd(const QaActBwdArgs* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K10 PPO loss forward + backward -- replaces the element-wise graph of SSInfoGAIL.update_actor_critic,
+ *     bbc/rsl_rl/algorithms/gail.py:367-408 (KL, clipped surrogate, clipped value loss, bound loss, entropy).
+ *     loss = c_surr*mean(surr) + c_value*mean(vl) + c_bound*mean(b) - c_entropy*mean(entropy); gradients w.r.t. the
+ *     action mean, the value and the std parameter are written, stats = {surrogate, value, bound, kl} means.
+ * ------------------------------------------------------------------------------------------ */
+#define QA_PPO_STATS 4
+typedef struct QaPpoLossArgs {
+    int64_t M;
+    const float* mu; int64_t mu_pitch;  /* (M,12) action mean */
+    const float* std;                   /* (12) */
+    const float* value; int64_t value_pitch; /* (M,1) */
+    const float* actions;               /* (M,12) */
+    const float* old_logp;              /* (M) */
+    const float* advantages;            /* (M) */
+    const float* returns;               /* (M) */
+    const float* target_values;         /* (M) */
+    const float* old_mu;                /* (M,12) */
+    const float* old_sigma;             /* (M,12) */
+    float clip, c_surr, c_value, c_bound, c_entropy;
+    int32_t use_clipped_value_loss;
+    float* dmu;                         /* (M,12) */
+    float* dvalue;                      /* (M) */
+    float* dstd;                        /* (12) */
+    float* stats;                       /* (QA_PPO_STATS) */
+} QaPpoLossArgs;
+int qa_ppo_loss(const QaPpoLossArgs* a, void* stream);
 
 #ifdef __cplusplus
 }

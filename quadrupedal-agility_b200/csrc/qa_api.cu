@@ -28,6 +28,8 @@ extern "C" int qa_struct_size(int which) {
         case 10: return (int)sizeof(QaGatherArgs);
         case 11: return (int)sizeof(QaClipAdamArgs);
         case 12: return (int)sizeof(QaLinearArgs);
+        case 13: return (int)sizeof(QaActBwdArgs);
+        case 14: return (int)sizeof(QaPpoLossArgs);
         default: return -1;
     }
 }

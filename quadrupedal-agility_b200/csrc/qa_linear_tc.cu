@@ -27,7 +27,7 @@
 
 #define TC_BM 128
 #define TC_BK 32              // floats per K block = 128 bytes = one swizzle span
-#define TC_STAGES 4
+#define TC_STAGES 3          // 3 x (16 KB A + <=16 KB B) = 96 KB -> two CTAs per SM: one's epilogue overlaps the other's main loop
 #define TC_THREADS 192
 
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) { mbar_expect_tx(bar, bytes); }
@@ -106,7 +106,7 @@ struct TcSmem {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, 2)
 k_linear_tf32(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
               const __grid_constant__ QaLinearArgs g) {
     extern __shared__ unsigned char smem_raw[];
@@ -172,42 +172,37 @@ k_linear_tf32(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
     } else {
         // ===== epilogue: warps 2..5 own TMEM lane quadrants (warp % 4) =====
         const int q = warp & 3;
-        const int row = m0 + q * 32 + lane;
         mbar_wait(&S.tmem_full, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const bool vec_ok = ((g.y_pitch & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.y) & 15u) == 0);
+        // The smem ring is idle once tmem_full has fired (every MMA that read it has retired): reuse it as a
+        // per-warp 32x33 transpose buffer so that the global stores are full 128-byte lines (lane = column).
+        float* stg = reinterpret_cast<float*>(&S.a[0][0]) + q * (32 * 33);
         constexpr int CH = BN >= 32 ? 32 : 16;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += CH) {
+            if (n0 + c0 >= g.N) break;
             uint32_t r[32];
             const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
             if (CH == 32) tmem_ld32(taddr, r);
             else tmem_ld16(taddr, r);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (row < g.M) {
-                float* yrow = g.y + (size_t)row * g.y_pitch;
 #pragma unroll
-                for (int j = 0; j < CH; j += 4) {
-                    const int col = n0 + c0 + j;
-                    float v[4];
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        float x = __uint_as_float(r[j + t]);
-                        const int cc = col + t;
-                        if (g.bias != nullptr && cc < g.N) x += __ldg(g.bias + cc);
-                        if (g.act == 1) x = x > 0.f ? x : expm1f(x);            // ELU(alpha = 1)
-                        else if (g.act == 2) x = fmaxf(x, 0.f);                 // ReLU
-                        v[t] = x;
-                    }
-                    if (vec_ok && col + 3 < g.N) {
-                        *reinterpret_cast<float4*>(yrow + col) = make_float4(v[0], v[1], v[2], v[3]);
-                    } else {
-#pragma unroll
-                        for (int t = 0; t < 4; ++t)
-                            if (col + t < g.N) yrow[col + t] = v[t];
-                    }
-                }
+            for (int j = 0; j < CH; ++j) {
+                float x = __uint_as_float(r[j]);
+                const int cc = n0 + c0 + j;
+                if (g.bias != nullptr && cc < g.N) x += __ldg(g.bias + cc);
+                if (g.act == 1) x = x > 0.f ? x : expm1f(x);                    // ELU(alpha = 1)
+                else if (g.act == 2) x = fmaxf(x, 0.f);                         // ReLU
+                stg[lane * 33 + j] = x;
             }
+            __syncwarp();
+            const int col = n0 + c0 + lane;
+            if (lane < CH && col < g.N) {
+                const int rows = min(32, g.M - (m0 + q * 32));
+                float* yp = g.y + (size_t)(m0 + q * 32) * g.y_pitch + col;
+                for (int rr = 0; rr < rows; ++rr) yp[(size_t)rr * g.y_pitch] = stg[rr * 33 + lane];
+            }
+            __syncwarp();
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -286,6 +281,5 @@ extern "C" int qa_linear_fwd(const QaLinearArgs* g, void* stream) {
     if (n <= 16) return launch_linear<16>(g, s);
     if (n <= 32) return launch_linear<32>(g, s);
     if (n <= 64) return launch_linear<64>(g, s);
-    if (n <= 128 || g->M < 8192) return launch_linear<128>(g, s);
-    return launch_linear<256>(g, s);
+    return launch_linear<128>(g, s);
 }

@@ -154,3 +154,177 @@ extern "C" int qa_clip_adam(const QaClipAdamArgs* a, void* stream) {
     k_clip_adam<<<(unsigned)blocks, 256, 0, s>>>(*a);
     QA_LAUNCH_RET();
 }
+
+// ------------------------------------------------------------------------------------------
+// K9: activation backward fused with the bias gradient:  gz = gy * act'(y),  db[c] = sum_r gz[r,c]
+//     (the element-wise half of the backward of every Linear+ELU/ReLU, actor_critic.py:113-129).  The ELU
+//     derivative is recovered from the saved OUTPUT: elu'(z) = 1 for y > 0, y + 1 otherwise.
+//     Block = 32 columns x 8 warps; each warp strides over the rows of a 256-row strip with lane = column
+//     (coalesced 128 B accesses), partial column sums meet in shared memory and leave with one atomicAdd per
+//     column per block.  3 passes over M x N (read gy, y; write gz).
+// ------------------------------------------------------------------------------------------
+#define AB_ROWS 256
+__global__ void __launch_bounds__(256) k_act_bwd(QaActBwdArgs a) {
+    __shared__ float s_part[8][33];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int col = blockIdx.x * 32 + lane;
+    const long long r0 = (long long)blockIdx.y * AB_ROWS;
+    const long long r1 = min((long long)a.M, r0 + AB_ROWS);
+    float acc = 0.f;
+    if (col < a.N) {
+        for (long long r = r0 + w; r < r1; r += 8) {
+            float g = a.gy[r * a.gy_pitch + col];
+            if (a.act != 0) {
+                const float y = a.y[r * a.y_pitch + col];
+                if (a.act == 1) g = y > 0.f ? g : g * (y + 1.0f);
+                else g = y > 0.f ? g : 0.f;
+            }
+            if (a.gz != nullptr) a.gz[r * a.gz_pitch + col] = g;
+            acc += g;
+        }
+    }
+    if (a.db != nullptr) {
+        s_part[w][lane] = acc;
+        __syncthreads();
+        if (w == 0 && col < a.N) {
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s += s_part[k][lane];
+            atomicAdd(a.db + col, s);
+        }
+    }
+}
+
+extern "C" int qa_act_bwd(const QaActBwdArgs* a, void* stream) {
+    QA_CHECK_PTR(a);
+    if (a->M == 0) return 0;
+    QA_CHECK_PTR(a->gy);
+    if (a->M < 0 || a->N <= 0 || a->act < 0 || a->act > 2) return QA_EINVAL;
+    if (a->act != 0) QA_CHECK_PTR(a->y);
+    if (a->gz == nullptr && a->db == nullptr) return QA_EINVAL;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (a->db != nullptr && a->zero_db) {
+        cudaError_t e = cudaMemsetAsync(a->db, 0, sizeof(float) * a->N, s);
+        if (e != cudaSuccess) return (int)e;
+    }
+    dim3 grid((a->N + 31) / 32, (unsigned)((a->M + AB_ROWS - 1) / AB_ROWS));
+    k_act_bwd<<<grid, 256, 0, s>>>(*a);
+    QA_LAUNCH_RET();
+}
+
+// ------------------------------------------------------------------------------------------
+// K10: PPO loss, forward + backward in one pass (gail.py:367-408): per sample the Normal log-prob, ratio,
+//      clipped surrogate, clipped value loss, bound loss and KL; the gradients w.r.t. the action mean, the value and
+//      the (broadcast) std parameter are produced in the same kernel, so autograd resumes at the network outputs.
+//      Thread per sample, 12 action dims in registers; block-level reductions, one atomic per block per quantity.
+//      torch.max(a, b) sends half of the gradient to each side on ties, which matters inside the clip range where
+//      surrogate == surrogate_clipped exactly: both halves carry the same derivative there.
+// ------------------------------------------------------------------------------------------
+#define PL_A QA_NUM_DOF
+__global__ void __launch_bounds__(256) k_ppo_loss(QaPpoLossArgs p) {
+    __shared__ float s_red[8][QA_PPO_STATS + PL_A];
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const float invM = 1.0f / (float)p.M;
+    float st[QA_PPO_STATS + PL_A];
+#pragma unroll
+    for (int k = 0; k < QA_PPO_STATS + PL_A; ++k) st[k] = 0.f;
+    if (i < p.M) {
+        float mu[PL_A], sg[PL_A], diff[PL_A];
+        float logp = 0.f, kl = 0.f, bl = 0.f;
+#pragma unroll
+        for (int j = 0; j < PL_A; ++j) {
+            mu[j] = p.mu[i * p.mu_pitch + j];
+            sg[j] = p.std[j];
+            const float a = p.actions[i * PL_A + j];
+            diff[j] = a - mu[j];
+            logp += -(diff[j] * diff[j]) / (2.f * sg[j] * sg[j]) - logf(sg[j]) - 0.9189385332046727f;
+            const float os = p.old_sigma[i * PL_A + j], om = p.old_mu[i * PL_A + j];
+            kl += logf(sg[j] / os + 1.e-5f) + (os * os + (om - mu[j]) * (om - mu[j])) / (2.0f * sg[j] * sg[j]) - 0.5f;
+            const float hi = fmaxf(mu[j] - 1.0f, 0.f), lo = fminf(mu[j] + 1.0f, 0.f);
+            bl += lo * lo + hi * hi;
+        }
+        const float adv = p.advantages[i];
+        const float ratio = expf(logp - p.old_logp[i]);
+        const float rc = fminf(fmaxf(ratio, 1.0f - p.clip), 1.0f + p.clip);
+        const float s1 = -adv * ratio, s2 = -adv * rc;
+        const float surr = fmaxf(s1, s2);
+        // d surr / d ratio
+        const float in_range = (ratio >= 1.0f - p.clip && ratio <= 1.0f + p.clip) ? 1.f : 0.f;
+        float w1, w2;
+        if (s1 > s2) { w1 = 1.f; w2 = 0.f; } else if (s2 > s1) { w1 = 0.f; w2 = 1.f; } else { w1 = 0.5f; w2 = 0.5f; }
+        const float dsurr_dratio = -adv * (w1 + w2 * in_range);
+        const float dlogp = p.c_surr * invM * dsurr_dratio * ratio;
+        // value loss
+        const float v = p.value[i * p.value_pitch], R = p.returns[i];
+        float vl, dv;
+        if (p.use_clipped_value_loss) {
+            const float tv = p.target_values[i];
+            const float dvt = v - tv;
+            const float vc = tv + fminf(fmaxf(dvt, -p.clip), p.clip);
+            const float l1 = (v - R) * (v - R), l2 = (vc - R) * (vc - R);
+            vl = fmaxf(l1, l2);
+            const float dvc = (dvt >= -p.clip && dvt <= p.clip) ? 1.f : 0.f;
+            float u1, u2;
+            if (l1 > l2) { u1 = 1.f; u2 = 0.f; } else if (l2 > l1) { u1 = 0.f; u2 = 1.f; } else { u1 = 0.5f; u2 = 0.5f; }
+            dv = u1 * 2.f * (v - R) + u2 * 2.f * (vc - R) * dvc;
+        } else {
+            vl = (R - v) * (R - v);
+            dv = 2.f * (v - R);
+        }
+        p.dvalue[i] = p.c_value * invM * dv;
+#pragma unroll
+        for (int j = 0; j < PL_A; ++j) {
+            const float s2j = sg[j] * sg[j];
+            const float hi = fmaxf(mu[j] - 1.0f, 0.f), lo = fminf(mu[j] + 1.0f, 0.f);
+            p.dmu[i * PL_A + j] = dlogp * diff[j] / s2j + p.c_bound * invM * 2.f * (lo + hi);
+            // d loss / d sigma_j of this sample: through log-prob, plus the entropy term (-c_ent * mean(sum log sigma))
+            st[QA_PPO_STATS + j] = dlogp * ((diff[j] * diff[j]) / (s2j * sg[j]) - 1.f / sg[j]) - p.c_entropy * invM / sg[j];
+        }
+        st[0] = surr * invM;
+        st[1] = vl * invM;
+        st[2] = bl * invM;
+        st[3] = kl * invM;
+    }
+    // block reduction: warp shuffles, then 8 partials in smem
+#pragma unroll
+    for (int k = 0; k < QA_PPO_STATS + PL_A; ++k) st[k] = warp_sum(st[k]);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < QA_PPO_STATS + PL_A; ++k) s_red[w][k] = st[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < QA_PPO_STATS + PL_A) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += s_red[k][threadIdx.x];
+        if (threadIdx.x < QA_PPO_STATS) atomicAdd(p.stats + threadIdx.x, s);
+        else atomicAdd(p.dstd + (threadIdx.x - QA_PPO_STATS), s);
+    }
+}
+
+extern "C" int qa_ppo_loss(const QaPpoLossArgs* p, void* stream) {
+    QA_CHECK_PTR(p);
+    if (p->M <= 0) return QA_EINVAL;
+    QA_CHECK_PTR(p->mu);
+    QA_CHECK_PTR(p->std);
+    QA_CHECK_PTR(p->value);
+    QA_CHECK_PTR(p->actions);
+    QA_CHECK_PTR(p->old_logp);
+    QA_CHECK_PTR(p->advantages);
+    QA_CHECK_PTR(p->returns);
+    QA_CHECK_PTR(p->target_values);
+    QA_CHECK_PTR(p->old_mu);
+    QA_CHECK_PTR(p->old_sigma);
+    QA_CHECK_PTR(p->dmu);
+    QA_CHECK_PTR(p->dvalue);
+    QA_CHECK_PTR(p->dstd);
+    QA_CHECK_PTR(p->stats);
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(p->stats, 0, sizeof(float) * QA_PPO_STATS, s);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemsetAsync(p->dstd, 0, sizeof(float) * PL_A, s);
+    if (e != cudaSuccess) return (int)e;
+    k_ppo_loss<<<(unsigned)((p->M + 255) / 256), 256, 0, s>>>(*p);
+    QA_LAUNCH_RET();
+}

@@ -129,6 +129,20 @@ class QaLinearArgs(C.Structure):
                 ("y_pitch", C.c_int64)]
 
 
+class QaActBwdArgs(C.Structure):
+    _fields_ = [("M", C.c_int64), ("N", C.c_int32), ("act", C.c_int32), ("gy", vp), ("gy_pitch", C.c_int64),
+                ("y", vp), ("y_pitch", C.c_int64), ("gz", vp), ("gz_pitch", C.c_int64), ("db", vp),
+                ("zero_db", C.c_int32)]
+
+
+class QaPpoLossArgs(C.Structure):
+    _fields_ = [("M", C.c_int64), ("mu", vp), ("mu_pitch", C.c_int64), ("std", vp), ("value", vp),
+                ("value_pitch", C.c_int64), ("actions", vp), ("old_logp", vp), ("advantages", vp), ("returns", vp),
+                ("target_values", vp), ("old_mu", vp), ("old_sigma", vp), ("clip", C.c_float), ("c_surr", C.c_float),
+                ("c_value", C.c_float), ("c_bound", C.c_float), ("c_entropy", C.c_float),
+                ("use_clipped_value_loss", C.c_int32), ("dmu", vp), ("dvalue", vp), ("dstd", vp), ("stats", vp)]
+
+
 # every symbol `include/qa_b200.h` declares: name -> (restype, argtypes)
 SYMBOLS = {
     "qa_version": (C.c_int, []),
@@ -144,10 +158,12 @@ SYMBOLS = {
     "qa_gather_minibatch": (C.c_int, [C.POINTER(QaGatherArgs), vp]),
     "qa_clip_adam": (C.c_int, [C.POINTER(QaClipAdamArgs), vp]),
     "qa_linear_fwd": (C.c_int, [C.POINTER(QaLinearArgs), vp]),
+    "qa_act_bwd": (C.c_int, [C.POINTER(QaActBwdArgs), vp]),
+    "qa_ppo_loss": (C.c_int, [C.POINTER(QaPpoLossArgs), vp]),
 }
 
 STRUCT_ORDER = [QaActionPushArgs, QaTorqueArgs, QaTerrain, QaHeightScanArgs, QaMocapTable, QaMocapBlendArgs,
-                QaBbcConst, QaBbcStepArgs, QaCompactArgs, QaGaeArgs, QaGatherArgs, QaClipAdamArgs, QaLinearArgs]
+                QaBbcConst, QaBbcStepArgs, QaCompactArgs, QaGaeArgs, QaGatherArgs, QaClipAdamArgs, QaLinearArgs, QaActBwdArgs, QaPpoLossArgs]
 
 _LIB = None
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libqa_b200.so")

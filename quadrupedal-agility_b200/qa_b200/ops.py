@@ -200,6 +200,38 @@ def linear_fwd(x, weight, bias, y, act) -> None:
     _count(1)
 
 
+# ---- K9 ---------------------------------------------------------------------------------------
+def act_bwd(gy, y, act, gz=None, db=None, zero_db=True) -> None:
+    """gz = gy * act'(y) (ELU' from the saved output: 1 if y > 0 else y + 1) and/or db = gz.sum(0)."""
+    lib = _abi.load()
+    M, N = gy.shape
+    for t in (gy, y, gz):
+        if t is not None and (t.stride(1) != 1 or t.dtype != torch.float32 or not t.is_cuda):
+            raise RuntimeError("qa_act_bwd: operands must be fp32 CUDA with unit inner stride")
+    a = _abi.QaActBwdArgs(M, N, ACT_ID[act], gy.data_ptr(), gy.stride(0), None if y is None else y.data_ptr(),
+                          0 if y is None else y.stride(0), None if gz is None else gz.data_ptr(),
+                          0 if gz is None else gz.stride(0), None if db is None else _p(db, torch.float32, "db"),
+                          int(zero_db))
+    _abi.check(lib.qa_act_bwd(C.byref(a), _stream()), "qa_act_bwd")
+    _count(1)
+
+
+# ---- K10 --------------------------------------------------------------------------------------
+def ppo_loss(mu, std, value, actions, old_logp, advantages, returns, target_values, old_mu, old_sigma, dmu, dvalue,
+             dstd, stats, clip, c_surr, c_value, c_bound, c_entropy, use_clipped_value_loss) -> None:
+    """Forward + backward of the PPO loss terms of gail.py:367-408 in one kernel (see include/qa_b200.h)."""
+    lib = _abi.load()
+    f = torch.float32
+    a = _abi.QaPpoLossArgs(mu.shape[0], mu.data_ptr(), mu.stride(0), _p(std, f, "std"), value.data_ptr(), value.stride(0),
+                           _p(actions, f, "actions"), _p(old_logp, f, "old_logp"), _p(advantages, f, "advantages"),
+                           _p(returns, f, "returns"), _p(target_values, f, "target_values"), _p(old_mu, f, "old_mu"),
+                           _p(old_sigma, f, "old_sigma"), float(clip), float(c_surr), float(c_value), float(c_bound),
+                           float(c_entropy), int(use_clipped_value_loss), _p(dmu, f, "dmu"), _p(dvalue, f, "dvalue"),
+                           _p(dstd, f, "dstd"), _p(stats, f, "stats"))
+    _abi.check(lib.qa_ppo_loss(C.byref(a), _stream()), "qa_ppo_loss")
+    _count(1)
+
+
 # ---- K2 constants ---------------------------------------------------------------------------------
 def bbc_const(cfg: "K.BbcEnvConfig", prior_parameters=None) -> _abi.QaBbcConst:
     """Flattens the task configuration into the POD the fused kernel takes by value."""

@@ -20,6 +20,7 @@ import torch
 import torch.distributed as dist
 
 from .. import ops
+from .. import dist as qdist
 from .storage import RolloutStorage
 
 
@@ -75,6 +76,30 @@ class FlatAdam:
         self.step_count.copy_(sd["step"])
 
 
+class _PPOLossFused(torch.autograd.Function):
+    """K10: the PPO loss terms of gail.py:367-408, forward and backward in one kernel launch."""
+
+    @staticmethod
+    def forward(ctx, mu, value, std, mb, cfg, stats):
+        M = mu.shape[0]
+        dmu = torch.empty(M, mu.shape[1], device=mu.device, dtype=torch.float32)
+        dvalue = torch.empty(M, device=mu.device, dtype=torch.float32)
+        dstd = torch.empty(std.shape[0], device=mu.device, dtype=torch.float32)
+        ops.ppo_loss(mu, std.detach().contiguous(), value, mb["actions"], mb["old_actions_log_prob"].view(-1),
+                     mb["advantages"].view(-1), mb["returns"].view(-1), mb["values"].view(-1), mb["old_mu"],
+                     mb["old_sigma"], dmu, dvalue, dstd, stats, cfg["clip"], cfg["c_surr"], cfg["c_value"],
+                     cfg["c_bound"], cfg["c_entropy"], cfg["clipped_value"])
+        ctx.save_for_backward(dmu, dvalue, dstd)
+        entropy = (1.4189385332046727 + torch.log(std.detach())).sum()
+        return (cfg["c_surr"] * stats[0] + cfg["c_value"] * stats[1] + cfg["c_bound"] * stats[2]
+                - cfg["c_entropy"] * entropy)
+
+    @staticmethod
+    def backward(ctx, g):
+        dmu, dvalue, dstd = ctx.saved_tensors
+        return g * dmu, (g * dvalue).unsqueeze(1), g * dstd, None, None, None
+
+
 STAT_NAMES = ("surrogate_loss", "value_loss", "b_loss", "entropy", "priv_reg_loss", "estimator_loss", "kl_mean")
 
 
@@ -87,7 +112,7 @@ class SSInfoGAIL:
                  lr_q=1e-3, max_grad_norm=1.0, use_clipped_value_loss=False, schedule="fixed", desired_kl=0.01,
                  device='cpu', disc_replay_buffer_size=100000, min_std=None, us_coef=1.0, ss_coef=4.0,
                  prior_soft_coef=1e-3, info_max_coef=2.0, begin_rim=100, priv_reg_coef_schedual=[0, 0.1, 0, 1],
-                 priv_reg_coef_schedual_resume=[0, 0.1, 0, 1], use_cuda_graph=True):
+                 priv_reg_coef_schedual_resume=[0, 0.1, 0, 1], use_cuda_graph=True, fused_loss=True):
         self.device, self.env = device, env
         self.desired_kl, self.schedule = desired_kl, schedule
         self.lr_disc, self.lr_q, self.min_std = lr_disc, lr_q, min_std
@@ -124,6 +149,8 @@ class SSInfoGAIL:
         self.world_size = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.use_cuda_graph = use_cuda_graph and torch.device(device).type == "cuda"
         self._graphs = None
+        self.fused_loss = fused_loss and torch.device(device).type == "cuda"
+        self._ppo_stats = torch.zeros(4, device=device)
         self._priv_reg_coef = torch.zeros((), device=device)
         self._stats = torch.zeros(len(STAT_NAMES), device=device)
         self.last_stats = {}
@@ -225,7 +252,7 @@ class SSInfoGAIL:
         p, e, l, h = self.num_prop, self.num_explicit, self.num_latent, self.num_hist * self.num_prop
         ac.update_distribution(obs, False)
         mu, sigma = ac.action_mean, ac.action_std
-        logp = ac.get_actions_log_prob(mb["actions"])
+        logp = None if self.fused_loss else ac.get_actions_log_prob(mb["actions"])
         value = ac.evaluate(mb["critic_obs"])
         entropy = ac.entropy
         priv_latent = ac.infer_priv_latent(obs[:, p + e:p + e + l])
@@ -236,27 +263,38 @@ class SSInfoGAIL:
         est_loss = (est(obs[:, :p]) - obs[:, p:p + e]).pow(2).mean()
         self.est_flat.zero_grad()
         est_loss.backward()
-        # KL for the adaptive schedule (:367-373)
-        with torch.no_grad():
-            osg, omu = mb["old_sigma"], mb["old_mu"]
-            kl = torch.sum(torch.log(sigma / osg + 1.e-5) + (torch.square(osg) + torch.square(omu - mu)) /
-                           (2.0 * torch.square(sigma)) - 0.5, dim=-1)
-            self._kl.copy_(kl.mean())
-        adv = mb["advantages"].squeeze(1)
-        ratio = torch.exp(logp - mb["old_actions_log_prob"].squeeze(1))
-        surrogate = -adv * ratio
-        surrogate_clipped = -adv * torch.clamp(ratio, 1.0 - self.clip_param, 1.0 + self.clip_param)
-        surrogate_loss = torch.max(surrogate, surrogate_clipped).mean()
-        if self.use_clipped_value_loss:
-            tv = mb["values"]
-            value_clipped = tv + (value - tv).clamp(-self.clip_param, self.clip_param)
-            value_loss = torch.max((value - mb["returns"]).pow(2), (value_clipped - mb["returns"]).pow(2)).mean()
+        if self.fused_loss:
+            cfg = dict(clip=self.clip_param, c_surr=self.surrogate_loss_coef, c_value=self.value_loss_coef,
+                       c_bound=self.bounds_loss_coef, c_entropy=self.entropy_coef,
+                       clipped_value=self.use_clipped_value_loss)
+            main = _PPOLossFused.apply(mu, value, ac.std, mb, cfg, self._ppo_stats)
+            ps = self._ppo_stats
+            surrogate_loss, value_loss, b_loss = ps[0], ps[1], ps[2]
+            self._kl.copy_(ps[3])
+            ent = entropy.mean()
+            loss = main + self._priv_reg_coef * priv_reg_loss
         else:
-            value_loss = (mb["returns"] - value).pow(2).mean()
-        b_loss = (torch.clamp(mu + 1.0, max=0.) ** 2 + torch.clamp(mu - 1.0, min=0.) ** 2).sum(dim=-1).mean()
-        ent = entropy.mean()
-        loss = (self.surrogate_loss_coef * surrogate_loss + self.value_loss_coef * value_loss +
-                self.bounds_loss_coef * b_loss - self.entropy_coef * ent + self._priv_reg_coef * priv_reg_loss)
+            # KL for the adaptive schedule (:367-373)
+            with torch.no_grad():
+                osg, omu = mb["old_sigma"], mb["old_mu"]
+                kl = torch.sum(torch.log(sigma / osg + 1.e-5) + (torch.square(osg) + torch.square(omu - mu)) /
+                               (2.0 * torch.square(sigma)) - 0.5, dim=-1)
+                self._kl.copy_(kl.mean())
+            adv = mb["advantages"].squeeze(1)
+            ratio = torch.exp(logp - mb["old_actions_log_prob"].squeeze(1))
+            surrogate = -adv * ratio
+            surrogate_clipped = -adv * torch.clamp(ratio, 1.0 - self.clip_param, 1.0 + self.clip_param)
+            surrogate_loss = torch.max(surrogate, surrogate_clipped).mean()
+            if self.use_clipped_value_loss:
+                tv = mb["values"]
+                value_clipped = tv + (value - tv).clamp(-self.clip_param, self.clip_param)
+                value_loss = torch.max((value - mb["returns"]).pow(2), (value_clipped - mb["returns"]).pow(2)).mean()
+            else:
+                value_loss = (mb["returns"] - value).pow(2).mean()
+            b_loss = (torch.clamp(mu + 1.0, max=0.) ** 2 + torch.clamp(mu - 1.0, min=0.) ** 2).sum(dim=-1).mean()
+            ent = entropy.mean()
+            loss = (self.surrogate_loss_coef * surrogate_loss + self.value_loss_coef * value_loss +
+                    self.bounds_loss_coef * b_loss - self.entropy_coef * ent + self._priv_reg_coef * priv_reg_loss)
         self.ac_flat.zero_grad()
         loss.backward()
         with torch.no_grad():
@@ -267,11 +305,9 @@ class SSInfoGAIL:
         """All-reduce (multi-GPU), adaptive LR on the device (:374-379), fused clip + Adam (:361-365, :409-412)."""
         scale = 1.0
         if self.world_size > 1:
-            dist.all_reduce(self.ac_flat.grad)
-            dist.all_reduce(self.est_flat.grad)
-            dist.all_reduce(self._kl)
-            self._kl /= self.world_size
-            scale = 1.0 / self.world_size
+            scale = qdist.allreduce_flat_(self.ac_flat.grad)
+            qdist.allreduce_flat_(self.est_flat.grad)
+            qdist.allreduce_mean_scalar_(self._kl)
         self.optim_estimator.step(scale)
         if self.desired_kl is not None and self.schedule == 'adaptive':
             lr, kl = self.optim_ac.lr, self._kl

@@ -40,15 +40,19 @@ class _LinearActTC(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy):
         x, weight, y = ctx.saved_tensors
-        if ctx.act == "elu":
-            gz = gy * torch.where(y > 0, torch.ones_like(y), y + 1.0)
-        elif ctx.act == "relu":
-            gz = gy * (y > 0).to(gy.dtype)
+        if gy.stride(1) != 1:
+            gy = gy.contiguous()
+        want_b = ctx.has_bias and ctx.needs_input_grad[2]
+        gb = torch.empty(weight.shape[0], device=gy.device, dtype=torch.float32) if want_b else None
+        if ctx.act in ("elu", "relu"):
+            gz = torch.empty_like(gy)
+            ops.act_bwd(gy, y, ctx.act, gz=gz, db=gb)            # K9: act'(y) and the bias gradient in one pass
         else:
             gz = gy
+            if want_b:
+                ops.act_bwd(gy, None, None, gz=None, db=gb)
         gx = gz @ weight if ctx.needs_input_grad[0] else None
         gw = gz.t() @ x if ctx.needs_input_grad[1] else None
-        gb = gz.sum(dim=0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
         return gx, gw, gb, None
 
 

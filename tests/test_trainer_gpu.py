@@ -29,7 +29,7 @@ def load_golden():
     return {k: torch.from_numpy(z[k]) for k in z.files}
 
 
-def build(w, n_envs=64):
+def build(w, n_envs=64, fused_loss=True):
     cfg = bbc_train_cfg()
     ac = ActorCritic(101, 671, 12, 57, 10, 4, 29, 11, **cfg["policy"])
     ac.load_state_dict(w["ac"])
@@ -41,7 +41,7 @@ def build(w, n_envs=64):
     disc.load_state_dict(w["disc"])
     norm = Normalizer(98)
     norm.mean, norm.var = w["norm_mean"].numpy().copy(), w["norm_var"].numpy().copy()
-    alg_cfg = dict(cfg["algorithm"], disc_replay_buffer_size=1024, use_cuda_graph=False)
+    alg_cfg = dict(cfg["algorithm"], disc_replay_buffer_size=1024, use_cuda_graph=False, fused_loss=fused_loss)
     alg = SSInfoGAIL(env, ac, disc, est, cfg["estimator"], None, norm, 2, 2, 49, 0.0, device=DEV, **alg_cfg)
     alg.init_storage(n_envs, 24, [671], [671], [12])
     return alg, env, norm
@@ -63,9 +63,10 @@ def test_act_and_disc_reward_match_reference_golden():
         assert_close(f"disc.{k}", v, g[f"disc.{k}"], rtol=NET_RTOL, atol=NET_ATOL)
 
 
-def test_ppo_minibatch_step_matches_reference_golden():
+@pytest.mark.parametrize("fused_loss", [False, True])
+def test_ppo_minibatch_step_matches_reference_golden(fused_loss):
     g = load_golden()
-    alg, env, norm = build(synthetic.make_weights(3))
+    alg, env, norm = build(synthetic.make_weights(3), fused_loss=fused_loss)
     alg.priv_reg_counter = int(g["in.priv_reg_counter"])
     alg._alloc_minibatch(64)
     alg._kl = torch.zeros((), device=DEV)
@@ -154,3 +155,56 @@ def test_update_runs_with_and_without_cuda_graph_identically():
         assert abs(a - b) <= 1e-4 * max(1.0, abs(a)), (outs[0][0], outs[1][0])
     assert_close("params eager vs graph", outs[1][1], outs[0][1], rtol=1e-4, atol=1e-5)
     assert outs[0][2] == outs[1][2]
+
+
+@pytest.mark.parametrize("act", [None, "elu", "relu"])
+def test_act_bwd_matches_torch(act):
+    """K9: gz = gy * act'(y) from the saved output, db = column sums (ragged M, N; strided views)."""
+    g = torch.Generator().manual_seed(9)
+    for M, N in ((24576, 512), (1000, 12), (257, 1), (4096, 128)):
+        z = torch.randn(M, N + 4, generator=g).to(DEV)[:, :N]
+        gy = torch.randn(M, N, generator=g).to(DEV)
+        y = torch.nn.functional.elu(z) if act == "elu" else (torch.relu(z) if act == "relu" else z)
+        want = gy * (torch.where(z > 0, 1.0, torch.exp(z)) if act == "elu" else ((z > 0).float() if act == "relu" else 1.0))
+        gz = torch.empty(M, N, device=DEV)
+        db = torch.full((N,), 7.0, device=DEV)
+        ops.act_bwd(gy, y.contiguous() if act is None else y, act, gz=gz, db=db)
+        assert_close("gz", gz, want, rtol=1e-5, atol=1e-6)
+        assert_close("db", db, want.sum(0), rtol=1e-4, atol=1e-3)
+
+
+def test_ppo_loss_kernel_matches_autograd():
+    """K10 against torch autograd on the reference's formulas (gail.py:367-408), incl. samples inside and outside
+    the clip range and on both sides of the value clip."""
+    g = torch.Generator().manual_seed(4)
+    M = 5000
+    mu = (0.8 * torch.randn(M, 12, generator=g)).to(DEV).requires_grad_(True)
+    value = torch.randn(M, 1, generator=g).to(DEV).requires_grad_(True)
+    std = (0.5 + torch.rand(12, generator=g)).to(DEV).requires_grad_(True)
+    actions = (mu.detach() + 0.7 * torch.randn(M, 12, generator=g).to(DEV))
+    sigma = mu * 0. + std
+    logp = (-((actions - mu) ** 2) / (2 * sigma ** 2) - torch.log(sigma) - 0.9189385332046727).sum(-1)
+    old_logp = (logp.detach() + 0.3 * torch.randn(M, generator=g).to(DEV))
+    adv = torch.randn(M, generator=g).to(DEV)
+    returns = torch.randn(M, generator=g).to(DEV)
+    tv = value.detach().view(-1) + 0.3 * torch.randn(M, generator=g).to(DEV)
+    old_mu = mu.detach() + 0.1 * torch.randn(M, 12, generator=g).to(DEV)
+    old_sigma = (sigma.detach() * 1.1).contiguous()
+    clip, cs, cv, cb, ce = 0.2, 2.0, 5.0, 0.3, 0.01
+    ratio = torch.exp(logp - old_logp)
+    surr = torch.max(-adv * ratio, -adv * torch.clamp(ratio, 1 - clip, 1 + clip)).mean()
+    v = value.view(-1)
+    vc = tv + (v - tv).clamp(-clip, clip)
+    vl = torch.max((v - returns) ** 2, (vc - returns) ** 2).mean()
+    bl = (torch.clamp(mu + 1, max=0.) ** 2 + torch.clamp(mu - 1, min=0.) ** 2).sum(-1).mean()
+    ent = (1.4189385332046727 + torch.log(sigma)).sum(-1).mean()
+    kl = torch.sum(torch.log(sigma / old_sigma + 1e-5) + (old_sigma ** 2 + (old_mu - mu) ** 2) / (2 * sigma ** 2) - 0.5, -1).mean()
+    (cs * surr + cv * vl + cb * bl - ce * ent).backward()
+    dmu, dvalue = torch.empty(M, 12, device=DEV), torch.empty(M, device=DEV)
+    dstd, stats = torch.empty(12, device=DEV), torch.empty(4, device=DEV)
+    ops.ppo_loss(mu.detach(), std.detach(), value.detach(), actions, old_logp, adv, returns, tv, old_mu, old_sigma, dmu,
+                 dvalue, dstd, stats, clip, cs, cv, cb, ce, True)
+    assert_close("stats", stats, torch.stack([surr, vl, bl, kl]).detach(), rtol=1e-4, atol=1e-6)
+    assert_close("dmu", dmu, mu.grad, rtol=1e-4, atol=1e-8)
+    assert_close("dvalue", dvalue, value.grad.view(-1), rtol=1e-4, atol=1e-8)
+    assert_close("dstd", dstd, std.grad, rtol=1e-3, atol=1e-6)
