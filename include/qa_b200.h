@@ -51,7 +51,7 @@ int qa_version(void);
 /* human readable build string ("sm_100a, nvcc 12.9, ...") */
 const char* qa_build_info(void);
 /* sizeof() of argument struct number `which` (order of declaration in this header, QaActionPushArgs
- * = 0 ... QaGaeArgs = 9, QaGatherArgs = 10, QaClipAdamArgs = 11, QaLinearArgs = 12, QaActBwdArgs = 13, QaPpoLossArgs = 14; -1 if unknown): a layout handshake for FFI mirrors of these structs */
+ * = 0 ... QaGaeArgs = 9, QaGatherArgs = 10, QaClipAdamArgs = 11, QaLinearArgs = 12, QaActBwdArgs = 13, QaPpoLossArgs = 14, QaLinearBwdArgs = 15; -1 if unknown): a layout handshake for FFI mirrors of these structs */
 int qa_struct_size(int which);
 
 /* ------------------------------------------------------------------------------------------
@@ -383,6 +383,20 @@ typedef struct QaLinearArgs {
     int64_t y_pitch;
 } QaLinearArgs;
 int qa_linear_fwd(const QaLinearArgs* a, void* stream);
+
+/* backward contractions of y = x W^T + b on the same tcgen05 kernel with MN-major operands:
+ *   dx  = gz W        (overwritten; skipped when dx == NULL)      -- autograd of actor_critic.py:113-129
+ *   dw += gz^T x      (ACCUMULATED with fp32 atomics over a split of the M reduction; skipped when dw == NULL)
+ * gz is the gradient w.r.t. the pre-activation (K9 output).  Same TMA constraints as qa_linear_fwd. */
+typedef struct QaLinearBwdArgs {
+    int32_t M, N, K;                    /* forward shapes: x (M,K), w (N,K), gz (M,N) */
+    const float* gz; int64_t gz_pitch;
+    const float* x;  int64_t x_pitch;
+    const float* w;  int64_t w_pitch;
+    float* dx;       int64_t dx_pitch;
+    float* dw;       int64_t dw_pitch;
+} QaLinearBwdArgs;
+int qa_linear_bwd(const QaLinearBwdArgs* a, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * K9  gz = gy * act'(y), db = column sums of gz -- the element-wise half of Linear+ELU/ReLU backward

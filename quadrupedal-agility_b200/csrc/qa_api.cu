@@ -30,6 +30,7 @@ extern "C" int qa_struct_size(int which) {
         case 12: return (int)sizeof(QaLinearArgs);
         case 13: return (int)sizeof(QaActBwdArgs);
         case 14: return (int)sizeof(QaPpoLossArgs);
+        case 15: return (int)sizeof(QaLinearBwdArgs);
         default: return -1;
     }
 }

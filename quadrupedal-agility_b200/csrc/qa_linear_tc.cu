@@ -95,6 +95,32 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[32]) {
         : "r"(taddr));
 }
 
+// UMMA shared-memory descriptor, MN-major operand, 128-byte swizzle.  The tile is a set of TMA boxes of 32 floats (the
+// contiguous MN direction, one 128 B swizzle span) x 32 reduction rows = 4096 B each: 8-row reduction groups are
+// 1024 B apart (SBO), consecutive 32-float MN chunks are 4096 B apart (LBO).  `kgroup` selects the 8 reduction rows of
+// one K=8 MMA.
+__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(const void* smem, int kgroup) {
+    const uint32_t addr = (uint32_t)__cvta_generic_to_shared(smem) + (uint32_t)kgroup * 1024u;
+    uint64_t d = 0;
+    d |= (uint64_t)((addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(4096 >> 4) << 16;                // leading byte offset: next 32-float MN chunk
+    d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset: next 8-row reduction group
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// A general tile problem  OUT[Mo, No] (+)= A[Mo, Kred] * B[No, Kred]^T  with each operand either K-major (reduction index
+// contiguous in memory) or MN-major (output index contiguous).
+struct TcProblem {
+    int Mo, No, Kred;
+    int kb_per_split;                   // reduction blocks (of 32) per blockIdx.z
+    float* out;
+    long long out_pitch;
+    const float* bias;                  // store epilogue only
+    int act;
+};
+
 template <int BN>
 struct TcSmem {
     float a[TC_STAGES][TC_BM * TC_BK];      // 16 KB per stage, 1024 B aligned
@@ -105,16 +131,20 @@ struct TcSmem {
     uint32_t tmem_base;
 };
 
-template <int BN>
+enum { EPI_STORE = 0, EPI_ATOMIC = 1 };
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 2)
-k_linear_tf32(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
-              const __grid_constant__ QaLinearArgs g) {
+k_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+            const __grid_constant__ TcProblem g) {
     extern __shared__ unsigned char smem_raw[];
     // 1024 B alignment for the 128 B swizzle atoms
     TcSmem<BN>& S = *reinterpret_cast<TcSmem<BN>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * BN;
-    const int num_kb = (g.K + TC_BK - 1) / TC_BK;
+    const int total_kb = (g.Kred + TC_BK - 1) / TC_BK;
+    const int kb0 = blockIdx.z * g.kb_per_split;
+    const int num_kb = min(g.kb_per_split, total_kb - kb0);
     constexpr unsigned TMEM_COLS = BN < 32 ? 32 : BN;
     constexpr unsigned STAGE_BYTES = (TC_BM + BN) * TC_BK * 4;
 
@@ -141,66 +171,87 @@ k_linear_tf32(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
 
     if (warp == 0) {
         // ===== TMA producer =====
-        if (lane == 0) {
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % TC_STAGES;
-                const unsigned ph = (kb / TC_STAGES) & 1;
+        if (lane == 0 && num_kb > 0) {
+            for (int i = 0; i < num_kb; ++i) {
+                const int kb = kb0 + i;
+                const int s = i % TC_STAGES;
+                const unsigned ph = (i / TC_STAGES) & 1;
                 mbar_wait(&S.empty[s], ph ^ 1);                      // slot free (passes immediately the first time)
                 mbar_arrive_expect_tx(&S.full[s], STAGE_BYTES);
-                tma_load_2d(S.a[s], &map_x, kb * TC_BK, m0, &S.full[s]);
-                tma_load_2d(S.b[s], &map_w, kb * TC_BK, n0, &S.full[s]);
+                if (A_MN) {
+#pragma unroll
+                    for (int c = 0; c < TC_BM / 32; ++c)
+                        tma_load_2d(S.a[s] + c * 1024, &map_a, m0 + c * 32, kb * TC_BK, &S.full[s]);
+                } else {
+                    tma_load_2d(S.a[s], &map_a, kb * TC_BK, m0, &S.full[s]);
+                }
+                if (B_MN) {
+#pragma unroll
+                    for (int c = 0; c < BN / 32; ++c)
+                        tma_load_2d(S.b[s] + c * 1024, &map_b, n0 + c * 32, kb * TC_BK, &S.full[s]);
+                } else {
+                    tma_load_2d(S.b[s], &map_b, kb * TC_BK, n0, &S.full[s]);
+                }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_tf32(BN);
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % TC_STAGES;
-                const unsigned ph = (kb / TC_STAGES) & 1;
+        if (lane == 0 && num_kb > 0) {
+            constexpr uint32_t idesc = umma_idesc_tf32(BN) | (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u);
+            for (int i = 0; i < num_kb; ++i) {
+                const int s = i % TC_STAGES;
+                const unsigned ph = (i / TC_STAGES) & 1;
                 mbar_wait(&S.full[s], ph);                           // TMA bytes have landed
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint64_t adesc = umma_desc_kmajor_sw128(S.a[s]);
-                const uint64_t bdesc = umma_desc_kmajor_sw128(S.b[s]);
 #pragma unroll
-                for (int k = 0; k < TC_BK / 8; ++k)                  // UMMA_K = 8 tf32 = 32 bytes -> +2 in the address field
-                    umma_tf32(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                for (int k = 0; k < TC_BK / 8; ++k) {                // UMMA_K = 8 tf32
+                    const uint64_t adesc = A_MN ? umma_desc_mnmajor_sw128(S.a[s], k) : umma_desc_kmajor_sw128(S.a[s]) + 2 * k;
+                    const uint64_t bdesc = B_MN ? umma_desc_mnmajor_sw128(S.b[s], k) : umma_desc_kmajor_sw128(S.b[s]) + 2 * k;
+                    umma_tf32(tmem_d, adesc, bdesc, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                }
                 umma_commit(&S.empty[s]);                            // frees the slot when these MMAs retire
             }
             umma_commit(&S.tmem_full);                               // accumulator complete
         }
-    } else {
+    } else if (num_kb > 0) {
         // ===== epilogue: warps 2..5 own TMEM lane quadrants (warp % 4) =====
         const int q = warp & 3;
         mbar_wait(&S.tmem_full, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         // The smem ring is idle once tmem_full has fired (every MMA that read it has retired): reuse it as a
-        // per-warp 32x33 transpose buffer so that the global stores are full 128-byte lines (lane = column).
+        // per-warp 32x33 transpose buffer so that the global accesses are full 128-byte lines (lane = column).
         float* stg = reinterpret_cast<float*>(&S.a[0][0]) + q * (32 * 33);
         constexpr int CH = BN >= 32 ? 32 : 16;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += CH) {
-            if (n0 + c0 >= g.N) break;
+            if (n0 + c0 >= g.No) break;
             uint32_t r[32];
             const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
             if (CH == 32) tmem_ld32(taddr, r);
             else tmem_ld16(taddr, r);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-            for (int j = 0; j < CH; ++j) {
-                float x = __uint_as_float(r[j]);
-                const int cc = n0 + c0 + j;
-                if (g.bias != nullptr && cc < g.N) x += __ldg(g.bias + cc);
-                if (g.act == 1) x = x > 0.f ? x : expm1f(x);                    // ELU(alpha = 1)
-                else if (g.act == 2) x = fmaxf(x, 0.f);                         // ReLU
-                stg[lane * 33 + j] = x;
-            }
+            for (int j = 0; j < CH; ++j) stg[lane * 33 + j] = __uint_as_float(r[j]);      // lane = row
             __syncwarp();
-            const int col = n0 + c0 + lane;
-            if (lane < CH && col < g.N) {
-                const int rows = min(32, g.M - (m0 + q * 32));
-                float* yp = g.y + (size_t)(m0 + q * 32) * g.y_pitch + col;
-                for (int rr = 0; rr < rows; ++rr) yp[(size_t)rr * g.y_pitch] = stg[rr * 33 + lane];
+            const int col = n0 + c0 + lane;                                             // lane = column from here on
+            if (lane < CH && col < g.No) {
+                const int rows = min(32, g.Mo - (m0 + q * 32));
+                float* yp = g.out + (size_t)(m0 + q * 32) * g.out_pitch + col;
+                if (EPI == EPI_ATOMIC) {
+                    for (int rr = 0; rr < rows; ++rr) atomicAdd(yp + (size_t)rr * g.out_pitch, stg[rr * 33 + lane]);
+                } else {
+                    const float bcol = g.bias != nullptr ? __ldg(g.bias + col) : 0.f;   // one bias load per lane per chunk
+                    if (g.act == 1) {
+                        for (int rr = 0; rr < rows; ++rr) {
+                            const float x = stg[rr * 33 + lane] + bcol;
+                            yp[(size_t)rr * g.out_pitch] = x > 0.f ? x : expm1f(x);     // ELU(alpha = 1)
+                        }
+                    } else if (g.act == 2) {
+                        for (int rr = 0; rr < rows; ++rr) yp[(size_t)rr * g.out_pitch] = fmaxf(stg[rr * 33 + lane] + bcol, 0.f);
+                    } else {
+                        for (int rr = 0; rr < rows; ++rr) yp[(size_t)rr * g.out_pitch] = stg[rr * 33 + lane] + bcol;
+                    }
+                }
             }
             __syncwarp();
         }
@@ -244,25 +295,35 @@ static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t c
     return r == CUDA_SUCCESS ? 0 : QA_EINVAL;
 }
 
-template <int BN>
-static int launch_linear(const QaLinearArgs* g, cudaStream_t stream) {
-    CUtensorMap mx, mw;
-    int rc = make_map(&mx, g->x, g->M, g->K, g->x_pitch, TC_BM);
+// Operand description for the launcher: a row-major 2-D tensor (rows, cols, pitch).  K-major operand: rows = output index,
+// cols = reduction index.  MN-major operand: rows = reduction index, cols = output index.
+struct TcOperand {
+    const float* base;
+    int64_t rows, cols, pitch;
+};
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
+static int launch_gemm(const TcOperand& A, const TcOperand& B, const TcProblem& prob, int splits, cudaStream_t stream) {
+    CUtensorMap ma, mb;
+    int rc = make_map(&ma, A.base, A.rows, A.cols, A.pitch, A_MN ? 32 : TC_BM);
     if (rc) return rc;
-    rc = make_map(&mw, g->w, g->N, g->K, g->w_pitch, BN);
+    rc = make_map(&mb, B.base, B.rows, B.cols, B.pitch, B_MN ? 32 : BN);
     if (rc) return rc;
     const size_t smem = sizeof(TcSmem<BN>) + 1024;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_linear_tf32<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_gemm_tf32<BN, A_MN, B_MN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
-    dim3 grid((g->M + TC_BM - 1) / TC_BM, (g->N + BN - 1) / BN);
-    k_linear_tf32<BN><<<grid, TC_THREADS, smem, stream>>>(mx, mw, *g);
+    dim3 grid((prob.Mo + TC_BM - 1) / TC_BM, (prob.No + BN - 1) / BN, splits);
+    k_gemm_tf32<BN, A_MN, B_MN, EPI><<<grid, TC_THREADS, smem, stream>>>(ma, mb, prob);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : (int)e;
 }
+
+static bool tma_ok(const void* p, int64_t pitch) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0 && (pitch & 3) == 0; }
 
 extern "C" int qa_linear_fwd(const QaLinearArgs* g, void* stream) {
     QA_CHECK_PTR(g);
@@ -273,13 +334,54 @@ extern "C" int qa_linear_fwd(const QaLinearArgs* g, void* stream) {
     if (g->M < 0 || g->N <= 0 || g->K <= 0) return QA_EINVAL;
     if (g->act < 0 || g->act > 2) return QA_EINVAL;
     // TMA constraints: 16 B aligned bases and row pitches
-    if ((g->x_pitch & 3) || (g->w_pitch & 3) || (reinterpret_cast<uintptr_t>(g->x) & 15u) ||
-        (reinterpret_cast<uintptr_t>(g->w) & 15u) || g->x_pitch < g->K || g->w_pitch < g->K || g->y_pitch < g->N)
+    if (!tma_ok(g->x, g->x_pitch) || !tma_ok(g->w, g->w_pitch) || g->x_pitch < g->K || g->w_pitch < g->K || g->y_pitch < g->N)
         return QA_EINVAL;
     cudaStream_t s = (cudaStream_t)stream;
+    const TcOperand A{g->x, g->M, g->K, g->x_pitch}, B{g->w, g->N, g->K, g->w_pitch};
+    TcProblem p{g->M, g->N, g->K, (g->K + TC_BK - 1) / TC_BK, g->y, g->y_pitch, g->bias, g->act};
     const int n = g->N;
-    if (n <= 16) return launch_linear<16>(g, s);
-    if (n <= 32) return launch_linear<32>(g, s);
-    if (n <= 64) return launch_linear<64>(g, s);
-    return launch_linear<128>(g, s);
+    if (n <= 16) return launch_gemm<16, false, false, EPI_STORE>(A, B, p, 1, s);
+    if (n <= 32) return launch_gemm<32, false, false, EPI_STORE>(A, B, p, 1, s);
+    if (n <= 64) return launch_gemm<64, false, false, EPI_STORE>(A, B, p, 1, s);
+    return launch_gemm<128, false, false, EPI_STORE>(A, B, p, 1, s);
+}
+
+// Backward of y = x W^T (+ b):  dx = gz W   (A = gz K-major, B = W MN-major, reduction over N)
+//                               dw += gz^T x (A = gz MN-major, B = x MN-major, reduction over M, split-K + atomics)
+extern "C" int qa_linear_bwd(const QaLinearBwdArgs* g, void* stream) {
+    QA_CHECK_PTR(g);
+    if (g->M == 0) return 0;
+    QA_CHECK_PTR(g->gz);
+    if (g->M < 0 || g->N <= 0 || g->K <= 0) return QA_EINVAL;
+    if (!tma_ok(g->gz, g->gz_pitch) || g->gz_pitch < g->N) return QA_EINVAL;
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = 0;
+    if (g->dx != nullptr) {
+        QA_CHECK_PTR(g->w);
+        if (!tma_ok(g->w, g->w_pitch) || g->w_pitch < g->K || g->dx_pitch < g->K) return QA_EINVAL;
+        const TcOperand A{g->gz, g->M, g->N, g->gz_pitch}, B{g->w, g->N, g->K, g->w_pitch};
+        TcProblem p{g->M, g->K, g->N, (g->N + TC_BK - 1) / TC_BK, g->dx, g->dx_pitch, nullptr, 0};
+        if (g->K <= 32) rc = launch_gemm<32, false, true, EPI_STORE>(A, B, p, 1, s);
+        else if (g->K <= 64) rc = launch_gemm<64, false, true, EPI_STORE>(A, B, p, 1, s);
+        else rc = launch_gemm<128, false, true, EPI_STORE>(A, B, p, 1, s);
+        if (rc) return rc;
+    }
+    if (g->dw != nullptr) {
+        QA_CHECK_PTR(g->x);
+        if (!tma_ok(g->x, g->x_pitch) || g->x_pitch < g->K || g->dw_pitch < g->K) return QA_EINVAL;
+        const TcOperand A{g->gz, g->M, g->N, g->gz_pitch}, B{g->x, g->M, g->K, g->x_pitch};
+        const int total_kb = (g->M + TC_BK - 1) / TC_BK;
+        const int bn = g->K <= 32 ? 32 : (g->K <= 64 ? 64 : 128);
+        const int tiles = ((g->N + TC_BM - 1) / TC_BM) * ((g->K + bn - 1) / bn);
+        int splits = (2 * 148 + tiles - 1) / tiles;
+        if (splits > total_kb) splits = total_kb;
+        if (splits < 1) splits = 1;
+        const int per = (total_kb + splits - 1) / splits;
+        splits = (total_kb + per - 1) / per;
+        TcProblem p{g->N, g->K, g->M, per, g->dw, g->dw_pitch, nullptr, 0};
+        if (bn == 32) rc = launch_gemm<32, true, true, EPI_ATOMIC>(A, B, p, splits, s);
+        else if (bn == 64) rc = launch_gemm<64, true, true, EPI_ATOMIC>(A, B, p, splits, s);
+        else rc = launch_gemm<128, true, true, EPI_ATOMIC>(A, B, p, splits, s);
+    }
+    return rc;
 }

@@ -143,6 +143,12 @@ class QaPpoLossArgs(C.Structure):
                 ("use_clipped_value_loss", C.c_int32), ("dmu", vp), ("dvalue", vp), ("dstd", vp), ("stats", vp)]
 
 
+class QaLinearBwdArgs(C.Structure):
+    _fields_ = [("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("gz", vp), ("gz_pitch", C.c_int64), ("x", vp),
+                ("x_pitch", C.c_int64), ("w", vp), ("w_pitch", C.c_int64), ("dx", vp), ("dx_pitch", C.c_int64),
+                ("dw", vp), ("dw_pitch", C.c_int64)]
+
+
 # every symbol `include/qa_b200.h` declares: name -> (restype, argtypes)
 SYMBOLS = {
     "qa_version": (C.c_int, []),
@@ -158,12 +164,13 @@ SYMBOLS = {
     "qa_gather_minibatch": (C.c_int, [C.POINTER(QaGatherArgs), vp]),
     "qa_clip_adam": (C.c_int, [C.POINTER(QaClipAdamArgs), vp]),
     "qa_linear_fwd": (C.c_int, [C.POINTER(QaLinearArgs), vp]),
+    "qa_linear_bwd": (C.c_int, [C.POINTER(QaLinearBwdArgs), vp]),
     "qa_act_bwd": (C.c_int, [C.POINTER(QaActBwdArgs), vp]),
     "qa_ppo_loss": (C.c_int, [C.POINTER(QaPpoLossArgs), vp]),
 }
 
 STRUCT_ORDER = [QaActionPushArgs, QaTorqueArgs, QaTerrain, QaHeightScanArgs, QaMocapTable, QaMocapBlendArgs,
-                QaBbcConst, QaBbcStepArgs, QaCompactArgs, QaGaeArgs, QaGatherArgs, QaClipAdamArgs, QaLinearArgs, QaActBwdArgs, QaPpoLossArgs]
+                QaBbcConst, QaBbcStepArgs, QaCompactArgs, QaGaeArgs, QaGatherArgs, QaClipAdamArgs, QaLinearArgs, QaActBwdArgs, QaPpoLossArgs, QaLinearBwdArgs]
 
 _LIB = None
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libqa_b200.so")

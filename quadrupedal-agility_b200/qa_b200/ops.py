@@ -200,6 +200,26 @@ def linear_fwd(x, weight, bias, y, act) -> None:
     _count(1)
 
 
+def linear_bwd(gz, x, weight, dx=None, dw=None) -> None:
+    """dx = gz @ weight (overwritten) and/or dw += gz.T @ x (accumulated) on the tcgen05 kernel, MN-major operands."""
+    lib = _abi.load()
+    M, N = gz.shape
+    K = weight.shape[1] if weight is not None else x.shape[1]
+    a = _abi.QaLinearBwdArgs(M, N, K, gz.data_ptr(), gz.stride(0),
+                             None if x is None else x.data_ptr(), 0 if x is None else x.stride(0),
+                             None if weight is None else weight.data_ptr(), 0 if weight is None else weight.stride(0),
+                             None if dx is None else dx.data_ptr(), 0 if dx is None else dx.stride(0),
+                             None if dw is None else dw.data_ptr(), 0 if dw is None else dw.stride(0))
+    _abi.check(lib.qa_linear_bwd(C.byref(a), _stream()), "qa_linear_bwd")
+    _count((dx is not None) + (dw is not None))
+
+
+def linear_bwd_ok(gz, x, weight) -> bool:
+    ok = lambda t: (t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.stride(1) == 1 and   # noqa: E731
+                    t.stride(0) % 4 == 0 and t.data_ptr() % 16 == 0)
+    return ok(gz) and ok(x) and ok(weight) and gz.shape[0] > 0
+
+
 # ---- K9 ---------------------------------------------------------------------------------------
 def act_bwd(gy, y, act, gz=None, db=None, zero_db=True) -> None:
     """gz = gy * act'(y) (ELU' from the saved output: 1 if y > 0 else y + 1) and/or db = gz.sum(0)."""
