@@ -95,18 +95,19 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[32]) {
         : "r"(taddr));
 }
 
-// UMMA shared-memory descriptor, MN-major operand, 128-byte swizzle.  The tile is a set of TMA boxes of 32 floats (the
-// contiguous MN direction, one 128 B swizzle span) x 32 reduction rows = 4096 B each: 8-row reduction groups are
-// 1024 B apart (SBO), consecutive 32-float MN chunks are 4096 B apart (LBO).  `kgroup` selects the 8 reduction rows of
-// one K=8 MMA.
+// UMMA shared-memory descriptor, MN-major 32-bit operand.  For tf32 the only MN-major layout the tensor core accepts
+// is SWIZZLE_128B_BASE32B: 128-byte rows, 4-row atoms, the 32-byte chunk index XORed with (row & 3) -- what TMA writes
+// with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  The tile is a set of TMA boxes of 32 floats (the contiguous MN direction)
+// x 32 reduction rows = 4096 B each: 4-row reduction atoms are 512 B apart (SBO), consecutive 32-float MN chunks are
+// 4096 B apart (LBO).  `kgroup` selects the 8 reduction rows of one K=8 MMA.
 __device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(const void* smem, int kgroup) {
     const uint32_t addr = (uint32_t)__cvta_generic_to_shared(smem) + (uint32_t)kgroup * 1024u;
     uint64_t d = 0;
     d |= (uint64_t)((addr & 0x3FFFF) >> 4);
     d |= (uint64_t)(4096 >> 4) << 16;                // leading byte offset: next 32-float MN chunk
-    d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset: next 8-row reduction group
+    d |= (uint64_t)(512 >> 4) << 32;                 // stride byte offset: next 4-row reduction atom
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)1 << 61;                          // layout type SWIZZLE_128B_BASE32B
     return d;
 }
 
@@ -282,7 +283,8 @@ static PFN_encodeTiled get_encode() {
 }
 
 // 2-D fp32 tensor (rows, cols) with `pitch` floats per row; box = (box_rows, 32 floats), 128 B swizzle, zero OOB fill
-static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t pitch, int box_rows) {
+static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t pitch, int box_rows,
+                    bool mn_major) {
     PFN_encodeTiled enc = get_encode();
     if (enc == nullptr) return QA_EINVAL;
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -290,7 +292,9 @@ static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t c
     cuuint32_t box[2] = {TC_BK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : QA_EINVAL;
 }
@@ -305,9 +309,9 @@ struct TcOperand {
 template <int BN, bool A_MN, bool B_MN, int EPI>
 static int launch_gemm(const TcOperand& A, const TcOperand& B, const TcProblem& prob, int splits, cudaStream_t stream) {
     CUtensorMap ma, mb;
-    int rc = make_map(&ma, A.base, A.rows, A.cols, A.pitch, A_MN ? 32 : TC_BM);
+    int rc = make_map(&ma, A.base, A.rows, A.cols, A.pitch, A_MN ? 32 : TC_BM, A_MN);
     if (rc) return rc;
-    rc = make_map(&mb, B.base, B.rows, B.cols, B.pitch, B_MN ? 32 : BN);
+    rc = make_map(&mb, B.base, B.rows, B.cols, B.pitch, B_MN ? 32 : BN, B_MN);
     if (rc) return rc;
     const size_t smem = sizeof(TcSmem<BN>) + 1024;
     static bool attr_set = false;

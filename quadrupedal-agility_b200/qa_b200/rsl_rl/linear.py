@@ -2,9 +2,10 @@
 
 Forward: the hand-written tcgen05 kernel `qa_linear_fwd` (K7: TMA-fed, TF32 operands, fp32 accumulate in TMEM, bias +
 ELU/ReLU fused in the epilogue) whenever the operands satisfy TMA's 16-byte pitch/alignment rules -- `FlatParams`
-lays the weights out so that they do.  Backward (training) reuses the saved OUTPUT for the activation derivative
-(ELU'(z) = y + 1 for z <= 0) and contracts through cuBLAS (dX = dZ W, dW = dZ^T X); porting the two MN-major backward
-contractions to tcgen05 is the next step.
+lays the weights out so that they do.  Backward: K9 turns the upstream gradient into the pre-activation gradient from
+the saved OUTPUT (ELU'(z) = y + 1 for z <= 0) and reduces the bias gradient in the same pass; `qa_linear_bwd` runs
+dX = dZ W and dW += dZ^T X on the same tcgen05 kernel with MN-major operands (dW: split-K over the batch, fp32 atomics
+straight into the flat gradient buffer).  Layers whose widths break the 16-byte rule (N = 1, 29) fall back to cuBLAS.
 
 `set_mode("fp32")` routes everything through `F.linear` in full fp32 -- the parity-test path.
 """
@@ -51,8 +52,26 @@ class _LinearActTC(torch.autograd.Function):
             gz = gy
             if want_b:
                 ops.act_bwd(gy, None, None, gz=None, db=gb)
-        gx = gz @ weight if ctx.needs_input_grad[0] else None
-        gw = gz.t() @ x if ctx.needs_input_grad[1] else None
+        need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if ops.linear_bwd_ok(gz, x, weight):
+            # both contractions on the tcgen05 kernel (MN-major operands); dW is accumulated by the kernel's split-K
+            # atomics straight into the flat gradient buffer when the weight lives in one
+            gx = torch.empty(x.shape[0], x.shape[1], device=x.device, dtype=torch.float32) if need_x else None
+            gw = None
+            dw_target = None
+            if need_w:
+                if weight.grad is not None and weight.grad.stride(1) == 1 and weight.grad.stride(0) % 4 == 0:
+                    dw_target = weight.grad
+                else:
+                    kp = (weight.shape[1] + 3) // 4 * 4
+                    gw = torch.zeros(weight.shape[0], kp, device=x.device, dtype=torch.float32)[:, :weight.shape[1]]
+                    dw_target = gw
+            if gx is not None or dw_target is not None:
+                ops.linear_bwd(gz, x if dw_target is not None else None, weight if gx is not None else None,
+                               dx=gx, dw=dw_target)
+            return gx, gw, gb, None
+        gx = gz @ weight if need_x else None
+        gw = gz.t() @ x if need_w else None
         return gx, gw, gb, None
 
 

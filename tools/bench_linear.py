@@ -18,19 +18,39 @@ SHAPES = [(24576, 512, 671), (24576, 512, 101), (24576, 256, 512), (24576, 128, 
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
 
-def timeit(fn, reps=20):
-    for _ in range(3):
-        fn()
+def graph_time(body, reps=10):
+    """us per replay of a CUDA graph holding `body` (no host launch gaps inside the measurement)."""
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        body()
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        body()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    tot = 0.0
+    g.replay()
+    torch.cuda.synchronize()
+    e0.record()
     for _ in range(reps):
-        flush.fill_(0)
-        e0.record()
-        fn()
-        e1.record()
-        e1.synchronize()
-        tot += e0.elapsed_time(e1)
-    return tot / reps * 1e3
+        g.replay()
+    e1.record()
+    e1.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e3
+
+
+NCALL = 8
+T_FLUSH = graph_time(lambda: [flush.fill_(0) for _ in range(NCALL)])
+
+
+def timeit(fn):
+    """us per call, L2 flushed before every call (flush time measured separately and subtracted)."""
+    def body():
+        for _ in range(NCALL):
+            flush.fill_(0)
+            fn()
+    return (graph_time(body) - T_FLUSH) / NCALL
 
 
 print(f"{'M':>6} {'N':>4} {'K':>4} | {'tcgen05 us':>10} {'TF/s':>7} | {'cuBLAS+elu us':>13} {'TF/s':>7} | {'GB/s(tc)':>9}")
@@ -45,3 +65,18 @@ for M, N, K in SHAPES:
     fl = 2.0 * M * N * K
     by = 4.0 * (M * K + N * K + M * N)
     print(f"{M:6d} {N:4d} {K:4d} | {t_tc:10.1f} {fl / t_tc / 1e6:7.1f} | {t_cb:13.1f} {fl / t_cb / 1e6:7.1f} | {by / t_tc / 1e3:9.0f}")
+
+print()
+print(f"{'M':>6} {'N':>4} {'K':>4} | {'tc dx us':>9} {'tc dw us':>9} | {'cuBLAS dx':>9} {'cuBLAS dw':>9}")
+for M, N, K in [(24576, 512, 671), (24576, 512, 101), (24576, 256, 512), (24576, 128, 256), (24576, 12, 128), (24576, 64, 128)]:
+    kp = (K + 3) // 4 * 4
+    x = torch.randn(M, kp, device=dev)[:, :K]
+    w = (torch.randn(N, kp, device=dev) / K ** 0.5)[:, :K]
+    gz = torch.randn(M, N, device=dev)
+    dx = torch.empty(M, K, device=dev)
+    dw = torch.zeros(N, kp, device=dev)[:, :K]
+    t1 = timeit(lambda: ops.linear_bwd(gz, None, w, dx=dx))
+    t2 = timeit(lambda: ops.linear_bwd(gz, x, None, dw=dw))
+    t3 = timeit(lambda: torch.matmul(gz, w))
+    t4 = timeit(lambda: torch.matmul(gz.t(), x))
+    print(f"{M:6d} {N:4d} {K:4d} | {t1:9.1f} {t2:9.1f} | {t3:9.1f} {t4:9.1f}")
