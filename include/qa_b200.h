@@ -51,7 +51,7 @@ int qa_version(void);
 /* human readable build string ("sm_100a, nvcc 12.9, ...") */
 const char* qa_build_info(void);
 /* sizeof() of argument struct number `which` (order of declaration in this header, QaActionPushArgs
- * = 0 ... QaGaeArgs = 9, QaGatherArgs = 10, QaClipAdamArgs = 11, QaLinearArgs = 12, QaActBwdArgs = 13, QaPpoLossArgs = 14, QaLinearBwdArgs = 15; -1 if unknown): a layout handshake for FFI mirrors of these structs */
+ * = 0 ... QaGaeArgs = 9, QaGatherArgs = 10, QaClipAdamArgs = 11, QaLinearArgs = 12, QaActBwdArgs = 13, QaPpoLossArgs = 14, QaLinearBwdArgs = 15, QaHistEncArgs = 16; -1 if unknown): a layout handshake for FFI mirrors of these structs */
 int qa_struct_size(int which);
 
 /* ------------------------------------------------------------------------------------------
@@ -441,6 +441,24 @@ typedef struct QaPpoLossArgs {
     float* stats;                       /* (QA_PPO_STATS) */
 } QaPpoLossArgs;
 int qa_ppo_loss(const QaPpoLossArgs* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K11 StateHistoryEncoder forward, fused (tsteps = 10, ELU): Linear(57->30) per step, Conv1d(30->20,k4,s2),
+ *     Conv1d(20->10,k2), Flatten, Linear(30->29) -- replaces bbc/rsl_rl/modules/actor_critic.py:51-59
+ *     (StateHistoryEncoder.forward) as used by infer_hist_latent (:219-220).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct QaHistEncArgs {
+    int64_t M;
+    const float* hist; int64_t hist_pitch;     /* (M, 570) = (M, 10, 57), e.g. obs + 90 with the obs pitch */
+    const float* w0; int64_t w0_pitch;         /* encoder.0.weight (30,57) */
+    const float* b0;                           /* (30) */
+    const float* w1; const float* b1;          /* conv_layers.0 weight (20,30,4) contiguous, bias (20) */
+    const float* w2; const float* b2;          /* conv_layers.2 weight (10,20,2) contiguous, bias (10) */
+    const float* w3; int64_t w3_pitch;         /* linear_output.0.weight (29,30) */
+    const float* b3;                           /* (29) */
+    float* out; int64_t out_pitch;             /* (M,29) */
+} QaHistEncArgs;
+int qa_hist_encoder_fwd(const QaHistEncArgs* a, void* stream);
 
 #ifdef __cplusplus
 }

@@ -31,6 +31,7 @@ extern "C" int qa_struct_size(int which) {
         case 13: return (int)sizeof(QaActBwdArgs);
         case 14: return (int)sizeof(QaPpoLossArgs);
         case 15: return (int)sizeof(QaLinearBwdArgs);
+        case 16: return (int)sizeof(QaHistEncArgs);
         default: return -1;
     }
 }

@@ -149,6 +149,12 @@ class QaLinearBwdArgs(C.Structure):
                 ("dw", vp), ("dw_pitch", C.c_int64)]
 
 
+class QaHistEncArgs(C.Structure):
+    _fields_ = [("M", C.c_int64), ("hist", vp), ("hist_pitch", C.c_int64), ("w0", vp), ("w0_pitch", C.c_int64),
+                ("b0", vp), ("w1", vp), ("b1", vp), ("w2", vp), ("b2", vp), ("w3", vp), ("w3_pitch", C.c_int64),
+                ("b3", vp), ("out", vp), ("out_pitch", C.c_int64)]
+
+
 # every symbol `include/qa_b200.h` declares: name -> (restype, argtypes)
 SYMBOLS = {
     "qa_version": (C.c_int, []),
@@ -166,11 +172,12 @@ SYMBOLS = {
     "qa_linear_fwd": (C.c_int, [C.POINTER(QaLinearArgs), vp]),
     "qa_linear_bwd": (C.c_int, [C.POINTER(QaLinearBwdArgs), vp]),
     "qa_act_bwd": (C.c_int, [C.POINTER(QaActBwdArgs), vp]),
+    "qa_hist_encoder_fwd": (C.c_int, [C.POINTER(QaHistEncArgs), vp]),
     "qa_ppo_loss": (C.c_int, [C.POINTER(QaPpoLossArgs), vp]),
 }
 
 STRUCT_ORDER = [QaActionPushArgs, QaTorqueArgs, QaTerrain, QaHeightScanArgs, QaMocapTable, QaMocapBlendArgs,
-                QaBbcConst, QaBbcStepArgs, QaCompactArgs, QaGaeArgs, QaGatherArgs, QaClipAdamArgs, QaLinearArgs, QaActBwdArgs, QaPpoLossArgs, QaLinearBwdArgs]
+                QaBbcConst, QaBbcStepArgs, QaCompactArgs, QaGaeArgs, QaGatherArgs, QaClipAdamArgs, QaLinearArgs, QaActBwdArgs, QaPpoLossArgs, QaLinearBwdArgs, QaHistEncArgs]
 
 _LIB = None
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libqa_b200.so")

@@ -220,6 +220,23 @@ def linear_bwd_ok(gz, x, weight) -> bool:
     return ok(gz) and ok(x) and ok(weight) and gz.shape[0] > 0
 
 
+# ---- K11 --------------------------------------------------------------------------------------
+def hist_encoder_fwd(hist, enc, out) -> None:
+    """StateHistoryEncoder.forward (tsteps=10, ELU) in one kernel.  hist: (M,570) view; enc: the module."""
+    lib = _abi.load()
+    f = torch.float32
+    w0, w3 = enc.encoder[0].weight, enc.linear_output[0].weight
+    w1, w2 = enc.conv_layers[0].weight, enc.conv_layers[2].weight
+    if hist.stride(1) != 1 or out.stride(1) != 1 or w0.stride(1) != 1 or w3.stride(1) != 1:
+        raise RuntimeError("qa_hist_encoder_fwd: unit inner strides required")
+    a = _abi.QaHistEncArgs(hist.shape[0], hist.data_ptr(), hist.stride(0), w0.data_ptr(), w0.stride(0),
+                           _p(enc.encoder[0].bias, f, "b0"), _p(w1, f, "w1"), _p(enc.conv_layers[0].bias, f, "b1"),
+                           _p(w2, f, "w2"), _p(enc.conv_layers[2].bias, f, "b2"), w3.data_ptr(), w3.stride(0),
+                           _p(enc.linear_output[0].bias, f, "b3"), out.data_ptr(), out.stride(0))
+    _abi.check(lib.qa_hist_encoder_fwd(C.byref(a), _stream()), "qa_hist_encoder_fwd")
+    _count(1)
+
+
 # ---- K9 ---------------------------------------------------------------------------------------
 def act_bwd(gy, y, act, gz=None, db=None, zero_db=True) -> None:
     """gz = gy * act'(y) (ELU' from the saved output: 1 if y > 0 else y + 1) and/or db = gz.sum(0)."""

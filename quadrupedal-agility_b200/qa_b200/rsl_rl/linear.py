@@ -28,10 +28,25 @@ def get_mode() -> str:
     return _MODE
 
 
+def _padded(rows: int, cols: int, device) -> torch.Tensor:
+    """(rows, cols) fp32 view whose row pitch is a multiple of 4 floats (16 B): a legal TMA operand."""
+    return torch.empty(rows, (cols + 3) // 4 * 4, device=device, dtype=torch.float32)[:, :cols]
+
+
+def _tma_operand(x: torch.Tensor) -> torch.Tensor:
+    """x itself when it already satisfies TMA's base/pitch alignment, else an aligned copy (odd-width inputs such as the
+    29 latent lanes sliced out of the observation row, or the 98-wide discriminator input)."""
+    if x.stride(1) == 1 and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0:
+        return x
+    v = _padded(x.shape[0], x.shape[1], x.device)
+    v.copy_(x)
+    return v
+
+
 class _LinearActTC(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, act):
-        y = torch.empty(x.shape[0], weight.shape[0], device=x.device, dtype=torch.float32)
+        y = _padded(x.shape[0], weight.shape[0], x.device)
         ops.linear_fwd(x, weight, bias, y, act)
         ctx.act = act
         ctx.has_bias = bias is not None
@@ -45,9 +60,10 @@ class _LinearActTC(torch.autograd.Function):
             gy = gy.contiguous()
         want_b = ctx.has_bias and ctx.needs_input_grad[2]
         gb = torch.empty(weight.shape[0], device=gy.device, dtype=torch.float32) if want_b else None
-        if ctx.act in ("elu", "relu"):
-            gz = torch.empty_like(gy)
-            ops.act_bwd(gy, y, ctx.act, gz=gz, db=gb)            # K9: act'(y) and the bias gradient in one pass
+        aligned = gy.stride(0) % 4 == 0 and gy.data_ptr() % 16 == 0
+        if ctx.act in ("elu", "relu") or not aligned:
+            gz = _padded(gy.shape[0], gy.shape[1], gy.device)   # K9: act'(y) and the bias gradient in one pass
+            ops.act_bwd(gy, y if ctx.act else None, ctx.act, gz=gz, db=gb)
         else:
             gz = gy
             if want_b:
@@ -76,8 +92,10 @@ class _LinearActTC(torch.autograd.Function):
 
 
 def linear_act(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, act):
-    if _MODE == "tc" and ops.linear_tc_ok(x, weight):
-        return _LinearActTC.apply(x, weight, bias, act)
+    if _MODE == "tc" and x.is_cuda and x.dim() == 2 and x.shape[0] > 0:
+        xa = _tma_operand(x)
+        if ops.linear_tc_ok(xa, weight):
+            return _LinearActTC.apply(xa, weight, bias, act)
     y = F.linear(x, weight, bias)
     if act == "elu":
         return F.elu(y)

@@ -231,7 +231,15 @@ class ActorCritic(nn.Module):
         return run_mlp(self.priv_encoder, obs) if not isinstance(self.priv_encoder, nn.Identity) else obs
 
     def infer_hist_latent(self, obs):
-        return self.history_encoder(obs.view(-1, self.num_hist, self.num_prop))
+        enc = self.history_encoder
+        fused_ok = (obs.is_cuda and not torch.is_grad_enabled() and obs.dim() == 2 and obs.stride(1) == 1
+                    and enc.tsteps == 10 and self.activation_name == "elu" and self.num_prop == 57)
+        if fused_ok:                                      # K11: forward only (inference / no-grad uses)
+            from .. import ops
+            out = torch.empty(obs.shape[0], self.num_latent, device=obs.device, dtype=torch.float32)
+            ops.hist_encoder_fwd(obs, enc, out)
+            return out
+        return enc(obs.reshape(-1, self.num_hist, self.num_prop))
 
     def evaluate(self, critic_observations, **kwargs):
         return linear_act(run_mlp(self.critic_trunk, critic_observations), self.critic_head.weight,

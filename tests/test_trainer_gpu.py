@@ -208,3 +208,23 @@ def test_ppo_loss_kernel_matches_autograd():
     assert_close("dmu", dmu, mu.grad, rtol=1e-4, atol=1e-8)
     assert_close("dvalue", dvalue, value.grad.view(-1), rtol=1e-4, atol=1e-8)
     assert_close("dstd", dstd, std.grad, rtol=1e-3, atol=1e-6)
+
+
+def test_fused_history_encoder_matches_module():
+    """K11 against the (reference-named) torch module it replaces, incl. a ragged tail block and the obs-row view."""
+    w = synthetic.make_weights(5)
+    ac = ActorCritic(101, 671, 12, 57, 10, 4, 29, 11, **bbc_train_cfg()["policy"]).to(DEV)
+    ac.load_state_dict(w["ac"])
+    ac.flatten_parameters()
+    g = torch.Generator().manual_seed(8)
+    for M in (24576, 4096, 37):
+        obs = torch.randn(M, 672, generator=g).to(DEV)[:, :671]
+        hist = obs[:, 90:660]
+        with torch.no_grad():
+            got = ac.infer_hist_latent(hist)                                    # fused kernel
+            want = ac.history_encoder(hist.reshape(-1, 10, 57))                  # cuBLAS + cuDNN path
+        assert got.shape == want.shape == (M, 29)
+        assert_close(f"hist latent M={M}", got, want, rtol=1e-4, atol=1e-5)
+    with torch.enable_grad():                                                   # gradients requested -> module path
+        out = ac.infer_hist_latent(hist)
+        assert out.requires_grad
