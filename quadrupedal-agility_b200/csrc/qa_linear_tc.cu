@@ -15,8 +15,10 @@
 //   warp 1      allocates TMEM (BN fp32 columns) and issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=BN, K=8) from
 //               one elected lane, 4 MMAs per 32-float K block; tcgen05.commit releases ring slots and finally signals
 //               the epilogue.
-//   warps 2..5  epilogue: tcgen05.ld 32x32b (lane = output row) -> bias + activation in registers -> 16-byte global
-//               stores of the row segment.
+//   warps 2..5  epilogue: tcgen05.ld 32x32b (lane = output row) -> bias + activation in registers -> swizzled 32x32
+//               slab in shared memory -> TMA store (cp.async.bulk.tensor, or cp.reduce...add for split-K partial sums).
+// The kernel is persistent (grid = min(#tiles, #SMs)) with two TMEM accumulators, so the epilogue of one tile overlaps
+// the main loop of the next.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -122,39 +124,66 @@ struct TcProblem {
     int act;
 };
 
-template <int BN>
+template <int BN, int STAGES>
 struct TcSmem {
-    float a[TC_STAGES][TC_BM * TC_BK];      // 16 KB per stage, 1024 B aligned
-    float b[TC_STAGES][BN * TC_BK];
-    uint64_t full[TC_STAGES];
-    uint64_t empty[TC_STAGES];
-    uint64_t tmem_full;
+    float a[STAGES][TC_BM * TC_BK];         // 16 KB per stage, 1024 B aligned
+    float b[STAGES][BN * TC_BK];
+    float stg[4][2][32 * 32];               // per-epilogue-warp, double-buffered 32 x 32 output slabs (TMA store source)
+    float bias_s[4][BN];                    // per-epilogue-warp copy of the tile's bias slice
+    uint64_t full[STAGES];
+    uint64_t empty[STAGES];
+    uint64_t tmem_full[2];
+    uint64_t tmem_empty[2];
     uint32_t tmem_base;
 };
 
 enum { EPI_STORE = 0, EPI_ATOMIC = 1 };
 
-template <int BN, bool A_MN, bool B_MN, int EPI>
-__global__ void __launch_bounds__(TC_THREADS, 2)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* ssrc, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const void* ssrc, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+
+// Persistent, warp-specialised tile loop.  grid = min(#work items, #SMs); a work item is (m tile, n tile, K split).
+// Two TMEM accumulators (2 x BN columns) let the epilogue of item i overlap the main loop of item i+1; the shared-memory
+// ring keeps streaming across items.
+template <int BN, int STAGES, bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(TC_THREADS, 1)
 k_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-            const __grid_constant__ TcProblem g) {
+            const __grid_constant__ CUtensorMap map_y, const __grid_constant__ TcProblem g) {
     extern __shared__ unsigned char smem_raw[];
     // 1024 B alignment for the 128 B swizzle atoms
-    TcSmem<BN>& S = *reinterpret_cast<TcSmem<BN>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    using Smem = TcSmem<BN, STAGES>;
+    Smem& S = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * BN;
+    const int tiles_m = (g.Mo + TC_BM - 1) / TC_BM, tiles_n = (g.No + BN - 1) / BN;
     const int total_kb = (g.Kred + TC_BK - 1) / TC_BK;
-    const int kb0 = blockIdx.z * g.kb_per_split;
-    const int num_kb = min(g.kb_per_split, total_kb - kb0);
-    constexpr unsigned TMEM_COLS = BN < 32 ? 32 : BN;
+    const int splits = (total_kb + g.kb_per_split - 1) / g.kb_per_split;
+    const int total_items = tiles_m * tiles_n * splits;
+    constexpr unsigned TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
     constexpr unsigned STAGE_BYTES = (TC_BM + BN) * TC_BK * 4;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) {
+        for (int s = 0; s < STAGES; ++s) {
             mbar_init(&S.full[s], 1);
             mbar_init(&S.empty[s], 1);
         }
-        mbar_init(&S.tmem_full, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&S.tmem_full[a], 1);
+            mbar_init(&S.tmem_empty[a], 4);                          // one arrive per epilogue warp
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -170,92 +199,138 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = S.tmem_base;
 
+    // work item -> (split, m tile, n tile); n fastest so that CTAs running concurrently share the A rows in L2
+    auto decode = [&](int w, int& m0, int& n0, int& kb0, int& nkb) {
+        const int tn = w % tiles_n;
+        const int tm = (w / tiles_n) % tiles_m;
+        const int sp = w / (tiles_n * tiles_m);
+        m0 = tm * TC_BM;
+        n0 = tn * BN;
+        kb0 = sp * g.kb_per_split;
+        nkb = min(g.kb_per_split, total_kb - kb0);
+    };
+
     if (warp == 0) {
         // ===== TMA producer =====
-        if (lane == 0 && num_kb > 0) {
-            for (int i = 0; i < num_kb; ++i) {
-                const int kb = kb0 + i;
-                const int s = i % TC_STAGES;
-                const unsigned ph = (i / TC_STAGES) & 1;
-                mbar_wait(&S.empty[s], ph ^ 1);                      // slot free (passes immediately the first time)
-                mbar_arrive_expect_tx(&S.full[s], STAGE_BYTES);
-                if (A_MN) {
+        if (lane == 0) {
+            unsigned it = 0;
+            for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+                int m0, n0, kb0, nkb;
+                decode(w, m0, n0, kb0, nkb);
+                for (int i = 0; i < nkb; ++i, ++it) {
+                    const int kb = kb0 + i;
+                    const int s = it % STAGES;
+                    const unsigned ph = (it / STAGES) & 1;
+                    mbar_wait(&S.empty[s], ph ^ 1);                  // slot free (passes immediately the first time)
+                    mbar_arrive_expect_tx(&S.full[s], STAGE_BYTES);
+                    if (A_MN) {
 #pragma unroll
-                    for (int c = 0; c < TC_BM / 32; ++c)
-                        tma_load_2d(S.a[s] + c * 1024, &map_a, m0 + c * 32, kb * TC_BK, &S.full[s]);
-                } else {
-                    tma_load_2d(S.a[s], &map_a, kb * TC_BK, m0, &S.full[s]);
-                }
-                if (B_MN) {
+                        for (int c = 0; c < TC_BM / 32; ++c)
+                            tma_load_2d(S.a[s] + c * 1024, &map_a, m0 + c * 32, kb * TC_BK, &S.full[s]);
+                    } else {
+                        tma_load_2d(S.a[s], &map_a, kb * TC_BK, m0, &S.full[s]);
+                    }
+                    if (B_MN) {
 #pragma unroll
-                    for (int c = 0; c < BN / 32; ++c)
-                        tma_load_2d(S.b[s] + c * 1024, &map_b, n0 + c * 32, kb * TC_BK, &S.full[s]);
-                } else {
-                    tma_load_2d(S.b[s], &map_b, kb * TC_BK, n0, &S.full[s]);
+                        for (int c = 0; c < BN / 32; ++c)
+                            tma_load_2d(S.b[s] + c * 1024, &map_b, n0 + c * 32, kb * TC_BK, &S.full[s]);
+                    } else {
+                        tma_load_2d(S.b[s], &map_b, kb * TC_BK, n0, &S.full[s]);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        if (lane == 0 && num_kb > 0) {
+        if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_tf32(BN) | (A_MN ? (1u << 15) : 0u) | (B_MN ? (1u << 16) : 0u);
-            for (int i = 0; i < num_kb; ++i) {
-                const int s = i % TC_STAGES;
-                const unsigned ph = (i / TC_STAGES) & 1;
-                mbar_wait(&S.full[s], ph);                           // TMA bytes have landed
+            unsigned it = 0, t = 0;
+            for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+                int m0, n0, kb0, nkb;
+                decode(w, m0, n0, kb0, nkb);
+                if (nkb <= 0) continue;
+                const unsigned acc = t & 1, aph = (t >> 1) & 1;
+                mbar_wait(&S.tmem_empty[acc], aph ^ 1);              // epilogue has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d = tmem_d + acc * BN;
+                for (int i = 0; i < nkb; ++i, ++it) {
+                    const int s = it % STAGES;
+                    const unsigned ph = (it / STAGES) & 1;
+                    mbar_wait(&S.full[s], ph);                       // TMA bytes have landed
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-                for (int k = 0; k < TC_BK / 8; ++k) {                // UMMA_K = 8 tf32
-                    const uint64_t adesc = A_MN ? umma_desc_mnmajor_sw128(S.a[s], k) : umma_desc_kmajor_sw128(S.a[s]) + 2 * k;
-                    const uint64_t bdesc = B_MN ? umma_desc_mnmajor_sw128(S.b[s], k) : umma_desc_kmajor_sw128(S.b[s]) + 2 * k;
-                    umma_tf32(tmem_d, adesc, bdesc, idesc, (i > 0 || k > 0) ? 1u : 0u);
-                }
-                umma_commit(&S.empty[s]);                            // frees the slot when these MMAs retire
-            }
-            umma_commit(&S.tmem_full);                               // accumulator complete
-        }
-    } else if (num_kb > 0) {
-        // ===== epilogue: warps 2..5 own TMEM lane quadrants (warp % 4) =====
-        const int q = warp & 3;
-        mbar_wait(&S.tmem_full, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // The smem ring is idle once tmem_full has fired (every MMA that read it has retired): reuse it as a
-        // per-warp 32x33 transpose buffer so that the global accesses are full 128-byte lines (lane = column).
-        float* stg = reinterpret_cast<float*>(&S.a[0][0]) + q * (32 * 33);
-        constexpr int CH = BN >= 32 ? 32 : 16;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += CH) {
-            if (n0 + c0 >= g.No) break;
-            uint32_t r[32];
-            const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-            if (CH == 32) tmem_ld32(taddr, r);
-            else tmem_ld16(taddr, r);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-            for (int j = 0; j < CH; ++j) stg[lane * 33 + j] = __uint_as_float(r[j]);      // lane = row
-            __syncwarp();
-            const int col = n0 + c0 + lane;                                             // lane = column from here on
-            if (lane < CH && col < g.No) {
-                const int rows = min(32, g.Mo - (m0 + q * 32));
-                float* yp = g.out + (size_t)(m0 + q * 32) * g.out_pitch + col;
-                if (EPI == EPI_ATOMIC) {
-                    for (int rr = 0; rr < rows; ++rr) atomicAdd(yp + (size_t)rr * g.out_pitch, stg[rr * 33 + lane]);
-                } else {
-                    const float bcol = g.bias != nullptr ? __ldg(g.bias + col) : 0.f;   // one bias load per lane per chunk
-                    if (g.act == 1) {
-                        for (int rr = 0; rr < rows; ++rr) {
-                            const float x = stg[rr * 33 + lane] + bcol;
-                            yp[(size_t)rr * g.out_pitch] = x > 0.f ? x : expm1f(x);     // ELU(alpha = 1)
-                        }
-                    } else if (g.act == 2) {
-                        for (int rr = 0; rr < rows; ++rr) yp[(size_t)rr * g.out_pitch] = fmaxf(stg[rr * 33 + lane] + bcol, 0.f);
-                    } else {
-                        for (int rr = 0; rr < rows; ++rr) yp[(size_t)rr * g.out_pitch] = stg[rr * 33 + lane] + bcol;
+                    for (int k = 0; k < TC_BK / 8; ++k) {            // UMMA_K = 8 tf32
+                        const uint64_t adesc = A_MN ? umma_desc_mnmajor_sw128(S.a[s], k) : umma_desc_kmajor_sw128(S.a[s]) + 2 * k;
+                        const uint64_t bdesc = B_MN ? umma_desc_mnmajor_sw128(S.b[s], k) : umma_desc_kmajor_sw128(S.b[s]) + 2 * k;
+                        umma_tf32(d, adesc, bdesc, idesc, (i > 0 || k > 0) ? 1u : 0u);
                     }
+                    umma_commit(&S.empty[s]);                        // frees the slot when these MMAs retire
+                }
+                umma_commit(&S.tmem_full[acc]);                      // accumulator complete
+                ++t;
+            }
+        }
+    } else {
+        // ===== epilogue: warps 2..5 own TMEM lane quadrants (warp % 4), i.e. 32 output rows each =====
+        // TMEM -> registers (tcgen05.ld, lane = row, 32 columns) -> bias + activation -> 128-byte-swizzled 32 x 32
+        // slab in shared memory -> TMA store (or TMA reduce-add for split-K).  TMA clips rows >= Mo / columns >= No.
+        const int q = warp & 3;
+        constexpr int CH = BN >= 32 ? 32 : 16;
+        float* bias_s = S.bias_s[q];
+        unsigned t = 0, chunk = 0;
+        for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
+            int m0, n0, kb0, nkb;
+            decode(w, m0, n0, kb0, nkb);
+            if (nkb <= 0) continue;
+            if (EPI == EPI_STORE) {
+                for (int i = lane; i < BN; i += 32)
+                    bias_s[i] = (g.bias != nullptr && n0 + i < g.No) ? __ldg(g.bias + n0 + i) : 0.f;
+                __syncwarp();
+            }
+            const unsigned acc = t & 1, aph = (t >> 1) & 1;
+            mbar_wait(&S.tmem_full[acc], aph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += CH, ++chunk) {
+                if (n0 + c0 >= g.No) break;
+                float* buf = S.stg[q][chunk & 1];
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // slab of 2 chunks ago is free
+                __syncwarp();
+                uint32_t r[32];
+                const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0);
+                if (CH == 32) tmem_ld32(taddr, r);
+                else tmem_ld16(taddr, r);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j4 = 0; j4 < CH / 4; ++j4) {
+                    float v[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float x = __uint_as_float(r[j4 * 4 + e]);
+                        if (EPI == EPI_STORE) {
+                            x += bias_s[c0 + j4 * 4 + e];
+                            if (g.act == 1) x = x > 0.f ? x : __expf(x) - 1.f;          // ELU(alpha = 1)
+                            else if (g.act == 2) x = fmaxf(x, 0.f);                     // ReLU
+                        }
+                        v[e] = x;
+                    }
+                    // row = lane; 16-byte chunk j4 of the 128-byte row lands at chunk (j4 ^ (row & 7)): SWIZZLE_128B
+                    *reinterpret_cast<float4*>(buf + lane * 32 + ((j4 ^ (lane & 7)) << 2)) = make_float4(v[0], v[1], v[2], v[3]);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    if (EPI == EPI_ATOMIC) tma_reduce_add_2d(&map_y, buf, n0 + c0, m0 + q * 32);
+                    else tma_store_2d(&map_y, buf, n0 + c0, m0 + q * 32);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
             }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
+            if (lane == 0) mbar_arrive(&S.tmem_empty[acc]);          // this warp's TMEM reads of the accumulator are done
+            ++t;
         }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -284,12 +359,12 @@ static PFN_encodeTiled get_encode() {
 
 // 2-D fp32 tensor (rows, cols) with `pitch` floats per row; box = (box_rows, 32 floats), 128 B swizzle, zero OOB fill
 static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t pitch, int box_rows,
-                    bool mn_major) {
+                    bool mn_major, int box_cols = TC_BK) {
     PFN_encodeTiled enc = get_encode();
     if (enc == nullptr) return QA_EINVAL;
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)pitch * 4};
-    cuuint32_t box[2] = {TC_BK, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -306,25 +381,71 @@ struct TcOperand {
     int64_t rows, cols, pitch;
 };
 
+static int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
 template <int BN, bool A_MN, bool B_MN, int EPI>
 static int launch_gemm(const TcOperand& A, const TcOperand& B, const TcProblem& prob, int splits, cudaStream_t stream) {
+    // ring depth: as many 128 x 32 + BN x 32 fp32 stages as fit next to the epilogue buffers (<= 8)
+    constexpr int STAGES = BN >= 256 ? 3 : (BN >= 128 ? 5 : (BN >= 64 ? 6 : 8));
     CUtensorMap ma, mb;
     int rc = make_map(&ma, A.base, A.rows, A.cols, A.pitch, A_MN ? 32 : TC_BM, A_MN);
     if (rc) return rc;
     rc = make_map(&mb, B.base, B.rows, B.cols, B.pitch, B_MN ? 32 : BN, B_MN);
     if (rc) return rc;
-    const size_t smem = sizeof(TcSmem<BN>) + 1024;
+    CUtensorMap my;                                                  // output slabs: 32 rows x 32 columns, 128 B swizzle
+    rc = make_map(&my, prob.out, prob.Mo, prob.No, prob.out_pitch, 32, false, 32);
+    if (rc) return rc;
+    const size_t smem = sizeof(TcSmem<BN, STAGES>) + 1024;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_gemm_tf32<BN, A_MN, B_MN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_gemm_tf32<BN, STAGES, A_MN, B_MN, EPI>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
-    dim3 grid((prob.Mo + TC_BM - 1) / TC_BM, (prob.No + BN - 1) / BN, splits);
-    k_gemm_tf32<BN, A_MN, B_MN, EPI><<<grid, TC_THREADS, smem, stream>>>(ma, mb, prob);
+    const int items = ((prob.Mo + TC_BM - 1) / TC_BM) * ((prob.No + BN - 1) / BN) * splits;
+    const int grid = items < num_sms() ? items : num_sms();
+    k_gemm_tf32<BN, STAGES, A_MN, B_MN, EPI><<<grid, TC_THREADS, smem, stream>>>(ma, mb, my, prob);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : (int)e;
+}
+
+// Tile width: the widest BN that still yields enough work items to occupy the chip (wide tiles read A fewer times).
+static int pick_bn(int Mo, int No, int splits, bool mn_major_b) {
+    const int tiles_m = (Mo + TC_BM - 1) / TC_BM;
+    const int cands[5] = {256, 128, 64, 32, 16};
+    // the epilogue stores 32-column slabs: a 16-wide tile is only legal when it is the single n tile (No <= 16)
+    const int smallest = (mn_major_b || No > 16) ? 32 : 16;
+    int need = 16;
+    while (need < No && need < 256) need <<= 1;                      // smallest power of two >= No (capped)
+    if (need < smallest) need = smallest;
+    int best = need;
+    for (int i = 0; i < 5; ++i) {
+        const int bn = cands[i];
+        if (bn > need || bn < smallest) continue;
+        best = bn;
+        if (tiles_m * ((No + bn - 1) / bn) * splits >= 120) break;   // enough items for 148 SMs
+    }
+    return best;
+}
+
+template <bool A_MN, bool B_MN, int EPI>
+static int dispatch_bn(int bn, const TcOperand& A, const TcOperand& B, const TcProblem& p, int splits, cudaStream_t s) {
+    switch (bn) {
+        case 256: return launch_gemm<256, A_MN, B_MN, EPI>(A, B, p, splits, s);
+        case 128: return launch_gemm<128, A_MN, B_MN, EPI>(A, B, p, splits, s);
+        case 64: return launch_gemm<64, A_MN, B_MN, EPI>(A, B, p, splits, s);
+        case 32: return launch_gemm<32, A_MN, B_MN, EPI>(A, B, p, splits, s);
+        default: return launch_gemm<16, A_MN, B_MN, EPI>(A, B, p, splits, s);
+    }
 }
 
 static bool tma_ok(const void* p, int64_t pitch) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0 && (pitch & 3) == 0; }
@@ -338,16 +459,13 @@ extern "C" int qa_linear_fwd(const QaLinearArgs* g, void* stream) {
     if (g->M < 0 || g->N <= 0 || g->K <= 0) return QA_EINVAL;
     if (g->act < 0 || g->act > 2) return QA_EINVAL;
     // TMA constraints: 16 B aligned bases and row pitches
-    if (!tma_ok(g->x, g->x_pitch) || !tma_ok(g->w, g->w_pitch) || g->x_pitch < g->K || g->w_pitch < g->K || g->y_pitch < g->N)
+    if (!tma_ok(g->x, g->x_pitch) || !tma_ok(g->w, g->w_pitch) || !tma_ok(g->y, g->y_pitch) || g->x_pitch < g->K ||
+        g->w_pitch < g->K || g->y_pitch < g->N)
         return QA_EINVAL;
     cudaStream_t s = (cudaStream_t)stream;
     const TcOperand A{g->x, g->M, g->K, g->x_pitch}, B{g->w, g->N, g->K, g->w_pitch};
     TcProblem p{g->M, g->N, g->K, (g->K + TC_BK - 1) / TC_BK, g->y, g->y_pitch, g->bias, g->act};
-    const int n = g->N;
-    if (n <= 16) return launch_gemm<16, false, false, EPI_STORE>(A, B, p, 1, s);
-    if (n <= 32) return launch_gemm<32, false, false, EPI_STORE>(A, B, p, 1, s);
-    if (n <= 64) return launch_gemm<64, false, false, EPI_STORE>(A, B, p, 1, s);
-    return launch_gemm<128, false, false, EPI_STORE>(A, B, p, 1, s);
+    return dispatch_bn<false, false, EPI_STORE>(pick_bn(g->M, g->N, 1, false), A, B, p, 1, s);
 }
 
 // Backward of y = x W^T (+ b):  dx = gz W   (A = gz K-major, B = W MN-major, reduction over N)
@@ -362,17 +480,15 @@ extern "C" int qa_linear_bwd(const QaLinearBwdArgs* g, void* stream) {
     int rc = 0;
     if (g->dx != nullptr) {
         QA_CHECK_PTR(g->w);
-        if (!tma_ok(g->w, g->w_pitch) || g->w_pitch < g->K || g->dx_pitch < g->K) return QA_EINVAL;
+        if (!tma_ok(g->w, g->w_pitch) || !tma_ok(g->dx, g->dx_pitch) || g->w_pitch < g->K || g->dx_pitch < g->K) return QA_EINVAL;
         const TcOperand A{g->gz, g->M, g->N, g->gz_pitch}, B{g->w, g->N, g->K, g->w_pitch};
         TcProblem p{g->M, g->K, g->N, (g->N + TC_BK - 1) / TC_BK, g->dx, g->dx_pitch, nullptr, 0};
-        if (g->K <= 32) rc = launch_gemm<32, false, true, EPI_STORE>(A, B, p, 1, s);
-        else if (g->K <= 64) rc = launch_gemm<64, false, true, EPI_STORE>(A, B, p, 1, s);
-        else rc = launch_gemm<128, false, true, EPI_STORE>(A, B, p, 1, s);
+        rc = dispatch_bn<false, true, EPI_STORE>(pick_bn(g->M, g->K, 1, true), A, B, p, 1, s);
         if (rc) return rc;
     }
     if (g->dw != nullptr) {
         QA_CHECK_PTR(g->x);
-        if (!tma_ok(g->x, g->x_pitch) || g->x_pitch < g->K || g->dw_pitch < g->K) return QA_EINVAL;
+        if (!tma_ok(g->x, g->x_pitch) || !tma_ok(g->dw, g->dw_pitch) || g->x_pitch < g->K || g->dw_pitch < g->K) return QA_EINVAL;
         const TcOperand A{g->gz, g->M, g->N, g->gz_pitch}, B{g->x, g->M, g->K, g->x_pitch};
         const int total_kb = (g->M + TC_BK - 1) / TC_BK;
         const int bn = g->K <= 32 ? 32 : (g->K <= 64 ? 64 : 128);
@@ -383,9 +499,7 @@ extern "C" int qa_linear_bwd(const QaLinearBwdArgs* g, void* stream) {
         const int per = (total_kb + splits - 1) / splits;
         splits = (total_kb + per - 1) / per;
         TcProblem p{g->N, g->K, g->M, per, g->dw, g->dw_pitch, nullptr, 0};
-        if (bn == 32) rc = launch_gemm<32, true, true, EPI_ATOMIC>(A, B, p, splits, s);
-        else if (bn == 64) rc = launch_gemm<64, true, true, EPI_ATOMIC>(A, B, p, splits, s);
-        else rc = launch_gemm<128, true, true, EPI_ATOMIC>(A, B, p, splits, s);
+        rc = dispatch_bn<true, true, EPI_ATOMIC>(bn, A, B, p, splits, s);
     }
     return rc;
 }

@@ -72,7 +72,7 @@ class _LinearActTC(torch.autograd.Function):
         if ops.linear_bwd_ok(gz, x, weight):
             # both contractions on the tcgen05 kernel (MN-major operands); dW is accumulated by the kernel's split-K
             # atomics straight into the flat gradient buffer when the weight lives in one
-            gx = torch.empty(x.shape[0], x.shape[1], device=x.device, dtype=torch.float32) if need_x else None
+            gx = _padded(x.shape[0], x.shape[1], x.device) if need_x else None
             gw = None
             dw_target = None
             if need_w:

@@ -40,7 +40,7 @@ def test_linear_fwd_matches_fp32_reference(shape, act):
     b = (0.1 * torch.randn(N, generator=g)).to(DEV)
     x, w = xbuf[:, :K], wbuf[:, :K]
     assert ops.linear_tc_ok(x, w)
-    y = torch.full((M, N), float("nan"), device=DEV)
+    y = torch.full((M, (N + 3) // 4 * 4), float("nan"), device=DEV)[:, :N]      # 16-byte row pitch (TMA store)
     ops.linear_fwd(x, w, b, y, act)
     torch.cuda.synchronize()
     want = ref(x, w, b, act)
@@ -60,6 +60,9 @@ def test_linear_rejects_unaligned_operands():
     assert not ops.linear_tc_ok(x, w)
     with pytest.raises(RuntimeError, match="QA_EINVAL"):
         ops.linear_fwd(x, w, None, torch.empty(64, 32, device=DEV), None)
+    xa, wa = torch.randn(64, 104, device=DEV)[:, :101], torch.randn(32, 104, device=DEV)[:, :101]
+    with pytest.raises(RuntimeError, match="QA_EINVAL"):                       # output pitch 30 floats: not TMA-storable
+        ops.linear_fwd(xa, wa, None, torch.empty(64, 30, device=DEV), None)
 
 
 def test_actor_critic_tc_mode_matches_fp32_mode_and_grads():
@@ -98,7 +101,7 @@ def test_linear_bwd_matches_fp32_reference(shape):
     w = (torch.randn(N, wp, generator=g) / K ** 0.5).to(DEV)[:, :K]
     gz = (torch.randn(M, N, generator=g) / N ** 0.5).to(DEV)
     assert ops.linear_bwd_ok(gz, x, w)
-    dx = torch.full((M, K), float("nan"), device=DEV)
+    dx = torch.full((M, (K + 3) // 4 * 4), float("nan"), device=DEV)[:, :K]
     dw_buf = torch.zeros(N, wp, device=DEV)
     dw = dw_buf[:, :K]
     dw.fill_(0.25)                                          # accumulate semantics: += on top of existing content
@@ -115,6 +118,6 @@ def test_linear_bwd_matches_fp32_reference(shape):
     assert ew < 2e-3, f"{shape}: dw scaled err {ew:.3e}"
     assert float(dw_buf[:, K:].abs().sum()) == 0.0          # the row padding of the flat layout is never touched
     # each half alone
-    dx2 = torch.empty(M, K, device=DEV)
+    dx2 = torch.empty(M, (K + 3) // 4 * 4, device=DEV)[:, :K]
     ops.linear_bwd(gz, None, w, dx=dx2)
     assert torch.equal(dx2, dx)
