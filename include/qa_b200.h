@@ -395,6 +395,12 @@ typedef struct QaLinearBwdArgs {
     const float* w;  int64_t w_pitch;
     float* dx;       int64_t dx_pitch;
     float* dw;       int64_t dw_pitch;
+    /* optional fusion with the PREVIOUS layer's activation backward (x is that layer's output y_prev = act(z_prev)):
+     * when act_prev != 0 the dx epilogue writes dx * act'(z_prev) -- i.e. the gradient w.r.t. z_prev -- and, if db_prev is
+     * given, its column sums (the previous layer's bias gradient, overwritten) */
+    int32_t act_prev;                   /* 0 none, 1 ELU, 2 ReLU */
+    const float* y_prev; int64_t y_prev_pitch;
+    float* db_prev;                     /* (K) or NULL */
 } QaLinearBwdArgs;
 int qa_linear_bwd(const QaLinearBwdArgs* a, void* stream);
 

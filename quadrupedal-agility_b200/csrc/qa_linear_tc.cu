@@ -122,6 +122,10 @@ struct TcProblem {
     long long out_pitch;
     const float* bias;                  // store epilogue only
     int act;
+    // EPI_ACTBWD (dx of layer L fused with the activation backward of layer L-1): out = acc * act'(yprev), db += colsum(out)
+    const float* yprev;
+    long long yprev_pitch;
+    float* db;
 };
 
 template <int BN, int STAGES>
@@ -137,7 +141,7 @@ struct TcSmem {
     uint32_t tmem_base;
 };
 
-enum { EPI_STORE = 0, EPI_ATOMIC = 1 };
+enum { EPI_STORE = 0, EPI_ATOMIC = 1, EPI_ACTBWD = 2 };
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* ssrc, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
@@ -314,11 +318,40 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                         }
                         v[e] = x;
                     }
+                    if (EPI == EPI_ACTBWD) {
+                        // gradient w.r.t. the previous layer's pre-activation: multiply by act'(z) recovered from its OUTPUT
+                        const int row = m0 + q * 32 + lane, col = n0 + c0 + j4 * 4;
+                        float yv[4] = {1.f, 1.f, 1.f, 1.f};
+                        if (row < g.Mo) {
+                            const float* yr = g.yprev + (size_t)row * g.yprev_pitch + col;
+                            if (col + 3 < g.No) {
+                                const float4 t4 = *reinterpret_cast<const float4*>(yr);
+                                yv[0] = t4.x, yv[1] = t4.y, yv[2] = t4.z, yv[3] = t4.w;
+                            } else {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e)
+                                    if (col + e < g.No) yv[e] = yr[e];
+                            }
+                        }
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            if (g.act == 1) v[e] = yv[e] > 0.f ? v[e] : v[e] * (yv[e] + 1.0f);      // ELU'
+                            else if (g.act == 2) v[e] = yv[e] > 0.f ? v[e] : 0.f;                   // ReLU'
+                        }
+                    }
                     // row = lane; 16-byte chunk j4 of the 128-byte row lands at chunk (j4 ^ (row & 7)): SWIZZLE_128B
                     *reinterpret_cast<float4*>(buf + lane * 32 + ((j4 ^ (lane & 7)) << 2)) = make_float4(v[0], v[1], v[2], v[3]);
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
+                if (EPI == EPI_ACTBWD && g.db != nullptr) {
+                    // bias gradient of the previous layer: column sums of the slab (rows >= Mo hold exact zeros)
+                    const int col = n0 + c0 + lane;
+                    float sum = 0.f;
+#pragma unroll 8
+                    for (int rr = 0; rr < 32; ++rr) sum += buf[rr * 32 + ((((lane >> 2) ^ (rr & 7)) << 2) | (lane & 3))];
+                    if (col < g.No) atomicAdd(g.db + col, sum);
+                }
                 if (lane == 0) {
                     if (EPI == EPI_ATOMIC) tma_reduce_add_2d(&map_y, buf, n0 + c0, m0 + q * 32);
                     else tma_store_2d(&map_y, buf, n0 + c0, m0 + q * 32);
@@ -464,7 +497,7 @@ extern "C" int qa_linear_fwd(const QaLinearArgs* g, void* stream) {
         return QA_EINVAL;
     cudaStream_t s = (cudaStream_t)stream;
     const TcOperand A{g->x, g->M, g->K, g->x_pitch}, B{g->w, g->N, g->K, g->w_pitch};
-    TcProblem p{g->M, g->N, g->K, (g->K + TC_BK - 1) / TC_BK, g->y, g->y_pitch, g->bias, g->act};
+    TcProblem p{g->M, g->N, g->K, (g->K + TC_BK - 1) / TC_BK, g->y, g->y_pitch, g->bias, g->act, nullptr, 0, nullptr};
     return dispatch_bn<false, false, EPI_STORE>(pick_bn(g->M, g->N, 1, false), A, B, p, 1, s);
 }
 
@@ -482,8 +515,23 @@ extern "C" int qa_linear_bwd(const QaLinearBwdArgs* g, void* stream) {
         QA_CHECK_PTR(g->w);
         if (!tma_ok(g->w, g->w_pitch) || !tma_ok(g->dx, g->dx_pitch) || g->w_pitch < g->K || g->dx_pitch < g->K) return QA_EINVAL;
         const TcOperand A{g->gz, g->M, g->N, g->gz_pitch}, B{g->w, g->N, g->K, g->w_pitch};
-        TcProblem p{g->M, g->K, g->N, (g->N + TC_BK - 1) / TC_BK, g->dx, g->dx_pitch, nullptr, 0};
-        rc = dispatch_bn<false, true, EPI_STORE>(pick_bn(g->M, g->K, 1, true), A, B, p, 1, s);
+        if (g->act_prev != 0) {
+            // fused with the previous layer's activation backward (+ its bias gradient)
+            QA_CHECK_PTR(g->y_prev);
+            if (g->act_prev < 0 || g->act_prev > 2 || g->y_prev_pitch < g->K || (g->y_prev_pitch & 3) ||
+                (reinterpret_cast<uintptr_t>(g->y_prev) & 15u))
+                return QA_EINVAL;
+            if (g->db_prev != nullptr) {
+                cudaError_t e = cudaMemsetAsync(g->db_prev, 0, sizeof(float) * g->K, s);
+                if (e != cudaSuccess) return (int)e;
+            }
+            TcProblem p{g->M, g->K, g->N, (g->N + TC_BK - 1) / TC_BK, g->dx, g->dx_pitch, nullptr, g->act_prev,
+                        g->y_prev, g->y_prev_pitch, g->db_prev};
+            rc = dispatch_bn<false, true, EPI_ACTBWD>(pick_bn(g->M, g->K, 1, true), A, B, p, 1, s);
+        } else {
+            TcProblem p{g->M, g->K, g->N, (g->N + TC_BK - 1) / TC_BK, g->dx, g->dx_pitch, nullptr, 0, nullptr, 0, nullptr};
+            rc = dispatch_bn<false, true, EPI_STORE>(pick_bn(g->M, g->K, 1, true), A, B, p, 1, s);
+        }
         if (rc) return rc;
     }
     if (g->dw != nullptr) {
@@ -498,7 +546,7 @@ extern "C" int qa_linear_bwd(const QaLinearBwdArgs* g, void* stream) {
         if (splits < 1) splits = 1;
         const int per = (total_kb + splits - 1) / splits;
         splits = (total_kb + per - 1) / per;
-        TcProblem p{g->N, g->K, g->M, per, g->dw, g->dw_pitch, nullptr, 0};
+        TcProblem p{g->N, g->K, g->M, per, g->dw, g->dw_pitch, nullptr, 0, nullptr, 0, nullptr};
         rc = dispatch_bn<true, true, EPI_ATOMIC>(bn, A, B, p, splits, s);
     }
     return rc;

@@ -146,7 +146,8 @@ class QaPpoLossArgs(C.Structure):
 class QaLinearBwdArgs(C.Structure):
     _fields_ = [("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("gz", vp), ("gz_pitch", C.c_int64), ("x", vp),
                 ("x_pitch", C.c_int64), ("w", vp), ("w_pitch", C.c_int64), ("dx", vp), ("dx_pitch", C.c_int64),
-                ("dw", vp), ("dw_pitch", C.c_int64)]
+                ("dw", vp), ("dw_pitch", C.c_int64), ("act_prev", C.c_int32), ("y_prev", vp), ("y_prev_pitch", C.c_int64),
+                ("db_prev", vp)]
 
 
 class QaHistEncArgs(C.Structure):

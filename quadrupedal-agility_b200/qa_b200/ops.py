@@ -200,8 +200,10 @@ def linear_fwd(x, weight, bias, y, act) -> None:
     _count(1)
 
 
-def linear_bwd(gz, x, weight, dx=None, dw=None) -> None:
-    """dx = gz @ weight (overwritten) and/or dw += gz.T @ x (accumulated) on the tcgen05 kernel, MN-major operands."""
+def linear_bwd(gz, x, weight, dx=None, dw=None, act_prev=None, y_prev=None, db_prev=None) -> None:
+    """dx = gz @ weight (overwritten) and/or dw += gz.T @ x (accumulated) on the tcgen05 kernel, MN-major operands.
+    With `act_prev` the dx epilogue also applies the previous layer's activation derivative (from its output `y_prev`)
+    and reduces that layer's bias gradient into `db_prev`."""
     lib = _abi.load()
     M, N = gz.shape
     K = weight.shape[1] if weight is not None else x.shape[1]
@@ -209,7 +211,10 @@ def linear_bwd(gz, x, weight, dx=None, dw=None) -> None:
                              None if x is None else x.data_ptr(), 0 if x is None else x.stride(0),
                              None if weight is None else weight.data_ptr(), 0 if weight is None else weight.stride(0),
                              None if dx is None else dx.data_ptr(), 0 if dx is None else dx.stride(0),
-                             None if dw is None else dw.data_ptr(), 0 if dw is None else dw.stride(0))
+                             None if dw is None else dw.data_ptr(), 0 if dw is None else dw.stride(0),
+                             ACT_ID[act_prev], None if y_prev is None else y_prev.data_ptr(),
+                             0 if y_prev is None else y_prev.stride(0),
+                             None if db_prev is None else _p(db_prev, torch.float32, "db_prev"))
     _abi.check(lib.qa_linear_bwd(C.byref(a), _stream()), "qa_linear_bwd")
     _count((dx is not None) + (dw is not None))
 

@@ -91,6 +91,90 @@ class _LinearActTC(torch.autograd.Function):
         return gx, gw, gb, None
 
 
+class _MlpChainTC(torch.autograd.Function):
+    """A stack of Linear(+ELU/ReLU) layers as ONE autograd node (K7 GEMM chain).
+
+    forward : one `qa_linear_fwd` per layer (bias + activation in the epilogue); every layer output is saved.
+    backward: per layer one split-K `dW += gz^T h` GEMM and one `dx` GEMM whose epilogue already applies the PREVIOUS
+              layer's activation derivative (from its saved output) and reduces that layer's bias gradient -- so the
+              hidden layers need no separate element-wise pass; only the last layer's upstream gradient goes through K9.
+    Weight gradients are accumulated by the kernels straight into the flat gradient buffer (`weight.grad`)."""
+
+    @staticmethod
+    def forward(ctx, x, acts, *params):
+        n = len(acts)
+        hs = [x]
+        for i in range(n):
+            w, b = params[2 * i], params[2 * i + 1]
+            y = _padded(x.shape[0], w.shape[0], x.device)
+            ops.linear_fwd(hs[-1], w, b, y, acts[i])
+            hs.append(y)
+        ctx.acts = acts
+        ctx.save_for_backward(*hs, *params)
+        return hs[-1]
+
+    @staticmethod
+    def backward(ctx, gout):
+        acts, n = ctx.acts, len(ctx.acts)
+        saved = ctx.saved_tensors
+        hs, params = saved[:n + 1], saved[n + 1:]
+        dev, M = gout.device, gout.shape[0]
+        if gout.stride(1) != 1:
+            gout = gout.contiguous()
+        grads = [None] * (2 * n)
+        # last layer: upstream gradient -> pre-activation gradient (+ bias gradient), K9
+        gb = torch.empty(params[2 * n - 2].shape[0], device=dev, dtype=torch.float32)
+        aligned = gout.stride(0) % 4 == 0 and gout.data_ptr() % 16 == 0
+        if acts[-1] is not None or not aligned:
+            gz = _padded(M, gout.shape[1], dev)
+            ops.act_bwd(gout, hs[n] if acts[-1] is not None else None, acts[-1], gz=gz, db=gb)
+        else:
+            gz = gout
+            ops.act_bwd(gout, None, None, gz=None, db=gb)
+        grads[2 * n - 1] = gb
+        gx = None
+        for i in range(n, 0, -1):                          # layer i: input hs[i-1], weight params[2(i-1)]
+            w = params[2 * (i - 1)]
+            h_in = hs[i - 1]
+            dw_target = None
+            if ctx.needs_input_grad[2 + 2 * (i - 1)]:
+                if w.grad is not None and w.grad.stride(1) == 1 and w.grad.stride(0) % 4 == 0:
+                    dw_target = w.grad
+                else:
+                    dw_target = _padded(w.shape[0], w.shape[1], dev).zero_()
+                    grads[2 * (i - 1)] = dw_target
+            if i > 1:
+                act_prev = acts[i - 2]
+                gz_prev = _padded(M, h_in.shape[1], dev)
+                db_prev = torch.empty(h_in.shape[1], device=dev, dtype=torch.float32)
+                if act_prev is not None:
+                    ops.linear_bwd(gz, h_in, w, dx=gz_prev, dw=dw_target, act_prev=act_prev, y_prev=h_in, db_prev=db_prev)
+                else:
+                    ops.linear_bwd(gz, h_in, w, dx=gz_prev, dw=dw_target)
+                    ops.act_bwd(gz_prev, None, None, gz=None, db=db_prev)
+                grads[2 * (i - 2) + 1] = db_prev
+                gz = gz_prev
+            else:
+                if ctx.needs_input_grad[0]:
+                    gx = _padded(M, h_in.shape[1], dev)
+                if gx is not None or dw_target is not None:
+                    ops.linear_bwd(gz, h_in if dw_target is not None else None, w if gx is not None else None,
+                                   dx=gx, dw=dw_target)
+        return (gx, None, *grads)
+
+
+def mlp_chain(x: torch.Tensor, layers, acts):
+    """layers: [(weight, bias), ...]; acts: ["elu" | "relu" | None, ...].  tcgen05 chain in "tc" mode, cuBLAS otherwise."""
+    if _MODE == "tc" and x.is_cuda and x.dim() == 2 and x.shape[0] > 0:
+        xa = _tma_operand(x)
+        if all(ops.linear_tc_ok(xa if i == 0 else w, w) and b is not None for i, (w, b) in enumerate(layers)):
+            flat = [t for wb in layers for t in wb]
+            return _MlpChainTC.apply(xa, tuple(acts), *flat)
+    for (w, b), a in zip(layers, acts):
+        x = linear_act(x, w, b, a)
+    return x
+
+
 def linear_act(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, act):
     if _MODE == "tc" and x.is_cuda and x.dim() == 2 and x.shape[0] > 0:
         xa = _tma_operand(x)

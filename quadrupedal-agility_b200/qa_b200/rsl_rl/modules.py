@@ -13,7 +13,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .linear import linear_act
+from .linear import linear_act, mlp_chain
 
 
 def get_activation(act_name):
@@ -36,22 +36,35 @@ def _mlp(dims: List[int], act_name: str, last_act: bool) -> nn.Sequential:
     return nn.Sequential(*layers)
 
 
-def run_mlp(seq: nn.Sequential, x: torch.Tensor) -> torch.Tensor:
-    """Evaluates a Linear/activation stack with the activation fused into the GEMM epilogue."""
+def _stack_spec(seq: nn.Sequential):
+    """[(weight, bias)], [act] of a Linear/ELU/ReLU stack, or None if the Sequential holds anything else."""
     mods = list(seq)
-    i = 0
+    layers, acts, i = [], [], 0
     while i < len(mods):
         m = mods[i]
-        if isinstance(m, nn.Linear):
-            act = None
-            if i + 1 < len(mods) and isinstance(mods[i + 1], (nn.ELU, nn.ReLU)):
-                act = "elu" if isinstance(mods[i + 1], nn.ELU) else "relu"
-                i += 1
-            x = linear_act(x, m.weight, m.bias, act)
-        else:
-            x = m(x)
+        if not isinstance(m, nn.Linear):
+            return None
+        act = None
+        if i + 1 < len(mods) and isinstance(mods[i + 1], (nn.ELU, nn.ReLU)):
+            act = "elu" if isinstance(mods[i + 1], nn.ELU) else "relu"
+            i += 1
+        layers.append((m.weight, m.bias))
+        acts.append(act)
         i += 1
-    return x
+    return layers, acts
+
+
+def run_mlp(seq: nn.Sequential, x: torch.Tensor, head: nn.Linear = None) -> torch.Tensor:
+    """Evaluates a Linear/activation stack (optionally followed by a linear `head`) as one GEMM chain with the bias and
+    activation fused into each GEMM's epilogue."""
+    spec = _stack_spec(seq)
+    if spec is None:
+        x = seq(x)
+        return x if head is None else linear_act(x, head.weight, head.bias, None)
+    layers, acts = spec
+    if head is not None:
+        layers, acts = layers + [(head.weight, head.bias)], acts + [None]
+    return mlp_chain(x, layers, acts)
 
 
 class FlatParams:
@@ -197,16 +210,15 @@ class ActorCritic(nn.Module):
         obs_prop, obs_explicit, obs_latent, obs_hist, obs_command = self._split(observations)
         if self.train_with_estimated_latent:
             obs_latent = self.infer_hist_latent(obs_hist) if hist_encoding else self.infer_priv_latent(obs_latent)
-        # [prop | explicit | latent | command] assembled in a buffer whose rows are 16-byte aligned (TMA operand)
+        # [prop | explicit | latent | command | zero pad]: ONE concatenation whose row pitch is a multiple of 16 bytes, so
+        # the result is a legal TMA operand for the first actor layer (the pad columns are sliced off again)
         n_in = self.num_actor_obs
-        buf = torch.empty(observations.shape[0], (n_in + 3) // 4 * 4, device=observations.device, dtype=observations.dtype)
-        x = buf[:, :n_in]
-        p, e, l = self.num_prop, self.num_explicit, self.num_latent
-        x[:, :p] = obs_prop
-        x[:, p:p + e] = obs_explicit
-        x[:, p + e:p + e + l] = obs_latent
-        x[:, p + e + l:] = obs_command
-        return linear_act(run_mlp(self.actor_trunk, x), self.actor_head.weight, self.actor_head.bias, None)
+        pad = (n_in + 3) // 4 * 4 - n_in
+        parts = [obs_prop, obs_explicit, obs_latent, obs_command]
+        if pad:
+            parts.append(torch.zeros(observations.shape[0], pad, device=observations.device, dtype=observations.dtype))
+        x = torch.cat(parts, dim=-1)[:, :n_in]
+        return run_mlp(self.actor_trunk, x, head=self.actor_head)
 
     def update_distribution(self, observations, hist_encoding: bool):
         mean = self._actor_mean(observations, hist_encoding)
@@ -242,8 +254,7 @@ class ActorCritic(nn.Module):
         return enc(obs.reshape(-1, self.num_hist, self.num_prop))
 
     def evaluate(self, critic_observations, **kwargs):
-        return linear_act(run_mlp(self.critic_trunk, critic_observations), self.critic_head.weight,
-                          self.critic_head.bias, None)
+        return run_mlp(self.critic_trunk, critic_observations, head=self.critic_head)
 
 
 class Estimator(nn.Module):

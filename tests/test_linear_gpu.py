@@ -121,3 +121,57 @@ def test_linear_bwd_matches_fp32_reference(shape):
     dx2 = torch.empty(M, (K + 3) // 4 * 4, device=DEV)[:, :K]
     ops.linear_bwd(gz, None, w, dx=dx2)
     assert torch.equal(dx2, dx)
+
+
+@pytest.mark.parametrize("act", ["elu", "relu"])
+def test_linear_bwd_fused_activation_backward(act):
+    """dx epilogue fused with the previous layer's activation derivative and bias gradient (EPI_ACTBWD)."""
+    g = torch.Generator().manual_seed(11)
+    for M, N, K in ((24576, 256, 512), (1000, 128, 256), (4096, 12, 128), (130, 64, 100)):
+        kp = (K + 3) // 4 * 4
+        z_prev = torch.randn(M, kp, generator=g).to(DEV)[:, :K]
+        y_prev = F.elu(z_prev) if act == "elu" else F.relu(z_prev)
+        yp = torch.empty(M, kp, device=DEV)[:, :K]
+        yp.copy_(y_prev)
+        w = (torch.randn(N, kp, generator=g) / K ** 0.5).to(DEV)[:, :K]
+        gz = (torch.randn(M, N, generator=g) / N ** 0.5).to(DEV)
+        out = torch.full((M, kp), float("nan"), device=DEV)[:, :K]
+        db = torch.full((K,), 3.0, device=DEV)
+        ops.linear_bwd(gz, None, w, dx=out, act_prev=act, y_prev=yp, db_prev=db)
+        torch.cuda.synchronize()
+        dact = torch.where(z_prev > 0, 1.0, torch.exp(z_prev)) if act == "elu" else (z_prev > 0).float()
+        want = (gz.double() @ w.double()) * dact.double()
+        scale = (gz.double().abs() @ w.double().abs()).clamp(min=1e-6)
+        assert torch.isfinite(out).all()
+        assert ((out.double() - want).abs() / scale).max().item() < 2e-3, (M, N, K)
+        sdb = (want.abs().sum(0)).clamp(min=1e-3)
+        assert ((db.double() - want.sum(0)).abs() / sdb).max().item() < 2e-3, (M, N, K)
+
+
+def test_mlp_chain_gradients_match_fp32_autograd():
+    """The fused GEMM chain (forward + backward with fused epilogues) against plain fp32 autograd."""
+    from qa_b200.rsl_rl.linear import mlp_chain
+    g = torch.Generator().manual_seed(2)
+    M = 4096
+    dims = [671, 512, 256, 128, 12]
+    x = torch.randn(M, 672, generator=g).to(DEV)[:, :671]
+    params = []
+    for i in range(4):
+        kp = (dims[i] + 3) // 4 * 4
+        w = (torch.randn(dims[i + 1], kp, generator=g) / dims[i] ** 0.5).to(DEV)[:, :dims[i]].requires_grad_(True)
+        b = (0.1 * torch.randn(dims[i + 1], generator=g)).to(DEV).requires_grad_(True)
+        params.append((w, b))
+    acts = ["elu", "elu", "elu", None]
+    tgt = torch.randn(M, 12, generator=g).to(DEV)
+    outs = {}
+    for mode in ("fp32", "tc"):
+        linear.set_mode(mode)
+        for w, b in params:
+            w.grad = None
+            b.grad = None
+        y = mlp_chain(x, params, acts)
+        ((y - tgt) ** 2).mean().backward()
+        outs[mode] = [y.detach().clone()] + [t.grad.clone() for wb in params for t in wb]
+    linear.set_mode("fp32")
+    errs = [((a - b).abs().max() / b.abs().max()).item() for a, b in zip(outs["tc"], outs["fp32"])]
+    assert max(errs) < 1e-2, errs
