@@ -7,13 +7,14 @@
 //   P0  one thread issues ~22 TMA bulk loads (cp.async.bulk + mbarrier complete_tx) for EVERY per-env array of
 //       the CTA's 8 envs -- each array's 8-env slice is contiguous and 16 B aligned -- while the other threads
 //       fetch the two strided inputs (feet positions, last action);
-//   P1  warp-per-env, lanes = DOFs / bodies: the nine 12-wide reward sums (warp-shuffle butterflies) and the
-//       contact-force norms (ballots) -> per-env scalars in shared memory;
-//   P2  thread-per-env (8 lanes of warp 0): the scalar program -- base-frame quantities, euler angles, centre
-//       terrain height, periodic resampling, push, termination, reward total, episode sums, reset decision;
-//       SIMD across envs instead of 32x redundant;
-//   P3  warp-per-env: reset envs blend their mocap frame (lanes = frame columns) and rewrite simulator state;
-//       then key-body positions, the 671-float row, history shift, noise on the <= 64 noisy lanes, clip, disc obs;
+//   P1  (env warps) warp-per-env, lanes = DOFs / bodies: the nine 12-wide reward sums (warp-shuffle butterflies) and
+//       the contact-force norms (ballots) -> per-env scalars in shared memory; then P3a: every lane of the row that
+//       depends on loaded inputs only (DOF lanes, latent lanes, history shift through registers);
+//   P2a (scalar warp, concurrently, thread-per-env = 8 lanes): base-frame quantities, euler angles, centre terrain
+//       height, key-body positions, periodic resampling, push -- SIMD across envs instead of 32x redundant;
+//   P2b (scalar warp, after a barrier): contacts, termination, reward total, episode sums, reset decision;
+//   P3b (env warps): reset envs blend their mocap frame (lanes = frame columns) and rewrite simulator state; the
+//       P2-dependent row lanes, newest history slot, noise on the <= 64 noisy lanes, clip, disc obs;
 //   P4  one thread issues the TMA bulk stores of every output tile (obs, privileged obs, history, disc obs,
 //       last_*, episode sums, commands ...); reset statistics are finalised by the last CTA as in the other kernel.
 //
@@ -21,7 +22,7 @@
 #include "qa_k2_common.cuh"
 
 #define T2_ENVS 8
-#define T2_THREADS (T2_ENVS * 32)
+#define T2_THREADS (T2_ENVS * 32 + 32)   // 8 env warps + 1 scalar warp
 
 // per-env scalar slots (floats) exchanged between the phases
 enum {
@@ -33,6 +34,7 @@ enum {
     SC_RESET = 15,
     SC_CH = 16,         // centre terrain height
     SC_MODE = 17,       // behaviour mode drawn at reset (int bits)
+    SC_KEY = 18,        // 4 x 3 key-body (feet) positions in the heading frame
     SC_N = 32
 };
 
@@ -82,7 +84,7 @@ __device__ __forceinline__ void resample_thread(const QaBbcConst& c, const K2Dra
     for (int k = 0; k < QA_DIM_C; ++k) lc[k] = (k == m) ? 1.f : 0.f;
 }
 
-__global__ void __launch_bounds__(T2_THREADS)
+__global__ void __launch_bounds__(T2_THREADS, 4)
 k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_constant__ QaBbcStepArgs a_in) {
     const K2Step a(a_in);
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -135,69 +137,112 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
                                             (QA_ACT_HIST_LEN - 1) * QA_NUM_DOF + k];
     }
     mbar_wait(&S.bar, 0);
+    __syncthreads();                                        // the two directly-loaded inputs are visible to every warp
 
-    // ---------------- P1: warp-per-env DOF sums and contact-force norms ------------------------------------
-    {
+    bool any_state_write = a.do_push != 0;
+    // scalar-warp registers that live across the phase barrier (P2a -> P2b)
+    Vec3 blv = {0.f, 0.f, 0.f}, bav = {0.f, 0.f, 0.f};
+    float center_h = 0.f;
+    long long ep = 0;
+
+    if (wid < T2_ENVS) {
+        // ---------------- P1: warp-per-env DOF sums and contact-force norms --------------------------------
         const int el = wid;
         const bool dl = lane < QA_NUM_DOF;
         const int d_ = dl ? lane : 0;
         const float dof_pos = S.dof[el * 24 + 2 * d_], dof_vel = S.dof[el * 24 + 2 * d_ + 1];
-        const float act = S.act[el * 12 + d_], lact = S.lact[el * 12 + d_];
-        const float tq = S.tq[el * 12 + d_], ltq = S.ltq[el * 12 + d_], ldv = S.ldv[el * 12 + d_];
-        float v, s[9];
-        v = lact - act;
-        s[0] = warp_sum(dl ? v * v : 0.f);                                         // action_rate
-        v = tq - ltq;
-        s[1] = warp_sum(dl ? v * v : 0.f);                                         // delta_torques
-        v = (ldv - dof_vel) / c.dt;
-        s[2] = warp_sum(dl ? v * v : 0.f);                                         // dof_acc
-        const float dq0 = dof_pos - c.default_dof_pos[d_];
-        s[3] = warp_sum(dl ? dq0 * dq0 : 0.f);                                     // dof_error
-        v = -fminf(dof_pos - c.dof_pos_lower[d_], 0.f);
-        v = v + fmaxf(dof_pos - c.dof_pos_upper[d_], 0.f);
-        s[4] = warp_sum(dl ? v : 0.f);                                             // dof_pos_limits
-        v = clampf(fabsf(dof_vel) - c.dof_vel_limits[d_] * c.soft_dof_vel_limit, 0.f, 1.f);
-        s[5] = warp_sum(dl ? v : 0.f);                                             // dof_vel_limits
-        s[6] = warp_sum((dl && ((c.hip_dof_mask >> d_) & 1u)) ? dq0 * dq0 : 0.f);  // hip_pos
-        v = fmaxf(fabsf(tq) - c.torque_limits[d_] * c.soft_torque_limit, 0.f);
-        s[7] = warp_sum(dl ? v : 0.f);                                             // torque_limits
-        s[8] = warp_sum(dl ? tq * tq : 0.f);                                       // torques
-        float nrm = 0.f;
-        if (lane < B) {
-            const float* f = S.cf + (el * B + lane) * 3;
-            nrm = sqrtf(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]);
+        {
+            const float act = S.act[el * 12 + d_], lact = S.lact[el * 12 + d_];
+            const float tq = S.tq[el * 12 + d_], ltq = S.ltq[el * 12 + d_], ldv = S.ldv[el * 12 + d_];
+            float v, s[9];
+            v = lact - act;
+            s[0] = warp_sum(dl ? v * v : 0.f);                                         // action_rate
+            v = tq - ltq;
+            s[1] = warp_sum(dl ? v * v : 0.f);                                         // delta_torques
+            v = (ldv - dof_vel) / c.dt;
+            s[2] = warp_sum(dl ? v * v : 0.f);                                         // dof_acc
+            const float dq0 = dof_pos - c.default_dof_pos[d_];
+            s[3] = warp_sum(dl ? dq0 * dq0 : 0.f);                                     // dof_error
+            v = -fminf(dof_pos - c.dof_pos_lower[d_], 0.f);
+            v = v + fmaxf(dof_pos - c.dof_pos_upper[d_], 0.f);
+            s[4] = warp_sum(dl ? v : 0.f);                                             // dof_pos_limits
+            v = clampf(fabsf(dof_vel) - c.dof_vel_limits[d_] * c.soft_dof_vel_limit, 0.f, 1.f);
+            s[5] = warp_sum(dl ? v : 0.f);                                             // dof_vel_limits
+            s[6] = warp_sum((dl && ((c.hip_dof_mask >> d_) & 1u)) ? dq0 * dq0 : 0.f);  // hip_pos
+            v = fmaxf(fabsf(tq) - c.torque_limits[d_] * c.soft_torque_limit, 0.f);
+            s[7] = warp_sum(dl ? v : 0.f);                                             // torque_limits
+            s[8] = warp_sum(dl ? tq * tq : 0.f);                                       // torques
+            float nrm = 0.f;
+            if (lane < B) {
+                const float* f = S.cf + (el * B + lane) * 3;
+                nrm = sqrtf(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]);
+            }
+            const unsigned hit_term = __ballot_sync(QA_FULL, nrm > 1.f) & c.termination_body_mask;
+            const unsigned hit_col = __ballot_sync(QA_FULL, nrm > 0.1f) & c.penalised_body_mask;
+            float ff[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ff[j] = __shfl_sync(QA_FULL, nrm, c.feet_indices[j]);
+            float out = 0.f;
+#pragma unroll
+            for (int k = 0; k < 9; ++k)
+                if (lane == k) out = s[k];
+            if (lane == SC_NCOL) out = (float)__popc(hit_col);
+            if (lane == SC_TERM) out = hit_term ? 1.f : 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (lane == SC_FF + j) out = ff[j];
+            if (lane < SC_RESET) S.scal[el][lane] = out;
         }
-        const unsigned hit_term = __ballot_sync(QA_FULL, nrm > 1.f) & c.termination_body_mask;
-        const unsigned hit_col = __ballot_sync(QA_FULL, nrm > 0.1f) & c.penalised_body_mask;
-        float ff[4];
+        // ---------------- P3a: everything of the row that depends on loaded inputs only ---------------------
+        // (overlaps the scalar warp's P2a; the reset path of P3b redoes the DOF lanes for the ~1.5 % reset envs)
+        {
+            float* row = S.obs + el * ROW;
+            float* disc = S.disc + el * QA_NUM_OBS_DISC;
+            if (dl) {
+                const float dq = (dof_pos - c.default_dof_pos[lane]) * c.s_dof_pos;
+                const float dv = dof_vel * c.s_dof_vel;
+                row[5 + lane] = dq;
+                row[17 + lane] = dv;
+                row[29 + lane] = S.alast[el * 12 + lane];
+                row[45 + lane] = 0.f;
+                row[66 + lane] = S.msp[el * 12 + lane] - 1.f;
+                row[78 + lane] = S.msd[el * 12 + lane] - 1.f;
+                disc[9 + lane] = dq;
+                disc[21 + lane] = dv;
+                S.dv_out[el * 12 + lane] = dof_vel;
+            }
+            if (lane >= 12 && lane < 16) row[61 + lane - 12] = S.mass[el * 4 + lane - 12];
+            if (lane == 16) row[65] = S.fric[el];
+            // history shift (:302-312, non-fill case), staged through registers: hazard-free in-place shift of the tile
+            float* h = S.hist + el * HIST_W;
+            constexpr int NSH = (HIST_W - QA_NUM_PROP + 31) / 32;
+            float hv[NSH];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) ff[j] = __shfl_sync(QA_FULL, nrm, c.feet_indices[j]);
-        float out = 0.f;
+            for (int k = 0; k < NSH; ++k) {
+                const int i = k * 32 + lane;
+                hv[k] = (i < HIST_W - QA_NUM_PROP) ? h[i + QA_NUM_PROP] : 0.f;
+            }
+            __syncwarp();
 #pragma unroll
-        for (int k = 0; k < 9; ++k)
-            if (lane == k) out = s[k];
-        if (lane == SC_NCOL) out = (float)__popc(hit_col);
-        if (lane == SC_TERM) out = hit_term ? 1.f : 0.f;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (lane == SC_FF + j) out = ff[j];
-        if (lane < SC_RESET) S.scal[el][lane] = out;
-    }
-    __syncthreads();
-
-    // ---------------- P2: thread-per-env scalar program -------------------------------------------------------
-    bool any_state_write = a.do_push != 0;
-    if (tid < T2_ENVS) {
-        const int el = tid, e = e0 + el;
+            for (int k = 0; k < NSH; ++k) {
+                const int i = k * 32 + lane;
+                if (i < HIST_W - QA_NUM_PROP) {
+                    const float v = clampf(hv[k], -c.clip_obs, c.clip_obs);
+                    row[HIST_OFF + i] = v;
+                    h[i] = v;
+                }
+            }
+        }
+    } else if (lane < T2_ENVS) {
+        // ---------------- P2a: thread-per-env scalar program, command / contact independent half ------------------
+        const int el = lane, e = e0 + el;
         float* R = S.root + el * 13;
         float* sc = S.scal[el];
-        float* cmd = S.cmd + el * 5;
         const Quat q = {R[3], R[4], R[5], R[6]};
-        long long ep = S.ep[el] + 1;                                               // :133
-        float center_h = 0.f;
+        ep = S.ep[el] + 1;                                                         // :133
         if (c.measure_heights) center_h = terrain_center_height(a.terrain, yaw_quat(q), R[0], R[1], c.center_px, c.center_py);
-        const Vec3 blv = quat_rotate_sgn(q, Vec3{R[7], R[8], R[9]}, -1.f);        // :138-140
-        const Vec3 bav = quat_rotate_sgn(q, Vec3{R[10], R[11], R[12]}, -1.f);
+        blv = quat_rotate_sgn(q, Vec3{R[7], R[8], R[9]}, -1.f);                     // :138-140
+        bav = quat_rotate_sgn(q, Vec3{R[10], R[11], R[12]}, -1.f);
         const Vec3 pg = quat_rotate_sgn(q, Vec3{0.f, 0.f, -1.f}, -1.f);
         float roll, pitch, yaw;
         {
@@ -211,17 +256,24 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
             const float t4 = 1.0f - 2.0f * (q.y * q.y + q.z * q.z);
             yaw = atan2f(t3, t4);
         }
+        S.blv[el * 3 + 0] = blv.x, S.blv[el * 3 + 1] = blv.y, S.blv[el * 3 + 2] = blv.z;
+        S.bav[el * 3 + 0] = bav.x, S.bav[el * 3 + 1] = bav.y, S.bav[el * 3 + 2] = bav.z;
+        S.pg[el * 3 + 0] = pg.x, S.pg[el * 3 + 1] = pg.y, S.pg[el * 3 + 2] = pg.z;
+        S.rpy[el * 3 + 0] = roll, S.rpy[el * 3 + 1] = pitch, S.rpy[el * 3 + 2] = yaw;
+        {
+            // compute_flat_key_pos (:1377-1396) on the current root; reset envs redo it in P3b on the mocap root
+            const Quat hq = heading_quat_inv(q);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {                                              // :143-146
-            const float f = sc[SC_FF + j];
-            const bool ct = f > 2.f;
-            S.ff[el * 4 + j] = f;
-            S.cont_out[el * 4 + j] = ct ? 1 : 0;
-            S.cfilt_out[el * 4 + j] = (ct || S.lcont[el * 4 + j] != 0) ? 1 : 0;
+            for (int j = 0; j < 4; ++j) {
+                const Vec3 local = {S.key[el * 12 + j * 3 + 0] - R[0], S.key[el * 12 + j * 3 + 1] - R[1],
+                                    S.key[el * 12 + j * 3 + 2] - R[2]};
+                const Vec3 o = quat_rotate_sgn(hq, local, 1.f);
+                sc[SC_KEY + j * 3 + 0] = o.x, sc[SC_KEY + j * 3 + 1] = o.y, sc[SC_KEY + j * 3 + 2] = o.z;
+            }
         }
         if (ep % (long long)c.resample_period == 0) {                              // :454-462
             const K2Draw d = draw_site(c, a, e, SITE_RS0, a.rs_eps_u, a.rs_c_idx, a.rs_cmd_u);
-            resample_thread(c, d, cmd, S.eps + el, S.lc + el * 5);
+            resample_thread(c, d, S.cmd + el * 5, S.eps + el, S.lc + el * 5);
         }
         if (a.do_push) {                                                           // :682-687
             float u0, u1;
@@ -237,6 +289,23 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
             const float span = c.max_push_vel_xy - (-c.max_push_vel_xy);
             R[7] = span * u0 + (-c.max_push_vel_xy);
             R[8] = span * u1 + (-c.max_push_vel_xy);
+        }
+    }
+    __syncthreads();                                        // P1 results visible to the scalar warp
+
+    if (wid == T2_ENVS && lane < T2_ENVS) {
+        // ---------------- P2b: contacts, termination, reward total, episode sums, reset decision --------------------
+        const int el = lane, e = e0 + el;
+        float* R = S.root + el * 13;
+        float* sc = S.scal[el];
+        float* cmd = S.cmd + el * 5;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {                                              // :143-146
+            const float f = sc[SC_FF + j];
+            const bool ct = f > 2.f;
+            S.ff[el * 4 + j] = f;
+            S.cont_out[el * 4 + j] = ct ? 1 : 0;
+            S.cfilt_out[el * 4 + j] = (ct || S.lcont[el * 4 + j] != 0) ? 1 : 0;
         }
         const float root_z_pre = R[2];
         const bool time_out = ((float)ep > c.max_episode_length) || (root_z_pre < -6.0f);   // :168-176
@@ -294,10 +363,6 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
         S.ep[el] = ep;
         S.rew[el] = rew;
         S.rooth[el] = root_h_pre;
-        S.blv[el * 3 + 0] = blv.x, S.blv[el * 3 + 1] = blv.y, S.blv[el * 3 + 2] = blv.z;
-        S.bav[el * 3 + 0] = bav.x, S.bav[el * 3 + 1] = bav.y, S.bav[el * 3 + 2] = bav.z;
-        S.pg[el * 3 + 0] = pg.x, S.pg[el * 3 + 1] = pg.y, S.pg[el * 3 + 2] = pg.z;
-        S.rpy[el * 3 + 0] = roll, S.rpy[el * 3 + 1] = pitch, S.rpy[el * 3 + 2] = yaw;
         sc[SC_RESET] = is_reset ? 1.f : 0.f;
         sc[SC_CH] = center_h;
         sc[SC_MODE] = __int_as_float(mode);
@@ -307,17 +372,15 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
     }
     any_state_write = __syncthreads_or(any_state_write ? 1 : 0) != 0;
 
-    // ---------------- P3: warp-per-env reset write, row assembly ---------------------------------------------
-    {
+    if (wid < T2_ENVS) {
+        // ---------------- P3b: reset write (rare), P2-dependent row lanes, last history slot, noise, clip --------------
         const int el = wid, e = e0 + el;
         float* sc = S.scal[el];
         float* R = S.root + el * 13;
         float* row = S.obs + el * ROW;
+        float* disc = S.disc + el * QA_NUM_OBS_DISC;
         const bool is_reset = sc[SC_RESET] != 0.f;
         const bool dl = lane < QA_NUM_DOF;
-        const int d_ = dl ? lane : 0;
-        float dof_pos = S.dof[el * 24 + 2 * d_], dof_vel = S.dof[el * 24 + 2 * d_ + 1];
-        float hla = S.alast[el * 12 + d_];
         if (is_reset) {
             int clip;
             double time_u;
@@ -342,10 +405,18 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
             const float bl = bi.blend;
             const Quat qs = slerp_ref(Quat{f0[3], f0[4], f0[5], f0[6]}, Quat{f1[3], f1[4], f1[5], f1[6]}, bl);
             if (dl) {
-                dof_pos = mocap_lerp(f0[7 + lane], f1[7 + lane], bl);
-                dof_vel = mocap_lerp(f0[37 + lane], f1[37 + lane], bl);
+                const float dof_pos = mocap_lerp(f0[7 + lane], f1[7 + lane], bl);
+                const float dof_vel = mocap_lerp(f0[37 + lane], f1[37 + lane], bl);
                 S.dof[el * 24 + 2 * lane] = dof_pos;
                 S.dof[el * 24 + 2 * lane + 1] = dof_vel;
+                const float dq = (dof_pos - c.default_dof_pos[lane]) * c.s_dof_pos;
+                const float dv = dof_vel * c.s_dof_vel;
+                row[5 + lane] = dq;
+                row[17 + lane] = dv;
+                row[29 + lane] = 0.f;                                           // action history is cleared (:227)
+                disc[9 + lane] = dq;
+                disc[21 + lane] = dv;
+                S.dv_out[el * 12 + lane] = dof_vel;
             }
             const Vec3 lin = quat_rotate_sgn(
                 qs, Vec3{mocap_lerp(f0[31], f1[31], bl), mocap_lerp(f0[32], f1[32], bl), mocap_lerp(f0[33], f1[33], bl)}, 1.f);
@@ -360,42 +431,30 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
                 R[7] = lin.x, R[8] = lin.y, R[9] = lin.z;
                 R[10] = ang.x, R[11] = ang.y, R[12] = ang.z;
             }
-            hla = 0.f;
             float* gah = a.action_history_buf + (size_t)e * QA_ACT_HIST_LEN * QA_NUM_DOF;
             for (int i = lane; i < QA_ACT_HIST_LEN * QA_NUM_DOF; i += 32) gah[i] = 0.f;
             if (lane < 4) a.feet_air_time[e * 4 + lane] = 0.f;
             __syncwarp();
+            if (lane < 4) {                                                     // key-body positions on the mocap root
+                const Quat hq = heading_quat_inv(Quat{R[3], R[4], R[5], R[6]});
+                const Vec3 local = {S.key[el * 12 + lane * 3 + 0] - R[0], S.key[el * 12 + lane * 3 + 1] - R[1],
+                                    S.key[el * 12 + lane * 3 + 2] - R[2]};
+                const Vec3 o = quat_rotate_sgn(hq, local, 1.f);
+                sc[SC_KEY + lane * 3 + 0] = o.x, sc[SC_KEY + lane * 3 + 1] = o.y, sc[SC_KEY + lane * 3 + 2] = o.z;
+            }
+            __syncwarp();
         }
-        // observations (:261-331) on post-reset root / dof, pre-reset base velocities / angles / contacts
+        // observations (:261-331): post-reset root / dof, pre-reset base velocities / angles / contacts
         const float root_h = R[2] - sc[SC_CH];
-        float* disc = S.disc + el * QA_NUM_OBS_DISC;
-        if (lane < 4) {                                                            // compute_flat_key_pos :1377-1396
-            const Quat hq = heading_quat_inv(Quat{R[3], R[4], R[5], R[6]});
-            const Vec3 local = {S.key[el * 12 + lane * 3 + 0] - R[0], S.key[el * 12 + lane * 3 + 1] - R[1],
-                                S.key[el * 12 + lane * 3 + 2] - R[2]};
-            const Vec3 o = quat_rotate_sgn(hq, local, 1.f);
-            disc[33 + lane * 3 + 0] = o.x * c.s_key_pos;
-            disc[33 + lane * 3 + 1] = o.y * c.s_key_pos;
-            disc[33 + lane * 3 + 2] = o.z * c.s_key_pos;
+        if (lane < 4) {
+            disc[33 + lane * 3 + 0] = sc[SC_KEY + lane * 3 + 0] * c.s_key_pos;
+            disc[33 + lane * 3 + 1] = sc[SC_KEY + lane * 3 + 1] * c.s_key_pos;
+            disc[33 + lane * 3 + 2] = sc[SC_KEY + lane * 3 + 2] * c.s_key_pos;
             const float cf_ = S.cfilt_out[el * 4 + lane] ? 1.f : 0.f;
             row[41 + lane] = cf_ - 0.5f;
-            row[61 + lane] = S.mass[el * 4 + lane];
             disc[45 + lane] = cf_ * c.s_foot_contact;
         }
-        if (dl) {
-            const float dq = (dof_pos - c.default_dof_pos[lane]) * c.s_dof_pos;
-            const float dv = dof_vel * c.s_dof_vel;
-            row[5 + lane] = dq;
-            row[17 + lane] = dv;
-            row[29 + lane] = hla;
-            row[45 + lane] = 0.f;
-            row[66 + lane] = S.msp[el * 12 + lane] - 1.f;
-            row[78 + lane] = S.msd[el * 12 + lane] - 1.f;
-            disc[9 + lane] = dq;
-            disc[21 + lane] = dv;
-            S.dv_out[el * 12 + lane] = dof_vel;
-        }
-        if (lane < 6) S.lrv[el * 6 + lane] = R[7 + lane];
+        if (lane >= 8 && lane < 14) S.lrv[el * 6 + lane - 8] = R[7 + lane - 8];
         if (lane >= 16 && lane < 19) {
             const int k = lane - 16;
             const float lv = S.blv[el * 3 + k], av = S.bav[el * 3 + k];
@@ -409,7 +468,6 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
             row[0] = roll;
             row[1] = pitch;
             row[57] = c.root_height_obs ? root_h : 0.f;
-            row[65] = S.fric[el];
             disc[0] = roll;
             disc[1] = pitch;
             disc[2] = root_h;
@@ -419,28 +477,19 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
             row[CMD_OFF + k] = k < 5 ? S.cmd[el * 5 + k] : (k == 5 ? S.eps[el] : S.lc[el * 5 + k - 6]);
         }
         __syncwarp();
-        // history (:302-312): staged through registers so that the in-place shift of the tile is hazard free
         {
-            const bool fill = S.ep[el] <= 1;
             float* h = S.hist + el * HIST_W;
-            float hv[(HIST_W + 31) / 32];
-#pragma unroll
-            for (int k = 0; k < (HIST_W + 31) / 32; ++k) {
-                const int i = k * 32 + lane;
-                float v = 0.f;
-                if (i < HIST_W) {
-                    if (fill) v = row[i % QA_NUM_PROP];
-                    else v = (i < HIST_W - QA_NUM_PROP) ? h[i + QA_NUM_PROP] : row[i - (HIST_W - QA_NUM_PROP)];
+            if (S.ep[el] <= 1) {                                                   // fill: all 10 slots = current 57-vector
+                for (int i = lane; i < HIST_W; i += 32) {
+                    const float v = row[i % QA_NUM_PROP];
+                    row[HIST_OFF + i] = v;
+                    h[i] = clampf(v, -c.clip_obs, c.clip_obs);
                 }
-                hv[k] = v;
-            }
-            __syncwarp();
-#pragma unroll
-            for (int k = 0; k < (HIST_W + 31) / 32; ++k) {
-                const int i = k * 32 + lane;
-                if (i < HIST_W) {
-                    row[HIST_OFF + i] = hv[k];
-                    h[i] = clampf(hv[k], -c.clip_obs, c.clip_obs);
+            } else {                                                               // newest slot only (shift done in P3a)
+                for (int i = lane; i < QA_NUM_PROP; i += 32) {
+                    const float v = row[i];
+                    row[HIST_OFF + HIST_W - QA_NUM_PROP + i] = v;
+                    h[HIST_W - QA_NUM_PROP + i] = clampf(v, -c.clip_obs, c.clip_obs);
                 }
             }
         }

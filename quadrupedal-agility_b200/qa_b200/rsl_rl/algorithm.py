@@ -112,7 +112,7 @@ class SSInfoGAIL:
                  lr_q=1e-3, max_grad_norm=1.0, use_clipped_value_loss=False, schedule="fixed", desired_kl=0.01,
                  device='cpu', disc_replay_buffer_size=100000, min_std=None, us_coef=1.0, ss_coef=4.0,
                  prior_soft_coef=1e-3, info_max_coef=2.0, begin_rim=100, priv_reg_coef_schedual=[0, 0.1, 0, 1],
-                 priv_reg_coef_schedual_resume=[0, 0.1, 0, 1], use_cuda_graph=True, fused_loss=True):
+                 priv_reg_coef_schedual_resume=[0, 0.1, 0, 1], use_cuda_graph=True, fused_loss=True, capture_collectives=True):
         self.device, self.env = device, env
         self.desired_kl, self.schedule = desired_kl, schedule
         self.lr_disc, self.lr_q, self.min_std = lr_disc, lr_q, min_std
@@ -150,6 +150,9 @@ class SSInfoGAIL:
         self.use_cuda_graph = use_cuda_graph and torch.device(device).type == "cuda"
         self._graphs = None
         self.fused_loss = fused_loss and torch.device(device).type == "cuda"
+        self.capture_collectives = capture_collectives
+        self._graph_has_apply = True
+        torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)   # capture runs on a side stream
         self._ppo_stats = torch.zeros(4, device=device)
         self._priv_reg_coef = torch.zeros((), device=device)
         self._stats = torch.zeros(len(STAT_NAMES), device=device)
@@ -333,7 +336,9 @@ class SSInfoGAIL:
                 self._minibatch_step()
         torch.cuda.current_stream().wait_stream(s)
         before = ops.launches
-        if self.world_size == 1:
+        self._graph_has_apply = True
+        if self.world_size == 1 or self.capture_collectives:
+            # single graph; with > 1 rank the NCCL all-reduces of the flat gradients are captured as graph nodes
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self._minibatch_step()
@@ -343,6 +348,7 @@ class SSInfoGAIL:
             with torch.cuda.graph(g1):
                 self._forward_backward()
             self._graphs = (g1,)
+            self._graph_has_apply = False
         self._graph_launches = ops.launches - before         # libqa_b200 kernels inside one replay
         # undo the warm-up / capture side effects on the trainable state
         for t, v in zip((self.ac_flat.data, self.est_flat.data, self.optim_ac.exp_avg, self.optim_ac.exp_avg_sq,
@@ -377,7 +383,7 @@ class SSInfoGAIL:
                 if self.use_cuda_graph:
                     self._graphs[0].replay()
                     ops._count(self._graph_launches)
-                    if self.world_size > 1:
+                    if not self._graph_has_apply:
                         self._apply()
                 else:
                     self._minibatch_step()
