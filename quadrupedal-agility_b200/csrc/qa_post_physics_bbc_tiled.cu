@@ -61,7 +61,6 @@ struct __align__(16) T2Smem {
     uint8_t cont_out[T2_ENVS * 4], cfilt_out[T2_ENVS * 4];
     float scal[T2_ENVS][SC_N];
     uint64_t bar;
-    int last;
 };
 
 // thread-level resampler (same arithmetic as resample_env)
@@ -86,14 +85,12 @@ __device__ __forceinline__ void resample_thread(const QaBbcConst& c, const K2Dra
 
 __global__ void __launch_bounds__(T2_THREADS, 4)
 k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_constant__ QaBbcStepArgs a_in) {
-    const K2Step a(a_in);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     T2Smem& S = *reinterpret_cast<T2Smem*>(smem_raw);
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int e0 = blockIdx.x * T2_ENVS;
     const int B = c.num_bodies;
-    const size_t nd = (size_t)a.num_envs * QA_NUM_DOF;
 
     // ---------------- P0: stage every per-env array of this tile ------------------------------------------
     if (tid == 0) {
@@ -102,33 +99,43 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
-    if (tid == 0) {
+    {
+        // 19 tiles, one issuing thread each (the issue latency of ~20 serial bulk copies was on the critical path);
+        // thread 0 arms the barrier with the total byte count
         const unsigned n12 = T2_ENVS * 12 * 4;
         const unsigned cf_bytes = (unsigned)(T2_ENVS * B * 3 * 4);
-        const unsigned total = T2_ENVS * HIST_W * 4 + T2_ENVS * 13 * 4 + T2_ENVS * 24 * 4 + cf_bytes + 7 * n12 +
-                               T2_ENVS * 5 * 4 * 2 + T2_ENVS * 4 + T2_ENVS * 4 * 4 + T2_ENVS * 4 +
-                               T2_ENVS * QA_EPSUM_PITCH * 4 + T2_ENVS * 8 + T2_ENVS * 4;
-        mbar_expect_tx(&S.bar, total);
-        bulk_load_tile(S.hist, a.obs_history_buf + (size_t)e0 * HIST_W, T2_ENVS * HIST_W * 4, &S.bar);
-        bulk_load_tile(S.root, a.root_states + (size_t)e0 * 13, T2_ENVS * 13 * 4, &S.bar);
-        bulk_load_tile(S.dof, a.dof_state + (size_t)e0 * 24, T2_ENVS * 24 * 4, &S.bar);
-        bulk_load_tile(S.cf, a.contact_forces + (size_t)e0 * B * 3, cf_bytes, &S.bar);
-        bulk_load_tile(S.act, a.actions + (size_t)e0 * 12, n12, &S.bar);
-        bulk_load_tile(S.lact, a.last_actions + (size_t)e0 * 12, n12, &S.bar);
-        bulk_load_tile(S.tq, a.torques_org + (size_t)e0 * 12, n12, &S.bar);
-        bulk_load_tile(S.ltq, a.last_torques_org + (size_t)e0 * 12, n12, &S.bar);
-        bulk_load_tile(S.ldv, a.last_dof_vel + (size_t)e0 * 12, n12, &S.bar);
-        bulk_load_tile(S.msp, a.motor_strength + (size_t)e0 * 12, n12, &S.bar);
-        bulk_load_tile(S.msd, a.motor_strength + nd + (size_t)e0 * 12, n12, &S.bar);
-        bulk_load_tile(S.cmd, a.commands + (size_t)e0 * 5, T2_ENVS * 5 * 4, &S.bar);
-        bulk_load_tile(S.lc, a.latent_c + (size_t)e0 * 5, T2_ENVS * 5 * 4, &S.bar);
-        bulk_load_tile(S.eps, a.latent_eps + e0, T2_ENVS * 4, &S.bar);
-        bulk_load_tile(S.mass, a.mass_params + (size_t)e0 * 4, T2_ENVS * 4 * 4, &S.bar);
-        bulk_load_tile(S.fric, a.friction_coeffs + e0, T2_ENVS * 4, &S.bar);
-        bulk_load_tile(S.epsum, a.episode_sums + (size_t)e0 * QA_EPSUM_PITCH, T2_ENVS * QA_EPSUM_PITCH * 4, &S.bar);
-        bulk_load_tile(S.ep, a.episode_length_buf + e0, T2_ENVS * 8, &S.bar);
-        bulk_load_tile(S.lcont, a.last_contacts + (size_t)e0 * 4, T2_ENVS * 4, &S.bar);
+        const QaBbcStepArgs& r = a_in;
+        const size_t nd_ = (size_t)r.num_envs * QA_NUM_DOF;
+        if (tid == 0) {
+            const unsigned total = T2_ENVS * HIST_W * 4 + T2_ENVS * 13 * 4 + T2_ENVS * 24 * 4 + cf_bytes + 7 * n12 +
+                                   T2_ENVS * 5 * 4 * 2 + T2_ENVS * 4 + T2_ENVS * 4 * 4 + T2_ENVS * 4 +
+                                   T2_ENVS * QA_EPSUM_PITCH * 4 + T2_ENVS * 8 + T2_ENVS * 4;
+            mbar_expect_tx(&S.bar, total);
+        }
+        switch (tid) {
+            case 0: bulk_load_tile(S.hist, r.obs_history_buf + (size_t)e0 * HIST_W, T2_ENVS * HIST_W * 4, &S.bar); break;
+            case 1: bulk_load_tile(S.root, r.root_states + (size_t)e0 * 13, T2_ENVS * 13 * 4, &S.bar); break;
+            case 2: bulk_load_tile(S.dof, r.dof_state + (size_t)e0 * 24, T2_ENVS * 24 * 4, &S.bar); break;
+            case 3: bulk_load_tile(S.cf, r.contact_forces + (size_t)e0 * B * 3, cf_bytes, &S.bar); break;
+            case 4: bulk_load_tile(S.act, r.actions + (size_t)e0 * 12, n12, &S.bar); break;
+            case 5: bulk_load_tile(S.lact, r.last_actions + (size_t)e0 * 12, n12, &S.bar); break;
+            case 6: bulk_load_tile(S.tq, r.torques_org + (size_t)e0 * 12, n12, &S.bar); break;
+            case 7: bulk_load_tile(S.ltq, r.last_torques_org + (size_t)e0 * 12, n12, &S.bar); break;
+            case 8: bulk_load_tile(S.ldv, r.last_dof_vel + (size_t)e0 * 12, n12, &S.bar); break;
+            case 9: bulk_load_tile(S.msp, r.motor_strength + (size_t)e0 * 12, n12, &S.bar); break;
+            case 10: bulk_load_tile(S.msd, r.motor_strength + nd_ + (size_t)e0 * 12, n12, &S.bar); break;
+            case 11: bulk_load_tile(S.cmd, r.commands + (size_t)e0 * 5, T2_ENVS * 5 * 4, &S.bar); break;
+            case 12: bulk_load_tile(S.lc, r.latent_c + (size_t)e0 * 5, T2_ENVS * 5 * 4, &S.bar); break;
+            case 13: bulk_load_tile(S.eps, r.latent_eps + e0, T2_ENVS * 4, &S.bar); break;
+            case 14: bulk_load_tile(S.mass, r.mass_params + (size_t)e0 * 4, T2_ENVS * 4 * 4, &S.bar); break;
+            case 15: bulk_load_tile(S.fric, r.friction_coeffs + e0, T2_ENVS * 4, &S.bar); break;
+            case 16: bulk_load_tile(S.epsum, r.episode_sums + (size_t)e0 * QA_EPSUM_PITCH, T2_ENVS * QA_EPSUM_PITCH * 4, &S.bar); break;
+            case 17: bulk_load_tile(S.ep, r.episode_length_buf + e0, T2_ENVS * 8, &S.bar); break;
+            case 18: bulk_load_tile(S.lcont, r.last_contacts + (size_t)e0 * 4, T2_ENVS * 4, &S.bar); break;
+            default: break;
+        }
     }
+    const K2Step a(a_in);                  // per-step scalars (device counter read) only after the loads are in flight
     if (tid < T2_ENVS * 12) {                      // the two strided inputs, straight to shared memory
         const int el = tid / 12, k = tid - el * 12;
         const int j = k / 3, x = k - j * 3;
@@ -481,9 +488,9 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
             float* h = S.hist + el * HIST_W;
             if (S.ep[el] <= 1) {                                                   // fill: all 10 slots = current 57-vector
                 for (int i = lane; i < HIST_W; i += 32) {
-                    const float v = row[i % QA_NUM_PROP];
+                    const float v = clampf(row[i % QA_NUM_PROP], -c.clip_obs, c.clip_obs);
                     row[HIST_OFF + i] = v;
-                    h[i] = clampf(v, -c.clip_obs, c.clip_obs);
+                    h[i] = v;
                 }
             } else {                                                               // newest slot only (shift done in P3a)
                 for (int i = lane; i < QA_NUM_PROP; i += 32) {
@@ -508,7 +515,10 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
             row[i] = row[i] + (2.f * u - 1.f) * c.noise_scale[k];
         }
         __syncwarp();
-        for (int i = lane; i < ROW; i += 32) row[i] = clampf(row[i], -c.clip_obs, c.clip_obs);
+        // clip: the 9 older history slots were clamped when they were shifted (P3a) / filled, and noise never lands on
+        // history lanes (checked by the host when it builds the noise list), so only [0, 90) and [603, 671) remain
+        for (int i = lane; i < HIST_OFF; i += 32) row[i] = clampf(row[i], -c.clip_obs, c.clip_obs);
+        for (int i = HIST_OFF + HIST_W - QA_NUM_PROP + lane; i < ROW; i += 32) row[i] = clampf(row[i], -c.clip_obs, c.clip_obs);
         if (lane < 4) {
             if (a.contact_buf)
                 a.contact_buf[((size_t)e * a.contact_ring_len + a.contact_ring_head) * 4 + lane] =
@@ -555,38 +565,33 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
         // to the next kernel at kernel end.  The shared-memory source is released by the .read wait at the end.
     }
 
-    // ---------------- epilogue: reset statistics, last CTA finalises (as in k_post_physics_bbc) ------------------
-    __threadfence();
+    // reset statistics are finalised by k_k2_finalize (one CTA, launched right behind this kernel): no grid-wide ticket,
+    // no __threadfence on the critical path of the 512 tiles
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+// One CTA behind the tiled kernel: episode reward means of the envs that reset (:230-234), extras["time_outs"] latch
+// (:239-240, only when >= 1 env reset), device step counter, workspace re-arm.
+__global__ void __launch_bounds__(256) k_k2_finalize(const __grid_constant__ QaBbcConst c, const __grid_constant__ QaBbcStepArgs a_in) {
+    const K2Step a(a_in);
+    K2Workspace* ws = reinterpret_cast<K2Workspace*>(a.workspace);
+    const int tid = threadIdx.x;
+    const unsigned cnt = ws->reset_count;
+    if (cnt > 0) {
+        if (tid < QA_NUM_REWARDS) {
+            const float mean = (float)(ws->sums[tid] / (double)cnt);
+            a.episode_rew_means[tid] = mean / c.episode_length_s;
+        }
+        for (int i = tid; i < a.num_envs; i += blockDim.x) a.time_outs_latched[i] = a.time_out_buf[i];
+    }
     __syncthreads();
     if (tid == 0) {
-        K2Workspace* ws = reinterpret_cast<K2Workspace*>(a.workspace);
-        const unsigned t = atomicAdd(&ws->ticket, 1u);
-        S.last = (t == gridDim.x - 1) ? 1 : 0;
+        *a.num_resets = (int)cnt;
+        if (a.step_state != nullptr) a.step_state[0] = (long long)a.rng_step;
+        ws->reset_count = 0u;
+        ws->ticket = 0u;
     }
-    __syncthreads();
-    if (S.last) {
-        __threadfence();
-        K2Workspace* ws = reinterpret_cast<K2Workspace*>(a.workspace);
-        const unsigned cnt = *reinterpret_cast<volatile unsigned*>(&ws->reset_count);
-        if (cnt > 0) {
-            if (tid < QA_NUM_REWARDS) {
-                const double s = *reinterpret_cast<volatile double*>(&ws->sums[tid]);
-                const float mean = (float)(s / (double)cnt);
-                a.episode_rew_means[tid] = mean / c.episode_length_s;
-            }
-            const volatile uint8_t* src = a.time_out_buf;
-            for (int i = tid; i < a.num_envs; i += T2_THREADS) a.time_outs_latched[i] = src[i];
-        }
-        __syncthreads();
-        if (tid == 0) {
-            *a.num_resets = (int)cnt;
-            if (a.step_state != nullptr) a.step_state[0] = (long long)a.rng_step;
-            ws->reset_count = 0u;
-            ws->ticket = 0u;
-        }
-        if (tid < QA_NUM_REWARDS) ws->sums[tid] = 0.0;
-    }
-    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    if (tid < QA_NUM_REWARDS) ws->sums[tid] = 0.0;
 }
 
 static bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
@@ -597,6 +602,8 @@ int qa_k2_try_launch_tiled(const QaBbcConst* c, const QaBbcStepArgs* a, cudaStre
     if (!(a->flags & QA_K2_TILED)) return 0;
     if (a->num_envs % T2_ENVS != 0 || a->obs_pitch != QA_OBS_WIDTH || c->num_bodies > 32) return 0;
     if (c->num_noise < 0 || c->num_noise > QA_MAX_NOISE_LANES) return QA_ERANGE;
+    for (int k = 0; k < c->num_noise; ++k)                       // the tiled kernel clips shifted history lanes before noise
+        if (c->noise_idx[k] >= HIST_OFF && c->noise_idx[k] < HIST_OFF + HIST_W - QA_NUM_PROP) return 0;
     const void* ptrs[] = {a->obs_buf, a->privileged_obs_buf, a->obs_history_buf, a->obs_disc_buf, a->root_states,
                           a->dof_state, a->contact_forces, a->actions, a->last_actions, a->torques_org,
                           a->last_torques_org, a->last_dof_vel, a->last_root_vel, a->motor_strength, a->commands,
@@ -616,5 +623,8 @@ int qa_k2_try_launch_tiled(const QaBbcConst* c, const QaBbcStepArgs* a, cudaStre
     k_post_physics_bbc_tiled<<<a->num_envs / T2_ENVS, T2_THREADS, sizeof(T2Smem), stream>>>(*c, *a);
     *launched = 1;
     cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    k_k2_finalize<<<1, 256, 0, stream>>>(*c, *a);
+    e = cudaGetLastError();
     return e == cudaSuccess ? 0 : (int)e;
 }
