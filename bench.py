@@ -38,6 +38,15 @@ ENVS_PER_GPU = 4096
 K2_BYTES_PER_ENV = 11158          # algorithmic bytes of the fused obs/reward kernel per env-step
 
 
+def k2_traffic():
+    """DRAM bytes per K2 launch from the committed `ncu --set full` capture (profiles/k2_traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "k2_traffic.json")
+    if not os.path.isfile(p):
+        return None
+    t = json.load(open(p))
+    return t["dram_bytes_read"] + t["dram_bytes_write"] if t.get("n_envs") == ENVS_PER_GPU else None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -199,7 +208,7 @@ def run_ours(args):
                          "us_per_launch": k2_avg_s * 1e6, "launches_timed": k2_launches,
                          "how": "CUDA events around graph replays of the rollout's 24 K2 launches (24 distinct state "
                                 "snapshots), 256 MiB L2 flush before each replay",
-                         "algorithmic_bytes_per_launch": K2_BYTES_PER_ENV * cfg.num_envs, "traffic": it.k2_traffic_bytes},
+                         "algorithmic_bytes_per_launch": K2_BYTES_PER_ENV * cfg.num_envs, "traffic": k2_traffic()},
             "clocks": clocks,
         }
         if cpu is not None:

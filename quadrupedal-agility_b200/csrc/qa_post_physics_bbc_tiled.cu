@@ -63,6 +63,35 @@ struct __align__(16) T2Smem {
     uint64_t bar;
 };
 
+// Optional phase trace (tools/k2_trace.py builds a -DQA_K2_TRACE variant of the library; never in the product build):
+// per-CTA clock64 stamps at the phase boundaries, slots 0..15, plus %globaltimer at entry / exit in slots 16, 17.
+#ifdef QA_K2_TRACE
+#define K2_TRACE_CTAS 1024
+__device__ long long g_k2_trace[K2_TRACE_CTAS][20];
+__device__ __forceinline__ long long k2_gtime() {
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define STAMP(slot, who)                                                                   \
+    do {                                                                                   \
+        if (threadIdx.x == (who) && blockIdx.x < K2_TRACE_CTAS) g_k2_trace[blockIdx.x][slot] = clock64(); \
+    } while (0)
+#define GSTAMP(slot, who)                                                                  \
+    do {                                                                                   \
+        if (threadIdx.x == (who) && blockIdx.x < K2_TRACE_CTAS) g_k2_trace[blockIdx.x][slot] = k2_gtime(); \
+    } while (0)
+extern "C" int qa_k2_trace_dump(long long* host, int max_ctas) {
+    const int n = max_ctas < K2_TRACE_CTAS ? max_ctas : K2_TRACE_CTAS;
+    return (int)cudaMemcpyFromSymbol(host, g_k2_trace, sizeof(long long) * 20 * n);
+}
+#else
+#define STAMP(slot, who) do { } while (0)
+#define GSTAMP(slot, who) do { } while (0)
+#endif
+#define T_ENV 0                          // first env warp, lane 0
+#define T_SCL (T2_ENVS * 32)             // scalar warp, lane 0
+
 // thread-level resampler (same arithmetic as resample_env)
 __device__ __forceinline__ void resample_thread(const QaBbcConst& c, const K2Draw& d, float* cmd, float* eps, float* lc) {
     const int m = d.c_idx;
@@ -91,6 +120,9 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int e0 = blockIdx.x * T2_ENVS;
     const int B = c.num_bodies;
+    GSTAMP(16, T_ENV);
+    STAMP(0, T_ENV);
+    STAMP(8, T_SCL);
 
     // ---------------- P0: stage every per-env array of this tile ------------------------------------------
     if (tid == 0) {
@@ -143,8 +175,12 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
         S.alast[tid] = a.action_history_buf[(size_t)(e0 + el) * QA_ACT_HIST_LEN * QA_NUM_DOF +
                                             (QA_ACT_HIST_LEN - 1) * QA_NUM_DOF + k];
     }
+    STAMP(1, T_ENV);
     mbar_wait(&S.bar, 0);
+    STAMP(2, T_ENV);
     __syncthreads();                                        // the two directly-loaded inputs are visible to every warp
+    STAMP(3, T_ENV);
+    STAMP(9, T_SCL);
 
     bool any_state_write = a.do_push != 0;
     // scalar-warp registers that live across the phase barrier (P2a -> P2b)
@@ -298,7 +334,10 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
             R[8] = span * u1 + (-c.max_push_vel_xy);
         }
     }
+    STAMP(4, T_ENV);
+    STAMP(10, T_SCL);
     __syncthreads();                                        // P1 results visible to the scalar warp
+    STAMP(11, T_SCL);
 
     if (wid == T2_ENVS && lane < T2_ENVS) {
         // ---------------- P2b: contacts, termination, reward total, episode sums, reset decision --------------------
@@ -377,7 +416,9 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
         a.time_out_buf[e] = time_out ? 1 : 0;
         any_state_write = any_state_write || is_reset;
     }
+    STAMP(12, T_SCL);
     any_state_write = __syncthreads_or(any_state_write ? 1 : 0) != 0;
+    STAMP(5, T_ENV);
 
     if (wid < T2_ENVS) {
         // ---------------- P3b: reset write (rare), P2-dependent row lanes, last history slot, noise, clip --------------
@@ -530,8 +571,10 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
     }
 
     // ---------------- P4: every output tile leaves through the TMA engine --------------------------------------
+    STAMP(6, T_ENV);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
+    STAMP(7, T_ENV);
     if (tid == 0) {
         const unsigned n12 = T2_ENVS * 12 * 4;
         bulk_store_bytes(a.obs_buf + (size_t)e0 * ROW, S.obs, T2_ENVS * ROW * 4);
@@ -567,7 +610,10 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
 
     // reset statistics are finalised by k_k2_finalize (one CTA, launched right behind this kernel): no grid-wide ticket,
     // no __threadfence on the critical path of the 512 tiles
+    STAMP(13, T_ENV);
     if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    STAMP(14, T_ENV);
+    GSTAMP(17, T_ENV);
 }
 
 // One CTA behind the tiled kernel: episode reward means of the envs that reset (:230-234), extras["time_outs"] latch

@@ -1,0 +1,123 @@
+#!/usr/bin/env python
+"""Phase trace + stand-alone timing of the fused post-physics kernel (K2, tiled variant).
+
+  python tools/k2_trace.py --build          (build container) compile a -DQA_K2_TRACE variant of libqa_b200.so into
+                                            tools/_k2trace/ (git-ignored, travels to the GPU box)
+  python tools/k2_trace.py [--envs N ...]   (GPU box) per-CTA clock64 stamps at the phase boundaries -> median / p90
+                                            of every phase, CTA start skew and kernel span from %globaltimer; then the
+                                            PRODUCT library is NOT touched: timing of the product build is bench.py's job.
+"""
+import argparse
+import ctypes
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "quadrupedal-agility_b200")
+OUT = os.path.join(ROOT, "tools", "_k2trace")
+sys.path.insert(0, PKG)
+sys.path.insert(0, ROOT)
+
+SEGMENTS = [  # (name, stamp_from, stamp_to)
+    ("P0 issue loads (+step counter, strided loads issued)", 0, 1),
+    ("P0 wait for TMA tiles", 1, 2),
+    ("barrier 0", 2, 3),
+    ("env warp: P1 + P3a", 3, 4),
+    ("scalar warp: P2a", 9, 10),
+    ("scalar warp: barrier 1 wait", 10, 11),
+    ("scalar warp: P2b", 11, 12),
+    ("env warp: barrier 1+2 wait (P2a tail + P2b)", 4, 5),
+    ("env warp: P3b", 5, 6),
+    ("barrier 3", 6, 7),
+    ("P4 issue stores", 7, 13),
+    ("P4 wait_group.read", 13, 14),
+    ("whole CTA (entry -> exit)", 0, 14),
+]
+
+
+def build():
+    csrc = os.path.join(PKG, "csrc")
+    os.makedirs(OUT, exist_ok=True)
+    objs, procs = [], []
+    for f in sorted(x for x in os.listdir(csrc) if x.endswith(".cu")):
+        exact = f.startswith(("qa_env_kernels", "qa_post_physics", "qa_gae"))
+        o = os.path.join(OUT, f[:-3] + ".o")
+        objs.append(o)
+        procs.append(subprocess.Popen(
+            ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
+             "-DQA_K2_TRACE", "-I" + os.path.join(ROOT, "include"), "-I" + csrc] + (["-fmad=false"] if exact else []) +
+            ["-c", os.path.join(csrc, f), "-o", o]))
+    for p in procs:
+        if p.wait() != 0:
+            raise SystemExit("nvcc failed")
+    subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", *objs, "-o",
+                    os.path.join(OUT, "libqa_b200.so")], check=True)
+    for o in objs:
+        os.unlink(o)
+    print("built", os.path.join(OUT, "libqa_b200.so"))
+
+
+def run(n_envs, reps):
+    import numpy as np
+    import torch
+    from qa_b200 import _abi
+    _abi.LIB_PATH = os.path.join(OUT, "libqa_b200.so")
+    lib = _abi.load()
+    lib.qa_k2_trace_dump.restype = ctypes.c_int
+    lib.qa_k2_trace_dump.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    import bench
+    from qa_b200.legged_robot import LeggedRobot, RecordedPhysics
+    dev = torch.device("cuda:0")
+    T = 4
+    cfg, static, snaps, table = bench.build_workload(0, dev, n_envs=n_envs, steps=T)
+    dev_snaps = [{k: s[k].to(dev) for k in bench.SIM_KEYS} for s in snaps]
+    env = LeggedRobot(cfg, RecordedPhysics(dev_snaps), static, table, device=dev, seed=1234, bulk_store=True, tiled=True)
+    from qa_b200.pipeline import CARRIED
+    env.load_state({k: v.to(dev) for k, v in snaps[0].items() if k in CARRIED})
+    env.global_counter = 1
+    env.use_device_step_counter(True)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    n_cta = min(n_envs // 8, 1024)
+    host = np.zeros((n_cta, 20), dtype=np.int64)
+    seg = {name: [] for name, _, _ in SEGMENTS}
+    spans, skews, times = [], [], []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for r in range(reps + 2):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        e0.record()
+        env._k2_only_step()
+        e1.record()
+        torch.cuda.synchronize()
+        if r < 2:
+            continue
+        times.append(e0.elapsed_time(e1) * 1e3)
+        rc = lib.qa_k2_trace_dump(host.ctypes.data, n_cta)
+        assert rc == 0, rc
+        g0, g1 = host[:, 16], host[:, 17]
+        spans.append(float(g1.max() - g0.min()) / 1e3)
+        skews.append(float(g0.max() - g0.min()) / 1e3)
+        cyc_per_ns = np.median((host[:, 14] - host[:, 0]) / np.maximum(g1 - g0, 1))
+        for name, a, b in SEGMENTS:
+            seg[name].append((host[:, b] - host[:, a]) / cyc_per_ns / 1e3)
+    print(f"== K2 tiled phase trace: {n_envs} envs, {n_envs // 8} CTAs (first {n_cta} traced), {reps} launches, L2 flushed; "
+          f"clock {cyc_per_ns:.3f} cycles/ns")
+    print(f"event time per launch (eager, incl. finalize kernel): median {np.median(times):.2f} us")
+    print(f"kernel span, first CTA entry -> last CTA exit: median {np.median(spans):.2f} us;  CTA start skew {np.median(skews):.2f} us")
+    for name, _, _ in SEGMENTS:
+        v = np.concatenate(seg[name])
+        print(f"  {name:55s} median {np.median(v):6.2f} us   p90 {np.percentile(v, 90):6.2f}   max {v.max():6.2f}")
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--build", action="store_true")
+    ap.add_argument("--envs", type=int, nargs="*", default=[4096, 32768])
+    ap.add_argument("--reps", type=int, default=10)
+    args = ap.parse_args()
+    if args.build:
+        build()
+    else:
+        for n in args.envs:
+            run(n, args.reps)
