@@ -4,25 +4,32 @@
 // the round-1 profile showed the warp-per-env kernel to be instruction/latency bound (3150 warp-instructions per
 // env, 32x redundant scalar math, serialised global->shared copies), not HBM bound:
 //
-//   P0  one thread issues ~22 TMA bulk loads (cp.async.bulk + mbarrier complete_tx) for EVERY per-env array of
-//       the CTA's 8 envs -- each array's 8-env slice is contiguous and 16 B aligned -- while the other threads
-//       fetch the two strided inputs (feet positions, last action);
-//   P1  (env warps) warp-per-env, lanes = DOFs / bodies: the nine 12-wide reward sums (warp-shuffle butterflies) and
-//       the contact-force norms (ballots) -> per-env scalars in shared memory; then P3a: every lane of the row that
-//       depends on loaded inputs only (DOF lanes, latent lanes, history shift through registers);
-//   P2a (scalar warp, concurrently, thread-per-env = 8 lanes): base-frame quantities, euler angles, centre terrain
-//       height, key-body positions, periodic resampling, push -- SIMD across envs instead of 32x redundant;
-//   P2b (scalar warp, after a barrier): contacts, termination, reward total, episode sums, reset decision;
-//   P3b (env warps): reset envs blend their mocap frame (lanes = frame columns) and rewrite simulator state; the
-//       P2-dependent row lanes, newest history slot, noise on the <= 64 noisy lanes, clip, disc obs;
-//   P4  one thread issues the TMA bulk stores of every output tile (obs, privileged obs, history, disc obs,
-//       last_*, episode sums, commands ...); reset statistics are finalised by the last CTA as in the other kernel.
+//   P0  every load of the tile is put in flight before the first barrier: the two scalar warps fetch what their
+//       thread-per-env programs need (root tile, feet positions, commands, counters; ~1.5 KB) with plain 16-B loads,
+//       8 threads of 8 different warps issue 13 TMA bulk loads (cp.async.bulk + mbarrier complete_tx; every per-env
+//       array's 8-env slice is contiguous and 16 B aligned) -- the 12 small tiles on one mbarrier, the 18 KB history
+//       tile on its own -- and the env warps draw this step's Philox noise while they wait;
+//   P2a (scalar warp A, thread-per-env, starts as soon as ITS loads land): base-frame quantities, euler angles, centre
+//       terrain height, periodic resampling, push;  (scalar warp B, lane = (env, foot)): key-body positions;
+//   P1  (env warps, after the small tiles): warp-per-env, lanes = DOFs / bodies: the nine 12-wide reward sums (warp
+//       shuffle butterflies) and the contact-force norms (ballots) -> per-env scalars; named barrier 1 hands them to
+//   P2b (scalar warp A): contacts, termination, reward total, episode sums, reset decision -- while the env warps run
+//   P3a: the row lanes that depend on loaded inputs only and, once the history tile has landed, the history shift;
+//   P3b (env warps, after barrier 2): reset envs blend their mocap frame (lanes = frame columns) and rewrite simulator
+//       state; the P2-dependent row lanes, newest history slot, noise on the <= 64 noisy lanes, clip, disc obs;
+//       meanwhile scalar warp A writes the ~14 small per-env outputs with plain 16-B stores;
+//   P4  four threads of four warps issue the TMA bulk stores of the big tiles (obs, privileged obs, history, disc obs;
+//       root / dof state only after a reset or push); the CTA that takes the last ticket finalises the reset statistics,
+//       latches extras["time_outs"] and advances the device step counter.
 //
-// Per env this is ~1100 warp-instructions, and all global traffic is full-line bulk copies.
+// Per env this is ~1000 warp-instructions, and all bulk global traffic is full-line copies.
+// profiles/r1_k2_phase_trace.txt has the per-phase clock trace that led here (tools/k2_trace.py).
 #include "qa_k2_common.cuh"
 
 #define T2_ENVS 8
-#define T2_THREADS (T2_ENVS * 32 + 32)   // 8 env warps + 1 scalar warp
+#define T2_THREADS (T2_ENVS * 32 + 64)   // 8 env warps + 2 scalar warps
+#define W_SA T2_ENVS                     // scalar warp A: base-frame quantities, terrain, rewards, reset decision
+#define W_SB (T2_ENVS + 1)               // scalar warp B: key-body positions
 
 // per-env scalar slots (floats) exchanged between the phases
 enum {
@@ -51,16 +58,16 @@ struct __align__(16) T2Smem {
     float epsum[T2_ENVS * QA_EPSUM_PITCH];
     long long ep[T2_ENVS];
     uint8_t lcont[T2_ENVS * 4];
-    float key[T2_ENVS * 12], alast[T2_ENVS * 12];
+    float key[T2_ENVS * 12];
     float disc[T2_ENVS * QA_NUM_OBS_DISC];
-    float dv_out[T2_ENVS * 12];
-    float lrv[T2_ENVS * 6];
     float rew[T2_ENVS], rooth[T2_ENVS];
     float blv[T2_ENVS * 3], bav[T2_ENVS * 3], pg[T2_ENVS * 3], rpy[T2_ENVS * 3];
     float ff[T2_ENVS * 4];
     uint8_t cont_out[T2_ENVS * 4], cfilt_out[T2_ENVS * 4];
     float scal[T2_ENVS][SC_N];
-    uint64_t bar;
+    float rootB[T2_ENVS * 13];           // scalar warp B's private copy of the root tile
+    uint64_t bar, bar_small;
+    unsigned last;
 };
 
 // Optional phase trace (tools/k2_trace.py builds a -DQA_K2_TRACE variant of the library; never in the product build):
@@ -90,7 +97,8 @@ extern "C" int qa_k2_trace_dump(long long* host, int max_ctas) {
 #define GSTAMP(slot, who) do { } while (0)
 #endif
 #define T_ENV 0                          // first env warp, lane 0
-#define T_SCL (T2_ENVS * 32)             // scalar warp, lane 0
+#define T_SA (W_SA * 32)                 // scalar warp A, lane 0
+#define T_SB (W_SB * 32)                 // scalar warp B, lane 0
 
 // thread-level resampler (same arithmetic as resample_env)
 __device__ __forceinline__ void resample_thread(const QaBbcConst& c, const K2Draw& d, float* cmd, float* eps, float* lc) {
@@ -112,6 +120,28 @@ __device__ __forceinline__ void resample_thread(const QaBbcConst& c, const K2Dra
     for (int k = 0; k < QA_DIM_C; ++k) lc[k] = (k == m) ? 1.f : 0.f;
 }
 
+// sum over the low 16 lanes (lanes 12..15 hold zeros): the 16-offset step of warp_sum would only add zeros
+__device__ __forceinline__ float half_warp_sum(float v) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(QA_FULL, v, o);
+    return v;
+}
+
+// 64-bit counters that in practice fit 32 bits: take the short hardware-divide path (the 64-bit software modulo was
+// ~10 % of the kernel's instructions)
+__device__ __forceinline__ bool divisible_by(long long v, int period) {
+    const unsigned long long u = (unsigned long long)v;
+    if ((u >> 32) == 0ull) return ((unsigned)u % (unsigned)period) == 0u;
+    return (v % (long long)period) == 0;
+}
+
+__device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+__device__ __forceinline__ void copy16(void* gdst, const void* ssrc, int n16, int lane) {
+    for (int i = lane; i < n16; i += 32) reinterpret_cast<float4*>(gdst)[i] = reinterpret_cast<const float4*>(ssrc)[i];
+}
+
 __global__ void __launch_bounds__(T2_THREADS, 4)
 k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_constant__ QaBbcStepArgs a_in) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -120,101 +150,127 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int e0 = blockIdx.x * T2_ENVS;
     const int B = c.num_bodies;
+    const QaBbcStepArgs& r = a_in;
     GSTAMP(16, T_ENV);
     STAMP(0, T_ENV);
-    STAMP(8, T_SCL);
 
-    // ---------------- P0: stage every per-env array of this tile ------------------------------------------
+    // ---------------- P0: every load of the tile is put in flight before the first barrier -----------------------
+    // scalar warps fetch what their thread-per-env programs need with plain 16-B loads (they start computing as soon
+    // as those ~1 KB land, long before the 18 KB history tile); env warps fetch their last action
+    float4 ld0 = {0.f, 0.f, 0.f, 0.f}, ld1 = {0.f, 0.f, 0.f, 0.f};
+    float4* st1 = nullptr;
+    float k0 = 0.f, k1 = 0.f, k2 = 0.f, alast = 0.f;
+    if (wid == W_SA) {
+        if (lane < 26) ld0 = reinterpret_cast<const float4*>(r.root_states + (size_t)e0 * 13)[lane];
+        const float4* g = nullptr;
+        if (lane < 10) g = reinterpret_cast<const float4*>(r.commands + (size_t)e0 * 5) + lane, st1 = reinterpret_cast<float4*>(S.cmd) + lane;
+        else if (lane < 20) g = reinterpret_cast<const float4*>(r.latent_c + (size_t)e0 * 5) + (lane - 10), st1 = reinterpret_cast<float4*>(S.lc) + (lane - 10);
+        else if (lane < 22) g = reinterpret_cast<const float4*>(r.latent_eps + e0) + (lane - 20), st1 = reinterpret_cast<float4*>(S.eps) + (lane - 20);
+        else if (lane < 26) g = reinterpret_cast<const float4*>(r.episode_length_buf + e0) + (lane - 22), st1 = reinterpret_cast<float4*>(S.ep) + (lane - 22);
+        else if (lane < 28) g = reinterpret_cast<const float4*>(r.last_contacts + (size_t)e0 * 4) + (lane - 26), st1 = reinterpret_cast<float4*>(S.lcont) + (lane - 26);
+        if (g != nullptr) ld1 = *g;
+    } else if (wid == W_SB) {
+        if (lane < 26) ld0 = reinterpret_cast<const float4*>(r.root_states + (size_t)e0 * 13)[lane];
+        // feet positions: 8 envs x 4 feet x 3, three per lane
+        const int el = lane >> 2, j = lane & 3;
+        const float* kp = r.rigid_body_state + ((size_t)(e0 + el) * B + c.feet_indices[j]) * 13;
+        k0 = kp[0], k1 = kp[1], k2 = kp[2];
+    } else if (lane < QA_NUM_DOF) {
+        alast = r.action_history_buf[(size_t)(e0 + wid) * QA_ACT_HIST_LEN * QA_NUM_DOF + (QA_ACT_HIST_LEN - 1) * QA_NUM_DOF + lane];
+    }
     if (tid == 0) {
+        mbar_init(&S.bar_small, 12);
         mbar_init(&S.bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
-    {
-        // 19 tiles, one issuing thread each (the issue latency of ~20 serial bulk copies was on the critical path);
-        // thread 0 arms the barrier with the total byte count
+    if (wid < T2_ENVS && lane == 0) {
+        // 13 TMA bulk loads, issued from 8 warps in parallel (two rounds): the 12 small tiles complete on bar_small,
+        // the history tile -- 60 % of the bytes, needed last -- on its own barrier
         const unsigned n12 = T2_ENVS * 12 * 4;
-        const unsigned cf_bytes = (unsigned)(T2_ENVS * B * 3 * 4);
-        const QaBbcStepArgs& r = a_in;
         const size_t nd_ = (size_t)r.num_envs * QA_NUM_DOF;
-        if (tid == 0) {
-            const unsigned total = T2_ENVS * HIST_W * 4 + T2_ENVS * 13 * 4 + T2_ENVS * 24 * 4 + cf_bytes + 7 * n12 +
-                                   T2_ENVS * 5 * 4 * 2 + T2_ENVS * 4 + T2_ENVS * 4 * 4 + T2_ENVS * 4 +
-                                   T2_ENVS * QA_EPSUM_PITCH * 4 + T2_ENVS * 8 + T2_ENVS * 4;
-            mbar_expect_tx(&S.bar, total);
-        }
-        switch (tid) {
-            case 0: bulk_load_tile(S.hist, r.obs_history_buf + (size_t)e0 * HIST_W, T2_ENVS * HIST_W * 4, &S.bar); break;
-            case 1: bulk_load_tile(S.root, r.root_states + (size_t)e0 * 13, T2_ENVS * 13 * 4, &S.bar); break;
-            case 2: bulk_load_tile(S.dof, r.dof_state + (size_t)e0 * 24, T2_ENVS * 24 * 4, &S.bar); break;
-            case 3: bulk_load_tile(S.cf, r.contact_forces + (size_t)e0 * B * 3, cf_bytes, &S.bar); break;
-            case 4: bulk_load_tile(S.act, r.actions + (size_t)e0 * 12, n12, &S.bar); break;
-            case 5: bulk_load_tile(S.lact, r.last_actions + (size_t)e0 * 12, n12, &S.bar); break;
-            case 6: bulk_load_tile(S.tq, r.torques_org + (size_t)e0 * 12, n12, &S.bar); break;
-            case 7: bulk_load_tile(S.ltq, r.last_torques_org + (size_t)e0 * 12, n12, &S.bar); break;
-            case 8: bulk_load_tile(S.ldv, r.last_dof_vel + (size_t)e0 * 12, n12, &S.bar); break;
-            case 9: bulk_load_tile(S.msp, r.motor_strength + (size_t)e0 * 12, n12, &S.bar); break;
-            case 10: bulk_load_tile(S.msd, r.motor_strength + nd_ + (size_t)e0 * 12, n12, &S.bar); break;
-            case 11: bulk_load_tile(S.cmd, r.commands + (size_t)e0 * 5, T2_ENVS * 5 * 4, &S.bar); break;
-            case 12: bulk_load_tile(S.lc, r.latent_c + (size_t)e0 * 5, T2_ENVS * 5 * 4, &S.bar); break;
-            case 13: bulk_load_tile(S.eps, r.latent_eps + e0, T2_ENVS * 4, &S.bar); break;
-            case 14: bulk_load_tile(S.mass, r.mass_params + (size_t)e0 * 4, T2_ENVS * 4 * 4, &S.bar); break;
-            case 15: bulk_load_tile(S.fric, r.friction_coeffs + e0, T2_ENVS * 4, &S.bar); break;
-            case 16: bulk_load_tile(S.epsum, r.episode_sums + (size_t)e0 * QA_EPSUM_PITCH, T2_ENVS * QA_EPSUM_PITCH * 4, &S.bar); break;
-            case 17: bulk_load_tile(S.ep, r.episode_length_buf + e0, T2_ENVS * 8, &S.bar); break;
-            case 18: bulk_load_tile(S.lcont, r.last_contacts + (size_t)e0 * 4, T2_ENVS * 4, &S.bar); break;
-            default: break;
+#pragma unroll
+        for (int round = 0; round < 2; ++round) {
+            void* dst = nullptr;
+            const void* src = nullptr;
+            unsigned bytes = 0;
+            switch (wid + round * 8) {
+                case 0: dst = S.dof, src = r.dof_state + (size_t)e0 * 24, bytes = T2_ENVS * 24 * 4; break;
+                case 1: dst = S.cf, src = r.contact_forces + (size_t)e0 * B * 3, bytes = (unsigned)(T2_ENVS * B * 3 * 4); break;
+                case 2: dst = S.act, src = r.actions + (size_t)e0 * 12, bytes = n12; break;
+                case 3: dst = S.lact, src = r.last_actions + (size_t)e0 * 12, bytes = n12; break;
+                case 4: dst = S.tq, src = r.torques_org + (size_t)e0 * 12, bytes = n12; break;
+                case 5: dst = S.ltq, src = r.last_torques_org + (size_t)e0 * 12, bytes = n12; break;
+                case 6: dst = S.ldv, src = r.last_dof_vel + (size_t)e0 * 12, bytes = n12; break;
+                case 7: dst = S.msp, src = r.motor_strength + (size_t)e0 * 12, bytes = n12; break;
+                case 8: dst = S.msd, src = r.motor_strength + nd_ + (size_t)e0 * 12, bytes = n12; break;
+                case 9: dst = S.mass, src = r.mass_params + (size_t)e0 * 4, bytes = T2_ENVS * 4 * 4; break;
+                case 10: dst = S.fric, src = r.friction_coeffs + e0, bytes = T2_ENVS * 4; break;
+                case 11: dst = S.epsum, src = r.episode_sums + (size_t)e0 * QA_EPSUM_PITCH, bytes = T2_ENVS * QA_EPSUM_PITCH * 4; break;
+                case 12: dst = S.hist, src = r.obs_history_buf + (size_t)e0 * HIST_W, bytes = T2_ENVS * HIST_W * 4; break;
+                default: break;
+            }
+            if (dst != nullptr) {
+                uint64_t* bar = (wid + round * 8 == 12) ? &S.bar : &S.bar_small;
+                mbar_expect_tx(bar, bytes);
+                bulk_load_tile(dst, src, bytes, bar);
+            }
         }
     }
     const K2Step a(a_in);                  // per-step scalars (device counter read) only after the loads are in flight
-    if (tid < T2_ENVS * 12) {                      // the two strided inputs, straight to shared memory
-        const int el = tid / 12, k = tid - el * 12;
-        const int j = k / 3, x = k - j * 3;
-        S.key[tid] = a.rigid_body_state[((size_t)(e0 + el) * B + c.feet_indices[j]) * 13 + x];
-        S.alast[tid] = a.action_history_buf[(size_t)(e0 + el) * QA_ACT_HIST_LEN * QA_NUM_DOF +
-                                            (QA_ACT_HIST_LEN - 1) * QA_NUM_DOF + k];
-    }
-    STAMP(1, T_ENV);
-    mbar_wait(&S.bar, 0);
-    STAMP(2, T_ENV);
-    __syncthreads();                                        // the two directly-loaded inputs are visible to every warp
-    STAMP(3, T_ENV);
-    STAMP(9, T_SCL);
 
     bool any_state_write = a.do_push != 0;
-    // scalar-warp registers that live across the phase barrier (P2a -> P2b)
-    Vec3 blv = {0.f, 0.f, 0.f}, bav = {0.f, 0.f, 0.f};
-    float center_h = 0.f;
-    long long ep = 0;
 
     if (wid < T2_ENVS) {
-        // ---------------- P1: warp-per-env DOF sums and contact-force norms --------------------------------
-        const int el = wid;
+        const int el = wid, e = e0 + el;
         const bool dl = lane < QA_NUM_DOF;
         const int d_ = dl ? lane : 0;
+        // noise of this step (:318-319) needs nothing but (env, lane, step): drawn while the tiles are in flight
+        float nz[QA_MAX_NOISE_LANES / 32];
+#pragma unroll
+        for (int kk = 0; kk < QA_MAX_NOISE_LANES / 32; ++kk) {
+            const int k = kk * 32 + lane;
+            nz[kk] = 0.f;
+            if (k < c.num_noise) {
+                const int i = c.noise_idx[k];
+                float u;
+                if (a.noise_u != nullptr) {
+                    u = a.noise_u[(size_t)e * ROW + i];
+                } else {
+                    Philox4 rr = philox4x32_10((uint32_t)e, SITE_NOISE0 + (i >> 2), (uint32_t)a.rng_step,
+                                               (uint32_t)(a.rng_step >> 32), (uint32_t)a.rng_seed, (uint32_t)(a.rng_seed >> 32));
+                    u = u32_to_unit_f32(rr.v[i & 3]);
+                }
+                nz[kk] = (2.f * u - 1.f) * c.noise_scale[k];
+            }
+        }
+        STAMP(1, T_ENV);
+        mbar_wait(&S.bar_small, 0);
+        STAMP(2, T_ENV);
+        // ---------------- P1: warp-per-env DOF sums and contact-force norms --------------------------------
         const float dof_pos = S.dof[el * 24 + 2 * d_], dof_vel = S.dof[el * 24 + 2 * d_ + 1];
         {
             const float act = S.act[el * 12 + d_], lact = S.lact[el * 12 + d_];
             const float tq = S.tq[el * 12 + d_], ltq = S.ltq[el * 12 + d_], ldv = S.ldv[el * 12 + d_];
             float v, s[9];
             v = lact - act;
-            s[0] = warp_sum(dl ? v * v : 0.f);                                         // action_rate
+            s[0] = half_warp_sum(dl ? v * v : 0.f);                                         // action_rate
             v = tq - ltq;
-            s[1] = warp_sum(dl ? v * v : 0.f);                                         // delta_torques
+            s[1] = half_warp_sum(dl ? v * v : 0.f);                                         // delta_torques
             v = (ldv - dof_vel) / c.dt;
-            s[2] = warp_sum(dl ? v * v : 0.f);                                         // dof_acc
+            s[2] = half_warp_sum(dl ? v * v : 0.f);                                         // dof_acc
             const float dq0 = dof_pos - c.default_dof_pos[d_];
-            s[3] = warp_sum(dl ? dq0 * dq0 : 0.f);                                     // dof_error
+            s[3] = half_warp_sum(dl ? dq0 * dq0 : 0.f);                                     // dof_error
             v = -fminf(dof_pos - c.dof_pos_lower[d_], 0.f);
             v = v + fmaxf(dof_pos - c.dof_pos_upper[d_], 0.f);
-            s[4] = warp_sum(dl ? v : 0.f);                                             // dof_pos_limits
+            s[4] = half_warp_sum(dl ? v : 0.f);                                             // dof_pos_limits
             v = clampf(fabsf(dof_vel) - c.dof_vel_limits[d_] * c.soft_dof_vel_limit, 0.f, 1.f);
-            s[5] = warp_sum(dl ? v : 0.f);                                             // dof_vel_limits
-            s[6] = warp_sum((dl && ((c.hip_dof_mask >> d_) & 1u)) ? dq0 * dq0 : 0.f);  // hip_pos
+            s[5] = half_warp_sum(dl ? v : 0.f);                                             // dof_vel_limits
+            s[6] = half_warp_sum((dl && ((c.hip_dof_mask >> d_) & 1u)) ? dq0 * dq0 : 0.f);  // hip_pos
             v = fmaxf(fabsf(tq) - c.torque_limits[d_] * c.soft_torque_limit, 0.f);
-            s[7] = warp_sum(dl ? v : 0.f);                                             // torque_limits
-            s[8] = warp_sum(dl ? tq * tq : 0.f);                                       // torques
+            s[7] = half_warp_sum(dl ? v : 0.f);                                             // torque_limits
+            s[8] = half_warp_sum(dl ? tq * tq : 0.f);                                       // torques
             float nrm = 0.f;
             if (lane < B) {
                 const float* f = S.cf + (el * B + lane) * 3;
@@ -235,28 +291,38 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
             for (int j = 0; j < 4; ++j)
                 if (lane == SC_FF + j) out = ff[j];
             if (lane < SC_RESET) S.scal[el][lane] = out;
-        }
-        // ---------------- P3a: everything of the row that depends on loaded inputs only ---------------------
-        // (overlaps the scalar warp's P2a; the reset path of P3b redoes the DOF lanes for the ~1.5 % reset envs)
-        {
-            float* row = S.obs + el * ROW;
-            float* disc = S.disc + el * QA_NUM_OBS_DISC;
+            // pure copies leave straight from the registers (:158, :161)
             if (dl) {
-                const float dq = (dof_pos - c.default_dof_pos[lane]) * c.s_dof_pos;
-                const float dv = dof_vel * c.s_dof_vel;
-                row[5 + lane] = dq;
-                row[17 + lane] = dv;
-                row[29 + lane] = S.alast[el * 12 + lane];
-                row[45 + lane] = 0.f;
-                row[66 + lane] = S.msp[el * 12 + lane] - 1.f;
-                row[78 + lane] = S.msd[el * 12 + lane] - 1.f;
-                disc[9 + lane] = dq;
-                disc[21 + lane] = dv;
-                S.dv_out[el * 12 + lane] = dof_vel;
+                a.last_actions[(size_t)e * 12 + lane] = act;
+                a.last_torques_org[(size_t)e * 12 + lane] = tq;
             }
-            if (lane >= 12 && lane < 16) row[61 + lane - 12] = S.mass[el * 4 + lane - 12];
-            if (lane == 16) row[65] = S.fric[el];
-            // history shift (:302-312, non-fill case), staged through registers: hazard-free in-place shift of the tile
+        }
+        bar_arrive(1, T2_THREADS);          // P1 results are in S.scal: the scalar warp may run P2b while this warp goes on
+        STAMP(3, T_ENV);
+        // ---------------- P3a: everything of the row that depends on loaded inputs only ---------------------
+        // (the reset path of P3b redoes the DOF lanes for the ~1.5 % reset envs)
+        float* row = S.obs + el * ROW;
+        float* disc = S.disc + el * QA_NUM_OBS_DISC;
+        if (dl) {
+            const float dq = (dof_pos - c.default_dof_pos[lane]) * c.s_dof_pos;
+            const float dv = dof_vel * c.s_dof_vel;
+            row[5 + lane] = dq;
+            row[17 + lane] = dv;
+            row[29 + lane] = alast;
+            row[45 + lane] = 0.f;
+            row[66 + lane] = S.msp[el * 12 + lane] - 1.f;
+            row[78 + lane] = S.msd[el * 12 + lane] - 1.f;
+            disc[9 + lane] = dq;
+            disc[21 + lane] = dv;
+        }
+        if (lane >= 12 && lane < 16) row[61 + lane - 12] = S.mass[el * 4 + lane - 12];
+        if (lane == 16) row[65] = S.fric[el];
+        STAMP(4, T_ENV);
+        mbar_wait(&S.bar, 0);
+        STAMP(5, T_ENV);
+        {
+            // history shift (:302-312, non-fill case), staged through registers: hazard-free in-place shift of the tile.
+            // Every stored history value was clamped when it entered the buffer, so the shifted slots need no clip.
             float* h = S.hist + el * HIST_W;
             constexpr int NSH = (HIST_W - QA_NUM_PROP + 31) / 32;
             float hv[NSH];
@@ -276,159 +342,15 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
                 }
             }
         }
-    } else if (lane < T2_ENVS) {
-        // ---------------- P2a: thread-per-env scalar program, command / contact independent half ------------------
-        const int el = lane, e = e0 + el;
-        float* R = S.root + el * 13;
-        float* sc = S.scal[el];
-        const Quat q = {R[3], R[4], R[5], R[6]};
-        ep = S.ep[el] + 1;                                                         // :133
-        if (c.measure_heights) center_h = terrain_center_height(a.terrain, yaw_quat(q), R[0], R[1], c.center_px, c.center_py);
-        blv = quat_rotate_sgn(q, Vec3{R[7], R[8], R[9]}, -1.f);                     // :138-140
-        bav = quat_rotate_sgn(q, Vec3{R[10], R[11], R[12]}, -1.f);
-        const Vec3 pg = quat_rotate_sgn(q, Vec3{0.f, 0.f, -1.f}, -1.f);
-        float roll, pitch, yaw;
-        {
-            const float t0 = 2.0f * (q.w * q.x + q.y * q.z);
-            const float t1 = 1.0f - 2.0f * (q.x * q.x + q.y * q.y);
-            roll = atan2f(t0, t1);
-            float t2 = 2.0f * (q.w * q.y - q.z * q.x);
-            t2 = clampf(t2, -1.f, 1.f);
-            pitch = asinf(t2);
-            const float t3 = 2.0f * (q.w * q.z + q.x * q.y);
-            const float t4 = 1.0f - 2.0f * (q.y * q.y + q.z * q.z);
-            yaw = atan2f(t3, t4);
-        }
-        S.blv[el * 3 + 0] = blv.x, S.blv[el * 3 + 1] = blv.y, S.blv[el * 3 + 2] = blv.z;
-        S.bav[el * 3 + 0] = bav.x, S.bav[el * 3 + 1] = bav.y, S.bav[el * 3 + 2] = bav.z;
-        S.pg[el * 3 + 0] = pg.x, S.pg[el * 3 + 1] = pg.y, S.pg[el * 3 + 2] = pg.z;
-        S.rpy[el * 3 + 0] = roll, S.rpy[el * 3 + 1] = pitch, S.rpy[el * 3 + 2] = yaw;
-        {
-            // compute_flat_key_pos (:1377-1396) on the current root; reset envs redo it in P3b on the mocap root
-            const Quat hq = heading_quat_inv(q);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const Vec3 local = {S.key[el * 12 + j * 3 + 0] - R[0], S.key[el * 12 + j * 3 + 1] - R[1],
-                                    S.key[el * 12 + j * 3 + 2] - R[2]};
-                const Vec3 o = quat_rotate_sgn(hq, local, 1.f);
-                sc[SC_KEY + j * 3 + 0] = o.x, sc[SC_KEY + j * 3 + 1] = o.y, sc[SC_KEY + j * 3 + 2] = o.z;
-            }
-        }
-        if (ep % (long long)c.resample_period == 0) {                              // :454-462
-            const K2Draw d = draw_site(c, a, e, SITE_RS0, a.rs_eps_u, a.rs_c_idx, a.rs_cmd_u);
-            resample_thread(c, d, S.cmd + el * 5, S.eps + el, S.lc + el * 5);
-        }
-        if (a.do_push) {                                                           // :682-687
-            float u0, u1;
-            if (a.push_u != nullptr) {
-                u0 = a.push_u[e * 2 + 0];
-                u1 = a.push_u[e * 2 + 1];
-            } else {
-                Philox4 r = philox4x32_10((uint32_t)e, SITE_PUSH, (uint32_t)a.rng_step, (uint32_t)(a.rng_step >> 32),
-                                          (uint32_t)a.rng_seed, (uint32_t)(a.rng_seed >> 32));
-                u0 = u32_to_unit_f32(r.v[0]);
-                u1 = u32_to_unit_f32(r.v[1]);
-            }
-            const float span = c.max_push_vel_xy - (-c.max_push_vel_xy);
-            R[7] = span * u0 + (-c.max_push_vel_xy);
-            R[8] = span * u1 + (-c.max_push_vel_xy);
-        }
-    }
-    STAMP(4, T_ENV);
-    STAMP(10, T_SCL);
-    __syncthreads();                                        // P1 results visible to the scalar warp
-    STAMP(11, T_SCL);
+        STAMP(6, T_ENV);
+        any_state_write = __syncthreads_or(any_state_write ? 1 : 0) != 0;      // barrier 2: P2b results are in
+        STAMP(7, T_ENV);
 
-    if (wid == T2_ENVS && lane < T2_ENVS) {
-        // ---------------- P2b: contacts, termination, reward total, episode sums, reset decision --------------------
-        const int el = lane, e = e0 + el;
-        float* R = S.root + el * 13;
-        float* sc = S.scal[el];
-        float* cmd = S.cmd + el * 5;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {                                              // :143-146
-            const float f = sc[SC_FF + j];
-            const bool ct = f > 2.f;
-            S.ff[el * 4 + j] = f;
-            S.cont_out[el * 4 + j] = ct ? 1 : 0;
-            S.cfilt_out[el * 4 + j] = (ct || S.lcont[el * 4 + j] != 0) ? 1 : 0;
-        }
-        const float root_z_pre = R[2];
-        const bool time_out = ((float)ep > c.max_episode_length) || (root_z_pre < -6.0f);   // :168-176
-        const bool is_reset = (sc[SC_TERM] != 0.f) || time_out;
-        const float root_h_pre = root_z_pre - center_h;
-        float rt[QA_NUM_REWARDS];                                                  // :1248-1335, dir() order
-        rt[0] = sc[SC_SUM0 + 0];
-        rt[1] = sc[SC_NCOL];
-        rt[2] = sc[SC_SUM0 + 1];
-        rt[3] = sc[SC_SUM0 + 2];
-        rt[4] = sc[SC_SUM0 + 3];
-        rt[5] = sc[SC_SUM0 + 4];
-        rt[6] = sc[SC_SUM0 + 5];
-        rt[7] = sc[SC_SUM0 + 6];
-        {
-            const float err = sqrtf((cmd[3] - root_h_pre) * (cmd[3] - root_h_pre));
-            rt[8] = ((err < 0.05f) && (cmd[3] >= c.jump_height_lo)) ? c.jump_goal : 0.f;
-        }
-        {
-            const float err = sqrtf((cmd[4] - root_h_pre) * (cmd[4] - root_h_pre));
-            const float rl = expf(-10.0f * (err * err) / c.tracking_sigma);
-            rt[9] = (!(cmd[3] > c.jump_height_lo)) ? rl : 0.f;
-        }
-        rt[10] = sc[SC_SUM0 + 7];
-        rt[11] = sc[SC_SUM0 + 8];
-        {
-            const float dw = cmd[2] - bav.z;
-            rt[12] = expf(-(dw * dw) / c.tracking_sigma);
-            const float dx = cmd[0] - blv.x, dy = cmd[1] - blv.y;
-            rt[13] = expf(-(dx * dx + dy * dy) / c.tracking_sigma);
-        }
-        float rew = 0.f;
-        float* es = S.epsum + el * QA_EPSUM_PITCH;
-#pragma unroll
-        for (int k = 0; k < QA_NUM_REWARDS; ++k) {
-            const float t = rt[k] * c.reward_scale[k];
-            rew = rew + t;
-            es[k] = es[k] + t;
-        }
-        if (c.only_positive_rewards) rew = fmaxf(rew, 0.f);
-        int mode = 0;
-        if (is_reset) {                                                            // :178-240 (scalar half)
-            K2Workspace* ws = reinterpret_cast<K2Workspace*>(a.workspace);
-#pragma unroll
-            for (int k = 0; k < QA_NUM_REWARDS; ++k) {
-                atomicAdd(&ws->sums[k], (double)es[k]);
-                es[k] = 0.f;
-            }
-            atomicAdd(&ws->reset_count, 1u);
-            const K2Draw d = draw_site(c, a, e, SITE_RT0, a.rt_eps_u, a.rt_c_idx, a.rt_cmd_u);
-            resample_thread(c, d, cmd, S.eps + el, S.lc + el * 5);
-            mode = d.c_idx;
-            ep = 0;
-        }
-        S.ep[el] = ep;
-        S.rew[el] = rew;
-        S.rooth[el] = root_h_pre;
-        sc[SC_RESET] = is_reset ? 1.f : 0.f;
-        sc[SC_CH] = center_h;
-        sc[SC_MODE] = __int_as_float(mode);
-        a.reset_buf[e] = is_reset ? 1 : 0;
-        a.time_out_buf[e] = time_out ? 1 : 0;
-        any_state_write = any_state_write || is_reset;
-    }
-    STAMP(12, T_SCL);
-    any_state_write = __syncthreads_or(any_state_write ? 1 : 0) != 0;
-    STAMP(5, T_ENV);
-
-    if (wid < T2_ENVS) {
         // ---------------- P3b: reset write (rare), P2-dependent row lanes, last history slot, noise, clip --------------
-        const int el = wid, e = e0 + el;
         float* sc = S.scal[el];
         float* R = S.root + el * 13;
-        float* row = S.obs + el * ROW;
-        float* disc = S.disc + el * QA_NUM_OBS_DISC;
         const bool is_reset = sc[SC_RESET] != 0.f;
-        const bool dl = lane < QA_NUM_DOF;
+        float dv_out = dof_vel;
         if (is_reset) {
             int clip;
             double time_u;
@@ -436,10 +358,10 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
                 clip = a.mocap_clip_idx[e];
                 time_u = a.mocap_time_u[e];
             } else {
-                Philox4 r = philox4x32_10((uint32_t)e, SITE_MOCAP, (uint32_t)a.rng_step, (uint32_t)(a.rng_step >> 32),
-                                          (uint32_t)a.rng_seed, (uint32_t)(a.rng_seed >> 32));
-                const double cu = u64_to_unit_f64(r.v[0], r.v[1]);
-                time_u = u64_to_unit_f64(r.v[2], r.v[3]);
+                Philox4 rr = philox4x32_10((uint32_t)e, SITE_MOCAP, (uint32_t)a.rng_step, (uint32_t)(a.rng_step >> 32),
+                                           (uint32_t)a.rng_seed, (uint32_t)(a.rng_seed >> 32));
+                const double cu = u64_to_unit_f64(rr.v[0], rr.v[1]);
+                time_u = u64_to_unit_f64(rr.v[2], rr.v[3]);
                 const int m = __float_as_int(sc[SC_MODE]);
                 const int lo = a.mocap.mode_offset[m], hi = a.mocap.mode_offset[m + 1];
                 int j = lo;
@@ -453,18 +375,18 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
             const float bl = bi.blend;
             const Quat qs = slerp_ref(Quat{f0[3], f0[4], f0[5], f0[6]}, Quat{f1[3], f1[4], f1[5], f1[6]}, bl);
             if (dl) {
-                const float dof_pos = mocap_lerp(f0[7 + lane], f1[7 + lane], bl);
-                const float dof_vel = mocap_lerp(f0[37 + lane], f1[37 + lane], bl);
-                S.dof[el * 24 + 2 * lane] = dof_pos;
-                S.dof[el * 24 + 2 * lane + 1] = dof_vel;
-                const float dq = (dof_pos - c.default_dof_pos[lane]) * c.s_dof_pos;
-                const float dv = dof_vel * c.s_dof_vel;
+                const float mp = mocap_lerp(f0[7 + lane], f1[7 + lane], bl);
+                const float mv = mocap_lerp(f0[37 + lane], f1[37 + lane], bl);
+                S.dof[el * 24 + 2 * lane] = mp;
+                S.dof[el * 24 + 2 * lane + 1] = mv;
+                const float dq = (mp - c.default_dof_pos[lane]) * c.s_dof_pos;
+                const float dv = mv * c.s_dof_vel;
                 row[5 + lane] = dq;
                 row[17 + lane] = dv;
                 row[29 + lane] = 0.f;                                           // action history is cleared (:227)
                 disc[9 + lane] = dq;
                 disc[21 + lane] = dv;
-                S.dv_out[el * 12 + lane] = dof_vel;
+                dv_out = mv;
             }
             const Vec3 lin = quat_rotate_sgn(
                 qs, Vec3{mocap_lerp(f0[31], f1[31], bl), mocap_lerp(f0[32], f1[32], bl), mocap_lerp(f0[33], f1[33], bl)}, 1.f);
@@ -492,6 +414,7 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
             }
             __syncwarp();
         }
+        if (dl) a.last_dof_vel[(size_t)e * 12 + lane] = dv_out;                    // :159 (post-reset dof_vel)
         // observations (:261-331): post-reset root / dof, pre-reset base velocities / angles / contacts
         const float root_h = R[2] - sc[SC_CH];
         if (lane < 4) {
@@ -501,8 +424,13 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
             const float cf_ = S.cfilt_out[el * 4 + lane] ? 1.f : 0.f;
             row[41 + lane] = cf_ - 0.5f;
             disc[45 + lane] = cf_ * c.s_foot_contact;
+            if (a.contact_buf)
+                a.contact_buf[((size_t)e * a.contact_ring_len + a.contact_ring_head) * 4 + lane] = cf_;
+            if (a.contact_force_buf)
+                a.contact_force_buf[((size_t)e * a.contact_ring_len + a.contact_ring_head) * 4 + lane] =
+                    clampf(S.ff[el * 4 + lane], -c.clip_obs, c.clip_obs);
         }
-        if (lane >= 8 && lane < 14) S.lrv[el * 6 + lane - 8] = R[7 + lane - 8];
+        if (lane >= 8 && lane < 14) a.last_root_vel[(size_t)e * 6 + lane - 8] = R[7 + lane - 8];      // :160
         if (lane >= 16 && lane < 19) {
             const int k = lane - 16;
             const float lv = S.blv[el * 3 + k], av = S.bav[el * 3 + k];
@@ -522,7 +450,8 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
         }
         if (lane >= 20 && lane < 31) {
             const int k = lane - 20;
-            row[CMD_OFF + k] = k < 5 ? S.cmd[el * 5 + k] : (k == 5 ? S.eps[el] : S.lc[el * 5 + k - 6]);
+            const float v = k < 5 ? S.cmd[el * 5 + k] : (k == 5 ? S.eps[el] : S.lc[el * 5 + k - 6]);
+            row[CMD_OFF + k] = clampf(v, -c.clip_obs, c.clip_obs);
         }
         __syncwarp();
         {
@@ -535,109 +464,263 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
                 }
             } else {                                                               // newest slot only (shift done in P3a)
                 for (int i = lane; i < QA_NUM_PROP; i += 32) {
-                    const float v = row[i];
+                    const float v = clampf(row[i], -c.clip_obs, c.clip_obs);
                     row[HIST_OFF + HIST_W - QA_NUM_PROP + i] = v;
-                    h[HIST_W - QA_NUM_PROP + i] = clampf(v, -c.clip_obs, c.clip_obs);
+                    h[HIST_W - QA_NUM_PROP + i] = v;
                 }
             }
         }
         __syncwarp();
-        // noise on the noisy lanes only (:318-319), then clip (:326-328)
-        for (int k = lane; k < c.num_noise; k += 32) {
-            const int i = c.noise_idx[k];
-            float u;
-            if (a.noise_u != nullptr) {
-                u = a.noise_u[(size_t)e * ROW + i];
-            } else {
-                Philox4 r = philox4x32_10((uint32_t)e, SITE_NOISE0 + (i >> 2), (uint32_t)a.rng_step,
-                                          (uint32_t)(a.rng_step >> 32), (uint32_t)a.rng_seed, (uint32_t)(a.rng_seed >> 32));
-                u = u32_to_unit_f32(r.v[i & 3]);
+        // noise on the noisy lanes only (:318-319) -- all of them lie in [0, HIST_OFF), checked at launch -- then the
+        // clip (:326-328) of the only lanes that are not clamped yet
+#pragma unroll
+        for (int kk = 0; kk < QA_MAX_NOISE_LANES / 32; ++kk) {
+            const int k = kk * 32 + lane;
+            if (k < c.num_noise) {
+                const int i = c.noise_idx[k];
+                row[i] = row[i] + nz[kk];
             }
-            row[i] = row[i] + (2.f * u - 1.f) * c.noise_scale[k];
         }
         __syncwarp();
-        // clip: the 9 older history slots were clamped when they were shifted (P3a) / filled, and noise never lands on
-        // history lanes (checked by the host when it builds the noise list), so only [0, 90) and [603, 671) remain
         for (int i = lane; i < HIST_OFF; i += 32) row[i] = clampf(row[i], -c.clip_obs, c.clip_obs);
-        for (int i = HIST_OFF + HIST_W - QA_NUM_PROP + lane; i < ROW; i += 32) row[i] = clampf(row[i], -c.clip_obs, c.clip_obs);
-        if (lane < 4) {
-            if (a.contact_buf)
-                a.contact_buf[((size_t)e * a.contact_ring_len + a.contact_ring_head) * 4 + lane] =
-                    S.cfilt_out[el * 4 + lane] ? 1.f : 0.f;
-            if (a.contact_force_buf)
-                a.contact_force_buf[((size_t)e * a.contact_ring_len + a.contact_ring_head) * 4 + lane] =
-                    clampf(S.ff[el * 4 + lane], -c.clip_obs, c.clip_obs);
+        STAMP(8, T_ENV);
+    } else if (wid == W_SA) {
+        // ---------------- P2a (scalar warp A, thread-per-env): base-frame quantities, euler angles, terrain, resample, push
+        if (lane < 26) reinterpret_cast<float4*>(S.root)[lane] = ld0;
+        if (st1 != nullptr) *st1 = ld1;
+        __syncwarp();
+        STAMP(12, T_SA);
+        Vec3 blv = {0.f, 0.f, 0.f}, bav = {0.f, 0.f, 0.f};
+        float center_h = 0.f;
+        long long ep = 0;
+        const int el = lane & (T2_ENVS - 1), e = e0 + el;
+        float* R = S.root + el * 13;
+        float* sc = S.scal[el];
+        float* cmd = S.cmd + el * 5;
+        if (lane < T2_ENVS) {
+            const Quat q = {R[3], R[4], R[5], R[6]};
+            ep = S.ep[el] + 1;                                                         // :133
+            if (c.measure_heights) center_h = terrain_center_height(a.terrain, yaw_quat(q), R[0], R[1], c.center_px, c.center_py);
+            blv = quat_rotate_sgn(q, Vec3{R[7], R[8], R[9]}, -1.f);                     // :138-140
+            bav = quat_rotate_sgn(q, Vec3{R[10], R[11], R[12]}, -1.f);
+            const Vec3 pg = quat_rotate_sgn(q, Vec3{0.f, 0.f, -1.f}, -1.f);
+            float roll, pitch, yaw;
+            {
+                const float t0 = 2.0f * (q.w * q.x + q.y * q.z);
+                const float t1 = 1.0f - 2.0f * (q.x * q.x + q.y * q.y);
+                roll = atan2f(t0, t1);
+                float t2 = 2.0f * (q.w * q.y - q.z * q.x);
+                t2 = clampf(t2, -1.f, 1.f);
+                pitch = asinf(t2);
+                const float t3 = 2.0f * (q.w * q.z + q.x * q.y);
+                const float t4 = 1.0f - 2.0f * (q.y * q.y + q.z * q.z);
+                yaw = atan2f(t3, t4);
+            }
+            S.blv[el * 3 + 0] = blv.x, S.blv[el * 3 + 1] = blv.y, S.blv[el * 3 + 2] = blv.z;
+            S.bav[el * 3 + 0] = bav.x, S.bav[el * 3 + 1] = bav.y, S.bav[el * 3 + 2] = bav.z;
+            S.pg[el * 3 + 0] = pg.x, S.pg[el * 3 + 1] = pg.y, S.pg[el * 3 + 2] = pg.z;
+            S.rpy[el * 3 + 0] = roll, S.rpy[el * 3 + 1] = pitch, S.rpy[el * 3 + 2] = yaw;
+            if (divisible_by(ep, c.resample_period)) {                                 // :454-462
+                const K2Draw d = draw_site(c, a, e, SITE_RS0, a.rs_eps_u, a.rs_c_idx, a.rs_cmd_u);
+                resample_thread(c, d, cmd, S.eps + el, S.lc + el * 5);
+            }
+            if (a.do_push) {                                                           // :682-687
+                float u0, u1;
+                if (a.push_u != nullptr) {
+                    u0 = a.push_u[e * 2 + 0];
+                    u1 = a.push_u[e * 2 + 1];
+                } else {
+                    Philox4 rr = philox4x32_10((uint32_t)e, SITE_PUSH, (uint32_t)a.rng_step, (uint32_t)(a.rng_step >> 32),
+                                               (uint32_t)a.rng_seed, (uint32_t)(a.rng_seed >> 32));
+                    u0 = u32_to_unit_f32(rr.v[0]);
+                    u1 = u32_to_unit_f32(rr.v[1]);
+                }
+                const float span = c.max_push_vel_xy - (-c.max_push_vel_xy);
+                R[7] = span * u0 + (-c.max_push_vel_xy);
+                R[8] = span * u1 + (-c.max_push_vel_xy);
+            }
         }
+        STAMP(13, T_SA);
+        mbar_wait(&S.bar_small, 0);          // episode sums tile (TMA) visible to this warp
+        bar_sync(1, T2_THREADS);             // P1 sums / force norms of the env warps are in S.scal
+        STAMP(14, T_SA);
+        if (lane < T2_ENVS) {
+            // ---------------- P2b: contacts, termination, reward total, episode sums, reset decision --------------------
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {                                              // :143-146
+                const float f = sc[SC_FF + j];
+                const bool ct = f > 2.f;
+                S.ff[el * 4 + j] = f;
+                S.cont_out[el * 4 + j] = ct ? 1 : 0;
+                S.cfilt_out[el * 4 + j] = (ct || S.lcont[el * 4 + j] != 0) ? 1 : 0;
+            }
+            const float root_z_pre = R[2];
+            const bool time_out = ((float)ep > c.max_episode_length) || (root_z_pre < -6.0f);   // :168-176
+            const bool is_reset = (sc[SC_TERM] != 0.f) || time_out;
+            const float root_h_pre = root_z_pre - center_h;
+            float rt[QA_NUM_REWARDS];                                                  // :1248-1335, dir() order
+            rt[0] = sc[SC_SUM0 + 0];
+            rt[1] = sc[SC_NCOL];
+            rt[2] = sc[SC_SUM0 + 1];
+            rt[3] = sc[SC_SUM0 + 2];
+            rt[4] = sc[SC_SUM0 + 3];
+            rt[5] = sc[SC_SUM0 + 4];
+            rt[6] = sc[SC_SUM0 + 5];
+            rt[7] = sc[SC_SUM0 + 6];
+            {
+                const float err = sqrtf((cmd[3] - root_h_pre) * (cmd[3] - root_h_pre));
+                rt[8] = ((err < 0.05f) && (cmd[3] >= c.jump_height_lo)) ? c.jump_goal : 0.f;
+            }
+            {
+                const float err = sqrtf((cmd[4] - root_h_pre) * (cmd[4] - root_h_pre));
+                const float rl = expf(-10.0f * (err * err) / c.tracking_sigma);
+                rt[9] = (!(cmd[3] > c.jump_height_lo)) ? rl : 0.f;
+            }
+            rt[10] = sc[SC_SUM0 + 7];
+            rt[11] = sc[SC_SUM0 + 8];
+            {
+                const float dw = cmd[2] - bav.z;
+                rt[12] = expf(-(dw * dw) / c.tracking_sigma);
+                const float dx = cmd[0] - blv.x, dy = cmd[1] - blv.y;
+                rt[13] = expf(-(dx * dx + dy * dy) / c.tracking_sigma);
+            }
+            float rew = 0.f;
+            float* es = S.epsum + el * QA_EPSUM_PITCH;
+#pragma unroll
+            for (int k = 0; k < QA_NUM_REWARDS; ++k) {
+                const float t = rt[k] * c.reward_scale[k];
+                rew = rew + t;
+                es[k] = es[k] + t;
+            }
+            if (c.only_positive_rewards) rew = fmaxf(rew, 0.f);
+            int mode = 0;
+            if (is_reset) {                                                            // :178-240 (scalar half)
+                K2Workspace* ws = reinterpret_cast<K2Workspace*>(a.workspace);
+#pragma unroll
+                for (int k = 0; k < QA_NUM_REWARDS; ++k) {
+                    atomicAdd(&ws->sums[k], (double)es[k]);
+                    es[k] = 0.f;
+                }
+                atomicAdd(&ws->reset_count, 1u);
+                const K2Draw d = draw_site(c, a, e, SITE_RT0, a.rt_eps_u, a.rt_c_idx, a.rt_cmd_u);
+                resample_thread(c, d, cmd, S.eps + el, S.lc + el * 5);
+                mode = d.c_idx;
+                ep = 0;
+            }
+            S.ep[el] = ep;
+            S.rew[el] = rew;
+            S.rooth[el] = root_h_pre;
+            sc[SC_RESET] = is_reset ? 1.f : 0.f;
+            sc[SC_CH] = center_h;
+            sc[SC_MODE] = __int_as_float(mode);
+            a.reset_buf[e] = is_reset ? 1 : 0;
+            a.time_out_buf[e] = time_out ? 1 : 0;
+            any_state_write = any_state_write || is_reset;
+        }
+        STAMP(15, T_SA);
+        any_state_write = __syncthreads_or(any_state_write ? 1 : 0) != 0;      // barrier 2
+        // the per-env scalar outputs leave with plain 16-B stores while the env warps assemble the rows
+        copy16(a.episode_sums + (size_t)e0 * QA_EPSUM_PITCH, S.epsum, T2_ENVS * QA_EPSUM_PITCH / 4, lane);
+        copy16(a.commands + (size_t)e0 * 5, S.cmd, T2_ENVS * 5 / 4, lane);
+        copy16(a.latent_c + (size_t)e0 * 5, S.lc, T2_ENVS * 5 / 4, lane);
+        copy16(a.latent_eps + e0, S.eps, T2_ENVS / 4, lane);
+        copy16(a.episode_length_buf + e0, S.ep, T2_ENVS * 2 / 4, lane);
+        copy16(a.last_contacts + (size_t)e0 * 4, S.cont_out, T2_ENVS / 4, lane);
+        copy16(a.contact_filt + (size_t)e0 * 4, S.cfilt_out, T2_ENVS / 4, lane);
+        copy16(a.feet_forces + (size_t)e0 * 4, S.ff, T2_ENVS, lane);
+        copy16(a.rew_buf + e0, S.rew, T2_ENVS / 4, lane);
+        copy16(a.root_h + e0, S.rooth, T2_ENVS / 4, lane);
+        copy16(a.base_lin_vel + (size_t)e0 * 3, S.blv, T2_ENVS * 3 / 4, lane);
+        copy16(a.base_ang_vel + (size_t)e0 * 3, S.bav, T2_ENVS * 3 / 4, lane);
+        copy16(a.projected_gravity + (size_t)e0 * 3, S.pg, T2_ENVS * 3 / 4, lane);
+        copy16(a.rpy + (size_t)e0 * 3, S.rpy, T2_ENVS * 3 / 4, lane);
+        STAMP(18, T_SA);
+    } else {
+        // ---------------- P2a (scalar warp B): key-body positions in the heading frame (:1377-1396) -----------------------
+        if (lane < 26) reinterpret_cast<float4*>(S.rootB)[lane] = ld0;
+        S.key[lane * 3 + 0] = k0, S.key[lane * 3 + 1] = k1, S.key[lane * 3 + 2] = k2;
+        __syncwarp();
+        {
+            // lane = (env, foot): the heading quaternion is computed 4x redundantly, the rotations run 32 wide
+            const int el = lane >> 2, j = lane & 3;
+            const float* R = S.rootB + el * 13;
+            const Quat hq = heading_quat_inv(Quat{R[3], R[4], R[5], R[6]});
+            const Vec3 local = {k0 - R[0], k1 - R[1], k2 - R[2]};
+            const Vec3 o = quat_rotate_sgn(hq, local, 1.f);
+            float* sc = S.scal[el];
+            sc[SC_KEY + j * 3 + 0] = o.x, sc[SC_KEY + j * 3 + 1] = o.y, sc[SC_KEY + j * 3 + 2] = o.z;
+        }
+        STAMP(19, T_SB);
+        bar_arrive(1, T2_THREADS);
+        any_state_write = __syncthreads_or(any_state_write ? 1 : 0) != 0;      // barrier 2
     }
 
-    // ---------------- P4: every output tile leaves through the TMA engine --------------------------------------
-    STAMP(6, T_ENV);
+    // ---------------- P4: the four big tiles leave through the TMA engine, one issuing thread each ------------------
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
-    STAMP(7, T_ENV);
-    if (tid == 0) {
-        const unsigned n12 = T2_ENVS * 12 * 4;
-        bulk_store_bytes(a.obs_buf + (size_t)e0 * ROW, S.obs, T2_ENVS * ROW * 4);
-        if (a.privileged_obs_buf != a.obs_buf) bulk_store_bytes(a.privileged_obs_buf + (size_t)e0 * ROW, S.obs, T2_ENVS * ROW * 4);
-        bulk_store_bytes(a.obs_history_buf + (size_t)e0 * HIST_W, S.hist, T2_ENVS * HIST_W * 4);
-        bulk_store_bytes(a.obs_disc_buf + (size_t)e0 * QA_NUM_OBS_DISC, S.disc, T2_ENVS * QA_NUM_OBS_DISC * 4);
-        bulk_store_bytes(a.last_actions + (size_t)e0 * 12, S.act, n12);                       // :158
-        bulk_store_bytes(a.last_dof_vel + (size_t)e0 * 12, S.dv_out, n12);                    // :159
-        bulk_store_bytes(a.last_root_vel + (size_t)e0 * 6, S.lrv, T2_ENVS * 6 * 4);           // :160
-        bulk_store_bytes(a.last_torques_org + (size_t)e0 * 12, S.tq, n12);                    // :161
-        bulk_store_bytes(a.episode_sums + (size_t)e0 * QA_EPSUM_PITCH, S.epsum, T2_ENVS * QA_EPSUM_PITCH * 4);
-        bulk_store_bytes(a.commands + (size_t)e0 * 5, S.cmd, T2_ENVS * 5 * 4);
-        bulk_store_bytes(a.latent_c + (size_t)e0 * 5, S.lc, T2_ENVS * 5 * 4);
-        bulk_store_bytes(a.latent_eps + e0, S.eps, T2_ENVS * 4);
-        bulk_store_bytes(a.episode_length_buf + e0, S.ep, T2_ENVS * 8);
-        bulk_store_bytes(a.last_contacts + (size_t)e0 * 4, S.cont_out, T2_ENVS * 4);
-        bulk_store_bytes(a.contact_filt + (size_t)e0 * 4, S.cfilt_out, T2_ENVS * 4);
-        bulk_store_bytes(a.feet_forces + (size_t)e0 * 4, S.ff, T2_ENVS * 4 * 4);
-        bulk_store_bytes(a.rew_buf + e0, S.rew, T2_ENVS * 4);
-        bulk_store_bytes(a.root_h + e0, S.rooth, T2_ENVS * 4);
-        bulk_store_bytes(a.base_lin_vel + (size_t)e0 * 3, S.blv, T2_ENVS * 3 * 4);
-        bulk_store_bytes(a.base_ang_vel + (size_t)e0 * 3, S.bav, T2_ENVS * 3 * 4);
-        bulk_store_bytes(a.projected_gravity + (size_t)e0 * 3, S.pg, T2_ENVS * 3 * 4);
-        bulk_store_bytes(a.rpy + (size_t)e0 * 3, S.rpy, T2_ENVS * 3 * 4);
-        if (any_state_write) {                          // simulator memory is only written on reset / push
-            bulk_store_bytes(a.root_states + (size_t)e0 * 13, S.root, T2_ENVS * 13 * 4);
-            bulk_store_bytes(a.dof_state + (size_t)e0 * 24, S.dof, T2_ENVS * 24 * 4);
+    STAMP(9, T_ENV);
+    if (lane == 0 && wid < 6) {
+        bool issued = true;
+        switch (wid) {
+            case 0: bulk_store_bytes(a.obs_buf + (size_t)e0 * ROW, S.obs, T2_ENVS * ROW * 4); break;
+            case 1:
+                if (a.privileged_obs_buf != a.obs_buf) bulk_store_bytes(a.privileged_obs_buf + (size_t)e0 * ROW, S.obs, T2_ENVS * ROW * 4);
+                else issued = false;
+                break;
+            case 2: bulk_store_bytes(a.obs_history_buf + (size_t)e0 * HIST_W, S.hist, T2_ENVS * HIST_W * 4); break;
+            case 3: bulk_store_bytes(a.obs_disc_buf + (size_t)e0 * QA_NUM_OBS_DISC, S.disc, T2_ENVS * QA_NUM_OBS_DISC * 4); break;
+            case 4:                                     // simulator memory is only written on reset / push
+                if (any_state_write) bulk_store_bytes(a.root_states + (size_t)e0 * 13, S.root, T2_ENVS * 13 * 4);
+                else issued = false;
+                break;
+            default:
+                if (any_state_write) bulk_store_bytes(a.dof_state + (size_t)e0 * 24, S.dof, T2_ENVS * 24 * 4);
+                else issued = false;
+                break;
         }
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        // not waited for here: the last CTA only reads time_out_buf (direct stores above); the tiles become visible
-        // to the next kernel at kernel end.  The shared-memory source is released by the .read wait at the end.
+        STAMP(10, T_ENV);
+        if (issued) {
+            // the tiles become visible to the next kernel at kernel end; the shared-memory source must outlive the reads
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
     }
+    STAMP(11, T_ENV);
 
-    // reset statistics are finalised by k_k2_finalize (one CTA, launched right behind this kernel): no grid-wide ticket,
-    // no __threadfence on the critical path of the 512 tiles
-    STAMP(13, T_ENV);
-    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-    STAMP(14, T_ENV);
-    GSTAMP(17, T_ENV);
-}
-
-// One CTA behind the tiled kernel: episode reward means of the envs that reset (:230-234), extras["time_outs"] latch
-// (:239-240, only when >= 1 env reset), device step counter, workspace re-arm.
-__global__ void __launch_bounds__(256) k_k2_finalize(const __grid_constant__ QaBbcConst c, const __grid_constant__ QaBbcStepArgs a_in) {
-    const K2Step a(a_in);
-    K2Workspace* ws = reinterpret_cast<K2Workspace*>(a.workspace);
-    const int tid = threadIdx.x;
-    const unsigned cnt = ws->reset_count;
-    if (cnt > 0) {
-        if (tid < QA_NUM_REWARDS) {
-            const float mean = (float)(ws->sums[tid] / (double)cnt);
-            a.episode_rew_means[tid] = mean / c.episode_length_s;
-        }
-        for (int i = tid; i < a.num_envs; i += blockDim.x) a.time_outs_latched[i] = a.time_out_buf[i];
+    // ---------------- epilogue: the CTA that takes the last ticket finalises the step (no extra kernel launch) --------
+    // Every CTA's direct stores (time_out_buf) and reset-statistics atomics precede barrier 3; thread 0's fence after that
+    // barrier is cumulative, so whoever observes the full ticket count also observes them.  The TMA tile stores are not
+    // needed by the finaliser.
+    if (tid == 0) {
+        K2Workspace* ws = reinterpret_cast<K2Workspace*>(a.workspace);
+        __threadfence();
+        S.last = (atomicAdd(&ws->ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
     }
     __syncthreads();
-    if (tid == 0) {
-        *a.num_resets = (int)cnt;
-        if (a.step_state != nullptr) a.step_state[0] = (long long)a.rng_step;
-        ws->reset_count = 0u;
-        ws->ticket = 0u;
+    if (S.last) {
+        __threadfence();
+        K2Workspace* ws = reinterpret_cast<K2Workspace*>(a.workspace);
+        const unsigned cnt = *reinterpret_cast<volatile unsigned*>(&ws->reset_count);
+        if (cnt > 0) {
+            if (tid < QA_NUM_REWARDS) {                                     // :230-234
+                const double sum = *reinterpret_cast<volatile double*>(&ws->sums[tid]);
+                a.episode_rew_means[tid] = (float)(sum / (double)cnt) / c.episode_length_s;
+            }
+            // extras["time_outs"] = time_out_buf, only on steps with >= 1 reset (:239-240); num_envs % 8 == 0
+            const unsigned long long* src = reinterpret_cast<const unsigned long long*>(a.time_out_buf);
+            unsigned long long* dst = reinterpret_cast<unsigned long long*>(a.time_outs_latched);
+            for (int i = tid; i < a.num_envs / 8; i += T2_THREADS) dst[i] = __ldcg(src + i);
+        }
+        __syncthreads();
+        if (tid < QA_NUM_REWARDS) ws->sums[tid] = 0.0;
+        if (tid == 0) {
+            *a.num_resets = (int)cnt;
+            if (a.step_state != nullptr) a.step_state[0] = (long long)a.rng_step;
+            ws->reset_count = 0u;
+            ws->ticket = 0u;
+        }
     }
-    if (tid < QA_NUM_REWARDS) ws->sums[tid] = 0.0;
+    GSTAMP(17, T_ENV);
 }
 
 static bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
@@ -648,14 +731,15 @@ int qa_k2_try_launch_tiled(const QaBbcConst* c, const QaBbcStepArgs* a, cudaStre
     if (!(a->flags & QA_K2_TILED)) return 0;
     if (a->num_envs % T2_ENVS != 0 || a->obs_pitch != QA_OBS_WIDTH || c->num_bodies > 32) return 0;
     if (c->num_noise < 0 || c->num_noise > QA_MAX_NOISE_LANES) return QA_ERANGE;
-    for (int k = 0; k < c->num_noise; ++k)                       // the tiled kernel clips shifted history lanes before noise
-        if (c->noise_idx[k] >= HIST_OFF && c->noise_idx[k] < HIST_OFF + HIST_W - QA_NUM_PROP) return 0;
+    for (int k = 0; k < c->num_noise; ++k)                       // the tiled kernel clamps history / command lanes as it writes them
+        if (c->noise_idx[k] < 0 || c->noise_idx[k] >= HIST_OFF) return 0;
     const void* ptrs[] = {a->obs_buf, a->privileged_obs_buf, a->obs_history_buf, a->obs_disc_buf, a->root_states,
                           a->dof_state, a->contact_forces, a->actions, a->last_actions, a->torques_org,
                           a->last_torques_org, a->last_dof_vel, a->last_root_vel, a->motor_strength, a->commands,
                           a->latent_c, a->latent_eps, a->mass_params, a->friction_coeffs, a->episode_sums,
                           a->episode_length_buf, a->last_contacts, a->contact_filt, a->feet_forces, a->rew_buf,
-                          a->root_h, a->base_lin_vel, a->base_ang_vel, a->projected_gravity, a->rpy};
+                          a->root_h, a->base_lin_vel, a->base_ang_vel, a->projected_gravity, a->rpy, a->time_out_buf,
+                          a->time_outs_latched};
     for (const void* p : ptrs)
         if (!aligned16(p)) return 0;
     if ((((size_t)a->num_envs * QA_NUM_DOF * 4) & 15u) != 0) return 0;       // second motor_strength plane
@@ -669,8 +753,5 @@ int qa_k2_try_launch_tiled(const QaBbcConst* c, const QaBbcStepArgs* a, cudaStre
     k_post_physics_bbc_tiled<<<a->num_envs / T2_ENVS, T2_THREADS, sizeof(T2Smem), stream>>>(*c, *a);
     *launched = 1;
     cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return (int)e;
-    k_k2_finalize<<<1, 256, 0, stream>>>(*c, *a);
-    e = cudaGetLastError();
     return e == cudaSuccess ? 0 : (int)e;
 }

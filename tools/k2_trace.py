@@ -19,20 +19,26 @@ OUT = os.path.join(ROOT, "tools", "_k2trace")
 sys.path.insert(0, PKG)
 sys.path.insert(0, ROOT)
 
-SEGMENTS = [  # (name, stamp_from, stamp_to)
-    ("P0 issue loads (+step counter, strided loads issued)", 0, 1),
-    ("P0 wait for TMA tiles", 1, 2),
-    ("barrier 0", 2, 3),
-    ("env warp: P1 + P3a", 3, 4),
-    ("scalar warp: P2a", 9, 10),
-    ("scalar warp: barrier 1 wait", 10, 11),
-    ("scalar warp: P2b", 11, 12),
-    ("env warp: barrier 1+2 wait (P2a tail + P2b)", 4, 5),
-    ("env warp: P3b", 5, 6),
-    ("barrier 3", 6, 7),
-    ("P4 issue stores", 7, 13),
-    ("P4 wait_group.read", 13, 14),
-    ("whole CTA (entry -> exit)", 0, 14),
+SEGMENTS = [  # (name, stamp_from, stamp_to); stamps 0-11 env warp 0, 12-15/18 scalar warp A, 19 scalar warp B
+    ("env: entry -> loads issued, noise drawn", 0, 1),
+    ("env: wait small tiles", 1, 2),
+    ("env: P1 (sums, norms)", 2, 3),
+    ("env: P3a row lanes", 3, 4),
+    ("env: wait history tile", 4, 5),
+    ("env: history shift", 5, 6),
+    ("env: barrier 2 wait (P2b)", 6, 7),
+    ("env: P3b", 7, 8),
+    ("env: barrier 3", 8, 9),
+    ("P4 issue store", 9, 10),
+    ("P4 wait_group.read", 10, 11),
+    ("scalar A: entry -> own loads landed", 0, 12),
+    ("scalar A: P2a", 12, 13),
+    ("scalar A: wait P1 (small tiles + barrier 1)", 13, 14),
+    ("scalar A: P2b", 14, 15),
+    ("scalar A: barrier 2 + small-output stores", 15, 18),
+    ("scalar B: entry -> key positions done", 0, 19),
+    ("env: entry -> barrier 2 passed", 0, 7),
+    ("whole CTA (entry -> stores issued and read)", 0, 11),
 ]
 
 
@@ -98,7 +104,7 @@ def run(n_envs, reps):
         g0, g1 = host[:, 16], host[:, 17]
         spans.append(float(g1.max() - g0.min()) / 1e3)
         skews.append(float(g0.max() - g0.min()) / 1e3)
-        cyc_per_ns = np.median((host[:, 14] - host[:, 0]) / np.maximum(g1 - g0, 1))
+        cyc_per_ns = np.median((host[:, 11] - host[:, 0]) / np.maximum(g1 - g0, 1))
         for name, a, b in SEGMENTS:
             seg[name].append((host[:, b] - host[:, a]) / cyc_per_ns / 1e3)
     print(f"== K2 tiled phase trace: {n_envs} envs, {n_envs // 8} CTAs (first {n_cta} traced), {reps} launches, L2 flushed; "
