@@ -51,7 +51,7 @@ int qa_version(void);
 /* human readable build string ("sm_100a, nvcc 12.9, ...") */
 const char* qa_build_info(void);
 /* sizeof() of argument struct number `which` (order of declaration in this header, QaActionPushArgs
- * = 0 ... QaGaeArgs = 9, QaGatherArgs = 10, QaClipAdamArgs = 11, QaLinearArgs = 12, QaActBwdArgs = 13, QaPpoLossArgs = 14, QaLinearBwdArgs = 15, QaHistEncArgs = 16; -1 if unknown): a layout handshake for FFI mirrors of these structs */
+ * = 0 ... QaGaeArgs = 9, QaGatherArgs = 10, QaClipAdamArgs = 11, QaLinearArgs = 12, QaActBwdArgs = 13, QaPpoLossArgs = 14, QaLinearBwdArgs = 15, QaHistEncArgs = 16, QaRowLossArgs = 17, QaPpoScalarsArgs = 18, QaDepthArgs = 19; -1 if unknown): a layout handshake for FFI mirrors of these structs */
 int qa_struct_size(int which);
 
 /* ------------------------------------------------------------------------------------------
@@ -336,8 +336,10 @@ typedef struct QaGatherArgs {
     int32_t num_tensors;
     const int64_t* indices;             /* (num_rows) rows of the flattened (T*N) storage */
     const float* src[QA_GATHER_MAX_TENSORS];   /* (T*N, width[t]) */
-    float* dst[QA_GATHER_MAX_TENSORS];         /* (num_rows, width[t]) */
+    float* dst[QA_GATHER_MAX_TENSORS];         /* (num_rows, width[t]), row pitch dst_pitch[t] */
     int32_t width[QA_GATHER_MAX_TENSORS];
+    int32_t dst_pitch[QA_GATHER_MAX_TENSORS];  /* destination row pitch in floats (0 = width[t]); a pitch that is a multiple
+                                                  of 4 floats makes the minibatch a legal TMA operand without a copy */
 } QaGatherArgs;
 int qa_gather_minibatch(const QaGatherArgs* a, void* stream);
 
@@ -465,6 +467,74 @@ typedef struct QaHistEncArgs {
     float* out; int64_t out_pitch;             /* (M,29) */
 } QaHistEncArgs;
 int qa_hist_encoder_fwd(const QaHistEncArgs* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K12 row losses, forward + backward in one pass -- the two auxiliary losses of a PPO minibatch step,
+ *     bbc/rsl_rl/algorithms/gail.py:352-365:
+ *       mode 0  mean squared error   loss = mean_{i,k} (a[i,k] - b[i,k])^2        (estimator loss, :359)
+ *       mode 1  mean row L2 distance loss = mean_i ||a[i,:] - b[i,:]||_2          (priv_reg_loss, :354)
+ *     da = d loss / d a is written in the same kernel (b is treated as a constant); *loss is zeroed first.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct QaRowLossArgs {
+    int64_t M;
+    int32_t W;                          /* row width, 1..32 */
+    int32_t mode;
+    const float* a; int64_t a_pitch;    /* (M,W) */
+    const float* b; int64_t b_pitch;    /* (M,W) */
+    float* da; int64_t da_pitch;        /* (M,W) out */
+    float* loss;                        /* (1) out */
+} QaRowLossArgs;
+int qa_row_loss(const QaRowLossArgs* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K13 per-minibatch scalar bookkeeping on the device (one thread): the adaptive-KL learning-rate rule
+ *     (gail.py:368-379: lr /= 1.5 above 2*desired_kl, *= 1.5 below desired_kl/2, clamped to [1e-5, 1e-2]) and the
+ *     running sums of the seven logged statistics (:277-282) -- replaces ~25 one-element torch kernels.
+ *     stats_accum[0..6] += {surrogate, value, bound, entropy, priv_reg, estimator, kl}.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct QaPpoScalarsArgs {
+    const float* ppo_stats;             /* (4) K10 output: surrogate, value, bound, kl */
+    const float* std;                   /* (num_actions) policy std parameter -> entropy */
+    int32_t num_actions;
+    const float* priv_reg_loss;         /* (1) */
+    const float* estimator_loss;        /* (1) */
+    const float* kl;                    /* (1) kl used by the schedule (all-reduced across ranks when sharded) */
+    float desired_kl;                   /* <= 0: fixed schedule, lr untouched */
+    float lr_min, lr_max;
+    float* lr;                          /* (1) in/out */
+    float* stats_accum;                 /* (7) in/out */
+} QaPpoScalarsArgs;
+int qa_ppo_scalars(const QaPpoScalarsArgs* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K14 TSC student depth preprocessing, all envs in one launch -- replaces the per-env loop of
+ *     LeggedRobot.update_depth_buffer / process_depth_image / crop_depth_image / normalize_depth_image,
+ *     tsc/legged_gym/envs/base/legged_robot.py:154-202.
+ *     Per env: crop the (in_h,in_w) camera image at (crop_top, crop_left) to (out_h,out_w), clip to [-far,-near],
+ *     x = (-x - near)/(far - near) - 0.5, + depth_noise*2*(u2-0.5) + (depth_noise*u1)*2*(u_pixel-0.5); then
+ *     depth_buffer[e] = new frame in all L slots if episode_length_buf[e] <= 1, else shift by one and append.
+ *     Random sources: dense uniforms (parity mode: all three arrays given) or in-kernel Philox4x32-10 keyed by
+ *     (rng_seed; env, site, rng_step).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct QaDepthArgs {
+    int32_t num_envs;
+    int32_t in_h, in_w;                 /* 60, 106 (cfg.depth.original is (W,H) = (106,60)) */
+    int32_t crop_top, crop_left;        /* 1, 10 */
+    int32_t out_h, out_w;               /* 58, 87 */
+    int32_t buffer_len;                 /* 2 */
+    const float* const* image_ptrs;     /* (N) device array of per-env camera tensors (gym.get_camera_image_gpu_tensor), or NULL */
+    const float* images;                /* batched alternative: env e at images + e*image_stride */
+    int64_t image_stride;
+    const int64_t* episode_length_buf;  /* (N) */
+    float near_clip, far_clip, depth_noise;
+    float clip_span;                    /* float32(far_clip - near_clip), the difference taken in double like the reference's Python */
+    const float* noise_scale_u;         /* (N) u1 or NULL */
+    const float* offset_u;              /* (N) u2 or NULL */
+    const float* pixel_u;               /* (N,out_h*out_w) or NULL */
+    uint64_t rng_seed, rng_step;
+    float* depth_buffer;                /* (N,L,out_h,out_w) in/out */
+} QaDepthArgs;
+int qa_depth_update(const QaDepthArgs* a, void* stream);
 
 #ifdef __cplusplus
 }

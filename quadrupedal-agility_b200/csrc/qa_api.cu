@@ -32,6 +32,9 @@ extern "C" int qa_struct_size(int which) {
         case 14: return (int)sizeof(QaPpoLossArgs);
         case 15: return (int)sizeof(QaLinearBwdArgs);
         case 16: return (int)sizeof(QaHistEncArgs);
+        case 17: return (int)sizeof(QaRowLossArgs);
+        case 18: return (int)sizeof(QaPpoScalarsArgs);
+        case 19: return (int)sizeof(QaDepthArgs);
         default: return -1;
     }
 }

@@ -30,16 +30,24 @@
 
 // Step arguments with the per-step scalars resolved: either the host-supplied fields or, under CUDA-graph
 // replay, values derived from the device-resident step counter (see QaBbcStepArgs::step_state).
+__device__ __forceinline__ long long k2_mod(long long v, int m) {      // counters fit 32 bits in practice
+    const unsigned long long u = (unsigned long long)v;
+    if ((u >> 32) == 0ull) return (long long)((unsigned)u % (unsigned)m);
+    return v % (long long)m;
+}
+__device__ __forceinline__ long long k2_load_step(const QaBbcStepArgs& in) {
+    return in.step_state != nullptr ? *reinterpret_cast<const volatile long long*>(in.step_state) : 0ll;
+}
 struct K2Step : QaBbcStepArgs {
-    __device__ __forceinline__ explicit K2Step(const QaBbcStepArgs& in) : QaBbcStepArgs(in) {
+    __device__ __forceinline__ K2Step(const QaBbcStepArgs& in, long long before) : QaBbcStepArgs(in) {
         if (in.step_state != nullptr) {
-            const long long before = *reinterpret_cast<const volatile long long*>(in.step_state);
             const long long cnt = before + 1;
             rng_step = (uint64_t)cnt;
-            do_push = (in.push_interval > 0 && (cnt % in.push_interval) == 0) ? 1 : 0;
-            contact_ring_head = in.contact_ring_len > 0 ? (int)(before % in.contact_ring_len) : 0;
+            do_push = (in.push_interval > 0 && k2_mod(cnt, in.push_interval) == 0) ? 1 : 0;
+            contact_ring_head = in.contact_ring_len > 0 ? (int)k2_mod(before, in.contact_ring_len) : 0;
         }
     }
+    __device__ __forceinline__ explicit K2Step(const QaBbcStepArgs& in) : K2Step(in, k2_load_step(in)) {}
 };
 
 struct K2Draw {

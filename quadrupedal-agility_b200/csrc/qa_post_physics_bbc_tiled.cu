@@ -153,6 +153,7 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
     const QaBbcStepArgs& r = a_in;
     GSTAMP(16, T_ENV);
     STAMP(0, T_ENV);
+    const long long step_before = k2_load_step(a_in);     // device step counter: in flight before anything else
 
     // ---------------- P0: every load of the tile is put in flight before the first barrier -----------------------
     // scalar warps fetch what their thread-per-env programs need with plain 16-B loads (they start computing as soon
@@ -218,7 +219,7 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
             }
         }
     }
-    const K2Step a(a_in);                  // per-step scalars (device counter read) only after the loads are in flight
+    const K2Step a(a_in, step_before);     // per-step scalars derived from the device counter
 
     bool any_state_write = a.do_push != 0;
 

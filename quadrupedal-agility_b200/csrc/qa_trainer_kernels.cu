@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(256) k_gather_minibatch(const __grid_constant_
         for (int t = 0; t < g.num_tensors; ++t) {
             const int w = g.width[t];
             const float* s = g.src[t] + src_row * w;
-            float* d = g.dst[t] + j * w;
+            float* d = g.dst[t] + j * (g.dst_pitch[t] > 0 ? g.dst_pitch[t] : w);
             int c = lane;
             // 4 independent loads in flight per lane
             for (; c + 96 < w; c += 128) {
@@ -45,6 +45,7 @@ extern "C" int qa_gather_minibatch(const QaGatherArgs* g, void* stream) {
         QA_CHECK_PTR(g->src[t]);
         QA_CHECK_PTR(g->dst[t]);
         if (g->width[t] <= 0) return QA_EINVAL;
+        if (g->dst_pitch[t] != 0 && g->dst_pitch[t] < g->width[t]) return QA_EINVAL;
     }
     long long blocks = (g->num_rows + 7) / 8;
     if (blocks > 148 * 16) blocks = 148 * 16;
@@ -326,5 +327,91 @@ extern "C" int qa_ppo_loss(const QaPpoLossArgs* p, void* stream) {
     e = cudaMemsetAsync(p->dstd, 0, sizeof(float) * PL_A, s);
     if (e != cudaSuccess) return (int)e;
     k_ppo_loss<<<(unsigned)((p->M + 255) / 256), 256, 0, s>>>(*p);
+    QA_LAUNCH_RET();
+}
+
+// ------------------------------------------------------------------------------------------
+// K12: row losses (gail.py:352-365), forward + gradient in one pass.  Warp per row, lanes = columns (coalesced),
+//      one shuffle butterfly per row, one atomic per block.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_row_loss(QaRowLossArgs p) {
+    __shared__ float s_red[8];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const float invM = 1.0f / (float)p.M;
+    const float inv_all = invM / (float)p.W;
+    float acc = 0.f;
+    for (long long i = (long long)blockIdx.x * 8 + w; i < p.M; i += (long long)gridDim.x * 8) {
+        float d = 0.f;
+        if (lane < p.W) d = p.a[i * p.a_pitch + lane] - p.b[i * p.b_pitch + lane];
+        const float ss = warp_sum(d * d);
+        if (p.mode == 0) {
+            acc += ss * inv_all;
+            if (lane < p.W) p.da[i * p.da_pitch + lane] = 2.f * d * inv_all;
+        } else {
+            const float n = sqrtf(ss);
+            acc += n * invM;
+            if (lane < p.W) p.da[i * p.da_pitch + lane] = n > 0.f ? d / n * invM : 0.f;   // torch: subgradient 0 at 0
+        }
+    }
+    if (lane == 0) s_red[w] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += s_red[k];
+        atomicAdd(p.loss, s);
+    }
+}
+
+extern "C" int qa_row_loss(const QaRowLossArgs* p, void* stream) {
+    QA_CHECK_PTR(p);
+    if (p->M <= 0 || p->W <= 0 || p->W > 32 || p->mode < 0 || p->mode > 1) return QA_EINVAL;
+    QA_CHECK_PTR(p->a);
+    QA_CHECK_PTR(p->b);
+    QA_CHECK_PTR(p->da);
+    QA_CHECK_PTR(p->loss);
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(p->loss, 0, sizeof(float), s);
+    if (e != cudaSuccess) return (int)e;
+    long long blocks = (p->M + 63) / 64;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    k_row_loss<<<(unsigned)blocks, 256, 0, s>>>(*p);
+    QA_LAUNCH_RET();
+}
+
+// ------------------------------------------------------------------------------------------
+// K13: adaptive-KL learning rate (gail.py:368-379) + running sums of the logged statistics, one thread.
+// ------------------------------------------------------------------------------------------
+__global__ void k_ppo_scalars(QaPpoScalarsArgs p) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const float kl = *p.kl;
+    if (p.desired_kl > 0.f) {
+        float lr = *p.lr;
+        if (kl > p.desired_kl * 2.0f) lr = fmaxf(lr / 1.5f, p.lr_min);
+        else if (kl < p.desired_kl / 2.0f && kl > 0.0f) lr = fminf(lr * 1.5f, p.lr_max);
+        *p.lr = lr;
+    }
+    float ent = 0.f;                                            // Normal.entropy().sum(-1).mean() with a broadcast std
+    for (int j = 0; j < p.num_actions; ++j) ent += 1.4189385332046727f + logf(p.std[j]);
+    p.stats_accum[0] += p.ppo_stats[0];
+    p.stats_accum[1] += p.ppo_stats[1];
+    p.stats_accum[2] += p.ppo_stats[2];
+    p.stats_accum[3] += ent;
+    p.stats_accum[4] += *p.priv_reg_loss;
+    p.stats_accum[5] += *p.estimator_loss;
+    p.stats_accum[6] += kl;
+}
+
+extern "C" int qa_ppo_scalars(const QaPpoScalarsArgs* p, void* stream) {
+    QA_CHECK_PTR(p);
+    QA_CHECK_PTR(p->ppo_stats);
+    QA_CHECK_PTR(p->std);
+    QA_CHECK_PTR(p->priv_reg_loss);
+    QA_CHECK_PTR(p->estimator_loss);
+    QA_CHECK_PTR(p->kl);
+    QA_CHECK_PTR(p->lr);
+    QA_CHECK_PTR(p->stats_accum);
+    if (p->num_actions <= 0) return QA_EINVAL;
+    k_ppo_scalars<<<1, 32, 0, (cudaStream_t)stream>>>(*p);
     QA_LAUNCH_RET();
 }

@@ -114,7 +114,7 @@ GATHER_MAX = 12
 
 class QaGatherArgs(C.Structure):
     _fields_ = [("num_rows", C.c_int64), ("num_tensors", C.c_int32), ("indices", vp), ("src", vp * GATHER_MAX),
-                ("dst", vp * GATHER_MAX), ("width", C.c_int32 * GATHER_MAX)]
+                ("dst", vp * GATHER_MAX), ("width", C.c_int32 * GATHER_MAX), ("dst_pitch", C.c_int32 * GATHER_MAX)]
 
 
 class QaClipAdamArgs(C.Structure):
@@ -156,6 +156,27 @@ class QaHistEncArgs(C.Structure):
                 ("b3", vp), ("out", vp), ("out_pitch", C.c_int64)]
 
 
+class QaRowLossArgs(C.Structure):
+    _fields_ = [("M", C.c_int64), ("W", C.c_int32), ("mode", C.c_int32), ("a", vp), ("a_pitch", C.c_int64),
+                ("b", vp), ("b_pitch", C.c_int64), ("da", vp), ("da_pitch", C.c_int64), ("loss", vp)]
+
+
+class QaPpoScalarsArgs(C.Structure):
+    _fields_ = [("ppo_stats", vp), ("std", vp), ("num_actions", C.c_int32), ("priv_reg_loss", vp),
+                ("estimator_loss", vp), ("kl", vp), ("desired_kl", C.c_float), ("lr_min", C.c_float),
+                ("lr_max", C.c_float), ("lr", vp), ("stats_accum", vp)]
+
+
+class QaDepthArgs(C.Structure):
+    _fields_ = [("num_envs", C.c_int32), ("in_h", C.c_int32), ("in_w", C.c_int32), ("crop_top", C.c_int32),
+                ("crop_left", C.c_int32), ("out_h", C.c_int32), ("out_w", C.c_int32), ("buffer_len", C.c_int32),
+                ("image_ptrs", vp), ("images", vp), ("image_stride", C.c_int64), ("episode_length_buf", vp),
+                ("near_clip", C.c_float), ("far_clip", C.c_float), ("depth_noise", C.c_float), ("clip_span", C.c_float),
+                ("noise_scale_u", vp),
+                ("offset_u", vp), ("pixel_u", vp), ("rng_seed", C.c_uint64), ("rng_step", C.c_uint64),
+                ("depth_buffer", vp)]
+
+
 # every symbol `include/qa_b200.h` declares: name -> (restype, argtypes)
 SYMBOLS = {
     "qa_version": (C.c_int, []),
@@ -175,10 +196,14 @@ SYMBOLS = {
     "qa_act_bwd": (C.c_int, [C.POINTER(QaActBwdArgs), vp]),
     "qa_hist_encoder_fwd": (C.c_int, [C.POINTER(QaHistEncArgs), vp]),
     "qa_ppo_loss": (C.c_int, [C.POINTER(QaPpoLossArgs), vp]),
+    "qa_row_loss": (C.c_int, [C.POINTER(QaRowLossArgs), vp]),
+    "qa_ppo_scalars": (C.c_int, [C.POINTER(QaPpoScalarsArgs), vp]),
+    "qa_depth_update": (C.c_int, [C.POINTER(QaDepthArgs), vp]),
 }
 
 STRUCT_ORDER = [QaActionPushArgs, QaTorqueArgs, QaTerrain, QaHeightScanArgs, QaMocapTable, QaMocapBlendArgs,
-                QaBbcConst, QaBbcStepArgs, QaCompactArgs, QaGaeArgs, QaGatherArgs, QaClipAdamArgs, QaLinearArgs, QaActBwdArgs, QaPpoLossArgs, QaLinearBwdArgs, QaHistEncArgs]
+                QaBbcConst, QaBbcStepArgs, QaCompactArgs, QaGaeArgs, QaGatherArgs, QaClipAdamArgs, QaLinearArgs, QaActBwdArgs, QaPpoLossArgs, QaLinearBwdArgs, QaHistEncArgs,
+                QaRowLossArgs, QaPpoScalarsArgs, QaDepthArgs]
 
 _LIB = None
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libqa_b200.so")

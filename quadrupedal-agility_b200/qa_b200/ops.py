@@ -38,6 +38,15 @@ def _p(t: Optional[torch.Tensor], dtype=None, name="tensor") -> Optional[int]:
     return t.data_ptr()
 
 
+def _p_strided(t: torch.Tensor, dtype, name) -> int:
+    """Device address of a 2-D tensor with unit column stride and an arbitrary row pitch (the wrapper passes the pitch)."""
+    if not t.is_cuda:
+        raise RuntimeError(f"qa_b200: {name} must be a CUDA tensor (no CPU fallback exists)")
+    if t.dim() != 2 or t.stride(1) != 1 or t.dtype != dtype:
+        raise RuntimeError(f"qa_b200: {name} must be a 2-D {dtype} tensor with unit column stride")
+    return t.data_ptr()
+
+
 def _bytep(t, name):
     if t.dtype not in (torch.bool, torch.uint8):
         raise RuntimeError(f"qa_b200: {name} must be bool/uint8")
@@ -155,7 +164,12 @@ def gather_minibatch(indices, srcs, dsts) -> None:
     for t, (s, d) in enumerate(zip(srcs, dsts)):
         if s.shape[1:] != d.shape[1:] or d.shape[0] != indices.shape[0]:
             raise RuntimeError("qa_gather_minibatch: shape mismatch")
-        a.src[t], a.dst[t] = _p(s, torch.float32, "src"), _p(d, torch.float32, "dst")
+        if d.dim() == 2 and d.stride(1) == 1 and d.stride(0) != d.shape[1]:      # padded rows (TMA-legal pitch)
+            a.src[t], a.dst[t] = _p(s, torch.float32, "src"), _p_strided(d, torch.float32, "dst")
+            a.dst_pitch[t] = int(d.stride(0))
+        else:
+            a.src[t], a.dst[t] = _p(s, torch.float32, "src"), _p(d, torch.float32, "dst")
+            a.dst_pitch[t] = 0
         a.width[t] = int(s[0].numel())
     _abi.check(lib.qa_gather_minibatch(C.byref(a), _stream()), "qa_gather_minibatch")
     _count(1)
@@ -353,4 +367,53 @@ def post_physics_bbc(const: _abi.QaBbcConst, args: _abi.QaBbcStepArgs) -> None:
     """One fused post-physics step (K2).  `args` is a pre-built, reusable struct of device pointers."""
     lib = _abi.load()
     _abi.check(lib.qa_post_physics_bbc(C.byref(const), C.byref(args), _stream()), "qa_post_physics_bbc")
+    _count(1)
+
+
+# ---- K12 / K13 ----------------------------------------------------------------------------------
+def row_loss(a, b, da, loss, mode: int) -> None:
+    """mode 0: loss = mean((a-b)^2); mode 1: loss = mean_i ||a_i - b_i||_2; da = d loss / d a (gail.py:352-365)."""
+    lib = _abi.load()
+    f = torch.float32
+    args = _abi.QaRowLossArgs(a.shape[0], a.shape[1], mode, _p_strided(a, f, "a"), a.stride(0), _p_strided(b, f, "b"),
+                              b.stride(0), _p_strided(da, f, "da"), da.stride(0), _p(loss, f, "loss"))
+    _abi.check(lib.qa_row_loss(C.byref(args), _stream()), "qa_row_loss")
+    _count(1)
+
+
+def ppo_scalars(ppo_stats, std, priv_reg_loss, estimator_loss, kl, desired_kl, lr, stats_accum,
+                lr_min=1e-5, lr_max=1e-2) -> None:
+    """Adaptive-KL learning rate (gail.py:368-379) + running sums of the seven logged statistics, on the device."""
+    lib = _abi.load()
+    f = torch.float32
+    args = _abi.QaPpoScalarsArgs(_p(ppo_stats, f, "ppo_stats"), _p(std, f, "std"), std.numel(),
+                                 _p(priv_reg_loss, f, "priv_reg_loss"), _p(estimator_loss, f, "estimator_loss"),
+                                 _p(kl, f, "kl"), float(desired_kl) if desired_kl else 0.0, lr_min, lr_max,
+                                 _p(lr, f, "lr"), _p(stats_accum, f, "stats_accum"))
+    _abi.check(lib.qa_ppo_scalars(C.byref(args), _stream()), "qa_ppo_scalars")
+    _count(1)
+
+
+# ---- K14 ----------------------------------------------------------------------------------------
+def depth_update(image_ptrs, images, episode_length_buf, depth_buffer, in_h, in_w, crop_top, crop_left, near_clip,
+                 far_clip, depth_noise, noise_scale_u=None, offset_u=None, pixel_u=None, rng_seed=0, rng_step=0) -> None:
+    """TSC update_depth_buffer for all envs (tsc/.../legged_robot.py:154-202).  `image_ptrs`: int64 device tensor of
+    N camera-tensor addresses, or `images`: one (N,in_h,in_w) tensor."""
+    lib = _abi.load()
+    f = torch.float32
+    N, L, H, W = depth_buffer.shape
+    a = _abi.QaDepthArgs()
+    a.num_envs, a.in_h, a.in_w, a.crop_top, a.crop_left, a.out_h, a.out_w, a.buffer_len = N, in_h, in_w, crop_top, crop_left, H, W, L
+    a.image_ptrs = _p(image_ptrs, torch.int64, "image_ptrs")
+    a.images = _p(images, f, "images")
+    a.image_stride = in_h * in_w
+    if image_ptrs is not None and image_ptrs.numel() != N:
+        raise RuntimeError("qa_depth_update: one camera pointer per env required")
+    a.episode_length_buf = _p(episode_length_buf, torch.int64, "episode_length_buf")
+    a.near_clip, a.far_clip, a.depth_noise = float(near_clip), float(far_clip), float(depth_noise)
+    a.clip_span = float(far_clip - near_clip)
+    a.noise_scale_u, a.offset_u, a.pixel_u = _p(noise_scale_u, f, "noise_scale_u"), _p(offset_u, f, "offset_u"), _p(pixel_u, f, "pixel_u")
+    a.rng_seed, a.rng_step = int(rng_seed), int(rng_step)
+    a.depth_buffer = _p(depth_buffer, f, "depth_buffer")
+    _abi.check(lib.qa_depth_update(C.byref(a), _stream()), "qa_depth_update")
     _count(1)

@@ -90,14 +90,32 @@ class _PPOLossFused(torch.autograd.Function):
                      mb["old_sigma"], dmu, dvalue, dstd, stats, cfg["clip"], cfg["c_surr"], cfg["c_value"],
                      cfg["c_bound"], cfg["c_entropy"], cfg["clipped_value"])
         ctx.save_for_backward(dmu, dvalue, dstd)
-        entropy = (1.4189385332046727 + torch.log(std.detach())).sum()
-        return (cfg["c_surr"] * stats[0] + cfg["c_value"] * stats[1] + cfg["c_bound"] * stats[2]
-                - cfg["c_entropy"] * entropy)
+        # the VALUE of the combined loss is never read (the logged statistics are its terms, accumulated by K13); the
+        # returned scalar only roots the backward pass
+        return stats[0] * cfg["c_surr"]
 
     @staticmethod
     def backward(ctx, g):
         dmu, dvalue, dstd = ctx.saved_tensors
         return g * dmu, (g * dvalue).unsqueeze(1), g * dstd, None, None, None
+
+
+class _RowLossFused(torch.autograd.Function):
+    """K12: estimator MSE (gail.py:359) / privileged-latent regulariser (:354), loss and gradient in one launch.
+    `b` is a constant (the reference detaches it / computes it under no_grad)."""
+
+    @staticmethod
+    def forward(ctx, a, b, mode, out):
+        M, W = a.shape
+        da = torch.empty(M, (W + 3) // 4 * 4, device=a.device, dtype=torch.float32)[:, :W]
+        ops.row_loss(a, b, da, out, mode)
+        ctx.save_for_backward(da)
+        return out[0] * 1.0
+
+    @staticmethod
+    def backward(ctx, g):
+        (da,) = ctx.saved_tensors
+        return da.mul_(g), None, None, None
 
 
 STAT_NAMES = ("surrogate_loss", "value_loss", "b_loss", "entropy", "priv_reg_loss", "estimator_loss", "kl_mean")
@@ -154,6 +172,7 @@ class SSInfoGAIL:
         self._graph_has_apply = True
         torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)   # capture runs on a side stream
         self._ppo_stats = torch.zeros(4, device=device)
+        self._aux_loss = torch.zeros(2, device=device)            # priv_reg_loss, estimator_loss of the current minibatch
         self._priv_reg_coef = torch.zeros((), device=device)
         self._stats = torch.zeros(len(STAT_NAMES), device=device)
         self.last_stats = {}
@@ -237,15 +256,29 @@ class SSInfoGAIL:
     def _alloc_minibatch(self, mb_size):
         st, dev = self.storage, self.device
         z = lambda w: torch.zeros(mb_size, w, device=dev)                       # noqa: E731
+        # observation rows are gathered straight into a 16-byte row pitch: a legal TMA operand for the first layers
+        zp = lambda w: torch.zeros(mb_size, (w + 3) // 4 * 4, device=dev)[:, :w]  # noqa: E731
         W, A = st.observations.shape[-1], st.actions.shape[-1]
         Wc = st.privileged_observations.shape[-1] if st.privileged_observations is not None else W
-        self._mb = dict(obs=z(W), critic_obs=z(Wc), actions=z(A), values=z(1), returns=z(1),
-                        old_actions_log_prob=z(1), advantages=z(1), old_mu=z(A), old_sigma=z(A))
+        self._mb = dict(obs=zp(W), critic_obs=zp(Wc), actions=z(A), values=z(1), returns=z(1),
+                        old_actions_log_prob=z(1), advantages=z(1), old_mu=z(A), old_sigma=z(A),
+                        hist_latent=z(self.num_latent))
         self._mb_keys = list(self._mb.keys())
+        # history-encoder latents of the whole rollout: the encoder is frozen during update() (it is trained by
+        # update_dagger), so its output per sample is computed once per update instead of once per epoch
+        self._hist_latent_all = torch.zeros(st.num_transitions_per_env * st.num_envs, self.num_latent, device=dev)
 
     def _gather(self, idx):
         v = self.storage.flat_views()
+        v["hist_latent"] = self._hist_latent_all
         ops.gather_minibatch(idx, [v[k] for k in self._mb_keys], [self._mb[k] for k in self._mb_keys])
+
+    @torch.no_grad()
+    def _encode_history(self):
+        """hist_latent (gail.py:352-353, under no_grad there too) for every stored sample, one K11 launch."""
+        p, e, l, h = self.num_prop, self.num_explicit, self.num_latent, self.num_hist * self.num_prop
+        flat_obs = self.storage.observations.flatten(0, 1)
+        self._hist_latent_all.copy_(self.actor_critic.infer_hist_latent(flat_obs[:, p + e + l:p + e + l + h]))
 
     def _forward_backward(self):
         """Forward + both backward passes of one minibatch (gail.py:328-408) on the static minibatch buffers.
@@ -257,13 +290,15 @@ class SSInfoGAIL:
         mu, sigma = ac.action_mean, ac.action_std
         logp = None if self.fused_loss else ac.get_actions_log_prob(mb["actions"])
         value = ac.evaluate(mb["critic_obs"])
-        entropy = ac.entropy
+        entropy = None if self.fused_loss else ac.entropy
         priv_latent = ac.infer_priv_latent(obs[:, p + e:p + e + l])
-        with torch.no_grad():
-            hist_latent = ac.infer_hist_latent(obs[:, p + e + l:p + e + l + h])
-        priv_reg_loss = (priv_latent - hist_latent).norm(p=2, dim=1).mean()
-        # estimator (:359-365)
-        est_loss = (est(obs[:, :p]) - obs[:, p:p + e]).pow(2).mean()
+        hist_latent = mb["hist_latent"]              # gathered; computed once per update by _encode_history()
+        if self.fused_loss:
+            priv_reg_loss = _RowLossFused.apply(priv_latent, hist_latent, 1, self._aux_loss[0:1])
+            est_loss = _RowLossFused.apply(est(obs[:, :p]), obs[:, p:p + e], 0, self._aux_loss[1:2])
+        else:
+            priv_reg_loss = (priv_latent - hist_latent).norm(p=2, dim=1).mean()
+            est_loss = (est(obs[:, :p]) - obs[:, p:p + e]).pow(2).mean()                 # estimator (:359-365)
         self.est_flat.zero_grad()
         est_loss.backward()
         if self.fused_loss:
@@ -272,9 +307,7 @@ class SSInfoGAIL:
                        clipped_value=self.use_clipped_value_loss)
             main = _PPOLossFused.apply(mu, value, ac.std, mb, cfg, self._ppo_stats)
             ps = self._ppo_stats
-            surrogate_loss, value_loss, b_loss = ps[0], ps[1], ps[2]
             self._kl.copy_(ps[3])
-            ent = entropy.mean()
             loss = main + self._priv_reg_coef * priv_reg_loss
         else:
             # KL for the adaptive schedule (:367-373)
@@ -300,9 +333,10 @@ class SSInfoGAIL:
                     self.bounds_loss_coef * b_loss - self.entropy_coef * ent + self._priv_reg_coef * priv_reg_loss)
         self.ac_flat.zero_grad()
         loss.backward()
-        with torch.no_grad():
-            self._stats += torch.stack([surrogate_loss.detach(), value_loss.detach(), b_loss.detach(), ent.detach(),
-                                        priv_reg_loss.detach(), est_loss.detach(), self._kl])
+        if not self.fused_loss:
+            with torch.no_grad():
+                self._aux_loss.copy_(torch.stack([priv_reg_loss.detach(), est_loss.detach()]))
+                self._ppo_stats.copy_(torch.stack([surrogate_loss.detach(), value_loss.detach(), b_loss.detach(), self._kl]))
 
     def _apply(self):
         """All-reduce (multi-GPU), adaptive LR on the device (:374-379), fused clip + Adam (:361-365, :409-412)."""
@@ -312,11 +346,21 @@ class SSInfoGAIL:
             qdist.allreduce_flat_(self.est_flat.grad)
             qdist.allreduce_mean_scalar_(self._kl)
         self.optim_estimator.step(scale)
-        if self.desired_kl is not None and self.schedule == 'adaptive':
-            lr, kl = self.optim_ac.lr, self._kl
-            hi = kl > self.desired_kl * 2.0
-            lo = (kl < self.desired_kl / 2.0) & (kl > 0.0)
-            lr.copy_(torch.where(hi, torch.clamp(lr / 1.5, min=1e-5), torch.where(lo, torch.clamp(lr * 1.5, max=1e-2), lr)))
+        adaptive = self.desired_kl is not None and self.schedule == 'adaptive'
+        if torch.device(self.device).type == "cuda":
+            # K13: adaptive LR + the seven running statistics, one launch
+            ops.ppo_scalars(self._ppo_stats, self.actor_critic.std.detach(), self._aux_loss[0:1], self._aux_loss[1:2],
+                            self._kl.view(1), self.desired_kl if adaptive else 0.0, self.optim_ac.lr, self._stats)
+        else:
+            with torch.no_grad():
+                ent = (1.4189385332046727 + torch.log(self.actor_critic.std.detach())).sum()
+                ps, ax = self._ppo_stats, self._aux_loss
+                self._stats += torch.stack([ps[0], ps[1], ps[2], ent, ax[0], ax[1], self._kl])
+            if adaptive:
+                lr, kl = self.optim_ac.lr, self._kl
+                hi = kl > self.desired_kl * 2.0
+                lo = (kl < self.desired_kl / 2.0) & (kl > 0.0)
+                lr.copy_(torch.where(hi, torch.clamp(lr / 1.5, min=1e-5), torch.where(lo, torch.clamp(lr * 1.5, max=1e-2), lr)))
         self.optim_ac.step(scale)
 
     def _minibatch_step(self):
@@ -373,6 +417,7 @@ class SSInfoGAIL:
         self._priv_reg_coef.fill_(stage * (sch[1] - sch[0]) + sch[0])
         if indices is None:
             indices = torch.randperm(self.num_mini_batches * mb_size, device=self.device)
+        self._encode_history()
         if self.use_cuda_graph and self._graphs is None:
             self._gather(indices[:mb_size])
             self._capture()

@@ -223,7 +223,8 @@ class ActorCritic(nn.Module):
     def update_distribution(self, observations, hist_encoding: bool):
         mean = self._actor_mean(observations, hist_encoding)
         self._mean = mean
-        self._std = mean * 0. + self.std.to(mean.device)
+        # Normal(mean, mean*0. + std) (actor_critic.py:189-190): the broadcast is a stride-0 view, not a materialised tensor
+        self._std = self.std.to(mean.device).expand_as(mean)
 
     def act(self, observations, hist_encoding=False, **kwargs):
         self.update_distribution(observations, hist_encoding)

@@ -77,6 +77,8 @@ def test_ppo_minibatch_step_matches_reference_golden(fused_loss):
                       ("old_actions_log_prob", "old_actions_log_prob"), ("advantages", "advantages"),
                       ("old_mu", "old_mu"), ("old_sigma", "old_sigma")):
         mb[k_mb].copy_(g["in.batch." + k_g])
+    with torch.no_grad():        # update() encodes the history of the whole rollout once; here: of this minibatch
+        mb["hist_latent"].copy_(alg.actor_critic.infer_hist_latent(mb["obs"][:, 90:660]))
     alg._priv_reg_coef.fill_(OT.priv_reg_coef(1500))
     alg._stats.zero_()
     alg._minibatch_step()
@@ -104,6 +106,55 @@ def test_gather_minibatch_matches_indexing():
     for s, d in zip(srcs, dsts):
         assert torch.equal(d, s[idx])
     ops.gather_minibatch(idx[:0], srcs, [d[:0] for d in dsts])         # empty minibatch
+
+
+def test_gather_minibatch_padded_destination_pitch():
+    g = torch.Generator().manual_seed(2)
+    R = 4096
+    srcs = [torch.randn(R, w, generator=g).to(DEV) for w in (671, 29, 12)]
+    idx = torch.randperm(R, generator=g)[:1000].to(DEV)
+    dsts = [torch.full((1000, (s.shape[1] + 3) // 4 * 4), 7.0, device=DEV)[:, :s.shape[1]] for s in srcs]
+    ops.gather_minibatch(idx, srcs, dsts)
+    for s, d in zip(srcs, dsts):
+        assert d.stride(0) % 4 == 0
+        assert torch.equal(d, s[idx])
+
+
+@pytest.mark.parametrize("mode,width", [(0, 4), (1, 29), (1, 32), (0, 1)])
+def test_row_loss_matches_torch_forward_and_gradient(mode, width):
+    """K12 against the reference expressions gail.py:354 (mean row L2 distance) and :359 (MSE)."""
+    g = torch.Generator().manual_seed(3)
+    M = 3001
+    a = torch.randn(M, width, generator=g).to(DEV).requires_grad_(True)
+    b = torch.randn(M, width, generator=g).to(DEV)
+    if mode == 1:
+        with torch.no_grad():
+            a[5] = b[5]                                                  # zero distance: subgradient 0, no NaN
+    want = (a - b).pow(2).mean() if mode == 0 else (a - b).norm(p=2, dim=1).mean()
+    (gw,) = torch.autograd.grad(want, a)
+    da = torch.empty(M, (width + 3) // 4 * 4, device=DEV)[:, :width]
+    loss = torch.zeros(1, device=DEV)
+    ops.row_loss(a.detach(), b, da, loss, mode)
+    assert_close("row loss", loss[0], want.detach(), rtol=1e-5, atol=1e-7)
+    assert_close("row loss grad", da, gw, rtol=1e-5, atol=1e-9)
+
+
+def test_ppo_scalars_adaptive_lr_and_running_stats():
+    """K13 against the rule of gail.py:374-379."""
+    std = torch.tensor([0.5, 1.0, 2.0], device=DEV)
+    ent = float((1.4189385332046727 + torch.log(std)).sum())
+    for kl, lr0, want_lr in ((0.05, 1e-3, 1e-3 / 1.5), (0.001, 1e-3, 1.5e-3), (0.01, 1e-3, 1e-3), (0.05, 1.2e-5, 1e-5),
+                             (0.001, 9e-3, 1e-2), (0.0, 1e-3, 1e-3)):
+        lr = torch.tensor([lr0], device=DEV)
+        acc = torch.ones(7, device=DEV)
+        ops.ppo_scalars(torch.tensor([1., 2., 3., kl], device=DEV), std, torch.tensor([4.], device=DEV),
+                        torch.tensor([5.], device=DEV), torch.tensor([kl], device=DEV), 0.01, lr, acc)
+        assert abs(float(lr) - want_lr) < 1e-9, (kl, lr0)
+        assert_close("stats", acc, torch.tensor([2., 3., 4., 1. + ent, 5., 6., 1. + kl]), rtol=1e-6, atol=1e-7)
+    lr = torch.tensor([1e-3], device=DEV)
+    ops.ppo_scalars(torch.zeros(4, device=DEV), std, torch.zeros(1, device=DEV), torch.zeros(1, device=DEV),
+                    torch.tensor([0.5], device=DEV), 0.0, lr, torch.zeros(7, device=DEV))     # fixed schedule
+    assert float(lr) == pytest.approx(1e-3)
 
 
 def test_clip_adam_matches_torch():

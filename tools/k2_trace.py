@@ -47,7 +47,7 @@ def build():
     os.makedirs(OUT, exist_ok=True)
     objs, procs = [], []
     for f in sorted(x for x in os.listdir(csrc) if x.endswith(".cu")):
-        exact = f.startswith(("qa_env_kernels", "qa_post_physics", "qa_gae"))
+        exact = f.startswith(("qa_env_kernels", "qa_post_physics", "qa_gae", "qa_depth", "qa_tsc"))
         o = os.path.join(OUT, f[:-3] + ".o")
         objs.append(o)
         procs.append(subprocess.Popen(
