@@ -51,7 +51,7 @@ int qa_version(void);
 /* human readable build string ("sm_100a, nvcc 12.9, ...") */
 const char* qa_build_info(void);
 /* sizeof() of argument struct number `which` (order of declaration in this header, QaActionPushArgs
- * = 0 ... QaGaeArgs = 9, QaGatherArgs = 10, QaClipAdamArgs = 11, QaLinearArgs = 12, QaActBwdArgs = 13, QaPpoLossArgs = 14, QaLinearBwdArgs = 15, QaHistEncArgs = 16, QaRowLossArgs = 17, QaPpoScalarsArgs = 18, QaDepthArgs = 19; -1 if unknown): a layout handshake for FFI mirrors of these structs */
+ * = 0 ... QaGaeArgs = 9, QaGatherArgs = 10, QaClipAdamArgs = 11, QaLinearArgs = 12, QaActBwdArgs = 13, QaPpoLossArgs = 14, QaLinearBwdArgs = 15, QaHistEncArgs = 16, QaRowLossArgs = 17, QaPpoScalarsArgs = 18, QaDepthArgs = 19, QaPpoLossTscArgs = 20; -1 if unknown): a layout handshake for FFI mirrors of these structs */
 int qa_struct_size(int which);
 
 /* ------------------------------------------------------------------------------------------
@@ -535,6 +535,41 @@ typedef struct QaDepthArgs {
     float* depth_buffer;                /* (N,L,out_h,out_w) in/out */
 } QaDepthArgs;
 int qa_depth_update(const QaDepthArgs* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K15 TSC PPO loss forward + backward -- the element-wise graph of PPO.update, tsc/rsl_rl/algorithms/ppo.py:176-262:
+ *     a Categorical over the behaviour modes (probs = softmax(logits), torch's clamped-log semantics) and a Normal over
+ *     the continuous actions, one clipped surrogate each, clipped value loss, KL of the Normal part, entropy
+ *     = mean_j H(Normal_j) + H(Categorical).
+ *     loss = surr_d + surr_c + c_value*value_loss - c_entropy*mean(entropy)   (+ priv_reg, added by the caller;
+ *     the reference's bound loss has coefficient 0.0).  Gradients w.r.t. the logits, the action mean, the value
+ *     and the std parameter are written; stats = means of {surrogate, value_loss, entropy, kl}.
+ * ------------------------------------------------------------------------------------------ */
+#define QA_TSC_NUM_MODES 3
+#define QA_TSC_NUM_CONT 18
+typedef struct QaPpoLossTscArgs {
+    int64_t M;
+    const float* logits; int64_t logits_pitch;   /* (M,3) mode head output (pre-softmax) */
+    const float* mu; int64_t mu_pitch;           /* (M,18) */
+    const float* std;                            /* (18) */
+    const float* value; int64_t value_pitch;     /* (M,1) */
+    const float* actions; int64_t actions_pitch; /* (M,19): [mode index as float | 18 continuous] */
+    const float* old_logp_d;                     /* (M) */
+    const float* old_logp_c;                     /* (M) */
+    const float* advantages;                     /* (M) */
+    const float* returns;                        /* (M) */
+    const float* target_values;                  /* (M) */
+    const float* old_mu;                         /* (M,18) */
+    const float* old_sigma;                      /* (M,18) */
+    float clip, c_value, c_entropy;
+    int32_t use_clipped_value_loss;
+    float* dlogits; int64_t dlogits_pitch;       /* (M,3) */
+    float* dmu; int64_t dmu_pitch;               /* (M,18) */
+    float* dvalue;                               /* (M) */
+    float* dstd;                                 /* (18) */
+    float* stats;                                /* (4) */
+} QaPpoLossTscArgs;
+int qa_ppo_loss_tsc(const QaPpoLossTscArgs* a, void* stream);
 
 #ifdef __cplusplus
 }

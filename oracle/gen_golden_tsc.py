@@ -67,12 +67,123 @@ def depth_case(ref, N, seed):
     return dict(images=images, ep=ep, buf0=buf0, u1=u1, u2=u2, up=up, want=want)
 
 
+STRIDE = 97
+
+
+def sample_params(sd):
+    return torch.cat([v.reshape(-1) for v in sd.values()])[::STRIDE].clone()
+
+
+def trainer_case(ref, seed=3, N=64):
+    """ActorCriticTSC forward + one full PPO.update() over a 1 x N storage (one minibatch, one epoch) with the
+    reference's own classes, against oracle/tsc_trainer.py."""
+    import tsc_trainer as OT
+    from qa_b200 import synthetic
+    torch.set_num_threads(1)
+    w = synthetic.make_tsc_weights(seed)
+    policy = dict(scan_encoder_dims=[128, 64, 32], actor_hidden_dims=[512, 256, 128], critic_hidden_dims=[512, 256, 128],
+                  priv_encoder_dims=[64], activation="elu", init_noise_std=1.0, tanh_encoder_output=False)
+    ac = ref.actor_critic.ActorCriticTSC(65, 8, 132, 800, 29, 4, 10, 3, 6, device="cpu", **policy)
+    ac.load_state_dict(w["ac"])
+    est = ref.estimator.Estimator(input_dim=57, output_dim=4, hidden_dims=[128, 64])
+    est.load_state_dict(w["est"])
+    g = torch.Generator().manual_seed(seed)
+    obs = torch.randn(N, 800, generator=g) * 0.5
+    obs[:, 65:197] = torch.clip(obs[:, 65:197], -1, 1)
+    draw, mode_u = torch.randn(N, 18, generator=g), torch.rand(N, generator=g)
+    P = ref.ppo.PPO
+    alg = P.__new__(P)
+    alg.device, alg.actor_critic, alg.estimator = "cpu", ac, est
+    alg.train_with_estimated_states, alg.num_prop, alg.num_auxiliary, alg.num_scan, alg.priv_states_dim = True, 57, 8, 132, 4
+    alg.transition = ref.RolloutStorage.Transition()
+    alg.optimizer = torch.optim.Adam(ac.parameters(), lr=5e-4)
+    alg.estimator_optimizer = torch.optim.Adam(est.parameters(), lr=1e-4)
+    alg.learning_rate, alg.desired_kl, alg.schedule = 5e-4, 0.01, "adaptive"
+    alg.clip_param, alg.use_clipped_value_loss, alg.value_loss_coef, alg.entropy_coef = 0.2, True, 1.0, 0.01
+    alg.max_grad_norm, alg.num_learning_epochs, alg.num_mini_batches = 1.0, 1, 1
+    alg.priv_reg_coef_schedual, alg.counter = [0, 0.1, 500, 1000], 800
+    alg.gamma, alg.lam = 0.99, 0.95
+    alg.update_counter = lambda: None
+    # ---- act (ppo.py:101-125) with the draws injected into Categorical.sample / Normal.sample -------------------
+    Normal, Categorical = torch.distributions.Normal, torch.distributions.Categorical
+    n_orig, c_orig = Normal.sample, Categorical.sample
+    Normal.sample = lambda self, sample_shape=torch.Size(): (self.loc + self.scale * draw).detach()
+    Categorical.sample = lambda self, sample_shape=torch.Size(): OT.sample_mode(self.probs, mode_u)
+    out = {}
+    for he in (False, True):
+        with torch.no_grad():
+            a = alg.act(obs.clone(), obs.clone(), None, hist_encoding=he)
+        tr = alg.transition
+        o = OT.act(w["ac"], w["est"], obs, obs, draw, mode_u, hist_encoding=he)
+        for k, rv in (("actions", a), ("values", tr.values), ("actions_log_prob_d", tr.actions_log_prob_d),
+                      ("actions_log_prob_c", tr.actions_log_prob_c), ("action_mean", tr.action_mean),
+                      ("action_sigma", tr.action_sigma)):
+            assert torch.allclose(o[k], rv, rtol=1e-6, atol=1e-6), ("act", he, k, float((o[k] - rv).abs().max()))
+            out[f"act{int(he)}.{k}"] = rv.clone()
+    # ---- one PPO.update() (ppo.py:159-262): T=1 storage, one minibatch, one epoch -----------------------------
+    o0 = OT.act(w["ac"], w["est"], obs, obs, draw, mode_u, hist_encoding=False)
+    batch = dict(obs=obs, critic_obs=obs, actions=o0["actions"], target_values=o0["values"],
+                 advantages=torch.randn(N, 1, generator=g), returns=o0["values"] + 0.3 * torch.randn(N, 1, generator=g),
+                 old_actions_log_prob_d=(o0["actions_log_prob_d"] + 0.05 * torch.randn(N, generator=g)).unsqueeze(1),
+                 old_actions_log_prob_c=(o0["actions_log_prob_c"] + 0.05 * torch.randn(N, generator=g)).unsqueeze(1),
+                 old_mu=o0["action_mean"] + 0.05 * torch.randn(N, 18, generator=g), old_sigma=o0["action_sigma"] * 1.05)
+    st = ref.RolloutStorage(N, 1, [800], [None], [19], device="cpu")
+    st.observations[0], st.actions[0], st.values[0] = batch["obs"], batch["actions"], batch["target_values"]
+    st.advantages[0], st.returns[0] = batch["advantages"], batch["returns"]
+    st.actions_log_prob_d[0], st.actions_log_prob_c[0] = batch["old_actions_log_prob_d"], batch["old_actions_log_prob_c"]
+    st.mu[0], st.sigma[0] = batch["old_mu"], batch["old_sigma"]
+    alg.storage = st
+    ret = alg.update()                          # (value, surrogate, estimator, 0, 0, priv_reg, priv_reg_coef)
+    Normal.sample, Categorical.sample = n_orig, c_orig
+    coef = OT.tsc_priv_reg_coef(800)
+    assert abs(coef - ret[6]) < 1e-12
+    sd_ac = {k: v.clone().requires_grad_(True) for k, v in w["ac"].items()}
+    sd_est = {k: v.clone().requires_grad_(True) for k, v in w["est"].items()}
+    L = OT.ppo_losses(sd_ac, sd_est, batch, priv_reg_coef=coef)
+    opt_e = torch.optim.Adam(list(sd_est.values()), lr=1e-4)
+    L["estimator_loss"].backward()
+    torch.nn.utils.clip_grad_norm_(list(sd_est.values()), 1.0)
+    opt_e.step()
+    lr_new = OT.adaptive_lr(5e-4, float(L["kl_mean"]))
+    opt_a = torch.optim.Adam(list(sd_ac.values()), lr=lr_new)
+    L["ppo_loss"].backward()
+    torch.nn.utils.clip_grad_norm_(list(sd_ac.values()), 1.0)
+    opt_a.step()
+    for k, rv in (("value_loss", ret[0]), ("surrogate_loss", ret[1]), ("estimator_loss", ret[2]), ("priv_reg_loss", ret[5])):
+        assert abs(float(L[k]) - rv) <= 1e-5 * abs(rv) + 1e-7, (k, float(L[k]), rv)
+        out[f"ppo.{k}"] = torch.tensor(rv, dtype=torch.float32)
+    assert abs(alg.learning_rate - lr_new) < 1e-12, (alg.learning_rate, lr_new)
+    ref_ac = {k: v.detach() for k, v in ac.state_dict().items()}
+    ref_est = {k: v.detach() for k, v in est.state_dict().items()}
+    for k in ref_ac:
+        d = (sd_ac[k].detach() - ref_ac[k]).abs()
+        # Adam's first step moves every weight by lr * g / (|g| + eps): entries whose gradient is ~1e-8 (dead ELU
+        # paths) amplify summation-order noise, so a handful of entries may differ by a fraction of lr
+        assert float(d.max()) <= 2.5 * lr_new and float((d > 1e-6).float().mean()) < 2e-3, ("post-step", k, float(d.max()), float((d > 1e-6).float().mean()))
+    for k in ref_est:
+        assert torch.allclose(sd_est[k].detach(), ref_est[k], rtol=1e-5, atol=1e-7), ("post-step est", k)
+    out["ppo.kl_mean"], out["ppo.entropy"] = L["kl_mean"].detach().clone(), L["entropy"].detach().clone()
+    out["ppo.lr_new"] = torch.tensor(lr_new, dtype=torch.float64)
+    out["ppo.ac_params_sampled"], out["ppo.est_params_sampled"] = sample_params(ref_ac), sample_params(ref_est)
+    print(f"  trainer: ActorCriticTSC act / PPO.update: oracle == reference (kl={float(L['kl_mean']):.4f}, "
+          f"lr 5e-4 -> {lr_new:.6f}, modes drawn {torch.bincount(o0['actions'][:, 0].long(), minlength=3).tolist()})")
+    save = {k: v.numpy() for k, v in out.items()}
+    save.update({"in.obs": obs.numpy(), "in.draw": draw.numpy(), "in.mode_u": mode_u.numpy(), "in.weights_seed": np.array(seed),
+                 "in.counter": np.array(800), "in.param_stride": np.array(STRIDE)})
+    for k in ("advantages", "returns", "old_actions_log_prob_d", "old_actions_log_prob_c", "old_mu", "old_sigma",
+              "target_values", "actions"):
+        save["in.batch." + k] = batch[k].numpy()
+    return save
+
+
 def main():
     ref = import_reference("tsc")
     print("reference tsc imported from", ref.root)
     d = depth_case(ref, 6, seed=11)
     np.savez_compressed(os.path.join(GOLD, "tsc_depth_n6.npz"), **{k: v.numpy() for k, v in d.items()})
     print("wrote tests/golden/tsc_depth_n6.npz")
+    np.savez_compressed(os.path.join(GOLD, "tsc_trainer_seed3.npz"), **trainer_case(ref))
+    print("wrote tests/golden/tsc_trainer_seed3.npz")
 
 
 if __name__ == "__main__":

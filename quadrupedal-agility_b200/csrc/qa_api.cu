@@ -35,6 +35,7 @@ extern "C" int qa_struct_size(int which) {
         case 17: return (int)sizeof(QaRowLossArgs);
         case 18: return (int)sizeof(QaPpoScalarsArgs);
         case 19: return (int)sizeof(QaDepthArgs);
+        case 20: return (int)sizeof(QaPpoLossTscArgs);
         default: return -1;
     }
 }

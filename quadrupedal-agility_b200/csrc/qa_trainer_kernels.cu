@@ -415,3 +415,171 @@ extern "C" int qa_ppo_scalars(const QaPpoScalarsArgs* p, void* stream) {
     k_ppo_scalars<<<1, 32, 0, (cudaStream_t)stream>>>(*p);
     QA_LAUNCH_RET();
 }
+
+// ------------------------------------------------------------------------------------------
+// K15: TSC PPO loss, forward + backward in one pass (tsc/rsl_rl/algorithms/ppo.py:176-262).  Thread per sample: the
+//      3 mode logits and the 18 continuous dims live in registers.  Categorical follows torch.distributions:
+//      probs = softmax(z) (re-normalised), logits = log(clamp(probs, eps, 1 - eps)), entropy = -sum(probs * logits);
+//      the clamp passes gradient only inside [eps, 1 - eps].
+// ------------------------------------------------------------------------------------------
+#define TL_D QA_TSC_NUM_MODES
+#define TL_A QA_TSC_NUM_CONT
+#define TL_STATS 4
+__global__ void __launch_bounds__(256) k_ppo_loss_tsc(QaPpoLossTscArgs p) {
+    __shared__ float s_red[8][TL_STATS + TL_A];
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const float invM = 1.0f / (float)p.M;
+    const float EPSF = 1.1920928955078125e-07f;
+    float st[TL_STATS + TL_A];
+#pragma unroll
+    for (int k = 0; k < TL_STATS + TL_A; ++k) st[k] = 0.f;
+    if (i < p.M) {
+        const float adv = p.advantages[i];
+        // ---- mode head ----
+        float z[TL_D], pr[TL_D], L[TL_D], msk[TL_D];
+        float zmax = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < TL_D; ++k) {
+            z[k] = p.logits[i * p.logits_pitch + k];
+            zmax = fmaxf(zmax, z[k]);
+        }
+        float S = 0.f;
+#pragma unroll
+        for (int k = 0; k < TL_D; ++k) {
+            pr[k] = expf(z[k] - zmax);
+            S += pr[k];
+        }
+        float S2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < TL_D; ++k) {
+            pr[k] = pr[k] / S;
+            S2 += pr[k];
+        }
+        float Hd = 0.f;
+#pragma unroll
+        for (int k = 0; k < TL_D; ++k) {
+            pr[k] = pr[k] / S2;                                     // Categorical(probs=...) normalises again
+            msk[k] = (pr[k] >= EPSF && pr[k] <= 1.f - EPSF) ? 1.f : 0.f;
+            L[k] = logf(fminf(fmaxf(pr[k], EPSF), 1.f - EPSF));
+            Hd -= pr[k] * L[k];
+        }
+        int a_d = (int)p.actions[i * p.actions_pitch];
+        a_d = min(max(a_d, 0), TL_D - 1);
+        float logp_d = 0.f, pa = 1.f, ma = 0.f;
+#pragma unroll
+        for (int k = 0; k < TL_D; ++k)
+            if (k == a_d) logp_d = L[k], pa = pr[k], ma = msk[k];
+        const float lo_c = 1.0f - p.clip, hi_c = 1.0f + p.clip;
+        float surr_total = 0.f;
+        float dlogp_d;
+        {
+            const float ratio = expf(logp_d - p.old_logp_d[i]);
+            const float rc = fminf(fmaxf(ratio, lo_c), hi_c);
+            const float s1 = -adv * ratio, s2 = -adv * rc;
+            surr_total += fmaxf(s1, s2);
+            const float in_range = (ratio >= lo_c && ratio <= hi_c) ? 1.f : 0.f;
+            float w1, w2;
+            if (s1 > s2) { w1 = 1.f; w2 = 0.f; } else if (s2 > s1) { w1 = 0.f; w2 = 1.f; } else { w1 = 0.5f; w2 = 0.5f; }
+            dlogp_d = invM * (-adv * (w1 + w2 * in_range)) * ratio;
+        }
+        {
+            // g_k = d loss / d probs_k ; dz_j = probs_j (g_j - sum_k g_k probs_k)
+            float g[TL_D], G = 0.f;
+#pragma unroll
+            for (int k = 0; k < TL_D; ++k) {
+                g[k] = p.c_entropy * invM * (L[k] + msk[k]);
+                if (k == a_d) g[k] += dlogp_d * ma / pa;
+                G += g[k] * pr[k];
+            }
+#pragma unroll
+            for (int k = 0; k < TL_D; ++k) p.dlogits[i * p.dlogits_pitch + k] = pr[k] * (g[k] - G);
+        }
+        // ---- continuous head ----
+        float mu[TL_A], sg[TL_A], diff[TL_A];
+        float logp = 0.f, kl = 0.f, ent_c = 0.f;
+#pragma unroll
+        for (int j = 0; j < TL_A; ++j) {
+            mu[j] = p.mu[i * p.mu_pitch + j];
+            sg[j] = p.std[j];
+            const float a = p.actions[i * p.actions_pitch + 1 + j];
+            diff[j] = a - mu[j];
+            const float lsg = logf(sg[j]);
+            logp += -(diff[j] * diff[j]) / (2.f * sg[j] * sg[j]) - lsg - 0.9189385332046727f;
+            ent_c += 1.4189385332046727f + lsg;
+            const float os = p.old_sigma[i * TL_A + j], om = p.old_mu[i * TL_A + j];
+            kl += logf(sg[j] / os + 1.e-5f) + (os * os + (om - mu[j]) * (om - mu[j])) / (2.0f * sg[j] * sg[j]) - 0.5f;
+        }
+        ent_c = ent_c / (float)TL_A;
+        float dlogp_c;
+        {
+            const float ratio = expf(logp - p.old_logp_c[i]);
+            const float rc = fminf(fmaxf(ratio, lo_c), hi_c);
+            const float s1 = -adv * ratio, s2 = -adv * rc;
+            surr_total += fmaxf(s1, s2);
+            const float in_range = (ratio >= lo_c && ratio <= hi_c) ? 1.f : 0.f;
+            float w1, w2;
+            if (s1 > s2) { w1 = 1.f; w2 = 0.f; } else if (s2 > s1) { w1 = 0.f; w2 = 1.f; } else { w1 = 0.5f; w2 = 0.5f; }
+            dlogp_c = invM * (-adv * (w1 + w2 * in_range)) * ratio;
+        }
+        // ---- value loss ----
+        const float v = p.value[i * p.value_pitch], R = p.returns[i];
+        float vl, dv;
+        if (p.use_clipped_value_loss) {
+            const float tv = p.target_values[i];
+            const float dvt = v - tv;
+            const float vc = tv + fminf(fmaxf(dvt, -p.clip), p.clip);
+            const float l1 = (v - R) * (v - R), l2 = (vc - R) * (vc - R);
+            vl = fmaxf(l1, l2);
+            const float dvc = (dvt >= -p.clip && dvt <= p.clip) ? 1.f : 0.f;
+            float u1, u2;
+            if (l1 > l2) { u1 = 1.f; u2 = 0.f; } else if (l2 > l1) { u1 = 0.f; u2 = 1.f; } else { u1 = 0.5f; u2 = 0.5f; }
+            dv = u1 * 2.f * (v - R) + u2 * 2.f * (vc - R) * dvc;
+        } else {
+            vl = (R - v) * (R - v);
+            dv = 2.f * (v - R);
+        }
+        p.dvalue[i] = p.c_value * invM * dv;
+#pragma unroll
+        for (int j = 0; j < TL_A; ++j) {
+            const float s2j = sg[j] * sg[j];
+            p.dmu[i * p.dmu_pitch + j] = dlogp_c * diff[j] / s2j;
+            st[TL_STATS + j] = dlogp_c * ((diff[j] * diff[j]) / (s2j * sg[j]) - 1.f / sg[j]) -
+                               p.c_entropy * invM / ((float)TL_A * sg[j]);
+        }
+        st[0] = surr_total * invM;
+        st[1] = vl * invM;
+        st[2] = (ent_c + Hd) * invM;
+        st[3] = kl * invM;                                          // same slot as K10, so K13 serves both trainers
+    }
+#pragma unroll
+    for (int k = 0; k < TL_STATS + TL_A; ++k) st[k] = warp_sum(st[k]);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < TL_STATS + TL_A; ++k) s_red[w][k] = st[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < TL_STATS + TL_A) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += s_red[k][threadIdx.x];
+        if (threadIdx.x < TL_STATS) atomicAdd(p.stats + threadIdx.x, s);
+        else atomicAdd(p.dstd + (threadIdx.x - TL_STATS), s);
+    }
+}
+
+extern "C" int qa_ppo_loss_tsc(const QaPpoLossTscArgs* p, void* stream) {
+    QA_CHECK_PTR(p);
+    if (p->M <= 0) return QA_EINVAL;
+    const void* need[] = {p->logits, p->mu, p->std, p->value, p->actions, p->old_logp_d, p->old_logp_c, p->advantages,
+                          p->returns, p->target_values, p->old_mu, p->old_sigma, p->dlogits, p->dmu, p->dvalue, p->dstd,
+                          p->stats};
+    for (const void* q : need) QA_CHECK_PTR(q);
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(p->stats, 0, sizeof(float) * TL_STATS, s);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemsetAsync(p->dstd, 0, sizeof(float) * TL_A, s);
+    if (e != cudaSuccess) return (int)e;
+    k_ppo_loss_tsc<<<(unsigned)((p->M + 255) / 256), 256, 0, s>>>(*p);
+    QA_LAUNCH_RET();
+}

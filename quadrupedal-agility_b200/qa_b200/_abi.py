@@ -177,6 +177,15 @@ class QaDepthArgs(C.Structure):
                 ("depth_buffer", vp)]
 
 
+class QaPpoLossTscArgs(C.Structure):
+    _fields_ = [("M", C.c_int64), ("logits", vp), ("logits_pitch", C.c_int64), ("mu", vp), ("mu_pitch", C.c_int64),
+                ("std", vp), ("value", vp), ("value_pitch", C.c_int64), ("actions", vp), ("actions_pitch", C.c_int64),
+                ("old_logp_d", vp), ("old_logp_c", vp), ("advantages", vp), ("returns", vp), ("target_values", vp),
+                ("old_mu", vp), ("old_sigma", vp), ("clip", C.c_float), ("c_value", C.c_float), ("c_entropy", C.c_float),
+                ("use_clipped_value_loss", C.c_int32), ("dlogits", vp), ("dlogits_pitch", C.c_int64), ("dmu", vp),
+                ("dmu_pitch", C.c_int64), ("dvalue", vp), ("dstd", vp), ("stats", vp)]
+
+
 # every symbol `include/qa_b200.h` declares: name -> (restype, argtypes)
 SYMBOLS = {
     "qa_version": (C.c_int, []),
@@ -199,11 +208,12 @@ SYMBOLS = {
     "qa_row_loss": (C.c_int, [C.POINTER(QaRowLossArgs), vp]),
     "qa_ppo_scalars": (C.c_int, [C.POINTER(QaPpoScalarsArgs), vp]),
     "qa_depth_update": (C.c_int, [C.POINTER(QaDepthArgs), vp]),
+    "qa_ppo_loss_tsc": (C.c_int, [C.POINTER(QaPpoLossTscArgs), vp]),
 }
 
 STRUCT_ORDER = [QaActionPushArgs, QaTorqueArgs, QaTerrain, QaHeightScanArgs, QaMocapTable, QaMocapBlendArgs,
                 QaBbcConst, QaBbcStepArgs, QaCompactArgs, QaGaeArgs, QaGatherArgs, QaClipAdamArgs, QaLinearArgs, QaActBwdArgs, QaPpoLossArgs, QaLinearBwdArgs, QaHistEncArgs,
-                QaRowLossArgs, QaPpoScalarsArgs, QaDepthArgs]
+                QaRowLossArgs, QaPpoScalarsArgs, QaDepthArgs, QaPpoLossTscArgs]
 
 _LIB = None
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libqa_b200.so")

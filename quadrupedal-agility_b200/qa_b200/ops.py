@@ -417,3 +417,27 @@ def depth_update(image_ptrs, images, episode_length_buf, depth_buffer, in_h, in_
     a.depth_buffer = _p(depth_buffer, f, "depth_buffer")
     _abi.check(lib.qa_depth_update(C.byref(a), _stream()), "qa_depth_update")
     _count(1)
+
+
+# ---- K15 ----------------------------------------------------------------------------------------
+def ppo_loss_tsc(logits, mu, std, value, actions, old_logp_d, old_logp_c, advantages, returns, target_values, old_mu,
+                 old_sigma, dlogits, dmu, dvalue, dstd, stats, clip, c_value, c_entropy, clipped_value) -> None:
+    """TSC PPO loss terms + gradients w.r.t. (logits, mu, value, std) in one launch (tsc ppo.py:176-262)."""
+    lib = _abi.load()
+    f = torch.float32
+    a = _abi.QaPpoLossTscArgs()
+    a.M = mu.shape[0]
+    a.logits, a.logits_pitch = _p_strided(logits, f, "logits"), logits.stride(0)
+    a.mu, a.mu_pitch = _p_strided(mu, f, "mu"), mu.stride(0)
+    a.std = _p(std, f, "std")
+    a.value, a.value_pitch = value.data_ptr(), value.stride(0)
+    a.actions, a.actions_pitch = _p_strided(actions, f, "actions"), actions.stride(0)
+    a.old_logp_d, a.old_logp_c = _p(old_logp_d, f, "old_logp_d"), _p(old_logp_c, f, "old_logp_c")
+    a.advantages, a.returns, a.target_values = _p(advantages, f, "advantages"), _p(returns, f, "returns"), _p(target_values, f, "target_values")
+    a.old_mu, a.old_sigma = _p(old_mu, f, "old_mu"), _p(old_sigma, f, "old_sigma")
+    a.clip, a.c_value, a.c_entropy, a.use_clipped_value_loss = float(clip), float(c_value), float(c_entropy), int(bool(clipped_value))
+    a.dlogits, a.dlogits_pitch = _p_strided(dlogits, f, "dlogits"), dlogits.stride(0)
+    a.dmu, a.dmu_pitch = _p_strided(dmu, f, "dmu"), dmu.stride(0)
+    a.dvalue, a.dstd, a.stats = _p(dvalue, f, "dvalue"), _p(dstd, f, "dstd"), _p(stats, f, "stats")
+    _abi.check(lib.qa_ppo_loss_tsc(C.byref(a), _stream()), "qa_ppo_loss_tsc")
+    _count(1)

@@ -4,3 +4,4 @@ from .modules import ActorCritic, Estimator, Discriminator, StateHistoryEncoder 
 from .storage import RolloutStorage  # noqa: F401
 from .utils import Normalizer, RunningMeanStd  # noqa: F401
 from .algorithm import SSInfoGAIL  # noqa: F401
+from .tsc import Actor, ActorCriticTSC, RolloutStorageTSC, PPO  # noqa: F401

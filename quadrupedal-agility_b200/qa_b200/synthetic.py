@@ -258,6 +258,35 @@ def _make_sd(shapes, gen):
     return sd
 
 
+# TSC teacher (tsc/rsl_rl/modules/actor_critic.py:60-225 ActorCriticTSC with the go2 agility config): obs 800 =
+# [prop 65 | scan 132 | priv explicit 4 | priv latent 29 | history 570]; actions = 1 mode index + 3 x 6 continuous
+TSC_AC_SHAPES = [("std", (18,)),
+                 ("actor.priv_encoder.0.weight", (64, 29)), ("actor.priv_encoder.0.bias", (64,)),
+                 ("actor.priv_encoder.2.weight", (29, 64)), ("actor.priv_encoder.2.bias", (29,)),
+                 ("actor.history_encoder.encoder.0.weight", (30, 57)), ("actor.history_encoder.encoder.0.bias", (30,)),
+                 ("actor.history_encoder.conv_layers.0.weight", (20, 30, 4)), ("actor.history_encoder.conv_layers.0.bias", (20,)),
+                 ("actor.history_encoder.conv_layers.2.weight", (10, 20, 2)), ("actor.history_encoder.conv_layers.2.bias", (10,)),
+                 ("actor.history_encoder.linear_output.0.weight", (29, 30)), ("actor.history_encoder.linear_output.0.bias", (29,)),
+                 ("actor.scan_encoder.0.weight", (128, 132)), ("actor.scan_encoder.0.bias", (128,)),
+                 ("actor.scan_encoder.2.weight", (64, 128)), ("actor.scan_encoder.2.bias", (64,)),
+                 ("actor.scan_encoder.4.weight", (32, 64)), ("actor.scan_encoder.4.bias", (32,)),
+                 ("actor.actor_trunk.0.weight", (512, 130)), ("actor.actor_trunk.0.bias", (512,)),
+                 ("actor.actor_trunk.2.weight", (256, 512)), ("actor.actor_trunk.2.bias", (256,)),
+                 ("actor.actor_trunk.4.weight", (128, 256)), ("actor.actor_trunk.4.bias", (128,)),
+                 ("actor.actor_d.weight", (3, 128)), ("actor.actor_d.bias", (3,)),
+                 ("actor.actor_c.weight", (18, 128)), ("actor.actor_c.bias", (18,)),
+                 ("critic.0.weight", (512, 800)), ("critic.0.bias", (512,)),
+                 ("critic.2.weight", (256, 512)), ("critic.2.bias", (256,)),
+                 ("critic.4.weight", (128, 256)), ("critic.4.bias", (128,)),
+                 ("critic.6.weight", (1, 128)), ("critic.6.bias", (1,))]
+
+
+def make_tsc_weights(seed: int = 0):
+    """Returns dict(ac=ActorCriticTSC state_dict, est=Estimator(57 -> [128, 64] -> 4) state_dict)."""
+    gen = torch.Generator().manual_seed(seed * 7919 + 5)
+    return dict(ac=_make_sd(TSC_AC_SHAPES, gen), est=_make_sd(EST_SHAPES, gen))
+
+
 def make_weights(seed: int = 0):
     """Returns dict(ac=..., est=..., disc=..., norm_mean (98,) f64, norm_var (98,) f64)."""
     gen = torch.Generator().manual_seed(seed * 31337 + 11)
