@@ -67,6 +67,136 @@ def depth_case(ref, N, seed):
     return dict(images=images, ep=ep, buf0=buf0, u1=u1, u2=u2, up=up, want=want)
 
 
+class _FakeSimGym:
+    """The gym calls post_physics_step / reset_idx make (:231-234, :381-384, :835-900).  `simulate` is a no-op; the
+    rigid-body refresh that follows it inside reset_idx swaps in the recorded post-reset snapshot."""
+
+    def __init__(self, env, rigid_post):
+        self.env, self.rigid_post, self.rb_refreshes, self.set_calls = env, rigid_post, 0, []
+
+    def refresh_actor_root_state_tensor(self, sim): pass
+    def refresh_net_contact_force_tensor(self, sim): pass
+    def refresh_force_sensor_tensor(self, sim): pass
+    def simulate(self, sim): pass
+    def fetch_results(self, sim, flag): pass
+
+    def refresh_rigid_body_state_tensor(self, sim):
+        self.rb_refreshes += 1
+        if self.rb_refreshes == 2:
+            self.env.rigid_body_states.copy_(self.rigid_post)
+
+    def set_dof_state_tensor_indexed(self, sim, t, ids, n):
+        self.set_calls.append(("dof", ids.clone()))
+
+    def set_actor_root_state_tensor_indexed(self, sim, t, ids, n):
+        self.set_calls.append(("root", ids.clone()))
+
+
+def env_case(ref, N, seed):
+    """One full TSC post_physics_step of the UNMODIFIED reference on injected synthetic state vs oracle/tsc_env.py."""
+    import importlib
+    import tsc_env as OE
+    from qa_b200 import synthetic
+    cfgmod = importlib.import_module("legged_gym.envs.go2.go2_agility_config")
+    rcfg = cfgmod.Go2AgilityCfg()
+    st = synthetic.make_tsc_static(N, seed)
+    sn = synthetic.make_tsc_snapshot(N, st, seed)
+    dr = synthetic.make_tsc_draws(N, seed)
+    cfg = OE.TscCfg(num_envs=N)
+    LR = ref.LeggedRobot
+    env = LR.__new__(LR)
+    env.cfg, env.sim_params, env.device, env.num_envs = rcfg, types.SimpleNamespace(dt=0.005), "cpu", N
+    env._parse_cfg(rcfg)
+    assert abs(env.dt - cfg.dt) < 1e-12 and float(env.max_episode_length) == cfg.max_episode_length
+    env._prepare_reward_function()
+    assert env.reward_names == cfg.reward_names, (env.reward_names, cfg.reward_names)
+    for k in cfg.reward_scales:
+        assert abs(env.reward_scales[k] - cfg.reward_scales[k] * cfg.dt) < 1e-12, k
+    c = lambda t: t.clone()                                                   # noqa: E731
+    env.sim, env.viewer, env.enable_viewer_sync, env.debug_viz, env.extras = None, None, False, False, {}
+    env.obstacle = types.SimpleNamespace(cfg=rcfg.obstacle, last_goal_repeat=2, num_goals=4, proportions=[0.2, 0.15, 0.2, 0.15, 0.2, 0.1],
+                                         frame_ang=[cfg.frame_ang0] * 6, seesaw_dof_pos=cfg.seesaw_dof_pos, num_envs=N)
+    env.terrain, env.custom_origins = None, True
+    env.root_states, env.dof_state = c(sn["root_states"]), c(sn["dof_state"])
+    env.dof_pos = env.dof_state.view(N, 12, 2)[..., 0]
+    env.dof_vel = env.dof_state.view(N, 12, 2)[..., 1]
+    env.num_dof = 12
+    env.base_quat = env.root_states[:, 3:7]
+    env.rigid_body_states = c(sn["rigid_body_state"])
+    env.rigid_body_pos = env.rigid_body_states[..., 0:3]
+    env.contact_forces = c(sn["contact_forces"])
+    env.obst_dof_state = c(sn["obst_dof_state"])
+    env.obst_dof_pos, env.obst_dof_vel = env.obst_dof_state[:, 0:1], env.obst_dof_state[:, 1:2]
+    env.obst_root_states, env.border_root_states = torch.zeros(6 * N, 13), torch.zeros(N, 13)
+    for k in ("feet_indices", "key_body_ids", "penalised_contact_indices", "termination_contact_indices", "height_samples",
+              "x_edge_mask", "height_points", "env_goals", "obstacle_types", "gravity_vec", "motor_strength"):
+        setattr(env, k, c(st[k]))
+    env.num_height_points = st["height_points"].shape[1]
+    env.default_dof_pos, env.default_dof_pos_all = c(st["default_dof_pos"]), st["default_dof_pos"].repeat(N, 1)
+    env.mass_params_tensor, env.friction_coeffs_tensor = c(st["mass_params"]), c(st["friction_coeffs"])
+    env.base_init_state = torch.tensor(cfg.base_init_state)
+    for k in ("episode_length_buf", "last_root_vel", "last_contacts", "reach_goal_timer", "cur_goal_idx", "cur_goals",
+              "next_goals", "actions", "last_actions", "torques_org", "last_torques_org", "last_dof_vel", "measured_heights",
+              "delta_yaw", "delta_next_yaw", "commands", "latent_eps", "latent_c", "obs_history_buf", "contact_buf",
+              "action_history_buf", "action_hl_history_buf", "feet_air_time", "obs_disc_buf"):
+        setattr(env, k, c(sn[k]))
+    env.common_step_counter, env.global_counter = sn["common_step_counter"], sn["global_counter"]
+    env.episode_sums = {name: c(sn["episode_sums"][:, i]) for i, name in enumerate(cfg.reward_names + ["termination"])}
+    env.base_lin_vel, env.base_ang_vel, env.projected_gravity = torch.zeros(N, 3), torch.zeros(N, 3), torch.zeros(N, 3)
+    env.rew_buf, env.reset_buf = torch.zeros(N), torch.ones(N, dtype=torch.long)
+    env.time_out_buf = torch.zeros(N, dtype=torch.bool)
+    env.gym = _FakeSimGym(env, sn["rigid_body_state_post"])
+    # random sources of _reset_root_states (:860-880): three torch_rand_float calls, in order yaw, x, y
+    lrmod = ref.legged_robot
+    calls = []
+    real = lrmod.torch_rand_float
+
+    def fake_rand_float(lower, upper, shape, device):
+        key = ("yaw_u", "x_u", "y_u")[len(calls)]
+        calls.append(key)
+        ids = env.reset_buf.nonzero(as_tuple=False).flatten()
+        assert shape == (len(ids), 1)
+        return ((upper - lower) * dr[key][ids] + lower).view(-1, 1)
+
+    lrmod.torch_rand_float = fake_rand_float
+    try:
+        env_ids, term = env.post_physics_step()                               # the reference's own code
+    finally:
+        lrmod.torch_rand_float = real
+    assert calls == ["yaw_u", "x_u", "y_u"], calls
+    assert env.gym.rb_refreshes == 2 and [k for k, _ in env.gym.set_calls] == ["dof", "root"]
+    pre = OE.post_physics_pre(cfg, st, sn, dr)
+    out = OE.post_physics_post(cfg, st, pre, sn["rigid_body_state_post"])
+    ref_out = dict(obs_buf=env.obs_buf, obs_bbc_buf=env.obs_bbc_buf, obs_disc_buf=env.obs_disc_buf, rew_buf=env.rew_buf,
+                   reset_buf=env.reset_buf, time_out_buf=env.time_out_buf, reset_env_ids=env_ids, terminal_disc_states=term,
+                   root_states=env.root_states, dof_state=env.dof_state, obst_dof_state=env.obst_dof_state,
+                   episode_length_buf=env.episode_length_buf, cur_goal_idx=env.cur_goal_idx, cur_goals=env.cur_goals,
+                   next_goals=env.next_goals, reach_goal_timer=env.reach_goal_timer, measured_heights=env.measured_heights,
+                   obs_history_buf=env.obs_history_buf, contact_buf=env.contact_buf, action_history_buf=env.action_history_buf,
+                   last_actions=env.last_actions, last_dof_vel=env.last_dof_vel, last_torques_org=env.last_torques_org,
+                   last_root_vel=env.last_root_vel, last_contacts=env.last_contacts, contact_filt=env.contact_filt,
+                   feet_air_time=env.feet_air_time, delta_yaw=env.delta_yaw, delta_next_yaw=env.delta_next_yaw,
+                   base_lin_vel=env.base_lin_vel, base_ang_vel=env.base_ang_vel, projected_gravity=env.projected_gravity,
+                   roll=env.roll, pitch=env.pitch, yaw=env.yaw, target_yaw=env.target_yaw, next_target_yaw=env.next_target_yaw,
+                   cur_obstacle_types=env.cur_obstacle_types, reach_goal=env.extras["reach_goal"],
+                   feet_at_edge=env.feet_at_edge, time_outs_latched=env.extras["time_outs"],
+                   episode_sums=torch.stack([env.episode_sums[k] for k in cfg.reward_names + ["termination"]], dim=1),
+                   episode_rew_means=torch.stack([env.extras["episode"]["rew_" + k] for k in cfg.reward_names + ["termination"]]))
+    worst = 0.0
+    for k, rv in ref_out.items():
+        ov = out[k]
+        assert ov.shape == rv.shape, (k, ov.shape, rv.shape)
+        if rv.dtype in (torch.bool, torch.int64, torch.int32, torch.uint8, torch.int16):
+            assert torch.equal(ov.to(torch.int64), rv.to(torch.int64)), f"{k}: oracle != reference"
+        else:
+            assert torch.equal(ov, rv), f"{k}: oracle != reference (max err {(ov - rv).abs().max()})"
+    n_reset = len(env_ids)
+    print(f"  env: N={N}: oracle == reference post_physics_step on {len(ref_out)} buffers (bit-exact); resets={n_reset}, "
+          f"time_outs={int(env.time_out_buf.sum())}, reached={int(env.reached_goal_ids.sum())}, leave={int(env.leave_goal_ids.sum())}")
+    assert n_reset >= 6
+    return st, sn, dr, ref_out
+
+
 STRIDE = 97
 
 
@@ -184,6 +314,13 @@ def main():
     print("wrote tests/golden/tsc_depth_n6.npz")
     np.savez_compressed(os.path.join(GOLD, "tsc_trainer_seed3.npz"), **trainer_case(ref))
     print("wrote tests/golden/tsc_trainer_seed3.npz")
+    env_case(ref, 512, seed=2)                                           # wider coverage, not stored
+    st, sn, dr, ref_out = env_case(ref, 64, seed=1)
+    # static / snapshot / draws are regenerated from the seed by the tests (qa_b200.synthetic); only the reference's
+    # outputs are stored
+    np.savez_compressed(os.path.join(GOLD, "tsc_env_n64.npz"), seed=np.array(1), num_envs=np.array(64),
+                        **{"ref." + k: v.numpy() for k, v in ref_out.items()})
+    print("wrote tests/golden/tsc_env_n64.npz")
 
 
 if __name__ == "__main__":

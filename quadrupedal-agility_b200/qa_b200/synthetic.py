@@ -293,3 +293,161 @@ def make_weights(seed: int = 0):
     return dict(ac=_make_sd(AC_SHAPES, gen), est=_make_sd(EST_SHAPES, gen), disc=_make_sd(DISC_SHAPES, gen),
                 norm_mean=0.2 * torch.randn(98, generator=gen, dtype=torch.float64),
                 norm_var=0.2 + torch.rand(98, generator=gen, dtype=torch.float64))
+
+
+# ------------------------------------------------------------------------------------------
+# TSC (agility teacher) synthetic state: obstacle course goals, obstacle types, 132-point height scan, edge mask.
+# Same role as make_static / make_snapshot above for the BBC env; distributions chosen so that every branch of
+# tsc/legged_gym/envs/base/legged_robot.py:204-515 is exercised at N >= 64 (goal reached / left, all six termination
+# causes, both tracking_goal_vel targets, history fill and shift).
+# ------------------------------------------------------------------------------------------
+TSC_NUM_BODIES = 17
+TSC_FEET = [4, 8, 12, 16]
+TSC_PENALISED = [0, 1, 2, 3, 5, 6, 7, 9, 10, 11, 13, 14, 15]
+TSC_TERMINATION = [0, 1, 2, 5, 6, 9, 10, 13, 14]
+TSC_NUM_GOALS_TOTAL = 6 * 4 + 2
+
+
+def make_tsc_static(num_envs: int, seed: int = 0, rows: int = 640, cols: int = 960):
+    g = torch.Generator().manual_seed(seed * 104729 + 3)
+    N = num_envs
+    st = {}
+    st["height_samples"] = torch.randint(-20, 120, (rows, cols), generator=g, dtype=torch.int16)
+    st["x_edge_mask"] = torch.rand(rows, cols, generator=g) < 0.25
+    x = torch.tensor([0.0, 0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 0.9, 1.0, 1.1])
+    y = torch.tensor([-0.5, -0.4, -0.3, -0.2, -0.1, 0., 0.1, 0.2, 0.3, 0.4, 0.5])
+    gx, gy = torch.meshgrid(x, y, indexing="ij")
+    pts = torch.zeros(N, gx.numel(), 3)
+    pts[:, :, 0], pts[:, :, 1] = gx.flatten(), gy.flatten()
+    st["height_points"] = pts
+    # goals: a course of 24 way points inside the 22 m x 38 m terrain (border 5 m), + the last goal repeated twice
+    start = torch.stack([2.0 + 16.0 * torch.rand(N, generator=g), 2.0 + 30.0 * torch.rand(N, generator=g)], dim=1)
+    steps = torch.cat([0.9 * torch.rand(N, 24, 1, generator=g) - 0.2, 0.8 * torch.rand(N, 24, 1, generator=g) - 0.4], dim=2)
+    xy = start[:, None, :] + torch.cumsum(steps, dim=1)
+    goals = torch.cat([xy, 0.1 * torch.rand(N, 24, 1, generator=g)], dim=2)
+    reps = []
+    for k in range(2):
+        last = goals[:, -1:, :].clone()
+        last[:, :, 1] += 0.1 * (k + 1)
+        reps.append(last)
+    st["env_goals"] = torch.cat([goals] + reps, dim=1)
+    st["obstacle_types"] = torch.stack([torch.randperm(6, generator=g) for _ in range(N)])
+    flat = st["obstacle_types"].flatten()
+    has_dof = (flat == 0) | (flat == 3) | (flat == 4)
+    st["seesaw_dof_index"] = (flat[has_dof] == 3).nonzero(as_tuple=False).flatten()
+    st["feet_indices"] = torch.tensor(TSC_FEET)
+    st["key_body_ids"] = torch.tensor(TSC_FEET)
+    st["penalised_contact_indices"] = torch.tensor(TSC_PENALISED)
+    st["termination_contact_indices"] = torch.tensor(TSC_TERMINATION)
+    st["default_dof_pos"] = torch.tensor([[0.0, 0.9, -1.8] * 4])
+    st["p_gains"], st["d_gains"] = torch.full((12,), 40.0), torch.full((12,), 1.0)
+    st["torque_limits"] = torch.tensor([23.7, 23.7, 45.43] * 4)
+    st["gravity_vec"] = torch.tensor([[0.0, 0.0, -1.0]]).repeat(N, 1)
+    st["mass_params"] = torch.cat([1.5 * torch.rand(N, 1, generator=g), 0.2 * torch.rand(N, 3, generator=g) - 0.1], dim=1)
+    st["friction_coeffs"] = 0.6 + 1.4 * torch.rand(N, 1, generator=g)
+    st["motor_strength"] = 0.8 + 0.4 * torch.rand(2, N, 12, generator=g)
+    return st
+
+
+def make_tsc_snapshot(num_envs: int, static, seed: int = 0, step: int = 0):
+    g = torch.Generator().manual_seed(seed * 15485863 + step * 7 + 1)
+    N, B = num_envs, TSC_NUM_BODIES
+    r = lambda *s: torch.rand(*s, generator=g)                               # noqa: E731
+    n = lambda *s: torch.randn(*s, generator=g)                              # noqa: E731
+    s = {}
+    cur = torch.randint(0, 24, (N,), generator=g)
+    cur[r(N) < 0.04] = 24                                                   # reach_goal_cutoff (>= G - last_goal_repeat)
+    plant = N >= 16                                                          # one env per termination cause, always
+    if plant:
+        cur[5] = 24
+    s["cur_goal_idx"] = cur
+    goals = static["env_goals"]
+    gi = cur[:, None, None]
+    s["cur_goals"] = goals.gather(1, gi.expand(-1, -1, 3)).squeeze(1)
+    s["next_goals"] = goals.gather(1, (gi + 1).expand(-1, -1, 3)).squeeze(1)
+    # root: mostly 0.2 .. 2 m from the current goal, 20 % inside the 0.4 m goal radius, 2 % further than 4 m
+    dist = 0.2 + 1.8 * r(N)
+    u = r(N)
+    dist = torch.where(u < 0.2, 0.35 * r(N), dist)
+    dist = torch.where(u > 0.98, 4.2 + r(N), dist)
+    if plant:
+        dist[1] = 4.5
+    ang = 2 * math.pi * r(N)
+    root = torch.zeros(N, 13)
+    root[:, 0] = s["cur_goals"][:, 0] - dist * torch.cos(ang)
+    root[:, 1] = s["cur_goals"][:, 1] - dist * torch.sin(ang)
+    root[:, 2] = 0.22 + 0.3 * r(N)
+    root[r(N) < 0.02, 2] = -0.3
+    if plant:
+        root[2, 2] = -0.3
+    yaw = ang + 0.5 * n(N)
+    roll, pitch = 0.15 * n(N), 0.15 * n(N)
+    roll[r(N) < 0.015] = 1.6
+    pitch[r(N) < 0.015] = -1.55
+    if plant:
+        roll[3], pitch[4] = 1.6, -1.55
+    cy, sy, cr, sr, cp, sp = (torch.cos(yaw / 2), torch.sin(yaw / 2), torch.cos(roll / 2), torch.sin(roll / 2),
+                              torch.cos(pitch / 2), torch.sin(pitch / 2))
+    q = torch.stack([cy * sr * cp - sy * cr * sp, cy * cr * sp + sy * sr * cp, sy * cr * cp - cy * sr * sp,
+                     cy * cr * cp + sy * sr * sp], dim=1)
+    root[:, 3:7] = q / q.norm(dim=1, keepdim=True)
+    root[:, 7:10] = 0.8 * n(N, 3)
+    root[:, 7] += 1.0 * torch.cos(ang)
+    root[:, 8] += 1.0 * torch.sin(ang)
+    root[:, 10:13] = 0.8 * n(N, 3)
+    s["root_states"] = root
+    dof = torch.zeros(N, 12, 2)
+    dof[:, :, 0] = static["default_dof_pos"] + 0.25 * n(N, 12)
+    dof[:, :, 1] = 3.0 * n(N, 12)
+    s["dof_state"] = dof.reshape(N * 12, 2)
+    rb = torch.zeros(N, B, 13)
+    rb[:, :, 0:3] = root[:, None, 0:3] + 0.2 * n(N, B, 3)
+    rb[:, :, 2] = rb[:, :, 2].clamp(min=0.0)
+    s["rigid_body_state"] = rb
+    post = rb.clone()
+    post[:, :, 0:3] += 0.05 * n(N, B, 3)                                    # what the physics step inside reset_idx leaves
+    s["rigid_body_state_post"] = post
+    cf = torch.zeros(N, B, 3)
+    feet = static["feet_indices"]
+    fz = torch.relu(40 + 40 * n(N, 4)) * (r(N, 4) < 0.5)
+    cf[:, feet, 2] = fz
+    cf[:, feet, 0:2] = 5 * n(N, 4, 2) * (fz > 0).unsqueeze(-1)
+    hit = r(N, B) < 0.01
+    hit[:, feet] = False
+    mag = 1 + 49 * r(N, B)
+    d = n(N, B, 3)
+    cf = torch.where(hit.unsqueeze(-1), d / d.norm(dim=-1, keepdim=True) * mag.unsqueeze(-1), cf)
+    s["contact_forces"] = cf
+    ep = torch.randint(0, 2000, (N,), generator=g)
+    ep[r(N) < 0.01] = 2000
+    ep[r(N) < 0.03] = 0
+    if plant:
+        ep[6], ep[7] = 2000, 0
+    s["episode_length_buf"] = ep
+    s["common_step_counter"], s["global_counter"] = 100 + step, 100 + step
+    s["last_root_vel"] = root[:, 7:13] + 0.1 * n(N, 6)
+    s["last_contacts"] = r(N, 4) < 0.4
+    s["reach_goal_timer"] = torch.randint(0, 3, (N,), generator=g).float()
+    s["actions"], s["last_actions"] = n(N, 12), n(N, 12)
+    s["torques_org"], s["last_torques_org"] = 8 * n(N, 12), 8 * n(N, 12)
+    s["last_dof_vel"] = dof[:, :, 1] + 0.5 * n(N, 12)
+    s["measured_heights"] = 0.3 * r(N, 132)
+    s["delta_yaw"], s["delta_next_yaw"] = n(N), n(N)
+    c_idx = torch.randint(0, 5, (N,), generator=g)
+    s["latent_c"] = torch.nn.functional.one_hot(c_idx, 5).float()
+    s["latent_eps"] = 2 * r(N, 1) - 1
+    s["commands"] = torch.cat([2 * r(N, 1), 0.6 * r(N, 1) - 0.3, 2 * r(N, 1) - 1, 0.5 * r(N, 2)], dim=1)
+    s["obs_history_buf"] = 0.5 * n(N, 10, 57)
+    s["contact_buf"] = (r(N, 100, 4) < 0.5).float()
+    s["action_history_buf"] = n(N, 8, 12)
+    s["action_hl_history_buf"] = torch.cat([torch.randint(0, 3, (N, 8, 1), generator=g).float(), n(N, 8, 18)], dim=2)
+    s["episode_sums"] = 0.3 * n(N, 8)
+    s["feet_air_time"] = r(N, 4)
+    s["obs_disc_buf"] = n(N, 49)
+    s["obst_dof_state"] = 0.2 * n(3 * N, 2)
+    return s
+
+
+def make_tsc_draws(num_envs: int, seed: int = 0, step: int = 0):
+    g = torch.Generator().manual_seed(seed * 32452843 + step * 11 + 2)
+    return {k: torch.rand(num_envs, generator=g) for k in ("yaw_u", "x_u", "y_u")}
