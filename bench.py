@@ -215,7 +215,13 @@ def run_ours(args):
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Leave without tearing NCCL down: destroy_process_group() blocks for minutes while CUDA graphs that captured
+        # collectives are still alive (seen on 2 x B200: the JSON line was out, the ranks never exited).
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def cpu_reference_sample(n_envs, rollout_steps, minibatch_steps, threads):

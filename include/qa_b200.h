@@ -51,7 +51,7 @@ int qa_version(void);
 /* human readable build string ("sm_100a, nvcc 12.9, ...") */
 const char* qa_build_info(void);
 /* sizeof() of argument struct number `which` (order of declaration in this header, QaActionPushArgs
- * = 0 ... QaGaeArgs = 9, QaGatherArgs = 10, QaClipAdamArgs = 11, QaLinearArgs = 12, QaActBwdArgs = 13, QaPpoLossArgs = 14, QaLinearBwdArgs = 15, QaHistEncArgs = 16, QaRowLossArgs = 17, QaPpoScalarsArgs = 18, QaDepthArgs = 19, QaPpoLossTscArgs = 20; -1 if unknown): a layout handshake for FFI mirrors of these structs */
+ * = 0 ... QaGaeArgs = 9, QaGatherArgs = 10, QaClipAdamArgs = 11, QaLinearArgs = 12, QaActBwdArgs = 13, QaPpoLossArgs = 14, QaLinearBwdArgs = 15, QaHistEncArgs = 16, QaRowLossArgs = 17, QaPpoScalarsArgs = 18, QaDepthArgs = 19, QaPpoLossTscArgs = 20, QaTscConst = 21, QaTscStepArgs = 22; -1 if unknown): a layout handshake for FFI mirrors of these structs */
 int qa_struct_size(int which);
 
 /* ------------------------------------------------------------------------------------------
@@ -570,6 +570,112 @@ typedef struct QaPpoLossTscArgs {
     float* stats;                                /* (4) */
 } QaPpoLossTscArgs;
 int qa_ppo_loss_tsc(const QaPpoLossTscArgs* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K16 / K17  TSC (agility) post-physics step -- replaces LeggedRobot.post_physics_step,
+ *     tsc/legged_gym/envs/base/legged_robot.py:226-298, split where the reference steps physics inside reset_idx
+ *     (:381-384), so reward/termination and the observations cannot be one kernel:
+ *
+ *     qa_post_physics_tsc_pre   :236-270 + the simulator-state half of reset_idx: counters, base-frame quantities, euler
+ *         angles, foot contacts, _update_goals (:204-224), the 132-point height scan (:1708-1755), current obstacle type,
+ *         check_termination (:322-346), the active reward terms (reach_goal, tracking_goal_vel, tracking_yaw, collision,
+ *         action_hl_rate, latent_c_rate, feet_edge, termination; :1779-1930), episode sums, and for envs that reset:
+ *         cur_goal_idx = 0, _reset_dofs (:798-838), _reset_root_states (:840-900), episode statistics (:398-405),
+ *         episode_length_buf = reach_goal_timer = 0.  The LAST block finalises: episode reward means, time-out latch
+ *         (:408-410), reset count, obst_dof_vel[:] = 0 flag.
+ *     -- caller: gym.set_*_tensor_indexed(reset ids), gym.simulate, refresh_rigid_body_state_tensor --
+ *     qa_post_physics_tsc_post  the buffer half of reset_idx (:386-396), cur/next goal gathers (:271-272),
+ *         compute_observations (:432-515: obs 800, obs_bbc 671, obs_disc 49, history fill/shift, contact ring, clip),
+ *         last_* copies (:278-281).
+ *     Random sources of the reset (yaw / x / y): dense uniforms (parity) or in-kernel Philox4x32-10.
+ * ------------------------------------------------------------------------------------------ */
+#define QA_TSC_NUM_REWARDS 8            /* 7 terms in dir() order + termination */
+#define QA_TSC_OBS 800
+#define QA_TSC_SCAN 132
+#define QA_TSC_AUX 8
+typedef struct QaTscConst {
+    int32_t num_bodies;
+    int32_t feet_indices[4];
+    uint32_t termination_body_mask, penalised_body_mask;
+    float dt, max_episode_length, episode_length_s;
+    float next_goal_threshold, leave_goal_threshold, reach_goal_delay_steps;   /* reach_goal_delay / dt */
+    int32_t num_goals_total, num_goals_per_obstacle, last_goal_repeat, num_obstacle_types;
+    int32_t update_interval, use_camera, root_height_obs, only_positive_rewards;
+    float target_lin_vel;
+    float reward_scale[QA_TSC_NUM_REWARDS];   /* already multiplied by dt; order: action_hl_rate, collision, feet_edge,
+                                                 latent_c_rate, reach_goal, tracking_goal_vel, tracking_yaw, termination */
+    float default_dof_pos[12];
+    float base_init_state[13];
+    float rand_yaw_range, rand_x_range, rand_y_range, frame_ang0, seesaw_dof_pos;
+    float s_lin_vel, s_ang_vel, s_dof_pos, s_dof_vel, s_key_pos, s_foot_contact, s_lin_vel_dist, s_ang_vel_dist, clip_obs;
+    int32_t num_height_points;                /* 132 */
+    int32_t hl_hist_len, hl_action_dim;       /* action_hl_history_buf (N, hl_hist_len, hl_action_dim); 0 = None */
+    int32_t contact_ring_len;                 /* 100 */
+} QaTscConst;
+
+typedef struct QaTscStepArgs {
+    int32_t num_envs;
+    int64_t global_counter;             /* value DURING this step (after step()'s increment) */
+    /* simulator tensors (IsaacGym layouts) */
+    float* root_states;                 /* (N,13) in/out */
+    float* dof_state;                   /* (N,12,2) in/out */
+    const float* rigid_body_state;      /* (N,B,13): pre kernel = before the reset step, post kernel = refreshed */
+    const float* contact_forces;        /* (N,B,3) */
+    float* obst_dof_state;              /* (num_obst_dofs,2) in/out */
+    const int64_t* seesaw_dof_index;    /* (N) row of env e's seesaw in obst_dof_state */
+    int64_t num_obst_dofs;
+    /* static */
+    QaTerrain terrain;                  /* obstacle height field */
+    const uint8_t* x_edge_mask;         /* (rows, cols) bool */
+    const float* height_points;         /* (N,P,3) */
+    const float* env_goals;             /* (N,G,3) */
+    const int64_t* obstacle_types;      /* (N, num_obstacle_types) */
+    const float* mass_params;           /* (N,4) */
+    const float* friction_coeffs;       /* (N,1) */
+    const float* motor_strength;        /* (2,N,12) */
+    /* carried buffers */
+    int64_t* episode_length_buf;        /* (N) */
+    const float* last_root_vel_in;      /* (N,6) read by the pre kernel (base_lin_acc) */
+    uint8_t* last_contacts;             /* (N,4) */
+    float* reach_goal_timer;            /* (N) */
+    int64_t* cur_goal_idx;              /* (N) */
+    float* cur_goals;                   /* (N,3) */
+    float* next_goals;                  /* (N,3) */
+    const float* actions;               /* (N,12) */
+    const float* torques_org;           /* (N,12) */
+    float* last_actions; float* last_dof_vel; float* last_torques_org; float* last_root_vel;   /* (N,12|12|12|6) */
+    const float* commands;              /* (N,5) */
+    const float* latent_eps;            /* (N,1) */
+    const float* latent_c;              /* (N,5) */
+    const float* action_hl_history_buf; /* (N,H,A) or NULL */
+    float* episode_sums;                /* (N,QA_TSC_NUM_REWARDS) */
+    float* feet_air_time;               /* (N,4) */
+    float* obs_history_buf;             /* (N,10,57) */
+    float* action_history_buf;          /* (N,8,12) */
+    float* contact_buf;                 /* (N,L,4) ring, slot head = newest */
+    int32_t contact_ring_head;
+    float* measured_heights;            /* (N,P) */
+    float* delta_yaw; float* delta_next_yaw;            /* (N) */
+    /* per-step outputs */
+    float* base_lin_vel; float* base_ang_vel; float* projected_gravity; float* base_lin_acc; float* rpy;   /* (N,3) */
+    uint8_t* contact_filt;              /* (N,4) */
+    float* target_yaw; float* next_target_yaw;          /* (N) */
+    int64_t* cur_obstacle_types;        /* (N) */
+    uint8_t* reached_goal; uint8_t* reach_goal_cutoff; uint8_t* feet_at_edge;   /* (N) (N) (N,4) */
+    uint8_t* reset_buf; uint8_t* time_out_buf; uint8_t* time_outs_latched;      /* (N) */
+    float* rew_buf;                     /* (N) */
+    float* episode_rew_means;           /* (QA_TSC_NUM_REWARDS) written when >= 1 env reset */
+    int32_t* num_resets;                /* (1) */
+    void* workspace;                    /* >= 128 B, zero-initialised once */
+    float* obs_buf;                     /* (N,800) */
+    float* obs_bbc_buf;                 /* (N,671) */
+    float* obs_disc_buf;                /* (N,49) */
+    /* reset randomness */
+    const float* yaw_u; const float* x_u; const float* y_u;   /* (N) each, or all NULL */
+    uint64_t rng_seed, rng_step;
+} QaTscStepArgs;
+int qa_post_physics_tsc_pre(const QaTscConst* c, const QaTscStepArgs* a, void* stream);
+int qa_post_physics_tsc_post(const QaTscConst* c, const QaTscStepArgs* a, void* stream);
 
 #ifdef __cplusplus
 }

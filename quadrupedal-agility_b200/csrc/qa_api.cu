@@ -36,6 +36,8 @@ extern "C" int qa_struct_size(int which) {
         case 18: return (int)sizeof(QaPpoScalarsArgs);
         case 19: return (int)sizeof(QaDepthArgs);
         case 20: return (int)sizeof(QaPpoLossTscArgs);
+        case 21: return (int)sizeof(QaTscConst);
+        case 22: return (int)sizeof(QaTscStepArgs);
         default: return -1;
     }
 }

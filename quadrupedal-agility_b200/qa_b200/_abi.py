@@ -186,6 +186,46 @@ class QaPpoLossTscArgs(C.Structure):
                 ("dmu_pitch", C.c_int64), ("dvalue", vp), ("dstd", vp), ("stats", vp)]
 
 
+TSC_NUM_REWARDS = 8
+
+
+class QaTscConst(C.Structure):
+    _fields_ = [("num_bodies", C.c_int32), ("feet_indices", C.c_int32 * 4), ("termination_body_mask", C.c_uint32),
+                ("penalised_body_mask", C.c_uint32), ("dt", C.c_float), ("max_episode_length", C.c_float),
+                ("episode_length_s", C.c_float), ("next_goal_threshold", C.c_float), ("leave_goal_threshold", C.c_float),
+                ("reach_goal_delay_steps", C.c_float), ("num_goals_total", C.c_int32), ("num_goals_per_obstacle", C.c_int32),
+                ("last_goal_repeat", C.c_int32), ("num_obstacle_types", C.c_int32), ("update_interval", C.c_int32),
+                ("use_camera", C.c_int32), ("root_height_obs", C.c_int32), ("only_positive_rewards", C.c_int32),
+                ("target_lin_vel", C.c_float), ("reward_scale", C.c_float * TSC_NUM_REWARDS),
+                ("default_dof_pos", C.c_float * 12), ("base_init_state", C.c_float * 13), ("rand_yaw_range", C.c_float),
+                ("rand_x_range", C.c_float), ("rand_y_range", C.c_float), ("frame_ang0", C.c_float),
+                ("seesaw_dof_pos", C.c_float), ("s_lin_vel", C.c_float), ("s_ang_vel", C.c_float), ("s_dof_pos", C.c_float),
+                ("s_dof_vel", C.c_float), ("s_key_pos", C.c_float), ("s_foot_contact", C.c_float),
+                ("s_lin_vel_dist", C.c_float), ("s_ang_vel_dist", C.c_float), ("clip_obs", C.c_float),
+                ("num_height_points", C.c_int32), ("hl_hist_len", C.c_int32), ("hl_action_dim", C.c_int32),
+                ("contact_ring_len", C.c_int32)]
+
+
+class QaTscStepArgs(C.Structure):
+    _fields_ = [("num_envs", C.c_int32), ("global_counter", C.c_int64), ("root_states", vp), ("dof_state", vp),
+                ("rigid_body_state", vp), ("contact_forces", vp), ("obst_dof_state", vp), ("seesaw_dof_index", vp),
+                ("num_obst_dofs", C.c_int64), ("terrain", QaTerrain), ("x_edge_mask", vp), ("height_points", vp),
+                ("env_goals", vp), ("obstacle_types", vp), ("mass_params", vp), ("friction_coeffs", vp),
+                ("motor_strength", vp), ("episode_length_buf", vp), ("last_root_vel_in", vp), ("last_contacts", vp),
+                ("reach_goal_timer", vp), ("cur_goal_idx", vp), ("cur_goals", vp), ("next_goals", vp), ("actions", vp),
+                ("torques_org", vp), ("last_actions", vp), ("last_dof_vel", vp), ("last_torques_org", vp),
+                ("last_root_vel", vp), ("commands", vp), ("latent_eps", vp), ("latent_c", vp),
+                ("action_hl_history_buf", vp), ("episode_sums", vp), ("feet_air_time", vp), ("obs_history_buf", vp),
+                ("action_history_buf", vp), ("contact_buf", vp), ("contact_ring_head", C.c_int32), ("measured_heights", vp),
+                ("delta_yaw", vp), ("delta_next_yaw", vp), ("base_lin_vel", vp), ("base_ang_vel", vp),
+                ("projected_gravity", vp), ("base_lin_acc", vp), ("rpy", vp), ("contact_filt", vp), ("target_yaw", vp),
+                ("next_target_yaw", vp), ("cur_obstacle_types", vp), ("reached_goal", vp), ("reach_goal_cutoff", vp),
+                ("feet_at_edge", vp), ("reset_buf", vp), ("time_out_buf", vp), ("time_outs_latched", vp), ("rew_buf", vp),
+                ("episode_rew_means", vp), ("num_resets", vp), ("workspace", vp), ("obs_buf", vp), ("obs_bbc_buf", vp),
+                ("obs_disc_buf", vp), ("yaw_u", vp), ("x_u", vp), ("y_u", vp), ("rng_seed", C.c_uint64),
+                ("rng_step", C.c_uint64)]
+
+
 # every symbol `include/qa_b200.h` declares: name -> (restype, argtypes)
 SYMBOLS = {
     "qa_version": (C.c_int, []),
@@ -209,11 +249,13 @@ SYMBOLS = {
     "qa_ppo_scalars": (C.c_int, [C.POINTER(QaPpoScalarsArgs), vp]),
     "qa_depth_update": (C.c_int, [C.POINTER(QaDepthArgs), vp]),
     "qa_ppo_loss_tsc": (C.c_int, [C.POINTER(QaPpoLossTscArgs), vp]),
+    "qa_post_physics_tsc_pre": (C.c_int, [C.POINTER(QaTscConst), C.POINTER(QaTscStepArgs), vp]),
+    "qa_post_physics_tsc_post": (C.c_int, [C.POINTER(QaTscConst), C.POINTER(QaTscStepArgs), vp]),
 }
 
 STRUCT_ORDER = [QaActionPushArgs, QaTorqueArgs, QaTerrain, QaHeightScanArgs, QaMocapTable, QaMocapBlendArgs,
                 QaBbcConst, QaBbcStepArgs, QaCompactArgs, QaGaeArgs, QaGatherArgs, QaClipAdamArgs, QaLinearArgs, QaActBwdArgs, QaPpoLossArgs, QaLinearBwdArgs, QaHistEncArgs,
-                QaRowLossArgs, QaPpoScalarsArgs, QaDepthArgs, QaPpoLossTscArgs]
+                QaRowLossArgs, QaPpoScalarsArgs, QaDepthArgs, QaPpoLossTscArgs, QaTscConst, QaTscStepArgs]
 
 _LIB = None
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libqa_b200.so")

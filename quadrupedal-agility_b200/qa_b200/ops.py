@@ -441,3 +441,12 @@ def ppo_loss_tsc(logits, mu, std, value, actions, old_logp_d, old_logp_c, advant
     a.dvalue, a.dstd, a.stats = _p(dvalue, f, "dvalue"), _p(dstd, f, "dstd"), _p(stats, f, "stats")
     _abi.check(lib.qa_ppo_loss_tsc(C.byref(a), _stream()), "qa_ppo_loss_tsc")
     _count(1)
+
+
+# ---- K16 / K17 ------------------------------------------------------------------------------------
+def post_physics_tsc(const, args, which: str) -> None:
+    """TSC post_physics_step halves (tsc/.../legged_robot.py:226-298): which = "pre" | "post"."""
+    lib = _abi.load()
+    fn = lib.qa_post_physics_tsc_pre if which == "pre" else lib.qa_post_physics_tsc_post
+    _abi.check(fn(C.byref(const), C.byref(args), _stream()), f"qa_post_physics_tsc_{which}")
+    _count(1)

@@ -14,6 +14,7 @@ for one B200 per process:
 The semi-supervised InfoGAIL discriminator update (`update_ss_info_gail`, :415-541) and DAgger
 (`update_dagger`, :543-575) are SURVEY.md 8(f) "next" rows and are not part of this path yet.
 """
+import os
 from typing import Optional
 
 import torch
@@ -130,7 +131,7 @@ class SSInfoGAIL:
                  lr_q=1e-3, max_grad_norm=1.0, use_clipped_value_loss=False, schedule="fixed", desired_kl=0.01,
                  device='cpu', disc_replay_buffer_size=100000, min_std=None, us_coef=1.0, ss_coef=4.0,
                  prior_soft_coef=1e-3, info_max_coef=2.0, begin_rim=100, priv_reg_coef_schedual=[0, 0.1, 0, 1],
-                 priv_reg_coef_schedual_resume=[0, 0.1, 0, 1], use_cuda_graph=True, fused_loss=True, capture_collectives=True):
+                 priv_reg_coef_schedual_resume=[0, 0.1, 0, 1], use_cuda_graph=True, fused_loss=True, capture_collectives=None):
         self.device, self.env = device, env
         self.desired_kl, self.schedule = desired_kl, schedule
         self.lr_disc, self.lr_q, self.min_std = lr_disc, lr_q, min_std
@@ -168,6 +169,11 @@ class SSInfoGAIL:
         self.use_cuda_graph = use_cuda_graph and torch.device(device).type == "cuda"
         self._graphs = None
         self.fused_loss = fused_loss and torch.device(device).type == "cuda"
+        # with > 1 rank the three NCCL all-reduces are captured inside the minibatch graph (measured: 95 % weak-scaling
+        # efficiency at 2 GPUs); QA_CAPTURE_COLLECTIVES=0 keeps only forward/backward in the graph and runs the
+        # all-reduces + K13/K8 eagerly between replays
+        if capture_collectives is None:
+            capture_collectives = os.environ.get("QA_CAPTURE_COLLECTIVES", "1") == "1"
         self.capture_collectives = capture_collectives
         self._graph_has_apply = True
         torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)   # capture runs on a side stream
