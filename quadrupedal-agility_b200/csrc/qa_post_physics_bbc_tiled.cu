@@ -11,8 +11,8 @@
 //       tile on its own -- and the env warps draw this step's Philox noise while they wait;
 //   P2a (scalar warp A, thread-per-env, starts as soon as ITS loads land): base-frame quantities, euler angles, centre
 //       terrain height, periodic resampling, push;  (scalar warp B, lane = (env, foot)): key-body positions;
-//   P1  (env warps, after the small tiles): warp-per-env, lanes = DOFs / bodies: the nine 12-wide reward sums (warp
-//       shuffle butterflies) and the contact-force norms (ballots) -> per-env scalars; named barrier 1 hands them to
+//   P1  after the small tiles: scalar warp B (lane = (env, leg), 3 DOFs per lane) forms the nine 12-wide reward sums,
+//       the env warps (lanes = bodies) the contact-force norms (ballots) -> per-env scalars; named barrier 1 hands them to
 //   P2b (scalar warp A): contacts, termination, reward total, episode sums, reset decision -- while the env warps run
 //   P3a: the row lanes that depend on loaded inputs only and, once the history tile has landed, the history shift;
 //   P3b (env warps, after barrier 2): reset envs blend their mocap frame (lanes = frame columns) and rewrite simulator
@@ -74,7 +74,7 @@ struct __align__(16) T2Smem {
 // per-CTA clock64 stamps at the phase boundaries, slots 0..15, plus %globaltimer at entry / exit in slots 16, 17.
 #ifdef QA_K2_TRACE
 #define K2_TRACE_CTAS 1024
-__device__ long long g_k2_trace[K2_TRACE_CTAS][20];
+__device__ long long g_k2_trace[K2_TRACE_CTAS][24];
 __device__ __forceinline__ long long k2_gtime() {
     long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -90,7 +90,7 @@ __device__ __forceinline__ long long k2_gtime() {
     } while (0)
 extern "C" int qa_k2_trace_dump(long long* host, int max_ctas) {
     const int n = max_ctas < K2_TRACE_CTAS ? max_ctas : K2_TRACE_CTAS;
-    return (int)cudaMemcpyFromSymbol(host, g_k2_trace, sizeof(long long) * 20 * n);
+    return (int)cudaMemcpyFromSymbol(host, g_k2_trace, sizeof(long long) * 24 * n);
 }
 #else
 #define STAMP(slot, who) do { } while (0)
@@ -249,29 +249,10 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
         STAMP(1, T_ENV);
         mbar_wait(&S.bar_small, 0);
         STAMP(2, T_ENV);
-        // ---------------- P1: warp-per-env DOF sums and contact-force norms --------------------------------
+        // ---------------- P1 (env-warp half): contact-force norms, lanes = bodies --------------------------------
+        // (the nine 12-wide DOF sums run on scalar warp B with lane = (env, leg): 8x fewer warp instructions)
         const float dof_pos = S.dof[el * 24 + 2 * d_], dof_vel = S.dof[el * 24 + 2 * d_ + 1];
         {
-            const float act = S.act[el * 12 + d_], lact = S.lact[el * 12 + d_];
-            const float tq = S.tq[el * 12 + d_], ltq = S.ltq[el * 12 + d_], ldv = S.ldv[el * 12 + d_];
-            float v, s[9];
-            v = lact - act;
-            s[0] = half_warp_sum(dl ? v * v : 0.f);                                         // action_rate
-            v = tq - ltq;
-            s[1] = half_warp_sum(dl ? v * v : 0.f);                                         // delta_torques
-            v = (ldv - dof_vel) / c.dt;
-            s[2] = half_warp_sum(dl ? v * v : 0.f);                                         // dof_acc
-            const float dq0 = dof_pos - c.default_dof_pos[d_];
-            s[3] = half_warp_sum(dl ? dq0 * dq0 : 0.f);                                     // dof_error
-            v = -fminf(dof_pos - c.dof_pos_lower[d_], 0.f);
-            v = v + fmaxf(dof_pos - c.dof_pos_upper[d_], 0.f);
-            s[4] = half_warp_sum(dl ? v : 0.f);                                             // dof_pos_limits
-            v = clampf(fabsf(dof_vel) - c.dof_vel_limits[d_] * c.soft_dof_vel_limit, 0.f, 1.f);
-            s[5] = half_warp_sum(dl ? v : 0.f);                                             // dof_vel_limits
-            s[6] = half_warp_sum((dl && ((c.hip_dof_mask >> d_) & 1u)) ? dq0 * dq0 : 0.f);  // hip_pos
-            v = fmaxf(fabsf(tq) - c.torque_limits[d_] * c.soft_torque_limit, 0.f);
-            s[7] = half_warp_sum(dl ? v : 0.f);                                             // torque_limits
-            s[8] = half_warp_sum(dl ? tq * tq : 0.f);                                       // torques
             float nrm = 0.f;
             if (lane < B) {
                 const float* f = S.cf + (el * B + lane) * 3;
@@ -283,19 +264,16 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
 #pragma unroll
             for (int j = 0; j < 4; ++j) ff[j] = __shfl_sync(QA_FULL, nrm, c.feet_indices[j]);
             float out = 0.f;
-#pragma unroll
-            for (int k = 0; k < 9; ++k)
-                if (lane == k) out = s[k];
             if (lane == SC_NCOL) out = (float)__popc(hit_col);
             if (lane == SC_TERM) out = hit_term ? 1.f : 0.f;
 #pragma unroll
             for (int j = 0; j < 4; ++j)
                 if (lane == SC_FF + j) out = ff[j];
-            if (lane < SC_RESET) S.scal[el][lane] = out;
-            // pure copies leave straight from the registers (:158, :161)
+            if (lane >= SC_NCOL && lane < SC_RESET) S.scal[el][lane] = out;
+            // pure copies leave straight from the staged tiles (:158, :161)
             if (dl) {
-                a.last_actions[(size_t)e * 12 + lane] = act;
-                a.last_torques_org[(size_t)e * 12 + lane] = tq;
+                a.last_actions[(size_t)e * 12 + lane] = S.act[el * 12 + lane];
+                a.last_torques_org[(size_t)e * 12 + lane] = S.tq[el * 12 + lane];
             }
         }
         bar_arrive(1, T2_THREADS);          // P1 results are in S.scal: the scalar warp may run P2b while this warp goes on
@@ -411,49 +389,21 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
                 const Vec3 local = {S.key[el * 12 + lane * 3 + 0] - R[0], S.key[el * 12 + lane * 3 + 1] - R[1],
                                     S.key[el * 12 + lane * 3 + 2] - R[2]};
                 const Vec3 o = quat_rotate_sgn(hq, local, 1.f);
-                sc[SC_KEY + lane * 3 + 0] = o.x, sc[SC_KEY + lane * 3 + 1] = o.y, sc[SC_KEY + lane * 3 + 2] = o.z;
+                disc[33 + lane * 3 + 0] = o.x * c.s_key_pos, disc[33 + lane * 3 + 1] = o.y * c.s_key_pos;
+                disc[33 + lane * 3 + 2] = o.z * c.s_key_pos;
             }
             __syncwarp();
         }
         if (dl) a.last_dof_vel[(size_t)e * 12 + lane] = dv_out;                    // :159 (post-reset dof_vel)
-        // observations (:261-331): post-reset root / dof, pre-reset base velocities / angles / contacts
-        const float root_h = R[2] - sc[SC_CH];
-        if (lane < 4) {
-            disc[33 + lane * 3 + 0] = sc[SC_KEY + lane * 3 + 0] * c.s_key_pos;
-            disc[33 + lane * 3 + 1] = sc[SC_KEY + lane * 3 + 1] * c.s_key_pos;
-            disc[33 + lane * 3 + 2] = sc[SC_KEY + lane * 3 + 2] * c.s_key_pos;
-            const float cf_ = S.cfilt_out[el * 4 + lane] ? 1.f : 0.f;
-            row[41 + lane] = cf_ - 0.5f;
-            disc[45 + lane] = cf_ * c.s_foot_contact;
-            if (a.contact_buf)
-                a.contact_buf[((size_t)e * a.contact_ring_len + a.contact_ring_head) * 4 + lane] = cf_;
-            if (a.contact_force_buf)
-                a.contact_force_buf[((size_t)e * a.contact_ring_len + a.contact_ring_head) * 4 + lane] =
-                    clampf(S.ff[el * 4 + lane], -c.clip_obs, c.clip_obs);
-        }
-        if (lane >= 8 && lane < 14) a.last_root_vel[(size_t)e * 6 + lane - 8] = R[7 + lane - 8];      // :160
-        if (lane >= 16 && lane < 19) {
-            const int k = lane - 16;
-            const float lv = S.blv[el * 3 + k], av = S.bav[el * 3 + k];
-            row[2 + k] = av * c.s_ang_vel;
-            row[58 + k] = lv * c.s_lin_vel;
-            disc[3 + k] = lv * c.s_lin_vel_dist;
-            disc[6 + k] = av * c.s_ang_vel_dist;
-        }
-        if (lane == 19) {
-            const float roll = S.rpy[el * 3 + 0], pitch = S.rpy[el * 3 + 1];
-            row[0] = roll;
-            row[1] = pitch;
+        // observations (:261-331): the P2-dependent row / disc lanes were written by the scalar warps (A: angles, base
+        // velocities, root height, contacts, commands; B: key-body positions); a reset env overrides the lanes that see
+        // its post-reset root
+        if (is_reset && lane == 0) {
+            const float root_h = R[2] - sc[SC_CH];
             row[57] = c.root_height_obs ? root_h : 0.f;
-            disc[0] = roll;
-            disc[1] = pitch;
             disc[2] = root_h;
         }
-        if (lane >= 20 && lane < 31) {
-            const int k = lane - 20;
-            const float v = k < 5 ? S.cmd[el * 5 + k] : (k == 5 ? S.eps[el] : S.lc[el * 5 + k - 6]);
-            row[CMD_OFF + k] = clampf(v, -c.clip_obs, c.clip_obs);
-        }
+        if (lane >= 8 && lane < 14) a.last_root_vel[(size_t)e * 6 + lane - 8] = R[7 + lane - 8];      // :160
         __syncwarp();
         {
             float* h = S.hist + el * HIST_W;
@@ -521,6 +471,19 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
             S.bav[el * 3 + 0] = bav.x, S.bav[el * 3 + 1] = bav.y, S.bav[el * 3 + 2] = bav.z;
             S.pg[el * 3 + 0] = pg.x, S.pg[el * 3 + 1] = pg.y, S.pg[el * 3 + 2] = pg.z;
             S.rpy[el * 3 + 0] = roll, S.rpy[el * 3 + 1] = pitch, S.rpy[el * 3 + 2] = yaw;
+            {
+                // this warp's lanes of the observation row and of the disc obs (pre-reset quantities, :263-291)
+                float* row = S.obs + el * ROW;
+                float* disc = S.disc + el * QA_NUM_OBS_DISC;
+                const float root_h_pre = R[2] - center_h;
+                row[0] = roll, row[1] = pitch;
+                row[2] = bav.x * c.s_ang_vel, row[3] = bav.y * c.s_ang_vel, row[4] = bav.z * c.s_ang_vel;
+                row[57] = c.root_height_obs ? root_h_pre : 0.f;
+                row[58] = blv.x * c.s_lin_vel, row[59] = blv.y * c.s_lin_vel, row[60] = blv.z * c.s_lin_vel;
+                disc[0] = roll, disc[1] = pitch, disc[2] = root_h_pre;
+                disc[3] = blv.x * c.s_lin_vel_dist, disc[4] = blv.y * c.s_lin_vel_dist, disc[5] = blv.z * c.s_lin_vel_dist;
+                disc[6] = bav.x * c.s_ang_vel_dist, disc[7] = bav.y * c.s_ang_vel_dist, disc[8] = bav.z * c.s_ang_vel_dist;
+            }
             if (divisible_by(ep, c.resample_period)) {                                 // :454-462
                 const K2Draw d = draw_site(c, a, e, SITE_RS0, a.rs_eps_u, a.rs_c_idx, a.rs_cmd_u);
                 resample_thread(c, d, cmd, S.eps + el, S.lc + el * 5);
@@ -553,7 +516,15 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
                 const bool ct = f > 2.f;
                 S.ff[el * 4 + j] = f;
                 S.cont_out[el * 4 + j] = ct ? 1 : 0;
-                S.cfilt_out[el * 4 + j] = (ct || S.lcont[el * 4 + j] != 0) ? 1 : 0;
+                const bool cfl = ct || S.lcont[el * 4 + j] != 0;
+                S.cfilt_out[el * 4 + j] = cfl ? 1 : 0;
+                const float cf_ = cfl ? 1.f : 0.f;                                       // :285, :275, :323-324
+                S.obs[el * ROW + 41 + j] = cf_ - 0.5f;
+                S.disc[el * QA_NUM_OBS_DISC + 45 + j] = cf_ * c.s_foot_contact;
+                if (a.contact_buf) a.contact_buf[((size_t)e * a.contact_ring_len + a.contact_ring_head) * 4 + j] = cf_;
+                if (a.contact_force_buf)
+                    a.contact_force_buf[((size_t)e * a.contact_ring_len + a.contact_ring_head) * 4 + j] =
+                        clampf(f, -c.clip_obs, c.clip_obs);
             }
             const float root_z_pre = R[2];
             const bool time_out = ((float)ep > c.max_episode_length) || (root_z_pre < -6.0f);   // :168-176
@@ -608,6 +579,14 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
                 mode = d.c_idx;
                 ep = 0;
             }
+            {
+                float* rowc = S.obs + el * ROW + CMD_OFF;                                // [commands 5 | eps 1 | c 5] (:314-316)
+#pragma unroll
+                for (int k = 0; k < 5; ++k) rowc[k] = clampf(cmd[k], -c.clip_obs, c.clip_obs);
+                rowc[5] = clampf(S.eps[el], -c.clip_obs, c.clip_obs);
+#pragma unroll
+                for (int k = 0; k < 5; ++k) rowc[6 + k] = clampf(S.lc[el * 5 + k], -c.clip_obs, c.clip_obs);
+            }
             S.ep[el] = ep;
             S.rew[el] = rew;
             S.rooth[el] = root_h_pre;
@@ -648,10 +627,51 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
             const Quat hq = heading_quat_inv(Quat{R[3], R[4], R[5], R[6]});
             const Vec3 local = {k0 - R[0], k1 - R[1], k2 - R[2]};
             const Vec3 o = quat_rotate_sgn(hq, local, 1.f);
-            float* sc = S.scal[el];
-            sc[SC_KEY + j * 3 + 0] = o.x, sc[SC_KEY + j * 3 + 1] = o.y, sc[SC_KEY + j * 3 + 2] = o.z;
+            float* disc = S.disc + el * QA_NUM_OBS_DISC;                                 // :272-274, on the pre-reset root
+            disc[33 + j * 3 + 0] = o.x * c.s_key_pos, disc[33 + j * 3 + 1] = o.y * c.s_key_pos, disc[33 + j * 3 + 2] = o.z * c.s_key_pos;
         }
         STAMP(19, T_SB);
+        // ---------------- P1 (DOF half): the nine 12-wide reward sums, lane = (env, leg), 3 DOFs per lane -----------------
+        mbar_wait(&S.bar_small, 0);
+        {
+            const int el = lane >> 2, leg = lane & 3;
+            float s[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) s[k] = 0.f;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const int d = leg * 3 + j;
+                const float dof_pos = S.dof[el * 24 + 2 * d], dof_vel = S.dof[el * 24 + 2 * d + 1];
+                const float act = S.act[el * 12 + d], lact = S.lact[el * 12 + d];
+                const float tq = S.tq[el * 12 + d], ltq = S.ltq[el * 12 + d], ldv = S.ldv[el * 12 + d];
+                float v;
+                v = lact - act;
+                s[0] = s[0] + v * v;                                                       // action_rate
+                v = tq - ltq;
+                s[1] = s[1] + v * v;                                                       // delta_torques
+                v = (ldv - dof_vel) / c.dt;
+                s[2] = s[2] + v * v;                                                       // dof_acc
+                const float dq0 = dof_pos - c.default_dof_pos[d];
+                s[3] = s[3] + dq0 * dq0;                                                   // dof_error
+                v = -fminf(dof_pos - c.dof_pos_lower[d], 0.f);
+                v = v + fmaxf(dof_pos - c.dof_pos_upper[d], 0.f);
+                s[4] = s[4] + v;                                                           // dof_pos_limits
+                v = clampf(fabsf(dof_vel) - c.dof_vel_limits[d] * c.soft_dof_vel_limit, 0.f, 1.f);
+                s[5] = s[5] + v;                                                           // dof_vel_limits
+                if ((c.hip_dof_mask >> d) & 1u) s[6] = s[6] + dq0 * dq0;                   // hip_pos
+                v = fmaxf(fabsf(tq) - c.torque_limits[d] * c.soft_torque_limit, 0.f);
+                s[7] = s[7] + v;                                                           // torque_limits
+                s[8] = s[8] + tq * tq;                                                     // torques
+            }
+            float* sc = S.scal[el];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                s[k] += __shfl_xor_sync(QA_FULL, s[k], 1);
+                s[k] += __shfl_xor_sync(QA_FULL, s[k], 2);
+                if (leg == 0) sc[SC_SUM0 + k] = s[k];
+            }
+        }
+        STAMP(15 + 5, T_SB);
         bar_arrive(1, T2_THREADS);
         any_state_write = __syncthreads_or(any_state_write ? 1 : 0) != 0;      // barrier 2
     }

@@ -22,7 +22,7 @@ sys.path.insert(0, ROOT)
 SEGMENTS = [  # (name, stamp_from, stamp_to); stamps 0-11 env warp 0, 12-15/18 scalar warp A, 19 scalar warp B
     ("env: entry -> loads issued, noise drawn", 0, 1),
     ("env: wait small tiles", 1, 2),
-    ("env: P1 (sums, norms)", 2, 3),
+    ("env: P1 (contact norms)", 2, 3),
     ("env: P3a row lanes", 3, 4),
     ("env: wait history tile", 4, 5),
     ("env: history shift", 5, 6),
@@ -37,6 +37,7 @@ SEGMENTS = [  # (name, stamp_from, stamp_to); stamps 0-11 env warp 0, 12-15/18 s
     ("scalar A: P2b", 14, 15),
     ("scalar A: barrier 2 + small-output stores", 15, 18),
     ("scalar B: entry -> key positions done", 0, 19),
+    ("scalar B: key positions -> DOF sums done (incl. wait for small tiles)", 19, 20),
     ("env: entry -> barrier 2 passed", 0, 7),
     ("whole CTA (entry -> stores issued and read)", 0, 11),
 ]
@@ -85,7 +86,7 @@ def run(n_envs, reps):
     env.use_device_step_counter(True)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     n_cta = min(n_envs // 8, 1024)
-    host = np.zeros((n_cta, 20), dtype=np.int64)
+    host = np.zeros((n_cta, 24), dtype=np.int64)
     seg = {name: [] for name, _, _ in SEGMENTS}
     spans, skews, times = [], [], []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
