@@ -51,7 +51,7 @@ int qa_version(void);
 /* human readable build string ("sm_100a, nvcc 12.9, ...") */
 const char* qa_build_info(void);
 /* sizeof() of argument struct number `which` (order of declaration in this header, QaActionPushArgs
- * = 0 ... QaGaeArgs = 9, QaGatherArgs = 10, QaClipAdamArgs = 11, QaLinearArgs = 12, QaActBwdArgs = 13, QaPpoLossArgs = 14, QaLinearBwdArgs = 15, QaHistEncArgs = 16, QaRowLossArgs = 17, QaPpoScalarsArgs = 18, QaDepthArgs = 19, QaPpoLossTscArgs = 20, QaTscConst = 21, QaTscStepArgs = 22; -1 if unknown): a layout handshake for FFI mirrors of these structs */
+ * = 0 ... QaGaeArgs = 9, QaGatherArgs = 10, QaClipAdamArgs = 11, QaLinearArgs = 12, QaActBwdArgs = 13, QaPpoLossArgs = 14, QaLinearBwdArgs = 15, QaHistEncArgs = 16, QaRowLossArgs = 17, QaPpoScalarsArgs = 18, QaDepthArgs = 19, QaPpoLossTscArgs = 20, QaTscConst = 21, QaTscStepArgs = 22, QaDiscInputArgs = 23, QaDiscRewardArgs = 24; -1 if unknown): a layout handshake for FFI mirrors of these structs */
 int qa_struct_size(int which);
 
 /* ------------------------------------------------------------------------------------------
@@ -676,6 +676,51 @@ typedef struct QaTscStepArgs {
 } QaTscStepArgs;
 int qa_post_physics_tsc_pre(const QaTscConst* c, const QaTscStepArgs* a, void* stream);
 int qa_post_physics_tsc_post(const QaTscConst* c, const QaTscStepArgs* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K18 discriminator input assembly -- the runner's disc-history bookkeeping and the front half of
+ *     Discriminator.predict_disc_reward in one pass: bbc/rsl_rl/runners/on_policy_runner.py:163-181 (terminal-state
+ *     patch, 2-step history roll, restart of the history of reset envs), bbc/rsl_rl/algorithms/discriminator.py:74-88
+ *     (task-obs weighting, per-step weight), bbc/rsl_rl/utils/utils.py:97-103 (Normalizer.normalize_torch).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct QaDiscInputArgs {
+    int32_t num_envs;
+    const uint8_t* dones;               /* (N) reset mask of this step */
+    const float* prev_disc;             /* (N,49) disc obs of the previous step (terminal state of envs that reset) */
+    const float* next_disc;             /* (N,49) disc obs of this step */
+    const float* hist_prev;             /* (N,2,49) */
+    float* hist_new;                    /* (N,2,49) history the reward is computed on / the replay buffer stores */
+    float* hist_next;                   /* (N,2,49) history carried to the next step (reset envs: [next, next]) */
+    float* x_norm; int64_t x_pitch;     /* (N,98) normalised discriminator input, row pitch in floats */
+    const float* norm_mean;             /* (98) float32(mean) */
+    const float* norm_std;              /* (98) sqrt(float32(var + eps)) */
+    float norm_clip;                    /* 10 */
+    int32_t task_obs_weight_decay; float task_obs_weight;
+    float obs_disc_weight_step;
+} QaDiscInputArgs;
+int qa_disc_input(const QaDiscInputArgs* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K19 style-reward tail -- the back half of Discriminator.predict_disc_reward (discriminator.py:64-69, 90-118, MSELoss
+ *     mapping) plus the reward half of SSInfoGAIL.process_env_step (gail.py:199-206): heads -> reward_i, reward_us,
+ *     reward_ss (float64 cross-entropy of the already soft-maxed classifier output), weighted total in float64,
+ *     + gamma * V * time_out, stored as float32 (rollout_storage.py:67).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct QaDiscRewardArgs {
+    int32_t num_envs;
+    const float* heads; int64_t heads_pitch;   /* (N, 2 + dim_c): [d | eps | classifier logits] */
+    const float* obs; int64_t obs_pitch; int32_t obs_width;   /* observation rows; the last dim_c + 1 lanes are eps, c */
+    const float* reward_t;              /* (N) task reward (env.rew_buf) */
+    float dt, coef_i, coef_us, coef_ss, coef_t;
+    const float* values; int64_t values_pitch;   /* (N,1) critic values of this step (row pitch in floats), or NULL */
+    const uint8_t* time_outs;           /* (N) infos["time_outs"], or NULL */
+    float gamma;
+    const uint8_t* dones;               /* (N) or NULL */
+    float* rewards_out;                 /* (N) e.g. storage.rewards[step] */
+    uint8_t* dones_out;                 /* (N) e.g. storage.dones[step], or NULL */
+    float* reward_terms;                /* (N,4) reward_i, reward_us, reward_ss, reward_t (already x dt), or NULL */
+} QaDiscRewardArgs;
+int qa_disc_reward(const QaDiscRewardArgs* a, void* stream);
 
 #ifdef __cplusplus
 }

@@ -38,6 +38,8 @@ extern "C" int qa_struct_size(int which) {
         case 20: return (int)sizeof(QaPpoLossTscArgs);
         case 21: return (int)sizeof(QaTscConst);
         case 22: return (int)sizeof(QaTscStepArgs);
+        case 23: return (int)sizeof(QaDiscInputArgs);
+        case 24: return (int)sizeof(QaDiscRewardArgs);
         default: return -1;
     }
 }

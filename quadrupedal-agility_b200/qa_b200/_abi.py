@@ -226,6 +226,20 @@ class QaTscStepArgs(C.Structure):
                 ("rng_step", C.c_uint64)]
 
 
+class QaDiscInputArgs(C.Structure):
+    _fields_ = [("num_envs", C.c_int32), ("dones", vp), ("prev_disc", vp), ("next_disc", vp), ("hist_prev", vp),
+                ("hist_new", vp), ("hist_next", vp), ("x_norm", vp), ("x_pitch", C.c_int64), ("norm_mean", vp),
+                ("norm_std", vp), ("norm_clip", C.c_float), ("task_obs_weight_decay", C.c_int32),
+                ("task_obs_weight", C.c_float), ("obs_disc_weight_step", C.c_float)]
+
+
+class QaDiscRewardArgs(C.Structure):
+    _fields_ = [("num_envs", C.c_int32), ("heads", vp), ("heads_pitch", C.c_int64), ("obs", vp), ("obs_pitch", C.c_int64),
+                ("obs_width", C.c_int32), ("reward_t", vp), ("dt", C.c_float), ("coef_i", C.c_float), ("coef_us", C.c_float),
+                ("coef_ss", C.c_float), ("coef_t", C.c_float), ("values", vp), ("values_pitch", C.c_int64), ("time_outs", vp), ("gamma", C.c_float),
+                ("dones", vp), ("rewards_out", vp), ("dones_out", vp), ("reward_terms", vp)]
+
+
 # every symbol `include/qa_b200.h` declares: name -> (restype, argtypes)
 SYMBOLS = {
     "qa_version": (C.c_int, []),
@@ -251,11 +265,14 @@ SYMBOLS = {
     "qa_ppo_loss_tsc": (C.c_int, [C.POINTER(QaPpoLossTscArgs), vp]),
     "qa_post_physics_tsc_pre": (C.c_int, [C.POINTER(QaTscConst), C.POINTER(QaTscStepArgs), vp]),
     "qa_post_physics_tsc_post": (C.c_int, [C.POINTER(QaTscConst), C.POINTER(QaTscStepArgs), vp]),
+    "qa_disc_input": (C.c_int, [C.POINTER(QaDiscInputArgs), vp]),
+    "qa_disc_reward": (C.c_int, [C.POINTER(QaDiscRewardArgs), vp]),
 }
 
 STRUCT_ORDER = [QaActionPushArgs, QaTorqueArgs, QaTerrain, QaHeightScanArgs, QaMocapTable, QaMocapBlendArgs,
                 QaBbcConst, QaBbcStepArgs, QaCompactArgs, QaGaeArgs, QaGatherArgs, QaClipAdamArgs, QaLinearArgs, QaActBwdArgs, QaPpoLossArgs, QaLinearBwdArgs, QaHistEncArgs,
-                QaRowLossArgs, QaPpoScalarsArgs, QaDepthArgs, QaPpoLossTscArgs, QaTscConst, QaTscStepArgs]
+                QaRowLossArgs, QaPpoScalarsArgs, QaDepthArgs, QaPpoLossTscArgs, QaTscConst, QaTscStepArgs,
+                QaDiscInputArgs, QaDiscRewardArgs]
 
 _LIB = None
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libqa_b200.so")

@@ -450,3 +450,44 @@ def post_physics_tsc(const, args, which: str) -> None:
     fn = lib.qa_post_physics_tsc_pre if which == "pre" else lib.qa_post_physics_tsc_post
     _abi.check(fn(C.byref(const), C.byref(args), _stream()), f"qa_post_physics_tsc_{which}")
     _count(1)
+
+
+# ---- K18 / K19 ------------------------------------------------------------------------------------
+def disc_input(dones, prev_disc, next_disc, hist_prev, hist_new, hist_next, x_norm, norm_mean, norm_std, norm_clip,
+               task_obs_weight_decay, task_obs_weight, obs_disc_weight_step) -> None:
+    """Disc-history bookkeeping of the rollout step + the normalised discriminator input (on_policy_runner.py:163-181,
+    discriminator.py:74-88)."""
+    lib = _abi.load()
+    f = torch.float32
+    a = _abi.QaDiscInputArgs(dones.shape[0], _bytep(dones, "dones"), _p(prev_disc, f, "prev_disc"), _p(next_disc, f, "next_disc"),
+                             _p(hist_prev, f, "hist_prev"), _p(hist_new, f, "hist_new"), _p(hist_next, f, "hist_next"),
+                             _p_strided(x_norm, f, "x_norm"), x_norm.stride(0), _p(norm_mean, f, "norm_mean"),
+                             _p(norm_std, f, "norm_std"), float(norm_clip), int(bool(task_obs_weight_decay)),
+                             float(task_obs_weight), float(obs_disc_weight_step))
+    _abi.check(lib.qa_disc_input(C.byref(a), _stream()), "qa_disc_input")
+    _count(1)
+
+
+def disc_reward(heads, obs, reward_t, dt, coefs, rewards_out, values=None, time_outs=None, gamma=0.0, dones=None,
+                dones_out=None, reward_terms=None) -> None:
+    """Style-reward tail + time-out bootstrap (discriminator.py:90-118, gail.py:199-206); coefs = (i, us, ss, t)."""
+    lib = _abi.load()
+    f = torch.float32
+    a = _abi.QaDiscRewardArgs()
+    a.num_envs = heads.shape[0]
+    a.heads, a.heads_pitch = _p_strided(heads, f, "heads"), heads.stride(0)
+    a.obs, a.obs_pitch, a.obs_width = _p_strided(obs, f, "obs"), obs.stride(0), obs.shape[1]
+    a.reward_t = _p(reward_t, f, "reward_t")
+    a.dt, (a.coef_i, a.coef_us, a.coef_ss, a.coef_t) = float(dt), (float(c) for c in coefs)
+    if values is not None and values.dim() == 1:
+        values = values.unsqueeze(1)
+    a.values = None if values is None else _p_strided(values, f, "values")
+    a.values_pitch = 1 if values is None else values.stride(0)
+    a.time_outs = None if time_outs is None else _bytep(time_outs, "time_outs")
+    a.gamma = float(gamma)
+    a.dones = None if dones is None else _bytep(dones, "dones")
+    a.rewards_out = _p(rewards_out, f, "rewards_out")
+    a.dones_out = None if dones_out is None else _bytep(dones_out, "dones_out")
+    a.reward_terms = None if reward_terms is None else _p(reward_terms, f, "reward_terms")
+    _abi.check(lib.qa_disc_reward(C.byref(a), _stream()), "qa_disc_reward")
+    _count(1)

@@ -254,6 +254,28 @@ class SSInfoGAIL:
         self.actor_critic.reset(dones)
 
     @torch.no_grad()
+    def process_env_step_fused(self, heads, obs, reward_t, dones, infos, flat_hist=None):
+        """`predict_disc_reward`'s tail + `process_env_step` (discriminator.py:90-118, gail.py:199-212) with the reward
+        arithmetic in ONE kernel (K19) that writes storage.rewards[step] / storage.dones[step] in place.  `heads` =
+        `Discriminator.heads_forward` of the normalised history; `flat_hist` = that history (N,98) when it is not already
+        in the staging slot of this step."""
+        tr, st, d = self.transition, self.storage, self.disc
+        t = st.step
+        tr.dones = dones
+        ops.disc_reward(heads, obs, reward_t, d.dt, (d.reward_i_coef, d.reward_us_coef, d.reward_ss_coef, d.reward_t_coef),
+                        st.rewards[t].view(-1), values=tr.values, time_outs=infos.get('time_outs'),
+                        gamma=self.gamma, dones=dones, dones_out=st.dones[t].view(-1))
+        if self._disc_stage is not None:
+            if flat_hist is not None:
+                self._disc_stage[0][t].copy_(flat_hist)
+            self._disc_stage[1][t].copy_(self.env.latent_eps)
+            self._disc_stage[2][t].copy_(self.env.latent_c)
+        elif flat_hist is not None:
+            self.disc_storage.insert(flat_hist, self.env.latent_eps, self.env.latent_c)
+        st.add_transitions(tr, rewards_dones_written=True)
+        self.actor_critic.reset(dones)
+
+    @torch.no_grad()
     def compute_returns(self, last_critic_obs):
         last_values = self.actor_critic.evaluate(last_critic_obs)
         self.storage.compute_returns(last_values, self.gamma, self.lam)

@@ -312,6 +312,15 @@ class Discriminator(nn.Module):
         c = torch.softmax(linear_act(x, self.classifier.weight, self.classifier.bias, None), -1)
         return d, eps, torch.clamp(c, 1e-20, torch.inf)
 
+    def heads_forward(self, x):
+        """[d | eps | classifier logits | 0] (M, 8) from the normalised input: trunk on the GEMM chain, the three heads as ONE
+        GEMM over their concatenated weights (padded to 8 rows so the output row pitch is TMA-legal)."""
+        h = run_mlp(self.trunk, x)
+        w = torch.cat([self.linear.weight, self.encoder_eps.weight, self.classifier.weight,
+                       torch.zeros(1, self.linear.weight.shape[1], device=x.device)], dim=0)
+        b = torch.cat([self.linear.bias, self.encoder_eps.bias, self.classifier.bias, torch.zeros(1, device=x.device)])
+        return linear_act(h, w, b, None)
+
     def predict_disc_reward(self, reward_t, obs, obs_disc, normalizer=None):
         """Returns (rewards, reward_i, reward_us, reward_ss, reward_t); like the reference, the semi-supervised
         term goes through a float64 cross-entropy on the already soft-maxed classifier output (:68-69, :108),

@@ -13,6 +13,7 @@ import time
 import torch
 
 from .. import config as K
+from .. import ops
 from .algorithm import SSInfoGAIL
 from .modules import ActorCritic, Estimator, Discriminator
 from .utils import Normalizer, install_pickle_alias
@@ -54,11 +55,41 @@ class OnPolicyRunner:
         self.tot_timesteps, self.tot_time, self.current_learning_iteration = 0, 0.0, 0
         self.perf = {}
         self._disc_hist = None
+        self._hist_pp = None
+        self.fused_rollout = bool(train_cfg["runner"].get("fused_rollout", True))
         env.reset()
 
     # ---- one rollout step (:156-181) ----------------------------------------------------------------------
+    def _rollout_step_fused(self, obs, critic_obs, hist_encoding):
+        """Same step with the disc-history bookkeeping, the normalisation, the reward tail and the time-out bootstrap in two
+        kernels (K18, K19) around the discriminator GEMMs."""
+        env, alg = self.env, self.alg
+        N, L, W = env.num_envs, self.disc_obs_len, env.num_obs_disc
+        if self._hist_pp is None:
+            dev = self.device
+            self._hist_pp = [torch.zeros(N, L, W, device=dev) for _ in range(2)]
+            self._hist_new = torch.zeros(N, L * W, device=dev)
+            self._x_norm = torch.zeros(N, (L * W + 3) // 4 * 4, device=dev)[:, :L * W]
+        actions = alg.act(obs, critic_obs, hist_encoding)
+        prev_disc = env.get_disc_observations()
+        next_obs, next_priv, rewards, dones, _ids, _cnt, _term = env.step_device(actions)
+        next_disc = env.get_disc_observations()
+        staged = alg._disc_stage is not None
+        hist_new = alg._disc_stage[0][alg.storage.step] if staged else self._hist_new
+        dst = self._hist_pp[0] if self._disc_hist is not self._hist_pp[0] else self._hist_pp[1]
+        mean, std = alg.disc_normalizer.device_moments(self.device)
+        ops.disc_input(dones, prev_disc, next_disc, self._disc_hist.contiguous(), hist_new, dst, self._x_norm, mean, std,
+                       alg.disc_normalizer.clip_obs, env.task_obs_weight_decay, env.task_obs_weight, self.obs_disc_weight_step)
+        heads = alg.disc.heads_forward(self._x_norm)
+        infos = {"time_outs": env._time_outs_latched} if env.cfg.send_timeouts else {}
+        alg.process_env_step_fused(heads, obs, rewards, dones, infos, None if staged else hist_new)
+        self._disc_hist = dst
+        return next_obs, next_priv
+
     def rollout_step(self, obs, critic_obs, hist_encoding=False):
         env, alg = self.env, self.alg
+        if self.fused_rollout and torch.device(self.device).type == "cuda" and self.disc_loss_function == "MSELoss":
+            return self._rollout_step_fused(obs, critic_obs, hist_encoding)
         actions = alg.act(obs, critic_obs, hist_encoding)
         prev_disc = env.get_disc_observations()
         next_obs, next_priv, rewards, dones, _ids, _cnt, _term = env.step_device(actions)

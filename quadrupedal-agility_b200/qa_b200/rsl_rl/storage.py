@@ -47,7 +47,8 @@ class RolloutStorage:
         self.step = 0
         self._gae_ws = torch.zeros(8, device=device, dtype=torch.float64) if torch.device(device).type == "cuda" else None
 
-    def add_transitions(self, transition: "RolloutStorage.Transition"):
+    def add_transitions(self, transition: "RolloutStorage.Transition", rewards_dones_written: bool = False):
+        """`rewards_dones_written`: rewards[step] / dones[step] were already written in place (fused reward kernel K19)."""
         if self.step >= self.num_transitions_per_env:
             raise AssertionError("Rollout buffer overflow")
         s = self.step
@@ -55,8 +56,9 @@ class RolloutStorage:
         if self.privileged_observations is not None:
             self.privileged_observations[s].copy_(transition.critic_observations)
         self.actions[s].copy_(transition.actions)
-        self.rewards[s].copy_(transition.rewards.view(-1, 1))
-        self.dones[s].copy_(transition.dones.view(-1, 1))
+        if not rewards_dones_written:
+            self.rewards[s].copy_(transition.rewards.view(-1, 1))
+            self.dones[s].copy_(transition.dones.view(-1, 1))
         self.values[s].copy_(transition.values)
         self.actions_log_prob[s].copy_(transition.actions_log_prob.view(-1, 1))
         self.mu[s].copy_(transition.action_mean)

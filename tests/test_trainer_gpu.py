@@ -279,3 +279,34 @@ def test_fused_history_encoder_matches_module():
     with torch.enable_grad():                                                   # gradients requested -> module path
         out = ac.infer_hist_latent(hist)
         assert out.requires_grad
+
+
+def test_fused_rollout_step_matches_torch_rollout_step():
+    """K18 + K19 around the discriminator GEMMs against the torch restatement of on_policy_runner.py:163-181 /
+    discriminator.py:71-118 / gail.py:199-212 (which is itself pinned against the reference golden above)."""
+    import bench
+    from qa_b200.pipeline import BbcIteration
+    torch.backends.cuda.matmul.allow_tf32 = False       # `import bench` switches TF32 on; this is the fp32 parity path
+    N, T = 256, 4
+    cfg, static, snaps, table = bench.build_workload(0, DEV, n_envs=N, steps=T)
+    out = []
+    for fused in (False, True):
+        it = BbcIteration(cfg, static, snaps, table, device=DEV, seed=77, use_cuda_graph=False)
+        it.runner.fused_rollout = fused
+        it.env.task_obs_weight = 0.7
+        torch.manual_seed(5)
+        it._rollout_eager(host=False)
+        st = it.runner.alg.storage
+        ds = it.runner.alg.disc_storage
+        out.append(dict(rewards=st.rewards.clone(), dones=st.dones.clone(), values=st.values.clone(),
+                        obs=st.observations.clone(), hist=it.runner._disc_hist.clone(),
+                        replay=ds.states[:T * N].clone(), replay_eps=ds.latent_eps[:T * N].clone(), n=ds.num_samples))
+    a, b = out
+    assert int(a["dones"].sum()) > 0 and a["n"] == b["n"] == T * N
+    assert torch.equal(a["dones"], b["dones"])
+    assert_close("obs", b["obs"], a["obs"])
+    assert_close("values", b["values"], a["values"], rtol=NET_RTOL, atol=NET_ATOL)
+    assert_close("rewards", b["rewards"], a["rewards"], rtol=NET_RTOL, atol=NET_ATOL)
+    assert_close("disc history", b["hist"], a["hist"])
+    assert_close("replay states", b["replay"], a["replay"])
+    assert_close("replay eps", b["replay_eps"], a["replay_eps"])
