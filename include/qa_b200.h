@@ -364,6 +364,8 @@ typedef struct QaClipAdamArgs {
     float grad_scale;
     float* grad_norm_out;               /* (1) total norm before clipping, may be NULL */
     double* workspace;                  /* >= 16 bytes */
+    float weight_decay;                 /* torch.optim.Adam(weight_decay=...): grad += weight_decay * param (after scaling /
+                                           clipping); 0 for the PPO optimisers, 1e-3 for the discriminator's (gail.py:107-128) */
 } QaClipAdamArgs;
 int qa_clip_adam(const QaClipAdamArgs* a, void* stream);
 

@@ -233,3 +233,86 @@ def priv_reg_coef(counter: int, sched=(0, 0.1, 1000, 2000)) -> float:
     """gail.py:354-357."""
     stage = min(max((counter - sched[2]), 0) / sched[3], 1)
     return stage * (sched[1] - sched[0]) + sched[0]
+
+
+# ------------------------------------------------------------------------------------------
+# 8(f)-1  SSInfoGAIL.update_ss_info_gail  (algorithms/gail.py:415-541), MSELoss discriminator
+# ------------------------------------------------------------------------------------------
+
+def disc_forward(sd, x):
+    """Discriminator.forward (discriminator.py:64-69): d, eps, clamped soft-maxed class probabilities."""
+    h = _mlp(x, sd, "trunk", [0, 2], last_act=True, act=F.relu)
+    d = F.linear(h, sd["linear.weight"], sd["linear.bias"])
+    eps = F.linear(h, sd["encoder_eps.weight"], sd["encoder_eps.bias"])
+    c = torch.softmax(F.linear(h, sd["classifier.weight"], sd["classifier.bias"]), -1)
+    return d, eps, torch.clamp(c, 1e-20, torch.inf)
+
+
+def disc_prepare(x, task_obs_weight, norm_mean, norm_var, disc_obs_len=2, num_disc_obs=49, obs_disc_weight_step=0.0,
+                 task_obs_weight_decay=True, norm_eps=1e-4, clip_obs=10.0):
+    """:423-452: task-obs weighting, per-step multipliers, normalisation of a (B, 98) batch of disc-obs histories."""
+    x = x.view(len(x), disc_obs_len, -1).clone()
+    if task_obs_weight_decay:
+        x[:, :, 3:9] *= task_obs_weight
+        x[:, :, 33:] *= task_obs_weight
+    x = x[:, -disc_obs_len:, :].reshape(len(x), -1)
+    mult = (torch.arange(disc_obs_len, dtype=torch.float32) * obs_disc_weight_step + 1)
+    x = x * mult.view(1, -1, 1).repeat(len(x), 1, num_disc_obs).view(len(x), -1)
+    mean_t = torch.as_tensor(norm_mean, dtype=torch.float64).to(torch.float32)
+    std_t = torch.sqrt((torch.as_tensor(norm_var, dtype=torch.float64) + norm_eps).to(torch.float32))
+    return torch.clamp((x - mean_t) / std_t, -clip_obs, clip_obs)
+
+
+def disc_losses(sd, policy_state, policy_latent_eps, policy_latent_c, expert_lb, label_lb, expert_ulb, dim_c=5,
+                ss_coef=1.0, info_max_coef_on=0.0, disc_coef=1.0, us_coef=1.0, disc_grad_penalty=0.1, disc_logit_reg=0.05,
+                disc_weight_decay=0.0001):
+    """:454-514 on already-normalised batches.  Returns the differentiable total loss and the logged terms."""
+    _, _, pred_c_lb = disc_forward(sd, expert_lb)
+    ss_loss = F.cross_entropy(pred_c_lb, label_lb)                                # CE on soft-maxed output (quirk)
+    logits_pi, eps, pred_c = disc_forward(sd, policy_state)
+    logits_exp, _, pred_c_ulb = disc_forward(sd, expert_ulb)
+    pred_c_ulb_mean = torch.mean(pred_c_ulb, dim=0)
+    info_max_loss = torch.mean(-torch.sum(pred_c_ulb * torch.log(pred_c_ulb + 1e-20), dim=-1))
+    disc_exp_loss = torch.mean(F.mse_loss(logits_exp, torch.ones_like(logits_exp), reduction='none'))
+    disc_pi_loss = torch.mean(F.mse_loss(logits_pi, -1 * torch.ones_like(logits_pi), reduction='none'))
+    disc_loss = 0.5 * (disc_pi_loss + disc_exp_loss)
+    us_loss = F.l1_loss(eps, policy_latent_eps)
+    disc_logit_loss = torch.sum(torch.square(torch.flatten(sd["linear.weight"])))
+    sample = expert_ulb.clone().requires_grad_(True)                              # gradient penalty :492-502
+    h = _mlp(sample, sd, "trunk", [0, 2], last_act=True, act=F.relu)
+    dd = F.linear(h, sd["linear.weight"], sd["linear.bias"])
+    (g,) = torch.autograd.grad(dd, sample, grad_outputs=torch.ones_like(dd), create_graph=True, retain_graph=True)
+    grad_pen_loss = torch.mean(torch.sum(torch.square(g), dim=-1))
+    ws = torch.cat([torch.flatten(sd["trunk.0.weight"]), torch.flatten(sd["trunk.2.weight"]), torch.flatten(sd["linear.weight"])])
+    weight_decay = torch.sum(torch.square(ws))
+    loss = (ss_coef * ss_loss + info_max_coef_on * info_max_loss + disc_coef * disc_loss + us_coef * us_loss +
+            disc_grad_penalty * grad_pen_loss + disc_logit_reg * disc_logit_loss + disc_weight_decay * weight_decay)
+    with torch.no_grad():
+        lab_pi = torch.argmax(policy_latent_c, dim=-1)
+        acc = dict(acc_lb=torch.mean((torch.argmax(pred_c_lb, -1) == label_lb).float()),
+                   acc_pi=(logits_pi < 0).float().mean(), acc_exp=(logits_exp > 0).float().mean(),
+                   acc_ulb=torch.mean((torch.argmax(pred_c, -1) == lab_pi).float()))
+    return dict(loss=loss, ss_loss=ss_loss, info_max_loss=info_max_loss, disc_loss=disc_loss, us_loss=us_loss,
+                grad_pen_loss=grad_pen_loss, disc_logit_loss=disc_logit_loss, disc_weight_decay=weight_decay,
+                pred_c_ulb_mean=pred_c_ulb_mean.detach(), **acc)
+
+
+def disc_optimizers(sd, lr_disc=5e-4, lr_q=1e-3):
+    """The three Adam optimisers of gail.py:107-128: the trunk is stepped by ALL of them, weight_decay 1e-3 each."""
+    trunk = [sd[k] for k in ("trunk.0.weight", "trunk.0.bias", "trunk.2.weight", "trunk.2.bias")]
+    grp = lambda ps: {'params': ps, 'weight_decay': 1e-3}                      # noqa: E731
+    return (torch.optim.Adam([grp(trunk), grp([sd["linear.weight"], sd["linear.bias"]])], lr=lr_disc),
+            torch.optim.Adam([grp(trunk), grp([sd["encoder_eps.weight"], sd["encoder_eps.bias"]])], lr=lr_q),
+            torch.optim.Adam([grp(trunk), grp([sd["classifier.weight"], sd["classifier.bias"]])], lr=lr_q))
+
+
+def normalizer_update(mean, var, count, arr):
+    """RunningMeanStd.update (utils/utils.py:63-83) on float64 numpy-like tensors; `arr` float32 (B, D)."""
+    bm = arr.mean(dim=0).double()                                                # np.mean of a float32 array is float32
+    bv = arr.var(dim=0, unbiased=False).double()
+    bc = arr.shape[0]
+    delta = bm - mean
+    tot = count + bc
+    new_mean = mean + delta * bc / tot
+    m2 = var * count + bv * bc + delta.square() * count * bc / (count + bc)
+    return new_mean, m2 / (count + bc), tot

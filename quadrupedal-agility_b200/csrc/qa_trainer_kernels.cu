@@ -99,6 +99,7 @@ __global__ void __launch_bounds__(256) k_clip_adam(QaClipAdamArgs a) {
     float coef = 1.f;
     if (a.max_grad_norm > 0.f) coef = fminf(a.max_grad_norm / (total_norm + 1e-6f), 1.0f);   // clip_grad_norm_
     const float gs = a.grad_scale * coef;
+    const float wd = a.weight_decay;
     const int step = *a.step;
     const float lr = *a.lr;
     const float bc1 = 1.f - powf(a.beta1, (float)step);
@@ -112,10 +113,10 @@ __global__ void __launch_bounds__(256) k_clip_adam(QaClipAdamArgs a) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         float4 p = p4[i], m = m4[i], v = v4[i];
         const float4 g = g4[i];
-        p.x = adam_one(p.x, g.x * gs, m.x, v.x, a.beta1, a.beta2, a.eps, step_size, bc2_sqrt);
-        p.y = adam_one(p.y, g.y * gs, m.y, v.y, a.beta1, a.beta2, a.eps, step_size, bc2_sqrt);
-        p.z = adam_one(p.z, g.z * gs, m.z, v.z, a.beta1, a.beta2, a.eps, step_size, bc2_sqrt);
-        p.w = adam_one(p.w, g.w * gs, m.w, v.w, a.beta1, a.beta2, a.eps, step_size, bc2_sqrt);
+        p.x = adam_one(p.x, g.x * gs + wd * p.x, m.x, v.x, a.beta1, a.beta2, a.eps, step_size, bc2_sqrt);
+        p.y = adam_one(p.y, g.y * gs + wd * p.y, m.y, v.y, a.beta1, a.beta2, a.eps, step_size, bc2_sqrt);
+        p.z = adam_one(p.z, g.z * gs + wd * p.z, m.z, v.z, a.beta1, a.beta2, a.eps, step_size, bc2_sqrt);
+        p.w = adam_one(p.w, g.w * gs + wd * p.w, m.w, v.w, a.beta1, a.beta2, a.eps, step_size, bc2_sqrt);
         p4[i] = p;
         m4[i] = m;
         v4[i] = v;
@@ -123,7 +124,7 @@ __global__ void __launch_bounds__(256) k_clip_adam(QaClipAdamArgs a) {
     if (blockIdx.x == 0 && threadIdx.x < (a.numel & 3)) {
         const long long i = (n4 << 2) + threadIdx.x;
         float m = a.exp_avg[i], v = a.exp_avg_sq[i];
-        a.params[i] = adam_one(a.params[i], a.grads[i] * gs, m, v, a.beta1, a.beta2, a.eps, step_size, bc2_sqrt);
+        a.params[i] = adam_one(a.params[i], a.grads[i] * gs + wd * a.params[i], m, v, a.beta1, a.beta2, a.eps, step_size, bc2_sqrt);
         a.exp_avg[i] = m;
         a.exp_avg_sq[i] = v;
     }

@@ -120,7 +120,8 @@ class QaGatherArgs(C.Structure):
 class QaClipAdamArgs(C.Structure):
     _fields_ = [("numel", C.c_int64), ("params", vp), ("grads", vp), ("exp_avg", vp), ("exp_avg_sq", vp),
                 ("lr", vp), ("step", vp), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
-                ("max_grad_norm", C.c_float), ("grad_scale", C.c_float), ("grad_norm_out", vp), ("workspace", vp)]
+                ("max_grad_norm", C.c_float), ("grad_scale", C.c_float), ("grad_norm_out", vp), ("workspace", vp),
+                ("weight_decay", C.c_float)]
 
 
 class QaLinearArgs(C.Structure):

@@ -177,7 +177,7 @@ def gather_minibatch(indices, srcs, dsts) -> None:
 
 # ---- K8 ---------------------------------------------------------------------------------------
 def clip_adam(params, grads, exp_avg, exp_avg_sq, lr, step, workspace, beta1=0.9, beta2=0.999, eps=1e-8,
-              max_grad_norm=1.0, grad_scale=1.0, grad_norm_out=None) -> None:
+              max_grad_norm=1.0, grad_scale=1.0, grad_norm_out=None, weight_decay=0.0) -> None:
     """clip_grad_norm_ + Adam.step on a flat fp32 buffer (gail.py:409-412); `lr` (f32) and `step` (i32) are
     1-element device tensors."""
     lib = _abi.load()
@@ -185,7 +185,8 @@ def clip_adam(params, grads, exp_avg, exp_avg_sq, lr, step, workspace, beta1=0.9
     a = _abi.QaClipAdamArgs(params.numel(), _p(params, f, "params"), _p(grads, f, "grads"), _p(exp_avg, f, "exp_avg"),
                             _p(exp_avg_sq, f, "exp_avg_sq"), _p(lr, f, "lr"), _p(step, torch.int32, "step"),
                             float(beta1), float(beta2), float(eps), float(max_grad_norm), float(grad_scale),
-                            _p(grad_norm_out, f, "grad_norm_out"), _p(workspace, torch.float64, "workspace"))
+                            _p(grad_norm_out, f, "grad_norm_out"), _p(workspace, torch.float64, "workspace"),
+                            float(weight_decay))
     _abi.check(lib.qa_clip_adam(C.byref(a), _stream()), "qa_clip_adam")
     _count(2)
 

@@ -11,14 +11,18 @@ for one B200 per process:
   * multi-GPU: envs are sharded one shard per rank; the only collectives are an in-place NCCL all-reduce of
     the flat gradient buffers and of the scalar KL, both before the fused optimiser pass.
 
-The semi-supervised InfoGAIL discriminator update (`update_ss_info_gail`, :415-541) and DAgger
-(`update_dagger`, :543-575) are SURVEY.md 8(f) "next" rows and are not part of this path yet.
+The semi-supervised InfoGAIL discriminator update (`update_ss_info_gail`, :415-541) is provided
+with the reference's signature: flat discriminator parameters, the reference's three weight-decayed Adam optimisers on
+K8, the double-backward gradient penalty on torch ops, the running normaliser merged on the device instead of through
+numpy; `update_disc` drives it over the replay buffer and the expert sets.  DAgger (`update_dagger`, :543-575) is not
+part of this path yet.
 """
 import os
 from typing import Optional
 
 import torch
 import torch.distributed as dist
+import torch.nn.functional as F
 
 from .. import ops
 from .. import dist as qdist
@@ -49,22 +53,26 @@ class ReplayBuffer:
 
 
 class FlatAdam:
-    """Adam state for one flat parameter buffer; `step()` = clip_grad_norm_ + Adam.step through K8."""
+    """Adam state for one flat parameter buffer (or a contiguous slice [lo, hi) of it); `step()` = clip_grad_norm_ +
+    Adam.step through K8.  `weight_decay` follows torch.optim.Adam (added to the gradient)."""
 
-    def __init__(self, flat, lr: float, max_grad_norm: float, betas=(0.9, 0.999), eps=1e-8):
+    def __init__(self, flat, lr: float, max_grad_norm: float, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, lo=0, hi=None):
         dev = flat.data.device
         self.flat = flat
-        self.exp_avg = torch.zeros_like(flat.data)
-        self.exp_avg_sq = torch.zeros_like(flat.data)
+        hi = flat.data.numel() if hi is None else hi
+        self.lo, self.hi = lo, hi
+        self.exp_avg = torch.zeros(hi - lo, device=dev)
+        self.exp_avg_sq = torch.zeros(hi - lo, device=dev)
         self.lr = torch.full((1,), lr, device=dev, dtype=torch.float32)
         self.step_count = torch.zeros(1, device=dev, dtype=torch.int32)
         self.grad_norm = torch.zeros(1, device=dev, dtype=torch.float32)
         self.ws = torch.zeros(2, device=dev, dtype=torch.float64)
-        self.betas, self.eps, self.max_grad_norm = betas, eps, max_grad_norm
+        self.betas, self.eps, self.max_grad_norm, self.weight_decay = betas, eps, max_grad_norm, weight_decay
 
     def step(self, grad_scale: float = 1.0):
-        ops.clip_adam(self.flat.data, self.flat.grad, self.exp_avg, self.exp_avg_sq, self.lr, self.step_count, self.ws,
-                      self.betas[0], self.betas[1], self.eps, self.max_grad_norm, grad_scale, self.grad_norm)
+        ops.clip_adam(self.flat.data[self.lo:self.hi], self.flat.grad[self.lo:self.hi], self.exp_avg, self.exp_avg_sq, self.lr,
+                      self.step_count, self.ws, self.betas[0], self.betas[1], self.eps, self.max_grad_norm, grad_scale,
+                      self.grad_norm, self.weight_decay)
 
     # torch.optim-compatible state for checkpoints
     def state_dict(self):
@@ -135,6 +143,9 @@ class SSInfoGAIL:
         self.device, self.env = device, env
         self.desired_kl, self.schedule = desired_kl, schedule
         self.lr_disc, self.lr_q, self.min_std = lr_disc, lr_q, min_std
+        self.disc_coef, self.disc_logit_reg, self.disc_grad_penalty = disc_coef, disc_logit_reg, disc_grad_penalty
+        self.disc_weight_decay, self.us_coef, self.ss_coef = disc_weight_decay, us_coef, ss_coef
+        self.prior_soft_coef, self.info_max_coef, self.begin_rim = prior_soft_coef, info_max_coef, begin_rim
         self.dim_c = env.dim_c
         self.disc_loss_function = disc_loss_function
         self.disc_history_len, self.disc_obs_len, self.num_disc_obs = disc_history_len, disc_obs_len, num_disc_obs
@@ -279,6 +290,130 @@ class SSInfoGAIL:
     def compute_returns(self, last_critic_obs):
         last_values = self.actor_critic.evaluate(last_critic_obs)
         self.storage.compute_returns(last_values, self.gamma, self.lam)
+
+    # ---- discriminator update (gail.py:415-541) ---------------------------------------------------------
+    def _init_disc_update(self):
+        """Flat discriminator parameters and the reference's three Adam optimisers (gail.py:107-128): optim_d = trunk + head,
+        optim_q_eps = trunk + encoder_eps, optim_q_c = trunk + classifier, weight_decay 1e-3 each -- the trunk is stepped
+        by all three, in that order, with separate moments."""
+        d = self.disc
+        self.disc_flat = d.flatten_parameters()
+        sl = self.disc_flat.slices
+        lo = lambda n: sl[n][0]                                                # noqa: E731
+        end = lambda n: sl[n][0] + sl[n][1]                                    # noqa: E731
+        t0, t1 = lo("trunk.0.weight"), end("trunk.2.bias")
+        l0, l1 = lo("linear.weight"), end("linear.bias")
+        c0, c1 = lo("classifier.weight"), end("classifier.bias")
+        e0, e1 = lo("encoder_eps.weight"), end("encoder_eps.bias")
+        assert t1 == l0, "trunk and head must be adjacent in the flat layout"
+        mk = lambda lr, a, b: FlatAdam(self.disc_flat, lr, 0.0, weight_decay=1e-3, lo=a, hi=b)      # noqa: E731  no clipping
+        self.optim_d = [mk(self.lr_disc, t0, l1)]
+        self.optim_q_eps = [mk(self.lr_q, t0, t1), mk(self.lr_q, e0, e1)]
+        self.optim_q_c = [mk(self.lr_q, t0, t1), mk(self.lr_q, c0, c1)]
+        self._disc_stats = torch.zeros(11, device=self.device)
+        self.info_max_coef_on = 0.0
+        self._info_max_coef_on = torch.zeros((), device=self.device)
+        if not torch.is_tensor(getattr(self.env, "prior_parameters", None)):
+            self.env.prior_parameters = torch.full((self.dim_c,), 1.0 / self.dim_c, device=self.device)
+
+    def _disc_prepare(self, x):
+        """gail.py:423-452: task-obs weighting, per-step multipliers, normalisation (no grad)."""
+        L, W = self.disc_obs_len, self.num_disc_obs
+        x = x.view(len(x), L, -1).clone()
+        if self.env.task_obs_weight_decay:
+            x[:, :, 3:9] *= self.env.task_obs_weight
+            x[:, :, 33:] *= self.env.task_obs_weight
+        x = x[:, -L:, :].reshape(len(x), -1)
+        if self.obs_disc_weight_step != 0.0:
+            x = x * (torch.arange(L, dtype=torch.float32, device=x.device) * self.obs_disc_weight_step + 1).repeat_interleave(W)
+        if self.disc_normalizer is not None:
+            with torch.no_grad():
+                x = self.disc_normalizer.normalize_torch(x, x.device)
+        return x
+
+    def update_ss_info_gail(self, sample_disc_policy, sample_disc_expert_lb, sample_disc_expert_ulb):
+        """One discriminator minibatch step with the reference's signature and 11-tuple (device tensors, no host sync).
+        MSELoss / BCEWithLogitsLoss / WassersteinLoss discriminator losses as in :471-481."""
+        if getattr(self, "disc_flat", None) is None:
+            self._init_disc_update()
+        d, env = self.disc, self.env
+        policy_state, policy_latent_eps, policy_latent_c = sample_disc_policy
+        expert_state_lb, label_exp_lb = sample_disc_expert_lb
+        policy_state = self._disc_prepare(policy_state)
+        expert_state_lb = self._disc_prepare(expert_state_lb)
+        expert_state_ulb = self._disc_prepare(sample_disc_expert_ulb)
+        _, _, pred_c_lb = d.forward_torch(expert_state_lb)
+        ss_loss = F.cross_entropy(pred_c_lb, label_exp_lb)                      # on the soft-maxed output, as the reference
+        lab_pi = torch.argmax(policy_latent_c, dim=-1)
+        logits_pi, eps, pred_c = d.forward_torch(policy_state)
+        logits_exp, _, pred_c_ulb = d.forward_torch(expert_state_ulb)
+        with torch.no_grad():                                                   # prior estimate :462-464
+            env.prior_parameters.mul_(1 - self.prior_soft_coef).add_(pred_c_ulb.mean(dim=0) * self.prior_soft_coef)
+        info_max_loss = torch.mean(-torch.sum(pred_c_ulb * torch.log(pred_c_ulb + 1e-20), dim=-1))
+        if self.disc_loss_function == "BCEWithLogitsLoss":
+            disc_exp_loss = F.binary_cross_entropy_with_logits(logits_exp, torch.ones_like(logits_exp))
+            disc_pi_loss = F.binary_cross_entropy_with_logits(logits_pi, torch.zeros_like(logits_pi))
+        elif self.disc_loss_function == "MSELoss":
+            disc_exp_loss = F.mse_loss(logits_exp, torch.ones_like(logits_exp))
+            disc_pi_loss = F.mse_loss(logits_pi, -1 * torch.ones_like(logits_pi))
+        elif self.disc_loss_function == "WassersteinLoss":
+            disc_exp_loss, disc_pi_loss = -logits_exp.mean(), logits_pi.mean()
+        else:
+            raise ValueError("Unexpected loss function specified")
+        disc_loss = 0.5 * (disc_pi_loss + disc_exp_loss)
+        us_loss = F.l1_loss(eps, policy_latent_eps)
+        disc_logit_loss = torch.sum(torch.square(d.get_disc_logit_weights()))
+        sample_expert = expert_state_ulb.clone().requires_grad_(True)           # gradient penalty :492-502
+        h = F.relu(F.linear(F.relu(F.linear(sample_expert, d.trunk[0].weight, d.trunk[0].bias)), d.trunk[2].weight, d.trunk[2].bias))
+        dd = F.linear(h, d.linear.weight, d.linear.bias)
+        (g,) = torch.autograd.grad(dd, sample_expert, grad_outputs=torch.ones_like(dd), create_graph=True, retain_graph=True)
+        grad_pen_loss = torch.mean(torch.sum(torch.square(g), dim=-1))
+        disc_weight_decay = torch.sum(torch.square(torch.cat(d.get_disc_weights(), dim=-1)))
+        loss = (self.ss_coef * ss_loss + self._info_max_coef_on * info_max_loss + self.disc_coef * disc_loss +
+                self.us_coef * us_loss + self.disc_grad_penalty * grad_pen_loss + self.disc_logit_reg * disc_logit_loss +
+                self.disc_weight_decay * disc_weight_decay)
+        self.disc_flat.zero_grad()
+        loss.backward()
+        for o in self.optim_d + self.optim_q_eps + self.optim_q_c:               # :519-521
+            o.step()
+        ac = self.actor_critic
+        if not ac.fixed_std and self.min_std is not None:                       # :523-524
+            ac.std.data.clamp_(min=self.min_std)
+        if self.disc_normalizer is not None:                                    # :527-529 (of the NORMALISED batches, as there)
+            for x in (policy_state, expert_state_lb, expert_state_ulb):
+                self.disc_normalizer.update_torch(x)
+        with torch.no_grad():
+            acc_lb = torch.mean((torch.argmax(pred_c_lb, dim=-1) == label_exp_lb).float())
+            acc_pi, acc_exp = (logits_pi < 0).float().mean(), (logits_exp > 0).float().mean()
+            acc_ulb = torch.mean((torch.argmax(pred_c, dim=-1) == lab_pi).float())
+        return (ss_loss.detach(), info_max_loss.detach(), disc_loss.detach(), us_loss.detach(), grad_pen_loss.detach(),
+                disc_logit_loss.detach(), disc_weight_decay.detach(), acc_lb, acc_pi, acc_exp, acc_ulb)
+
+    def update_disc(self, expert, num_updates=None):
+        """The discriminator half of SSInfoGAIL.update (gail.py:258-300): `4 * epochs * minibatches` minibatch steps of
+        `T*N / that` samples each from the policy replay buffer and the labelled / unlabelled expert sets
+        (`expert.preloaded_s_lb (n,98)`, `expert.preloaded_label (n,)`, `expert.preloaded_s_ulb (n,98)` as in
+        motion_loader.py:513-526).  Index draws (np.random.choice with replacement there) are torch.randint on the device;
+        the per-minibatch statistics are accumulated on the device and read back once.  Returns the reference's 11 means."""
+        if getattr(self, "disc_flat", None) is None:
+            self._init_disc_update()
+        st, ds = self.storage, self.disc_storage
+        n_mb = self.num_learning_epochs * self.num_mini_batches * 4 if num_updates is None else num_updates
+        mb = st.num_envs * st.num_transitions_per_env // (self.num_learning_epochs * self.num_mini_batches * 4)
+        if self.learning_steps >= self.begin_rim:                               # :251-253
+            self.info_max_coef_on = min(self.info_max_coef * (self.learning_steps - self.begin_rim) / 10000, self.info_max_coef)
+        self._info_max_coef_on.fill_(self.info_max_coef_on)
+        dev = self.device
+        i_pi = torch.randint(ds.num_samples, (n_mb, mb), device=dev)
+        i_lb = torch.randint(expert.preloaded_s_lb.shape[0], (n_mb, mb), device=dev)
+        i_ulb = torch.randint(expert.preloaded_s_ulb.shape[0], (n_mb, mb), device=dev)
+        self._disc_stats.zero_()
+        for k in range(n_mb):
+            out = self.update_ss_info_gail((ds.states[i_pi[k]], ds.latent_eps[i_pi[k]], ds.latent_c[i_pi[k]]),
+                                           (expert.preloaded_s_lb[i_lb[k]], expert.preloaded_label[i_lb[k]]),
+                                           expert.preloaded_s_ulb[i_ulb[k]])
+            self._disc_stats += torch.stack(out)
+        return tuple((self._disc_stats / n_mb).tolist())
 
     # ---- PPO minibatch step ------------------------------------------------------------------------------
     def _alloc_minibatch(self, mb_size):

@@ -305,6 +305,19 @@ class Discriminator(nn.Module):
         nn.init.uniform_(self.linear.weight, -1.0, 1.0)
         nn.init.zeros_(self.linear.bias)
 
+    def flatten_parameters(self) -> FlatParams:
+        self.flat = FlatParams(self)
+        return self.flat
+
+    def forward_torch(self, x):
+        """forward() on plain torch ops: the discriminator update needs double backward (gradient penalty, gail.py:492-502),
+        which the tcgen05 autograd nodes do not provide; its batches are 1 228 rows, launch-bound either way."""
+        h = F.relu(F.linear(F.relu(F.linear(x, self.trunk[0].weight, self.trunk[0].bias)), self.trunk[2].weight, self.trunk[2].bias))
+        d = F.linear(h, self.linear.weight, self.linear.bias)
+        eps = F.linear(h, self.encoder_eps.weight, self.encoder_eps.bias)
+        c = torch.softmax(F.linear(h, self.classifier.weight, self.classifier.bias), -1)
+        return d, eps, torch.clamp(c, 1e-20, torch.inf)
+
     def forward(self, x):
         x = run_mlp(self.trunk, x)
         d = linear_act(x, self.linear.weight, self.linear.bias, None)

@@ -32,6 +32,7 @@ class RunningMeanStd(object):
         self.var = m2 / tot
         self.count = tot
         self.__dict__.pop("_dev_cache", None)
+        self.__dict__.pop("_dev_state", None)
 
 
 class Normalizer(RunningMeanStd):
@@ -57,9 +58,49 @@ class Normalizer(RunningMeanStd):
         mean, std = self.device_moments(device)
         return torch.clamp((input - mean) / std, -self.clip_obs, self.clip_obs)
 
+    # ---- device-side running moments (the reference round-trips every batch through numpy: 240 D2H syncs per iteration,
+    #      gail.py:527-529) ------------------------------------------------------------------------------------------
+    def _device_state(self, device):
+        st = self.__dict__.get("_dev_state")
+        if st is None or st[0] != str(device):
+            mean32, std32 = self.device_moments(device)
+            st = (str(device), torch.tensor(self.mean, device=device, dtype=torch.float64),
+                  torch.tensor(self.var, device=device, dtype=torch.float64),
+                  torch.tensor(float(self.count), device=device, dtype=torch.float64), mean32, std32)
+            self.__dict__["_dev_state"] = st
+        return st
+
+    @torch.no_grad()
+    def update_torch(self, x: torch.Tensor) -> None:
+        """RunningMeanStd.update (utils.py:63-83) on the device, float64 merge; refreshes the float32 (mean, std) that
+        `normalize_torch` / K18 read IN PLACE (fixed addresses: CUDA-graph safe).  Call `sync_host()` before reading
+        `.mean / .var / .count` or pickling."""
+        _, mean, var, count, mean32, std32 = self._device_state(x.device)
+        bm = x.mean(dim=0).double()                       # numpy's mean / var of a float32 batch are float32
+        bv = x.var(dim=0, unbiased=False).double()
+        bc = float(x.shape[0])
+        delta = bm - mean
+        tot = count + bc
+        m2 = var * count + bv * bc + delta.square() * count * bc / tot
+        mean.add_(delta * bc / tot)
+        var.copy_(m2 / tot)
+        count.copy_(tot)
+        mean32.copy_(mean.float())
+        std32.copy_(torch.sqrt((var + self.epsilon).float()))
+        self.__dict__["_dev_dirty"] = True
+
+    def sync_host(self) -> None:
+        st = self.__dict__.get("_dev_state")
+        if st is not None and self.__dict__.get("_dev_dirty"):
+            self.mean, self.var, self.count = st[1].cpu().numpy(), st[2].cpu().numpy(), float(st[3].item())
+            self.__dict__["_dev_dirty"] = False
+
     def __getstate__(self):
+        self.sync_host()
         d = dict(self.__dict__)
         d.pop("_dev_cache", None)
+        d.pop("_dev_state", None)
+        d.pop("_dev_dirty", None)
         return d
 
 

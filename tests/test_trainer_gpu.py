@@ -310,3 +310,60 @@ def test_fused_rollout_step_matches_torch_rollout_step():
     assert_close("disc history", b["hist"], a["hist"])
     assert_close("replay states", b["replay"], a["replay"])
     assert_close("replay eps", b["replay_eps"], a["replay_eps"])
+
+
+def test_discriminator_update_matches_reference_golden():
+    """Two consecutive `update_ss_info_gail` steps (gail.py:415-541) against the numbers the UNMODIFIED reference
+    produced (oracle/gen_golden_disc.py): the 11 returned statistics, post-update parameters (three interleaved Adam
+    optimisers with weight decay on the shared trunk), running-normaliser moments, prior estimate, std floor."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    z = np.load(f"{GOLD}/trainer_disc_seed3.npz")
+    g = {k: torch.from_numpy(z[k]) for k in z.files}
+    alg, env, norm = build(synthetic.make_weights(3))
+    env.task_obs_weight, env.prior_parameters = 0.8, torch.full((5,), 0.2, device=DEV)
+    norm.count = 5000.0
+    alg.min_std = g["in.min_std"].to(DEV)
+    with torch.no_grad():
+        alg.actor_critic.std.copy_(g["in.std0"].to(DEV))
+    alg._init_disc_update()
+    alg._info_max_coef_on.fill_(0.3)
+    dev = lambda k: g[k].to(DEV)                                               # noqa: E731
+    names = ("ss_loss", "info_max_loss", "disc_loss", "us_loss", "grad_pen_loss", "disc_logit_loss", "disc_weight_decay",
+             "acc_lb", "acc_pi", "acc_exp", "acc_ulb")
+    for step in range(2):
+        out = alg.update_ss_info_gail((dev("in.pol"), dev("in.pol_eps"), dev("in.pol_c")), (dev("in.exp_lb"), dev("in.lab_lb")),
+                                      dev("in.exp_ulb"))
+        for k, v in zip(names, out):
+            assert_close(f"s{step}.{k}", v, g[f"s{step}.{k}"], rtol=NET_RTOL, atol=NET_ATOL)
+    stride = int(g["in.param_stride"])
+    flat = torch.cat([v.reshape(-1) for v in alg.disc.state_dict().values()])[::stride].cpu()
+    d = (flat - g["post.params_sampled"]).abs()
+    assert float(d.max()) <= 2.5e-3 and float((d > 2e-5).float().mean()) < 1e-2, (float(d.max()), float((d > 2e-5).float().mean()))
+    norm.sync_host()
+    assert_close("normaliser mean", torch.from_numpy(norm.mean), g["post.norm_mean"], rtol=1e-5, atol=1e-8)
+    assert_close("normaliser var", torch.from_numpy(norm.var), g["post.norm_var"], rtol=1e-5, atol=1e-8)
+    assert abs(norm.count - float(g["post.norm_count"])) < 1e-6
+    assert_close("prior", env.prior_parameters, g["post.prior"], rtol=1e-5, atol=1e-8)
+    assert_close("std floor", alg.actor_critic.std.detach(), g["post.std"])
+
+
+def test_update_disc_runs_over_replay_and_expert_sets():
+    """`update_disc` end to end: 16 minibatch steps over a filled replay buffer and synthetic expert sets; finite
+    statistics, parameters move, the normaliser count grows by 3 x minibatch x steps."""
+    alg, env, norm = build(synthetic.make_weights(3), n_envs=64)
+    env.task_obs_weight, env.prior_parameters = 1.0, torch.full((5,), 0.2, device=DEV)
+    gen = torch.Generator().manual_seed(4)
+    alg.disc_storage.insert(torch.randn(900, 98, generator=gen).to(DEV), torch.rand(900, 1, generator=gen).to(DEV),
+                            torch.nn.functional.one_hot(torch.randint(0, 5, (900,), generator=gen), 5).float().to(DEV))
+    expert = types.SimpleNamespace(preloaded_s_lb=torch.randn(500, 98, generator=gen).to(DEV),
+                                   preloaded_label=torch.randint(0, 5, (500,), generator=gen).to(DEV),
+                                   preloaded_s_ulb=torch.randn(700, 98, generator=gen).to(DEV))
+    before = torch.cat([v.reshape(-1) for v in alg.disc.state_dict().values()]).clone()
+    c0 = norm.count
+    stats = alg.update_disc(expert, num_updates=16)
+    assert len(stats) == 11 and all(np.isfinite(s) for s in stats)
+    after = torch.cat([v.reshape(-1) for v in alg.disc.state_dict().values()])
+    assert float((after - before).abs().max()) > 1e-5
+    norm.sync_host()
+    mb = 64 * 24 // (5 * 4 * 4)
+    assert abs(norm.count - (c0 + 3 * mb * 16)) < 1e-6
