@@ -184,6 +184,9 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = T_STEPS * cfg.num_envs * world / (float(t.item()) / args.steps * 1e-3)
 
+    disc_ms = None
+    if world == 1:                                  # SURVEY 8f-1, reported beside the metric (not part of it): one full
+        disc_ms = it.time_disc_update()             # discriminator update = 80 minibatch steps of 1228 x 3 samples
     k2_ms, k2_launches = it.time_k2_only()          # roofline leg: the 24 K2 launches of a rollout, alone in a graph
     if rank == 0:
         pk, pk_src = peaks()
@@ -211,6 +214,8 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": K2_BYTES_PER_ENV * cfg.num_envs, "traffic": k2_traffic()},
             "clocks": clocks,
         }
+        if disc_ms is not None:
+            line["disc_update_ms"] = disc_ms
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)

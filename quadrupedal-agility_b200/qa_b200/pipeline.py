@@ -195,6 +195,28 @@ class BbcIteration:
             total += e0.elapsed_time(e1)
         return total, reps * self.T
 
+    def time_disc_update(self, reps=3):
+        """Device milliseconds of one full discriminator update (gail.py:284-300: 4 x epochs x minibatches steps) over the
+        replay buffer this rollout filled and synthetic expert sets of the reference's preload size (200 000 x 98)."""
+        import types
+        alg, dev = self.runner.alg, self.device
+        g = torch.Generator().manual_seed(99)
+        n = 200000
+        expert = types.SimpleNamespace(preloaded_s_lb=torch.randn(n, 98, generator=g).to(dev),
+                                       preloaded_label=torch.randint(0, 5, (n,), generator=g).to(dev),
+                                       preloaded_s_ulb=torch.randn(n, 98, generator=g).to(dev))
+        if alg.disc_storage.num_samples == 0:
+            return None
+        alg.storage.step = 0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        alg.update_disc(expert)                                  # warm-up + graph capture
+        e0.record()
+        for _ in range(reps):
+            alg.update_disc(expert)
+        e1.record()
+        e1.synchronize()
+        return e0.elapsed_time(e1) / reps
+
     def run_host(self):
         runner = self.runner
         self._rollout(host=True)

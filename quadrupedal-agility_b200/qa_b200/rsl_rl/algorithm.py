@@ -408,12 +408,63 @@ class SSInfoGAIL:
         i_lb = torch.randint(expert.preloaded_s_lb.shape[0], (n_mb, mb), device=dev)
         i_ulb = torch.randint(expert.preloaded_s_ulb.shape[0], (n_mb, mb), device=dev)
         self._disc_stats.zero_()
-        for k in range(n_mb):
-            out = self.update_ss_info_gail((ds.states[i_pi[k]], ds.latent_eps[i_pi[k]], ds.latent_c[i_pi[k]]),
-                                           (expert.preloaded_s_lb[i_lb[k]], expert.preloaded_label[i_lb[k]]),
-                                           expert.preloaded_s_ulb[i_ulb[k]])
-            self._disc_stats += torch.stack(out)
+        if self.use_cuda_graph:
+            key = (id(expert), mb, ds.states.data_ptr())
+            if getattr(self, "_disc_graph_key", None) != key:
+                self._capture_disc(expert, mb)
+                self._disc_graph_key = key
+                self._disc_stats.zero_()
+            b = self._disc_mb
+            for k in range(n_mb):
+                b["i_pi"].copy_(i_pi[k])
+                b["i_lb"].copy_(i_lb[k])
+                b["i_ulb"].copy_(i_ulb[k])
+                self._disc_graph.replay()
+                ops._count(self._disc_graph_launches)
+        else:
+            for k in range(n_mb):
+                self._disc_step(expert, i_pi[k], i_lb[k], i_ulb[k])
         return tuple((self._disc_stats / n_mb).tolist())
+
+    def _disc_step(self, expert, i_pi, i_lb, i_ulb):
+        ds = self.disc_storage
+        out = self.update_ss_info_gail((ds.states[i_pi], ds.latent_eps[i_pi], ds.latent_c[i_pi]),
+                                       (expert.preloaded_s_lb[i_lb], expert.preloaded_label[i_lb]), expert.preloaded_s_ulb[i_ulb])
+        self._disc_stats += torch.stack(out)
+
+    def _capture_disc(self, expert, mb):
+        """One discriminator minibatch step (3 x 2 gathers, ~150 torch kernels incl. the double backward, 5 K8 launches,
+        the normaliser merge) as ONE CUDA graph over static index buffers; warm-up side effects are rolled back."""
+        dev = self.device
+        z = lambda: torch.zeros(mb, dtype=torch.int64, device=dev)             # noqa: E731
+        self._disc_mb = dict(i_pi=z(), i_lb=z(), i_ulb=z())
+        b = self._disc_mb
+        if self.disc_normalizer is not None:
+            self.disc_normalizer._device_state(dev)
+        opts = self.optim_d + self.optim_q_eps + self.optim_q_c
+        state = [self.disc_flat.data, self.env.prior_parameters, self._disc_stats]
+        for o in opts:
+            state += [o.exp_avg, o.exp_avg_sq, o.step_count]
+        if not self.actor_critic.fixed_std:
+            state.append(self.actor_critic.std.data)
+        if self.disc_normalizer is not None:
+            state += list(self.disc_normalizer._device_state(dev)[1:])
+        snap = [t.clone() for t in state]
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(3):
+                self._disc_step(expert, b["i_pi"], b["i_lb"], b["i_ulb"])
+        torch.cuda.current_stream().wait_stream(s)
+        before = ops.launches
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._disc_step(expert, b["i_pi"], b["i_lb"], b["i_ulb"])
+        self._disc_graph, self._disc_graph_launches = g, ops.launches - before
+        for t, v in zip(state, snap):
+            t.copy_(v)
+        if self.disc_normalizer is not None:
+            self.disc_normalizer.__dict__["_dev_dirty"] = True
 
     # ---- PPO minibatch step ------------------------------------------------------------------------------
     def _alloc_minibatch(self, mb_size):
@@ -563,10 +614,12 @@ class SSInfoGAIL:
                          self.optim_ac.step_count, self.optim_estimator.step_count, self._stats), snap):
             t.copy_(v)
 
-    def update(self, indices: Optional[torch.Tensor] = None):
-        """PPO part of SSInfoGAIL.update (:231-326): num_learning_epochs x num_mini_batches minibatch steps over
-        ONE permutation.  Returns the reference's first six means (surrogate, value, bound, entropy, priv_reg,
-        estimator); the discriminator statistics are not produced (next row)."""
+    def update(self, indices: Optional[torch.Tensor] = None, expert=None):
+        """SSInfoGAIL.update (:231-326): num_learning_epochs x num_mini_batches PPO minibatch steps over ONE permutation,
+        then -- when `expert` (an object with preloaded_s_lb / preloaded_label / preloaded_s_ulb, e.g. the reference's
+        MotionLoader) is given -- the 4x as many discriminator minibatch steps (:284-300).  Returns the reference's
+        first six means (surrogate, value, bound, entropy, priv_reg, estimator), followed by the eleven discriminator
+        means when the discriminator was updated."""
         st = self.storage
         batch = st.num_envs * st.num_transitions_per_env
         mb_size = batch // self.num_mini_batches
@@ -598,6 +651,9 @@ class SSInfoGAIL:
         n = self.num_learning_epochs * self.num_mini_batches
         vals = (self._stats / n).tolist()                      # the one host sync of the update
         self.last_stats = dict(zip(STAT_NAMES, vals))
+        disc_stats = ()
+        if expert is not None and self.world_size == 1:
+            disc_stats = self.update_disc(expert)
         st.clear()
         self.priv_reg_counter += 1
-        return tuple(vals[:6])
+        return tuple(vals[:6]) + tuple(disc_stats)

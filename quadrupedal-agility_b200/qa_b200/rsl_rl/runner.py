@@ -124,7 +124,8 @@ class OnPolicyRunner:
                 collection_time = stop - start
                 start = stop
                 alg.compute_returns(critic_obs)
-            stats = alg.update()
+            expert = alg.motion_loader if hasattr(alg.motion_loader, "preloaded_s_lb") else None
+            stats = alg.update(expert=expert)
             if env.task_obs_weight_decay_steps:
                 env.task_obs_weight = max(0, env.task_obs_weight - 1.0 / env.task_obs_weight_decay_steps)
             learn_time = time.time() - start

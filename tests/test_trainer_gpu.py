@@ -367,3 +367,27 @@ def test_update_disc_runs_over_replay_and_expert_sets():
     norm.sync_host()
     mb = 64 * 24 // (5 * 4 * 4)
     assert abs(norm.count - (c0 + 3 * mb * 16)) < 1e-6
+
+
+def test_update_disc_cuda_graph_matches_eager():
+    res = []
+    for graph in (False, True):
+        alg, env, norm = build(synthetic.make_weights(3), n_envs=64)
+        alg.use_cuda_graph = graph
+        env.task_obs_weight, env.prior_parameters = 0.9, torch.full((5,), 0.2, device=DEV)
+        gen = torch.Generator().manual_seed(4)
+        alg.disc_storage.insert(torch.randn(900, 98, generator=gen).to(DEV), torch.rand(900, 1, generator=gen).to(DEV),
+                                torch.nn.functional.one_hot(torch.randint(0, 5, (900,), generator=gen), 5).float().to(DEV))
+        expert = types.SimpleNamespace(preloaded_s_lb=torch.randn(500, 98, generator=gen).to(DEV),
+                                       preloaded_label=torch.randint(0, 5, (500,), generator=gen).to(DEV),
+                                       preloaded_s_ulb=torch.randn(700, 98, generator=gen).to(DEV))
+        torch.manual_seed(11)
+        stats = alg.update_disc(expert, num_updates=6)
+        norm.sync_host()
+        res.append((stats, torch.cat([v.reshape(-1) for v in alg.disc.state_dict().values()]).clone(), norm.mean.copy(),
+                    env.prior_parameters.clone()))
+    for a, b in zip(res[0][0], res[1][0]):
+        assert abs(a - b) <= 1e-4 * abs(a) + 1e-6, (res[0][0], res[1][0])
+    assert_close("params", res[1][1], res[0][1], rtol=1e-4, atol=2e-5)
+    assert np.allclose(res[0][2], res[1][2], rtol=1e-6, atol=1e-9)
+    assert_close("prior", res[1][3], res[0][3])
