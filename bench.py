@@ -216,6 +216,8 @@ def run_ours(args):
         }
         if disc_ms is not None:
             line["disc_update_ms"] = disc_ms
+        if world == 1:
+            line["tsc_env"] = time_tsc_env(dev)
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
@@ -227,6 +229,56 @@ def run_ours(args):
         sys.stdout.flush()
         sys.stderr.flush()
         os._exit(0)
+
+
+TSC_BYTES_PER_ENV = 12634      # algorithmic bytes of the TSC post-physics pair (K16 + K17) per env-step
+
+
+def time_tsc_env(dev, n_envs=ENVS_PER_GPU, steps=T_STEPS, reps=10):
+    """Config 3 of BASELINE.json (TSC teacher, 4096 envs): the two post-physics kernels K16 + K17 of `steps` env steps
+    (distinct synthetic snapshots) replayed as one CUDA graph; returns a dict reported beside the metric."""
+    from qa_b200 import ops, synthetic
+    from qa_b200.legged_robot_tsc import LeggedRobotTSC, RecordedPhysicsTSC, TscEnvConfig
+    st = synthetic.make_tsc_static(n_envs, seed=1234)
+    snaps = [synthetic.make_tsc_snapshot(n_envs, st, seed=1234, step=t) for t in range(4)]
+    dev_snaps = [{k: v.to(dev).contiguous() for k, v in s.items() if isinstance(v, torch.Tensor)} for s in snaps]
+    env = LeggedRobotTSC(TscEnvConfig(num_envs=n_envs), RecordedPhysicsTSC(dev_snaps), st, device=dev, seed=1234)
+    env.load_state(snaps[0])
+    env.action_hl_history_buf = dev_snaps[0]["action_hl_history_buf"]
+
+    def body():
+        for _ in range(steps):
+            env.physics.refresh()
+            env.common_step_counter += 1
+            a = env._args()
+            ops.post_physics_tsc(env._const, a, "pre")
+            ops.post_physics_tsc(env._const, a, "post")
+
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        body()
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        body()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    total = 0.0
+    for _ in range(reps):
+        flush.fill_(1)
+        e0.record()
+        g.replay()
+        e1.record()
+        e1.synchronize()
+        total += e0.elapsed_time(e1)
+    us = total / (reps * steps) * 1e3
+    pk, _ = peaks()
+    achieved = TSC_BYTES_PER_ENV * n_envs / (us * 1e-6) / 1e9
+    return {"workload": f"tsc_go2_agility_teacher_{n_envs}: qa_post_physics_tsc_pre + _post per env step", "us_per_step": us,
+            "env_steps_per_sec_env_only": n_envs / (us * 1e-6), "achieved_gbs": achieved, "frac_of_hbm_peak": achieved / pk["hbm_gbs"],
+            "algorithmic_bytes_per_env_step": TSC_BYTES_PER_ENV}
 
 
 def cpu_reference_sample(n_envs, rollout_steps, minibatch_steps, threads):
