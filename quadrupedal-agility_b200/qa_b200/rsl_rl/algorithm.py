@@ -14,8 +14,8 @@ for one B200 per process:
 The semi-supervised InfoGAIL discriminator update (`update_ss_info_gail`, :415-541) is provided
 with the reference's signature: flat discriminator parameters, the reference's three weight-decayed Adam optimisers on
 K8, the double-backward gradient penalty on torch ops, the running normaliser merged on the device instead of through
-numpy; `update_disc` drives it over the replay buffer and the expert sets.  DAgger (`update_dagger`, :543-575) is not
-part of this path yet.
+numpy; `update_disc` drives it over the replay buffer and the expert sets.  DAgger (`update_dagger`, :543-575) fits the
+history encoder on its slice of the flat buffer.
 """
 import os
 from typing import Optional
@@ -290,6 +290,49 @@ class SSInfoGAIL:
     def compute_returns(self, last_critic_obs):
         last_values = self.actor_critic.evaluate(last_critic_obs)
         self.storage.compute_returns(last_values, self.gamma, self.lam)
+
+    # ---- DAgger: history-encoder adaptation (gail.py:543-575) --------------------------------------------------------
+    def update_dagger(self, indices: Optional[torch.Tensor] = None):
+        """Fits the history encoder to the (frozen) privileged-latent encoder over the stored rollout: per minibatch
+        loss = mean ||priv_latent - hist_latent||_2 (K12 forward+backward), clip_grad_norm_ over the encoder's parameters
+        and Adam through K8 on the encoder's slice of the flat buffer.  The privileged latents do not change during the
+        update, so they are computed once for the whole rollout.  Returns the mean loss (one host sync)."""
+        st, ac = self.storage, self.actor_critic
+        p, e, l, h = self.num_prop, self.num_explicit, self.num_latent, self.num_hist * self.num_prop
+        if getattr(self, "optim_hist_encoder", None) is None:
+            names = [n for n in self.ac_flat.slices if n.startswith("history_encoder.")]
+            lo = min(self.ac_flat.slices[n][0] for n in names)
+            hi = max(self.ac_flat.slices[n][0] + self.ac_flat.slices[n][1] for n in names)
+            self.optim_hist_encoder = FlatAdam(self.ac_flat, float(self.optim_estimator.lr.item()), self.max_grad_norm, lo=lo, hi=hi)
+            self._dagger_loss = torch.zeros(1, device=self.device)
+        opt = self.optim_hist_encoder
+        flat_obs = st.observations.flatten(0, 1)
+        batch = flat_obs.shape[0]
+        mb_size = batch // self.num_mini_batches
+        if indices is None:
+            indices = torch.randperm(self.num_mini_batches * mb_size, device=self.device)
+        with torch.no_grad():
+            priv_all = ac.infer_priv_latent(flat_obs[:, p + e:p + e + l])
+        total = torch.zeros((), device=self.device)
+        fused = self.fused_loss
+        for _ in range(self.num_learning_epochs):
+            for i in range(self.num_mini_batches):
+                idx = indices[i * mb_size:(i + 1) * mb_size]
+                obs_hist = flat_obs[idx][:, p + e + l:p + e + l + h]
+                hist_latent = ac.infer_hist_latent(obs_hist)                     # with grad: torch modules (Linear / Conv1d)
+                priv = priv_all[idx]
+                if fused:
+                    loss = _RowLossFused.apply(hist_latent, priv, 1, self._dagger_loss)
+                else:
+                    loss = (priv - hist_latent).norm(p=2, dim=1).mean()
+                self.ac_flat.grad[opt.lo:opt.hi].zero_()
+                loss.backward()
+                opt.step()
+                total += loss.detach()
+        n = self.num_learning_epochs * self.num_mini_batches
+        st.clear()
+        self.priv_reg_counter += 1
+        return float(total.item()) / n
 
     # ---- discriminator update (gail.py:415-541, SURVEY 8f-1) ---------------------------------------------------------
     def _init_disc_update(self):

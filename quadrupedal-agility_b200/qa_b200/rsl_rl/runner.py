@@ -126,6 +126,8 @@ class OnPolicyRunner:
                 alg.compute_returns(critic_obs)
             expert = alg.motion_loader if hasattr(alg.motion_loader, "preloaded_s_lb") else None
             stats = alg.update(expert=expert)
+            if hist_encoding:                                                   # on_policy_runner.py:220-221
+                self.perf_hist_latent_loss = alg.update_dagger()
             if env.task_obs_weight_decay_steps:
                 env.task_obs_weight = max(0, env.task_obs_weight - 1.0 / env.task_obs_weight_decay_steps)
             learn_time = time.time() - start

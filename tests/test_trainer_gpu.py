@@ -391,3 +391,26 @@ def test_update_disc_cuda_graph_matches_eager():
     assert_close("params", res[1][1], res[0][1], rtol=1e-4, atol=2e-5)
     assert np.allclose(res[0][2], res[1][2], rtol=1e-6, atol=1e-9)
     assert_close("prior", res[1][3], res[0][3])
+
+
+@pytest.mark.parametrize("fused_loss", [False, True])
+def test_update_dagger_matches_reference_golden(fused_loss):
+    """History-encoder adaptation (gail.py:543-575): two epochs over one 64-row minibatch against the reference's mean loss
+    and post-update encoder parameters; every other actor-critic parameter must stay untouched."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    z = np.load(f"{GOLD}/trainer_dagger_seed3.npz")
+    w = synthetic.make_weights(3)
+    alg, env, norm = build(w, n_envs=64, fused_loss=fused_loss)
+    alg.num_learning_epochs, alg.num_mini_batches = 2, 1
+    alg.init_storage(64, 1, [671], [671], [12])
+    alg.storage.observations[0].copy_(torch.from_numpy(z["obs"]).to(DEV))
+    before = {k: v.clone() for k, v in alg.actor_critic.state_dict().items()}
+    loss = alg.update_dagger()
+    assert abs(loss - float(z["mean_loss"])) <= 1e-4 * abs(float(z["mean_loss"])) + 1e-6
+    sd = alg.actor_critic.state_dict()
+    enc = torch.cat([v.reshape(-1) for k, v in sd.items() if k.startswith("history_encoder.")])
+    assert_close("encoder params", enc, torch.from_numpy(z["encoder_params"]), rtol=1e-4, atol=2e-6)
+    for k, v in sd.items():
+        if not k.startswith("history_encoder."):
+            assert torch.equal(v, before[k]), k
+    assert alg.storage.step == 0
