@@ -223,3 +223,24 @@ def bbc_train_cfg() -> dict:
                        disc_hidden_units=[512, 256], min_normalized_std=[0.05, 0.02, 0.05] * 4,
                        resume=False, load_run=-1, checkpoint=-1, resume_path=None),
     }
+
+
+def tsc_train_cfg() -> dict:
+    """`class_to_dict(Go2AgilityCfgPPO())` of the reference (tsc/legged_gym/envs/base/legged_robot_config.py:365-470 +
+    go2_agility_config.py:52-60): the dict the TSC `OnPolicyRunner(env, train_cfg, ...)` takes (teacher path)."""
+    return {
+        "seed": 1,
+        "runner_class_name": "OnPolicyRunner",
+        "policy": dict(init_noise_std=1.0, continue_from_last_std=True, scan_encoder_dims=[128, 64, 32],
+                       actor_hidden_dims=[512, 256, 128], critic_hidden_dims=[512, 256, 128], priv_encoder_dims=[64],
+                       activation="elu", tanh_encoder_output=False),
+        "algorithm": dict(value_loss_coef=1.0, use_clipped_value_loss=True, clip_param=0.2, entropy_coef=0.01,
+                          num_learning_epochs=5, num_mini_batches=4, learning_rate=5.e-4, schedule="adaptive", gamma=0.99,
+                          lam=0.95, desired_kl=0.01, max_grad_norm=1.0, dagger_update_freq=20,
+                          priv_reg_coef_schedual=[0, 0.1, 500, 1000]),
+        "estimator": dict(train_with_estimated_states=True, learning_rate=1.e-4, hidden_dims=[128, 64]),
+        "runner": dict(policy_class_name="ActorCritic", algorithm_class_name="PPO", num_steps_per_env=24, max_iterations=50000,
+                       save_interval=100, experiment_name="agility", run_name="", disc_loss_function="MSELoss",
+                       reward_i_coef=0.05, reward_us_coef=0.0, reward_ss_coef=0.0, reward_t_coef=2.0,
+                       disc_hidden_units=[512, 256], bbc_path="weights/bbc/model.pt"),
+    }

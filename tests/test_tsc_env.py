@@ -130,3 +130,45 @@ def test_abi_rejects_bad_tsc_arguments():
     c.num_bodies = 40
     assert lib.qa_post_physics_tsc_pre(ctypes.byref(c), ctypes.byref(a), None) == -2
     assert lib.qa_post_physics_tsc_post(ctypes.byref(c), ctypes.byref(a), None) == -2
+
+
+@pytest.mark.gpu
+def test_tsc_runner_teacher_iteration_runs_and_rewards_match_torch_path():
+    """OnPolicyRunnerTSC (tsc on_policy_runner.py:164-300, teacher): a 4-step rollout over recorded state + GAE + PPO update.
+    The style reward of the first step is checked against the torch restatement (`Discriminator.predict_disc_reward`)."""
+    from qa_b200.config import tsc_train_cfg
+    from qa_b200.legged_robot_tsc import LeggedRobotTSC, RecordedPhysicsTSC, TscEnvConfig
+    from qa_b200.rsl_rl.tsc_runner import OnPolicyRunnerTSC
+    torch.backends.cuda.matmul.allow_tf32 = False
+    dev, N, T = "cuda:0", 256, 4
+    st = synthetic.make_tsc_static(N, 4)
+    snaps = [synthetic.make_tsc_snapshot(N, st, 4, step=t) for t in range(T + 1)]
+    dsn = [{k: v.to(dev).contiguous() for k, v in s.items() if isinstance(v, torch.Tensor)} for s in snaps]
+    env = LeggedRobotTSC(TscEnvConfig(num_envs=N), RecordedPhysicsTSC(dsn), st, device=dev, seed=4)
+    env.load_state(snaps[0])
+    env.post_physics_step()                                       # reference ctor: one post_physics_step fills the obs (:106)
+    cfg = tsc_train_cfg()
+    cfg["runner"]["num_steps_per_env"] = T
+    cfg["runner"].update(reward_i_coef=1.0, reward_us_coef=0.01, reward_ss_coef=0.2, reward_t_coef=0.2)
+    cfg["algorithm"].update(num_learning_epochs=2, num_mini_batches=2)
+    torch.manual_seed(0)
+    r = OnPolicyRunnerTSC(env, cfg, device=dev)
+    obs, obs_bbc = env.get_observations(), env.get_observations_bbc().clone()
+    r._disc_hist = torch.stack([env.get_observations_disc()] * 2, dim=1)
+    hist0, disc0 = r._disc_hist.clone(), env.get_observations_disc().clone()
+    obs, obs_bbc2, critic, infos = r.rollout_step(obs, obs_bbc, obs, {})
+    # torch restatement of the reward of that step
+    dones = env.reset_buf
+    with_term = torch.where(dones.unsqueeze(1), disc0, env.get_observations_disc())
+    hist = torch.stack([hist0[:, 1], with_term], dim=1)
+    want = r.discriminator.predict_disc_reward(env.rew_buf.unsqueeze(1), obs_bbc, hist, normalizer=r.disc_normalizer)[0]
+    want = want + r.alg.gamma * (r.alg.storage.values[0].squeeze(1) * infos["time_outs"]) if "time_outs" in infos else want
+    assert_close("style reward", r.alg.storage.rewards[0].squeeze(1), want.float(), rtol=1e-4, atol=2e-5)
+    assert r.alg.storage.actions[0].shape == (N, 19) and float(r.alg.storage.actions[0][:, 0].max()) <= 2
+    for _ in range(T - 1):
+        obs, obs_bbc2, critic, infos = r.rollout_step(obs, obs_bbc2, critic, infos)
+    assert r.alg.storage.step == T
+    r.alg.compute_returns(critic)
+    out = r.alg.update()
+    assert len(out) == 7 and all(np.isfinite(v) for v in out)
+    assert torch.isfinite(env.obs_buf).all() and torch.isfinite(env.obs_bbc_buf).all()
