@@ -26,6 +26,7 @@ import torch.nn.functional as F
 
 from .. import ops
 from .. import dist as qdist
+from . import checkpoint as ckpt
 from .storage import RolloutStorage
 
 
@@ -164,6 +165,7 @@ class SSInfoGAIL:
         self.est_flat = self.estimator.flatten_parameters()
         self.optim_ac = FlatAdam(self.ac_flat, lr_ac, max_grad_norm)
         self.optim_estimator = FlatAdam(self.est_flat, estimator_paras["learning_rate"], max_grad_norm)
+        self._lr_estimator0 = float(estimator_paras["learning_rate"])
         self.train_with_estimated_explicit = estimator_paras["train_with_estimated_explicit"]
         self.priv_reg_coef_schedual = priv_reg_coef_schedual
         self.priv_reg_counter = 0
@@ -265,7 +267,7 @@ class SSInfoGAIL:
         self.actor_critic.reset(dones)
 
     @torch.no_grad()
-    def process_env_step_fused(self, heads, obs, reward_t, dones, infos, flat_hist=None):
+    def process_env_step_fused(self, heads, obs, reward_t, dones, infos, flat_hist=None, reward_terms=None):
         """`predict_disc_reward`'s tail + `process_env_step` (discriminator.py:90-118, gail.py:199-212) with the reward
         arithmetic in ONE kernel (K19) that writes storage.rewards[step] / storage.dones[step] in place.  `heads` =
         `Discriminator.heads_forward` of the normalised history; `flat_hist` = that history (N,98) when it is not already
@@ -275,7 +277,7 @@ class SSInfoGAIL:
         tr.dones = dones
         ops.disc_reward(heads, obs, reward_t, d.dt, (d.reward_i_coef, d.reward_us_coef, d.reward_ss_coef, d.reward_t_coef),
                         st.rewards[t].view(-1), values=tr.values, time_outs=infos.get('time_outs'),
-                        gamma=self.gamma, dones=dones, dones_out=st.dones[t].view(-1))
+                        gamma=self.gamma, dones=dones, dones_out=st.dones[t].view(-1), reward_terms=reward_terms)
         if self._disc_stage is not None:
             if flat_hist is not None:
                 self._disc_stage[0][t].copy_(flat_hist)
@@ -299,13 +301,7 @@ class SSInfoGAIL:
         update, so they are computed once for the whole rollout.  Returns the mean loss (one host sync)."""
         st, ac = self.storage, self.actor_critic
         p, e, l, h = self.num_prop, self.num_explicit, self.num_latent, self.num_hist * self.num_prop
-        if getattr(self, "optim_hist_encoder", None) is None:
-            names = [n for n in self.ac_flat.slices if n.startswith("history_encoder.")]
-            lo = min(self.ac_flat.slices[n][0] for n in names)
-            hi = max(self.ac_flat.slices[n][0] + self.ac_flat.slices[n][1] for n in names)
-            self.optim_hist_encoder = FlatAdam(self.ac_flat, float(self.optim_estimator.lr.item()), self.max_grad_norm, lo=lo, hi=hi)
-            self._dagger_loss = torch.zeros(1, device=self.device)
-        opt = self.optim_hist_encoder
+        opt = self._ensure_hist_optimizer()
         flat_obs = st.observations.flatten(0, 1)
         batch = flat_obs.shape[0]
         mb_size = batch // self.num_mini_batches
@@ -334,6 +330,77 @@ class SSInfoGAIL:
         self.priv_reg_counter += 1
         return float(total.item()) / n
 
+    def _ensure_hist_optimizer(self):
+        """gail.py:99-100: Adam over the history encoder's parameters = a slice of the actor-critic's flat buffer."""
+        if getattr(self, "optim_hist_encoder", None) is None:
+            names = [n for n in self.ac_flat.slices if n.startswith("history_encoder.")]
+            lo = min(self.ac_flat.slices[n][0] for n in names)
+            hi = max(self.ac_flat.slices[n][0] + self.ac_flat.slices[n][1] for n in names)
+            self.optim_hist_encoder = FlatAdam(self.ac_flat, self._lr_estimator0, self.max_grad_norm, lo=lo, hi=hi)
+            self._dagger_loss = torch.zeros(1, device=self.device)
+        return self.optim_hist_encoder
+
+    # ---- checkpoints: the six torch.optim.Adam dicts of on_policy_runner.py:306-339 ------------------------------------
+    @staticmethod
+    def _disc_groups(disc, flat, optim_d, optim_q_eps, optim_q_c):
+        wd = lambda name: {"weight_decay": 1e-3, "momentum": 0.9, "name": name}          # noqa: E731  gail.py:109-126
+        trunk, head = ckpt.layout(flat, disc.trunk, "trunk."), ckpt.layout(flat, disc.linear, "linear.")
+        eps, cls = ckpt.layout(flat, disc.encoder_eps, "encoder_eps."), ckpt.layout(flat, disc.classifier, "classifier.")
+        return {"optim_d": [dict(adam=optim_d[0], params=trunk, extra=wd("trunk")), dict(adam=optim_d[0], params=head, extra=wd("head"))],
+                "optim_q_eps": [dict(adam=optim_q_eps[0], params=trunk, extra=wd("trunk")),
+                                dict(adam=optim_q_eps[1], params=eps, extra=wd("encoder_eps"))],
+                "optim_q_c": [dict(adam=optim_q_c[0], params=trunk, extra=wd("trunk")),
+                              dict(adam=optim_q_c[1], params=cls, extra=wd("classifier"))]}
+
+    def _optim_groups(self):
+        ac, he = self.actor_critic, self.actor_critic.history_encoder
+        g = {"optim_ac": [dict(adam=self.optim_ac, params=ckpt.layout(self.ac_flat, ac), extra={"name": "actor_critic"})],
+             "optim_hist_encoder": [dict(adam=self._ensure_hist_optimizer(), params=ckpt.layout(self.ac_flat, he, "history_encoder."))],
+             "optim_estimator": [dict(adam=self.optim_estimator, params=ckpt.layout(self.est_flat, self.estimator))]}
+        if getattr(self, "disc_flat", None) is not None:
+            g.update(self._disc_groups(self.disc, self.disc_flat, self.optim_d, self.optim_q_eps, self.optim_q_c))
+        return g
+
+    def optimizer_state_dicts(self):
+        """{'optim_ac', 'optim_hist_encoder', 'optim_estimator', 'optim_d', 'optim_q_eps', 'optim_q_c'} in the
+        `torch.optim.Adam.state_dict()` layout of the reference (parameter numbering of gail.py:96-128)."""
+        out = {k: ckpt.to_torch_state_dict(g) for k, g in self._optim_groups().items()}
+        if "optim_d" not in out and self.disc is not None:
+            pend = getattr(self, "_pending_disc_optim", None)
+            if pend is not None:                                   # loaded, not yet stepped: hand the same dicts back
+                out.update(pend)
+            else:                                                  # never stepped: zero moments of the right shapes
+                import copy
+                d = copy.deepcopy(self.disc)
+                flat = d.flatten_parameters()
+                sl = flat.slices
+                rng = lambda a, b: (sl[a][0], sl[b][0] + sl[b][1])                       # noqa: E731
+                mk = lambda lr, r: FlatAdam(flat, lr, 0.0, weight_decay=1e-3, lo=r[0], hi=r[1])   # noqa: E731
+                t = rng("trunk.0.weight", "trunk.2.bias")
+                groups = self._disc_groups(d, flat, [mk(self.lr_disc, rng("trunk.0.weight", "linear.bias"))],
+                                           [mk(self.lr_q, t), mk(self.lr_q, rng("encoder_eps.weight", "encoder_eps.bias"))],
+                                           [mk(self.lr_q, t), mk(self.lr_q, rng("classifier.weight", "classifier.bias"))])
+                out.update({k: ckpt.to_torch_state_dict(g) for k, g in groups.items()})
+        return out
+
+    def load_optimizer_state_dicts(self, d):
+        """Accepts the reference's torch.optim dicts (e.g. the shipped tsc/weights/bbc/model.pt) and this package's older flat
+        format ({'exp_avg', 'exp_avg_sq', 'lr', 'step'})."""
+        groups = self._optim_groups()
+        for k in ("optim_ac", "optim_hist_encoder", "optim_estimator", "optim_d", "optim_q_eps", "optim_q_c"):
+            sd = d.get(k)
+            if sd is None:
+                continue
+            if ckpt.is_torch_state_dict(sd):
+                if k in groups:
+                    ckpt.from_torch_state_dict(sd, groups[k])
+                else:                                              # discriminator optimisers are built on the first update
+                    if getattr(self, "_pending_disc_optim", None) is None:
+                        self._pending_disc_optim = {}
+                    self._pending_disc_optim[k] = sd
+            elif isinstance(sd, dict) and "exp_avg" in sd and k in groups and len(groups[k]) == 1:
+                groups[k][0]["adam"].load_state_dict(sd)
+
     # ---- discriminator update (gail.py:415-541, SURVEY 8f-1) ---------------------------------------------------------
     def _init_disc_update(self):
         """Flat discriminator parameters and the reference's three Adam optimisers (gail.py:107-128): optim_d = trunk + head,
@@ -358,6 +425,12 @@ class SSInfoGAIL:
         self._info_max_coef_on = torch.zeros((), device=self.device)
         if not torch.is_tensor(getattr(self.env, "prior_parameters", None)):
             self.env.prior_parameters = torch.full((self.dim_c,), 1.0 / self.dim_c, device=self.device)
+        pend = getattr(self, "_pending_disc_optim", None)
+        if pend:                                                   # optimiser state loaded before the first update
+            groups = self._disc_groups(d, self.disc_flat, self.optim_d, self.optim_q_eps, self.optim_q_c)
+            for k, sd in pend.items():
+                ckpt.from_torch_state_dict(sd, groups[k])
+            self._pending_disc_optim = None
 
     def _disc_prepare(self, x):
         """gail.py:423-452: task-obs weighting, per-step multipliers, normalisation (no grad)."""

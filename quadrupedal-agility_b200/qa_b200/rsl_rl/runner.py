@@ -4,8 +4,8 @@
 Loop order per step is the reference's (:156-181): act -> env.step -> disc-history update with the terminal
 states patched in -> predict_disc_reward -> process_env_step -> reset rows of the disc history.  The
 variable-length `reset_env_ids` indexing of the reference is replaced by dense masked selects on the reset
-mask (same values, no host sync); TensorBoard bookkeeping (:183-206, :238-304) is SURVEY 8(f) "next" and only
-the throughput numbers the reference logs as Perf/* are kept.
+mask (same values, no host sync).  The episode bookkeeping and TensorBoard scalars (:183-206, :238-304) are staged on
+the device and flushed once per iteration (`train_log.py`); they are active when `log_dir` is given, as in the reference.
 """
 import os
 import time
@@ -16,7 +16,8 @@ from .. import config as K
 from .. import ops
 from .algorithm import SSInfoGAIL
 from .modules import ActorCritic, Estimator, Discriminator
-from .utils import Normalizer, install_pickle_alias
+from .train_log import EpisodeBook, ScalarLog, log_bbc
+from .utils import Normalizer, install_pickle_alias, reference_picklable
 
 
 class OnPolicyRunner:
@@ -56,6 +57,7 @@ class OnPolicyRunner:
         self.perf = {}
         self._disc_hist = None
         self._hist_pp = None
+        self.book, self.writer = None, None
         self.fused_rollout = bool(train_cfg["runner"].get("fused_rollout", True))
         env.reset()
 
@@ -82,7 +84,14 @@ class OnPolicyRunner:
                        alg.disc_normalizer.clip_obs, env.task_obs_weight_decay, env.task_obs_weight, self.obs_disc_weight_step)
         heads = alg.disc.heads_forward(self._x_norm)
         infos = {"time_outs": env._time_outs_latched} if env.cfg.send_timeouts else {}
-        alg.process_env_step_fused(heads, obs, rewards, dones, infos, None if staged else hist_new)
+        book = self.book
+        alg.process_env_step_fused(heads, obs, rewards, dones, infos, None if staged else hist_new,
+                                   reward_terms=None if book is None else self._terms4)
+        if book is not None:                                                # :183-206, staged on the device
+            slot = book.term_slot()
+            slot[:, 1:].copy_(self._terms4)
+            slot[:, 0].copy_(self._terms4 @ self._reward_coefs)
+            book.record(dones, episode_means=env._episode_rew_means)
         self._disc_hist = dst
         return next_obs, next_priv
 
@@ -102,6 +111,8 @@ class OnPolicyRunner:
                                                                  normalizer=alg.disc_normalizer)
         infos = {"time_outs": env._time_outs_latched} if env.cfg.send_timeouts else {}
         alg.process_env_step(rew, dones, infos, hist)
+        if self.book is not None:
+            self.book.record(dones, torch.stack([rew.float(), r_i, r_us, r_ss.float(), r_t], dim=1), env._episode_rew_means)
         # fresh episodes restart their discriminator history (:180-181)
         self._disc_hist = torch.where(done_col.unsqueeze(2), next_disc.unsqueeze(1).expand(-1, self.disc_obs_len, -1), hist)
         return next_obs, next_priv
@@ -113,6 +124,15 @@ class OnPolicyRunner:
         obs, critic_obs = env.get_observations(), env.get_privileged_observations()
         self._disc_hist = torch.stack([env.get_disc_observations()] * self.disc_obs_len, dim=1)
         alg.actor_critic.train()
+        if self.log_dir is not None and self.writer is None:               # :120-121
+            self.writer = ScalarLog(self.log_dir)
+            self.book = EpisodeBook(env.num_envs, self.num_steps_per_env, ("total", "i", "us", "ss", "t"), self.device,
+                                    num_episode_keys=len(env.reward_names))
+            d = alg.disc
+            self._terms4 = torch.zeros(env.num_envs, 4, device=self.device)
+            self._reward_coefs = torch.tensor([d.reward_i_coef, d.reward_us_coef, d.reward_ss_coef, d.reward_t_coef],
+                                              device=self.device)
+        hist_latent_loss = None
         for it in range(self.current_learning_iteration, self.current_learning_iteration + num_learning_iterations):
             start = time.time()
             hist_encoding = it % self.dagger_update_freq == 0
@@ -127,7 +147,7 @@ class OnPolicyRunner:
             expert = alg.motion_loader if hasattr(alg.motion_loader, "preloaded_s_lb") else None
             stats = alg.update(expert=expert)
             if hist_encoding:                                                   # on_policy_runner.py:220-221
-                self.perf_hist_latent_loss = alg.update_dagger()
+                hist_latent_loss = self.perf_hist_latent_loss = alg.update_dagger()
             if env.task_obs_weight_decay_steps:
                 env.task_obs_weight = max(0, env.task_obs_weight - 1.0 / env.task_obs_weight_decay_steps)
             learn_time = time.time() - start
@@ -135,20 +155,25 @@ class OnPolicyRunner:
             self.tot_time += collection_time + learn_time
             self.perf = {"total_fps": int(self.num_steps_per_env * env.num_envs / (collection_time + learn_time)),
                          "collection_time": collection_time, "learning_time": learn_time, "stats": stats}
+            if self.book is not None:                                           # :229-230
+                self.book.flush()
+                self.train_means = log_bbc(self, self.writer, it, stats, hist_latent_loss, collection_time, learn_time)
             if self.log_dir is not None and (it + 1) % self.save_interval == 0:
                 self.save(os.path.join(self.log_dir, 'model.pt'))
         self.current_learning_iteration += num_learning_iterations
         if self.log_dir is not None:
             self.save(os.path.join(self.log_dir, 'model.pt'))
 
-    # ---- checkpoints (:306-339): same top-level keys; flat Adam state replaces the torch.optim dicts ----------
+    # ---- checkpoints (:306-339): the reference's dict, key for key, optimiser states in torch.optim layout ------------
     def save(self, path, infos=None):
         os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
-        torch.save({'actor_critic': self.alg.actor_critic.state_dict(), 'estimator': self.alg.estimator.state_dict(),
-                    'disc': self.alg.disc.state_dict(), 'optim_ac': self.alg.optim_ac.state_dict(),
-                    'optim_estimator': self.alg.optim_estimator.state_dict(),
-                    'disc_normalizer': self.alg.disc_normalizer, 'reward_i_normalizer': None,
-                    'iter': self.current_learning_iteration, 'infos': infos}, path)
+        d = {'actor_critic': self.alg.actor_critic.state_dict(), 'estimator': self.alg.estimator.state_dict(),
+             'disc': self.alg.disc.state_dict()}
+        d.update(self.alg.optimizer_state_dicts())
+        d.update({'disc_normalizer': reference_picklable(self.alg.disc_normalizer),
+                  'reward_i_normalizer': getattr(self.alg.disc, "reward_i_normalizer", None),
+                  'iter': self.current_learning_iteration, 'infos': infos})
+        torch.save(d, path)
 
     def load(self, path, load_optimizer=True):
         install_pickle_alias()
@@ -161,9 +186,10 @@ class OnPolicyRunner:
             mine = Normalizer(n.mean.shape[0], epsilon=n.epsilon, clip_obs=n.clip_obs)
             mine.mean, mine.var, mine.count = n.mean, n.var, n.count
             self.alg.disc_normalizer = mine
-        if load_optimizer and isinstance(d.get('optim_ac'), dict) and 'exp_avg' in d['optim_ac']:
-            self.alg.optim_ac.load_state_dict(d['optim_ac'])
-            self.alg.optim_estimator.load_state_dict(d['optim_estimator'])
+        if d.get('reward_i_normalizer'):
+            self.alg.disc.reward_i_normalizer = d['reward_i_normalizer']
+        if load_optimizer:
+            self.alg.load_optimizer_state_dicts(d)
         self.current_learning_iteration = d.get('iter', 0)
         return d.get('infos')
 

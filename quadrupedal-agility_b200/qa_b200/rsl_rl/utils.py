@@ -114,3 +114,19 @@ def install_pickle_alias() -> None:
     sys.modules["rsl_rl.utils.utils"] = me
     pkg.utils = sub
     sub.utils = me
+
+
+def reference_picklable(n):
+    """The running normaliser as an object that pickles under the reference's class path `rsl_rl.utils.utils.Normalizer`
+    (bbc/rsl_rl/utils/utils.py:86), so that a checkpoint written here un-pickles inside the reference (its `load` assigns the
+    object as is, on_policy_runner.py:327) as well as here (through `install_pickle_alias`)."""
+    if n is None:
+        return None
+    install_pickle_alias()
+    mod = sys.modules["rsl_rl.utils.utils"]
+    if mod is sys.modules[__name__]:
+        Normalizer.__module__ = "rsl_rl.utils.utils"               # resolves to this very class through the alias
+        return n
+    obj = mod.Normalizer.__new__(mod.Normalizer)                   # the real reference package is importable
+    obj.__dict__.update(n.__getstate__() if hasattr(n, "__getstate__") else n.__dict__)
+    return obj
