@@ -150,3 +150,25 @@ def ppo_losses(sd_ac, sd_est, batch, clip_param=0.2, priv_reg_coef=0.0, value_lo
 def tsc_priv_reg_coef(counter, sched=(0, 0.1, 500, 1000)):
     """ppo.py:186-187 with the go2 agility schedule (legged_robot_config.py:399)."""
     return priv_reg_coef(counter, sched)
+
+
+def update_dagger(sd_ac, obs, lr, epochs, max_grad_norm=1.0):
+    """PPO.update_dagger (algorithms/ppo.py:284-314) over ONE minibatch holding every row of `obs` (the mean of the row norms
+    does not depend on the generator's permutation): `epochs` Adam steps on the history encoder towards the frozen
+    privileged-latent encoder.  Returns (mean loss, {name: updated tensor} of the history encoder)."""
+    sd = {k: v.clone() for k, v in sd_ac.items()}
+    enc_names = [k for k in sd if k.startswith("actor.history_encoder.")]
+    for k in enc_names:
+        sd[k].requires_grad_(True)
+    opt = torch.optim.Adam([sd[k] for k in enc_names], lr=lr)                  # hist_encoder_optimizer (:64)
+    total = 0.0
+    for _ in range(epochs):
+        with torch.no_grad():
+            target = priv_latent(sd, obs)
+        loss = (target.detach() - hist_latent(sd, obs)).norm(p=2, dim=1).mean()
+        opt.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_([sd[k] for k in enc_names], max_grad_norm)
+        opt.step()
+        total += float(loss.detach())
+    return total / epochs, {k: sd[k].detach() for k in enc_names}

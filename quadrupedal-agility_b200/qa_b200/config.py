@@ -225,10 +225,13 @@ def bbc_train_cfg() -> dict:
     }
 
 
-def tsc_train_cfg() -> dict:
+def tsc_train_cfg(use_camera: bool = False) -> dict:
     """`class_to_dict(Go2AgilityCfgPPO())` of the reference (tsc/legged_gym/envs/base/legged_robot_config.py:365-470 +
-    go2_agility_config.py:52-60): the dict the TSC `OnPolicyRunner(env, train_cfg, ...)` takes (teacher path)."""
+    go2_agility_config.py:52-60): the dict the TSC `OnPolicyRunner(env, train_cfg, ...)` takes.  `use_camera=True` is the
+    student configuration (`--use_camera`): `depth_encoder.if_depth` follows `depth.use_camera` (:406-414)."""
     return {
+        "depth_encoder": dict(if_depth=use_camera, depth_shape=(87, 58), buffer_len=2, hidden_dims=512, learning_rate=1.e-3,
+                              learning_rate_byol=3.e-4, learning_rate_min=1.e-5, num_steps_per_env=24),
         "seed": 1,
         "runner_class_name": "OnPolicyRunner",
         "policy": dict(init_noise_std=1.0, continue_from_last_std=True, scan_encoder_dims=[128, 64, 32],
@@ -238,7 +241,7 @@ def tsc_train_cfg() -> dict:
                           num_learning_epochs=5, num_mini_batches=4, learning_rate=5.e-4, schedule="adaptive", gamma=0.99,
                           lam=0.95, desired_kl=0.01, max_grad_norm=1.0, dagger_update_freq=20,
                           priv_reg_coef_schedual=[0, 0.1, 500, 1000]),
-        "estimator": dict(train_with_estimated_states=True, learning_rate=1.e-4, hidden_dims=[128, 64]),
+        "estimator": dict(train_with_estimated_states=True, learning_rate=1.e-4, hidden_dims=[128, 64], load_estimator_bbc=True),
         "runner": dict(policy_class_name="ActorCritic", algorithm_class_name="PPO", num_steps_per_env=24, max_iterations=50000,
                        save_interval=100, experiment_name="agility", run_name="", disc_loss_function="MSELoss",
                        reward_i_coef=0.05, reward_us_coef=0.0, reward_ss_coef=0.0, reward_t_coef=2.0,

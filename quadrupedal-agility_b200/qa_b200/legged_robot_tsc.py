@@ -102,6 +102,7 @@ class LeggedRobotTSC:
         dev, N, B = self.device, cfg.num_envs, cfg.num_bodies
         self.num_envs, self.dt = N, cfg.dt
         self.max_episode_length = cfg.max_episode_length
+        self.depth = None
         f = lambda *s: torch.zeros(*s, device=dev)                             # noqa: E731
         u8 = lambda *s: torch.zeros(*s, device=dev, dtype=torch.uint8)         # noqa: E731
         self.static = {k: v.to(dev).contiguous() for k, v in static.items()}
@@ -296,7 +297,27 @@ class LeggedRobotTSC:
         self.extras["reach_goal"] = self._reach_goal_cutoff
         terminal = self._terminal_disc[:count].clone()
         ops.post_physics_tsc(self._const, a, "post")
+        if self.depth is not None:                                           # :275, after reset_idx: fresh episodes refill
+            self.depth.update_depth_buffer(self.episode_length_buf, self.global_counter)   # their whole history (K14)
         return self._reset_ids[:count], terminal
+
+    def reconfigure(self, **changes) -> None:
+        """Change config scalars after construction (the student loop raises `next_goal_threshold`, tsc
+        on_policy_runner.py:286) and rebuild the kernels' constant block."""
+        for k, v in changes.items():
+            if not hasattr(self.cfg, k):
+                raise AttributeError(k)
+            setattr(self.cfg, k, v)
+        self._const = self._build_const()
+
+    def attach_depth(self, depth) -> None:
+        """Student path (`--use_camera`): `depth` is a `qa_b200.depth.DepthBuffer` bound to the simulator's camera tensors;
+        `post_physics_step` then refreshes it every `update_interval` steps and `step` hands out `extras["depth"]` (:145-148)."""
+        self.depth = depth
+
+    @property
+    def depth_buffer(self):
+        return None if self.depth is None else self.depth.depth_buffer
 
     def _pre_physics(self, actions, action_hl_history_buf=None):
         cfg = self.cfg
@@ -317,7 +338,11 @@ class LeggedRobotTSC:
         self._pre_physics(actions, action_hl_history_buf)
         ids, terminal = self.post_physics_step()
         self.extras["delta_yaw_ok"] = torch.abs(self.delta_yaw) < 0.6
-        self.extras["depth"] = None
+        d = self.depth
+        if d is not None and d.cfg.use_camera and self.global_counter % d.cfg.update_interval == 0:
+            self.extras["depth"] = d.depth_buffer[:, -2]                        # "have already selected last one" (:146)
+        else:
+            self.extras["depth"] = None
         return self.obs_buf, self.privileged_obs_buf, self.rew_buf, self.reset_buf, self.extras, ids, terminal
 
     def get_observations(self):

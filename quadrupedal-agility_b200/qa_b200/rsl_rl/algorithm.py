@@ -370,17 +370,16 @@ class SSInfoGAIL:
             if pend is not None:                                   # loaded, not yet stepped: hand the same dicts back
                 out.update(pend)
             else:                                                  # never stepped: zero moments of the right shapes
-                import copy
-                d = copy.deepcopy(self.disc)
-                flat = d.flatten_parameters()
-                sl = flat.slices
-                rng = lambda a, b: (sl[a][0], sl[b][0] + sl[b][1])                       # noqa: E731
-                mk = lambda lr, r: FlatAdam(flat, lr, 0.0, weight_decay=1e-3, lo=r[0], hi=r[1])   # noqa: E731
-                t = rng("trunk.0.weight", "trunk.2.bias")
-                groups = self._disc_groups(d, flat, [mk(self.lr_disc, rng("trunk.0.weight", "linear.bias"))],
-                                           [mk(self.lr_q, t), mk(self.lr_q, rng("encoder_eps.weight", "encoder_eps.bias"))],
-                                           [mk(self.lr_q, t), mk(self.lr_q, rng("classifier.weight", "classifier.bias"))])
-                out.update({k: ckpt.to_torch_state_dict(g) for k, g in groups.items()})
+                d = self.disc
+                shapes = lambda m: [tuple(p.shape) for p in m.parameters()]              # noqa: E731
+                grp = lambda m, name, lr: dict(shapes=shapes(m), lr=lr,                      # noqa: E731
+                                               extra={"weight_decay": 1e-3, "momentum": 0.9, "name": name})
+                dev = next(d.parameters()).device
+                out["optim_d"] = ckpt.zero_torch_state_dict([grp(d.trunk, "trunk", self.lr_disc), grp(d.linear, "head", self.lr_disc)], dev)
+                out["optim_q_eps"] = ckpt.zero_torch_state_dict([grp(d.trunk, "trunk", self.lr_q),
+                                                                 grp(d.encoder_eps, "encoder_eps", self.lr_q)], dev)
+                out["optim_q_c"] = ckpt.zero_torch_state_dict([grp(d.trunk, "trunk", self.lr_q),
+                                                               grp(d.classifier, "classifier", self.lr_q)], dev)
         return out
 
     def load_optimizer_state_dicts(self, d):

@@ -103,3 +103,24 @@ def from_torch_state_dict(sd, groups, load_lr=True):
         adam.step_count.fill_(step)
         if load_lr:
             adam.lr.fill_(float(pg["lr"]))
+
+
+def zero_torch_state_dict(groups, device="cpu"):
+    """The dict of an Adam optimiser that has not stepped yet but whose moments are materialised (what this package writes for
+    optimisers it builds lazily).  groups: [{"shapes": [shape, ...], "lr": float, "weight_decay": float, "extra": {...}}]."""
+    state, param_groups, idx = {}, [], 0
+    for g in groups:
+        ids = []
+        for shape in g["shapes"]:
+            state[idx] = {"step": torch.zeros((), dtype=torch.float32), "exp_avg": torch.zeros(shape, device=device),
+                          "exp_avg_sq": torch.zeros(shape, device=device)}
+            ids.append(idx)
+            idx += 1
+        pg = dict(g.get("extra", {}))
+        pg.update(lr=float(g["lr"]), betas=(0.9, 0.999), eps=1e-8)
+        pg.setdefault("weight_decay", g.get("weight_decay", 0.0))
+        for k, v in _ADAM_DEFAULTS.items():
+            pg.setdefault(k, v)
+        pg["params"] = ids
+        param_groups.append(pg)
+    return {"state": state, "param_groups": param_groups}

@@ -19,13 +19,16 @@ import torch
 
 
 class EpisodeBook:
-    def __init__(self, num_envs, num_steps, term_names, device, maxlen=100, num_episode_keys=0):
-        self.N, self.T, self.names = num_envs, num_steps, tuple(term_names)
-        C = len(self.names)
+    def __init__(self, num_envs, num_steps, term_names, device, maxlen=100, num_episode_keys=0, snap_names=()):
+        """`term_names`: per-step quantities SUMMED over an episode (rewards); `snap_names`: per-step quantities whose value
+        AT the finishing step is recorded (e.g. the TSC runner's `reach_goal`, tsc on_policy_runner.py:248)."""
+        self.N, self.T, self.names, self.snap_names = num_envs, num_steps, tuple(term_names), tuple(snap_names)
+        self.n_sum = len(self.names)
+        C = len(self.names) + len(self.snap_names)
         self.terms = torch.zeros(num_steps, num_envs, C, device=device)
         self.dones = torch.zeros(num_steps, num_envs, device=device, dtype=torch.uint8)
         self.ep_means = torch.zeros(num_steps, max(num_episode_keys, 1), device=device)
-        self.buffers = {n: deque(maxlen=maxlen) for n in self.names}
+        self.buffers = {n: deque(maxlen=maxlen) for n in self.names + self.snap_names}
         self.len_buffer = deque(maxlen=maxlen)
         self._cur = np.zeros((num_envs, C), dtype=np.float32)          # cur_reward_* (:141-146), fp32 like the reference
         self._len = np.zeros(num_envs, dtype=np.float32)
@@ -47,7 +50,8 @@ class EpisodeBook:
             self.terms[t].copy_(terms)
         self.dones[t].copy_(dones)
         if episode_means is not None:
-            self.ep_means[t, :episode_means.numel()].copy_(episode_means.reshape(-1))
+            k = min(self.ep_means.shape[1], episode_means.numel())
+            self.ep_means[t, :k].copy_(episode_means.reshape(-1)[:k])
         self._t = t + 1
 
     def flush(self):
@@ -62,12 +66,14 @@ class EpisodeBook:
             torch.cuda.current_stream().synchronize()
         terms, dones = self._h_terms[:n].numpy(), self._h_dones[:n].numpy()
         self.episode_rows = [self._h_ep[i].numpy().copy() for i in range(n)]
+        k = self.n_sum
         for t in range(n):
-            self._cur += terms[t]
+            self._cur[:, :k] += terms[t][:, :k]
+            self._cur[:, k:] = terms[t][:, k:]
             self._len += 1
             ids = np.nonzero(dones[t])[0]
             if ids.size:
-                for c, name in enumerate(self.names):
+                for c, name in enumerate(self.names + self.snap_names):
                     self.buffers[name].extend(self._cur[ids, c].tolist())
                 self.len_buffer.extend(self._len[ids].tolist())
                 self._cur[ids] = 0
@@ -141,4 +147,31 @@ def log_bbc(runner, log, it, stats, hist_latent_loss, collection_time, learn_tim
         for k in ("i", "us", "ss", "t"):
             log.add_scalar("Train/mean_reward_" + k, m[k], it)
         log.add_scalar("Train/mean_episode_length", m["episode_length"], it)
+    return m
+
+
+def log_tsc(runner, log, it, tags, collection_time, learn_time):
+    """The scalar groups of tsc/rsl_rl/runners/on_policy_runner.py `log` / `log_vision` (:462-594): `tags` = {tag: value} of the
+    iteration's loss statistics; episode means, throughput and the bookkeeping means are added here."""
+    env, book = runner.env, runner.book
+    rows = book.episode_rows
+    if rows:
+        mean_per_key = np.mean(np.stack(rows, axis=0), axis=0)
+        for i, name in enumerate(env.cfg.reward_names):
+            log.add_scalar("Episode_rew/rew_" + name, mean_per_key[i], it)
+    for tag, v in tags.items():
+        log.add_scalar(tag, v, it)
+    fps = int(runner.num_steps_per_env * env.num_envs / (collection_time + learn_time))
+    log.add_scalar("Perf/total_fps", fps, it)
+    log.add_scalar("Perf/collection time", collection_time, it)
+    log.add_scalar("Perf/learning_time", learn_time, it)
+    m = book.means()
+    if m:
+        log.add_scalar("Train/mean_reward", m["total"], it)
+        for k in ("i", "us", "ss", "t"):
+            if k in m:
+                log.add_scalar("Train/mean_reward_" + k, m[k], it)
+        log.add_scalar("Train/mean_episode_length", m["episode_length"], it)
+        if "reach_goal" in m:
+            log.add_scalar("Train/mean_success_rate", m["reach_goal"], it)
     return m

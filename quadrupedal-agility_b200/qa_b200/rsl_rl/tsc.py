@@ -273,7 +273,8 @@ class _PPOLossTSCFused(torch.autograd.Function):
 
 
 class PPO:
-    """tsc/rsl_rl/algorithms/ppo.py:8-282 (teacher path; the depth-student distillation updates are SURVEY 8f-3)."""
+    """tsc/rsl_rl/algorithms/ppo.py:8-383: teacher PPO (`act`, `process_env_step`, `compute_returns`, `update`, `update_dagger`)
+    and the depth-student distillation updates (`update_depth_encoder` / `update_depth_actor` / `update_depth_both`)."""
 
     def __init__(self, actor_critic, actor_critic_bbc, estimator, estimator_paras, depth_encoder=None,
                  depth_encoder_paras=None, depth_actor=None, num_learning_epochs=1, num_mini_batches=1, clip_param=0.2,
@@ -301,6 +302,18 @@ class PPO:
         self.train_with_estimated_states = estimator_paras["train_with_estimated_states"]
         self.if_depth = depth_encoder is not None
         self.num_actions_d = self.actor_critic.num_actions_d
+        self._lr0, self.hist_encoder_optimizer = learning_rate, None
+        if self.if_depth:
+            # student distillation (ppo.py:78-88): conv / GRU / batch-norm modules on cuDNN with torch.optim.Adam;
+            # the three optimisers overlap on purpose, each with its own moments
+            self.depth_encoder, self.depth_actor = depth_encoder.to(device), depth_actor.to(device)
+            self.depth_encoder_paras = depth_encoder_paras
+            lr = depth_encoder_paras["learning_rate"]
+            self.depth_encoder_optimizer = torch.optim.Adam(self.depth_encoder.parameters(), lr=lr)
+            self.depth_actor_optimizer = torch.optim.Adam([*self.depth_actor.parameters(), *self.depth_encoder.parameters()], lr=lr)
+            self.byol_optimizer = torch.optim.Adam(self.depth_encoder.byol_learner.parameters(),
+                                                   lr=depth_encoder_paras["learning_rate_byol"])
+        self.CE_loss = nn.CrossEntropyLoss()
         self.world_size = (torch.distributed.get_world_size()
                            if torch.distributed.is_available() and torch.distributed.is_initialized() else 1)
         cuda = torch.device(device).type == "cuda"
@@ -537,3 +550,108 @@ class PPO:
 
     def update_counter(self):
         self.counter += 1
+
+    # ---- DAgger: history-encoder adaptation (ppo.py:284-314) -----------------------------------------------------------
+    def update_dagger(self, indices: Optional[torch.Tensor] = None):
+        """Fits `actor.history_encoder` to the frozen privileged-latent encoder over the stored rollout (the buffers still
+        hold it after `update()`'s `storage.clear()`, exactly what the reference relies on): per minibatch
+        mean ||priv_latent - hist_latent||_2 (K12 forward+backward), clip_grad_norm_ over the encoder, Adam (K8) on the
+        encoder's slice of the flat buffer at the PPO learning rate the optimiser was built with (:64).  Returns the mean loss."""
+        st, actor = self.storage, self.actor_critic.actor
+        if self.hist_encoder_optimizer is None:
+            names = [n for n in self.ac_flat.slices if n.startswith("actor.history_encoder.")]
+            lo = min(self.ac_flat.slices[n][0] for n in names)
+            hi = max(self.ac_flat.slices[n][0] + self.ac_flat.slices[n][1] for n in names)
+            self.hist_encoder_optimizer = FlatAdam(self.ac_flat, self._lr0, self.max_grad_norm, lo=lo, hi=hi)
+            self._dagger_loss = torch.zeros(1, device=self.device)
+        opt = self.hist_encoder_optimizer
+        flat_obs = st.observations.flatten(0, 1)
+        mb_size = flat_obs.shape[0] // self.num_mini_batches
+        if indices is None:
+            indices = torch.randperm(self.num_mini_batches * mb_size, device=self.device)
+        with torch.no_grad():
+            priv_all = actor.infer_priv_latent(flat_obs)
+        total = torch.zeros((), device=self.device)
+        w = actor.num_prop - actor.num_auxiliary                              # the actor's proprioception incl. auxiliary lanes
+        for _ in range(self.num_learning_epochs):
+            for i in range(self.num_mini_batches):
+                idx = indices[i * mb_size:(i + 1) * mb_size]
+                hist = flat_obs[idx][:, flat_obs.shape[1] - actor.num_hist * w:]
+                hist_latent = actor.history_encoder(hist.reshape(-1, actor.num_hist, w))      # with grad: torch modules
+                priv = priv_all[idx]
+                if self.fused_loss:
+                    loss = _RowLossFused.apply(hist_latent, priv, 1, self._dagger_loss)
+                else:
+                    loss = (priv - hist_latent).norm(p=2, dim=1).mean()
+                self.ac_flat.grad[opt.lo:opt.hi].zero_()
+                loss.backward()
+                opt.step()
+                total += loss.detach()
+        st.clear()
+        self.update_counter()
+        return float(total.item()) / (self.num_learning_epochs * self.num_mini_batches)
+
+    # ---- depth-student distillation (ppo.py:316-383, SURVEY 8f-3) --------------------------------------------------------
+    def update_depth_encoder(self, depth_latent_batch, scandots_latent_batch):
+        if not self.if_depth:
+            return None
+        loss = (scandots_latent_batch.detach() - depth_latent_batch).norm(p=2, dim=1).mean()
+        self.depth_encoder_optimizer.zero_grad()
+        loss.backward()
+        nn.utils.clip_grad_norm_(self.depth_encoder.parameters(), self.max_grad_norm)
+        self.depth_encoder_optimizer.step()
+        return loss.item()
+
+    def depth_actor_losses(self, actions_student, actions_teacher, yaw_student, yaw_teacher, obst_student, obst_teacher):
+        """The three distillation terms of :329-336 as tensors: (mode cross-entropy + continuous L2, yaw L2 with lane
+        weights (2, 0.5), obstacle-type cross-entropy -- on the ALREADY soft-maxed student lanes, as the reference does)."""
+        nd = self.num_actions_d
+        d_loss = self.CE_loss(actions_student[:, :nd], actions_teacher[:, 0].detach().to(torch.int64))
+        c_loss = (actions_teacher[:, 1:].detach() - actions_student[:, nd:]).norm(p=2, dim=1).mean()
+        scale = torch.tensor([2.0, 0.5], device=yaw_teacher.device)
+        yaw_loss = ((yaw_teacher.detach() - yaw_student) * scale).norm(p=2, dim=1).mean()
+        obst_loss = self.CE_loss(obst_student, torch.argmax(obst_teacher, dim=-1))
+        return d_loss + c_loss, yaw_loss, obst_loss
+
+    def update_depth_actor(self, actions_student_batch, actions_teacher_batch, yaw_student_batch, yaw_teacher_batch,
+                           obst_type_buffer_student, obst_type_buffer_teacher, depth_batch, byol_perm=None):
+        """One distillation step through the whole rollout's graph (student actor + depth encoder incl. the GRU), then six
+        BYOL minibatch steps over the rollout's shuffled depth images with the EMA target update after each (:338-358).
+        Returns (depth_actor_loss, yaw_loss, obst_type_loss, mean_byol_loss)."""
+        if not self.if_depth:
+            return None
+        actor_loss, yaw_loss, obst_loss = self.depth_actor_losses(
+            actions_student_batch, actions_teacher_batch, yaw_student_batch, yaw_teacher_batch, obst_type_buffer_student,
+            obst_type_buffer_teacher)
+        loss = actor_loss + yaw_loss + obst_loss
+        self.depth_actor_optimizer.zero_grad()
+        loss.backward()
+        nn.utils.clip_grad_norm_(self.depth_actor.parameters(), self.max_grad_norm)
+        self.depth_actor_optimizer.step()
+        n = depth_batch.size(0)
+        bs = n // 6
+        perm = torch.randperm(n) if byol_perm is None else byol_perm
+        depth_batch = depth_batch[perm.to(depth_batch.device)]
+        byol_total = torch.zeros((), device=depth_batch.device)
+        learner = self.depth_encoder.byol_learner
+        for i in range(0, n, bs):
+            byol_loss = learner(depth_batch[i:i + bs])
+            self.byol_optimizer.zero_grad()
+            byol_loss.backward()
+            self.byol_optimizer.step()
+            byol_total += byol_loss.detach()
+            learner.update_moving_average()
+        stats = torch.stack([actor_loss.detach(), yaw_loss.detach(), obst_loss.detach(), byol_total / (n // bs)])
+        a, y, o, b = stats.tolist()                                     # one host sync for the four statistics
+        return a, y, o, b
+
+    def update_depth_both(self, depth_latent_batch, scandots_latent_batch, actions_student_batch, actions_teacher_batch):
+        if not self.if_depth:
+            return None
+        enc_loss = (scandots_latent_batch.detach() - depth_latent_batch).norm(p=2, dim=1).mean()
+        act_loss = (actions_teacher_batch.detach() - actions_student_batch).norm(p=2, dim=1).mean()
+        self.depth_actor_optimizer.zero_grad()
+        (enc_loss + act_loss).backward()
+        nn.utils.clip_grad_norm_([*self.depth_actor.parameters(), *self.depth_encoder.parameters()], self.max_grad_norm)
+        self.depth_actor_optimizer.step()
+        return enc_loss.item(), act_loss.item()

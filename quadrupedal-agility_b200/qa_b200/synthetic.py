@@ -451,3 +451,38 @@ def make_tsc_snapshot(num_envs: int, static, seed: int = 0, step: int = 0):
 def make_tsc_draws(num_envs: int, seed: int = 0, step: int = 0):
     g = torch.Generator().manual_seed(seed * 32452843 + step * 11 + 2)
     return {k: torch.rand(num_envs, generator=g) for k in ("yaw_u", "x_u", "y_u")}
+
+
+# ---- TSC depth student: formula-generated weights / inputs shared by the reference pin and the tests -----------
+def load_student_weights(module, seed: int) -> None:
+    """Deterministic weights for a student module, drawn key by key in `state_dict()` order (the 62 400 x 128 linear layer of
+    the depth backbone makes a stored fixture impractical).  Tensors that appear under several keys are written several
+    times; the last write wins, identically for any implementation with the same keys."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for k, v in module.state_dict().items():
+            if not v.is_floating_point():
+                continue
+            if k.endswith("running_var"):
+                v.copy_(1.0 + 0.1 * torch.rand(v.shape, generator=g))
+            elif v.dim() >= 2:
+                fan_in = v[0].numel()
+                v.copy_(torch.randn(v.shape, generator=g) / fan_in ** 0.5)
+            else:
+                v.copy_(0.01 * torch.randn(v.shape, generator=g))
+
+
+def make_student_inputs(num_envs: int, steps: int, seed: int):
+    """obs (T,N,800) with plausible auxiliary lanes [57:59] = delta yaw, [59:65] = obstacle one-hot; depth images (T,N,58,87) in
+    the normalised range of `process_depth_image`; teacher actions (T*N,19) = [mode index | 18 continuous]; yaw-ok masks."""
+    g = torch.Generator().manual_seed(seed)
+    T, N = steps, num_envs
+    obs = 0.5 * torch.randn(T, N, 800, generator=g)
+    obs[:, :, 57:59] = 0.3 * torch.randn(T, N, 2, generator=g)
+    kind = torch.randint(0, 6, (T, N), generator=g)
+    obs[:, :, 59:65] = torch.nn.functional.one_hot(kind, 6).float()
+    depth = torch.rand(T, N, 58, 87, generator=g) - 0.5
+    teacher = 0.5 * torch.randn(T * N, 19, generator=g)
+    teacher[:, 0] = torch.randint(0, 3, (T * N,), generator=g).float()
+    ok = torch.rand(T, N, generator=g) < 0.8
+    return dict(obs=obs, depth=depth, actions_teacher=teacher, delta_yaw_ok=ok)

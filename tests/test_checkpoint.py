@@ -5,6 +5,7 @@
 * when the reference tree is present (build container only): the six optimiser dicts of the SHIPPED checkpoint
   `tsc/weights/bbc/model.pt` load into the flat layout and come back out entry for entry."""
 import copy
+import ctypes
 import os
 import types
 
@@ -25,7 +26,8 @@ def _alg():
     ac = ActorCritic(101, 671, 12, 57, 10, 4, 29, 11, **cfg["policy"])
     est = Estimator(57, 4, hidden_dims=[128, 64])
     env = types.SimpleNamespace(task_obs_weight_decay=True, task_obs_weight=0.7, dim_c=5, num_obs_disc=49,
-                                cfg=types.SimpleNamespace(), latent_eps=None, latent_c=None)
+                                cfg=types.SimpleNamespace(), latent_eps=None, latent_c=None,
+                                abi_args=ctypes.pointer(ctypes.c_int(0)))      # like LeggedRobot: not deep-copyable / picklable
     disc = Discriminator(env, 98, 49, 5, 0.02, "MSELoss", None, 1.0, 0.01, 0.2, 0.2, 2, 2, 0.0, [512, 256], "cpu")
     alg_cfg = dict(cfg["algorithm"], disc_replay_buffer_size=64, use_cuda_graph=False, fused_loss=False)
     return SSInfoGAIL(env, ac, disc, est, cfg["estimator"], None, Normalizer(98), 2, 2, 49, 0.0, device="cpu", **alg_cfg)

@@ -1,0 +1,54 @@
+"""`OnPolicyRunner.learn` with a log_dir on the device: episode bookkeeping, the reference's scalar tags and the checkpoint
+round trip (bbc/rsl_rl/runners/on_policy_runner.py:118-339).  The host halves of this (deque accounting, tag list, optimiser
+dict codec) are covered on CPU in tests/test_train_log.py and tests/test_checkpoint.py."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def test_runner_learn_books_episodes_logs_reference_tags_and_round_trips_checkpoint(tmp_path):
+    """`OnPolicyRunner.learn` with a log_dir (on_policy_runner.py:118-233): device-staged episode bookkeeping (fused K19
+    reward terms == torch path), the reference's scalar tags, and `save` / `load` with the six torch.optim-layout dicts."""
+    import bench
+    from qa_b200.pipeline import BbcIteration
+    torch.backends.cuda.matmul.allow_tf32 = False
+    N, T = 256, 4
+    cfg, static, snaps, table = bench.build_workload(0, DEV, n_envs=N, steps=T)
+    runs = []
+    for fused in (False, True):
+        it = BbcIteration(cfg, static, snaps, table, device=DEV, seed=77, use_cuda_graph=False)
+        r = it.runner
+        r.fused_rollout, r.log_dir, r.save_interval = fused, str(tmp_path / f"run{int(fused)}"), 1
+        torch.manual_seed(5)
+        r.learn(2)
+        runs.append(r)
+    a, b = runs[0].writer.scalars, runs[1].writer.scalars
+    for tag in ("Loss/surrogate_loss", "Loss/value_loss", "Loss/estimator_loss", "Loss/hist_latent_loss", "Loss/mean_noise_std",
+                "LR/lr_ac", "Perf/total_fps", "Perf/collection time", "Perf/learning_time", "Episode/rew_torques",
+                "Episode/rew_tracking_lin_vel", "Train/mean_reward", "Train/mean_reward_i", "Train/mean_reward_us",
+                "Train/mean_reward_ss", "Train/mean_reward_t", "Train/mean_episode_length"):
+        assert tag in a and tag in b, tag
+        assert [s for s, _ in b[tag]] == [0, 1][-len(b[tag]):] and all(np.isfinite(v) for _, v in b[tag]), tag
+    for tag in ("Train/mean_reward", "Train/mean_reward_i", "Train/mean_reward_us", "Train/mean_reward_ss", "Train/mean_reward_t",
+                "Train/mean_episode_length", "Episode/rew_torques"):            # first iteration: identical policy in both runs
+        va, vb = a[tag][0][1], b[tag][0][1]
+        assert abs(va - vb) <= 5e-3 * abs(va) + 1e-4, (tag, va, vb)
+    assert len(runs[1].book.len_buffer) > 0
+    r = runs[1]
+    path = f"{r.log_dir}/model.pt"
+    d = torch.load(path, map_location="cpu", weights_only=False)
+    assert list(d) == ['actor_critic', 'estimator', 'disc', 'optim_ac', 'optim_hist_encoder', 'optim_estimator', 'optim_d',
+                       'optim_q_eps', 'optim_q_c', 'disc_normalizer', 'reward_i_normalizer', 'iter', 'infos'] and d["iter"] == 2
+    assert float(d["optim_ac"]["state"][0]["step"]) == 2 * 20 and float(d["optim_hist_encoder"]["state"][0]["step"]) == 20
+    it2 = BbcIteration(cfg, static, snaps, table, device=DEV, seed=3, use_cuda_graph=False)
+    it2.runner.load(path)
+    assert it2.runner.current_learning_iteration == 2
+    for (k, v), w in zip(r.alg.actor_critic.state_dict().items(), it2.runner.alg.actor_critic.state_dict().values()):
+        assert torch.equal(v, w), k
+    for o1, o2 in ((r.alg.optim_ac, it2.runner.alg.optim_ac), (r.alg.optim_estimator, it2.runner.alg.optim_estimator),
+                   (r.alg.optim_hist_encoder, it2.runner.alg.optim_hist_encoder)):
+        assert torch.equal(o1.exp_avg, o2.exp_avg) and torch.equal(o1.exp_avg_sq, o2.exp_avg_sq)
+        assert int(o1.step_count) == int(o2.step_count) and float(o1.lr) == pytest.approx(float(o2.lr))
