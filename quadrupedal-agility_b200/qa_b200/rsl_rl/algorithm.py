@@ -189,6 +189,9 @@ class SSInfoGAIL:
             capture_collectives = os.environ.get("QA_CAPTURE_COLLECTIVES", "1") == "1"
         self.capture_collectives = capture_collectives
         self._graph_has_apply = True
+        # discriminator minibatch step with one shared forward (see update_ss_info_gail); opt-in until it has been measured
+        # and re-pinned on the B200 (same values up to the summation order of the weight gradients)
+        self.disc_batched = os.environ.get("QA_DISC_BATCHED", "0") == "1"
         torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)   # capture runs on a side stream
         self._ppo_stats = torch.zeros(4, device=device)
         self._aux_loss = torch.zeros(2, device=device)            # priv_reg_loss, estimator_loss of the current minibatch
@@ -454,14 +457,31 @@ class SSInfoGAIL:
         d, env = self.disc, self.env
         policy_state, policy_latent_eps, policy_latent_c = sample_disc_policy
         expert_state_lb, label_exp_lb = sample_disc_expert_lb
-        policy_state = self._disc_prepare(policy_state)
-        expert_state_lb = self._disc_prepare(expert_state_lb)
-        expert_state_ulb = self._disc_prepare(sample_disc_expert_ulb)
-        _, _, pred_c_lb = d.forward_torch(expert_state_lb)
+        g = None
+        if self.disc_batched:
+            # ONE input preparation and ONE trunk pass over [policy | labelled | unlabelled] rows instead of three plus the
+            # gradient penalty's own forward (:492-502 re-runs the same weights on the same unlabelled batch, so its `dd` is
+            # `logits_exp`): same per-row values, a third of the launches.  The penalty's input gradient is taken from the
+            # shared graph, restricted to the unlabelled rows.
+            sizes = [len(policy_state), len(expert_state_lb), len(sample_disc_expert_ulb)]
+            x_all = self._disc_prepare(torch.cat([policy_state, expert_state_lb, sample_disc_expert_ulb], dim=0))
+            policy_state, expert_state_lb, expert_state_ulb = x_all.split(sizes)
+            x_req = x_all.detach().requires_grad_(True)
+            d_all, eps_all, c_all = d.forward_torch(x_req)
+            (logits_pi, _, logits_exp), (eps, _, _) = d_all.split(sizes), eps_all.split(sizes)
+            pred_c, pred_c_lb, pred_c_ulb = c_all.split(sizes)
+            (g_all,) = torch.autograd.grad(logits_exp, x_req, grad_outputs=torch.ones_like(logits_exp), create_graph=True,
+                                           retain_graph=True)
+            g = g_all[sizes[0] + sizes[1]:]
+        else:
+            policy_state = self._disc_prepare(policy_state)
+            expert_state_lb = self._disc_prepare(expert_state_lb)
+            expert_state_ulb = self._disc_prepare(sample_disc_expert_ulb)
+            _, _, pred_c_lb = d.forward_torch(expert_state_lb)
+            logits_pi, eps, pred_c = d.forward_torch(policy_state)
+            logits_exp, _, pred_c_ulb = d.forward_torch(expert_state_ulb)
         ss_loss = F.cross_entropy(pred_c_lb, label_exp_lb)                      # on the soft-maxed output, as the reference
         lab_pi = torch.argmax(policy_latent_c, dim=-1)
-        logits_pi, eps, pred_c = d.forward_torch(policy_state)
-        logits_exp, _, pred_c_ulb = d.forward_torch(expert_state_ulb)
         with torch.no_grad():                                                   # prior estimate :462-464
             env.prior_parameters.mul_(1 - self.prior_soft_coef).add_(pred_c_ulb.mean(dim=0) * self.prior_soft_coef)
         info_max_loss = torch.mean(-torch.sum(pred_c_ulb * torch.log(pred_c_ulb + 1e-20), dim=-1))
@@ -478,10 +498,11 @@ class SSInfoGAIL:
         disc_loss = 0.5 * (disc_pi_loss + disc_exp_loss)
         us_loss = F.l1_loss(eps, policy_latent_eps)
         disc_logit_loss = torch.sum(torch.square(d.get_disc_logit_weights()))
-        sample_expert = expert_state_ulb.clone().requires_grad_(True)           # gradient penalty :492-502
-        h = F.relu(F.linear(F.relu(F.linear(sample_expert, d.trunk[0].weight, d.trunk[0].bias)), d.trunk[2].weight, d.trunk[2].bias))
-        dd = F.linear(h, d.linear.weight, d.linear.bias)
-        (g,) = torch.autograd.grad(dd, sample_expert, grad_outputs=torch.ones_like(dd), create_graph=True, retain_graph=True)
+        if g is None:
+            sample_expert = expert_state_ulb.clone().requires_grad_(True)       # gradient penalty :492-502
+            h = F.relu(F.linear(F.relu(F.linear(sample_expert, d.trunk[0].weight, d.trunk[0].bias)), d.trunk[2].weight, d.trunk[2].bias))
+            dd = F.linear(h, d.linear.weight, d.linear.bias)
+            (g,) = torch.autograd.grad(dd, sample_expert, grad_outputs=torch.ones_like(dd), create_graph=True, retain_graph=True)
         grad_pen_loss = torch.mean(torch.sum(torch.square(g), dim=-1))
         disc_weight_decay = torch.sum(torch.square(torch.cat(d.get_disc_weights(), dim=-1)))
         loss = (self.ss_coef * ss_loss + self._info_max_coef_on * info_max_loss + self.disc_coef * disc_loss +
@@ -489,20 +510,26 @@ class SSInfoGAIL:
                 self.disc_weight_decay * disc_weight_decay)
         self.disc_flat.zero_grad()
         loss.backward()
-        for o in self.optim_d + self.optim_q_eps + self.optim_q_c:               # :519-521
-            o.step()
+        self._disc_optim_step()
         ac = self.actor_critic
         if not ac.fixed_std and self.min_std is not None:                       # :523-524
             ac.std.data.clamp_(min=self.min_std)
         if self.disc_normalizer is not None:                                    # :527-529 (of the NORMALISED batches, as there)
-            for x in (policy_state, expert_state_lb, expert_state_ulb):
-                self.disc_normalizer.update_torch(x)
+            if self.disc_batched:                                               # one merge of the three batches' pooled moments
+                self.disc_normalizer.update_torch(x_all)                        # (Chan's merge is associative: same result
+            else:                                                               # up to the fp32 rounding of the batch moments)
+                for x in (policy_state, expert_state_lb, expert_state_ulb):
+                    self.disc_normalizer.update_torch(x)
         with torch.no_grad():
             acc_lb = torch.mean((torch.argmax(pred_c_lb, dim=-1) == label_exp_lb).float())
             acc_pi, acc_exp = (logits_pi < 0).float().mean(), (logits_exp > 0).float().mean()
             acc_ulb = torch.mean((torch.argmax(pred_c, dim=-1) == lab_pi).float())
         return (ss_loss.detach(), info_max_loss.detach(), disc_loss.detach(), us_loss.detach(), grad_pen_loss.detach(),
                 disc_logit_loss.detach(), disc_weight_decay.detach(), acc_lb, acc_pi, acc_exp, acc_ulb)
+
+    def _disc_optim_step(self):
+        for o in self.optim_d + self.optim_q_eps + self.optim_q_c:               # :519-521
+            o.step()
 
     def update_disc(self, expert, num_updates=None):
         """The discriminator half of SSInfoGAIL.update (gail.py:258-300): `4 * epochs * minibatches` minibatch steps of

@@ -1,0 +1,58 @@
+"""Opt-in batched discriminator minibatch step (`QA_DISC_BATCHED=1`, DESIGN.md open item 3): one input preparation and one
+trunk pass over [policy | labelled | unlabelled] rows, the gradient penalty taken from the shared graph.  Host-logic check on
+CPU: the 11 statistics of gail.py:415-541, the parameter gradients (incl. the double-backward term), the prior update and the
+running normaliser must equal the three-pass path (itself pinned against the reference on the GPU) up to summation order."""
+import types
+
+import torch
+
+from qa_b200.config import bbc_train_cfg
+from qa_b200.rsl_rl import ActorCritic, Discriminator, Estimator, Normalizer, SSInfoGAIL
+
+
+def _alg(batched, loss_fn):
+    torch.manual_seed(3)
+    cfg = bbc_train_cfg()
+    ac = ActorCritic(101, 671, 12, 57, 10, 4, 29, 11, **cfg["policy"])
+    est = Estimator(57, 4, hidden_dims=[128, 64])
+    env = types.SimpleNamespace(task_obs_weight_decay=True, task_obs_weight=0.7, dim_c=5, num_obs_disc=49,
+                                cfg=types.SimpleNamespace(), latent_eps=None, latent_c=None)
+    disc = Discriminator(env, 98, 49, 5, 0.02, loss_fn, None, 1.0, 0.01, 0.2, 0.2, 2, 2, 0.0, [512, 256], "cpu")
+    norm = Normalizer(98)
+    g = torch.Generator().manual_seed(4)
+    norm.mean[:] = 0.1 * torch.randn(98, generator=g).numpy()
+    norm.var[:] = (0.5 + torch.rand(98, generator=g)).numpy()
+    alg_cfg = dict(cfg["algorithm"], disc_replay_buffer_size=64, use_cuda_graph=False, fused_loss=False, disc_loss_function=loss_fn)
+    alg = SSInfoGAIL(env, ac, disc, est, cfg["estimator"], None, norm, 2, 2, 49, 0.0, device="cpu", **alg_cfg)
+    alg.disc_batched = batched
+    alg._init_disc_update()
+    alg._disc_optim_step = lambda: None                                  # K8 is CUDA-only; the gradients are what is compared
+    alg.info_max_coef_on = 0.3
+    alg._info_max_coef_on.fill_(0.3)
+    return alg, env, norm
+
+
+def _batches(seed, n_pi=48, n_lb=40, n_ulb=56):
+    g = torch.Generator().manual_seed(seed)
+    c = torch.nn.functional.one_hot(torch.randint(0, 5, (n_pi,), generator=g), 5).float()
+    return ((torch.randn(n_pi, 98, generator=g), torch.rand(n_pi, 1, generator=g) * 2 - 1, c),
+            (torch.randn(n_lb, 98, generator=g), torch.randint(0, 5, (n_lb,), generator=g)),
+            torch.randn(n_ulb, 98, generator=g))
+
+
+def test_batched_step_equals_three_pass_step():
+    for loss_fn in ("MSELoss", "BCEWithLogitsLoss"):
+        res = []
+        for batched in (False, True):
+            alg, env, norm = _alg(batched, loss_fn)
+            for step in range(2):                                        # the second step sees the updated normaliser and prior
+                stats = alg.update_ss_info_gail(*_batches(10 + step))
+            norm.sync_host()
+            res.append((torch.stack(stats), alg.disc_flat.grad.clone(), env.prior_parameters.clone(),
+                        torch.from_numpy(norm.mean.copy()), torch.from_numpy(norm.var.copy()), norm.count))
+        (s0, g0, p0, m0, v0, c0), (s1, g1, p1, m1, v1, c1) = res
+        assert float(g0.abs().max()) > 0
+        assert torch.allclose(s1, s0, rtol=1e-5, atol=1e-6), (loss_fn, s0, s1)
+        assert torch.allclose(g1, g0, rtol=1e-4, atol=1e-6 * float(g0.abs().max())), (loss_fn, float((g1 - g0).abs().max()))
+        assert torch.allclose(p1, p0, rtol=1e-6, atol=1e-8)
+        assert torch.allclose(m1, m0, rtol=1e-5, atol=1e-6) and torch.allclose(v1, v0, rtol=1e-5, atol=1e-6) and c0 == c1

@@ -52,3 +52,34 @@ def test_runner_learn_books_episodes_logs_reference_tags_and_round_trips_checkpo
                    (r.alg.optim_hist_encoder, it2.runner.alg.optim_hist_encoder)):
         assert torch.equal(o1.exp_avg, o2.exp_avg) and torch.equal(o1.exp_avg_sq, o2.exp_avg_sq)
         assert int(o1.step_count) == int(o2.step_count) and float(o1.lr) == pytest.approx(float(o2.lr))
+
+
+def test_batched_discriminator_step_matches_three_pass_step_on_device():
+    """`QA_DISC_BATCHED=1` path (one shared trunk pass, DESIGN.md open item 3) against the default three-pass step, eager and as
+    a CUDA graph: the 11 statistics of the first minibatch step agree; post-step parameters agree up to Adam's sign-like
+    response to summation-order noise in the weight gradients."""
+    import types
+    from qa_b200 import synthetic
+    from test_trainer_gpu import build
+    res = []
+    for batched, graph in ((False, False), (True, False), (True, True)):
+        alg, env, norm = build(synthetic.make_weights(3), n_envs=64)
+        alg.use_cuda_graph, alg.disc_batched = graph, batched
+        env.task_obs_weight, env.prior_parameters = 0.9, torch.full((5,), 0.2, device=DEV)
+        gen = torch.Generator().manual_seed(4)
+        alg.disc_storage.insert(torch.randn(900, 98, generator=gen).to(DEV), torch.rand(900, 1, generator=gen).to(DEV),
+                                torch.nn.functional.one_hot(torch.randint(0, 5, (900,), generator=gen), 5).float().to(DEV))
+        expert = types.SimpleNamespace(preloaded_s_lb=torch.randn(500, 98, generator=gen).to(DEV),
+                                       preloaded_label=torch.randint(0, 5, (500,), generator=gen).to(DEV),
+                                       preloaded_s_ulb=torch.randn(700, 98, generator=gen).to(DEV))
+        torch.manual_seed(11)
+        stats = alg.update_disc(expert, num_updates=1)
+        norm.sync_host()
+        res.append((stats, torch.cat([v.reshape(-1) for v in alg.disc.state_dict().values()]).clone().cpu(), norm.mean.copy(),
+                    max(alg.lr_disc, alg.lr_q)))
+    for other in res[1:]:
+        for a, b in zip(res[0][0], other[0]):
+            assert abs(a - b) <= 1e-4 * abs(a) + 1e-6, (res[0][0], other[0])
+        d = (other[1] - res[0][1]).abs()
+        assert float(d.max()) <= 3 * 2.5 * res[0][3] and float((d > 2e-5).float().mean()) < 1e-2, float(d.max())
+        assert np.allclose(res[0][2], other[2], rtol=1e-5, atol=1e-7)
