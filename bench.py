@@ -35,6 +35,8 @@ METRIC = "env_steps_per_sec"
 UNIT = "env-steps/s"
 T_STEPS = 24
 ENVS_PER_GPU = 4096
+# one name for the workload in both arms (the driver compares the lines' `config`); == pipeline.BbcIteration.workload_name
+WORKLOAD_NAME = "bbc_go2_locomotion_4096x24: rollout (act, env step, disc reward, storage) + GAE + PPO update"
 K2_BYTES_PER_ENV = 11158          # algorithmic bytes of the fused obs/reward kernel per env-step
 
 
@@ -198,7 +200,7 @@ def run_ours(args):
             "ms_per_step": ms_per_step, "collection_ms": collect_ms, "learning_ms": learn_ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "tf32 GEMM operands / f32 accumulate and everything else", "data": "synthetic",
-            "config": {"workload": it.workload_name, "envs_per_gpu": cfg.num_envs, "steps_per_env": T_STEPS,
+            "config": {"workload": WORKLOAD_NAME, "envs_per_gpu": cfg.num_envs, "steps_per_env": T_STEPS,
                        "stages": it.stage_names, "rng": "in-kernel Philox4x32-10",
                        "l2": "256 MiB flush between timed iterations; per-step working set 46 MB < 126 MB L2",
                        "parallelism": f"env-sharded dp{world}"},
@@ -332,8 +334,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": full * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "bbc_go2_locomotion_4096x24: rollout + GAE + PPO update (CPU, bounded sample per step)",
-                       "envs_per_gpu": ENVS_PER_GPU, "steps_per_env": T_STEPS},
+            "config": {"workload": WORKLOAD_NAME, "envs_per_gpu": ENVS_PER_GPU, "steps_per_env": T_STEPS,
+                       "sample": "host cores, bounded sample of the workload per step (see cpu_baseline.sample)"},
             "cpu_baseline": _cpu_line(threads, rs, ms, full, r),
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
