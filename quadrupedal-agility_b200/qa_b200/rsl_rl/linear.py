@@ -7,14 +7,21 @@ the saved OUTPUT (ELU'(z) = y + 1 for z <= 0) and reduces the bias gradient in t
 dX = dZ W and dW += dZ^T X on the same tcgen05 kernel with MN-major operands (dW: split-K over the batch, fp32 atomics
 straight into the flat gradient buffer).  Layers whose widths break the 16-byte rule (N = 1, 29) fall back to cuBLAS.
 
-`set_mode("fp32")` routes everything through `F.linear` in full fp32 -- the parity-test path.
+The tcgen05 path is the DEFAULT.  `set_mode("fp32")` (or QA_LINEAR_MODE=fp32) routes everything through `F.linear` in full
+fp32 -- the parity-test path, which `tests/conftest.py` selects for the whole test session (the TF32-vs-fp32 tests switch
+modes themselves).
 """
+import os
+
 import torch
 import torch.nn.functional as F
 
 from .. import ops
 
-_MODE = "fp32"          # "fp32": cuBLAS fp32 everywhere (parity tests) | "tc": tcgen05 TF32 forward
+# "tc": tcgen05 TF32 operands / fp32 accumulate, forward and both backward contractions | "fp32": cuBLAS fp32 (parity tests)
+_MODE = os.environ.get("QA_LINEAR_MODE", "tc")
+if _MODE not in ("fp32", "tc"):
+    raise ValueError(f"QA_LINEAR_MODE must be 'tc' or 'fp32', not {_MODE!r}")
 
 
 def set_mode(mode: str) -> None:
