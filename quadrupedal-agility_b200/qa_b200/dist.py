@@ -45,3 +45,23 @@ def allreduce_mean_scalar_(x: torch.Tensor) -> torch.Tensor:
         dist.all_reduce(x, op=dist.ReduceOp.SUM)
         x /= w
     return x
+
+
+def allreduce_mean_grads_(params) -> None:
+    """In-place mean over ranks of the gradients of `params` (those that have one), as ONE all-reduce of a flat staging buffer.
+    For the torch-optimiser modules of the TSC depth student (conv / GRU on cuDNN), whose parameters do not live in a
+    `FlatParams` buffer; with equal env shards the mean of the per-shard mean-loss gradients is the union batch's gradient."""
+    _, w = world()
+    if w == 1:
+        return
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    flat /= w
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].view_as(g))
+        off += n

@@ -598,6 +598,7 @@ class PPO:
         loss = (scandots_latent_batch.detach() - depth_latent_batch).norm(p=2, dim=1).mean()
         self.depth_encoder_optimizer.zero_grad()
         loss.backward()
+        qdist.allreduce_mean_grads_(list(self.depth_encoder.parameters()))
         nn.utils.clip_grad_norm_(self.depth_encoder.parameters(), self.max_grad_norm)
         self.depth_encoder_optimizer.step()
         return loss.item()
@@ -626,6 +627,8 @@ class PPO:
         loss = actor_loss + yaw_loss + obst_loss
         self.depth_actor_optimizer.zero_grad()
         loss.backward()
+        # env-sharded ranks (SURVEY 8e, config "TSC-student ... 2xB200"): one gradient all-reduce per optimiser step
+        qdist.allreduce_mean_grads_([*self.depth_actor.parameters(), *self.depth_encoder.parameters()])
         nn.utils.clip_grad_norm_(self.depth_actor.parameters(), self.max_grad_norm)
         self.depth_actor_optimizer.step()
         n = depth_batch.size(0)
@@ -638,6 +641,7 @@ class PPO:
             byol_loss = learner(depth_batch[i:i + bs])
             self.byol_optimizer.zero_grad()
             byol_loss.backward()
+            qdist.allreduce_mean_grads_(list(learner.parameters()))           # batch-norm statistics: SyncBatchNorm (byol.py:44-46)
             self.byol_optimizer.step()
             byol_total += byol_loss.detach()
             learner.update_moving_average()
@@ -652,6 +656,7 @@ class PPO:
         act_loss = (actions_teacher_batch.detach() - actions_student_batch).norm(p=2, dim=1).mean()
         self.depth_actor_optimizer.zero_grad()
         (enc_loss + act_loss).backward()
+        qdist.allreduce_mean_grads_([*self.depth_actor.parameters(), *self.depth_encoder.parameters()])
         nn.utils.clip_grad_norm_([*self.depth_actor.parameters(), *self.depth_encoder.parameters()], self.max_grad_norm)
         self.depth_actor_optimizer.step()
         return enc_loss.item(), act_loss.item()

@@ -37,6 +37,31 @@ def student_rollout_and_update(alg, inputs, aug_p, seed, stride=997):
         m.fn, m.p = counted(m.fn), aug_p
     random.seed(seed)
     torch.manual_seed(seed)
+    cat = student_forward(alg, inputs)
+    dev = next(actor.parameters()).device
+    stats = alg.update_depth_actor(cat["student"], inputs["actions_teacher"].to(dev), cat["yaw_s"], cat["yaw_t"], cat["obst_s"],
+                                   cat["obst_t"], cat["depth"])
+    enc.detach_hidden_states()
+    for m, fn, p in saved:
+        m.fn, m.p = fn, p
+    flat = lambda mod: torch.cat([p.detach().reshape(-1) for p in mod.parameters()])[::stride].cpu().clone()   # noqa: E731
+    return {"encoder_out": cat["out"].detach().cpu(), "student_actions": cat["student"].detach().cpu(),
+            "stats": torch.tensor(stats, dtype=torch.float64), "hidden": enc.hidden_states.detach().cpu().clone(),
+            "actor_params": flat(actor), "encoder_params": flat(enc), "target_params": flat(enc.byol_learner.target_encoder),
+            "n_aug_applied": applied[0]}
+
+
+def shard_inputs(inputs, lo, hi):
+    """The env shard [lo, hi) of a `synthetic.make_student_inputs` dict."""
+    T, N = inputs["obs"].shape[:2]
+    teacher = inputs["actions_teacher"].reshape(T, N, -1)[:, lo:hi].flatten(0, 1)
+    return dict(obs=inputs["obs"][:, lo:hi], depth=inputs["depth"][:, lo:hi], delta_yaw_ok=inputs["delta_yaw_ok"][:, lo:hi],
+                actions_teacher=teacher)
+
+
+def student_forward(alg, inputs):
+    """T recurrent student steps (on_policy_runner.py:320-371) from a fresh GRU state; returns the concatenated buffers."""
+    enc, actor = alg.depth_encoder, alg.depth_actor
     enc.train()
     actor.train()
     enc.hidden_states = None
@@ -60,17 +85,7 @@ def student_rollout_and_update(alg, inputs, aug_p, seed, stride=997):
         buf["obst_s"].append(obst)
         buf["obst_t"].append(obs[:, P - A + Y:P])
         buf["depth"].append(depth.clone())
-    cat = {k: torch.cat(v, dim=0) for k, v in buf.items()}
-    stats = alg.update_depth_actor(cat["student"], inputs["actions_teacher"].to(dev), cat["yaw_s"], cat["yaw_t"], cat["obst_s"],
-                                   cat["obst_t"], cat["depth"])
-    enc.detach_hidden_states()
-    for m, fn, p in saved:
-        m.fn, m.p = fn, p
-    flat = lambda mod: torch.cat([p.detach().reshape(-1) for p in mod.parameters()])[::stride].cpu().clone()   # noqa: E731
-    return {"encoder_out": cat["out"].detach().cpu(), "student_actions": cat["student"].detach().cpu(),
-            "stats": torch.tensor(stats, dtype=torch.float64), "hidden": enc.hidden_states.detach().cpu().clone(),
-            "actor_params": flat(actor), "encoder_params": flat(enc), "target_params": flat(enc.byol_learner.target_encoder),
-            "n_aug_applied": applied[0]}
+    return {k: torch.cat(v, dim=0) for k, v in buf.items()}
 
 
 def byol_forward_backward(alg, inputs, aug_p, seed):

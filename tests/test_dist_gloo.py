@@ -65,3 +65,61 @@ def test_shard_envs_rejects_uneven_split():
         qdist.shard_envs(10, 0, 4)
     assert qdist.shard_envs(32768, 7, 8) == (28672, 4096)
     assert qdist.world() == (0, 1)
+
+
+# ---- TSC depth student (config "TSC-student ... 2xB200"): one gradient all-reduce per distillation step --------------------
+_STUDENT_KEYS = ("actor_trunk.0.weight", "actor_c.bias")
+_ENCODER_KEYS = ("base_backbone.image_compression.0.weight", "combination_mlp.2.weight", "rnn.weight_hh_l0", "output_mlp.0.bias")
+
+
+def _student_grads(alg, inputs):
+    """Distillation loss of update_depth_actor (ppo.py:329-337) on `inputs`, backward, rank-mean of the gradients."""
+    from student_case import student_forward
+    for m in alg.depth_encoder.byol_learner.augment1:
+        m.p = -1.0                                                  # augmentation off: ranks would draw different noise
+    cat = student_forward(alg, inputs)
+    a, y, o = alg.depth_actor_losses(cat["student"], inputs["actions_teacher"], cat["yaw_s"], cat["yaw_t"], cat["obst_s"], cat["obst_t"])
+    params = [*alg.depth_actor.parameters(), *alg.depth_encoder.parameters()]
+    for p in params:
+        p.grad = None
+    (a + y + o).backward()
+    qdist.allreduce_mean_grads_(params)
+    an, en = dict(alg.depth_actor.named_parameters()), dict(alg.depth_encoder.named_parameters())
+    return {**{k: an[k].grad.clone() for k in _STUDENT_KEYS}, **{k: en[k].grad.clone() for k in _ENCODER_KEYS}}
+
+
+def _student_worker(rank, world, port, q):
+    import test_tsc_student as TS
+    from qa_b200 import synthetic
+    from student_case import shard_inputs
+    torch.set_num_threads(2)
+    alg = TS.build("cpu")                                           # before init_process_group: BatchNorm1d, not SyncBatchNorm
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    inputs = synthetic.make_student_inputs(4, 2, 5)
+    start, n = qdist.shard_envs(4, rank, world)
+    grads = _student_grads(alg, shard_inputs(inputs, start, start + n))
+    q.put((rank, {k: v.numpy() for k, v in grads.items()}))
+    dist.destroy_process_group()
+
+
+def test_student_distillation_gradients_average_to_the_union_batch_gloo():
+    import numpy as np
+    import test_tsc_student as TS
+    from qa_b200 import synthetic
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_student_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    out = dict(q.get(timeout=300) for _ in range(world))
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = _student_grads(TS.build("cpu"), synthetic.make_student_inputs(4, 2, 5))       # one process, all four envs
+    for k, w in want.items():
+        w = w.numpy()
+        assert np.array_equal(out[0][k], out[1][k]), k                                   # ranks agree bit for bit
+        assert float(np.abs(w).max()) > 0
+        assert np.allclose(out[0][k], w, rtol=1e-4, atol=1e-6 * float(np.abs(w).max())), (k, float(np.abs(out[0][k] - w).max()))
