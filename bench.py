@@ -222,6 +222,8 @@ def run_ours(args):
             line["tsc_env"] = time_tsc_env(dev)
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if world == 1 and not args.no_torch_gpu_baseline:
+            line["torch_gpu_baseline"] = torch_gpu_baseline_sample(dev)
         print(json.dumps(line), flush=True)
     if world > 1:
         # Leave without tearing NCCL down: destroy_process_group() blocks for minutes while CUDA graphs that captured
@@ -309,6 +311,43 @@ def _cpu_line(threads, rollout_steps, minibatch_steps, full, r):
                        f"extrapolated to one full iteration = {full:.2f} s")}
 
 
+def torch_gpu_baseline_sample(dev, n_envs=ENVS_PER_GPU):
+    """the reference's own single-GPU path -- its PyTorch op sequence (the oracle port, eager torch kernels, fp32)
+    on the SAME B200 and workload, one full iteration (24 env steps + GAE + 20 PPO minibatch steps) after a short warm-up.
+    This is the number north_star's ">= 4x the reference's single-GPU env-steps/sec" refers to; a reported baseline, guarded so
+    that a failure here can never cost the benchmark line."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import bbc_env as O
+        import trainer as OT
+        from qa_b200 import pipeline, synthetic
+        tf32 = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False                  # the reference runs fp32 matmuls (torch default)
+        mv = lambda d: {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in d.items()}     # noqa: E731
+        cfg, static, snaps, table = build_workload(0, "cpu", n_envs=n_envs)
+        draws = []
+        for t in range(T_STEPS):
+            d = synthetic.make_rng_draws(cfg, seed=1234, step=t)
+            d["mocap_clip_idx"] = table.sample_clip(d["rt_c_idx"], d["mocap_clip_u"])
+            draws.append(mv(d))
+        static, snaps, table = mv(static), [mv(s) for s in snaps], table.to(dev)
+        w = synthetic.make_weights(1)
+        w = {k: (mv(v) if isinstance(v, dict) else v.to(dev)) for k, v in w.items()}
+        run = lambda rs, ms: pipeline.cpu_oracle_iteration(O, OT, cfg, static, snaps, draws, table, w, rollout_steps=rs,   # noqa: E731
+                                                           minibatch_steps=ms, device=dev)
+        run(2, 2)                                                        # warm-up: allocator, cuBLAS handles, autotuning
+        r = run(T_STEPS, 20)
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        full = r["t_rollout"] + r["t_gae"] + r["t_update"]
+        return {"value": T_STEPS * n_envs / full, "unit": UNIT, "kind": "port",
+                "ms_per_step": full * 1e3, "collection_ms": r["t_rollout"] * 1e3, "learning_ms": (r["t_gae"] + r["t_update"]) * 1e3,
+                "sample": f"oracle/ port of the reference's PyTorch path, eager fp32 torch {torch.__version__} kernels on the same GPU, "
+                          f"{n_envs} envs, one full iteration (24 env steps, GAE, 20 PPO minibatch steps of {6 * n_envs}), wall clock "
+                          f"with device synchronisation"}
+    except Exception as e:                                               # noqa: BLE001  (a baseline must not break the line)
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
+
+
 def cpu_baseline_sample():
     threads = os.cpu_count() or 1
     rs, ms = 12, 6                                   # ~10-20 s of CPU work
@@ -350,6 +389,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--linear", default="tc", choices=["tc", "cublas"],
                     help="dense layers: tc = hand-written tcgen05 TF32 forward (default), cublas = library TF32 GEMMs")
+    ap.add_argument("--no-torch-gpu-baseline", action="store_true",
+                    help="skip the reference's PyTorch path timed on the same GPU (reported beside the metric)")
     ap.add_argument("--k2-bulk", type=int, default=2,
                     help="K2 variant: 2 = 8-env TMA tiles (default), 1 = warp-per-env + TMA row stores, 0 = warp stores")
     args = ap.parse_args()

@@ -230,10 +230,27 @@ class BbcIteration:
 
 
 def cpu_oracle_iteration(O, OT, cfg, static, snaps, draws, table, weights, rollout_steps=None, minibatch_steps=20,
-                         gamma=0.99, lam=0.95, num_mini_batches=4):
-    """The same iteration through the CPU oracle (test infrastructure; called only by bench.py's cpu_baseline /
-    --impl reference legs).  `rollout_steps` <= T env steps and `minibatch_steps` <= 20 PPO minibatch steps are
-    executed (a bounded sample); returns dict(t_rollout, t_gae, t_update, rollout_steps, minibatch_steps)."""
+                         gamma=0.99, lam=0.95, num_mini_batches=4, device="cpu"):
+    """The same iteration through the oracle port of the reference's PyTorch path (test infrastructure; called only by
+    bench.py's baseline legs: cpu_baseline / --impl reference on the host cores, torch_gpu_baseline with `device` = the
+    GPU, i.e. the reference's own single-GPU path of north_star's >= 4x target).  `rollout_steps` <= T env steps and
+    `minibatch_steps` <= 20 PPO minibatch steps are executed (a bounded sample); every input must already live on `device`.
+    Returns dict(t_rollout, t_gae, t_update, rollout_steps, minibatch_steps)."""
+    dev = torch.device(device)
+    if dev.type == "cuda":
+        _zeros, _ones, _clock = torch.zeros, torch.ones, time.perf_counter
+
+        def zeros(*a, **k):
+            return _zeros(*a, device=dev, **k)
+
+        def ones(*a, **k):
+            return _ones(*a, device=dev, **k)
+
+        def clock():
+            torch.cuda.synchronize(dev)
+            return _clock()
+    else:
+        zeros, ones, clock = torch.zeros, torch.ones, time.perf_counter
     T, N = len(snaps), cfg.num_envs
     R = T if rollout_steps is None else min(rollout_steps, T)
     g = torch.Generator().manual_seed(7)
@@ -243,16 +260,16 @@ def cpu_oracle_iteration(O, OT, cfg, static, snaps, draws, table, weights, rollo
     opt_a = torch.optim.Adam(list(sd_ac.values()), lr=1e-3)
     opt_e = torch.optim.Adam(list(sd_est.values()), lr=1e-4)
     W = 671
-    st = dict(obs=torch.zeros(T, N, W), actions=torch.zeros(T, N, 12), rewards=torch.zeros(T, N, 1),
-              dones=torch.zeros(T, N, 1, dtype=torch.uint8), values=torch.zeros(T, N, 1), logp=torch.zeros(T, N, 1),
-              mu=torch.zeros(T, N, 12), sigma=torch.ones(T, N, 12))
-    obs = torch.zeros(N, W)
+    st = dict(obs=zeros(T, N, W), actions=zeros(T, N, 12), rewards=zeros(T, N, 1),
+              dones=zeros(T, N, 1, dtype=torch.uint8), values=zeros(T, N, 1), logp=zeros(T, N, 1),
+              mu=zeros(T, N, 12), sigma=ones(T, N, 12))
+    obs = zeros(N, W)
     disc_hist = torch.stack([carried["obs_disc_buf"]] * 2, dim=1)
-    time_outs = torch.zeros(N, dtype=torch.bool)
-    t0 = time.perf_counter()
+    time_outs = zeros(N, dtype=torch.bool)
+    t0 = clock()
     with torch.no_grad():
         for t in range(R):
-            a = OT.act(sd_ac, sd_est, obs, obs, torch.randn(N, 12, generator=g))
+            a = OT.act(sd_ac, sd_est, obs, obs, torch.randn(N, 12, generator=g).to(dev))
             hist, act = O.action_push(cfg, carried["action_history_buf"], a["actions"], delay=0)
             s = dict(snaps[t])
             s.update({k: carried[k] for k in CARRIED})
@@ -275,13 +292,13 @@ def cpu_oracle_iteration(O, OT, cfg, static, snaps, draws, table, weights, rollo
             obs = out["obs_buf"]
             for k in CARRIED:
                 carried[k] = out[k]
-    t1 = time.perf_counter()
+    t1 = clock()
     with torch.no_grad():
         last_values = OT.critic_value(sd_ac, obs)
         returns, adv = OT.compute_returns(st["rewards"], st["values"], st["dones"], last_values, gamma, lam)
-    t2 = time.perf_counter()
+    t2 = clock()
     flat = lambda x: x.flatten(0, 1)                                                        # noqa: E731
-    idx = torch.randperm(T * N, generator=g)
+    idx = torch.randperm(T * N, generator=g).to(dev)
     mb = (T * N) // num_mini_batches
     lr = 1e-3
     for k in range(minibatch_steps):
@@ -301,5 +318,5 @@ def cpu_oracle_iteration(O, OT, cfg, static, snaps, draws, table, weights, rollo
         L["ppo_loss"].backward()
         torch.nn.utils.clip_grad_norm_(list(sd_ac.values()), 1.0)
         opt_a.step()
-    t3 = time.perf_counter()
+    t3 = clock()
     return dict(t_rollout=t1 - t0, t_gae=t2 - t1, t_update=t3 - t2, rollout_steps=R, minibatch_steps=minibatch_steps)

@@ -34,3 +34,19 @@ def test_reference_arm_on_a_non_zero_rank_prints_nothing():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                           "--warmup", "0"], env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and not any(l.startswith("{") for l in out.stdout.splitlines()), out.stdout + out.stderr
+
+
+def test_torch_baseline_leg_runs_the_full_iteration_and_never_raises():
+    """The leg that times the reference's PyTorch path on the bench device (here: the host, 256 envs) -- same code, `device`
+    is the only difference on the GPU box; a failure inside must come back as an `error` entry, not as an exception."""
+    import torch
+    import bench
+    threads = torch.get_num_threads()
+    try:
+        out = bench.torch_gpu_baseline_sample(torch.device("cpu"), n_envs=256)
+        assert "error" not in out, out
+        assert out["value"] > 0 and out["kind"] == "port" and abs(out["ms_per_step"] - out["collection_ms"] - out["learning_ms"]) < 1e-6
+        bad = bench.torch_gpu_baseline_sample("no-such-device", n_envs=256)
+        assert set(bad) == {"error"}
+    finally:
+        torch.set_num_threads(threads)
