@@ -174,6 +174,17 @@ class BbcEnvConfig:
     def center_height_index(self) -> int:       # legged_robot.py:266 (shape[1] // 2 + 1)
         return self.num_height_points // 2 + 1
 
+    @property
+    def env(self):
+        """`cfg.env.*` as the reference's trainer reads it (bbc/rsl_rl/runners/on_policy_runner.py:37-63, gail.py:68-87;
+        values of go2_locomotion_config.py:9-32): lets the reference's own runner be constructed over this env."""
+        import types
+        return types.SimpleNamespace(
+            num_envs=self.num_envs, num_prop=NUM_PROP, num_explicit=NUM_EXPLICIT, num_latent=NUM_LATENT, num_command=NUM_COMMAND,
+            num_obs=NUM_PROP + NUM_EXPLICIT + NUM_LATENT + NUM_COMMAND, num_privileged_obs=NUM_PROP + NUM_EXPLICIT + NUM_LATENT + NUM_COMMAND,
+            num_obs_disc=49, history_len=HISTORY_LEN, disc_history_len=2, disc_obs_len=DISC_OBS_LEN, obs_disc_weight_step=0.0,
+            frame_duration_scale=1.0, root_height_obs=self.root_height_obs, send_timeouts=self.send_timeouts)
+
     def reward_scales_dt(self) -> List[float]:
         """scale_k * dt in REWARD_NAMES order, rounded the way python does (legged_robot.py:932)."""
         return [REWARD_SCALES_RAW[k] * self.dt for k in REWARD_NAMES]

@@ -81,6 +81,32 @@ class TscEnvConfig:
     def max_episode_length(self) -> float:
         return float(math.ceil(self.episode_length_s / self.dt))
 
+    # `cfg.env.* / cfg.domain_rand.* / ...` as the reference's TSC runner reads them (tsc/rsl_rl/runners/on_policy_runner.py:33-57,
+    # 281-296): read-only views; change scalars through `LeggedRobotTSC.reconfigure(...)`, which rebuilds the kernel constants
+    @property
+    def env(self):
+        import types
+        return types.SimpleNamespace(
+            num_envs=self.num_envs, n_proprio=65, n_delta_yaw=2, n_obst_type=self.num_obstacle_types, n_auxiliary=2 + self.num_obstacle_types,
+            n_scan=132, n_priv=4, n_priv_latent=29, history_len=self.history_len, num_command=self.num_actions_c + len(self.mocap_category_all),
+            num_observations_bbc=671 - 570, num_actions_bbc=12, num_obs_disc=49, disc_obs_len=2, next_goal_threshold=self.next_goal_threshold,
+            draw_height_maps=False)
+
+    @property
+    def domain_rand(self):
+        import types
+        return types.SimpleNamespace(action_buf_len=self.action_buf_len, randomize_action=self.randomize_action)
+
+    @property
+    def noise(self):
+        import types
+        return types.SimpleNamespace(add_noise=False)
+
+    @property
+    def obstacle(self):
+        import types
+        return types.SimpleNamespace(curriculum=False)
+
     @property
     def reward_names(self):
         return [k for k in self.reward_scales if k != "termination"] + ["termination"]
