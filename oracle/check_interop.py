@@ -1,0 +1,95 @@
+"""TEST INFRASTRUCTURE (build container only): the drop-in boundary of SURVEY 8(b), checked from the REFERENCE's side.
+
+The unmodified `SSInfoGAIL.act` / `update_actor_critic` (bbc/rsl_rl/algorithms/gail.py:176-197, 328-413) are run twice on the
+same inputs -- once over the reference's own `ActorCritic` / `Estimator`, once over THIS package's classes constructed with the
+same arguments and loaded from the same `state_dict` -- and must produce the same actions, values, log-probs, the same six loss
+statistics, the same adapted learning rate and the same post-step parameters.  I.e. a maintainer can hand
+`qa_b200.rsl_rl.ActorCritic` to the reference trainer unchanged.  (CPU, fp32 mode; exits non-zero on any mismatch.)
+
+  python oracle/check_interop.py
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.join(ROOT, "quadrupedal-agility_b200"))
+
+from gen_golden_policy import build_reference_nets, make_alg  # noqa: E402
+from qa_b200 import synthetic  # noqa: E402
+from qa_b200.config import bbc_train_cfg  # noqa: E402
+from ref_harness import import_reference  # noqa: E402
+
+
+def run(ref, ac, est, obs, draw, batch_noise):
+    alg = make_alg(ref, ac, est)
+    Normal = torch.distributions.Normal
+    orig, orig_randn_like = Normal.sample, torch.randn_like
+    out = {}
+    try:
+        # the same N(0,1) draw for both implementations: the reference samples through Normal.sample, this package through
+        # mean + std * randn_like(mean)
+        Normal.sample = lambda self, sample_shape=torch.Size(): (self.loc + self.scale * draw).detach()
+        torch.randn_like = lambda t, **k: draw.clone() if t.shape == draw.shape else orig_randn_like(t, **k)
+        for he in (False, True):
+            with torch.inference_mode():
+                a = alg.act(obs.clone(), obs.clone(), hist_encoding=he)
+            tr = alg.transition
+            out[f"act{int(he)}"] = [t.clone() for t in (a, tr.values, tr.actions_log_prob, tr.action_mean, tr.action_sigma)]
+        a0, v0, lp0, mu0, sg0 = out["act0"]
+        n1, n2, n3, n4 = batch_noise
+        sample = (obs, obs, a0, v0, n1, v0 + 0.3 * n2, (lp0 + 0.05 * n3).unsqueeze(1), mu0 + 0.05 * n4, sg0 * 1.05, (None, None), None)
+        Normal.sample = lambda self, sample_shape=torch.Size(): self.loc.detach()
+        losses = alg.update_actor_critic(sample)
+    finally:
+        Normal.sample, torch.randn_like = orig, orig_randn_like
+    out["losses"] = [torch.as_tensor(x).float().mean().detach() for x in losses]
+    out["lr"] = alg.lr_ac
+    out["ac"] = {k: v.detach().clone() for k, v in ac.state_dict().items()}
+    out["est"] = {k: v.detach().clone() for k, v in est.state_dict().items()}
+    return out
+
+
+def main():
+    ref = import_reference("bbc")
+    from qa_b200.rsl_rl import ActorCritic, Estimator
+    from qa_b200.rsl_rl import linear
+    linear.set_mode("fp32")
+    torch.set_num_threads(1)
+    w = synthetic.make_weights(3)
+    z = np.load(os.path.join(ROOT, "tests", "golden", "bbc_env_n64a.npz"))
+    obs = torch.from_numpy(z["ref.obs_buf"]).clone()
+    N = obs.shape[0]
+    g = torch.Generator().manual_seed(5)
+    draw = torch.randn(N, 12, generator=g)
+    noise = (torch.randn(N, 1, generator=g), torch.randn(N, 1, generator=g), torch.randn(N, generator=g), torch.randn(N, 12, generator=g))
+    ac_r, est_r, _, _, _ = build_reference_nets(ref, w)
+    cfg = bbc_train_cfg()
+    ac_o = ActorCritic(101, 671, 12, 57, 10, 4, 29, 11, **cfg["policy"])
+    ac_o.load_state_dict(w["ac"])
+    est_o = Estimator(input_dim=57, output_dim=4, hidden_dims=[128, 64])
+    est_o.load_state_dict(w["est"])
+    assert list(ac_o.state_dict()) == list(ac_r.state_dict()) and list(est_o.state_dict()) == list(est_r.state_dict())
+    assert [tuple(p.shape) for p in ac_o.parameters()] == [tuple(p.shape) for p in ac_r.parameters()]
+    want, got = run(ref, ac_r, est_r, obs, draw, noise), run(ref, ac_o, est_o, obs, draw, noise)
+    worst = 0.0
+    for he in ("act0", "act1"):
+        for a, b in zip(want[he], got[he]):
+            assert torch.allclose(a, b, rtol=1e-5, atol=1e-6), (he, float((a - b).abs().max()))
+            worst = max(worst, float((a - b).abs().max()))
+    for a, b in zip(want["losses"], got["losses"]):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-7), (float(a), float(b))
+    assert abs(want["lr"] - got["lr"]) < 1e-12
+    for part in ("ac", "est"):
+        for k in want[part]:
+            assert torch.allclose(want[part][k], got[part][k], rtol=1e-5, atol=1e-6), (part, k)
+    print(f"interop OK: reference SSInfoGAIL.act / update_actor_critic over qa_b200 ActorCritic + Estimator == over the reference's "
+          f"(max |diff| of act outputs {worst:.1e}; losses {[round(float(x), 6) for x in got['losses']]}; lr {got['lr']:.6g})")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,16 @@
+"""Drop-in boundary, seen from the reference's side: the UNMODIFIED reference trainer code runs over this package's
+`ActorCritic` / `Estimator` and gives the results it gives over its own modules.  Needs the reference tree (build container);
+runs in a fresh interpreter because the reference's `rsl_rl` package and this package's pickle alias share a module name."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/bbc"), reason="the reference tree only exists in the build container")
+def test_reference_ssinfogail_runs_over_this_packages_actor_critic():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "check_interop.py")], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "interop OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
