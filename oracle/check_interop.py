@@ -6,7 +6,10 @@ same arguments and loaded from the same `state_dict` -- and must produce the sam
 statistics, the same adapted learning rate and the same post-step parameters.  I.e. a maintainer can hand
 `qa_b200.rsl_rl.ActorCritic` to the reference trainer unchanged.  (CPU, fp32 mode; exits non-zero on any mismatch.)
 
-  python oracle/check_interop.py
+The same for the TSC fork: `PPO.act` / `PPO.update` (tsc/rsl_rl/algorithms/ppo.py:101-262) over `qa_b200.rsl_rl.ActorCriticTSC`.
+
+  python oracle/check_interop.py          # bbc
+  python oracle/check_interop.py tsc      # tsc (own process: the two forks share package names)
 """
 import os
 import sys
@@ -91,5 +94,92 @@ def main():
           f"(max |diff| of act outputs {worst:.1e}; losses {[round(float(x), 6) for x in got['losses']]}; lr {got['lr']:.6g})")
 
 
+def run_tsc(ref, OT, ac, est, obs, draw, mode_u, noise):
+    """tsc/rsl_rl/algorithms/ppo.py: PPO.act (:101-125) and one PPO.update (:159-262) over the given modules."""
+    N = obs.shape[0]
+    P = ref.ppo.PPO
+    alg = P.__new__(P)
+    alg.device, alg.actor_critic, alg.estimator = "cpu", ac, est
+    alg.train_with_estimated_states, alg.num_prop, alg.num_auxiliary, alg.num_scan, alg.priv_states_dim = True, 57, 8, 132, 4
+    alg.transition = ref.RolloutStorage.Transition()
+    alg.optimizer = torch.optim.Adam(ac.parameters(), lr=5e-4)
+    alg.estimator_optimizer = torch.optim.Adam(est.parameters(), lr=1e-4)
+    alg.learning_rate, alg.desired_kl, alg.schedule = 5e-4, 0.01, "adaptive"
+    alg.clip_param, alg.use_clipped_value_loss, alg.value_loss_coef, alg.entropy_coef = 0.2, True, 1.0, 0.01
+    alg.max_grad_norm, alg.num_learning_epochs, alg.num_mini_batches = 1.0, 1, 1
+    alg.priv_reg_coef_schedual, alg.counter = [0, 0.1, 500, 1000], 800
+    alg.gamma, alg.lam = 0.99, 0.95
+    alg.update_counter = lambda: None
+    Normal, Categorical = torch.distributions.Normal, torch.distributions.Categorical
+    saved = (Normal.sample, Categorical.sample, torch.randn_like, torch.rand)
+    out = {}
+    try:
+        Normal.sample = lambda self, sample_shape=torch.Size(): (self.loc + self.scale * draw).detach()
+        Categorical.sample = lambda self, sample_shape=torch.Size(): OT.sample_mode(self.probs, mode_u)
+        torch.randn_like = lambda t, **k: draw.clone() if t.shape == draw.shape else saved[2](t, **k)
+        torch.rand = lambda *a, **k: mode_u.clone() if a == (N,) else saved[3](*a, **k)
+        for he in (False, True):
+            with torch.no_grad():
+                a = alg.act(obs.clone(), obs.clone(), None, hist_encoding=he)
+            tr = alg.transition
+            out[f"act{int(he)}"] = [t.clone() for t in (a, tr.values, tr.actions_log_prob_d, tr.actions_log_prob_c, tr.action_mean,
+                                                         tr.action_sigma)]
+        a0, v0, lpd, lpc, mu0, sg0 = out["act0"]
+        n1, n2, n3, n4, n5 = noise
+        st = ref.RolloutStorage(N, 1, [800], [None], [19], device="cpu")
+        st.observations[0], st.actions[0], st.values[0] = obs, a0, v0
+        st.advantages[0], st.returns[0] = n1, v0 + 0.3 * n2
+        st.actions_log_prob_d[0], st.actions_log_prob_c[0] = (lpd.reshape(N) + 0.05 * n3).unsqueeze(1), (lpc.reshape(N) + 0.05 * n4).unsqueeze(1)
+        st.mu[0], st.sigma[0] = mu0 + 0.05 * n5, sg0 * 1.05
+        alg.storage = st
+        out["update"] = [float(x) for x in alg.update()]
+    finally:
+        Normal.sample, Categorical.sample, torch.randn_like, torch.rand = saved
+    out["lr"] = alg.learning_rate
+    out["ac"] = {k: v.detach().clone() for k, v in ac.state_dict().items()}
+    out["est"] = {k: v.detach().clone() for k, v in est.state_dict().items()}
+    return out
+
+
+def main_tsc():
+    ref = import_reference("tsc")
+    import tsc_trainer as OT
+    from qa_b200.rsl_rl import ActorCriticTSC, Estimator
+    from qa_b200.rsl_rl import linear
+    linear.set_mode("fp32")
+    torch.set_num_threads(1)
+    w = synthetic.make_tsc_weights(3)
+    policy = dict(scan_encoder_dims=[128, 64, 32], actor_hidden_dims=[512, 256, 128], critic_hidden_dims=[512, 256, 128],
+                  priv_encoder_dims=[64], activation="elu", init_noise_std=1.0, tanh_encoder_output=False)
+    N = 64
+    g = torch.Generator().manual_seed(3)
+    obs = torch.randn(N, 800, generator=g) * 0.5
+    obs[:, 65:197] = torch.clip(obs[:, 65:197], -1, 1)
+    draw, mode_u = torch.randn(N, 18, generator=g), torch.rand(N, generator=g)
+    noise = (torch.randn(N, 1, generator=g), torch.randn(N, 1, generator=g), torch.randn(N, generator=g), torch.randn(N, generator=g),
+             torch.randn(N, 18, generator=g))
+    res = []
+    for AC, E in ((ref.actor_critic.ActorCriticTSC, ref.estimator.Estimator), (ActorCriticTSC, Estimator)):
+        ac = AC(65, 8, 132, 800, 29, 4, 10, 3, 6, device="cpu", **policy)
+        ac.load_state_dict(w["ac"])
+        est = E(input_dim=57, output_dim=4, hidden_dims=[128, 64])
+        est.load_state_dict(w["est"])
+        res.append(run_tsc(ref, OT, ac, est, obs, draw, mode_u, noise))
+    want, got = res
+    worst = 0.0
+    for he in ("act0", "act1"):
+        for a, b in zip(want[he], got[he]):
+            assert a.shape == b.shape and torch.allclose(a, b, rtol=1e-5, atol=1e-6), (he, float((a - b).abs().max()))
+            worst = max(worst, float((a - b).abs().max()))
+    for a, b in zip(want["update"], got["update"]):
+        assert abs(a - b) <= 1e-5 * abs(a) + 1e-7, (want["update"], got["update"])
+    assert abs(want["lr"] - got["lr"]) < 1e-12
+    for part in ("ac", "est"):
+        for k in want[part]:
+            assert torch.allclose(want[part][k], got[part][k], rtol=1e-5, atol=1e-6), (part, k)
+    print(f"interop OK (tsc): reference PPO.act / PPO.update over qa_b200 ActorCriticTSC + Estimator == over the reference's "
+          f"(max |diff| of act outputs {worst:.1e}; update() = {[round(x, 6) for x in got['update']]}; lr {got['lr']:.6g})")
+
+
 if __name__ == "__main__":
-    main()
+    main_tsc() if sys.argv[1:] == ["tsc"] else main()

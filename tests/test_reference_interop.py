@@ -14,3 +14,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_reference_ssinfogail_runs_over_this_packages_actor_critic():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "check_interop.py")], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "interop OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/tsc"), reason="the reference tree only exists in the build container")
+def test_reference_tsc_ppo_runs_over_this_packages_actor_critic_tsc():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "check_interop.py"), "tsc"], capture_output=True, text=True,
+                         timeout=600)
+    assert out.returncode == 0 and "interop OK (tsc)" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
