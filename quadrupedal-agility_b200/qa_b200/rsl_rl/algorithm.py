@@ -326,7 +326,7 @@ class SSInfoGAIL:
                     loss = (priv - hist_latent).norm(p=2, dim=1).mean()
                 self.ac_flat.grad[opt.lo:opt.hi].zero_()
                 loss.backward()
-                opt.step()
+                opt.step(qdist.allreduce_flat_(self.ac_flat.grad[opt.lo:opt.hi]))       # env shards: rank-mean gradient (1/W in K8)
                 total += loss.detach()
         n = self.num_learning_epochs * self.num_mini_batches
         st.clear()

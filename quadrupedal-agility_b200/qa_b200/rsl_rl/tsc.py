@@ -585,7 +585,7 @@ class PPO:
                     loss = (priv - hist_latent).norm(p=2, dim=1).mean()
                 self.ac_flat.grad[opt.lo:opt.hi].zero_()
                 loss.backward()
-                opt.step()
+                opt.step(qdist.allreduce_flat_(self.ac_flat.grad[opt.lo:opt.hi]))       # env shards: rank-mean gradient (1/W in K8)
                 total += loss.detach()
         st.clear()
         self.update_counter()
