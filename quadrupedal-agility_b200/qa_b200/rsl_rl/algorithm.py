@@ -483,7 +483,10 @@ class SSInfoGAIL:
         ss_loss = F.cross_entropy(pred_c_lb, label_exp_lb)                      # on the soft-maxed output, as the reference
         lab_pi = torch.argmax(policy_latent_c, dim=-1)
         with torch.no_grad():                                                   # prior estimate :462-464
-            env.prior_parameters.mul_(1 - self.prior_soft_coef).add_(pred_c_ulb.mean(dim=0) * self.prior_soft_coef)
+            prior_batch = pred_c_ulb.mean(dim=0)
+            if self.world_size > 1:                                             # the union batch's mean (equal shards)
+                prior_batch = qdist.allreduce_mean_scalar_(prior_batch.clone())
+            env.prior_parameters.mul_(1 - self.prior_soft_coef).add_(prior_batch * self.prior_soft_coef)
         info_max_loss = torch.mean(-torch.sum(pred_c_ulb * torch.log(pred_c_ulb + 1e-20), dim=-1))
         if self.disc_loss_function == "BCEWithLogitsLoss":
             disc_exp_loss = F.binary_cross_entropy_with_logits(logits_exp, torch.ones_like(logits_exp))
@@ -510,16 +513,16 @@ class SSInfoGAIL:
                 self.disc_weight_decay * disc_weight_decay)
         self.disc_flat.zero_grad()
         loss.backward()
-        self._disc_optim_step()
+        self._disc_optim_step(qdist.allreduce_flat_(self.disc_flat.grad))       # env shards: ONE all-reduce per step, 1/W in K8
         ac = self.actor_critic
         if not ac.fixed_std and self.min_std is not None:                       # :523-524
             ac.std.data.clamp_(min=self.min_std)
         if self.disc_normalizer is not None:                                    # :527-529 (of the NORMALISED batches, as there)
             if self.disc_batched:                                               # one merge of the three batches' pooled moments
-                self.disc_normalizer.update_torch(x_all)                        # (Chan's merge is associative: same result
+                self.disc_normalizer.update_torch(x_all, self.world_size)       # (Chan's merge is associative: same result
             else:                                                               # up to the fp32 rounding of the batch moments)
                 for x in (policy_state, expert_state_lb, expert_state_ulb):
-                    self.disc_normalizer.update_torch(x)
+                    self.disc_normalizer.update_torch(x, self.world_size)
         with torch.no_grad():
             acc_lb = torch.mean((torch.argmax(pred_c_lb, dim=-1) == label_exp_lb).float())
             acc_pi, acc_exp = (logits_pi < 0).float().mean(), (logits_exp > 0).float().mean()
@@ -527,9 +530,9 @@ class SSInfoGAIL:
         return (ss_loss.detach(), info_max_loss.detach(), disc_loss.detach(), us_loss.detach(), grad_pen_loss.detach(),
                 disc_logit_loss.detach(), disc_weight_decay.detach(), acc_lb, acc_pi, acc_exp, acc_ulb)
 
-    def _disc_optim_step(self):
+    def _disc_optim_step(self, grad_scale: float = 1.0):
         for o in self.optim_d + self.optim_q_eps + self.optim_q_c:               # :519-521
-            o.step()
+            o.step(grad_scale)
 
     def update_disc(self, expert, num_updates=None):
         """The discriminator half of SSInfoGAIL.update (gail.py:258-300): `4 * epochs * minibatches` minibatch steps of
@@ -550,7 +553,7 @@ class SSInfoGAIL:
         i_lb = torch.randint(expert.preloaded_s_lb.shape[0], (n_mb, mb), device=dev)
         i_ulb = torch.randint(expert.preloaded_s_ulb.shape[0], (n_mb, mb), device=dev)
         self._disc_stats.zero_()
-        if self.use_cuda_graph:
+        if self.use_cuda_graph and (self.world_size == 1 or self.capture_collectives):
             key = (id(expert), mb, ds.states.data_ptr())
             if getattr(self, "_disc_graph_key", None) != key:
                 self._capture_disc(expert, mb)
@@ -566,6 +569,8 @@ class SSInfoGAIL:
         else:
             for k in range(n_mb):
                 self._disc_step(expert, i_pi[k], i_lb[k], i_ulb[k])
+        if self.world_size > 1:                                                 # logged statistics: mean over the ranks
+            qdist.allreduce_mean_scalar_(self._disc_stats)
         return tuple((self._disc_stats / n_mb).tolist())
 
     def _disc_step(self, expert, i_pi, i_lb, i_ulb):
@@ -794,7 +799,7 @@ class SSInfoGAIL:
         vals = (self._stats / n).tolist()                      # the one host sync of the update
         self.last_stats = dict(zip(STAT_NAMES, vals))
         disc_stats = ()
-        if expert is not None and self.world_size == 1:
+        if expert is not None:
             disc_stats = self.update_disc(expert)
         st.clear()
         self.priv_reg_counter += 1

@@ -71,7 +71,7 @@ class Normalizer(RunningMeanStd):
         return st
 
     @torch.no_grad()
-    def update_torch(self, x: torch.Tensor) -> None:
+    def update_torch(self, x: torch.Tensor, world_size: int = 1) -> None:
         """RunningMeanStd.update (utils.py:63-83) on the device, float64 merge; refreshes the float32 (mean, std) that
         `normalize_torch` / K18 read IN PLACE (fixed addresses: CUDA-graph safe).  Call `sync_host()` before reading
         `.mean / .var / .count` or pickling."""
@@ -79,6 +79,14 @@ class Normalizer(RunningMeanStd):
         bm = x.mean(dim=0).double()                       # numpy's mean / var of a float32 batch are float32
         bv = x.var(dim=0, unbiased=False).double()
         bc = float(x.shape[0])
+        if world_size > 1:
+            # env-sharded ranks: pool the equal-sized per-rank batches into the moments of their union, so that every
+            # rank holds the normaliser one big run would hold: mean_g = E_r[mean_r], var_g = E_r[var_r + mean_r^2] - mean_g^2
+            import torch.distributed as dist
+            pooled = torch.stack([bm, bv + bm.square()])
+            dist.all_reduce(pooled, op=dist.ReduceOp.SUM)
+            pooled /= world_size
+            bm, bv, bc = pooled[0], pooled[1] - pooled[0].square(), bc * world_size
         delta = bm - mean
         tot = count + bc
         m2 = var * count + bv * bc + delta.square() * count * bc / tot

@@ -26,7 +26,7 @@ def _alg(batched, loss_fn):
     alg = SSInfoGAIL(env, ac, disc, est, cfg["estimator"], None, norm, 2, 2, 49, 0.0, device="cpu", **alg_cfg)
     alg.disc_batched = batched
     alg._init_disc_update()
-    alg._disc_optim_step = lambda: None                                  # K8 is CUDA-only; the gradients are what is compared
+    alg._disc_optim_step = lambda *a: None                               # K8 is CUDA-only; the gradients are what is compared
     alg.info_max_coef_on = 0.3
     alg._info_max_coef_on.fill_(0.3)
     return alg, env, norm

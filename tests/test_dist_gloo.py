@@ -123,3 +123,58 @@ def test_student_distillation_gradients_average_to_the_union_batch_gloo():
         assert np.array_equal(out[0][k], out[1][k]), k                                   # ranks agree bit for bit
         assert float(np.abs(w).max()) > 0
         assert np.allclose(out[0][k], w, rtol=1e-4, atol=1e-6 * float(np.abs(w).max())), (k, float(np.abs(out[0][k] - w).max()))
+
+
+# ---- discriminator update under env sharding: gradient all-reduce, pooled normaliser moments, prior mean ---------
+def _disc_result(alg, env, norm, batches, scale):
+    stats = alg.update_ss_info_gail(*batches)
+    norm.sync_host()
+    return dict(stats=torch.stack(stats).numpy(), grad=(alg.disc_flat.grad * scale).numpy().copy(), prior=env.prior_parameters.numpy().copy(),
+                mean=norm.mean.copy(), var=norm.var.copy(), count=float(norm.count))
+
+
+def _disc_shard(batches, rank, world):
+    (s, e, c), (sl, lab), su = batches
+    cut = lambda t: t[rank * (len(t) // world):(rank + 1) * (len(t) // world)]      # noqa: E731
+    return (cut(s), cut(e), cut(c)), (cut(sl), cut(lab)), cut(su)
+
+
+def _disc_worker(rank, world, port, q):
+    import test_disc_batched as TD
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)        # before the algorithm: it reads the world size
+    torch.set_num_threads(2)
+    out = {}
+    for batched in (False, True):
+        alg, env, norm = TD._alg(batched, "MSELoss")
+        assert alg.world_size == world
+        out[batched] = _disc_result(alg, env, norm, _disc_shard(TD._batches(10), rank, world), 1.0 / world)
+    q.put((rank, out))
+    dist.destroy_process_group()
+
+
+def test_discriminator_step_under_env_sharding_equals_the_union_batch_gloo():
+    import numpy as np
+    import test_disc_batched as TD
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_disc_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    out = dict(q.get(timeout=300) for _ in range(world))
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for batched in (False, True):
+        alg, env, norm = TD._alg(batched, "MSELoss")                    # one process, the union batches
+        want = _disc_result(alg, env, norm, TD._batches(10), 1.0)
+        a, b = out[0][batched], out[1][batched]
+        for k in ("grad", "prior", "mean", "var"):
+            assert np.array_equal(a[k], b[k]), (batched, k)             # ranks hold identical state
+        assert a["count"] == b["count"] == want["count"]
+        assert np.allclose(a["grad"], want["grad"], rtol=1e-4, atol=1e-6 * float(np.abs(want["grad"]).max())), batched
+        assert np.allclose(a["prior"], want["prior"], rtol=1e-6, atol=1e-8)
+        assert np.allclose(a["mean"], want["mean"], rtol=1e-5, atol=1e-6) and np.allclose(a["var"], want["var"], rtol=1e-5, atol=1e-6)
+        # loss statistics are means over the rank's own rows: their rank-mean is the union's value
+        assert np.allclose(0.5 * (a["stats"][:7] + b["stats"][:7]), want["stats"][:7], rtol=1e-4, atol=1e-6)
