@@ -1,0 +1,110 @@
+"""Host logic of `OnPolicyRunner.learn` (bbc/rsl_rl/runners/on_policy_runner.py:118-233) on CPU: the rollout loop over a stand-in
+env (the reference-shaped non-fused step), device-staged episode bookkeeping, the TensorBoard tags, `save` every iteration and
+`load` into a second runner.  The CUDA-only pieces (GAE K5, minibatch gather K6, clip+Adam K8) are stubbed out; the device run
+of the same loop is tests/test_zz_runner_gpu.py."""
+import ctypes
+import types
+
+import numpy as np
+import torch
+
+from qa_b200 import config as K
+from qa_b200.config import bbc_train_cfg
+from qa_b200.rsl_rl.runner import OnPolicyRunner
+
+
+class FakeEnv:
+    """What the runner and SSInfoGAIL touch of `LeggedRobot`, with random dynamics."""
+
+    def __init__(self, n=32, seed=0):
+        self.num_envs, self.num_obs, self.num_privileged_obs, self.num_actions, self.num_obs_disc = n, 101, 101, 12, 49
+        self.dt, self.dim_c, self.mocap_category = 0.02, 5, ["walk", "pace", "trot", "canter", "jump"]
+        self.reward_names = list(K.REWARD_NAMES)
+        self.reward_scales = {k: 0.5 for k in self.reward_names}
+        self.task_obs_weight_decay, self.task_obs_weight, self.task_obs_weight_decay_steps = True, 1.0, 50000
+        self.cfg = types.SimpleNamespace(send_timeouts=True)
+        self.abi_args = ctypes.pointer(ctypes.c_int(0))            # like the real env: neither deep-copyable nor picklable
+        self.g = torch.Generator().manual_seed(seed)
+        self.dof_pos_limits = torch.stack([-torch.ones(12), torch.ones(12)], dim=1)
+        self.episode_length_buf, self.max_episode_length = torch.zeros(n, dtype=torch.int64), 1000.0
+        self.latent_eps, self.latent_c = torch.zeros(n, 1), torch.nn.functional.one_hot(torch.arange(n) % 5, 5).float()
+        self._time_outs_latched = torch.zeros(n, dtype=torch.bool)
+        self._episode_rew_means = torch.zeros(len(self.reward_names))
+        self.prior_parameters = torch.full((5,), 0.2)
+        self.prior_prob = self.prior_parameters.clone()
+        self._draw()
+
+    def _draw(self):
+        n, g = self.num_envs, self.g
+        self.obs = 0.3 * torch.randn(n, 671, generator=g)
+        self.disc = 0.3 * torch.randn(n, 49, generator=g)
+        self.rew = 0.05 * torch.rand(n, generator=g)
+        self.reset_buf = torch.rand(n, generator=g) < 0.2
+
+    def reset(self):
+        return self.obs, self.obs
+
+    def get_observations(self):
+        return self.obs
+
+    def get_privileged_observations(self):
+        return self.obs
+
+    def get_disc_observations(self):
+        return self.disc
+
+    def step_device(self, actions):
+        assert actions.shape == (self.num_envs, 12)
+        self._draw()
+        if bool(self.reset_buf.any()):
+            self._episode_rew_means = torch.rand(len(self.reward_names), generator=self.g)
+            self._time_outs_latched = self.reset_buf & (torch.rand(self.num_envs, generator=self.g) < 0.5)
+        return self.obs, self.obs, self.rew, self.reset_buf, None, None, None
+
+
+def _runner(tmp, seed):
+    torch.manual_seed(seed)
+    cfg = bbc_train_cfg()
+    cfg["runner"]["num_steps_per_env"], cfg["runner"]["save_interval"] = 6, 1
+    cfg["algorithm"].update(disc_replay_buffer_size=512, use_cuda_graph=False, fused_loss=False)
+    r = OnPolicyRunner(FakeEnv(seed=seed), cfg, log_dir=tmp, device="cpu")
+    alg = r.alg
+
+    def update(expert=None):                                        # K6 / K8 are CUDA-only: keep the bookkeeping side effects
+        alg.storage.clear()
+        alg.optim_ac.exp_avg.add_(0.25)
+        alg.optim_ac.step_count.add_(20)
+        return (0.1, 0.2, 0.0, 0.3, 0.4, 0.5)
+
+    alg.update, alg.update_dagger, alg.compute_returns = update, (lambda: 0.75), (lambda critic_obs: None)
+    return r
+
+
+def test_learn_loop_books_logs_saves_and_loads_on_host(tmp_path):
+    r = _runner(str(tmp_path / "a"), 1)
+    r.learn(3)
+    assert r.current_learning_iteration == 3 and r.alg.storage.step == 0
+    sc = r.writer.scalars
+    for tag in ("Loss/surrogate_loss", "Loss/estimator_loss", "Loss/hist_latent_loss", "Loss/mean_noise_std", "LR/lr_ac", "LR/lr_disc",
+                "Perf/total_fps", "Episode/rew_torques", "Train/mean_reward", "Train/mean_reward_ss", "Train/mean_episode_length"):
+        assert [s for s, _ in sc[tag]] == [0, 1, 2] and all(np.isfinite(v) for _, v in sc[tag]), tag
+    assert "Loss/ss_loss" not in sc                                  # no expert set: the discriminator was not updated
+    assert sc["Loss/hist_latent_loss"][-1][1] == 0.75 and sc["Loss/value_loss"][0][1] == 0.2
+    assert r.book.len_buffer and max(r.book.len_buffer) <= 18
+    # the bookkeeping saw exactly the rewards that went into the storage (before the time-out bootstrap), per finished episode
+    assert abs(r.env.task_obs_weight - (1.0 - 3 / 50000)) < 1e-9
+    d = torch.load(str(tmp_path / "a" / "model.pt"), map_location="cpu", weights_only=False)
+    assert list(d) == ['actor_critic', 'estimator', 'disc', 'optim_ac', 'optim_hist_encoder', 'optim_estimator', 'optim_d',
+                       'optim_q_eps', 'optim_q_c', 'disc_normalizer', 'reward_i_normalizer', 'iter', 'infos'] and d["iter"] == 3
+    assert float(d["optim_ac"]["state"][0]["step"]) == 60 and float(d["optim_d"]["state"][0]["step"]) == 0
+    r2 = _runner(str(tmp_path / "b"), 2)
+    r2.load(str(tmp_path / "a" / "model.pt"))
+    assert r2.current_learning_iteration == 3
+    for (k, v), w in zip(r.alg.actor_critic.state_dict().items(), r2.alg.actor_critic.state_dict().values()):
+        assert torch.equal(v, w), k
+    sa, sb = r.alg.optimizer_state_dicts()["optim_ac"]["state"], r2.alg.optimizer_state_dicts()["optim_ac"]["state"]
+    assert all(torch.equal(sa[i]["exp_avg"], sb[i]["exp_avg"]) and float(sa[i]["exp_avg"].min()) == 0.75 for i in sa)
+    assert int(r2.alg.optim_ac.step_count) == 60          # (the stub also wrote the row padding, which a checkpoint does not carry)
+    assert set(r2.alg._pending_disc_optim) == {"optim_d", "optim_q_eps", "optim_q_c"}
+    r2.learn(1)                                                      # resumes at iteration 3
+    assert [s for s, _ in r2.writer.scalars["Perf/total_fps"]] == [3]
