@@ -192,6 +192,8 @@ class SSInfoGAIL:
         # discriminator minibatch step with one shared forward (see update_ss_info_gail); opt-in until it has been measured
         # and re-pinned on the B200 (same values up to the summation order of the weight gradients)
         self.disc_batched = os.environ.get("QA_DISC_BATCHED", "0") == "1"
+        # PPO minibatch step with ONE privileged-latent encoder pass (see _forward_backward); opt-in for the same reason
+        self.share_priv_latent = os.environ.get("QA_SHARE_PRIV_LATENT", "0") == "1"
         torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)   # capture runs on a side stream
         self._ppo_stats = torch.zeros(4, device=device)
         self._aux_loss = torch.zeros(2, device=device)            # priv_reg_loss, estimator_loss of the current minibatch
@@ -647,12 +649,19 @@ class SSInfoGAIL:
         mb, ac, est = self._mb, self.actor_critic, self.estimator
         obs = mb["obs"]
         p, e, l, h = self.num_prop, self.num_explicit, self.num_latent, self.num_hist * self.num_prop
-        ac.update_distribution(obs, False)
+        if self.share_priv_latent:
+            # the privileged-latent encoder feeds both the actor and the regulariser (gail.py:338, :352): one pass (and one
+            # aligned copy of the 29 unaligned lanes) instead of two; autograd sums the two gradients into it
+            priv_latent = ac.infer_priv_latent(obs[:, p + e:p + e + l])
+            ac.update_distribution(obs, False, priv_latent=priv_latent)
+        else:
+            ac.update_distribution(obs, False)
         mu, sigma = ac.action_mean, ac.action_std
         logp = None if self.fused_loss else ac.get_actions_log_prob(mb["actions"])
         value = ac.evaluate(mb["critic_obs"])
         entropy = None if self.fused_loss else ac.entropy
-        priv_latent = ac.infer_priv_latent(obs[:, p + e:p + e + l])
+        if not self.share_priv_latent:
+            priv_latent = ac.infer_priv_latent(obs[:, p + e:p + e + l])
         hist_latent = mb["hist_latent"]              # gathered; computed once per update by _encode_history()
         if self.fused_loss:
             priv_reg_loss = _RowLossFused.apply(priv_latent, hist_latent, 1, self._aux_loss[0:1])

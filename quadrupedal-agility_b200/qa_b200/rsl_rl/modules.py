@@ -206,10 +206,13 @@ class ActorCritic(nn.Module):
         return (observations[:, :p], observations[:, p:p + e], observations[:, p + e:p + e + l],
                 observations[:, p + e + l:p + e + l + h], observations[:, p + e + l + h:])
 
-    def _actor_mean(self, observations, hist_encoding: bool):
+    def _actor_mean(self, observations, hist_encoding: bool, priv_latent=None):
         obs_prop, obs_explicit, obs_latent, obs_hist, obs_command = self._split(observations)
         if self.train_with_estimated_latent:
-            obs_latent = self.infer_hist_latent(obs_hist) if hist_encoding else self.infer_priv_latent(obs_latent)
+            if hist_encoding:
+                obs_latent = self.infer_hist_latent(obs_hist)
+            else:                                         # a caller that also needs the latent may hand it in (one encoder pass)
+                obs_latent = self.infer_priv_latent(obs_latent) if priv_latent is None else priv_latent
         # [prop | explicit | latent | command | zero pad]: ONE concatenation whose row pitch is a multiple of 16 bytes, so
         # the result is a legal TMA operand for the first actor layer (the pad columns are sliced off again)
         n_in = self.num_actor_obs
@@ -220,8 +223,8 @@ class ActorCritic(nn.Module):
         x = torch.cat(parts, dim=-1)[:, :n_in]
         return run_mlp(self.actor_trunk, x, head=self.actor_head)
 
-    def update_distribution(self, observations, hist_encoding: bool):
-        mean = self._actor_mean(observations, hist_encoding)
+    def update_distribution(self, observations, hist_encoding: bool, priv_latent=None):
+        mean = self._actor_mean(observations, hist_encoding, priv_latent)
         self._mean = mean
         # Normal(mean, mean*0. + std) (actor_critic.py:189-190): the broadcast is a stride-0 view, not a materialised tensor
         self._std = self.std.to(mean.device).expand_as(mean)

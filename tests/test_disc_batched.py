@@ -56,3 +56,35 @@ def test_batched_step_equals_three_pass_step():
         assert torch.allclose(g1, g0, rtol=1e-4, atol=1e-6 * float(g0.abs().max())), (loss_fn, float((g1 - g0).abs().max()))
         assert torch.allclose(p1, p0, rtol=1e-6, atol=1e-8)
         assert torch.allclose(m1, m0, rtol=1e-5, atol=1e-6) and torch.allclose(v1, v0, rtol=1e-5, atol=1e-6) and c0 == c1
+
+
+def test_shared_priv_latent_pass_gives_the_same_ppo_step_gradients():
+    """Opt-in `QA_SHARE_PRIV_LATENT=1`: the PPO minibatch step evaluates the privileged-latent encoder once for the actor and the
+    regulariser (gail.py:338, :352 evaluate it twice).  Same losses, same gradients up to the accumulation order."""
+    res = []
+    for share in (False, True):
+        alg, env, norm = _alg(False, "MSELoss")
+        alg.share_priv_latent = share
+        alg.init_storage(64, 24, [671], [671], [12])
+        alg._alloc_minibatch(384)
+        alg._kl = torch.zeros(())
+        alg._priv_reg_coef.fill_(0.07)
+        g = torch.Generator().manual_seed(0)
+        mb = alg._mb
+        mb["obs"].copy_(0.5 * torch.randn(384, 671, generator=g))
+        mb["critic_obs"].copy_(mb["obs"])
+        mb["actions"].copy_(torch.randn(384, 12, generator=g))
+        mb["old_mu"].copy_(0.1 * torch.randn(384, 12, generator=g))
+        mb["old_sigma"].fill_(1.05)
+        mb["old_actions_log_prob"].copy_(-12 + torch.randn(384, 1, generator=g))
+        mb["advantages"].copy_(torch.randn(384, 1, generator=g))
+        mb["returns"].copy_(torch.randn(384, 1, generator=g))
+        mb["values"].copy_(torch.randn(384, 1, generator=g))
+        mb["hist_latent"].copy_(0.3 * torch.randn(384, 29, generator=g))
+        alg._forward_backward()
+        res.append((alg.ac_flat.grad.clone(), alg.est_flat.grad.clone(), alg._ppo_stats.clone(), alg._aux_loss.clone()))
+    (ga, ge, ps, ax), (gb, ge2, ps2, ax2) = res
+    assert float(ga.abs().max()) > 0 and torch.allclose(gb, ga, rtol=1e-5, atol=1e-7 * float(ga.abs().max()))
+    assert torch.equal(ge, ge2) and torch.allclose(ps, ps2, rtol=1e-6, atol=1e-8) and torch.allclose(ax, ax2, rtol=1e-6, atol=1e-8)
+    lo, n = alg.ac_flat.slices["priv_encoder.0.weight"]
+    assert float(ga[lo:lo + n].abs().max()) > 0                   # the encoder does receive both gradient paths

@@ -17,4 +17,14 @@ for f in ("gpurun_out/bench.json", "gpurun_out/bench_disc_batched.json"):
     except Exception as e:
         print(f, "unreadable:", e)
 PY
+QA_SHARE_PRIV_LATENT=1 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-torch-gpu-baseline > gpurun_out/bench_share_priv.json 2> gpurun_out/bench_share_priv.err
+echo "bench(shared priv latent) rc=$?"; python - <<'PY'
+import json
+for f in ("gpurun_out/bench.json", "gpurun_out/bench_share_priv.json"):
+    try:
+        d = [json.loads(l) for l in open(f) if l.startswith("{")][-1]
+        print(f, "value", d.get("value"), "learning_ms", d.get("learning_ms"))
+    except Exception as e:
+        print(f, "unreadable:", e)
+PY
 timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?"; cat gpurun_out/bench_ref.json
