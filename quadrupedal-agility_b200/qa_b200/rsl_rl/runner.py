@@ -42,6 +42,8 @@ class OnPolicyRunner:
                                       env.dt, self.disc_loss_function, None, r["reward_i_coef"], r["reward_us_coef"],
                                       r["reward_ss_coef"], r["reward_t_coef"], self.disc_history_len, self.disc_obs_len,
                                       self.obs_disc_weight_step, r["disc_hidden_units"], device).to(device)
+        if motion_loader is None and r.get("motion_files_lb"):
+            motion_loader = self.build_motion_loader(env, r, device)
         min_std = (torch.tensor(r["min_normalized_std"], device=device) *
                    torch.abs(env.dof_pos_limits[:, 1] - env.dof_pos_limits[:, 0]))
         self.alg = SSInfoGAIL(env, actor_critic, discriminator, estimator, self.estimator_cfg, motion_loader,
@@ -60,6 +62,18 @@ class OnPolicyRunner:
         self.book, self.writer = None, None
         self.fused_rollout = bool(train_cfg["runner"].get("fused_rollout", True))
         env.reset()
+
+    def build_motion_loader(self, env, r, device):
+        """What the reference's runner does at :56-71 (`MotionLoader(..., preload_transitions=True)`): the labelled clips as a
+        `MocapTable`, the unlabelled ones as one trajectory, `num_preload_transitions` expert windows of each blended on the
+        device (`ExpertData.build`, bit-exact against `MotionLoader.pre_load_data` under injected draws)."""
+        from ..expert import ExpertData, load_unlabelled_clips
+        from ..mocap import MocapTable
+        fds = getattr(getattr(env.cfg, "env", None), "frame_duration_scale", 1.0)
+        table = MocapTable.from_json_files(sorted(r["motion_files_lb"]), mocap_category=list(env.mocap_category), frame_duration_scale=fds)
+        ulb = load_unlabelled_clips(sorted(r["motion_files_ulb"]), frame_duration_scale=fds)
+        return ExpertData.build(table, ulb, int(r["num_preload_transitions"]), env.dt, env.default_dof_pos, env.obs_scales,
+                                disc_obs_len=self.disc_obs_len, device=device, seed=int(r.get("seed", 0)))
 
     # ---- one rollout step (:156-181) ----------------------------------------------------------------------
     def _rollout_step_fused(self, obs, critic_obs, hist_encoding):

@@ -29,6 +29,9 @@ class FakeEnv:
         self.episode_length_buf, self.max_episode_length = torch.zeros(n, dtype=torch.int64), 1000.0
         self.latent_eps, self.latent_c = torch.zeros(n, 1), torch.nn.functional.one_hot(torch.arange(n) % 5, 5).float()
         self._time_outs_latched = torch.zeros(n, dtype=torch.bool)
+        self.default_dof_pos = torch.tensor([0.0, 0.9, -1.8] * 4).unsqueeze(0)
+        self.obs_scales = types.SimpleNamespace(lin_vel=0.5, ang_vel=0.25, dof_pos=1.0, dof_vel=0.05, key_pos=1.0, foot_contact=1.0,
+                                                lin_vel_dist=0.5, ang_vel_dist=0.25)
         self._episode_rew_means = torch.zeros(len(self.reward_names))
         self.prior_parameters = torch.full((5,), 0.2)
         self.prior_prob = self.prior_parameters.clone()
@@ -108,3 +111,26 @@ def test_learn_loop_books_logs_saves_and_loads_on_host(tmp_path):
     assert set(r2.alg._pending_disc_optim) == {"optim_d", "optim_q_eps", "optim_q_c"}
     r2.learn(1)                                                      # resumes at iteration 3
     assert [s for s, _ in r2.writer.scalars["Perf/total_fps"]] == [3]
+
+
+def test_runner_builds_the_expert_sets_from_the_shipped_clips_like_the_reference_runner():
+    """on_policy_runner.py:56-71: with `motion_files_lb / _ulb` in the runner cfg the expert transitions are preloaded at
+    construction and `learn` hands them to the discriminator update.  Needs the reference's mocap clips (build container)."""
+    import glob
+    import os
+    import pytest
+    lb = glob.glob("/root/reference/bbc/mocap_data/mocap_all_lb/*")
+    ulb = glob.glob("/root/reference/bbc/mocap_data/mocap_all_ulb/*")
+    if not lb or not ulb:
+        pytest.skip("the reference tree only exists in the build container")
+    torch.manual_seed(0)
+    cfg = bbc_train_cfg()
+    cfg["runner"].update(num_steps_per_env=4, motion_files_lb=lb, motion_files_ulb=ulb[:3], num_preload_transitions=500)
+    cfg["algorithm"].update(disc_replay_buffer_size=512, use_cuda_graph=False, fused_loss=False)
+    r = OnPolicyRunner(FakeEnv(seed=3), cfg, log_dir=None, device="cpu")
+    ml = r.alg.motion_loader
+    assert tuple(ml.preloaded_s_lb.shape) == (500, 98) and tuple(ml.preloaded_s_ulb.shape) == (500, 98)
+    assert ml.preloaded_label.shape == (500,) and int(ml.preloaded_label.min()) >= 0 and int(ml.preloaded_label.max()) <= 4
+    assert torch.isfinite(ml.preloaded_s_lb).all() and torch.isfinite(ml.preloaded_s_ulb).all()
+    s, lab = next(ml.feed_forward_generator_lb(1, 16))
+    assert tuple(s.shape) == (16, 98) and lab.shape == (16,)
