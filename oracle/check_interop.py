@@ -184,6 +184,28 @@ def main_tsc():
         assert abs(a - b) <= 1e-5 * abs(a) + 1e-7, (want["update"], got["update"])
     assert abs(want["lr"] - got["lr"]) < 1e-12
     post_step_equal(want, got, lr_ac=5e-4, lr_est=1e-4)
+    # storage: the reference's 12-tuple generator and get_statistics over this package's RolloutStorageTSC
+    from qa_b200.rsl_rl import RolloutStorageTSC
+    gs = torch.Generator().manual_seed(11)
+    sr, so = ref.RolloutStorage(8, 6, [800], [None], [19], device="cpu"), RolloutStorageTSC(8, 6, [800], [None], [19], device="cpu")
+    for name in ("observations", "actions", "values", "advantages", "returns", "actions_log_prob_d", "actions_log_prob_c", "mu", "sigma",
+                 "rewards"):
+        v = torch.randn(getattr(sr, name).shape, generator=gs)
+        getattr(sr, name).copy_(v)
+        getattr(so, name).copy_(v)
+    d = (torch.rand(6, 8, 1, generator=gs) < 0.2).to(torch.uint8)
+    sr.dones.copy_(d)
+    so.dones.copy_(d)
+    torch.manual_seed(3)
+    a = list(sr.mini_batch_generator(3, 2))
+    torch.manual_seed(3)
+    b = list(so.mini_batch_generator(3, 2))
+    assert len(a) == len(b) == 6
+    for ta, tb in zip(a, b):
+        assert len(ta) == len(tb) == 12 and ta[10] == tb[10] == (None, None) and ta[11] is None and tb[11] is None
+        assert all(torch.equal(x, y) for x, y in zip(ta[:10], tb[:10]))
+    (la, ra), (lb, rb) = sr.get_statistics(), so.get_statistics()
+    assert torch.equal(la, lb) and torch.equal(ra, rb)
     print(f"interop OK (tsc): reference PPO.act / PPO.update over qa_b200 ActorCriticTSC + Estimator == over the reference's "
           f"(max |diff| of act outputs {worst:.1e}; update() = {[round(x, 6) for x in got['update']]}; lr {got['lr']:.6g})")
 

@@ -52,6 +52,12 @@ class ReplayBuffer:
         self.num_samples = min(self.buffer_size, max(self.step + n, self.num_samples))
         self.step = (self.step + n) % self.buffer_size
 
+    def feed_forward_generator(self, num_mini_batch, mini_batch_size):
+        """storage/replay_buffer.py:44-50 with the index draw (np.random.choice with replacement there) on the device."""
+        for _ in range(num_mini_batch):
+            idx = torch.randint(self.num_samples, (mini_batch_size,), device=self.states.device)
+            yield self.states[idx], self.latent_eps[idx], self.latent_c[idx]
+
 
 class FlatAdam:
     """Adam state for one flat parameter buffer (or a contiguous slice [lo, hi) of it); `step()` = clip_grad_norm_ +
@@ -614,6 +620,32 @@ class SSInfoGAIL:
             t.copy_(v)
         if self.disc_normalizer is not None:
             self.disc_normalizer.__dict__["_dev_dirty"] = True
+
+    def update_actor_critic(self, sample):
+        """The reference's per-minibatch entry point (gail.py:328-413) for code written against it: `sample` is the 11-tuple
+        `RolloutStorage.mini_batch_generator` yields.  Copies it into the static minibatch buffers and runs the same fused step
+        `update()` replays (estimator step, adaptive LR, clip + Adam); returns this step's six loss statistics as device scalars
+        (surrogate, value, bound, entropy, priv_reg, estimator)."""
+        obs, critic_obs, actions, target_values, advantages, returns, old_logp, old_mu, old_sigma = sample[:9]
+        n = obs.shape[0]
+        if getattr(self, "_mb", None) is None or self._mb["obs"].shape[0] != n:
+            self._alloc_minibatch(n)
+            self._kl = torch.zeros((), device=self.device)
+            self._graphs = None
+        mb = self._mb
+        for k, v in (("obs", obs), ("critic_obs", critic_obs), ("actions", actions), ("values", target_values),
+                     ("advantages", advantages), ("returns", returns), ("old_actions_log_prob", old_logp), ("old_mu", old_mu),
+                     ("old_sigma", old_sigma)):
+            mb[k].copy_(v.reshape(mb[k].shape))
+        p, e, l, h = self.num_prop, self.num_explicit, self.num_latent, self.num_hist * self.num_prop
+        with torch.no_grad():
+            mb["hist_latent"].copy_(self.actor_critic.infer_hist_latent(mb["obs"][:, p + e + l:p + e + l + h]))
+        sch = self.priv_reg_coef_schedual
+        stage = min(max((self.priv_reg_counter - sch[2]), 0) / sch[3], 1)
+        self._priv_reg_coef.fill_(stage * (sch[1] - sch[0]) + sch[0])
+        before = self._stats.clone()
+        self._minibatch_step()
+        return tuple((self._stats - before)[:6])
 
     # ---- PPO minibatch step ------------------------------------------------------------------------------
     def _alloc_minibatch(self, mb_size):

@@ -241,6 +241,29 @@ class RolloutStorageTSC:
         ops.gae(self.rewards, self.values, self.dones, last_values.contiguous(), self.returns, self.advantages,
                 self._gae_ws, gamma, lam)
 
+    def get_statistics(self):
+        """rollout_storage.py:118-125 (mean trajectory length, mean reward); like the reference it marks the last step done."""
+        done = self.dones
+        done[-1] = 1
+        flat_dones = done.permute(1, 0, 2).reshape(-1, 1)
+        done_indices = torch.cat((flat_dones.new_tensor([-1], dtype=torch.int64), flat_dones.nonzero(as_tuple=False)[:, 0]))
+        return (done_indices[1:] - done_indices[:-1]).float().mean(), self.rewards.mean()
+
+    def mini_batch_generator(self, num_mini_batches, num_epochs=8, indices=None):
+        """The reference's 12-tuple generator (:127-166): ONE permutation per call, the same slices in every epoch.  `PPO.update`
+        gathers through K6 instead; this is for code written against the reference's storage."""
+        mb = self.num_envs * self.num_transitions_per_env // num_mini_batches
+        if indices is None:
+            indices = torch.randperm(num_mini_batches * mb, device=self.device)
+        obs = self.observations.flatten(0, 1)
+        critic = self.privileged_observations.flatten(0, 1) if self.privileged_observations is not None else obs
+        cols = [t.flatten(0, 1) for t in (self.actions, self.values, self.advantages, self.returns, self.actions_log_prob_d,
+                                          self.actions_log_prob_c, self.mu, self.sigma)]
+        for _ in range(num_epochs):
+            for i in range(num_mini_batches):
+                idx = indices[i * mb:(i + 1) * mb]
+                yield (obs[idx], critic[idx], *(c[idx] for c in cols), (None, None), None)
+
     def flat_views(self):
         f = lambda t: t.flatten(0, 1)                                           # noqa: E731
         crit = self.privileged_observations if self.privileged_observations is not None else self.observations

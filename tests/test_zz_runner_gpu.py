@@ -140,3 +140,25 @@ def test_ppo_minibatch_step_at_full_size_matches_oracle():
         assert_close(f"ppo.{k}", stats[i], L[k].float(), rtol=NET_RTOL, atol=NET_ATOL)
     assert_close("kl_mean", stats[6], L["kl_mean"].float(), rtol=1e-3, atol=1e-5)
     assert abs(alg.lr_ac - OT.adaptive_lr(1e-3, float(L["kl_mean"]))) < 1e-9
+
+
+def test_update_actor_critic_entry_point_matches_reference_golden():
+    """`SSInfoGAIL.update_actor_critic(sample)` (gail.py:328-413), the reference's per-minibatch entry point, on the golden
+    minibatch of tests/test_trainer_gpu.py::test_ppo_minibatch_step_matches_reference_golden."""
+    from helpers import assert_close
+    from qa_b200 import synthetic
+    from test_trainer_gpu import NET_ATOL, NET_RTOL, build, load_golden
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = load_golden()
+    alg, env, norm = build(synthetic.make_weights(3))
+    alg.priv_reg_counter = int(g["in.priv_reg_counter"])
+    b = {k: g["in.batch." + k].to(DEV) for k in ("actions", "target_values", "advantages", "returns", "old_actions_log_prob",
+                                                  "old_mu", "old_sigma")}
+    obs = g["in.obs"].to(DEV)
+    sample = (obs, obs, b["actions"], b["target_values"], b["advantages"], b["returns"], b["old_actions_log_prob"], b["old_mu"],
+              b["old_sigma"], (None, None), None)
+    out = alg.update_actor_critic(sample)
+    torch.cuda.synchronize()
+    for v, k in zip(out, ("surrogate_loss", "value_loss", "b_loss", "entropy", "priv_reg_loss", "estimator_loss")):
+        assert_close(f"ppo.{k}", v.cpu(), g[f"ppo.{k}"], rtol=NET_RTOL, atol=NET_ATOL)
+    assert abs(alg.lr_ac - float(g["ppo.lr_new"])) < 1e-9
