@@ -4,9 +4,10 @@ Every number is the shipped value of the reference configuration; the citation a
 each group is the file:line in /root/reference it restates.  Kept as a plain dataclass
 (not the reference's nested-class config) because the kernels need a flat POD.
 """
+import math
+import types
 from dataclasses import dataclass, field
 from typing import List, Tuple
-import math
 
 # ---- dimensions (bbc/legged_gym/envs/go2/go2_locomotion_config.py:9-32) -------------------
 NUM_DOF = 12
@@ -178,7 +179,6 @@ class BbcEnvConfig:
     def env(self):
         """`cfg.env.*` as the reference's trainer reads it (bbc/rsl_rl/runners/on_policy_runner.py:37-63, gail.py:68-87;
         values of go2_locomotion_config.py:9-32): lets the reference's own runner be constructed over this env."""
-        import types
         return types.SimpleNamespace(
             num_envs=self.num_envs, num_prop=NUM_PROP, num_explicit=NUM_EXPLICIT, num_latent=NUM_LATENT, num_command=NUM_COMMAND,
             num_obs=NUM_PROP + NUM_EXPLICIT + NUM_LATENT + NUM_COMMAND, num_privileged_obs=NUM_PROP + NUM_EXPLICIT + NUM_LATENT + NUM_COMMAND,

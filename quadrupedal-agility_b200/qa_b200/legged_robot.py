@@ -13,6 +13,7 @@ simulate), K2 fused post-physics, reset compaction -- no per-term Python, no hos
 caller asks for the variable-length `reset_env_ids` (`step()` does, `step_device()` does not).
 """
 import ctypes as C
+import types
 from typing import Dict, Optional
 
 import torch
@@ -95,8 +96,7 @@ class LeggedRobot:
         self.mocap_category = list(K.MOCAP_CATEGORY)
         self.mocap_category_all = list(K.MOCAP_CATEGORY)
         self.reward_names = list(K.REWARD_NAMES)
-        import types as _types
-        self.obs_scales = _types.SimpleNamespace(                               # cfg.normalization.obs_scales (:139-148); the
+        self.obs_scales = types.SimpleNamespace(                               # cfg.normalization.obs_scales (:139-148); the
             lin_vel=cfg.s_lin_vel, ang_vel=cfg.s_ang_vel, dof_pos=cfg.s_dof_pos, dof_vel=cfg.s_dof_vel, key_pos=cfg.s_key_pos,
             foot_contact=cfg.s_foot_contact, lin_vel_dist=cfg.s_lin_vel_dist, ang_vel_dist=cfg.s_ang_vel_dist)   # MotionLoader reads it
         self.reward_scales = dict(zip(K.REWARD_NAMES, cfg.reward_scales_dt()))

@@ -8,6 +8,7 @@ config has randomize_motor False, i.e. unit motor strengths), K16 `qa_post_physi
 `set_commands` (the high-level action -> BBC command mapping) stays a handful of torch ops.
 """
 import math
+import types
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional
 
@@ -85,7 +86,6 @@ class TscEnvConfig:
     # 281-296): read-only views; change scalars through `LeggedRobotTSC.reconfigure(...)`, which rebuilds the kernel constants
     @property
     def env(self):
-        import types
         return types.SimpleNamespace(
             num_envs=self.num_envs, n_proprio=65, n_delta_yaw=2, n_obst_type=self.num_obstacle_types, n_auxiliary=2 + self.num_obstacle_types,
             n_scan=132, n_priv=4, n_priv_latent=29, history_len=self.history_len, num_command=self.num_actions_c + len(self.mocap_category_all),
@@ -94,17 +94,14 @@ class TscEnvConfig:
 
     @property
     def domain_rand(self):
-        import types
         return types.SimpleNamespace(action_buf_len=self.action_buf_len, randomize_action=self.randomize_action)
 
     @property
     def noise(self):
-        import types
         return types.SimpleNamespace(add_noise=False)
 
     @property
     def obstacle(self):
-        import types
         return types.SimpleNamespace(curriculum=False)
 
     @property
