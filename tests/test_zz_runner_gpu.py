@@ -162,3 +162,30 @@ def test_update_actor_critic_entry_point_matches_reference_golden():
     for v, k in zip(out, ("surrogate_loss", "value_loss", "b_loss", "entropy", "priv_reg_loss", "estimator_loss")):
         assert_close(f"ppo.{k}", v.cpu(), g[f"ppo.{k}"], rtol=NET_RTOL, atol=NET_ATOL)
     assert abs(alg.lr_ac - float(g["ppo.lr_new"])) < 1e-9
+
+
+def test_post_physics_matches_oracle_at_32768():
+    """K2 at eight times the per-GPU size of BASELINE config 5 (32 768 envs in ONE launch: 4 096 CTAs, several waves, unlike the
+    one-wave 4 096-env case) against the CPU oracle, with the push step; masks, indices and counters bit-exact."""
+    import bbc_env as O
+    from helpers import mocap_table
+    from qa_b200 import synthetic
+    from qa_b200.config import BbcEnvConfig
+    from test_env_gpu import check_against, make_env
+    cfg = BbcEnvConfig(num_envs=32768)
+    static = synthetic.make_static(cfg, seed=4321)
+    snap = synthetic.make_snapshot(cfg, seed=4321, step=0)
+    draws = synthetic.make_rng_draws(cfg, seed=4321, step=0)
+    table = mocap_table()
+    draws["mocap_clip_idx"] = table.sample_clip(draws["rt_c_idx"], draws["mocap_clip_u"])
+    threads = torch.get_num_threads()
+    torch.set_num_threads(8)
+    try:
+        want = O.post_physics_step(cfg, static, snap, draws, table, 400)
+    finally:
+        torch.set_num_threads(threads)
+    env = make_env(cfg, static, snap, draws, 399, bulk="tiled", table=table)
+    env.post_physics_step()
+    torch.cuda.synchronize()
+    check_against(env, want, None, want["terminal_disc_states"], "n32768[399]")
+    assert int(want["reset_buf"].sum()) > 200
