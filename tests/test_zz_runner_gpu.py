@@ -1,12 +1,97 @@
-"""`OnPolicyRunner.learn` with a log_dir on the device: episode bookkeeping, the reference's scalar tags and the checkpoint
-round trip (bbc/rsl_rl/runners/on_policy_runner.py:118-339).  The host halves of this (deque accounting, tag list, optimiser
-dict codec) are covered on CPU in tests/test_train_log.py and tests/test_checkpoint.py."""
+"""Device tests written at the end of round 1, after the round's GPU budget was spent: they have not run on a B200 yet (the
+host halves -- deque accounting, tag list, optimiser-dict codec, the runner's learn loop, the batched discriminator step's
+gradients -- are covered on CPU in tests/test_train_log.py, test_checkpoint.py, test_runner_host.py, test_disc_batched.py).
+The file sorts last so that nothing here can mask the verified suite under `pytest -x`.
+
+* `SSInfoGAIL.update_actor_critic(sample)` and one full-size PPO minibatch step (BASELINE config 0) against golden / oracle;
+* `OnPolicyRunner.learn` with a log_dir: episode bookkeeping, the reference's scalar tags, checkpoint round trip
+  (bbc/rsl_rl/runners/on_policy_runner.py:118-339);
+* the opt-in batched discriminator step against the default one; K2 against the oracle at 32 768 envs in one launch."""
 import numpy as np
 import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
+
+
+def test_update_actor_critic_entry_point_matches_reference_golden():
+    """`SSInfoGAIL.update_actor_critic(sample)` (gail.py:328-413), the reference's per-minibatch entry point, on the golden
+    minibatch of tests/test_trainer_gpu.py::test_ppo_minibatch_step_matches_reference_golden."""
+    from helpers import assert_close
+    from qa_b200 import synthetic
+    from test_trainer_gpu import NET_ATOL, NET_RTOL, build, load_golden
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = load_golden()
+    alg, env, norm = build(synthetic.make_weights(3))
+    alg.priv_reg_counter = int(g["in.priv_reg_counter"])
+    b = {k: g["in.batch." + k].to(DEV) for k in ("actions", "target_values", "advantages", "returns", "old_actions_log_prob",
+                                                  "old_mu", "old_sigma")}
+    obs = g["in.obs"].to(DEV)
+    sample = (obs, obs, b["actions"], b["target_values"], b["advantages"], b["returns"], b["old_actions_log_prob"], b["old_mu"],
+              b["old_sigma"], (None, None), None)
+    out = alg.update_actor_critic(sample)
+    torch.cuda.synchronize()
+    for v, k in zip(out, ("surrogate_loss", "value_loss", "b_loss", "entropy", "priv_reg_loss", "estimator_loss")):
+        assert_close(f"ppo.{k}", v.cpu(), g[f"ppo.{k}"], rtol=NET_RTOL, atol=NET_ATOL)
+    assert abs(alg.lr_ac - float(g["ppo.lr_new"])) < 1e-9
+
+
+def test_ppo_minibatch_step_at_full_size_matches_oracle():
+    """BASELINE config 0 at its full size: one PPO minibatch step (24 576 rows gathered by K6 out of a recorded 4096 x 24
+    RolloutStorage whose returns / advantages come from K5) against the CPU oracle's loss graph on the same rows."""
+    import trainer as OT
+    from helpers import assert_close
+    from qa_b200 import synthetic
+    from test_trainer_gpu import NET_ATOL, NET_RTOL, build
+    torch.backends.cuda.matmul.allow_tf32 = False
+    N, T = 4096, 24
+    w = synthetic.make_weights(3)
+    alg, env, norm = build(w, n_envs=N)
+    st = alg.storage
+    g = torch.Generator().manual_seed(2)
+    st.observations.copy_(0.5 * torch.randn(T, N, 671, generator=g))
+    st.privileged_observations.copy_(st.observations)
+    with torch.no_grad():
+        for t in range(T):
+            o = st.observations[t]
+            alg.act(o, o, normal_draw=torch.randn(N, 12, generator=g).to(DEV))
+            tr = alg.transition
+            st.actions[t], st.values[t] = tr.actions, tr.values
+            st.actions_log_prob[t, :, 0], st.mu[t], st.sigma[t] = tr.actions_log_prob, tr.action_mean, tr.action_sigma
+    # make the step non-trivial: the behaviour policy differs a little from the current one
+    st.mu.add_(0.05 * torch.randn(T, N, 12, generator=g).to(DEV))
+    st.sigma.mul_(1.05)
+    st.actions_log_prob.add_(0.05 * torch.randn(T, N, 1, generator=g).to(DEV))
+    st.rewards.copy_(0.05 * torch.rand(T, N, 1, generator=g))
+    st.dones.copy_((torch.rand(T, N, 1, generator=g) < 0.02).byte())
+    st.compute_returns(torch.zeros(N, 1, device=DEV), 0.99, 0.95)
+    mb_size = T * N // 4
+    idx = torch.randperm(T * N, generator=g).to(DEV)
+    alg._alloc_minibatch(mb_size)
+    alg._kl = torch.zeros((), device=DEV)
+    alg._encode_history()
+    alg._gather(idx[:mb_size])
+    coef = OT.priv_reg_coef(1500)
+    alg._priv_reg_coef.fill_(coef)
+    alg._stats.zero_()
+    mb = {k: v.clone() for k, v in alg._mb.items()}
+    alg._minibatch_step()
+    torch.cuda.synchronize()
+    stats = alg._stats.cpu()
+    batch = dict(obs=mb["obs"].cpu(), critic_obs=mb["critic_obs"].cpu(), actions=mb["actions"].cpu(), target_values=mb["values"].cpu(),
+                 advantages=mb["advantages"].cpu(), returns=mb["returns"].cpu(), old_actions_log_prob=mb["old_actions_log_prob"].cpu(),
+                 old_mu=mb["old_mu"].cpu(), old_sigma=mb["old_sigma"].cpu())
+    # the gathered rows are the storage rows the permutation names (K6), with K5's normalised advantages
+    rows = idx[:mb_size].cpu()
+    assert torch.equal(batch["obs"], st.observations.flatten(0, 1).cpu()[rows])
+    assert abs(float(st.advantages.mean())) < 1e-4 and abs(float(st.advantages.std()) - 1.0) < 1e-3
+    with torch.no_grad():
+        L = OT.ppo_losses(w["ac"], w["est"], batch, priv_reg_coef=coef)
+    for i, k in enumerate(("surrogate_loss", "value_loss", "b_loss", "entropy", "priv_reg_loss", "estimator_loss")):
+        assert_close(f"ppo.{k}", stats[i], L[k].float(), rtol=NET_RTOL, atol=NET_ATOL)
+    assert_close("kl_mean", stats[6], L["kl_mean"].float(), rtol=1e-3, atol=1e-5)
+    assert abs(alg.lr_ac - OT.adaptive_lr(1e-3, float(L["kl_mean"]))) < 1e-9
 
 
 def test_runner_learn_books_episodes_logs_reference_tags_and_round_trips_checkpoint(tmp_path):
@@ -83,85 +168,6 @@ def test_batched_discriminator_step_matches_three_pass_step_on_device():
         d = (other[1] - res[0][1]).abs()
         assert float(d.max()) <= 3 * 2.5 * res[0][3] and float((d > 2e-5).float().mean()) < 1e-2, float(d.max())
         assert np.allclose(res[0][2], other[2], rtol=1e-5, atol=1e-7)
-
-
-def test_ppo_minibatch_step_at_full_size_matches_oracle():
-    """BASELINE config 0 at its full size: one PPO minibatch step (24 576 rows gathered by K6 out of a recorded 4096 x 24
-    RolloutStorage whose returns / advantages come from K5) against the CPU oracle's loss graph on the same rows."""
-    import trainer as OT
-    from helpers import assert_close
-    from qa_b200 import synthetic
-    from test_trainer_gpu import NET_ATOL, NET_RTOL, build
-    torch.backends.cuda.matmul.allow_tf32 = False
-    N, T = 4096, 24
-    w = synthetic.make_weights(3)
-    alg, env, norm = build(w, n_envs=N)
-    st = alg.storage
-    g = torch.Generator().manual_seed(2)
-    st.observations.copy_(0.5 * torch.randn(T, N, 671, generator=g))
-    st.privileged_observations.copy_(st.observations)
-    with torch.no_grad():
-        for t in range(T):
-            o = st.observations[t]
-            alg.act(o, o, normal_draw=torch.randn(N, 12, generator=g).to(DEV))
-            tr = alg.transition
-            st.actions[t], st.values[t] = tr.actions, tr.values
-            st.actions_log_prob[t, :, 0], st.mu[t], st.sigma[t] = tr.actions_log_prob, tr.action_mean, tr.action_sigma
-    # make the step non-trivial: the behaviour policy differs a little from the current one
-    st.mu.add_(0.05 * torch.randn(T, N, 12, generator=g).to(DEV))
-    st.sigma.mul_(1.05)
-    st.actions_log_prob.add_(0.05 * torch.randn(T, N, 1, generator=g).to(DEV))
-    st.rewards.copy_(0.05 * torch.rand(T, N, 1, generator=g))
-    st.dones.copy_((torch.rand(T, N, 1, generator=g) < 0.02).byte())
-    st.compute_returns(torch.zeros(N, 1, device=DEV), 0.99, 0.95)
-    mb_size = T * N // 4
-    idx = torch.randperm(T * N, generator=g).to(DEV)
-    alg._alloc_minibatch(mb_size)
-    alg._kl = torch.zeros((), device=DEV)
-    alg._encode_history()
-    alg._gather(idx[:mb_size])
-    coef = OT.priv_reg_coef(1500)
-    alg._priv_reg_coef.fill_(coef)
-    alg._stats.zero_()
-    mb = {k: v.clone() for k, v in alg._mb.items()}
-    alg._minibatch_step()
-    torch.cuda.synchronize()
-    stats = alg._stats.cpu()
-    batch = dict(obs=mb["obs"].cpu(), critic_obs=mb["critic_obs"].cpu(), actions=mb["actions"].cpu(), target_values=mb["values"].cpu(),
-                 advantages=mb["advantages"].cpu(), returns=mb["returns"].cpu(), old_actions_log_prob=mb["old_actions_log_prob"].cpu(),
-                 old_mu=mb["old_mu"].cpu(), old_sigma=mb["old_sigma"].cpu())
-    # the gathered rows are the storage rows the permutation names (K6), with K5's normalised advantages
-    rows = idx[:mb_size].cpu()
-    assert torch.equal(batch["obs"], st.observations.flatten(0, 1).cpu()[rows])
-    assert abs(float(st.advantages.mean())) < 1e-4 and abs(float(st.advantages.std()) - 1.0) < 1e-3
-    with torch.no_grad():
-        L = OT.ppo_losses(w["ac"], w["est"], batch, priv_reg_coef=coef)
-    for i, k in enumerate(("surrogate_loss", "value_loss", "b_loss", "entropy", "priv_reg_loss", "estimator_loss")):
-        assert_close(f"ppo.{k}", stats[i], L[k].float(), rtol=NET_RTOL, atol=NET_ATOL)
-    assert_close("kl_mean", stats[6], L["kl_mean"].float(), rtol=1e-3, atol=1e-5)
-    assert abs(alg.lr_ac - OT.adaptive_lr(1e-3, float(L["kl_mean"]))) < 1e-9
-
-
-def test_update_actor_critic_entry_point_matches_reference_golden():
-    """`SSInfoGAIL.update_actor_critic(sample)` (gail.py:328-413), the reference's per-minibatch entry point, on the golden
-    minibatch of tests/test_trainer_gpu.py::test_ppo_minibatch_step_matches_reference_golden."""
-    from helpers import assert_close
-    from qa_b200 import synthetic
-    from test_trainer_gpu import NET_ATOL, NET_RTOL, build, load_golden
-    torch.backends.cuda.matmul.allow_tf32 = False
-    g = load_golden()
-    alg, env, norm = build(synthetic.make_weights(3))
-    alg.priv_reg_counter = int(g["in.priv_reg_counter"])
-    b = {k: g["in.batch." + k].to(DEV) for k in ("actions", "target_values", "advantages", "returns", "old_actions_log_prob",
-                                                  "old_mu", "old_sigma")}
-    obs = g["in.obs"].to(DEV)
-    sample = (obs, obs, b["actions"], b["target_values"], b["advantages"], b["returns"], b["old_actions_log_prob"], b["old_mu"],
-              b["old_sigma"], (None, None), None)
-    out = alg.update_actor_critic(sample)
-    torch.cuda.synchronize()
-    for v, k in zip(out, ("surrogate_loss", "value_loss", "b_loss", "entropy", "priv_reg_loss", "estimator_loss")):
-        assert_close(f"ppo.{k}", v.cpu(), g[f"ppo.{k}"], rtol=NET_RTOL, atol=NET_ATOL)
-    assert abs(alg.lr_ac - float(g["ppo.lr_new"])) < 1e-9
 
 
 def test_post_physics_matches_oracle_at_32768():
