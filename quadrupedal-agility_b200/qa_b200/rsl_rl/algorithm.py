@@ -195,6 +195,12 @@ class SSInfoGAIL:
             capture_collectives = os.environ.get("QA_CAPTURE_COLLECTIVES", "1") == "1"
         self.capture_collectives = capture_collectives
         self._graph_has_apply = True
+        # north_star's "single NCCL allreduce of PPO gradients": with QA_SINGLE_ALLREDUCE=1 the actor-critic gradients, the
+        # estimator gradients and the KL scalar live in ONE arena reduced by one collective per optimiser step (instead of
+        # three); opt-in until it has run over NCCL (the arithmetic is checked over gloo, tests/test_dist_gloo.py)
+        self._grad_arena = None
+        if self.world_size > 1 and os.environ.get("QA_SINGLE_ALLREDUCE", "0") == "1":
+            self.use_grad_arena()
         # discriminator minibatch step with one shared forward (see update_ss_info_gail); opt-in until it has been measured
         # and re-pinned on the B200 (same values up to the summation order of the weight gradients)
         self.disc_batched = os.environ.get("QA_DISC_BATCHED", "0") == "1"
@@ -207,6 +213,26 @@ class SSInfoGAIL:
         self._stats = torch.zeros(len(STAT_NAMES), device=device)
         self.last_stats = {}
         self._disc_stage = None
+
+    def use_grad_arena(self):
+        """[actor-critic grads | estimator grads | kl, pad] in one contiguous buffer; `_allreduce_grads` then needs one collective."""
+        n_ac, n_est = self.ac_flat.numel, self.est_flat.numel
+        arena = torch.zeros(n_ac + n_est + 4, device=self.device)
+        self.ac_flat.rebind_grad(arena[:n_ac])
+        self.est_flat.rebind_grad(arena[n_ac:n_ac + n_est])
+        self._kl = arena[n_ac + n_est]
+        self._grad_arena = arena
+
+    def _allreduce_grads(self) -> float:
+        """SUM of the flat gradients over the ranks (the 1/W goes into K8's grad_scale) and the rank-mean of the KL."""
+        if self._grad_arena is not None:
+            scale = qdist.allreduce_flat_(self._grad_arena)
+            self._kl.mul_(scale)
+            return scale
+        scale = qdist.allreduce_flat_(self.ac_flat.grad)
+        qdist.allreduce_flat_(self.est_flat.grad)
+        qdist.allreduce_mean_scalar_(self._kl)
+        return scale
 
     def stage_disc_inserts(self, on: bool = True):
         """Replay-buffer inserts of a rollout go to a (T,N,.) staging area at fixed addresses (so that the rollout can
@@ -630,7 +656,8 @@ class SSInfoGAIL:
         n = obs.shape[0]
         if getattr(self, "_mb", None) is None or self._mb["obs"].shape[0] != n:
             self._alloc_minibatch(n)
-            self._kl = torch.zeros((), device=self.device)
+            if self._grad_arena is None:
+                self._kl = torch.zeros((), device=self.device)
             self._graphs = None
         mb = self._mb
         for k, v in (("obs", obs), ("critic_obs", critic_obs), ("actions", actions), ("values", target_values),
@@ -744,9 +771,7 @@ class SSInfoGAIL:
         """All-reduce (multi-GPU), adaptive LR on the device (:374-379), fused clip + Adam (:361-365, :409-412)."""
         scale = 1.0
         if self.world_size > 1:
-            scale = qdist.allreduce_flat_(self.ac_flat.grad)
-            qdist.allreduce_flat_(self.est_flat.grad)
-            qdist.allreduce_mean_scalar_(self._kl)
+            scale = self._allreduce_grads()
         self.optim_estimator.step(scale)
         adaptive = self.desired_kl is not None and self.schedule == 'adaptive'
         if torch.device(self.device).type == "cuda":
@@ -813,7 +838,8 @@ class SSInfoGAIL:
         mb_size = batch // self.num_mini_batches
         if getattr(self, "_mb", None) is None or self._mb["obs"].shape[0] != mb_size:
             self._alloc_minibatch(mb_size)
-            self._kl = torch.zeros((), device=self.device)
+            if self._grad_arena is None:
+                self._kl = torch.zeros((), device=self.device)
             self._graphs = None
         self.learning_steps += 1
         sch = self.priv_reg_coef_schedual

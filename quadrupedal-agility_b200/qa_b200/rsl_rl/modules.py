@@ -104,9 +104,20 @@ class FlatParams:
             p.data = view(self.data, p, o, n)
             p.grad = view(self.grad, p, o, n)
             self.slices[names[id(p)]] = (o, n)
+        self._plan, self._view = plan, view
 
     def zero_grad(self):
         self.grad.zero_()
+
+    def rebind_grad(self, buf: torch.Tensor) -> None:
+        """Move the gradient twin into `buf` (a contiguous fp32 slice of `numel` elements, e.g. of an arena shared with other
+        parameter sets so that ONE collective reduces them all); every Parameter's `.grad` becomes a view of it."""
+        if buf.numel() != self.numel or buf.dtype != torch.float32 or not buf.is_contiguous():
+            raise ValueError("rebind_grad: need a contiguous fp32 buffer of the flat size")
+        buf.copy_(self.grad)
+        self.grad = buf
+        for p, o, n in self._plan:
+            p.grad = self._view(buf, p, o, n)
 
 
 class StateHistoryEncoder(nn.Module):

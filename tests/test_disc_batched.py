@@ -62,12 +62,15 @@ def test_shared_priv_latent_pass_gives_the_same_ppo_step_gradients():
     """Opt-in `QA_SHARE_PRIV_LATENT=1`: the PPO minibatch step evaluates the privileged-latent encoder once for the actor and the
     regulariser (gail.py:338, :352 evaluate it twice).  Same losses, same gradients up to the accumulation order."""
     res = []
-    for share in (False, True):
+    for share in (False, True, "arena"):
         alg, env, norm = _alg(False, "MSELoss")
-        alg.share_priv_latent = share
+        alg.share_priv_latent = share is True
+        if share == "arena":                                          # gradients re-homed into the single-all-reduce arena
+            alg.use_grad_arena()
         alg.init_storage(64, 24, [671], [671], [12])
         alg._alloc_minibatch(384)
-        alg._kl = torch.zeros(())
+        if alg._grad_arena is None:
+            alg._kl = torch.zeros(())
         alg._priv_reg_coef.fill_(0.07)
         g = torch.Generator().manual_seed(0)
         mb = alg._mb
@@ -83,7 +86,12 @@ def test_shared_priv_latent_pass_gives_the_same_ppo_step_gradients():
         mb["hist_latent"].copy_(0.3 * torch.randn(384, 29, generator=g))
         alg._forward_backward()
         res.append((alg.ac_flat.grad.clone(), alg.est_flat.grad.clone(), alg._ppo_stats.clone(), alg._aux_loss.clone()))
-    (ga, ge, ps, ax), (gb, ge2, ps2, ax2) = res
+    (ga, ge, ps, ax), (gb, ge2, ps2, ax2), (gc, ge3, ps3, ax3) = res
+    # the arena run is the default computation with the gradients landing in one shared buffer (autograd accumulates in place)
+    assert torch.equal(gc, ga) and torch.equal(ge3, ge) and torch.equal(ps3, ps)
+    n_ac = alg.ac_flat.numel
+    assert torch.equal(alg._grad_arena[:n_ac], gc) and torch.equal(alg._grad_arena[n_ac:n_ac + alg.est_flat.numel], ge3)
+    assert alg._kl.data_ptr() == alg._grad_arena[n_ac + alg.est_flat.numel:].data_ptr() and float(alg._kl) == float(ps3[3])
     assert float(ga.abs().max()) > 0 and torch.allclose(gb, ga, rtol=1e-5, atol=1e-7 * float(ga.abs().max()))
     assert torch.equal(ge, ge2) and torch.allclose(ps, ps2, rtol=1e-6, atol=1e-8) and torch.allclose(ax, ax2, rtol=1e-6, atol=1e-8)
     lo, n = alg.ac_flat.slices["priv_encoder.0.weight"]

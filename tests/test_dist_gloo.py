@@ -178,3 +178,58 @@ def test_discriminator_step_under_env_sharding_equals_the_union_batch_gloo():
         assert np.allclose(a["mean"], want["mean"], rtol=1e-5, atol=1e-6) and np.allclose(a["var"], want["var"], rtol=1e-5, atol=1e-6)
         # loss statistics are means over the rank's own rows: their rank-mean is the union's value
         assert np.allclose(0.5 * (a["stats"][:7] + b["stats"][:7]), want["stats"][:7], rtol=1e-4, atol=1e-6)
+
+
+# ---- north_star: "a single NCCL allreduce of PPO gradients" -- the opt-in gradient arena ---------------------------------------
+def _arena_worker(rank, world, port, q):
+    import test_disc_batched as TD
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    out = {}
+    for arena in (False, True):
+        alg, env, norm = TD._alg(False, "MSELoss")
+        if arena:
+            alg.use_grad_arena()
+        g = torch.Generator().manual_seed(100 + rank)
+        alg.ac_flat.grad.copy_(torch.randn(alg.ac_flat.numel, generator=g))
+        alg.est_flat.grad.copy_(torch.randn(alg.est_flat.numel, generator=g))
+        if not arena:
+            alg._kl = torch.zeros(())
+        alg._kl.fill_(0.01 * (rank + 1))
+        # every Parameter's .grad must alias the (possibly re-homed) flat gradient
+        w = alg.actor_critic.actor_trunk[0].weight
+        lo, n = alg.ac_flat.slices["actor_trunk.0.weight"]
+        assert w.grad.data_ptr() == alg.ac_flat.grad[lo:lo + n].data_ptr()
+        calls = [0]
+        orig = dist.all_reduce
+
+        def counting(*a, **k):
+            calls[0] += 1
+            return orig(*a, **k)
+        dist.all_reduce = counting
+        scale = alg._allreduce_grads()
+        dist.all_reduce = orig
+        out[arena] = (scale, calls[0], alg.ac_flat.grad.clone().numpy(), alg.est_flat.grad.clone().numpy(), float(alg._kl),
+                      float(w.grad.abs().sum()))
+    q.put((rank, out))
+    dist.destroy_process_group()
+
+
+def test_gradient_arena_reduces_everything_in_one_collective_gloo():
+    import numpy as np
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_arena_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    out = dict(q.get(timeout=300) for _ in range(world))
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in range(world):
+        (s3, c3, ga3, ge3, kl3, _), (s1, c1, ga1, ge1, kl1, wsum) = out[r][False], out[r][True]
+        assert (c3, c1) == (3, 1) and s3 == s1 == 0.5                      # three collectives -> one
+        assert np.array_equal(ga3, ga1) and np.array_equal(ge3, ge1) and abs(kl3 - kl1) < 1e-9 and abs(kl1 - 0.015) < 1e-8
+        assert wsum > 0
+    assert np.array_equal(out[0][True][2], out[1][True][2])

@@ -1,4 +1,5 @@
 #!/bin/bash
+# (a 2-GPU follow-up: QA_SINGLE_ALLREDUCE=1 torchrun ... bench.py --gpus 2 against the default three collectives)
 # First GPU call of round 2 (~3 min of box time): everything that was written at the end of round 1 without a GPU.
 #   1. the whole GPU suite WITHOUT -x (tests/test_zz_runner_gpu.py holds the two tests that have not run on a device yet)
 #   2. the bench line (now with torch_gpu_baseline = the reference's PyTorch path on the same GPU) and the reference arm
