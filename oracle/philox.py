@@ -92,3 +92,23 @@ def k2_draws(num_envs, obs_width, noise_lanes, prior_cdf_f32, mode_offset, mode_
         clip[n] = clips[j]
     d["mocap_clip_idx"] = clip
     return d
+
+
+SITE_DEPTH_ENV, SITE_DEPTH_PIX = 32, 64
+
+
+def depth_draws(num_envs, out_h, out_w, seed, step):
+    """The production stream of K14 `qa_depth_update` (csrc/qa_depth.cu) at (seed, step) as the parity draws of
+    `oracle/tsc_depth.update_depth_buffer`: noise_scale_u (N,), offset_u (N,), pixel_u (N,H,W) -- pixel p of an env comes from
+    word p & 3 of the call at site SITE_DEPTH_PIX + (p >> 2)."""
+    e = np.arange(num_envs, dtype=np.uint32)
+    r = _site(e, SITE_DEPTH_ENV, step, seed)
+    P = out_h * out_w
+    groups = (P + 3) >> 2
+    pix = np.zeros((num_envs, groups * 4), dtype=np.float32)
+    g = np.arange(groups, dtype=np.uint32)
+    v = philox4x32_10(e[:, None], (np.uint32(SITE_DEPTH_PIX) + g)[None, :], np.uint32(step & 0xFFFFFFFF),
+                      np.uint32((step >> 32) & 0xFFFFFFFF), seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    for k in range(4):
+        pix[:, k::4] = u32_to_unit_f32(v[k])
+    return dict(noise_scale_u=u32_to_unit_f32(r[0]), offset_u=u32_to_unit_f32(r[1]), pixel_u=pix[:, :P].reshape(num_envs, out_h, out_w))

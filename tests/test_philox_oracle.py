@@ -40,3 +40,13 @@ def test_k2_draws_shapes_and_ranges():
         assert 0 <= m <= 4 and off[m] <= clips.index(int(d["mocap_clip_idx"][n])) < off[m + 1]
     d2 = P.k2_draws(64, 671, [0, 1, 2, 58], P.prior_cdf([0.2] * 5, 0.25), off, clips, cdf, seed=7, step=5)
     assert not np.array_equal(d["rs_eps_u"], d2["rs_eps_u"])
+
+
+def test_depth_draws_layout():
+    d = P.depth_draws(3, 58, 87, seed=77, step=1)
+    assert d["pixel_u"].shape == (3, 58, 87) and d["noise_scale_u"].shape == (3,) and d["pixel_u"].dtype == np.float32
+    # pixel p = word (p & 3) of the call at site 64 + (p >> 2), counter word 0 = env
+    p, env = 4 * 1000 + 2, 2
+    v = P.philox4x32_10(np.array([env], dtype=np.uint32), np.uint32(64 + 1000), np.uint32(1), np.uint32(0), 77, 0)
+    assert d["pixel_u"].reshape(3, -1)[env, p] == P.u32_to_unit_f32(v[2])[0]
+    assert 0.45 < float(d["pixel_u"].mean()) < 0.55

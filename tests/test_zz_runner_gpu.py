@@ -227,3 +227,23 @@ def test_production_rng_mode_is_bit_exact_against_the_oracle_fed_with_the_same_p
         torch.cuda.synchronize()
         check_against(env, want, None, want["terminal_disc_states"], f"philox[{counter_before}]")
         assert int(want["reset_buf"].sum()) > 20
+
+
+def test_depth_update_production_rng_is_bit_exact_against_the_oracle():
+    """K14 in production mode (in-kernel Philox) against `oracle/tsc_depth.update_depth_buffer` fed with the same stream
+    (`oracle/philox.depth_draws`): two consecutive frames, fill and shift, bit-exact."""
+    import philox as P
+    import tsc_depth as OD
+    from qa_b200.depth import DepthBuffer
+    from test_tsc_depth import FAR, NEAR, NOISE, _synthetic
+    N, seed = 64, 77
+    images, ep, buf0, _, _, _ = _synthetic(N, seed=3)
+    db = DepthBuffer(N, device=DEV, seed=seed)
+    db.depth_buffer.copy_(buf0)
+    db.set_batched_images(images.to(DEV))
+    want = buf0
+    for frame, ep_t in enumerate((ep, ep + 1)):
+        d = {k: torch.from_numpy(v) for k, v in P.depth_draws(N, 58, 87, seed=seed, step=frame + 1).items()}   # step counts updates
+        want = OD.update_depth_buffer(want, images, ep_t, NEAR, FAR, NOISE, d["noise_scale_u"], d["offset_u"], d["pixel_u"])
+        db.update_depth_buffer(ep_t.to(DEV))
+        assert torch.equal(db.depth_buffer.cpu(), want), frame
