@@ -112,3 +112,13 @@ def depth_draws(num_envs, out_h, out_w, seed, step):
     for k in range(4):
         pix[:, k::4] = u32_to_unit_f32(v[k])
     return dict(noise_scale_u=u32_to_unit_f32(r[0]), offset_u=u32_to_unit_f32(r[1]), pixel_u=pix[:, :P].reshape(num_envs, out_h, out_w))
+
+
+SITE_TSC_RESET = 40
+
+
+def tsc_draws(num_envs, seed, step):
+    """The reset randomisation stream of K16 `qa_post_physics_tsc_pre` (csrc/qa_tsc_env.cu) at (seed, step) as the parity
+    draws {yaw_u, x_u, y_u} (N,) f32 of `oracle/tsc_env.post_physics_pre`."""
+    r = _site(np.arange(num_envs, dtype=np.uint32), SITE_TSC_RESET, step, seed)
+    return dict(yaw_u=u32_to_unit_f32(r[0]), x_u=u32_to_unit_f32(r[1]), y_u=u32_to_unit_f32(r[2]))

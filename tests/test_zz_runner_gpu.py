@@ -247,3 +247,24 @@ def test_depth_update_production_rng_is_bit_exact_against_the_oracle():
         want = OD.update_depth_buffer(want, images, ep_t, NEAR, FAR, NOISE, d["noise_scale_u"], d["offset_u"], d["pixel_u"])
         db.update_depth_buffer(ep_t.to(DEV))
         assert torch.equal(db.depth_buffer.cpu(), want), frame
+
+
+def test_tsc_env_production_rng_is_bit_exact_against_the_oracle():
+    """K16 / K17 with the in-kernel Philox reset randomisation against the TSC oracle fed with the same stream."""
+    import philox as P
+    import tsc_env as OE
+    from helpers import assert_close
+    from qa_b200 import synthetic
+    from test_tsc_env import KEYS, collect, run_kernels
+    N, seed = 4096, 7
+    st = synthetic.make_tsc_static(N, seed)
+    sn = synthetic.make_tsc_snapshot(N, st, seed)
+    dr = {k: torch.from_numpy(v) for k, v in P.tsc_draws(N, seed=seed, step=1).items()}      # the env's first step
+    cfg = OE.TscCfg(num_envs=N)
+    want = OE.post_physics_post(cfg, st, OE.post_physics_pre(cfg, st, sn, dr), sn["rigid_body_state_post"])
+    env, ids, terminal, _ = run_kernels(N, seed, parity=False)
+    got = collect(env)
+    for k in KEYS:
+        assert_close(k, got[k], want[k])
+    assert torch.equal(ids.cpu(), want["reset_env_ids"]) and len(ids) > 20
+    assert_close("terminal", terminal, want["terminal_disc_states"])
