@@ -259,10 +259,11 @@ def test_tsc_env_production_rng_is_bit_exact_against_the_oracle():
     N, seed = 4096, 7
     st = synthetic.make_tsc_static(N, seed)
     sn = synthetic.make_tsc_snapshot(N, st, seed)
-    dr = {k: torch.from_numpy(v) for k, v in P.tsc_draws(N, seed=seed, step=1).items()}      # the env's first step
+    env, ids, terminal, _ = run_kernels(N, seed, parity=False)
+    # the launch was keyed by the step counter AFTER post_physics_step advanced it, and by the env's seed
+    dr = {k: torch.from_numpy(v) for k, v in P.tsc_draws(N, seed=env.seed, step=env.common_step_counter).items()}
     cfg = OE.TscCfg(num_envs=N)
     want = OE.post_physics_post(cfg, st, OE.post_physics_pre(cfg, st, sn, dr), sn["rigid_body_state_post"])
-    env, ids, terminal, _ = run_kernels(N, seed, parity=False)
     got = collect(env)
     for k in KEYS:
         assert_close(k, got[k], want[k])
