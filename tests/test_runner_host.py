@@ -134,3 +134,93 @@ def test_runner_builds_the_expert_sets_from_the_shipped_clips_like_the_reference
     assert torch.isfinite(ml.preloaded_s_lb).all() and torch.isfinite(ml.preloaded_s_ulb).all()
     s, lab = next(ml.feed_forward_generator_lb(1, 16))
     assert tuple(s.shape) == (16, 98) and lab.shape == (16,)
+
+
+class FakeTscEnv:
+    """What `OnPolicyRunnerTSC` touches of `LeggedRobotTSC`, with random dynamics."""
+
+    def __init__(self, n=16, seed=0):
+        from qa_b200.legged_robot_tsc import TscEnvConfig
+        self.cfg = TscEnvConfig(num_envs=n)
+        self.num_envs, self.num_obs, self.num_privileged_obs, self.num_actions = n, 800, None, 12
+        self.num_obs_disc, self.num_obs_bbc, self.dim_c, self.dt = 49, 671, 5, 0.02
+        self.g = torch.Generator().manual_seed(seed)
+        self.episode_length_buf, self.max_episode_length = torch.zeros(n, dtype=torch.int64), 2000.0
+        self._episode_rew_means = torch.zeros(len(self.cfg.reward_names))
+        self.extras = {}
+        self._draw()
+
+    def _draw(self):
+        n, g = self.num_envs, self.g
+        self.obs_buf, self.obs_bbc_buf = 0.3 * torch.randn(n, 800, generator=g), 0.3 * torch.randn(n, 671, generator=g)
+        self.obs_disc_buf = 0.3 * torch.randn(n, 49, generator=g)
+        self.rew_buf, self.reset_buf = 0.05 * torch.rand(n, generator=g), torch.rand(n, generator=g) < 0.25
+
+    def get_observations(self):
+        return self.obs_buf
+
+    def get_privileged_observations(self):
+        return None
+
+    def get_observations_bbc(self):
+        return self.obs_bbc_buf
+
+    def get_observations_disc(self):
+        return self.obs_disc_buf
+
+    def set_commands(self, actions, action_noise_u=None):
+        assert actions.shape == (self.num_envs, 19)
+        return torch.zeros(self.num_envs, 11)
+
+    def step(self, actions_bbc, action_hl_history_buf=None):
+        assert actions_bbc.shape == (self.num_envs, 12) and action_hl_history_buf.shape == (self.num_envs, 8, 19)
+        self._draw()
+        if bool(self.reset_buf.any()):
+            self._episode_rew_means = torch.rand(len(self.cfg.reward_names), generator=self.g)
+            self.extras["time_outs"] = self.reset_buf.clone()
+        self.extras["reach_goal"] = torch.rand(self.num_envs, generator=self.g) < 0.5
+        return self.obs_buf, None, self.rew_buf, self.reset_buf, self.extras, None, None
+
+
+def test_tsc_teacher_learn_loop_logs_and_saves_on_host(tmp_path, monkeypatch):
+    """`OnPolicyRunnerTSC.learn_RL` (tsc/rsl_rl/runners/on_policy_runner.py:164-276) host logic: rollout loop, high-level action
+    history, bookkeeping incl. the success rate, the reference's tags, checkpoint keys.  K18 / K19 and the update are stubbed."""
+    from qa_b200 import ops
+    from qa_b200.config import tsc_train_cfg
+    from qa_b200.rsl_rl.tsc_runner import OnPolicyRunnerTSC
+
+    def disc_input(dones, prev_disc, next_disc, hist_prev, hist_new, hist_next, x_norm, mean, std, clip, *rest):
+        hist_next.copy_(torch.stack([hist_prev[:, 1], next_disc], dim=1))
+        x_norm.copy_(hist_next.reshape(len(dones), -1))
+
+    def disc_reward(heads, obs, reward_t, dt, coefs, out, **kw):
+        out.copy_(reward_t * coefs[3] + 0.01 * heads[:, 0])
+
+    monkeypatch.setattr(ops, "disc_input", disc_input)
+    monkeypatch.setattr(ops, "disc_reward", disc_reward)
+    torch.manual_seed(0)
+    cfg = tsc_train_cfg()
+    cfg["runner"].update(num_steps_per_env=5, save_interval=1)
+    cfg["algorithm"].update(use_cuda_graph=False, fused_loss=False)
+    env = FakeTscEnv()
+    r = OnPolicyRunnerTSC(env, cfg, log_dir=str(tmp_path), device="cpu")
+    assert r.learn.__func__ is OnPolicyRunnerTSC.learn_RL
+    alg = r.alg
+    alg.compute_returns = lambda critic_obs: None
+    alg.update = lambda: (alg.storage.clear(), (0.1, 0.2, 0.3, 0.0, 0.0, 0.4, 0.05))[1]
+    alg.update_dagger = lambda: 0.6
+    r.learn(2)
+    sc = r.writer.scalars
+    for tag in ("Loss/value_function", "Loss/surrogate", "Loss/estimator", "Loss/hist_latent_loss", "Loss/priv_reg_loss",
+                "Loss/priv_ref_lambda", "Loss/learning_rate", "Policy/mean_noise_std", "Perf/total_fps", "Episode_rew/rew_reach_goal",
+                "Train/mean_reward", "Train/mean_episode_length", "Train/mean_success_rate"):
+        assert [s for s, _ in sc[tag]] == [0, 1], tag
+    assert sc["Loss/hist_latent_loss"][0][1] == 0.6 and 0.0 <= env.success_rate <= 1.0
+    assert r.action_history_buf.shape == (16, 8, 19) and float(r.action_history_buf.abs().sum()) > 0
+    d = torch.load(str(tmp_path / "model.pt"), map_location="cpu", weights_only=False)
+    assert list(d) == ["model_state_dict", "estimator_state_dict", "optimizer_state_dict", "iter", "infos"]
+    assert len(d["optimizer_state_dict"]["param_groups"][0]["params"]) == sum(1 for _ in alg.actor_critic.parameters())
+    r2 = OnPolicyRunnerTSC(FakeTscEnv(seed=1), cfg, log_dir=None, device="cpu")
+    r2.load(str(tmp_path / "model.pt"))
+    for (k, v), w in zip(alg.actor_critic.state_dict().items(), r2.alg.actor_critic.state_dict().values()):
+        assert torch.equal(v, w), k
