@@ -206,6 +206,21 @@ def main_tsc():
         assert all(torch.equal(x, y) for x, y in zip(ta[:10], tb[:10]))
     (la, ra), (lb, rb) = sr.get_statistics(), so.get_statistics()
     assert torch.equal(la, lb) and torch.equal(ra, rb)
+    # discriminator: the TSC fork's constructor / predict_disc_reward over the same weights and normaliser
+    from qa_b200.rsl_rl import DiscriminatorTSC, Normalizer
+    wd = synthetic.make_weights(3)
+    nr, no = ref.utils.Normalizer(98), Normalizer(98)
+    for nn_ in (nr, no):
+        nn_.mean, nn_.var = wd["norm_mean"].numpy().copy(), wd["norm_var"].numpy().copy()
+    args = (98, 49, 5, 0.02, "MSELoss", None, 0.05, 0.3, 0.2, 2.0, 2, [512, 256])
+    dr_, do_ = ref.discriminator.Discriminator(*args, nr, "cpu"), DiscriminatorTSC(*args, no, "cpu")
+    dr_.load_state_dict(wd["disc"])
+    do_.load_state_dict(wd["disc"])
+    obs_b = torch.randn(N, 671, generator=g)
+    hist = 0.5 * torch.randn(N, 2, 49, generator=g)
+    rew_t = torch.rand(N, 1, generator=g)
+    for a, b in zip(dr_.predict_disc_reward(rew_t, obs_b, hist), do_.predict_disc_reward(rew_t, obs_b, hist)):
+        assert a.dtype == b.dtype and torch.allclose(a, b, rtol=1e-6, atol=1e-7), float((a - b).abs().max())
     print(f"interop OK (tsc): reference PPO.act / PPO.update over qa_b200 ActorCriticTSC + Estimator == over the reference's "
           f"(max |diff| of act outputs {worst:.1e}; update() = {[round(x, 6) for x in got['update']]}; lr {got['lr']:.6g})")
 

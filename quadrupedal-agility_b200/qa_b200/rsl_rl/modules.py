@@ -9,6 +9,8 @@ dense-contraction site of the hot path.
 """
 from typing import List
 
+import types
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -295,7 +297,7 @@ class Estimator(nn.Module):
 
 class Discriminator(nn.Module):
     """Trunk 98->512->256 (ReLU) + heads d(1) / classifier(dim_c) / encoder_eps(1); per-step style reward
-    `predict_disc_reward` (discriminator.py:12-118).  The discriminator UPDATE is SURVEY 8(f) "next"."""
+    `predict_disc_reward` (discriminator.py:12-118); its update is `SSInfoGAIL.update_ss_info_gail`."""
 
     def __init__(self, env, input_dim, num_disc_obs, dim_c, dt, disc_loss_function, reward_i_normalizer,
                  reward_i_coef, reward_us_coef, reward_ss_coef, reward_t_coef, disc_history_len, disc_obs_len,
@@ -389,3 +391,19 @@ class Discriminator(nn.Module):
         ws = [torch.flatten(m.weight) for m in self.trunk.modules() if isinstance(m, nn.Linear)]
         ws.append(torch.flatten(self.linear.weight))
         return ws
+
+
+class DiscriminatorTSC(Discriminator):
+    """The TSC fork's constructor and call signature (tsc/rsl_rl/algorithms/discriminator.py:12-110): no env argument, no
+    task-observation weighting, the running normaliser is a member and `predict_disc_reward(reward_t, obs, obs_disc)` uses it.
+    Same parameters / `state_dict` keys as the BBC class, so a BBC checkpoint's `disc` loads into it (`load_bbc`, :647-660)."""
+
+    def __init__(self, input_dim, num_disc_obs, dim_c, dt, disc_loss_function, reward_i_normalizer, reward_i_coef,
+                 reward_us_coef, reward_ss_coef, reward_t_coef, disc_obs_len, hidden_units, normalizer, device):
+        env = types.SimpleNamespace(task_obs_weight_decay=False, task_obs_weight=1.0, dim_c=dim_c)
+        super().__init__(env, input_dim, num_disc_obs, dim_c, dt, disc_loss_function, reward_i_normalizer, reward_i_coef,
+                         reward_us_coef, reward_ss_coef, reward_t_coef, disc_obs_len, disc_obs_len, 0.0, hidden_units, device)
+        self.normalizer = normalizer
+
+    def predict_disc_reward(self, reward_t, obs, obs_disc, normalizer=None):
+        return super().predict_disc_reward(reward_t, obs, obs_disc, normalizer=self.normalizer if normalizer is None else normalizer)
