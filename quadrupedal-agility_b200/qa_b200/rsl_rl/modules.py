@@ -7,9 +7,8 @@ buffer (`FlatParams`), with a matching flat gradient buffer -- the unit the NCCL
 clip+Adam kernel (K8) operate on; and the dense layers run through `qa_b200.rsl_rl.linear`, the single
 dense-contraction site of the hot path.
 """
-from typing import List
-
 import types
+from typing import List
 
 import torch
 import torch.nn as nn
