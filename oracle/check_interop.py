@@ -206,6 +206,21 @@ def main_tsc():
         assert all(torch.equal(x, y) for x, y in zip(ta[:10], tb[:10]))
     (la, ra), (lb, rb) = sr.get_statistics(), so.get_statistics()
     assert torch.equal(la, lb) and torch.equal(ra, rb)
+    # the frozen low-level controller: the fork's ActorCriticBBC over a BBC checkpoint's weights
+    from qa_b200.rsl_rl import ActorCriticBBC
+    wb = synthetic.make_weights(3)
+    bbc_policy = dict(actor_hidden_dims=[512, 256, 128], critic_hidden_dims=[512, 256, 128], priv_encoder_dims=[64], activation="elu")
+    br = ref.actor_critic.ActorCriticBBC(101, 671, 12, 65, 8, 10, 4, 29, 11, **bbc_policy)
+    bo = ActorCriticBBC(101, 671, 12, 65, 8, 10, 4, 29, 11, **bbc_policy)
+    br.load_state_dict(wb["ac"])
+    bo.load_state_dict(wb["ac"])
+    assert list(br.state_dict()) == list(bo.state_dict()) and br.train_with_estimated_latent and bo.train_with_estimated_latent
+    obs_bbc = 0.5 * torch.randn(N, 671, generator=g)
+    with torch.no_grad():
+        for he in (True, False):
+            a, b = br.act_inference(obs_bbc, hist_encoding=he), bo.act_inference(obs_bbc, hist_encoding=he)
+            assert torch.allclose(a, b, rtol=1e-6, atol=1e-6), (he, float((a - b).abs().max()))
+        assert not torch.allclose(bo.act_inference(obs_bbc, hist_encoding=True), bo.act_inference(obs_bbc, hist_encoding=False))
     # discriminator: the TSC fork's constructor / predict_disc_reward over the same weights and normaliser
     from qa_b200.rsl_rl import DiscriminatorTSC, Normalizer
     wd = synthetic.make_weights(3)

@@ -392,6 +392,21 @@ class Discriminator(nn.Module):
         return ws
 
 
+class ActorCriticBBC(ActorCritic):
+    """The frozen low-level controller as the TSC fork constructs it (tsc/rsl_rl/modules/actor_critic.py:286-447): the BBC
+    `ActorCritic` with the fork's argument list -- `num_prop` INCLUDES the auxiliary lanes and `num_auxiliary` is subtracted
+    (:312) -- and the fork's default `train_with_estimated_latent=True` (the controller acts on the history-encoder latent).
+    Same parameters / `state_dict` keys as `ActorCritic`: a BBC checkpoint's `actor_critic` loads into it (`load_bbc`)."""
+
+    def __init__(self, num_actor_obs, num_critic_obs, num_actions, num_prop, num_auxiliary, num_hist, num_explicit, num_latent,
+                 num_command, actor_hidden_dims=[256, 256, 256], critic_hidden_dims=[256, 256, 256], priv_encoder_dims=[256, 256],
+                 activation='elu', init_noise_std=1.0, fixed_std=False, train_with_estimated_latent=True, **kwargs):
+        super().__init__(num_actor_obs, num_critic_obs, num_actions, num_prop - num_auxiliary, num_hist, num_explicit, num_latent,
+                         num_command, actor_hidden_dims=actor_hidden_dims, critic_hidden_dims=critic_hidden_dims,
+                         priv_encoder_dims=priv_encoder_dims, activation=activation, init_noise_std=init_noise_std,
+                         fixed_std=fixed_std, train_with_estimated_latent=train_with_estimated_latent, **kwargs)
+
+
 class DiscriminatorTSC(Discriminator):
     """The TSC fork's constructor and call signature (tsc/rsl_rl/algorithms/discriminator.py:12-110): no env argument, no
     task-observation weighting, the running normaliser is a member and `predict_disc_reward(reward_t, obs, obs_disc)` uses it.

@@ -24,7 +24,7 @@ import torch.nn.functional as F
 from .. import ops
 from . import checkpoint as ckpt
 from .depth_backbone import DepthOnlyFCBackbone58x87, RecurrentDepthBackbone
-from .modules import ActorCritic, Discriminator, Estimator
+from .modules import ActorCriticBBC, Discriminator, Estimator
 from .train_log import EpisodeBook, ScalarLog, log_tsc
 from .tsc import ActorCriticTSC, PPO
 from .utils import Normalizer, install_pickle_alias
@@ -51,9 +51,10 @@ class OnPolicyRunnerTSC:
         bbc_cfg = {k: v for k, v in self.policy_cfg.items() if k not in ("scan_encoder_dims", "tanh_encoder_output",
                                                                          "continue_from_last_std", "rnn_type",
                                                                          "rnn_hidden_size", "rnn_num_layers")}
-        self.actor_critic_bbc = ActorCritic(self.num_obs_bbc, self.num_critic_obs, env.num_actions,
-                                            self.n_proprio - self.n_auxiliary, self.history_len, self.n_priv,
-                                            self.n_priv_latent, self.num_command, **bbc_cfg).to(device)
+        # the fork's ActorCriticBBC (:72-81): acts on the history-encoder latent (train_with_estimated_latent defaults to True)
+        self.actor_critic_bbc = ActorCriticBBC(self.num_obs_bbc, self.num_critic_obs, env.num_actions, self.n_proprio,
+                                               self.n_auxiliary, self.history_len, self.n_priv, self.n_priv_latent,
+                                               self.num_command, **bbc_cfg).to(device)
         self.estimator = Estimator(input_dim=self.n_proprio - self.n_auxiliary, output_dim=self.n_priv,
                                    hidden_dims=self.estimator_cfg["hidden_dims"]).to(device)
         est_paras = dict(priv_states_dim=self.n_priv, num_prop=self.n_proprio - self.n_auxiliary, num_auxiliary=self.n_auxiliary,
