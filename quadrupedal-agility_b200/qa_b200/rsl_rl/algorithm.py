@@ -234,6 +234,14 @@ class SSInfoGAIL:
         qdist.allreduce_mean_scalar_(self._kl)
         return scale
 
+    @staticmethod
+    def weighted_bce_loss(predictions, targets, weights):                     # gail.py:219-223
+        return (weights * F.binary_cross_entropy_with_logits(predictions, targets, reduction='none')).mean()
+
+    @staticmethod
+    def weighted_mse_loss(predictions, targets, weights):                     # gail.py:225-229
+        return (weights * F.mse_loss(predictions, targets, reduction='none')).mean()
+
     def stage_disc_inserts(self, on: bool = True):
         """Replay-buffer inserts of a rollout go to a (T,N,.) staging area at fixed addresses (so that the rollout can
         be a replayed CUDA graph) and are appended to the ring by `flush_disc_stage()` after the rollout."""

@@ -235,6 +235,12 @@ class ActorCritic(nn.Module):
         x = torch.cat(parts, dim=-1)[:, :n_in]
         return run_mlp(self.actor_trunk, x, head=self.actor_head)
 
+    @staticmethod
+    def init_weights(sequential, scales):
+        """Orthogonal re-initialisation of a stack's Linear layers, gain per layer (actor_critic.py:147-151; unused there too)."""
+        for gain, layer in zip(scales, (m for m in sequential if isinstance(m, nn.Linear))):
+            nn.init.orthogonal_(layer.weight, gain=gain)
+
     def update_distribution(self, observations, hist_encoding: bool, priv_latent=None):
         mean = self._actor_mean(observations, hist_encoding, priv_latent)
         self._mean = mean

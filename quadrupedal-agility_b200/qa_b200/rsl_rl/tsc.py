@@ -21,7 +21,7 @@ from .. import ops
 from .. import dist as qdist
 from .algorithm import FlatAdam, _RowLossFused
 from .linear import linear_act
-from .modules import FlatParams, StateHistoryEncoder, _mlp, get_activation, run_mlp
+from .modules import ActorCritic, FlatParams, StateHistoryEncoder, _mlp, get_activation, run_mlp
 
 EPS = torch.finfo(torch.float32).eps
 
@@ -127,6 +127,8 @@ class ActorCriticTSC(nn.Module):
 
     def reset(self, dones=None):
         pass
+
+    init_weights = staticmethod(ActorCritic.init_weights)
 
     def forward(self):
         raise NotImplementedError
