@@ -228,7 +228,8 @@ def bbc_train_cfg() -> dict:
                           priv_reg_coef_schedual_resume=[0, 0.1, 0, 1]),
         "estimator": dict(train_with_estimated_explicit=True, learning_rate=1.0e-4, hidden_dims=[128, 64]),
         "runner": dict(policy_class_name="ActorCritic", algorithm_class_name="SSInfoGAIL", num_steps_per_env=24,
-                       max_iterations=500000, save_interval=100, experiment_name="go2_locomotion", run_name="",
+                       max_iterations=500000, save_interval=100, experiment_name="go2_locomotion", run_name="", experiment_idx=0,
+                       pre_trained_actor_path=[],
                        dagger_update_freq=20, motion_files_lb=[], motion_files_ulb=[], num_preload_transitions=200000,
                        reward_i_coef=1.0, reward_us_coef=0.01, reward_ss_coef=0.2, reward_t_coef=0.2,
                        disc_hidden_units=[512, 256], min_normalized_std=[0.05, 0.02, 0.05] * 4,
@@ -247,14 +248,16 @@ def tsc_train_cfg(use_camera: bool = False) -> dict:
         "runner_class_name": "OnPolicyRunner",
         "policy": dict(init_noise_std=1.0, continue_from_last_std=True, scan_encoder_dims=[128, 64, 32],
                        actor_hidden_dims=[512, 256, 128], critic_hidden_dims=[512, 256, 128], priv_encoder_dims=[64],
-                       activation="elu", tanh_encoder_output=False),
+                       activation="elu", tanh_encoder_output=False, rnn_type="lstm", rnn_hidden_size=512, rnn_num_layers=1),
         "algorithm": dict(value_loss_coef=1.0, use_clipped_value_loss=True, clip_param=0.2, entropy_coef=0.01,
                           num_learning_epochs=5, num_mini_batches=4, learning_rate=5.e-4, schedule="adaptive", gamma=0.99,
                           lam=0.95, desired_kl=0.01, max_grad_norm=1.0, dagger_update_freq=20,
-                          priv_reg_coef_schedual=[0, 0.1, 500, 1000]),
-        "estimator": dict(train_with_estimated_states=True, learning_rate=1.e-4, hidden_dims=[128, 64], load_estimator_bbc=True),
+                          priv_reg_coef_schedual=[0, 0.1, 500, 1000], priv_reg_coef_schedual_resume=[0, 0.1, 0, 1]),
+        "estimator": dict(train_with_estimated_states=True, learning_rate=1.e-4, hidden_dims=[128, 64], load_estimator_bbc=True,
+                          priv_states_dim=4, num_prop=57, num_auxiliary=8, num_scan=132),
         "runner": dict(policy_class_name="ActorCritic", algorithm_class_name="PPO", num_steps_per_env=24, max_iterations=50000,
                        save_interval=100, experiment_name="agility", run_name="", disc_loss_function="MSELoss",
                        reward_i_coef=0.05, reward_us_coef=0.0, reward_ss_coef=0.0, reward_t_coef=2.0,
-                       disc_hidden_units=[512, 256], bbc_path="weights/bbc/model.pt"),
+                       disc_hidden_units=[512, 256], bbc_path="weights/bbc/model.pt", resume=False, load_run=-1, checkpoint=-1,
+                       resume_path=None),
     }
