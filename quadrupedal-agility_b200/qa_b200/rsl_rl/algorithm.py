@@ -154,6 +154,7 @@ class SSInfoGAIL:
         self.disc_weight_decay, self.us_coef, self.ss_coef = disc_weight_decay, us_coef, ss_coef
         self.prior_soft_coef, self.info_max_coef, self.begin_rim = prior_soft_coef, info_max_coef, begin_rim
         self.dim_c = env.dim_c
+        self.info_max_coef_on = 0.0                                 # gail.py:143; ramps up after `begin_rim` updates (:251-253)
         self.disc_loss_function = disc_loss_function
         self.disc_history_len, self.disc_obs_len, self.num_disc_obs = disc_history_len, disc_obs_len, num_disc_obs
         self.obs_disc_weight_step = obs_disc_weight_step
