@@ -236,6 +236,16 @@ def main_tsc():
     rew_t = torch.rand(N, 1, generator=g)
     for a, b in zip(dr_.predict_disc_reward(rew_t, obs_b, hist), do_.predict_disc_reward(rew_t, obs_b, hist)):
         assert a.dtype == b.dtype and torch.allclose(a, b, rtol=1e-6, atol=1e-7), float((a - b).abs().max())
+    for loss_fn in ("BCEWithLogitsLoss", "WassersteinLoss"):                       # the other two style-reward mappings
+        ri_r, ri_o = ref.utils.Normalizer(1), Normalizer(1)
+        args2 = (98, 49, 5, 0.02, loss_fn, None, 0.05, 0.3, 0.2, 2.0, 2, [512, 256])
+        d1, d2 = ref.discriminator.Discriminator(*args2, nr, "cpu"), DiscriminatorTSC(*args2, no, "cpu")
+        d1.reward_i_normalizer, d2.reward_i_normalizer = ri_r, ri_o
+        d1.load_state_dict(wd["disc"])
+        d2.load_state_dict(wd["disc"])
+        for _ in range(2):                                                          # second call sees the updated normaliser
+            for a, b in zip(d1.predict_disc_reward(rew_t, obs_b, hist), d2.predict_disc_reward(rew_t, obs_b, hist)):
+                assert a.dtype == b.dtype and torch.allclose(a, b, rtol=1e-5, atol=1e-6), (loss_fn, float((a - b).abs().max()))
     print(f"interop OK (tsc): reference PPO.act / PPO.update over qa_b200 ActorCriticTSC + Estimator == over the reference's "
           f"(max |diff| of act outputs {worst:.1e}; update() = {[round(x, 6) for x in got['update']]}; lr {got['lr']:.6g})")
 

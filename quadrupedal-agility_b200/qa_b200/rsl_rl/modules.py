@@ -378,6 +378,12 @@ class Discriminator(nn.Module):
                 reward_i = -torch.log(torch.maximum(1 - 1 / (1 + torch.exp(-d)), torch.tensor(0.0001, device=d.device)))
             elif self.disc_loss_function == "MSELoss":
                 reward_i = torch.clamp(1 - (1 / 4) * torch.square(d - 1), min=0)
+            elif self.disc_loss_function == "WassersteinLoss":             # :97-99: running normalisation of the critic output
+                reward_i = self.reward_i_normalizer.normalize_torch(d, d.device)
+                if hasattr(self.reward_i_normalizer, "update_torch"):
+                    self.reward_i_normalizer.update_torch(d)
+                else:
+                    self.reward_i_normalizer.update(d.cpu().numpy())
             else:
                 raise ValueError("Unexpected style reward mapping specified")
             reward_us = -torch.abs(eps - label_eps)
