@@ -452,6 +452,10 @@ class SSInfoGAIL:
         optim_q_eps = trunk + encoder_eps, optim_q_c = trunk + classifier, weight_decay 1e-3 each -- the trunk is stepped
         by all three, in that order, with separate moments."""
         d = self.disc
+        if self.disc_loss_function == "WassersteinLoss":
+            # the reference steps the critic with RMSprop in that mode (gail.py:124-125); K8 is an Adam kernel -- refuse rather
+            # than train with a different optimiser (the Wasserstein REWARD mapping of predict_disc_reward is supported)
+            raise NotImplementedError("discriminator update with WassersteinLoss needs RMSprop for optim_d (gail.py:124-125)")
         self.disc_flat = d.flatten_parameters()
         sl = self.disc_flat.slices
         lo = lambda n: sl[n][0]                                                # noqa: E731
