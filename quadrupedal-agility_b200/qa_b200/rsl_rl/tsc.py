@@ -12,6 +12,7 @@ launch per minibatch (K6), the TSC loss graph as one forward+backward kernel (K1
 adaptive LR (K13), fused clip+Adam (K8), GAE warp-scan (K5), the whole minibatch step replayed as a CUDA graph.
 Random draws can be injected (`normal_draw`, `mode_u`) for parity with the oracle.
 """
+import os
 from typing import Optional
 
 import torch
@@ -68,10 +69,13 @@ class Actor(nn.Module):
         x = run_mlp(nn.Sequential(*mods[:-2]), x)                               # Linear+ELU stack on the GEMM chain
         return torch.tanh(linear_act(x, mods[-2].weight, mods[-2].bias, None))
 
-    def forward(self, obs, hist_encoding: bool, eval=False, scandots_latent=None):
+    def forward(self, obs, hist_encoding: bool, eval=False, scandots_latent=None, priv_latent=None):
         scan = self._scan_latent(obs) if scandots_latent is None else scandots_latent
         o = self.num_prop + self.num_scan
-        latent = self.infer_hist_latent(obs) if hist_encoding else self.infer_priv_latent(obs)
+        if hist_encoding:
+            latent = self.infer_hist_latent(obs)
+        else:                                             # a caller that also needs the latent may hand it in (one encoder pass)
+            latent = self.infer_priv_latent(obs) if priv_latent is None else priv_latent
         n_in = self.num_prop + self.scan_encoder_output_dim + self.num_priv_explicit + self.num_priv_latent
         parts = [obs[:, :self.num_prop], scan, obs[:, o:o + self.num_priv_explicit], latent]
         pad = (n_in + 3) // 4 * 4 - n_in                                        # 16-byte row pitch: a legal TMA operand
@@ -150,8 +154,8 @@ class ActorCriticTSC(nn.Module):
     def entropy_d(self):
         return -(self._logit * self._prob).sum(-1)
 
-    def update_distribution(self, observations, hist_encoding=False):
-        emb = self.actor(observations, hist_encoding)
+    def update_distribution(self, observations, hist_encoding=False, priv_latent=None):
+        emb = self.actor(observations, hist_encoding, priv_latent=priv_latent)
         self._logits = linear_act(emb, self.actor.actor_d.weight, self.actor.actor_d.bias, None)
         prob = torch.softmax(self._logits, dim=-1)
         self._prob = prob / prob.sum(-1, keepdim=True)                          # Categorical(probs=prob)
@@ -328,6 +332,7 @@ class PPO:
         self.if_depth = depth_encoder is not None
         self.num_actions_d = self.actor_critic.num_actions_d
         self._lr0, self.hist_encoder_optimizer = learning_rate, None
+        self.share_priv_latent = os.environ.get("QA_SHARE_PRIV_LATENT", "0") == "1"   # opt-in, see SSInfoGAIL
         if self.if_depth:
             # student distillation (ppo.py:78-88): conv / GRU / batch-norm modules on cuDNN with torch.optim.Adam;
             # the three optimisers overlap on purpose, each with its own moments
@@ -446,9 +451,14 @@ class PPO:
     def _forward_backward(self):
         mb, ac, est = self._mb, self.actor_critic, self.estimator
         obs = mb["obs"]
-        ac.update_distribution(obs, False)
+        if self.share_priv_latent:                                          # ppo.py:176, :186 evaluate the encoder twice
+            priv_latent = ac.actor.infer_priv_latent(obs)
+            ac.update_distribution(obs, False, priv_latent=priv_latent)
+        else:
+            ac.update_distribution(obs, False)
         value = ac.evaluate(mb["critic_obs"])
-        priv_latent = ac.actor.infer_priv_latent(obs)
+        if not self.share_priv_latent:
+            priv_latent = ac.actor.infer_priv_latent(obs)
         sl = self._explicit_slice()
         if self.fused_loss:
             priv_reg_loss = _RowLossFused.apply(priv_latent, mb["hist_latent"], 1, self._aux_loss[0:1])

@@ -96,3 +96,40 @@ def test_shared_priv_latent_pass_gives_the_same_ppo_step_gradients():
     assert torch.equal(ge, ge2) and torch.allclose(ps, ps2, rtol=1e-6, atol=1e-8) and torch.allclose(ax, ax2, rtol=1e-6, atol=1e-8)
     lo, n = alg.ac_flat.slices["priv_encoder.0.weight"]
     assert float(ga[lo:lo + n].abs().max()) > 0                   # the encoder does receive both gradient paths
+
+
+def test_tsc_shared_priv_latent_pass_gives_the_same_ppo_step_gradients():
+    """The same opt-in for the TSC `PPO` minibatch step (ppo.py:176, :186 evaluate the encoder twice)."""
+    from qa_b200 import synthetic
+    from qa_b200.config import tsc_train_cfg
+    from qa_b200.rsl_rl import ActorCriticTSC, Estimator, PPO
+    res = []
+    for share in (False, True):
+        torch.manual_seed(0)
+        cfg = tsc_train_cfg()
+        ac = ActorCriticTSC(65, 8, 132, 800, 29, 4, 10, 3, 6, device="cpu", **cfg["policy"])
+        est = Estimator(input_dim=57, output_dim=4, hidden_dims=[128, 64])
+        paras = dict(priv_states_dim=4, num_prop=57, num_auxiliary=8, num_scan=132, learning_rate=1e-4, train_with_estimated_states=True)
+        alg = PPO(ac, None, est, paras, device="cpu", use_cuda_graph=False, fused_loss=False, **cfg["algorithm"])
+        synthetic.load_student_weights(alg.actor_critic, 3)
+        with torch.no_grad():
+            alg.actor_critic.std.fill_(0.8)
+        alg.share_priv_latent = share
+        alg.init_storage(32, 8, [800], [None], [19])
+        alg._alloc_minibatch(128)
+        alg._priv_reg_coef.fill_(0.05)
+        g = torch.Generator().manual_seed(1)
+        mb = alg._mb
+        mb["obs"].copy_(0.5 * torch.randn(128, 800, generator=g))
+        mb["critic_obs"].copy_(mb["obs"])
+        mb["actions"].copy_(torch.randn(128, 19, generator=g))
+        mb["actions"][:, 0] = torch.randint(0, 3, (128,), generator=g).float()
+        for k in ("old_actions_log_prob_d", "old_actions_log_prob_c", "advantages", "returns", "values"):
+            mb[k].copy_(torch.randn(128, 1, generator=g))
+        mb["old_mu"].copy_(0.1 * torch.randn(128, 18, generator=g))
+        mb["old_sigma"].fill_(0.9)
+        mb["hist_latent"].copy_(0.3 * torch.randn(128, 29, generator=g))
+        alg._forward_backward()
+        res.append((alg.ac_flat.grad.clone(), alg.est_flat.grad.clone()))
+    (ga, ge), (gb, ge2) = res
+    assert float(ga.abs().max()) > 0 and torch.allclose(gb, ga, rtol=1e-5, atol=1e-7 * float(ga.abs().max())) and torch.equal(ge, ge2)
