@@ -222,6 +222,8 @@ def run_ours(args):
             line["tsc_env"] = time_tsc_env(dev)
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if world == 1:
+            line["roofline_gemm"] = gemm_roofline_sample(dev, pk)
         if world == 1 and not args.no_torch_gpu_baseline:
             line["torch_gpu_baseline"] = torch_gpu_baseline_sample(dev)
         print(json.dumps(line), flush=True)
@@ -309,6 +311,54 @@ def _cpu_line(threads, rollout_steps, minibatch_steps, full, r):
                        f"{rollout_steps}/24 rollout steps ({r['t_rollout']:.2f} s), GAE ({r['t_gae']:.3f} s), "
                        f"{minibatch_steps}/20 PPO minibatch steps of 24576 ({r['t_update']:.2f} s), "
                        f"extrapolated to one full iteration = {full:.2f} s")}
+
+
+def gemm_roofline_sample(dev, pk, reps=20):
+    """The kernel that dominates the step by TIME (the tcgen05 GEMM, ~50 % of an iteration; K2 is ~1 %): the critic's first
+    layer at minibatch size (24576 x 512 x 671) forward with the fused bias + ELU epilogue, and its dX / dW contractions, each
+    timed alone with CUDA events after a 256 MiB L2 flush.  Tensor-core roofline: TF32 operands run at half the bf16 rate, so
+    the peak is MEASURED_PEAKS.json's bf16 figure / 2.  Guarded like the baseline legs."""
+    try:
+        from qa_b200 import ops
+        M, N, K = 24576, 512, 671
+        kp = (K + 3) // 4 * 4
+        g = torch.Generator().manual_seed(0)
+        x = torch.randn(M, kp, generator=g).to(dev)[:, :K]
+        w = (torch.randn(N, kp, generator=g) / K ** 0.5).to(dev)[:, :K]
+        b = torch.randn(N, generator=g).to(dev)
+        y = torch.empty(M, N, device=dev)
+        gz = torch.randn(M, N, generator=g).to(dev)
+        dx = torch.empty(M, kp, device=dev)[:, :K]
+        dw = torch.zeros(N, kp, device=dev)[:, :K]
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+        def timed(fn):
+            for _ in range(3):
+                fn()
+            tot = 0.0
+            for _ in range(reps):
+                flush.fill_(0)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn()
+                e1.record()
+                e1.synchronize()
+                tot += e0.elapsed_time(e1)
+            return tot / reps * 1e3                                  # us per launch
+
+        t_fwd = timed(lambda: ops.linear_fwd(x, w, b, y, "elu"))
+        t_dx = timed(lambda: ops.linear_bwd(gz, None, w, dx=dx))
+        t_dw = timed(lambda: ops.linear_bwd(gz, x, None, dw=dw))
+        flops = 2.0 * M * N * K
+        peak = pk["bf16_tflops"] / 2.0
+        ach = flops / t_fwd / 1e6
+        return {"bound": "tensor", "kernel": "k_gemm_tf32 (tcgen05, TF32 operands / fp32 accumulate)", "shape": [M, N, K],
+                "achieved": ach, "peak": peak, "peak_source": "MEASURED_PEAKS.json bf16_tflops / 2 (TF32 runs at half the bf16 rate)",
+                "unit": "TFLOP/s", "frac": ach / peak, "us_per_launch": t_fwd, "dx_us_per_launch": t_dx, "dw_us_per_launch": t_dw,
+                "dx_tflops": flops / t_dx / 1e6, "dw_tflops": flops / t_dw / 1e6, "flops_per_launch": flops,
+                "how": f"CUDA events around single launches, 256 MiB L2 flush before each, mean of {reps}"}
+    except Exception as e:                                               # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
 
 
 def torch_gpu_baseline_sample(dev, n_envs=ENVS_PER_GPU):

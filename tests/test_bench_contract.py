@@ -50,3 +50,12 @@ def test_torch_baseline_leg_runs_the_full_iteration_and_never_raises():
         assert set(bad) == {"error"}
     finally:
         torch.set_num_threads(threads)
+
+
+def test_gemm_roofline_leg_never_raises():
+    """Without a GPU the tcgen05 launch is refused; the leg must hand that back as an `error` entry (it is reported beside the
+    K2 roofline: the tcgen05 GEMM is the kernel that dominates the step by time)."""
+    import torch
+    import bench
+    out = bench.gemm_roofline_sample(torch.device("cpu"), {"bf16_tflops": 1600.0}, reps=1)
+    assert set(out) == {"error"} and out["error"].startswith("RuntimeError")
