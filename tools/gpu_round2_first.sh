@@ -14,7 +14,7 @@ import json
 for f in ("gpurun_out/bench.json", "gpurun_out/bench_disc_batched.json"):
     try:
         d = [json.loads(l) for l in open(f) if l.startswith("{")][-1]
-        print(f, "disc_update_ms", d.get("disc_update_ms"), "value", d.get("value"), "torch_gpu_baseline", d.get("torch_gpu_baseline"))
+        print(f, "disc_update_ms", d.get("disc_update_ms"), "value", d.get("value"), "torch_gpu_baseline", d.get("torch_gpu_baseline"), "roofline_gemm", d.get("roofline_gemm"))
     except Exception as e:
         print(f, "unreadable:", e)
 PY
