@@ -99,6 +99,22 @@ def main():
         assert torch.allclose(a, b, rtol=1e-5, atol=1e-7), (float(a), float(b))
     assert abs(want["lr"] - got["lr"]) < 1e-12
     post_step_equal(want, got, lr_ac=1e-3, lr_est=1e-4)
+    # storage: the reference's 11-tuple generator over this package's RolloutStorage (same permutation under the same seed)
+    from qa_b200.rsl_rl import RolloutStorage
+    gs = torch.Generator().manual_seed(11)
+    sr, so = ref.RolloutStorage(8, 6, [671], [671], [12], device="cpu"), RolloutStorage(8, 6, [671], [671], [12], device="cpu")
+    for name in ("observations", "privileged_observations", "actions", "values", "advantages", "returns", "actions_log_prob", "mu", "sigma"):
+        v = torch.randn(getattr(sr, name).shape, generator=gs)
+        getattr(sr, name).copy_(v)
+        getattr(so, name).copy_(v)
+    torch.manual_seed(3)
+    a = list(sr.mini_batch_generator(3, 2))
+    torch.manual_seed(3)
+    b = list(so.mini_batch_generator(3, 2))
+    assert len(a) == len(b) == 6
+    for ta, tb in zip(a, b):
+        assert len(ta) == len(tb) == 11 and ta[9] == tb[9] == (None, None) and ta[10] is None and tb[10] is None
+        assert all(torch.equal(x, y) for x, y in zip(ta[:9], tb[:9]))
     print(f"interop OK: reference SSInfoGAIL.act / update_actor_critic over qa_b200 ActorCritic + Estimator == over the reference's "
           f"(max |diff| of act outputs {worst:.1e}; losses {[round(float(x), 6) for x in got['losses']]}; lr {got['lr']:.6g})")
 
