@@ -115,6 +115,16 @@ def main():
     for ta, tb in zip(a, b):
         assert len(ta) == len(tb) == 11 and ta[9] == tb[9] == (None, None) and ta[10] is None and tb[10] is None
         assert all(torch.equal(x, y) for x, y in zip(ta[:9], tb[:9]))
+    # replay buffer ring (storage/replay_buffer.py:23-42): inserts across the wrap-around
+    import importlib
+    from qa_b200.rsl_rl.algorithm import ReplayBuffer
+    rr_, ro_ = importlib.import_module("rsl_rl.storage.replay_buffer").ReplayBuffer(49, 5, 2, 50, "cpu"), ReplayBuffer(49, 5, 2, 50, "cpu")
+    for n_ins in (20, 20, 25, 50, 7):
+        st_, e_, c_ = torch.randn(n_ins, 98, generator=gs), torch.rand(n_ins, 1, generator=gs), torch.rand(n_ins, 5, generator=gs)
+        rr_.insert(st_, e_, c_)
+        ro_.insert(st_, e_, c_)
+        assert (rr_.step, rr_.num_samples) == (ro_.step, ro_.num_samples)
+        assert torch.equal(rr_.states, ro_.states) and torch.equal(rr_.latent_eps, ro_.latent_eps) and torch.equal(rr_.latent_c, ro_.latent_c)
     print(f"interop OK: reference SSInfoGAIL.act / update_actor_critic over qa_b200 ActorCritic + Estimator == over the reference's "
           f"(max |diff| of act outputs {worst:.1e}; losses {[round(float(x), 6) for x in got['losses']]}; lr {got['lr']:.6g})")
 
