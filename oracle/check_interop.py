@@ -236,26 +236,28 @@ def main_tsc():
     # driven unbound over the same injected state and the same multiplicative-noise draw
     import types
     from qa_b200.legged_robot_tsc import LeggedRobotTSC, TscEnvConfig
-    cfg_o = TscEnvConfig(num_envs=N)
     ep = torch.randint(0, 3, (N,), generator=g)
     acts = torch.cat([torch.randint(0, 3, (N, 1), generator=g).float(), 1.4 * torch.randn(N, 18, generator=g)], dim=1)
     u = torch.rand(N, 5, generator=g)
-    state = lambda: dict(episode_length_buf=ep.clone(), latent_c=torch.zeros(N, 5), latent_eps=torch.zeros(N, 1),   # noqa: E731
-                         commands=0.3 * torch.ones(N, 5), dim_c=5, device="cpu",
-                         mocap_indices=torch.tensor([2, 3, 4]))
-    so = types.SimpleNamespace(cfg=cfg_o, **state())
-    cmd_o = LeggedRobotTSC.set_commands(so, acts, action_noise_u=u)
-    rcfg = types.SimpleNamespace(commands=types.SimpleNamespace(resampling_time=cfg_o.resampling_time),
-                                 domain_rand=types.SimpleNamespace(randomize_action=True, action_noise=list(cfg_o.action_noise)))
-    sr_ = types.SimpleNamespace(cfg=rcfg, dt=cfg_o.dt, num_actions_c=6, command_ranges=cfg_o.command_ranges, **state())
-    saved_rand = ref.legged_robot.torch_rand_float
-    ref.legged_robot.torch_rand_float = lambda lo, hi, shape, device=None: (hi - lo) * u + lo
-    try:
-        want_cmd = ref.LeggedRobot.set_commands(sr_, acts)
-    finally:
-        ref.legged_robot.torch_rand_float = saved_rand
-    assert torch.equal(cmd_o, want_cmd) and torch.equal(so.commands, sr_.commands) and torch.equal(so.latent_c, sr_.latent_c)
-    assert torch.equal(so.latent_eps, sr_.latent_eps) and float(cmd_o.abs().sum()) > 0
+    for resampling_time in (0.02, 0.04):                             # every step (the shipped value) / every other step (masked)
+        cfg_o = TscEnvConfig(num_envs=N, resampling_time=resampling_time)
+        state = lambda: dict(episode_length_buf=ep.clone(), latent_c=torch.zeros(N, 5), latent_eps=torch.zeros(N, 1),   # noqa: E731
+                             commands=0.3 * torch.ones(N, 5), dim_c=5, device="cpu", mocap_indices=torch.tensor([2, 3, 4]))
+        so = types.SimpleNamespace(cfg=cfg_o, **state())
+        cmd_o = LeggedRobotTSC.set_commands(so, acts, action_noise_u=u)
+        rcfg = types.SimpleNamespace(commands=types.SimpleNamespace(resampling_time=cfg_o.resampling_time),
+                                     domain_rand=types.SimpleNamespace(randomize_action=True, action_noise=list(cfg_o.action_noise)))
+        sr_ = types.SimpleNamespace(cfg=rcfg, dt=cfg_o.dt, num_actions_c=6, command_ranges=cfg_o.command_ranges, **state())
+        saved_rand = ref.legged_robot.torch_rand_float
+        ref.legged_robot.torch_rand_float = lambda lo, hi, shape, device=None: (hi - lo) * u + lo
+        try:
+            want_cmd = ref.LeggedRobot.set_commands(sr_, acts)
+        finally:
+            ref.legged_robot.torch_rand_float = saved_rand
+        assert torch.equal(cmd_o, want_cmd) and torch.equal(so.commands, sr_.commands) and torch.equal(so.latent_c, sr_.latent_c)
+        assert torch.equal(so.latent_eps, sr_.latent_eps) and float(cmd_o.abs().sum()) > 0
+        due = (ep % int(resampling_time / cfg_o.dt) == 0)
+        assert bool(due.any()) and (resampling_time == 0.02 or not bool(due.all()))
     # the frozen low-level controller: the fork's ActorCriticBBC over a BBC checkpoint's weights
     from qa_b200.rsl_rl import ActorCriticBBC
     wb = synthetic.make_weights(3)

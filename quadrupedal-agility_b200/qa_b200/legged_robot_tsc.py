@@ -332,6 +332,7 @@ class LeggedRobotTSC:
                 raise AttributeError(k)
             setattr(self.cfg, k, v)
         self._const = self._build_const()
+        self._cmd_range_tensors = None                                       # set_commands' cached range table
 
     def attach_depth(self, depth) -> None:
         """Student path (`--use_camera`): `depth` is a `qa_b200.depth.DepthBuffer` bound to the simulator's camera tensors;
@@ -385,36 +386,38 @@ class LeggedRobotTSC:
 
     @torch.no_grad()
     def set_commands(self, actions, action_noise_u: Optional[torch.Tensor] = None):
-        """High-level action (mode index + 3 x 6 continuous) -> BBC command vector (:699-760)."""
+        """High-level action (mode index + 3 x 6 continuous) -> BBC command vector (:699-760).  The reference writes the
+        envs whose episode step is a multiple of the resampling period through `nonzero()` index lists (a host sync per
+        step); here the same values are computed for every env and selected with the mask, in place -- bit-equal results
+        (`oracle/check_interop.py tsc`), no sync."""
         cfg, dev = self.cfg, self.device
         period = int(cfg.resampling_time / cfg.dt)
-        env_ids = (self.episode_length_buf % period == 0).nonzero(as_tuple=False).flatten()
+        due = (self.episode_length_buf % period == 0)
         actions_d = actions[:, 0].to(torch.long)
-        mapped = self.mocap_indices[actions_d]
+        m = self.mocap_indices[actions_d]
         cols = actions_d[:, None] * cfg.num_actions_c + torch.arange(cfg.num_actions_c, device=dev) + 1
-        actions_c = actions[torch.arange(actions.size(0), device=dev)[:, None], cols]
-        if len(env_ids):
-            m = mapped[env_ids]
-            cmd = torch.clip(actions_c[env_ids, :], -1, 1)
-            self.latent_c[env_ids, :] = 0
-            self.latent_c[env_ids, m] = 1
-            self.latent_eps[env_ids, 0] = cmd[:, -1].clone()
-            cmd = (cmd + 1) / 2
-            self.commands[env_ids, :] = 0.0
+        cmd = torch.clip(torch.gather(actions, 1, cols), -1, 1)
+        rt = getattr(self, "_cmd_range_tensors", None)
+        if rt is None:                                                       # (3, dim_c, 2): lin_vel_x / lin_vel_y / ang_vel_yaw
             r = cfg.command_ranges
-            for k, name in enumerate(("lin_vel_x", "lin_vel_y", "ang_vel_yaw")):
-                t = torch.tensor(r[name], device=dev)
-                lo, hi = t[m, 0], t[m, 1]
-                self.commands[env_ids, k] = lo + (hi - lo) * cmd[:, k]
-            jump = m == (self.dim_c - 1)
-            jl, jh = r["jump_height"]
-            ll, lh = r["locomotion_height"]
-            self.commands[env_ids, 3] = (jl + (jh - jl) * cmd[:, 3]) * jump.float()
-            self.commands[env_ids, 4] = (ll + (lh - ll) * cmd[:, 4]) * (~jump).float()
+            rt = self._cmd_range_tensors = torch.tensor([r["lin_vel_x"], r["lin_vel_y"], r["ang_vel_yaw"]], device=dev)
+        self.latent_c.copy_(torch.where(due[:, None], torch.nn.functional.one_hot(m, self.latent_c.shape[1]).to(self.latent_c.dtype),
+                                        self.latent_c))
+        self.latent_eps[:, 0].copy_(torch.where(due, cmd[:, -1], self.latent_eps[:, 0]))
+        cmd01 = (cmd + 1) / 2
+        lo, hi = rt[:, m, 0].t(), rt[:, m, 1].t()                              # (N, 3)
+        new = torch.zeros_like(self.commands)
+        new[:, 0:3] = lo + (hi - lo) * cmd01[:, 0:3]
+        jump = m == (self.dim_c - 1)
+        jl, jh = cfg.command_ranges["jump_height"]
+        ll, lh = cfg.command_ranges["locomotion_height"]
+        new[:, 3] = (jl + (jh - jl) * cmd01[:, 3]) * jump.float()
+        new[:, 4] = (ll + (lh - ll) * cmd01[:, 4]) * (~jump).float()
+        self.commands.copy_(torch.where(due[:, None], new, self.commands))
         if cfg.randomize_action:
-            lo, hi = cfg.action_noise
+            lo_n, hi_n = cfg.action_noise
             u = torch.rand(self.commands.shape, device=dev) if action_noise_u is None else action_noise_u
-            self.commands *= (hi - lo) * u + lo
+            self.commands *= (hi_n - lo_n) * u + lo_n
         return torch.cat([self.commands, self.latent_eps, self.latent_c], dim=-1)
 
 
