@@ -224,3 +224,34 @@ def test_tsc_teacher_learn_loop_logs_and_saves_on_host(tmp_path, monkeypatch):
     r2.load(str(tmp_path / "model.pt"))
     for (k, v), w in zip(alg.actor_critic.state_dict().items(), r2.alg.actor_critic.state_dict().values()):
         assert torch.equal(v, w), k
+
+
+def test_tsc_runner_load_bbc_takes_the_shipped_checkpoint():
+    """tsc/rsl_rl/runners/on_policy_runner.py:647-660 on the checkpoint the reference ships (`tsc/weights/bbc/model.pt`): the
+    frozen controller, the estimator, the discriminator and its pickled normaliser."""
+    import os
+    import pytest
+    from qa_b200.config import tsc_train_cfg
+    from qa_b200.rsl_rl.tsc_runner import OnPolicyRunnerTSC
+    from qa_b200.rsl_rl.utils import install_pickle_alias
+    path = "/root/reference/tsc/weights/bbc/model.pt"
+    if not os.path.exists(path):
+        pytest.skip("the reference tree only exists in the build container")
+    cfg = tsc_train_cfg()
+    cfg["algorithm"].update(use_cuda_graph=False, fused_loss=False)
+    r = OnPolicyRunnerTSC(FakeTscEnv(), cfg, log_dir=None, device="cpu")
+    r.load_bbc(path)
+    install_pickle_alias()
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    for k, v in ck["actor_critic"].items():
+        assert torch.equal(r.actor_critic_bbc.state_dict()[k], v), k
+    for k, v in ck["estimator"].items():
+        assert torch.equal(r.estimator.state_dict()[k], v), k
+    for k, v in ck["disc"].items():
+        assert torch.equal(r.discriminator.state_dict()[k], v), k
+    assert np.array_equal(r.disc_normalizer.mean, ck["disc_normalizer"].mean) and r.disc_normalizer.count == ck["disc_normalizer"].count
+    assert not r.actor_critic_bbc.training and r.actor_critic_bbc.train_with_estimated_latent
+    obs_bbc = 0.3 * torch.randn(4, 671, generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        a = r.get_inference_policy_bbc()(obs_bbc, hist_encoding=True)
+    assert a.shape == (4, 12) and torch.isfinite(a).all()
