@@ -212,6 +212,9 @@ def main():
     run_env_case("n64a", 64, 7, counter_before=12, files=files, table=table, reset_frac=0.25, plant_frac=0.06)
     run_env_case("n64b_push", 64, 8, counter_before=399, files=files, table=table, reset_frac=0.25, plant_frac=0.06)
     run_env_case("n4096_check", 4096, 1234, counter_before=3, files=files, table=table, save=False)
+    # a step on which nothing resets, nothing times out and nothing is resampled: reset_idx's empty-set early return and the
+    # untouched extras (SURVEY a')
+    run_env_case("zero_reset_check", 64, 11, counter_before=5, files=files, table=table, save=False, reset_frac=0.0, plant_frac=0.0)
     import gen_golden_trainer
     gen_golden_trainer.main()
 
