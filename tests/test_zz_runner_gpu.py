@@ -269,3 +269,29 @@ def test_tsc_env_production_rng_is_bit_exact_against_the_oracle():
         assert_close(k, got[k], want[k])
     assert torch.equal(ids.cpu(), want["reset_env_ids"]) and len(ids) > 20
     assert_close("terminal", terminal, want["terminal_disc_states"])
+
+
+def test_post_physics_on_a_step_without_any_reset():
+    """A step on which no env resets, times out or resamples (the oracle is pinned against the reference on exactly this case,
+    oracle/gen_golden.py): empty compaction, every buffer equal, latched `extras` quantities untouched."""
+    import bbc_env as O
+    from helpers import mocap_table
+    from qa_b200 import synthetic
+    from qa_b200.config import BbcEnvConfig
+    from test_env_gpu import check_against, make_env
+    for N in (64, 4096):
+        cfg = BbcEnvConfig(num_envs=N)
+        static = synthetic.make_static(cfg, seed=11)
+        snap = synthetic.make_snapshot(cfg, seed=11, step=0, reset_frac=0.0, plant_frac=0.0)
+        draws = synthetic.make_rng_draws(cfg, seed=11, step=0)
+        table = mocap_table()
+        draws["mocap_clip_idx"] = table.sample_clip(draws["rt_c_idx"], draws["mocap_clip_u"])
+        want = O.post_physics_step(cfg, static, snap, draws, table, 6)
+        assert int(want["reset_buf"].sum()) == 0
+        env = make_env(cfg, static, snap, draws, 5, table=table)
+        means0, latched0 = env._episode_rew_means.clone(), env._time_outs_latched.clone()
+        env.post_physics_step()
+        torch.cuda.synchronize()
+        check_against(env, want, None, want["terminal_disc_states"], f"zero-reset[{N}]")
+        assert int(env._reset_count.item()) == 0
+        assert torch.equal(env._episode_rew_means, means0) and torch.equal(env._time_outs_latched, latched0)
