@@ -437,3 +437,8 @@ class LeggedRobot:
         # ... then the reference steps once with zero actions and returns that observation
         obs, priv, *_ = self.step(torch.zeros(self.num_envs, self.num_actions, device=self.device))
         return obs, priv
+
+
+from .rsl_rl.vec_env import VecEnv  # noqa: E402  (bottom of the module: rsl_rl imports nothing from here)
+
+VecEnv.register(LeggedRobot)

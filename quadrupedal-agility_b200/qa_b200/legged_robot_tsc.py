@@ -451,3 +451,8 @@ class RecordedPhysicsTSC(PhysicsBackend):
             return
         self.cursor = (self.cursor + 1) % len(self.snapshots)
         self._bind(self.cursor)
+
+
+from .rsl_rl.vec_env import VecEnv  # noqa: E402  (bottom of the module: rsl_rl imports nothing from here)
+
+VecEnv.register(LeggedRobotTSC)

@@ -19,3 +19,16 @@ def test_tsc_cfg_namespaces():
     assert c.domain_rand.action_buf_len == 8 and c.noise.add_noise is False and c.obstacle.curriculum is False
     c.next_goal_threshold = 0.45
     assert c.env.next_goal_threshold == 0.45
+
+
+def test_envs_implement_the_vec_env_interface():
+    """bbc/rsl_rl/env/vec_env.py:7-36, tsc/rsl_rl/env/vec_env.py:6-30."""
+    from qa_b200.legged_robot import LeggedRobot
+    from qa_b200.legged_robot_tsc import LeggedRobotTSC
+    from qa_b200.rsl_rl.vec_env import METHODS, VecEnv, missing_members
+    assert issubclass(LeggedRobot, VecEnv) and issubclass(LeggedRobotTSC, VecEnv)
+    assert all(callable(getattr(LeggedRobot, m)) for m in METHODS + ("get_disc_observations",))
+    assert all(callable(getattr(LeggedRobotTSC, m)) for m in ("step", "get_observations", "get_privileged_observations",
+                                                              "get_observations_bbc", "get_observations_disc", "set_commands"))
+    import types
+    assert "step" in missing_members(types.SimpleNamespace(num_envs=1)) and missing_members(types.SimpleNamespace(), tsc=True)
