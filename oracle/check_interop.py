@@ -115,6 +115,16 @@ def main():
     for ta, tb in zip(a, b):
         assert len(ta) == len(tb) == 11 and ta[9] == tb[9] == (None, None) and ta[10] is None and tb[10] is None
         assert all(torch.equal(x, y) for x, y in zip(ta[:9], tb[:9]))
+    # StateHistoryEncoder for every history length the reference defines (actor_critic.py:9-59: tsteps 10 / 20 / 50)
+    from qa_b200.rsl_rl import StateHistoryEncoder
+    for tsteps in (10, 20, 50):
+        er = ref.actor_critic.StateHistoryEncoder(torch.nn.ELU(), 57, tsteps, 29)
+        eo = StateHistoryEncoder(torch.nn.ELU(), 57, tsteps, 29)
+        assert [(k, tuple(v.shape)) for k, v in er.state_dict().items()] == [(k, tuple(v.shape)) for k, v in eo.state_dict().items()], tsteps
+        eo.load_state_dict(er.state_dict())
+        xh = torch.randn(5, tsteps, 57, generator=gs)
+        with torch.no_grad():
+            assert torch.allclose(er(xh), eo(xh), rtol=1e-6, atol=1e-7), tsteps
     # replay buffer ring (storage/replay_buffer.py:23-42): inserts across the wrap-around
     import importlib
     from qa_b200.rsl_rl.algorithm import ReplayBuffer
