@@ -226,7 +226,7 @@ def run_ours(args):
             line["roofline_gemm"] = gemm_roofline_sample(dev, pk)
         if world == 1 and not args.no_torch_gpu_baseline:
             line["torch_gpu_baseline"] = torch_gpu_baseline_sample(dev)
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line, default=str), flush=True)
     if world > 1:
         # Leave without tearing NCCL down: destroy_process_group() blocks for minutes while CUDA graphs that captured
         # collectives are still alive (seen on 2 x B200: the JSON line was out, the ranks never exited).
@@ -427,7 +427,7 @@ def run_reference(args):
                        "sample": "host cores, bounded sample of the workload per step (see cpu_baseline.sample)"},
             "cpu_baseline": _cpu_line(threads, rs, ms, full, r),
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line, default=str), flush=True)
 
 
 def main():
