@@ -240,6 +240,21 @@ def main_tsc():
     for ta, tb in zip(a, b):
         assert len(ta) == len(tb) == 12 and ta[10] == tb[10] == (None, None) and ta[11] is None and tb[11] is None
         assert all(torch.equal(x, y) for x, y in zip(ta[:10], tb[:10]))
+    # add_transitions: the same Transition fields land in the same buffers
+    sr2, so2 = ref.RolloutStorage(8, 3, [800], [None], [19], device="cpu"), RolloutStorageTSC(8, 3, [800], [None], [19], device="cpu")
+    for step in range(3):
+        fields = dict(observations=torch.randn(8, 800, generator=gs), critic_observations=None, actions=torch.randn(8, 19, generator=gs),
+                      rewards=torch.randn(8, generator=gs), dones=(torch.rand(8, generator=gs) < 0.3), values=torch.randn(8, 1, generator=gs),
+                      actions_log_prob_d=torch.randn(8, generator=gs), actions_log_prob_c=torch.randn(8, generator=gs),
+                      action_mean=torch.randn(8, 18, generator=gs), action_sigma=torch.rand(8, 18, generator=gs))
+        for st_, T_ in ((sr2, ref.RolloutStorage.Transition), (so2, RolloutStorageTSC.Transition)):
+            tr_ = T_()
+            for k_, v_ in fields.items():
+                setattr(tr_, k_, v_)
+            st_.add_transitions(tr_)
+    for name in ("observations", "actions", "rewards", "dones", "values", "actions_log_prob_d", "actions_log_prob_c", "mu", "sigma"):
+        assert torch.equal(getattr(sr2, name).float(), getattr(so2, name).float()), name
+    assert sr2.step == so2.step == 3
     (la, ra), (lb, rb) = sr.get_statistics(), so.get_statistics()
     assert torch.equal(la, lb) and torch.equal(ra, rb)
     # env.set_commands (tsc/legged_gym/envs/base/legged_robot.py:699-760): the reference method and this package's, both
