@@ -115,6 +115,21 @@ def main():
     for ta, tb in zip(a, b):
         assert len(ta) == len(tb) == 11 and ta[9] == tb[9] == (None, None) and ta[10] is None and tb[10] is None
         assert all(torch.equal(x, y) for x, y in zip(ta[:9], tb[:9]))
+    sr2, so2 = ref.RolloutStorage(8, 3, [671], [671], [12], device="cpu"), RolloutStorage(8, 3, [671], [671], [12], device="cpu")
+    for step in range(3):
+        fields = dict(observations=torch.randn(8, 671, generator=gs), critic_observations=torch.randn(8, 671, generator=gs),
+                      actions=torch.randn(8, 12, generator=gs), rewards=torch.randn(8, generator=gs),
+                      dones=(torch.rand(8, generator=gs) < 0.3), values=torch.randn(8, 1, generator=gs),
+                      actions_log_prob=torch.randn(8, generator=gs), action_mean=torch.randn(8, 12, generator=gs),
+                      action_sigma=torch.rand(8, 12, generator=gs))
+        for st_, T_ in ((sr2, ref.RolloutStorage.Transition), (so2, RolloutStorage.Transition)):
+            tr_ = T_(8, [671], [671], [12], "cpu")                   # the BBC fork's Transition pre-allocates (rollout_storage.py:8-22)
+            for k_, v_ in fields.items():
+                setattr(tr_, k_, v_)
+            st_.add_transitions(tr_)
+    for name in ("observations", "privileged_observations", "actions", "rewards", "dones", "values", "actions_log_prob", "mu", "sigma"):
+        assert torch.equal(getattr(sr2, name).float(), getattr(so2, name).float()), name
+    assert sr2.step == so2.step == 3
     # StateHistoryEncoder for every history length the reference defines (actor_critic.py:9-59: tsteps 10 / 20 / 50)
     from qa_b200.rsl_rl import StateHistoryEncoder
     for tsteps in (10, 20, 50):
