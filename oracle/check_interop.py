@@ -8,6 +8,11 @@ statistics, the same adapted learning rate and the same post-step parameters.  I
 
 The same for the TSC fork: `PPO.act` / `PPO.update` (tsc/rsl_rl/algorithms/ppo.py:101-262) over `qa_b200.rsl_rl.ActorCriticTSC`.
 
+Beside the trainer runs, class by class on the same inputs: the rollout storages (Transition / add_transitions, the mini-batch
+generators under one seed, get_statistics), the replay-buffer ring across its wrap-around, `StateHistoryEncoder` for tsteps
+10 / 20 / 50, the fork's `ActorCriticBBC` and `Discriminator` (all three style-reward mappings), and the env's
+`set_commands` against the reference method on injected state -- all bit-equal or within 1e-6.
+
   python oracle/check_interop.py          # bbc
   python oracle/check_interop.py tsc      # tsc (own process: the two forks share package names)
 """
