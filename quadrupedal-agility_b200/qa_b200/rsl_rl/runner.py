@@ -207,6 +207,21 @@ class OnPolicyRunner:
         self.current_learning_iteration = d.get('iter', 0)
         return d.get('infos')
 
+    def log(self, locs, pbar=None):
+        """The reference's entry point (:238-304), fed with its `locals()`-style dict: `it`, `collection_time`, `learn_time` and the
+        `mean_*` statistics (the six PPO means; the eleven discriminator means when present)."""
+        names = ("mean_surrogate_loss", "mean_value_loss", "mean_b_loss", "mean_entropy_batch", "mean_priv_reg_loss",
+                 "mean_estimator_loss", "mean_ss_loss", "mean_info_max_loss", "mean_disc_loss", "mean_us_loss", "mean_grad_pen_loss",
+                 "mean_disc_logit_loss", "mean_disc_weight_decay", "mean_acc_lb", "mean_acc_pi", "mean_acc_exp", "mean_acc_ulb")
+        stats = tuple(locs[k] for k in names if k in locs)
+        if self.writer is None:
+            self.writer = ScalarLog(self.log_dir)
+        if self.book is None:
+            self.book = EpisodeBook(self.env.num_envs, self.num_steps_per_env, ("total", "i", "us", "ss", "t"), self.device,
+                                    num_episode_keys=len(self.env.reward_names))
+        return log_bbc(self, self.writer, locs["it"], stats, locs.get("mean_hist_latent_loss"), locs["collection_time"],
+                       locs["learn_time"])
+
     def get_inference_policy(self, device=None):
         self.alg.actor_critic.eval()
         if device is not None:

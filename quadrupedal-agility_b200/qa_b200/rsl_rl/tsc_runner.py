@@ -340,6 +340,14 @@ class OnPolicyRunnerTSC:
             module.to(device)
         return module
 
+    @staticmethod
+    def s_to_hms(seconds):                                                  # :603-608
+        return seconds // 3600, (seconds % 3600) // 60, seconds % 60
+
+    def get_disc_inference_policy(self, device=None):
+        """The style discriminator in eval mode (the reference's method reads an attribute that does not exist, :699-703)."""
+        return self._eval(self.discriminator, device)
+
     def get_inference_policy(self, device=None):
         return self._eval(self.alg.actor_critic, device).act_inference
 

@@ -111,6 +111,10 @@ def test_learn_loop_books_logs_saves_and_loads_on_host(tmp_path):
     assert set(r2.alg._pending_disc_optim) == {"optim_d", "optim_q_eps", "optim_q_c"}
     r2.learn(1)                                                      # resumes at iteration 3
     assert [s for s, _ in r2.writer.scalars["Perf/total_fps"]] == [3]
+    # the reference's log(locals()) entry point
+    r2.log(dict(it=9, collection_time=0.5, learn_time=0.5, mean_surrogate_loss=1.0, mean_value_loss=2.0, mean_b_loss=0.0,
+                mean_entropy_batch=3.0, mean_priv_reg_loss=4.0, mean_estimator_loss=5.0, mean_hist_latent_loss=6.0))
+    assert r2.writer.scalars["Loss/value_loss"][-1] == (9, 2.0) and r2.writer.scalars["Loss/hist_latent_loss"][-1] == (9, 6.0)
 
 
 def test_runner_builds_the_expert_sets_from_the_shipped_clips_like_the_reference_runner():
