@@ -51,8 +51,13 @@ int qa_version(void);
 /* human readable build string ("sm_100a, nvcc 12.9, ...") */
 const char* qa_build_info(void);
 /* sizeof() of argument struct number `which` (order of declaration in this header, QaActionPushArgs
- * = 0 ... QaGaeArgs = 9, QaGatherArgs = 10, QaClipAdamArgs = 11, QaLinearArgs = 12, QaActBwdArgs = 13, QaPpoLossArgs = 14, QaLinearBwdArgs = 15, QaHistEncArgs = 16, QaRowLossArgs = 17, QaPpoScalarsArgs = 18, QaDepthArgs = 19, QaPpoLossTscArgs = 20, QaTscConst = 21, QaTscStepArgs = 22, QaDiscInputArgs = 23, QaDiscRewardArgs = 24; -1 if unknown): a layout handshake for FFI mirrors of these structs */
+ * = 0 ... QaGaeArgs = 9, QaGatherArgs = 10, QaClipAdamArgs = 11, QaLinearArgs = 12, QaActBwdArgs = 13, QaPpoLossArgs = 14, QaLinearBwdArgs = 15, QaHistEncArgs = 16, QaRowLossArgs = 17, QaPpoScalarsArgs = 18, QaDepthArgs = 19, QaPpoLossTscArgs = 20, QaTscConst = 21, QaTscStepArgs = 22, QaDiscInputArgs = 23, QaDiscRewardArgs = 24, QaHeadFwdArgs = 25, QaHeadBwdArgs = 26; -1 if unknown): a layout handshake for FFI mirrors of these structs */
 int qa_struct_size(int which);
+/* stream-ordered fill-with-zero / device-to-device copy of `bytes` bytes (cudaMemsetAsync / cudaMemcpyAsync): lets a captured
+ * training step zero its flat gradient buffer (optimizer.zero_grad(), gail.py:361, :409) and move device scalars without a
+ * framework kernel in between */
+int qa_zero_async(void* dst, uint64_t bytes, void* stream);
+int qa_copy_async(void* dst, const void* src, uint64_t bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * K0  action history push + delayed-action select + clip
@@ -292,6 +297,10 @@ typedef struct QaBbcStepArgs {
     const float* push_u;                /* (N,2) */
     const int32_t* mocap_clip_idx;      /* (N) */
     const double* mocap_time_u;         /* (N) */
+    /* live skill prior (legged_robot.py:536-538): inclusive CDF of softmax(prior_parameters / T), (QA_DIM_C) floats in
+     * DEVICE memory, re-derived by the host wrapper whenever the trainer moves env.prior_parameters (gail.py:462-464);
+     * read by the Philox-mode mode draw -- also under CUDA-graph replay.  NULL => QaBbcConst.prior_cdf */
+    const float* prior_cdf;
 } QaBbcStepArgs;
 int qa_post_physics_bbc(const QaBbcConst* c, const QaBbcStepArgs* a, void* stream);
 
@@ -340,6 +349,12 @@ typedef struct QaGatherArgs {
     int32_t width[QA_GATHER_MAX_TENSORS];
     int32_t dst_pitch[QA_GATHER_MAX_TENSORS];  /* destination row pitch in floats (0 = width[t]); a pitch that is a multiple
                                                   of 4 floats makes the minibatch a legal TMA operand without a copy */
+    /* column windows (all 0 = whole rows): entry t copies src[t][row, src_col0 : src_col0+width] (rows src_pitch floats
+     * apart, 0 = width) to dst[t][j, dst_col0 : dst_col0+width] -- e.g. the actor's input row [prop 57 | explicit 4 | . 29 . |
+     * command 11] is assembled from two windows of the stored observation row (actor_critic.py:171-187) by the gather */
+    int32_t src_pitch[QA_GATHER_MAX_TENSORS];
+    int32_t src_col0[QA_GATHER_MAX_TENSORS];
+    int32_t dst_col0[QA_GATHER_MAX_TENSORS];
 } QaGatherArgs;
 int qa_gather_minibatch(const QaGatherArgs* a, void* stream);
 
@@ -385,6 +400,10 @@ typedef struct QaLinearArgs {
     const float* bias;                  /* (N) or NULL */
     float* y;                           /* (M,N) */
     int64_t y_pitch;
+    /* column windows inside wider rows (0 = the tensor starts at its base): x[:, x_col0 : x_col0+K] is the input and
+     * y[:, y_col0 : y_col0+N] the output; the bases and pitches, not the windows, carry TMA's 16-byte rule -- e.g. the
+     * privileged-latent lanes 61..89 of the observation row in, the actor-input lanes 61..89 out */
+    int32_t x_col0, y_col0;
 } QaLinearArgs;
 int qa_linear_fwd(const QaLinearArgs* a, void* stream);
 
@@ -403,8 +422,11 @@ typedef struct QaLinearBwdArgs {
      * when act_prev != 0 the dx epilogue writes dx * act'(z_prev) -- i.e. the gradient w.r.t. z_prev -- and, if db_prev is
      * given, its column sums (the previous layer's bias gradient, overwritten) */
     int32_t act_prev;                   /* 0 none, 1 ELU, 2 ReLU */
-    const float* y_prev; int64_t y_prev_pitch;
+    const float* y_prev; int64_t y_prev_pitch;   /* read through TMA: 16 B aligned base, pitch % 4 == 0 */
     float* db_prev;                     /* (K) or NULL */
+    int32_t db_accumulate;              /* 0: db_prev is zeroed first; 1: accumulate (flat gradient buffer zeroed by the caller) */
+    int32_t x_col0;                     /* dw: x[:, x_col0 : x_col0+K] is the layer input */
+    int32_t w_col0;                     /* dx: uses w[:, w_col0 : w_col0+K] (gradient w.r.t. a window of the input row) */
 } QaLinearBwdArgs;
 int qa_linear_bwd(const QaLinearBwdArgs* a, void* stream);
 
@@ -421,8 +443,45 @@ typedef struct QaActBwdArgs {
     float* gz;       int64_t gz_pitch;  /* (M,N) out, may alias gy, may be NULL (bias gradient only) */
     float* db;                          /* (N) out, may be NULL */
     int32_t zero_db;                    /* 1: db is zeroed first, 0: accumulate */
+    /* optional second upstream gradient: gz = (gy + *addend_scale * addend) * act'(y) -- the privileged-latent encoder's output
+     * receives the actor's input gradient AND the regulariser's (gail.py:352-354, coefficient = a device scalar) */
+    const float* addend; int64_t addend_pitch;
+    const float* addend_scale;          /* (1) device scalar, NULL = 1 */
 } QaActBwdArgs;
 int qa_act_bwd(const QaActBwdArgs* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K20 / K21  narrow output layers (N <= 16 columns) on the CUDA cores, full fp32 -- actor_head Linear(128,12) and critic_head
+ *     Linear(128,1) (bbc/rsl_rl/modules/actor_critic.py:118-119, 128-129), the estimator's last Linear(64,4)
+ *     (modules/estimator.py:24-33).  Kh in {32, 64, 128}; h: 16 B aligned base, pitch % 4 == 0.
+ *     qa_head_fwd:  y = h W^T + b
+ *     qa_head_bwd:  gz_prev = ((gz_scale * gz) W) * act'(h)  [act = activation that PRODUCED h: 0 none, 1 ELU, 2 ReLU],
+ *                   dw += (gz_scale * gz)^T h, db += colsum(gz_scale * gz), db_prev += colsum(gz_prev)   (all ACCUMULATED)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct QaHeadFwdArgs {
+    int64_t M;
+    int32_t N, Kh;
+    const float* h; int64_t h_pitch;    /* (M,Kh) */
+    const float* w; int64_t w_pitch;    /* (N,Kh) */
+    const float* bias;                  /* (N) or NULL */
+    float* y; int64_t y_pitch;          /* (M,N) */
+} QaHeadFwdArgs;
+int qa_head_fwd(const QaHeadFwdArgs* a, void* stream);
+
+typedef struct QaHeadBwdArgs {
+    int64_t M;
+    int32_t N, Kh;
+    int32_t act;
+    float gz_scale;
+    const float* gz; int64_t gz_pitch;  /* (M,N) gradient w.r.t. the head's output */
+    const float* h;  int64_t h_pitch;   /* (M,Kh) the head's input = previous layer's output */
+    const float* w;  int64_t w_pitch;   /* (N,Kh) */
+    float* gz_prev;  int64_t gz_prev_pitch;   /* (M,Kh) out, may be NULL */
+    float* dw;       int64_t dw_pitch;  /* (N,Kh) accumulated, may be NULL */
+    float* db;                          /* (N) accumulated, may be NULL */
+    float* db_prev;                     /* (Kh) accumulated, may be NULL */
+} QaHeadBwdArgs;
+int qa_head_bwd(const QaHeadBwdArgs* a, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * K10 PPO loss forward + backward -- replaces the element-wise graph of SSInfoGAIL.update_actor_critic,

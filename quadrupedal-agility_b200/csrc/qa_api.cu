@@ -40,6 +40,20 @@ extern "C" int qa_struct_size(int which) {
         case 22: return (int)sizeof(QaTscStepArgs);
         case 23: return (int)sizeof(QaDiscInputArgs);
         case 24: return (int)sizeof(QaDiscRewardArgs);
+        case 25: return (int)sizeof(QaHeadFwdArgs);
+        case 26: return (int)sizeof(QaHeadBwdArgs);
         default: return -1;
     }
+}
+
+extern "C" int qa_zero_async(void* dst, uint64_t bytes, void* stream) {
+    if (bytes == 0) return 0;
+    if (dst == nullptr) return QA_EINVAL;
+    return (int)cudaMemsetAsync(dst, 0, (size_t)bytes, (cudaStream_t)stream);
+}
+
+extern "C" int qa_copy_async(void* dst, const void* src, uint64_t bytes, void* stream) {
+    if (bytes == 0) return 0;
+    if (dst == nullptr || src == nullptr) return QA_EINVAL;
+    return (int)cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
 }

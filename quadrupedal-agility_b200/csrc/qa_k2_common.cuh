@@ -56,10 +56,11 @@ struct K2Draw {
     float cmd_u[5];
 };
 
-__device__ __forceinline__ int pick_mode(const QaBbcConst& c, float u) {
+// mode ~ Categorical(softmax(prior / T)) by CDF inversion; the CDF is the live device copy when the host supplies one
+__device__ __forceinline__ int pick_mode(const QaBbcConst& c, const float* cdf_dev, float u) {
     int k = 0;
 #pragma unroll
-    for (int i = 0; i < QA_DIM_C - 1; ++i) k += (u >= c.prior_cdf[i]) ? 1 : 0;
+    for (int i = 0; i < QA_DIM_C - 1; ++i) k += (u >= (cdf_dev != nullptr ? __ldcg(cdf_dev + i) : c.prior_cdf[i])) ? 1 : 0;
     return k;
 }
 
@@ -77,7 +78,7 @@ __device__ __forceinline__ K2Draw draw_site(const QaBbcConst& c, const QaBbcStep
         Philox4 r0 = philox4x32_10((uint32_t)e, site0, slo, shi, k0, k1);
         Philox4 r1 = philox4x32_10((uint32_t)e, site0 + 1, slo, shi, k0, k1);
         d.eps_u = u64_to_unit_f64(r0.v[0], r0.v[1]);
-        d.c_idx = pick_mode(c, u32_to_unit_f32(r0.v[2]));
+        d.c_idx = pick_mode(c, a.prior_cdf, u32_to_unit_f32(r0.v[2]));
         d.cmd_u[0] = u32_to_unit_f32(r0.v[3]);
 #pragma unroll
         for (int k = 0; k < 4; ++k) d.cmd_u[k + 1] = u32_to_unit_f32(r1.v[k]);

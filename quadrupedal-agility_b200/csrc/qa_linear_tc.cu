@@ -126,22 +126,29 @@ struct TcProblem {
     const float* yprev;
     long long yprev_pitch;
     float* db;
+    // offsets added to the contiguous-dimension TMA coordinate of each operand: a column window of a wider row-major tensor
+    // (e.g. the 29 privileged-latent lanes at column 61 of the 671-wide observation row) is read / written in place
+    int a_c0, b_c0, out_c0;
 };
 
-template <int BN, int STAGES>
+enum { EPI_STORE = 0, EPI_ATOMIC = 1, EPI_ACTBWD = 2 };
+
+template <int BN, int STAGES, int EPI>
 struct TcSmem {
     float a[STAGES][TC_BM * TC_BK];         // 16 KB per stage, 1024 B aligned
     float b[STAGES][BN * TC_BK];
     float stg[4][2][32 * 32];               // per-epilogue-warp, double-buffered 32 x 32 output slabs (TMA store source)
+    // EPI_ACTBWD: per-epilogue-warp, double-buffered 32 x 32 slabs of the previous layer's OUTPUT, prefetched by TMA one
+    // chunk ahead (the loads do not depend on the accumulator, so their latency hides behind the main loop)
+    float ybuf[EPI == EPI_ACTBWD ? 4 : 1][2][EPI == EPI_ACTBWD ? 32 * 32 : 4];
     float bias_s[4][BN];                    // per-epilogue-warp copy of the tile's bias slice
     uint64_t full[STAGES];
     uint64_t empty[STAGES];
     uint64_t tmem_full[2];
     uint64_t tmem_empty[2];
+    uint64_t ybar[4][2];
     uint32_t tmem_base;
 };
-
-enum { EPI_STORE = 0, EPI_ATOMIC = 1, EPI_ACTBWD = 2 };
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* ssrc, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
@@ -166,10 +173,11 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 template <int BN, int STAGES, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-            const __grid_constant__ CUtensorMap map_y, const __grid_constant__ TcProblem g) {
+            const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_yp,
+            const __grid_constant__ TcProblem g) {
     extern __shared__ unsigned char smem_raw[];
     // 1024 B alignment for the 128 B swizzle atoms
-    using Smem = TcSmem<BN, STAGES>;
+    using Smem = TcSmem<BN, STAGES, EPI>;
     Smem& S = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_m = (g.Mo + TC_BM - 1) / TC_BM, tiles_n = (g.No + BN - 1) / BN;
@@ -187,6 +195,10 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         for (int a = 0; a < 2; ++a) {
             mbar_init(&S.tmem_full[a], 1);
             mbar_init(&S.tmem_empty[a], 4);                          // one arrive per epilogue warp
+        }
+        for (int q = 0; q < 4; ++q) {
+            mbar_init(&S.ybar[q][0], 1);
+            mbar_init(&S.ybar[q][1], 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -230,16 +242,16 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                     if (A_MN) {
 #pragma unroll
                         for (int c = 0; c < TC_BM / 32; ++c)
-                            tma_load_2d(S.a[s] + c * 1024, &map_a, m0 + c * 32, kb * TC_BK, &S.full[s]);
+                            tma_load_2d(S.a[s] + c * 1024, &map_a, g.a_c0 + m0 + c * 32, kb * TC_BK, &S.full[s]);
                     } else {
-                        tma_load_2d(S.a[s], &map_a, kb * TC_BK, m0, &S.full[s]);
+                        tma_load_2d(S.a[s], &map_a, g.a_c0 + kb * TC_BK, m0, &S.full[s]);
                     }
                     if (B_MN) {
 #pragma unroll
                         for (int c = 0; c < BN / 32; ++c)
-                            tma_load_2d(S.b[s] + c * 1024, &map_b, n0 + c * 32, kb * TC_BK, &S.full[s]);
+                            tma_load_2d(S.b[s] + c * 1024, &map_b, g.b_c0 + n0 + c * 32, kb * TC_BK, &S.full[s]);
                     } else {
-                        tma_load_2d(S.b[s], &map_b, kb * TC_BK, n0, &S.full[s]);
+                        tma_load_2d(S.b[s], &map_b, g.b_c0 + kb * TC_BK, n0, &S.full[s]);
                     }
                 }
             }
@@ -282,6 +294,27 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         constexpr int CH = BN >= 32 ? 32 : 16;
         float* bias_s = S.bias_s[q];
         unsigned t = 0, chunk = 0;
+        // EPI_ACTBWD: the previous layer's output slab of chunk i+1 is requested (TMA, same 128 B swizzle as the output slab)
+        // before chunk i is processed; the very first request is issued before the accumulator wait.
+        auto y_request = [&](int w, int c0, unsigned ch) {
+            int m0, n0, kb0, nkb;
+            decode(w, m0, n0, kb0, nkb);
+            uint64_t* bar = &S.ybar[q][ch & 1];
+            mbar_arrive_expect_tx(bar, 32 * 32 * 4);
+            tma_load_2d(S.ybuf[EPI == EPI_ACTBWD ? q : 0][ch & 1], &map_yp, n0 + c0, m0 + q * 32, bar);
+        };
+        auto n_chunks = [&](int w) {                      // chunks of work item w that the epilogue visits
+            int m0, n0, kb0, nkb;
+            decode(w, m0, n0, kb0, nkb);
+            if (nkb <= 0) return 0;
+            const int cols = min(BN, g.No - n0);
+            return (cols + CH - 1) / CH;
+        };
+        if (EPI == EPI_ACTBWD && lane == 0) {
+            int w = blockIdx.x;
+            while (w < total_items && n_chunks(w) == 0) w += gridDim.x;
+            if (w < total_items) y_request(w, 0, 0);
+        }
         for (int w = blockIdx.x; w < total_items; w += gridDim.x) {
             int m0, n0, kb0, nkb;
             decode(w, m0, n0, kb0, nkb);
@@ -294,17 +327,33 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             const unsigned acc = t & 1, aph = (t >> 1) & 1;
             mbar_wait(&S.tmem_full[acc], aph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int nch = n_chunks(w);
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += CH, ++chunk) {
-                if (n0 + c0 >= g.No) break;
+            for (int ci = 0; ci < nch; ++ci, ++chunk) {
+                const int c0 = ci * CH;
                 float* buf = S.stg[q][chunk & 1];
-                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // slab of 2 chunks ago is free
+                const float* ys = S.ybuf[EPI == EPI_ACTBWD ? q : 0][chunk & 1];
+                if (lane == 0) {
+                    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // slab of 2 chunks ago is free
+                    if (EPI == EPI_ACTBWD) {
+                        // request the NEXT chunk's y slab (its buffer was consumed two chunks ago: program order + the
+                        // __syncwarp below each chunk make those reads precede this async write)
+                        if (ci + 1 < nch) {
+                            y_request(w, c0 + CH, chunk + 1);
+                        } else {
+                            int w2 = w + gridDim.x;
+                            while (w2 < total_items && n_chunks(w2) == 0) w2 += gridDim.x;
+                            if (w2 < total_items) y_request(w2, 0, chunk + 1);
+                        }
+                    }
+                }
                 __syncwarp();
                 uint32_t r[32];
                 const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0);
                 if (CH == 32) tmem_ld32(taddr, r);
                 else tmem_ld16(taddr, r);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (EPI == EPI_ACTBWD) mbar_wait(&S.ybar[q][chunk & 1], (chunk >> 1) & 1);
 #pragma unroll
                 for (int j4 = 0; j4 < CH / 4; ++j4) {
                     float v[4];
@@ -318,29 +367,19 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                         }
                         v[e] = x;
                     }
+                    const int sw = lane * 32 + ((j4 ^ (lane & 7)) << 2);                // SWIZZLE_128B position of (row, chunk j4)
                     if (EPI == EPI_ACTBWD) {
                         // gradient w.r.t. the previous layer's pre-activation: multiply by act'(z) recovered from its OUTPUT
-                        const int row = m0 + q * 32 + lane, col = n0 + c0 + j4 * 4;
-                        float yv[4] = {1.f, 1.f, 1.f, 1.f};
-                        if (row < g.Mo) {
-                            const float* yr = g.yprev + (size_t)row * g.yprev_pitch + col;
-                            if (col + 3 < g.No) {
-                                const float4 t4 = *reinterpret_cast<const float4*>(yr);
-                                yv[0] = t4.x, yv[1] = t4.y, yv[2] = t4.z, yv[3] = t4.w;
-                            } else {
-#pragma unroll
-                                for (int e = 0; e < 4; ++e)
-                                    if (col + e < g.No) yv[e] = yr[e];
-                            }
-                        }
+                        // (rows >= Mo / columns >= No of the slab are TMA zero fill; the store clips them anyway)
+                        const float4 t4 = *reinterpret_cast<const float4*>(ys + sw);
+                        const float yv[4] = {t4.x, t4.y, t4.z, t4.w};
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             if (g.act == 1) v[e] = yv[e] > 0.f ? v[e] : v[e] * (yv[e] + 1.0f);      // ELU'
                             else if (g.act == 2) v[e] = yv[e] > 0.f ? v[e] : 0.f;                   // ReLU'
                         }
                     }
-                    // row = lane; 16-byte chunk j4 of the 128-byte row lands at chunk (j4 ^ (row & 7)): SWIZZLE_128B
-                    *reinterpret_cast<float4*>(buf + lane * 32 + ((j4 ^ (lane & 7)) << 2)) = make_float4(v[0], v[1], v[2], v[3]);
+                    *reinterpret_cast<float4*>(buf + sw) = make_float4(v[0], v[1], v[2], v[3]);
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
@@ -353,8 +392,8 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                     if (col < g.No) atomicAdd(g.db + col, sum);
                 }
                 if (lane == 0) {
-                    if (EPI == EPI_ATOMIC) tma_reduce_add_2d(&map_y, buf, n0 + c0, m0 + q * 32);
-                    else tma_store_2d(&map_y, buf, n0 + c0, m0 + q * 32);
+                    if (EPI == EPI_ATOMIC) tma_reduce_add_2d(&map_y, buf, g.out_c0 + n0 + c0, m0 + q * 32);
+                    else tma_store_2d(&map_y, buf, g.out_c0 + n0 + c0, m0 + q * 32);
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
             }
@@ -408,10 +447,12 @@ static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t c
 }
 
 // Operand description for the launcher: a row-major 2-D tensor (rows, cols, pitch).  K-major operand: rows = output index,
-// cols = reduction index.  MN-major operand: rows = reduction index, cols = output index.
+// cols = reduction index.  MN-major operand: rows = reduction index, cols = output index.  `c0` = first column of the window
+// inside a wider row (the TMA map then spans columns [0, c0 + cols) so that reads past the window are zero fill).
 struct TcOperand {
     const float* base;
     int64_t rows, cols, pitch;
+    int c0;
 };
 
 static int num_sms() {
@@ -425,18 +466,25 @@ static int num_sms() {
 }
 
 template <int BN, bool A_MN, bool B_MN, int EPI>
-static int launch_gemm(const TcOperand& A, const TcOperand& B, const TcProblem& prob, int splits, cudaStream_t stream) {
+static int launch_gemm(const TcOperand& A, const TcOperand& B, TcProblem prob, int splits, cudaStream_t stream) {
     // ring depth: as many 128 x 32 + BN x 32 fp32 stages as fit next to the epilogue buffers (<= 8)
     constexpr int STAGES = BN >= 256 ? 3 : (BN >= 128 ? 5 : (BN >= 64 ? 6 : 8));
     CUtensorMap ma, mb;
-    int rc = make_map(&ma, A.base, A.rows, A.cols, A.pitch, A_MN ? 32 : TC_BM, A_MN);
+    int rc = make_map(&ma, A.base, A.rows, A.c0 + A.cols, A.pitch, A_MN ? 32 : TC_BM, A_MN);
     if (rc) return rc;
-    rc = make_map(&mb, B.base, B.rows, B.cols, B.pitch, B_MN ? 32 : BN, B_MN);
+    rc = make_map(&mb, B.base, B.rows, B.c0 + B.cols, B.pitch, B_MN ? 32 : BN, B_MN);
     if (rc) return rc;
-    CUtensorMap my;                                                  // output slabs: 32 rows x 32 columns, 128 B swizzle
-    rc = make_map(&my, prob.out, prob.Mo, prob.No, prob.out_pitch, 32, false, 32);
+    prob.a_c0 = A.c0;
+    prob.b_c0 = B.c0;
+    CUtensorMap my, myp;                                             // output slabs: 32 rows x 32 columns, 128 B swizzle
+    rc = make_map(&my, prob.out, prob.Mo, prob.out_c0 + prob.No, prob.out_pitch, 32, false, 32);
     if (rc) return rc;
-    const size_t smem = sizeof(TcSmem<BN, STAGES>) + 1024;
+    myp = my;
+    if (EPI == EPI_ACTBWD) {
+        rc = make_map(&myp, prob.yprev, prob.Mo, prob.No, prob.yprev_pitch, 32, false, 32);
+        if (rc) return rc;
+    }
+    const size_t smem = sizeof(TcSmem<BN, STAGES, EPI>) + 1024;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(k_gemm_tf32<BN, STAGES, A_MN, B_MN, EPI>,
@@ -446,7 +494,7 @@ static int launch_gemm(const TcOperand& A, const TcOperand& B, const TcProblem& 
     }
     const int items = ((prob.Mo + TC_BM - 1) / TC_BM) * ((prob.No + BN - 1) / BN) * splits;
     const int grid = items < num_sms() ? items : num_sms();
-    k_gemm_tf32<BN, STAGES, A_MN, B_MN, EPI><<<grid, TC_THREADS, smem, stream>>>(ma, mb, my, prob);
+    k_gemm_tf32<BN, STAGES, A_MN, B_MN, EPI><<<grid, TC_THREADS, smem, stream>>>(ma, mb, my, myp, prob);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : (int)e;
 }
@@ -483,6 +531,13 @@ static int dispatch_bn(int bn, const TcOperand& A, const TcOperand& B, const TcP
 
 static bool tma_ok(const void* p, int64_t pitch) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0 && (pitch & 3) == 0; }
 
+static TcProblem make_problem(int Mo, int No, int Kred, int kb_per_split, float* out, int64_t out_pitch, int out_c0) {
+    TcProblem p{};
+    p.Mo = Mo, p.No = No, p.Kred = Kred, p.kb_per_split = kb_per_split;
+    p.out = out, p.out_pitch = out_pitch, p.out_c0 = out_c0;
+    return p;
+}
+
 extern "C" int qa_linear_fwd(const QaLinearArgs* g, void* stream) {
     QA_CHECK_PTR(g);
     if (g->M == 0) return 0;
@@ -490,14 +545,15 @@ extern "C" int qa_linear_fwd(const QaLinearArgs* g, void* stream) {
     QA_CHECK_PTR(g->w);
     QA_CHECK_PTR(g->y);
     if (g->M < 0 || g->N <= 0 || g->K <= 0) return QA_EINVAL;
-    if (g->act < 0 || g->act > 2) return QA_EINVAL;
+    if (g->act < 0 || g->act > 2 || g->x_col0 < 0 || g->y_col0 < 0) return QA_EINVAL;
     // TMA constraints: 16 B aligned bases and row pitches
-    if (!tma_ok(g->x, g->x_pitch) || !tma_ok(g->w, g->w_pitch) || !tma_ok(g->y, g->y_pitch) || g->x_pitch < g->K ||
-        g->w_pitch < g->K || g->y_pitch < g->N)
+    if (!tma_ok(g->x, g->x_pitch) || !tma_ok(g->w, g->w_pitch) || !tma_ok(g->y, g->y_pitch) || g->x_pitch < g->x_col0 + g->K ||
+        g->w_pitch < g->K || g->y_pitch < g->y_col0 + g->N)
         return QA_EINVAL;
     cudaStream_t s = (cudaStream_t)stream;
-    const TcOperand A{g->x, g->M, g->K, g->x_pitch}, B{g->w, g->N, g->K, g->w_pitch};
-    TcProblem p{g->M, g->N, g->K, (g->K + TC_BK - 1) / TC_BK, g->y, g->y_pitch, g->bias, g->act, nullptr, 0, nullptr};
+    const TcOperand A{g->x, g->M, g->K, g->x_pitch, g->x_col0}, B{g->w, g->N, g->K, g->w_pitch, 0};
+    TcProblem p = make_problem(g->M, g->N, g->K, (g->K + TC_BK - 1) / TC_BK, g->y, g->y_pitch, g->y_col0);
+    p.bias = g->bias, p.act = g->act;
     return dispatch_bn<false, false, EPI_STORE>(pick_bn(g->M, g->N, 1, false), A, B, p, 1, s);
 }
 
@@ -507,37 +563,38 @@ extern "C" int qa_linear_bwd(const QaLinearBwdArgs* g, void* stream) {
     QA_CHECK_PTR(g);
     if (g->M == 0) return 0;
     QA_CHECK_PTR(g->gz);
-    if (g->M < 0 || g->N <= 0 || g->K <= 0) return QA_EINVAL;
+    if (g->M < 0 || g->N <= 0 || g->K <= 0 || g->x_col0 < 0 || g->w_col0 < 0) return QA_EINVAL;
     if (!tma_ok(g->gz, g->gz_pitch) || g->gz_pitch < g->N) return QA_EINVAL;
     cudaStream_t s = (cudaStream_t)stream;
     int rc = 0;
     if (g->dx != nullptr) {
+        // dx (M, K) = gz (M, N) W[:, w_col0 : w_col0 + K]
         QA_CHECK_PTR(g->w);
-        if (!tma_ok(g->w, g->w_pitch) || !tma_ok(g->dx, g->dx_pitch) || g->w_pitch < g->K || g->dx_pitch < g->K) return QA_EINVAL;
-        const TcOperand A{g->gz, g->M, g->N, g->gz_pitch}, B{g->w, g->N, g->K, g->w_pitch};
+        if (!tma_ok(g->w, g->w_pitch) || !tma_ok(g->dx, g->dx_pitch) || g->w_pitch < g->w_col0 + g->K || g->dx_pitch < g->K)
+            return QA_EINVAL;
+        const TcOperand A{g->gz, g->M, g->N, g->gz_pitch, 0}, B{g->w, g->N, g->K, g->w_pitch, g->w_col0};
+        TcProblem p = make_problem(g->M, g->K, g->N, (g->N + TC_BK - 1) / TC_BK, g->dx, g->dx_pitch, 0);
         if (g->act_prev != 0) {
-            // fused with the previous layer's activation backward (+ its bias gradient)
+            // fused with the previous layer's activation backward (+ its bias gradient); y_prev is read through TMA
             QA_CHECK_PTR(g->y_prev);
-            if (g->act_prev < 0 || g->act_prev > 2 || g->y_prev_pitch < g->K || (g->y_prev_pitch & 3) ||
-                (reinterpret_cast<uintptr_t>(g->y_prev) & 15u))
-                return QA_EINVAL;
-            if (g->db_prev != nullptr) {
+            if (g->act_prev < 0 || g->act_prev > 2 || g->y_prev_pitch < g->K || !tma_ok(g->y_prev, g->y_prev_pitch)) return QA_EINVAL;
+            if (g->db_prev != nullptr && !g->db_accumulate) {
                 cudaError_t e = cudaMemsetAsync(g->db_prev, 0, sizeof(float) * g->K, s);
                 if (e != cudaSuccess) return (int)e;
             }
-            TcProblem p{g->M, g->K, g->N, (g->N + TC_BK - 1) / TC_BK, g->dx, g->dx_pitch, nullptr, g->act_prev,
-                        g->y_prev, g->y_prev_pitch, g->db_prev};
+            p.act = g->act_prev, p.yprev = g->y_prev, p.yprev_pitch = g->y_prev_pitch, p.db = g->db_prev;
             rc = dispatch_bn<false, true, EPI_ACTBWD>(pick_bn(g->M, g->K, 1, true), A, B, p, 1, s);
         } else {
-            TcProblem p{g->M, g->K, g->N, (g->N + TC_BK - 1) / TC_BK, g->dx, g->dx_pitch, nullptr, 0, nullptr, 0, nullptr};
             rc = dispatch_bn<false, true, EPI_STORE>(pick_bn(g->M, g->K, 1, true), A, B, p, 1, s);
         }
         if (rc) return rc;
     }
     if (g->dw != nullptr) {
+        // dw (N, K) += gz^T x[:, x_col0 : x_col0 + K]
         QA_CHECK_PTR(g->x);
-        if (!tma_ok(g->x, g->x_pitch) || !tma_ok(g->dw, g->dw_pitch) || g->x_pitch < g->K || g->dw_pitch < g->K) return QA_EINVAL;
-        const TcOperand A{g->gz, g->M, g->N, g->gz_pitch}, B{g->x, g->M, g->K, g->x_pitch};
+        if (!tma_ok(g->x, g->x_pitch) || !tma_ok(g->dw, g->dw_pitch) || g->x_pitch < g->x_col0 + g->K || g->dw_pitch < g->K)
+            return QA_EINVAL;
+        const TcOperand A{g->gz, g->M, g->N, g->gz_pitch, 0}, B{g->x, g->M, g->K, g->x_pitch, g->x_col0};
         const int total_kb = (g->M + TC_BK - 1) / TC_BK;
         const int bn = g->K <= 32 ? 32 : (g->K <= 64 ? 64 : 128);
         const int tiles = ((g->N + TC_BM - 1) / TC_BM) * ((g->K + bn - 1) / bn);
@@ -546,7 +603,7 @@ extern "C" int qa_linear_bwd(const QaLinearBwdArgs* g, void* stream) {
         if (splits < 1) splits = 1;
         const int per = (total_kb + splits - 1) / splits;
         splits = (total_kb + per - 1) / per;
-        TcProblem p{g->N, g->K, g->M, per, g->dw, g->dw_pitch, nullptr, 0, nullptr, 0, nullptr};
+        TcProblem p = make_problem(g->N, g->K, g->M, per, g->dw, g->dw_pitch, 0);
         rc = dispatch_bn<true, true, EPI_ATOMIC>(bn, A, B, p, splits, s);
     }
     return rc;

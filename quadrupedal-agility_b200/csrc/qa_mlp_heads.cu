@@ -1,0 +1,173 @@
+// K20 / K21: the narrow output layers of the actor, the critic and the estimator on the CUDA cores, full fp32.
+//
+//   actor_head    Linear(128 -> 12)   bbc/rsl_rl/modules/actor_critic.py:118-119
+//   critic_head   Linear(128 -> 1)    bbc/rsl_rl/modules/actor_critic.py:128-129
+//   estimator.4   Linear(64 -> 4)     bbc/rsl_rl/modules/estimator.py:24-33
+//
+// These layers have 1..16 output columns: a tensor-core tile would be >= 87 % padding and the layer is a pure stream over
+// the (M, 128) hidden activation -- HBM bound at 4 B/flop.  They therefore do not go through K7; they run as row-streaming
+// kernels that also absorb their neighbours:
+//   K20 qa_head_fwd   y = h W^T + b
+//   K21 qa_head_bwd   gz_prev = (gz W) * act'(h)   (the gradient w.r.t. the PREVIOUS layer's pre-activation, ELU'/ReLU'
+//                     recovered from its output h), dW += gz^T h, db += colsum(gz), db_prev += colsum(gz_prev)
+//                     -- what autograd does in 5 kernels (mm, mm, sum, elu_backward, sum) in ONE pass over h.
+// Lane = 4 consecutive hidden columns (float4); a row of 128 columns is one warp-wide 512 B access, a row of 64 columns half
+// a warp (two rows per pass).  W sits in shared memory as [n][Kh].
+#include "qa_b200.h"
+#include "qa_common.cuh"
+
+#define HD_THREADS 256
+#define HD_MAXN 16
+#define HD_MAXK 128
+
+template <int NT>
+__global__ void __launch_bounds__(HD_THREADS) k_head_fwd(const __grid_constant__ QaHeadFwdArgs a) {
+    __shared__ __align__(16) float s_w[NT * HD_MAXK];
+    __shared__ float s_b[NT];
+    const int Kh = a.Kh, N = a.N;
+    for (int i = threadIdx.x; i < NT * Kh; i += HD_THREADS) {
+        const int n = i / Kh, k = i - n * Kh;
+        s_w[i] = n < N ? __ldg(a.w + (size_t)n * a.w_pitch + k) : 0.f;
+    }
+    if (threadIdx.x < NT) s_b[threadIdx.x] = (threadIdx.x < N && a.bias != nullptr) ? __ldg(a.bias + threadIdx.x) : 0.f;
+    __syncthreads();
+    const int lpr = Kh >> 2;                       // lanes per row: 32 (Kh = 128), 16 (64), 8 (32)
+    const int rpp = 32 / lpr;                      // rows per warp pass
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane % lpr, rsel = lane / lpr;
+    const long long warps_total = (long long)gridDim.x * (HD_THREADS / 32);
+    for (long long r0 = ((long long)blockIdx.x * (HD_THREADS / 32) + warp) * rpp; r0 < a.M; r0 += warps_total * rpp) {
+        const long long r = r0 + rsel;
+        float4 h4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < a.M) h4 = *reinterpret_cast<const float4*>(a.h + r * a.h_pitch + sub * 4);
+        float p[NT];
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+            const float4 w4 = *reinterpret_cast<const float4*>(s_w + n * Kh + sub * 4);
+            p[n] = h4.x * w4.x + h4.y * w4.y + h4.z * w4.z + h4.w * w4.w;
+        }
+#pragma unroll
+        for (int n = 0; n < NT; ++n)
+            for (int o = lpr >> 1; o > 0; o >>= 1) p[n] += __shfl_xor_sync(QA_FULL, p[n], o);
+        if (r < a.M) {
+#pragma unroll
+            for (int n = 0; n < NT; ++n)
+                if (n < N && (n % lpr) == sub) a.y[r * a.y_pitch + n] = p[n] + s_b[n];
+        }
+    }
+}
+
+extern "C" int qa_head_fwd(const QaHeadFwdArgs* a, void* stream) {
+    QA_CHECK_PTR(a);
+    if (a->M == 0) return 0;
+    QA_CHECK_PTR(a->h);
+    QA_CHECK_PTR(a->w);
+    QA_CHECK_PTR(a->y);
+    if (a->M < 0 || a->N <= 0 || a->N > HD_MAXN) return QA_EINVAL;
+    if (a->Kh != 32 && a->Kh != 64 && a->Kh != 128) return QA_EINVAL;
+    if ((reinterpret_cast<uintptr_t>(a->h) & 15u) || (a->h_pitch & 3) || a->h_pitch < a->Kh || a->w_pitch < a->Kh || a->y_pitch < a->N)
+        return QA_EINVAL;
+    const int rpp = 32 / (a->Kh >> 2);
+    long long blocks = (a->M + 8LL * rpp - 1) / (8LL * rpp);
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (a->N == 1) k_head_fwd<1><<<(unsigned)blocks, HD_THREADS, 0, s>>>(*a);
+    else if (a->N <= 4) k_head_fwd<4><<<(unsigned)blocks, HD_THREADS, 0, s>>>(*a);
+    else k_head_fwd<16><<<(unsigned)blocks, HD_THREADS, 0, s>>>(*a);
+    QA_LAUNCH_RET();
+}
+
+// Backward.  Every lane keeps dW[n][4 columns] partial sums over the rows it visits; the block folds them in shared memory
+// (shared atomics) and leaves with one global atomicAdd per element.
+template <int NT>
+__global__ void __launch_bounds__(HD_THREADS) k_head_bwd(const __grid_constant__ QaHeadBwdArgs a) {
+    __shared__ __align__(16) float s_w[NT * HD_MAXK];
+    __shared__ __align__(16) float s_dw[NT * HD_MAXK];
+    __shared__ float s_dbp[HD_MAXK];
+    __shared__ float s_db[NT];
+    const int Kh = a.Kh, N = a.N;
+    for (int i = threadIdx.x; i < NT * Kh; i += HD_THREADS) {
+        const int n = i / Kh, k = i - n * Kh;
+        s_w[i] = n < N ? __ldg(a.w + (size_t)n * a.w_pitch + k) : 0.f;
+        s_dw[i] = 0.f;
+    }
+    if (threadIdx.x < Kh) s_dbp[threadIdx.x] = 0.f;
+    if (threadIdx.x < NT) s_db[threadIdx.x] = 0.f;
+    __syncthreads();
+    const int lpr = Kh >> 2, rpp = 32 / lpr;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane % lpr, rsel = lane / lpr;
+    const long long warps_total = (long long)gridDim.x * (HD_THREADS / 32);
+    float4 dw[NT];
+    float dbn[NT];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) dw[n] = make_float4(0.f, 0.f, 0.f, 0.f), dbn[n] = 0.f;
+    float4 dbp = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long long r0 = ((long long)blockIdx.x * (HD_THREADS / 32) + warp) * rpp; r0 < a.M; r0 += warps_total * rpp) {
+        const long long r = r0 + rsel;
+        if (r >= a.M) continue;
+        const float4 h4 = *reinterpret_cast<const float4*>(a.h + r * a.h_pitch + sub * 4);
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+            if (n < N) {
+                const float g = __ldg(a.gz + r * a.gz_pitch + n) * a.gz_scale;     // same address across the row's lanes: broadcast
+                const float4 w4 = *reinterpret_cast<const float4*>(s_w + n * Kh + sub * 4);
+                o.x += g * w4.x, o.y += g * w4.y, o.z += g * w4.z, o.w += g * w4.w;
+                dw[n].x += g * h4.x, dw[n].y += g * h4.y, dw[n].z += g * h4.z, dw[n].w += g * h4.w;
+                dbn[n] += g;
+            }
+        }
+        if (a.act == 1) {                                                          // ELU'(z) from the output: 1 if h > 0 else h + 1
+            o.x = h4.x > 0.f ? o.x : o.x * (h4.x + 1.0f), o.y = h4.y > 0.f ? o.y : o.y * (h4.y + 1.0f);
+            o.z = h4.z > 0.f ? o.z : o.z * (h4.z + 1.0f), o.w = h4.w > 0.f ? o.w : o.w * (h4.w + 1.0f);
+        } else if (a.act == 2) {
+            o.x = h4.x > 0.f ? o.x : 0.f, o.y = h4.y > 0.f ? o.y : 0.f, o.z = h4.z > 0.f ? o.z : 0.f, o.w = h4.w > 0.f ? o.w : 0.f;
+        }
+        if (a.gz_prev != nullptr) *reinterpret_cast<float4*>(a.gz_prev + r * a.gz_prev_pitch + sub * 4) = o;
+        dbp.x += o.x, dbp.y += o.y, dbp.z += o.z, dbp.w += o.w;
+    }
+    // fold: lanes that share the columns (the rpp row groups of a warp, the 8 warps) meet in shared memory
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+        if (n < N) {
+            float* d = s_dw + n * Kh + sub * 4;
+            atomicAdd(d + 0, dw[n].x), atomicAdd(d + 1, dw[n].y), atomicAdd(d + 2, dw[n].z), atomicAdd(d + 3, dw[n].w);
+            if (sub == 0) atomicAdd(s_db + n, dbn[n]);
+        }
+    }
+    atomicAdd(s_dbp + sub * 4 + 0, dbp.x), atomicAdd(s_dbp + sub * 4 + 1, dbp.y);
+    atomicAdd(s_dbp + sub * 4 + 2, dbp.z), atomicAdd(s_dbp + sub * 4 + 3, dbp.w);
+    __syncthreads();
+    if (a.dw != nullptr)
+        for (int i = threadIdx.x; i < N * Kh; i += HD_THREADS) {
+            const int n = i / Kh, k = i - n * Kh;
+            atomicAdd(a.dw + (size_t)n * a.dw_pitch + k, s_dw[i]);
+        }
+    if (a.db != nullptr && threadIdx.x < N) atomicAdd(a.db + threadIdx.x, s_db[threadIdx.x]);
+    if (a.db_prev != nullptr && threadIdx.x < Kh) atomicAdd(a.db_prev + threadIdx.x, s_dbp[threadIdx.x]);
+}
+
+extern "C" int qa_head_bwd(const QaHeadBwdArgs* a, void* stream) {
+    QA_CHECK_PTR(a);
+    if (a->M == 0) return 0;
+    QA_CHECK_PTR(a->gz);
+    QA_CHECK_PTR(a->h);
+    QA_CHECK_PTR(a->w);
+    if (a->M < 0 || a->N <= 0 || a->N > HD_MAXN || a->act < 0 || a->act > 2) return QA_EINVAL;
+    if (a->Kh != 32 && a->Kh != 64 && a->Kh != 128) return QA_EINVAL;
+    if ((reinterpret_cast<uintptr_t>(a->h) & 15u) || (a->h_pitch & 3) || a->h_pitch < a->Kh || a->w_pitch < a->Kh || a->gz_pitch < a->N)
+        return QA_EINVAL;
+    if (a->gz_prev != nullptr && ((reinterpret_cast<uintptr_t>(a->gz_prev) & 15u) || (a->gz_prev_pitch & 3) || a->gz_prev_pitch < a->Kh))
+        return QA_EINVAL;
+    if (a->dw != nullptr && a->dw_pitch < a->Kh) return QA_EINVAL;
+    const int rpp = 32 / (a->Kh >> 2);
+    long long blocks = (a->M + 8LL * rpp * 4 - 1) / (8LL * rpp * 4);        // >= 4 passes per warp: the fold is amortised
+    if (blocks > 148 * 2) blocks = 148 * 2;
+    if (blocks < 1) blocks = 1;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (a->N == 1) k_head_bwd<1><<<(unsigned)blocks, HD_THREADS, 0, s>>>(*a);
+    else if (a->N <= 4) k_head_bwd<4><<<(unsigned)blocks, HD_THREADS, 0, s>>>(*a);
+    else k_head_bwd<16><<<(unsigned)blocks, HD_THREADS, 0, s>>>(*a);
+    QA_LAUNCH_RET();
+}

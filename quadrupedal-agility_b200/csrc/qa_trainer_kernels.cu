@@ -19,8 +19,8 @@ __global__ void __launch_bounds__(256) k_gather_minibatch(const __grid_constant_
 #pragma unroll 1
         for (int t = 0; t < g.num_tensors; ++t) {
             const int w = g.width[t];
-            const float* s = g.src[t] + src_row * w;
-            float* d = g.dst[t] + j * (g.dst_pitch[t] > 0 ? g.dst_pitch[t] : w);
+            const float* s = g.src[t] + src_row * (g.src_pitch[t] > 0 ? g.src_pitch[t] : w) + g.src_col0[t];
+            float* d = g.dst[t] + j * (g.dst_pitch[t] > 0 ? g.dst_pitch[t] : w) + g.dst_col0[t];
             int c = lane;
             // 4 independent loads in flight per lane
             for (; c + 96 < w; c += 128) {
@@ -45,7 +45,10 @@ extern "C" int qa_gather_minibatch(const QaGatherArgs* g, void* stream) {
         QA_CHECK_PTR(g->src[t]);
         QA_CHECK_PTR(g->dst[t]);
         if (g->width[t] <= 0) return QA_EINVAL;
-        if (g->dst_pitch[t] != 0 && g->dst_pitch[t] < g->width[t]) return QA_EINVAL;
+        if (g->src_col0[t] < 0 || g->dst_col0[t] < 0) return QA_EINVAL;
+        if (g->dst_pitch[t] != 0 && g->dst_pitch[t] < g->dst_col0[t] + g->width[t]) return QA_EINVAL;
+        if (g->src_pitch[t] != 0 && g->src_pitch[t] < g->src_col0[t] + g->width[t]) return QA_EINVAL;
+        if ((g->dst_pitch[t] == 0 && g->dst_col0[t] != 0) || (g->src_pitch[t] == 0 && g->src_col0[t] != 0)) return QA_EINVAL;
     }
     long long blocks = (g->num_rows + 7) / 8;
     if (blocks > 148 * 16) blocks = 148 * 16;
@@ -173,9 +176,11 @@ __global__ void __launch_bounds__(256) k_act_bwd(QaActBwdArgs a) {
     const long long r0 = (long long)blockIdx.y * AB_ROWS;
     const long long r1 = min((long long)a.M, r0 + AB_ROWS);
     float acc = 0.f;
+    const float addend_scale = (a.addend != nullptr && a.addend_scale != nullptr) ? __ldg(a.addend_scale) : 1.f;
     if (col < a.N) {
         for (long long r = r0 + w; r < r1; r += 8) {
             float g = a.gy[r * a.gy_pitch + col];
+            if (a.addend != nullptr) g = g + addend_scale * a.addend[r * a.addend_pitch + col];
             if (a.act != 0) {
                 const float y = a.y[r * a.y_pitch + col];
                 if (a.act == 1) g = y > 0.f ? g : g * (y + 1.0f);

@@ -94,7 +94,7 @@ class QaBbcStepArgs(C.Structure):
         ("episode_rew_means", vp), ("time_outs_latched", vp), ("num_resets", vp), ("workspace", vp),
         ("step_state", vp), ("push_interval", C.c_int32),
         ("noise_u", vp), ("rs_eps_u", vp), ("rs_c_idx", vp), ("rs_cmd_u", vp), ("rt_eps_u", vp),
-        ("rt_c_idx", vp), ("rt_cmd_u", vp), ("push_u", vp), ("mocap_clip_idx", vp), ("mocap_time_u", vp),
+        ("rt_c_idx", vp), ("rt_cmd_u", vp), ("push_u", vp), ("mocap_clip_idx", vp), ("mocap_time_u", vp), ("prior_cdf", vp),
     ]
 
 
@@ -114,7 +114,8 @@ GATHER_MAX = 12
 
 class QaGatherArgs(C.Structure):
     _fields_ = [("num_rows", C.c_int64), ("num_tensors", C.c_int32), ("indices", vp), ("src", vp * GATHER_MAX),
-                ("dst", vp * GATHER_MAX), ("width", C.c_int32 * GATHER_MAX), ("dst_pitch", C.c_int32 * GATHER_MAX)]
+                ("dst", vp * GATHER_MAX), ("width", C.c_int32 * GATHER_MAX), ("dst_pitch", C.c_int32 * GATHER_MAX),
+                ("src_pitch", C.c_int32 * GATHER_MAX), ("src_col0", C.c_int32 * GATHER_MAX), ("dst_col0", C.c_int32 * GATHER_MAX)]
 
 
 class QaClipAdamArgs(C.Structure):
@@ -127,13 +128,25 @@ class QaClipAdamArgs(C.Structure):
 class QaLinearArgs(C.Structure):
     _fields_ = [("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("act", C.c_int32), ("x", vp),
                 ("x_pitch", C.c_int64), ("w", vp), ("w_pitch", C.c_int64), ("bias", vp), ("y", vp),
-                ("y_pitch", C.c_int64)]
+                ("y_pitch", C.c_int64), ("x_col0", C.c_int32), ("y_col0", C.c_int32)]
 
 
 class QaActBwdArgs(C.Structure):
     _fields_ = [("M", C.c_int64), ("N", C.c_int32), ("act", C.c_int32), ("gy", vp), ("gy_pitch", C.c_int64),
                 ("y", vp), ("y_pitch", C.c_int64), ("gz", vp), ("gz_pitch", C.c_int64), ("db", vp),
-                ("zero_db", C.c_int32)]
+                ("zero_db", C.c_int32), ("addend", vp), ("addend_pitch", C.c_int64), ("addend_scale", vp)]
+
+
+class QaHeadFwdArgs(C.Structure):
+    _fields_ = [("M", C.c_int64), ("N", C.c_int32), ("Kh", C.c_int32), ("h", vp), ("h_pitch", C.c_int64), ("w", vp),
+                ("w_pitch", C.c_int64), ("bias", vp), ("y", vp), ("y_pitch", C.c_int64)]
+
+
+class QaHeadBwdArgs(C.Structure):
+    _fields_ = [("M", C.c_int64), ("N", C.c_int32), ("Kh", C.c_int32), ("act", C.c_int32), ("gz_scale", C.c_float),
+                ("gz", vp), ("gz_pitch", C.c_int64), ("h", vp), ("h_pitch", C.c_int64), ("w", vp), ("w_pitch", C.c_int64),
+                ("gz_prev", vp), ("gz_prev_pitch", C.c_int64), ("dw", vp), ("dw_pitch", C.c_int64), ("db", vp),
+                ("db_prev", vp)]
 
 
 class QaPpoLossArgs(C.Structure):
@@ -148,7 +161,7 @@ class QaLinearBwdArgs(C.Structure):
     _fields_ = [("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("gz", vp), ("gz_pitch", C.c_int64), ("x", vp),
                 ("x_pitch", C.c_int64), ("w", vp), ("w_pitch", C.c_int64), ("dx", vp), ("dx_pitch", C.c_int64),
                 ("dw", vp), ("dw_pitch", C.c_int64), ("act_prev", C.c_int32), ("y_prev", vp), ("y_prev_pitch", C.c_int64),
-                ("db_prev", vp)]
+                ("db_prev", vp), ("db_accumulate", C.c_int32), ("x_col0", C.c_int32), ("w_col0", C.c_int32)]
 
 
 class QaHistEncArgs(C.Structure):
@@ -268,12 +281,16 @@ SYMBOLS = {
     "qa_post_physics_tsc_post": (C.c_int, [C.POINTER(QaTscConst), C.POINTER(QaTscStepArgs), vp]),
     "qa_disc_input": (C.c_int, [C.POINTER(QaDiscInputArgs), vp]),
     "qa_disc_reward": (C.c_int, [C.POINTER(QaDiscRewardArgs), vp]),
+    "qa_zero_async": (C.c_int, [vp, C.c_uint64, vp]),
+    "qa_copy_async": (C.c_int, [vp, vp, C.c_uint64, vp]),
+    "qa_head_fwd": (C.c_int, [C.POINTER(QaHeadFwdArgs), vp]),
+    "qa_head_bwd": (C.c_int, [C.POINTER(QaHeadBwdArgs), vp]),
 }
 
 STRUCT_ORDER = [QaActionPushArgs, QaTorqueArgs, QaTerrain, QaHeightScanArgs, QaMocapTable, QaMocapBlendArgs,
                 QaBbcConst, QaBbcStepArgs, QaCompactArgs, QaGaeArgs, QaGatherArgs, QaClipAdamArgs, QaLinearArgs, QaActBwdArgs, QaPpoLossArgs, QaLinearBwdArgs, QaHistEncArgs,
                 QaRowLossArgs, QaPpoScalarsArgs, QaDepthArgs, QaPpoLossTscArgs, QaTscConst, QaTscStepArgs,
-                QaDiscInputArgs, QaDiscRewardArgs]
+                QaDiscInputArgs, QaDiscRewardArgs, QaHeadFwdArgs, QaHeadBwdArgs]
 
 _LIB = None
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libqa_b200.so")

@@ -126,6 +126,7 @@ class LeggedRobot:
         self.noise_scale_vec = to(static["noise_scale_vec"])
         self.prior_parameters = to(static["prior_parameters"])
         self.prior_prob = self.prior_parameters.clone()
+        self._prior_cdf = torch.zeros(K.DIM_C, device=dev, dtype=torch.float32)   # live CDF the fused step samples modes from
         self.mocap = mocap.to(dev)
 
         z = lambda *s: torch.zeros(*s, **f32)                                  # noqa: E731
@@ -172,6 +173,7 @@ class LeggedRobot:
         self._measured_heights = z(N, cfg.num_height_points)
 
         self._const = ops.bbc_const(cfg, self.prior_parameters.tolist())
+        self.refresh_prior()
         # kernel variant request; the library falls back to the warp-per-env kernel when a tile constraint fails
         self._flags = (_abi.QA_K2_BULK_STORE if (bulk_store and N % 4 == 0) else 0) | (_abi.QA_K2_TILED if tiled else 0)
         self._draws = None
@@ -276,6 +278,7 @@ class LeggedRobot:
         a.num_resets = p(self._num_resets, i32)
         a.workspace = p(self._workspace, f64)
         a.push_interval = int(cfg.push_interval) if cfg.push_robots else 0
+        a.prior_cdf = p(self._prior_cdf, f)
         return a
 
     def set_parity_draws(self, draws: Optional[Dict[str, torch.Tensor]]) -> None:
@@ -326,10 +329,20 @@ class LeggedRobot:
         if self._ring_len:
             self._ring_head = (self.common_step_counter - 1) % self._ring_len
 
+    def refresh_prior(self) -> None:
+        """`_resample_latent_c` re-derives `prior_prob = softmax(prior_parameters / T)` on every call (:536-538).  Here the
+        mode draw happens inside the fused step, which reads the inclusive CDF from a device tensor at a fixed address:
+        three tiny torch kernels, no host sync, visible to captured graphs.  The trainer calls this after every
+        discriminator update (the only writer of `prior_parameters`, gail.py:462-464)."""
+        with torch.no_grad():
+            prob = torch.softmax(self.prior_parameters.to(torch.float32) / self.cfg.latent_c_temperature, dim=-1)
+            self.prior_prob.copy_(prob)
+            torch.cumsum(prob, dim=0, out=self._prior_cdf)
+
     def set_prior_parameters(self, prior: torch.Tensor) -> None:
-        """The trainer updates `env.prior_parameters` (gail.py:463-464); refresh the in-kernel CDF."""
-        self.prior_parameters = prior.to(self.device)
-        self._const = ops.bbc_const(self.cfg, self.prior_parameters.tolist())
+        """Overwrite `env.prior_parameters` IN PLACE (the trainer and captured graphs hold the tensor) and refresh the CDF."""
+        self.prior_parameters.copy_(prior.to(self.device))
+        self.refresh_prior()
 
     # ---- VecEnv API ---------------------------------------------------------------------------------
     def get_observations(self):

@@ -53,6 +53,21 @@ def _bytep(t, name):
     return _p(t, None, name)
 
 
+def zero_(t: torch.Tensor) -> None:
+    """Stream-ordered memset of a contiguous CUDA tensor (a memset node under graph capture, not a kernel)."""
+    lib = _abi.load()
+    _abi.check(lib.qa_zero_async(_p(t, None, "tensor"), t.numel() * t.element_size(), _stream()), "qa_zero_async")
+
+
+def copy_(dst: torch.Tensor, src: torch.Tensor) -> None:
+    """Stream-ordered device-to-device copy between contiguous CUDA tensors of equal byte size."""
+    lib = _abi.load()
+    n = dst.numel() * dst.element_size()
+    if n != src.numel() * src.element_size():
+        raise RuntimeError("qa_copy_async: size mismatch")
+    _abi.check(lib.qa_copy_async(_p(dst, None, "dst"), _p(src, None, "src"), n, _stream()), "qa_copy_async")
+
+
 # ---- K0 ---------------------------------------------------------------------------------------
 def action_push(actions_in, action_history_buf, actions_out, delay: int, clip: float) -> None:
     """LeggedRobot.step front half, legged_robot.py:84-98 (history shifted IN PLACE)."""
@@ -152,6 +167,25 @@ def gae(rewards, values, dones, last_values, returns, advantages, workspace, gam
 
 
 # ---- K6 ---------------------------------------------------------------------------------------
+def gather_minibatch_windows(indices, entries) -> None:
+    """One launch of K6 over `entries` = [(src, src_col0, dst, dst_col0, width)]: dst[j, dst_col0:+width] =
+    src[indices[j], src_col0:+width].  `src` / `dst` are 2-D fp32 with unit column stride (any row pitch)."""
+    lib = _abi.load()
+    a = _abi.QaGatherArgs()
+    a.num_rows, a.num_tensors = indices.shape[0], len(entries)
+    if len(entries) > _abi.GATHER_MAX:
+        raise RuntimeError("qa_gather_minibatch: too many tensors")
+    a.indices = _p(indices, torch.int64, "indices")
+    for t, (s, sc, d, dc, w) in enumerate(entries):
+        if d.shape[0] != indices.shape[0] or sc + w > s.shape[1] or dc + w > d.shape[1]:
+            raise RuntimeError("qa_gather_minibatch: window outside the tensor")
+        a.src[t], a.dst[t] = _p_strided(s, torch.float32, "src"), _p_strided(d, torch.float32, "dst")
+        a.src_pitch[t], a.dst_pitch[t] = int(s.stride(0)), int(d.stride(0))
+        a.src_col0[t], a.dst_col0[t], a.width[t] = int(sc), int(dc), int(w)
+    _abi.check(lib.qa_gather_minibatch(C.byref(a), _stream()), "qa_gather_minibatch")
+    _count(1)
+
+
 def gather_minibatch(indices, srcs, dsts) -> None:
     """dst[t][j] = src[t][indices[j]] for every (src, dst) pair (2-D float32, same width), one launch.
     Replaces the per-tensor advanced indexing of mini_batch_generator, rollout_storage.py:147-155."""
@@ -202,26 +236,35 @@ def linear_tc_ok(x, weight) -> bool:
             x.data_ptr() % 16 == 0 and weight.data_ptr() % 16 == 0 and x.shape[0] > 0)
 
 
-def linear_fwd(x, weight, bias, y, act) -> None:
-    """y = act(x @ weight.T + bias) on the tcgen05 tensor cores (TF32 operands, fp32 accumulate)."""
+def linear_fwd(x, weight, bias, y, act, x_col0: int = 0, y_col0: int = 0) -> None:
+    """y[:, y_col0:y_col0+N] = act(x[:, x_col0:x_col0+K] @ weight.T + bias) on the tcgen05 tensor cores (TF32 operands, fp32
+    accumulate).  With a column offset, `x` / `y` are the WIDE row-major tensors (16-byte aligned base and pitch) and K / N come
+    from `weight`."""
     lib = _abi.load()
-    M, K = x.shape
-    N = weight.shape[0]
+    M = x.shape[0]
+    N, K = weight.shape
     if y.stride(1) != 1 or y.dtype != torch.float32 or not y.is_cuda:
         raise RuntimeError("qa_linear_fwd: bad output tensor")
+    if x.shape[1] < x_col0 + K or y.shape[1] < y_col0 + N:
+        raise RuntimeError("qa_linear_fwd: column window outside the tensor")
     a = _abi.QaLinearArgs(M, N, K, ACT_ID[act], x.data_ptr(), x.stride(0), weight.data_ptr(), weight.stride(0),
-                          None if bias is None else _p(bias, torch.float32, "bias"), y.data_ptr(), y.stride(0))
+                          None if bias is None else _p(bias, torch.float32, "bias"), y.data_ptr(), y.stride(0),
+                          int(x_col0), int(y_col0))
     _abi.check(lib.qa_linear_fwd(C.byref(a), _stream()), "qa_linear_fwd")
     _count(1)
 
 
-def linear_bwd(gz, x, weight, dx=None, dw=None, act_prev=None, y_prev=None, db_prev=None) -> None:
-    """dx = gz @ weight (overwritten) and/or dw += gz.T @ x (accumulated) on the tcgen05 kernel, MN-major operands.
-    With `act_prev` the dx epilogue also applies the previous layer's activation derivative (from its output `y_prev`)
-    and reduces that layer's bias gradient into `db_prev`."""
+def linear_bwd(gz, x, weight, dx=None, dw=None, act_prev=None, y_prev=None, db_prev=None, db_accumulate=False,
+               x_col0: int = 0, w_col0: int = 0, K: int = None) -> None:
+    """dx = gz @ weight[:, w_col0:w_col0+K] (overwritten) and/or dw += gz.T @ x[:, x_col0:x_col0+K] (accumulated) on the tcgen05
+    kernel, MN-major operands.  With `act_prev` the dx epilogue also applies the previous layer's activation derivative (from
+    its output `y_prev`) and reduces that layer's bias gradient into `db_prev` (zeroed first unless `db_accumulate`).
+    `K` defaults to the width of `dx` / `dw` / `weight` / `x`, in that order."""
     lib = _abi.load()
     M, N = gz.shape
-    K = weight.shape[1] if weight is not None else x.shape[1]
+    if K is None:
+        K = (dx.shape[1] if dx is not None else dw.shape[1] if dw is not None else
+             weight.shape[1] if weight is not None else x.shape[1])
     a = _abi.QaLinearBwdArgs(M, N, K, gz.data_ptr(), gz.stride(0),
                              None if x is None else x.data_ptr(), 0 if x is None else x.stride(0),
                              None if weight is None else weight.data_ptr(), 0 if weight is None else weight.stride(0),
@@ -229,7 +272,8 @@ def linear_bwd(gz, x, weight, dx=None, dw=None, act_prev=None, y_prev=None, db_p
                              None if dw is None else dw.data_ptr(), 0 if dw is None else dw.stride(0),
                              ACT_ID[act_prev], None if y_prev is None else y_prev.data_ptr(),
                              0 if y_prev is None else y_prev.stride(0),
-                             None if db_prev is None else _p(db_prev, torch.float32, "db_prev"))
+                             None if db_prev is None else _p(db_prev, torch.float32, "db_prev"), int(bool(db_accumulate)),
+                             int(x_col0), int(w_col0))
     _abi.check(lib.qa_linear_bwd(C.byref(a), _stream()), "qa_linear_bwd")
     _count((dx is not None) + (dw is not None))
 
@@ -258,18 +302,51 @@ def hist_encoder_fwd(hist, enc, out) -> None:
 
 
 # ---- K9 ---------------------------------------------------------------------------------------
-def act_bwd(gy, y, act, gz=None, db=None, zero_db=True) -> None:
-    """gz = gy * act'(y) (ELU' from the saved output: 1 if y > 0 else y + 1) and/or db = gz.sum(0)."""
+def act_bwd(gy, y, act, gz=None, db=None, zero_db=True, addend=None, addend_scale=None) -> None:
+    """gz = (gy [+ addend_scale * addend]) * act'(y) (ELU' from the saved output: 1 if y > 0 else y + 1) and/or db = gz.sum(0);
+    `addend_scale` is a 1-element device tensor."""
     lib = _abi.load()
     M, N = gy.shape
-    for t in (gy, y, gz):
+    for t in (gy, y, gz, addend):
         if t is not None and (t.stride(1) != 1 or t.dtype != torch.float32 or not t.is_cuda):
             raise RuntimeError("qa_act_bwd: operands must be fp32 CUDA with unit inner stride")
     a = _abi.QaActBwdArgs(M, N, ACT_ID[act], gy.data_ptr(), gy.stride(0), None if y is None else y.data_ptr(),
                           0 if y is None else y.stride(0), None if gz is None else gz.data_ptr(),
                           0 if gz is None else gz.stride(0), None if db is None else _p(db, torch.float32, "db"),
-                          int(zero_db))
+                          int(zero_db), None if addend is None else addend.data_ptr(),
+                          0 if addend is None else addend.stride(0),
+                          None if addend_scale is None else _p(addend_scale.reshape(1), torch.float32, "addend_scale"))
     _abi.check(lib.qa_act_bwd(C.byref(a), _stream()), "qa_act_bwd")
+    _count(1)
+
+
+# ---- K20 / K21 ----------------------------------------------------------------------------------
+def head_fwd(h, weight, bias, y) -> None:
+    """y = h @ weight.T + bias for a narrow output layer (N <= 16, Kh in {32, 64, 128}), CUDA cores, full fp32."""
+    lib = _abi.load()
+    f = torch.float32
+    N, Kh = weight.shape
+    a = _abi.QaHeadFwdArgs(h.shape[0], N, Kh, _p_strided(h, f, "h"), h.stride(0), _p_strided(weight, f, "weight"),
+                           weight.stride(0), None if bias is None else _p(bias, f, "bias"), _p_strided(y, f, "y"), y.stride(0))
+    _abi.check(lib.qa_head_fwd(C.byref(a), _stream()), "qa_head_fwd")
+    _count(1)
+
+
+def head_bwd(gz, h, weight, act, gz_prev=None, dw=None, db=None, db_prev=None, gz_scale: float = 1.0) -> None:
+    """Backward of a narrow output layer in one pass over its input `h` (see include/qa_b200.h K21); dw / db / db_prev are
+    ACCUMULATED.  `gz` may be (M,) for a single output column."""
+    lib = _abi.load()
+    f = torch.float32
+    N, Kh = weight.shape
+    if gz.dim() == 1:
+        gz = gz.unsqueeze(1)
+    a = _abi.QaHeadBwdArgs(h.shape[0], N, Kh, ACT_ID[act], float(gz_scale), _p_strided(gz, f, "gz"), gz.stride(0),
+                           _p_strided(h, f, "h"), h.stride(0), _p_strided(weight, f, "weight"), weight.stride(0),
+                           None if gz_prev is None else _p_strided(gz_prev, f, "gz_prev"),
+                           0 if gz_prev is None else gz_prev.stride(0),
+                           None if dw is None else _p_strided(dw, f, "dw"), 0 if dw is None else dw.stride(0),
+                           None if db is None else _p(db, f, "db"), None if db_prev is None else _p(db_prev, f, "db_prev"))
+    _abi.check(lib.qa_head_bwd(C.byref(a), _stream()), "qa_head_bwd")
     _count(1)
 
 

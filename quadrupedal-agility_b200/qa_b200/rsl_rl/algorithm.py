@@ -207,6 +207,10 @@ class SSInfoGAIL:
         self.disc_batched = os.environ.get("QA_DISC_BATCHED", "0") == "1"
         # PPO minibatch step with ONE privileged-latent encoder pass (see _forward_backward); opt-in for the same reason
         self.share_priv_latent = os.environ.get("QA_SHARE_PRIV_LATENT", "0") == "1"
+        # the PPO minibatch step as a static schedule of libqa_b200 launches (ppo_plan.PpoStepPlan) instead of an autograd graph:
+        # the default on CUDA with the tcgen05 layers; QA_PPO_PLAN=0 (or linear mode "fp32", the cuBLAS parity mode) keeps autograd
+        self.use_plan = os.environ.get("QA_PPO_PLAN", "1") == "1"
+        self._plan = None
         torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)   # capture runs on a side stream
         self._ppo_stats = torch.zeros(4, device=device)
         self._aux_loss = torch.zeros(2, device=device)            # priv_reg_loss, estimator_loss of the current minibatch
@@ -486,8 +490,11 @@ class SSInfoGAIL:
         L, W = self.disc_obs_len, self.num_disc_obs
         x = x.view(len(x), L, -1).clone()
         if self.env.task_obs_weight_decay:
-            x[:, :, 3:9] *= self.env.task_obs_weight
-            x[:, :, 33:] *= self.env.task_obs_weight
+            # the weight decays every iteration (on_policy_runner.py:224-225): it is read from a DEVICE scalar so that a
+            # captured discriminator step sees the current value (a Python float would be frozen into the graph)
+            w = self._task_obs_weight_dev()
+            x[:, :, 3:9] *= w
+            x[:, :, 33:] *= w
         x = x[:, -L:, :].reshape(len(x), -1)
         if self.obs_disc_weight_step != 0.0:
             x = x * (torch.arange(L, dtype=torch.float32, device=x.device) * self.obs_disc_weight_step + 1).repeat_interleave(W)
@@ -495,6 +502,17 @@ class SSInfoGAIL:
             with torch.no_grad():
                 x = self.disc_normalizer.normalize_torch(x, x.device)
         return x
+
+    def _task_obs_weight_dev(self, refresh: bool = None) -> torch.Tensor:
+        """env.task_obs_weight as a 0-d device tensor at a fixed address.  Refreshed from the env on every call outside a
+        CUDA-graph capture (`update_disc` refreshes it before replaying), never during one."""
+        t = getattr(self, "_tow", None)
+        if t is None:
+            t = self._tow = torch.ones((), device=self.device)
+        capturing = torch.device(self.device).type == "cuda" and torch.cuda.is_current_stream_capturing()
+        if refresh or (refresh is None and not capturing):
+            t.fill_(float(self.env.task_obs_weight))
+        return t
 
     def update_ss_info_gail(self, sample_disc_policy, sample_disc_expert_lb, sample_disc_expert_ulb):
         """One discriminator minibatch step with the reference's signature and 11-tuple (device tensors, no host sync).
@@ -595,6 +613,7 @@ class SSInfoGAIL:
         if self.learning_steps >= self.begin_rim:                               # :251-253
             self.info_max_coef_on = min(self.info_max_coef * (self.learning_steps - self.begin_rim) / 10000, self.info_max_coef)
         self._info_max_coef_on.fill_(self.info_max_coef_on)
+        self._task_obs_weight_dev(refresh=True)
         dev = self.device
         i_pi = torch.randint(ds.num_samples, (n_mb, mb), device=dev)
         i_lb = torch.randint(expert.preloaded_s_lb.shape[0], (n_mb, mb), device=dev)
@@ -618,6 +637,8 @@ class SSInfoGAIL:
                 self._disc_step(expert, i_pi[k], i_lb[k], i_ulb[k])
         if self.world_size > 1:                                                 # logged statistics: mean over the ranks
             qdist.allreduce_mean_scalar_(self._disc_stats)
+        if hasattr(self.env, "refresh_prior"):                                  # the steps above moved env.prior_parameters
+            self.env.refresh_prior()                                            # (:462-464): next rollout samples from it
         return tuple((self._disc_stats / n_mb).tolist())
 
     def _disc_step(self, expert, i_pi, i_lb, i_ulb):
@@ -672,6 +693,18 @@ class SSInfoGAIL:
             if self._grad_arena is None:
                 self._kl = torch.zeros((), device=self.device)
             self._graphs = None
+        sch = self.priv_reg_coef_schedual
+        stage = min(max((self.priv_reg_counter - sch[2]), 0) / sch[3], 1)
+        plan = self._ensure_plan(n)
+        if plan is not None:                                   # static schedule, eager (no graph for a one-off sample)
+            plan.load(0, sample)
+            p, e, l, h = self.num_prop, self.num_explicit, self.num_latent, self.num_hist * self.num_prop
+            with torch.no_grad():
+                plan.sets[0]["hist_latent"].copy_(self.actor_critic.infer_hist_latent(plan.sets[0]["obs"][:, p + e + l:p + e + l + h]))
+            self._priv_reg_coef.fill_(stage * (sch[1] - sch[0]) + sch[0])
+            before = self._stats.clone()
+            plan.step(0)
+            return tuple((self._stats - before)[:6])
         mb = self._mb
         for k, v in (("obs", obs), ("critic_obs", critic_obs), ("actions", actions), ("values", target_values),
                      ("advantages", advantages), ("returns", returns), ("old_actions_log_prob", old_logp), ("old_mu", old_mu),
@@ -702,6 +735,19 @@ class SSInfoGAIL:
         # history-encoder latents of the whole rollout: the encoder is frozen during update() (it is trained by
         # update_dagger), so its output per sample is computed once per update instead of once per epoch
         self._hist_latent_all = torch.zeros(st.num_transitions_per_env * st.num_envs, self.num_latent, device=dev)
+
+    def _ensure_plan(self, mb_size):
+        """The static-schedule step (ppo_plan) when it applies to this configuration, else None (autograd path)."""
+        from . import linear
+        from .ppo_plan import PpoStepPlan
+        if not self.use_plan or linear.get_mode() != "tc" or PpoStepPlan.supported(self) is not None:
+            if self._plan is not None:
+                self._plan, self._graphs = None, None
+            return None
+        if self._plan is None or self._plan.M != mb_size:
+            self._plan = PpoStepPlan(self, mb_size, self.num_mini_batches)
+            self._graphs = None
+        return self._plan
 
     def _gather(self, idx):
         v = self.storage.flat_views()
@@ -815,25 +861,28 @@ class SSInfoGAIL:
         snap = [t.clone() for t in (self.ac_flat.data, self.est_flat.data, self.optim_ac.exp_avg, self.optim_ac.exp_avg_sq,
                                     self.optim_estimator.exp_avg, self.optim_estimator.exp_avg_sq, self.optim_ac.lr,
                                     self.optim_ac.step_count, self.optim_estimator.step_count, self._stats)]
+        plan = self._plan
+        sets = range(plan.num_sets) if plan is not None else (None,)
+        fb = (lambda k: plan.forward_backward(k)) if plan is not None else (lambda k: self._forward_backward())
         with torch.cuda.stream(s):
             for _ in range(3):
-                self._minibatch_step()
+                fb(sets[0])
+                self._apply()
         torch.cuda.current_stream().wait_stream(s)
-        before = ops.launches
-        self._graph_has_apply = True
-        if self.world_size == 1 or self.capture_collectives:
-            # single graph; with > 1 rank the NCCL all-reduces of the flat gradients are captured as graph nodes
+        self._graph_has_apply = self.world_size == 1 or self.capture_collectives
+        graphs = []
+        for k in sets:                                  # one graph per minibatch buffer set (the plan) or the single autograd one
+            before = ops.launches
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self._minibatch_step()
-            self._graphs = (g,)
-        else:
-            g1 = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g1):
-                self._forward_backward()
-            self._graphs = (g1,)
-            self._graph_has_apply = False
-        self._graph_launches = ops.launches - before         # libqa_b200 kernels inside one replay
+                # with > 1 rank the NCCL all-reduce of the flat gradients is captured as a graph node, unless
+                # QA_CAPTURE_COLLECTIVES=0: then the graph ends after the backward pass and _apply() runs eagerly
+                fb(k)
+                if self._graph_has_apply:
+                    self._apply()
+            graphs.append(g)
+            self._graph_launches = ops.launches - before     # libqa_b200 kernels inside one replay
+        self._graphs = tuple(graphs)
         # undo the warm-up / capture side effects on the trainable state
         for t, v in zip((self.ac_flat.data, self.est_flat.data, self.optim_ac.exp_avg, self.optim_ac.exp_avg_sq,
                          self.optim_estimator.exp_avg, self.optim_estimator.exp_avg_sq, self.optim_ac.lr,
@@ -861,20 +910,39 @@ class SSInfoGAIL:
         if indices is None:
             indices = torch.randperm(self.num_mini_batches * mb_size, device=self.device)
         self._encode_history()
-        if self.use_cuda_graph and self._graphs is None:
-            self._gather(indices[:mb_size])
-            self._capture()
-        self._stats.zero_()
-        for _ in range(self.num_learning_epochs):
+        plan = self._ensure_plan(mb_size)
+        if plan is not None:
+            # every minibatch is gathered ONCE per update: the generator re-uses the same slices of one permutation in every
+            # epoch (rollout_storage.py:125, 140-145) and the storage does not change during the update
             for i in range(self.num_mini_batches):
-                self._gather(indices[i * mb_size:(i + 1) * mb_size])
-                if self.use_cuda_graph:
-                    self._graphs[0].replay()
-                    ops._count(self._graph_launches)
-                    if not self._graph_has_apply:
-                        self._apply()
-                else:
-                    self._minibatch_step()
+                plan.gather(i, indices[i * mb_size:(i + 1) * mb_size], self._hist_latent_all)
+            if self.use_cuda_graph and self._graphs is None:
+                self._capture()
+            self._stats.zero_()
+            for _ in range(self.num_learning_epochs):
+                for i in range(self.num_mini_batches):
+                    if self.use_cuda_graph:
+                        self._graphs[i].replay()
+                        ops._count(self._graph_launches)
+                        if not self._graph_has_apply:
+                            self._apply()
+                    else:
+                        plan.step(i)
+        else:
+            if self.use_cuda_graph and self._graphs is None:
+                self._gather(indices[:mb_size])
+                self._capture()
+            self._stats.zero_()
+            for _ in range(self.num_learning_epochs):
+                for i in range(self.num_mini_batches):
+                    self._gather(indices[i * mb_size:(i + 1) * mb_size])
+                    if self.use_cuda_graph:
+                        self._graphs[0].replay()
+                        ops._count(self._graph_launches)
+                        if not self._graph_has_apply:
+                            self._apply()
+                    else:
+                        self._minibatch_step()
         n = self.num_learning_epochs * self.num_mini_batches
         vals = (self._stats / n).tolist()                      # the one host sync of the update
         self.last_stats = dict(zip(STAT_NAMES, vals))

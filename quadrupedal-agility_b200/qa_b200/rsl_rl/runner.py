@@ -105,7 +105,7 @@ class OnPolicyRunner:
             slot = book.term_slot()
             slot[:, 1:].copy_(self._terms4)
             slot[:, 0].copy_(self._terms4 @ self._reward_coefs)
-            book.record(dones, episode_means=env._episode_rew_means)
+            book.record(dones, episode_means=env._episode_rew_means, num_resets=getattr(env, '_num_resets', None))
         self._disc_hist = dst
         return next_obs, next_priv
 
@@ -126,7 +126,7 @@ class OnPolicyRunner:
         infos = {"time_outs": env._time_outs_latched} if env.cfg.send_timeouts else {}
         alg.process_env_step(rew, dones, infos, hist)
         if self.book is not None:
-            self.book.record(dones, torch.stack([rew.float(), r_i, r_us, r_ss.float(), r_t], dim=1), env._episode_rew_means)
+            self.book.record(dones, torch.stack([rew.float(), r_i, r_us, r_ss.float(), r_t], dim=1), env._episode_rew_means, getattr(env, '_num_resets', None))
         # fresh episodes restart their discriminator history (:180-181)
         self._disc_hist = torch.where(done_col.unsqueeze(2), next_disc.unsqueeze(1).expand(-1, self.disc_obs_len, -1), hist)
         return next_obs, next_priv
@@ -197,9 +197,11 @@ class OnPolicyRunner:
         self.alg.disc.load_state_dict(d['disc'])
         n = d['disc_normalizer']
         if n is not None:
-            mine = Normalizer(n.mean.shape[0], epsilon=n.epsilon, clip_obs=n.clip_obs)
-            mine.mean, mine.var, mine.count = n.mean, n.var, n.count
-            self.alg.disc_normalizer = mine
+            mine = self.alg.disc_normalizer
+            if mine is None or mine.mean.shape != n.mean.shape:
+                mine = self.alg.disc_normalizer = Normalizer(n.mean.shape[0], epsilon=n.epsilon, clip_obs=n.clip_obs)
+            mine.load_moments(n.mean, n.var, n.count, epsilon=n.epsilon, clip_obs=n.clip_obs)
+            self.alg._disc_graph_key = None            # a captured discriminator step is re-captured on the next update
         if d.get('reward_i_normalizer'):
             self.alg.disc.reward_i_normalizer = d['reward_i_normalizer']
         if load_optimizer:

@@ -70,6 +70,11 @@ class RolloutStorage:
 
     def compute_returns(self, last_values, gamma, lam):
         """GAE + advantage normalisation (rollout_storage.py:97-111) through libqa_b200 (K5)."""
+        if not self.rewards.is_cuda:
+            # host construction (OnPolicyRunner's default device is 'cpu', as in the reference) is for plumbing and tests
+            # only: the product path is the CUDA kernel and says so instead of failing deep inside ops.gae
+            raise RuntimeError("RolloutStorage.compute_returns: qa_b200 computes GAE on the GPU only (K5, libqa_b200); "
+                               "construct the runner / storage with a CUDA device")
         ops.gae(self.rewards, self.values, self.dones, last_values.contiguous(), self.returns, self.advantages,
                 self._gae_ws, gamma, lam)
 

@@ -28,6 +28,10 @@ class EpisodeBook:
         self.terms = torch.zeros(num_steps, num_envs, C, device=device)
         self.dones = torch.zeros(num_steps, num_envs, device=device, dtype=torch.uint8)
         self.ep_means = torch.zeros(num_steps, max(num_episode_keys, 1), device=device)
+        # infos['episode'] only exists once some env has been reset (legged_robot.py:188-189, 230-234), so the reference appends
+        # nothing before that (on_policy_runner.py:185-186): per-step validity flag, latched on the device
+        self.ep_valid = torch.zeros(num_steps, device=device)
+        self._ever_reset = torch.zeros((), device=device)
         self.buffers = {n: deque(maxlen=maxlen) for n in self.names + self.snap_names}
         self.len_buffer = deque(maxlen=maxlen)
         self._cur = np.zeros((num_envs, C), dtype=np.float32)          # cur_reward_* (:141-146), fp32 like the reference
@@ -37,14 +41,16 @@ class EpisodeBook:
         self._h_terms = torch.zeros(num_steps, num_envs, C, pin_memory=pin)
         self._h_dones = torch.zeros(num_steps, num_envs, dtype=torch.uint8, pin_memory=pin)
         self._h_ep = torch.zeros(num_steps, max(num_episode_keys, 1), pin_memory=pin)
+        self._h_valid = torch.zeros(num_steps, pin_memory=pin)
         self.episode_rows = []                                          # ep_infos of the current iteration (one row per step)
 
     def term_slot(self, t=None):
         """(N, C) view a kernel may write the step's reward terms into directly."""
         return self.terms[self._t if t is None else t]
 
-    def record(self, dones, terms=None, episode_means=None):
-        """One env step: `terms` (N, C) or None when already written through `term_slot()`."""
+    def record(self, dones, terms=None, episode_means=None, num_resets=None):
+        """One env step: `terms` (N, C) or None when already written through `term_slot()`.  `num_resets`: the env's device
+        count of resets in this step (any dtype); without it the step's `dones` decide whether an episode info exists yet."""
         t = self._t
         if terms is not None:
             self.terms[t].copy_(terms)
@@ -52,6 +58,9 @@ class EpisodeBook:
         if episode_means is not None:
             k = min(self.ep_means.shape[1], episode_means.numel())
             self.ep_means[t, :k].copy_(episode_means.reshape(-1)[:k])
+            any_reset = (num_resets.reshape(-1)[0] > 0) if num_resets is not None else dones.any()
+            torch.maximum(self._ever_reset, any_reset.to(self._ever_reset.dtype), out=self._ever_reset)
+            self.ep_valid[t].copy_(self._ever_reset)
         self._t = t + 1
 
     def flush(self):
@@ -62,10 +71,11 @@ class EpisodeBook:
         self._h_terms[:n].copy_(self.terms[:n], non_blocking=True)
         self._h_dones[:n].copy_(self.dones[:n], non_blocking=True)
         self._h_ep[:n].copy_(self.ep_means[:n], non_blocking=True)
+        self._h_valid[:n].copy_(self.ep_valid[:n], non_blocking=True)
         if self.terms.is_cuda:
             torch.cuda.current_stream().synchronize()
         terms, dones = self._h_terms[:n].numpy(), self._h_dones[:n].numpy()
-        self.episode_rows = [self._h_ep[i].numpy().copy() for i in range(n)]
+        self.episode_rows = [self._h_ep[i].numpy().copy() for i in range(n) if self._h_valid[i] > 0]
         k = self.n_sum
         for t in range(n):
             self._cur[:, :k] += terms[t][:, :k]

@@ -112,9 +112,12 @@ class OnPolicyRunnerTSC:
             self.discriminator.load_state_dict(d["disc"])
         n = d.get("disc_normalizer")
         if n is not None:
-            mine = Normalizer(n.mean.shape[0], epsilon=n.epsilon, clip_obs=n.clip_obs)
-            mine.mean, mine.var, mine.count = n.mean, n.var, n.count
-            self.disc_normalizer = mine
+            mine = self.disc_normalizer                 # in place: the discriminator (and anything captured) holds this object
+            if mine is None or mine.mean.shape != n.mean.shape:
+                mine = self.disc_normalizer = Normalizer(n.mean.shape[0], epsilon=n.epsilon, clip_obs=n.clip_obs)
+                if hasattr(self.discriminator, "normalizer"):
+                    self.discriminator.normalizer = mine
+            mine.load_moments(n.mean, n.var, n.count, epsilon=n.epsilon, clip_obs=n.clip_obs)
         if d.get("reward_i_normalizer"):
             self.discriminator.reward_i_normalizer = d["reward_i_normalizer"]
         self.actor_critic_bbc.eval()
@@ -178,7 +181,7 @@ class OnPolicyRunnerTSC:
             slot = self.book.term_slot()
             slot[:, 0].copy_(self._rew)
             slot[:, 1].copy_(infos["reach_goal"])
-            self.book.record(dones, episode_means=env._episode_rew_means)
+            self.book.record(dones, episode_means=env._episode_rew_means, num_resets=getattr(env, '_num_resets', None))
         self._disc_hist = dst
         return obs, next_obs_bbc.clone(), critic_obs, infos
 
@@ -302,7 +305,7 @@ class OnPolicyRunnerTSC:
                     slot = self.book.term_slot()
                     slot[:, 0].copy_(rewards)
                     slot[:, 1].copy_(infos["reach_goal"])
-                    self.book.record(dones, episode_means=env._episode_rew_means)
+                    self.book.record(dones, episode_means=env._episode_rew_means, num_resets=getattr(env, '_num_resets', None))
             torch.cuda.synchronize() if torch.device(self.device).type == "cuda" else None
             stop = time.time()
             collection_time, start = stop - start, stop

@@ -97,6 +97,29 @@ class Normalizer(RunningMeanStd):
         std32.copy_(torch.sqrt((var + self.epsilon).float()))
         self.__dict__["_dev_dirty"] = True
 
+    def load_moments(self, mean, var, count, epsilon=None, clip_obs=None) -> None:
+        """Overwrite the running moments IN PLACE: the host arrays and, when they exist, the device tensors that captured
+        CUDA graphs and K18 read (their addresses do not change)."""
+        self.mean = np.array(mean, dtype=np.float64).reshape(self.mean.shape)
+        self.var = np.array(var, dtype=np.float64).reshape(self.var.shape)
+        self.count = float(count)
+        if epsilon is not None:
+            self.epsilon = epsilon
+        if clip_obs is not None:
+            self.clip_obs = clip_obs
+        cache, st = self.__dict__.get("_dev_cache"), self.__dict__.get("_dev_state")
+        if st is not None:
+            dev = st[1].device
+            st[1].copy_(torch.tensor(self.mean, dtype=torch.float64, device=dev))
+            st[2].copy_(torch.tensor(self.var, dtype=torch.float64, device=dev))
+            st[3].fill_(self.count)
+            st[4].copy_(st[1].float())
+            st[5].copy_(torch.sqrt((st[2] + self.epsilon).float()))
+            self.__dict__["_dev_dirty"] = False
+        elif cache is not None:
+            cache[1].copy_(torch.tensor(self.mean, dtype=torch.float32, device=cache[1].device))
+            cache[2].copy_(torch.sqrt(torch.tensor(self.var + self.epsilon, dtype=torch.float32, device=cache[2].device)))
+
     def sync_host(self) -> None:
         st = self.__dict__.get("_dev_state")
         if st is not None and self.__dict__.get("_dev_dirty"):

@@ -1,0 +1,327 @@
+"""GPU parity of the path `bench.py` times: the PPO minibatch step as a static schedule of libqa_b200 launches
+(`qa_b200.rsl_rl.ppo_plan.PpoStepPlan`: tcgen05 TF32 GEMMs with column windows + fused activation backward, fp32 head kernels,
+fused losses) inside a CUDA graph -- against the CPU oracle (`oracle/trainer.py`, pinned on the reference's
+`update_actor_critic`, bbc/rsl_rl/algorithms/gail.py:328-413) and the reference golden.
+
+Tolerance of the tensor-core layers, derived: `tcgen05.mma.kind::tf32` reads fp32 operands with a 10-bit mantissa (the low 13
+bits are dropped), so each operand carries a relative error <= 2^-10 and each product <= 2^-9 (first order); a dot product
+sum_k x_k w_k is therefore within 2^-9 * sum_k |x_k||w_k| of the exact one, accumulation is fp32.  Tests of a single layer
+assert exactly that bound (`scaled error` = |y - ref| / (|x| @ |w|^T + |b|) <= 2e-3 ~ 2^-9).  Through a depth-4 trunk of
+1-Lipschitz activations the bound compounds to <= 4 * 2^-9 ~ 8e-3 relative to the layer-wise absolute-value products; the loss
+statistics are means over the minibatch of smooth functions of the outputs, asserted at rtol 1e-2 (observed ~1e-3).  Everything that
+is NOT a tensor-core contraction (head layers, losses, gathers, Adam) is full fp32 and held to the fp32 bars of the other tests."""
+import numpy as np
+import pytest
+import torch
+
+import trainer as OT
+from helpers import GOLD, assert_close
+from qa_b200 import ops, synthetic
+from qa_b200.rsl_rl import linear
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TF32_BOUND = 2e-3          # 2^-9 = 1.95e-3, see the module docstring
+TC_STAT_RTOL = 1e-2
+
+
+@pytest.fixture()
+def tc_mode():
+    prev = linear.get_mode()
+    linear.set_mode("tc")
+    tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    linear.set_mode(prev)
+    torch.backends.cuda.matmul.allow_tf32 = tf32
+
+
+def _padded(rows, cols, fill=None, gen=None):
+    t = torch.zeros(rows, (cols + 3) // 4 * 4, device=DEV)
+    if gen is not None:
+        t.copy_(torch.randn(t.shape, generator=gen))
+    if fill is not None:
+        t.fill_(fill)
+    return t[:, :cols]
+
+
+def _scaled_err(y, ref, x, w, b=None):
+    scale = x.double().abs() @ w.double().abs().t()
+    if b is not None:
+        scale = scale + b.double().abs()
+    return float(((y.double() - ref) .abs() / scale.clamp(min=1e-6)).max())
+
+
+# ---- K20 / K21 ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,Kh,act", [(24576, 12, 128, "elu"), (4096, 1, 128, "elu"), (3001, 4, 64, "elu"), (515, 16, 32, "relu"),
+                                        (7, 5, 128, None)])
+def test_head_fwd_bwd_match_torch(M, N, Kh, act):
+    g = torch.Generator().manual_seed(M + N)
+    h = _padded(M, Kh, gen=g)
+    if act == "relu":
+        h = h.clamp_(min=0)
+    w = (torch.randn(N, Kh, generator=g) / Kh ** 0.5).to(DEV)
+    b = torch.randn(N, generator=g).to(DEV)
+    y = _padded(M, N)
+    ops.head_fwd(h, w, b, y)
+    ref = h.double() @ w.double().t() + b.double()
+    assert_close("head_fwd", y, ref.float(), rtol=1e-5, atol=1e-5)
+    gz = torch.randn(M, N, generator=g).to(DEV)
+    gz_prev = _padded(M, Kh)
+    dw, db, dbp = torch.ones(N, Kh, device=DEV), torch.ones(N, device=DEV), torch.ones(Kh, device=DEV)     # accumulate onto 1
+    ops.head_bwd(gz, h, w, act, gz_prev=gz_prev, dw=dw, db=db, db_prev=dbp, gz_scale=0.5)
+    gzd = 0.5 * gz.double()
+    dh = gzd @ w.double()
+    if act == "elu":
+        dh = torch.where(h.double() > 0, dh, dh * (h.double() + 1))
+    elif act == "relu":
+        dh = torch.where(h.double() > 0, dh, torch.zeros_like(dh))
+    tol = dict(rtol=2e-5, atol=2e-5 * max(1.0, M ** 0.5 / 16))
+    assert_close("gz_prev", gz_prev, dh.float(), rtol=1e-5, atol=1e-5)
+    assert_close("dw", dw, (1 + gzd.t() @ h.double()).float(), **tol)
+    assert_close("db", db, (1 + gzd.sum(0)).float(), **tol)
+    assert_close("db_prev", dbp, (1 + dh.sum(0)).float(), **tol)
+
+
+# ---- K7 with column windows / fused activation backward -----------------------------------------------------------------------
+def test_linear_fwd_reads_and_writes_column_windows():
+    """Privileged-latent encoder shapes: input = lanes 61..89 of the 671-wide observation row, output = lanes 61..89 of the
+    101-wide actor input row (neighbouring lanes must stay untouched)."""
+    g = torch.Generator().manual_seed(1)
+    M = 5000
+    obs = _padded(M, 671, gen=g)
+    w1, b1 = (torch.randn(64, 29, generator=g) / 29 ** 0.5), torch.randn(64, generator=g)
+    w1p = _padded(64, 29)
+    w1p.copy_(w1)
+    h = _padded(M, 64)
+    ops.linear_fwd(obs, w1p, b1.to(DEV), h, "elu", x_col0=61)
+    x = obs[:, 61:90]
+    ref = torch.nn.functional.elu(x.double() @ w1.double().t().to(DEV) + b1.double().to(DEV))
+    assert _scaled_err(h, ref, x, w1p, b1.to(DEV)) < TF32_BOUND
+    w2, b2 = (torch.randn(29, 64, generator=g) / 8).to(DEV), torch.randn(29, generator=g).to(DEV)
+    xa = _padded(M, 101, fill=7.0)
+    ops.linear_fwd(h, w2, b2, xa, "elu", y_col0=61)
+    ref2 = torch.nn.functional.elu(h.double() @ w2.double().t() + b2.double())
+    assert _scaled_err(xa[:, 61:90], ref2, h, w2, b2) < TF32_BOUND
+    assert bool((xa[:, :61] == 7.0).all()) and bool((xa[:, 90:] == 7.0).all())
+
+
+@pytest.mark.parametrize("M,N,K,act", [(24576, 256, 512, "elu"), (4100, 128, 256, "elu"), (1000, 29, 64, "elu"), (777, 64, 128, "relu")])
+def test_linear_bwd_dx_fused_activation_backward_tma_prefetch(M, N, K, act):
+    """dx epilogue = act'(y_prev) (y_prev slabs prefetched by TMA) + bias gradient, accumulate and overwrite modes."""
+    g = torch.Generator().manual_seed(N)
+    gz, w = _padded(M, N, gen=g), _padded(N, K, gen=g)
+    w.mul_(1 / N ** 0.5)
+    yprev = _padded(M, K, gen=g)
+    if act == "relu":
+        yprev.clamp_(min=0)
+    else:
+        yprev.copy_(torch.nn.functional.elu(yprev))
+    dx = _padded(M, K)
+    db = torch.full((K,), 3.0, device=DEV)
+    ops.linear_bwd(gz, None, w, dx=dx, act_prev=act, y_prev=yprev, db_prev=db, db_accumulate=True)
+    raw = gz.double() @ w.double()
+    d = torch.where(yprev.double() > 0, torch.ones_like(raw), (yprev.double() + 1) if act == "elu" else torch.zeros_like(raw))
+    ref = raw * d
+    scale = (gz.double().abs() @ w.double().abs()).clamp(min=1e-6) * d.abs().clamp(min=1e-3)
+    assert float(((dx.double() - ref).abs() / scale).max()) < TF32_BOUND
+    assert_close("db accumulate", db, (3.0 + dx.double().sum(0)).float(), rtol=1e-4, atol=1e-3 * M ** 0.5 / 16)
+    ops.linear_bwd(gz, None, w, dx=dx, act_prev=act, y_prev=yprev, db_prev=db)
+    assert_close("db overwrite", db, dx.double().sum(0).float(), rtol=1e-4, atol=1e-3 * M ** 0.5 / 16)
+
+
+def test_linear_bwd_column_windows():
+    """dX w.r.t. a window of the input row (actor layer 1 -> the 29 latent lanes) and dW from a window of a wider input."""
+    g = torch.Generator().manual_seed(4)
+    M = 6000
+    gz, w = _padded(M, 512, gen=g), _padded(512, 101, gen=g)
+    dx = _padded(M, 29, fill=9.0)
+    ops.linear_bwd(gz, None, w, dx=dx, w_col0=61, K=29)
+    ref = gz.double() @ w.double()[:, 61:90]
+    scale = gz.double().abs() @ w.double().abs()[:, 61:90]
+    assert float(((dx.double() - ref).abs() / scale.clamp(min=1e-6)).max()) < TF32_BOUND
+    obs = _padded(M, 671, gen=g)
+    gz1 = _padded(M, 64, gen=g)
+    dw = _padded(64, 29)
+    ops.linear_bwd(gz1, obs, None, dw=dw, x_col0=61, K=29)
+    ref = gz1.double().t() @ obs.double()[:, 61:90]
+    scale = gz1.double().abs().t() @ obs.double().abs()[:, 61:90]
+    assert float(((dw.double() - ref).abs() / scale.clamp(min=1e-6)).max()) < TF32_BOUND
+
+
+def test_act_bwd_with_second_upstream_gradient():
+    g = torch.Generator().manual_seed(5)
+    M, N = 4099, 29
+    gy, y, add = _padded(M, N, gen=g), _padded(M, 101, gen=g)[:, 61:90], _padded(M, N, gen=g)
+    coef = torch.full((), 0.37, device=DEV)
+    gz, db = _padded(M, N), torch.full((N,), 2.0, device=DEV)
+    ops.act_bwd(gy, y, "elu", gz=gz, db=db, zero_db=False, addend=add, addend_scale=coef)
+    up = gy.double() + 0.37 * add.double()
+    ref = torch.where(y.double() > 0, up, up * (y.double() + 1))
+    assert_close("gz", gz, ref.float(), rtol=1e-5, atol=1e-6)
+    assert_close("db", db, (2.0 + ref.sum(0)).float(), rtol=1e-4, atol=1e-3)
+
+
+def test_gather_windows_builds_actor_input_row():
+    g = torch.Generator().manual_seed(6)
+    R, M = 5000, 1234
+    obs = torch.randn(R, 671, generator=g).to(DEV)
+    lat = torch.randn(R, 29, generator=g).to(DEV)
+    idx = torch.randperm(R, generator=g)[:M].to(DEV)
+    xa, ob, hl = _padded(M, 101, fill=5.0), _padded(M, 671), _padded(M, 29)
+    ops.gather_minibatch_windows(idx, [(obs, 0, ob, 0, 671), (obs, 0, xa, 0, 61), (obs, 660, xa, 90, 11), (lat, 0, hl, 0, 29)])
+    assert torch.equal(ob, obs[idx]) and torch.equal(hl, lat[idx])
+    assert torch.equal(xa[:, :61], obs[idx][:, :61]) and torch.equal(xa[:, 90:], obs[idx][:, 660:])
+    assert bool((xa[:, 61:90] == 5.0).all())
+
+
+# ---- the scheduled step -------------------------------------------------------------------------------------------------------
+def _load_golden():
+    z = np.load(f"{GOLD}/trainer_policy_seed3.npz")
+    return {k: torch.from_numpy(z[k]) for k in z.files}
+
+
+def _sample_from_golden(g):
+    b = {k: g["in.batch." + k].to(DEV) for k in ("actions", "target_values", "advantages", "returns", "old_actions_log_prob",
+                                                  "old_mu", "old_sigma")}
+    obs = g["in.obs"].to(DEV)
+    return (obs, obs, b["actions"], b["target_values"], b["advantages"], b["returns"], b["old_actions_log_prob"], b["old_mu"],
+            b["old_sigma"], (None, None), None)
+
+
+def test_plan_step_matches_reference_golden(tc_mode):
+    """`update_actor_critic(sample)` on the static schedule (tcgen05 layers) against the UNMODIFIED reference's statistics,
+    adaptive learning rate and post-step parameters (tests/golden/trainer_policy_seed3.npz)."""
+    from test_trainer_gpu import build
+    g = _load_golden()
+    alg, env, norm = build(synthetic.make_weights(3))
+    alg.priv_reg_counter = int(g["in.priv_reg_counter"])
+    out = alg.update_actor_critic(_sample_from_golden(g))
+    assert alg._plan is not None, "the static schedule must be the path under test"
+    torch.cuda.synchronize()
+    for v, k in zip(out, ("surrogate_loss", "value_loss", "b_loss", "entropy", "priv_reg_loss", "estimator_loss")):
+        assert_close(f"ppo.{k}", v.cpu(), g[f"ppo.{k}"], rtol=TC_STAT_RTOL, atol=1e-4)
+    assert abs(alg.lr_ac - float(g["ppo.lr_new"])) < 1e-9
+    stride = int(g["in.param_stride"])
+    ac_flat = torch.cat([v.reshape(-1) for v in alg.actor_critic.state_dict().values()])[::stride].cpu()
+    est_flat = torch.cat([v.reshape(-1) for v in alg.estimator.state_dict().values()])[::stride].cpu()
+    # Adam's first step is lr * g / (|g| + eps): sign-like, so an entry whose gradient is ~0 can flip; bound = 2 * lr per entry,
+    # and >= 99 % of the sampled entries within the TF32-perturbed fp32 bar
+    lr = 1e-3
+    for name, got, want in (("ac", ac_flat, g["ppo.ac_params_sampled"]), ("est", est_flat, g["ppo.est_params_sampled"])):
+        err = (got - want).abs()
+        assert float(err.max()) <= 2.5 * lr, name
+        assert float((err <= 2e-4 + 1e-3 * want.abs()).float().mean()) > 0.99, name
+
+
+def test_plan_gradients_match_fp32_autograd_path(tc_mode):
+    """Every flat gradient entry of the scheduled step (forward + hand-written backward) against the autograd path on fp32
+    cuBLAS layers, same minibatch: relative L2 error of each parameter tensor's gradient below the TF32 bound compounded over
+    the depth of the network."""
+    from test_trainer_gpu import build
+    g = _load_golden()
+    w = synthetic.make_weights(3)
+    sample = _sample_from_golden(g)
+    coef = OT.priv_reg_coef(1500)
+    # fp32 autograd
+    linear.set_mode("fp32")
+    ref, _, _ = build(w)
+    ref._alloc_minibatch(64)
+    ref._kl = torch.zeros((), device=DEV)
+    for k, v in zip(("obs", "critic_obs", "actions", "values", "advantages", "returns", "old_actions_log_prob", "old_mu", "old_sigma"),
+                    sample[:9]):
+        ref._mb[k].copy_(v.reshape(ref._mb[k].shape))
+    with torch.no_grad():
+        ref._mb["hist_latent"].copy_(ref.actor_critic.infer_hist_latent(ref._mb["obs"][:, 90:660]))
+    ref._priv_reg_coef.fill_(coef)
+    ref._forward_backward()
+    # static schedule
+    linear.set_mode("tc")
+    alg, _, _ = build(w)
+    alg._kl = torch.zeros((), device=DEV)
+    plan = alg._ensure_plan(64)
+    assert plan is not None
+    plan.load(0, sample)
+    with torch.no_grad():
+        plan.sets[0]["hist_latent"].copy_(alg.actor_critic.infer_hist_latent(plan.sets[0]["obs"][:, 90:660]))
+    alg._priv_reg_coef.fill_(coef)
+    plan.forward_backward(0)
+    torch.cuda.synchronize()
+    for (name, p), (_, q) in zip(list(alg.actor_critic.named_parameters()) + list(alg.estimator.named_parameters()),
+                                 list(ref.actor_critic.named_parameters()) + list(ref.estimator.named_parameters())):
+        a, b = p.grad.double(), q.grad.double()
+        if float(b.norm()) == 0.0:
+            assert float(a.norm()) == 0.0, name          # frozen history encoder: no gradient in either path
+            continue
+        rel = float((a - b).norm() / b.norm())
+        assert rel < 1e-2, f"{name}: relative L2 gradient error {rel:.3e}"
+    assert_close("ppo stats", alg._ppo_stats, ref._ppo_stats, rtol=TC_STAT_RTOL, atol=1e-5)
+    assert_close("aux losses", alg._aux_loss, ref._aux_loss, rtol=TC_STAT_RTOL, atol=1e-5)
+
+
+def test_plan_update_full_size_in_cuda_graph_matches_oracle(tc_mode):
+    """BASELINE config 0 at full size on the path the bench times: `update()` over a recorded 4096 x 24 storage = K5, K11, four
+    K6 gathers, 20 replays of the captured static-schedule graphs.  The mean statistics of the FIRST epoch's first minibatch
+    are checked against the CPU oracle's loss graph (later minibatches see updated parameters); the whole update is checked for
+    self-consistency against the eager (un-captured) schedule: same statistics and same final parameters."""
+    from test_trainer_gpu import build
+    N, T = 4096, 24
+    w = synthetic.make_weights(3)
+    runs = []
+    for graph in (True, False):
+        alg, env, norm = build(w, n_envs=N)
+        alg.use_cuda_graph = graph
+        st = alg.storage
+        g = torch.Generator().manual_seed(2)
+        st.observations.copy_(0.5 * torch.randn(T, N, 671, generator=g))
+        st.privileged_observations.copy_(st.observations)
+        linear.set_mode("fp32")
+        with torch.no_grad():
+            for t in range(T):
+                o = st.observations[t]
+                alg.act(o, o, normal_draw=torch.randn(N, 12, generator=g).to(DEV))
+                tr = alg.transition
+                st.actions[t], st.values[t] = tr.actions, tr.values
+                st.actions_log_prob[t, :, 0], st.mu[t], st.sigma[t] = tr.actions_log_prob, tr.action_mean, tr.action_sigma
+        linear.set_mode("tc")
+        st.mu.add_(0.05 * torch.randn(T, N, 12, generator=g).to(DEV))
+        st.sigma.mul_(1.05)
+        st.actions_log_prob.add_(0.05 * torch.randn(T, N, 1, generator=g).to(DEV))
+        st.rewards.copy_(0.05 * torch.rand(T, N, 1, generator=g))
+        st.dones.copy_((torch.rand(T, N, 1, generator=g) < 0.02).byte())
+        st.compute_returns(torch.zeros(N, 1, device=DEV), 0.99, 0.95)
+        idx = torch.randperm(T * N, generator=g).to(DEV)
+        alg.priv_reg_counter = 1500
+        if graph:
+            # oracle on the first minibatch with the initial weights
+            rows = idx[:T * N // 4].cpu()
+            v = st.flat_views()
+            batch = dict(obs=v["obs"].cpu()[rows], critic_obs=v["critic_obs"].cpu()[rows], actions=v["actions"].cpu()[rows],
+                         target_values=v["values"].cpu()[rows], advantages=v["advantages"].cpu()[rows], returns=v["returns"].cpu()[rows],
+                         old_actions_log_prob=v["old_actions_log_prob"].cpu()[rows], old_mu=v["old_mu"].cpu()[rows],
+                         old_sigma=v["old_sigma"].cpu()[rows])
+            with torch.no_grad():
+                L = OT.ppo_losses(w["ac"], w["est"], batch, priv_reg_coef=OT.priv_reg_coef(1500))
+            # one scheduled step on that minibatch (eager), statistics only -- then restore and run the full update
+            alg._alloc_minibatch(T * N // 4)
+            alg._kl = torch.zeros((), device=DEV)
+            alg._encode_history()
+            plan = alg._ensure_plan(T * N // 4)
+            plan.gather(0, idx[:T * N // 4], alg._hist_latent_all)
+            alg._priv_reg_coef.fill_(OT.priv_reg_coef(1500))
+            plan.forward_backward(0)
+            torch.cuda.synchronize()
+            ps, ax = alg._ppo_stats.cpu(), alg._aux_loss.cpu()
+            for got, k in ((ps[0], "surrogate_loss"), (ps[1], "value_loss"), (ps[2], "b_loss"), (ax[0], "priv_reg_loss"),
+                           (ax[1], "estimator_loss"), (ps[3], "kl_mean")):
+                assert_close(f"first minibatch {k}", got, L[k].float(), rtol=TC_STAT_RTOL, atol=1e-5)
+        stats = alg.update(indices=idx)
+        torch.cuda.synchronize()
+        assert alg._plan is not None and (not graph or len(alg._graphs) == 4)
+        runs.append((stats, alg.ac_flat.data.clone(), alg.est_flat.data.clone(), alg.lr_ac))
+    (s0, a0, e0, lr0), (s1, a1, e1, lr1) = runs
+    assert lr0 == lr1
+    for x, y in zip(s0, s1):
+        assert abs(x - y) <= 1e-4 + 1e-3 * abs(y)         # split-K / atomic summation order differs between runs
+    assert float((a0 - a1).abs().max()) <= 2.5e-3 and float(((a0 - a1).abs() < 1e-4).float().mean()) > 0.98
+    assert float((e0 - e1).abs().max()) <= 2.5e-3
