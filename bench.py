@@ -199,11 +199,15 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "collection_ms": collect_ms, "learning_ms": learn_ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "tf32 GEMM operands / f32 accumulate and everything else", "data": "synthetic",
+            "dtype": "tf32 GEMM operands / f32 accumulate (wide ActorCritic layers on tcgen05); f32 everything else incl. the output heads", "data": "synthetic",
             "config": {"workload": WORKLOAD_NAME, "envs_per_gpu": cfg.num_envs, "steps_per_env": T_STEPS,
                        "stages": it.stage_names, "rng": "in-kernel Philox4x32-10",
                        "l2": "256 MiB flush between timed iterations; per-step working set 46 MB < 126 MB L2",
-                       "parallelism": f"env-sharded dp{world}"},
+                       "parallelism": f"env-sharded dp{world}",
+                       "collectives_per_optimiser_step": (1 if it.runner.alg._grad_arena is not None else 3) if world > 1 else 0,
+                       "advantage_normalisation": "per rank (each rank normalises its own 98 304 samples, rollout_storage.py:111: "
+                                                  "W ranks behave like W reference runs of 4096 envs whose gradients are averaged)",
+                       "ppo_step": "static schedule (ppo_plan)" if it.runner.alg._plan is not None else "autograd"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": it.h2d_bytes_per_iteration,
                     "d2h_bytes_per_step": it.d2h_bytes_per_iteration},
             "gpu_launches": launches,
@@ -224,17 +228,31 @@ def run_ours(args):
             line["cpu_baseline"] = cpu
         if world == 1:
             line["roofline_gemm"] = gemm_roofline_sample(dev, pk)
+            line["roofline_32768"] = k2_roofline_32768(dev, pk)
+            if not args.no_fp32_value:
+                line["value_fp32_linear"] = fp32_linear_value(args, rank, dev)
         if world == 1 and not args.no_torch_gpu_baseline:
             line["torch_gpu_baseline"] = torch_gpu_baseline_sample(dev)
         print(json.dumps(line, default=str), flush=True)
     if world > 1:
-        # Leave without tearing NCCL down: destroy_process_group() blocks for minutes while CUDA graphs that captured
-        # collectives are still alive (seen on 2 x B200: the JSON line was out, the ranks never exited).
+        # Tear down in dependency order: the CUDA graphs that captured NCCL collectives first, then the process group (round 1
+        # destroyed the group while those graphs were alive and blocked for minutes).  A watchdog keeps a hang here from
+        # costing the run: the JSON line is already out.
+        import gc
+        import threading
         dist.barrier()
         torch.cuda.synchronize()
         sys.stdout.flush()
         sys.stderr.flush()
-        os._exit(0)
+        it.release_graphs()
+        del it
+        gc.collect()
+        torch.cuda.synchronize()
+        wd = threading.Timer(30.0, lambda: os._exit(0))
+        wd.daemon = True
+        wd.start()
+        dist.destroy_process_group()
+        wd.cancel()
 
 
 TSC_BYTES_PER_ENV = 12634      # algorithmic bytes of the TSC post-physics pair (K16 + K17) per env-step
@@ -291,16 +309,15 @@ def cpu_reference_sample(n_envs, rollout_steps, minibatch_steps, threads):
     """The reference algorithm's CPU path (oracle port): `rollout_steps` of the 24 env steps, GAE, and
     `minibatch_steps` of the 20 PPO minibatch steps.  Returns (extrapolated seconds per full iteration, detail)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import bbc_env as O
-    import trainer as OT
-    from qa_b200 import pipeline, synthetic
+    import iteration as oracle_iteration
+    from qa_b200 import synthetic
     torch.set_num_threads(threads)
     cfg, static, snaps, table = build_workload(0, "cpu", n_envs=n_envs, steps=T_STEPS)
     draws = [synthetic.make_rng_draws(cfg, seed=1234, step=t) for t in range(rollout_steps)]
     for d in draws:
         d["mocap_clip_idx"] = table.sample_clip(d["rt_c_idx"], d["mocap_clip_u"])
-    r = pipeline.cpu_oracle_iteration(O, OT, cfg, static, snaps, draws, table, synthetic.make_weights(1),
-                                      rollout_steps=rollout_steps, minibatch_steps=minibatch_steps)
+    r = oracle_iteration.oracle_iteration(cfg, static, snaps, draws, table, synthetic.make_weights(1),
+                                          rollout_steps=rollout_steps, minibatch_steps=minibatch_steps)
     full = r["t_rollout"] * (T_STEPS / rollout_steps) + r["t_gae"] + r["t_update"] * (20 / minibatch_steps)
     return full, r
 
@@ -310,7 +327,8 @@ def _cpu_line(threads, rollout_steps, minibatch_steps, full, r):
             "sample": (f"oracle/ port of the reference on torch {torch.__version__} CPU, {threads} threads, {ENVS_PER_GPU} envs: "
                        f"{rollout_steps}/24 rollout steps ({r['t_rollout']:.2f} s), GAE ({r['t_gae']:.3f} s), "
                        f"{minibatch_steps}/20 PPO minibatch steps of 24576 ({r['t_update']:.2f} s), "
-                       f"extrapolated to one full iteration = {full:.2f} s")}
+                       + (f"one full iteration measured = {full:.2f} s" if rollout_steps == T_STEPS and minibatch_steps == 20 else
+                          f"extrapolated to one full iteration = {full:.2f} s"))}
 
 
 def gemm_roofline_sample(dev, pk, reps=20):
@@ -361,6 +379,92 @@ def gemm_roofline_sample(dev, pk, reps=20):
         return {"error": f"{type(e).__name__}: {e}"[:300]}
 
 
+def k2_roofline_32768(dev, pk, n_envs=32768, n_snaps=4, launches=8, reps=10):
+    """"the 32 768-env config is the honest bandwidth test" -- the fused post-physics kernel at 32 768 envs on ONE
+    GPU (4096 CTAs, several waves: loads, compute and stores of different tiles overlap, unlike the one-wave 4096-env launch).
+    `launches` K2 launches over `n_snaps` distinct state snapshots in a CUDA graph, 256 MiB L2 flush before each replay; the
+    per-launch working set (366 MB) is larger than L2 by itself.  Guarded like the baseline legs."""
+    try:
+        from qa_b200 import synthetic
+        from qa_b200.config import BbcEnvConfig
+        from qa_b200.legged_robot import LeggedRobot, RecordedPhysics
+        from qa_b200.mocap import MocapTable
+        cfg = BbcEnvConfig(num_envs=n_envs)
+        static = synthetic.make_static(cfg, seed=4321)
+        snaps = [synthetic.make_snapshot(cfg, seed=4321, step=t) for t in range(n_snaps)]
+        table = MocapTable.from_npz(os.path.join(ROOT, "tests", "golden", "mocap_lb_table.npz"))
+        dev_snaps = [{k: s[k].to(dev) for k in SIM_KEYS} for s in snaps]
+        env = LeggedRobot(cfg, RecordedPhysics(dev_snaps), static, table, device=dev, seed=4321)
+        env.load_state({k: v.to(dev) for k, v in snaps[0].items() if k not in SIM_KEYS})
+        env.use_device_step_counter(True)
+        st = torch.cuda.Stream()
+        st.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(st):
+            env._k2_only_step()
+        torch.cuda.current_stream().wait_stream(st)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(launches):
+                env._k2_only_step()
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        total = 0.0
+        for _ in range(reps):
+            flush.fill_(1)
+            e0.record()
+            g.replay()
+            e1.record()
+            e1.synchronize()
+            total += e0.elapsed_time(e1)
+        us = total / (reps * launches) * 1e3
+        ach = K2_BYTES_PER_ENV * n_envs / (us * 1e-6) / 1e9
+        return {"bound": "hbm", "kernel": "k_post_physics_bbc", "envs": n_envs, "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": ach / pk["hbm_gbs"], "us_per_launch": us, "launches_timed": reps * launches,
+                "algorithmic_bytes_per_launch": K2_BYTES_PER_ENV * n_envs,
+                "how": f"CUDA events around graph replays of {launches} K2 launches ({n_snaps} distinct snapshots), 256 MiB L2 flush before each"}
+    except Exception as e:                                               # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
+
+
+def fp32_linear_value(args, rank, dev, steps=3):
+    """The same iteration with every dense layer in full fp32 (QA_LINEAR_MODE=fp32: cuBLAS sgemm through autograd, the parity-test
+    mode) -- printed beside `value` because the headline runs the ActorCritic GEMMs with TF32 operands (north_star puts them on
+    the tensor cores; there is no fp32 tensor-core mode).  Device-resident timing like `value`."""
+    try:
+        from qa_b200.pipeline import BbcIteration
+        from qa_b200.rsl_rl import linear
+        tf32 = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        prev = linear.get_mode()
+        linear.set_mode("fp32")
+        try:
+            cfg, static, snaps, table = build_workload(rank, dev)
+            it = BbcIteration(cfg, static, snaps, table, device=dev, seed=1234 + rank)
+            for _ in range(3):
+                it.run_resident()
+            flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ms = 0.0
+            for _ in range(steps):
+                flush.fill_(1)
+                torch.cuda.synchronize()
+                e0.record()
+                it.run_resident()
+                e1.record()
+                e1.synchronize()
+                ms += e0.elapsed_time(e1)
+            it.release_graphs()
+        finally:
+            linear.set_mode(prev)
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+        ms /= steps
+        return {"value": T_STEPS * cfg.num_envs / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
+                "dtype": "f32 everywhere (cuBLAS sgemm, allow_tf32=False)"}
+    except Exception as e:                                               # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
+
+
 def torch_gpu_baseline_sample(dev, n_envs=ENVS_PER_GPU):
     """the reference's own single-GPU path -- its PyTorch op sequence (the oracle port, eager torch kernels, fp32)
     on the SAME B200 and workload, one full iteration (24 env steps + GAE + 20 PPO minibatch steps) after a short warm-up.
@@ -368,9 +472,8 @@ def torch_gpu_baseline_sample(dev, n_envs=ENVS_PER_GPU):
     that a failure here can never cost the benchmark line."""
     try:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
-        import bbc_env as O
-        import trainer as OT
-        from qa_b200 import pipeline, synthetic
+        import iteration as oracle_iteration
+        from qa_b200 import synthetic
         tf32 = torch.backends.cuda.matmul.allow_tf32
         torch.backends.cuda.matmul.allow_tf32 = False                  # the reference runs fp32 matmuls (torch default)
         mv = lambda d: {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in d.items()}     # noqa: E731
@@ -383,8 +486,8 @@ def torch_gpu_baseline_sample(dev, n_envs=ENVS_PER_GPU):
         static, snaps, table = mv(static), [mv(s) for s in snaps], table.to(dev)
         w = synthetic.make_weights(1)
         w = {k: (mv(v) if isinstance(v, dict) else v.to(dev)) for k, v in w.items()}
-        run = lambda rs, ms: pipeline.cpu_oracle_iteration(O, OT, cfg, static, snaps, draws, table, w, rollout_steps=rs,   # noqa: E731
-                                                           minibatch_steps=ms, device=dev)
+        run = lambda rs, ms: oracle_iteration.oracle_iteration(cfg, static, snaps, draws, table, w, rollout_steps=rs,   # noqa: E731
+                                                               minibatch_steps=ms, device=dev)
         run(2, 2)                                                        # warm-up: allocator, cuBLAS handles, autotuning
         r = run(T_STEPS, 20)
         torch.backends.cuda.matmul.allow_tf32 = tf32
@@ -410,7 +513,9 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    rs, ms = 6, 2
+    # the WHOLE iteration (24/24 env steps, GAE, 20/20 PPO minibatch steps of 24 576): measured, not extrapolated -- about 3 s per
+    # step on 16 host cores, so the driver's --steps / --warmup stay within minutes
+    rs, ms = T_STEPS, 20
     for _ in range(min(args.warmup, 1)):
         cpu_reference_sample(ENVS_PER_GPU, 2, 1, threads)
     fulls = []
@@ -424,7 +529,8 @@ def run_reference(args):
             "warmup": args.warmup, "ms_per_step": full * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD_NAME, "envs_per_gpu": ENVS_PER_GPU, "steps_per_env": T_STEPS,
-                       "sample": "host cores, bounded sample of the workload per step (see cpu_baseline.sample)"},
+                       "sample": "host cores, one FULL iteration per step (24 env steps + GAE + 20 PPO minibatch steps), "
+                                 "see cpu_baseline.sample"},
             "cpu_baseline": _cpu_line(threads, rs, ms, full, r),
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line, default=str), flush=True)
@@ -441,6 +547,7 @@ def main():
                     help="dense layers: tc = hand-written tcgen05 TF32 forward (default), cublas = library TF32 GEMMs")
     ap.add_argument("--no-torch-gpu-baseline", action="store_true",
                     help="skip the reference's PyTorch path timed on the same GPU (reported beside the metric)")
+    ap.add_argument("--no-fp32-value", action="store_true", help="skip the full-fp32 (cuBLAS) run of the same iteration")
     ap.add_argument("--k2-bulk", type=int, default=2,
                     help="K2 variant: 2 = 8-env TMA tiles (default), 1 = warp-per-env + TMA row stores, 0 = warp stores")
     args = ap.parse_args()

@@ -334,10 +334,10 @@ class LeggedRobot:
         mode draw happens inside the fused step, which reads the inclusive CDF from a device tensor at a fixed address:
         three tiny torch kernels, no host sync, visible to captured graphs.  The trainer calls this after every
         discriminator update (the only writer of `prior_parameters`, gail.py:462-464)."""
-        with torch.no_grad():
-            prob = torch.softmax(self.prior_parameters.to(torch.float32) / self.cfg.latent_c_temperature, dim=-1)
+        with torch.no_grad():        # float64 like ops.bbc_const / oracle/philox.prior_cdf, rounded to fp32 once at the end
+            prob = torch.softmax(self.prior_parameters.to(torch.float64) / self.cfg.latent_c_temperature, dim=-1)
             self.prior_prob.copy_(prob)
-            torch.cumsum(prob, dim=0, out=self._prior_cdf)
+            self._prior_cdf.copy_(torch.cumsum(prob, dim=0))
 
     def set_prior_parameters(self, prior: torch.Tensor) -> None:
         """Overwrite `env.prior_parameters` IN PLACE (the trainer and captured graphs hold the tensor) and refresh the CDF."""
@@ -368,10 +368,11 @@ class LeggedRobot:
             self.physics.set_dof_actuation_force(self.torques)
             self.physics.simulate()
 
-    def post_physics_step(self) -> None:
+    def post_physics_step(self, refresh: bool = True) -> None:
         """K2 + reset compaction, all on the current stream, no host sync."""
         ph, a, cfg = self.physics, self._args, self.cfg
-        ph.refresh()
+        if refresh:
+            ph.refresh()
         self.common_step_counter += 1
         do_push = bool(cfg.push_robots and (self.common_step_counter % cfg.push_interval == 0))
         prev_disc = self._disc[self._pp]
@@ -440,15 +441,48 @@ class LeggedRobot:
                 self._reset_ids[:k], self._terminal_disc[:k])
 
     def reset(self):
-        """Reset all robots (:67-76): every env takes the reset branch of the next fused step."""
-        # reset_idx(all envs): one fused pass with episode_length_buf beyond max_episode_length takes the
-        # reset branch (resample + mocap state + buffer clears) for every env ...
-        counter = self.common_step_counter
-        self.episode_length_buf.fill_(int(self.max_episode_length) + 1)
-        self.post_physics_step()
-        self.common_step_counter = counter
+        """Reset all robots (:67-76): `reset_idx(all envs)` followed by one step with zero actions.
+
+        `reset_idx` is the reset branch of the fused step, so the first half runs K2 once with every env past its episode
+        limit and then puts back what `reset_idx` itself does not touch but a full step does (:178-240 vs :124-166): the step
+        counters and push schedule, `last_contacts` and the contact rings, the latched `extras["time_outs"]` (the time-out mask
+        from BEFORE the reset, :239-240), `extras["episode"]` (means of the episode sums as they were, without the phantom
+        step's reward, :230-234) and the zeroed `last_*` buffers (:217-221).  Parity: tests/test_env_gpu.py against the
+        reference's own `reset()` (tests/golden/bbc_env_reset_n64.npz)."""
+        dev_counter = self.device_step_counter
+        if dev_counter:
+            self.sync_step_counter()
+            self.device_step_counter = False
+        counter, ring_head = self.common_step_counter, self._ring_head
+        keep = [t.clone() for t in (self.last_contacts, self.time_out_buf, self.obs_disc_buf)]
+        rings = [r.clone() for r in (self._contact_ring, self._contact_force_ring)] if self._ring_len else []
+        means = self._episode_sums[:, :K.NUM_REWARDS].mean(dim=0) / self.max_episode_length_s
+        # a counter value that neither pushes nor resamples in this pass and keys a Philox stream no real step uses
+        fake = counter + (1 << 40)
+        if self.cfg.push_robots and (fake + 1) % self.cfg.push_interval == 0:
+            fake += 1
+        self.common_step_counter = fake
+        over = int(self.max_episode_length) + 1
+        if (over + 1) % self.cfg.resample_period == 0:
+            over += 1
+        self.episode_length_buf.fill_(over)
+        self.post_physics_step(refresh=False)
+        self.common_step_counter, self._ring_head = counter, ring_head
+        self.last_contacts.copy_(keep[0])
+        self._time_outs_latched.copy_(keep[1])
+        self.obs_disc_buf.copy_(keep[2])                    # the next step's "previous disc obs" (terminal states, :153-154)
+        for ring, saved in zip((self._contact_ring, self._contact_force_ring), rings):
+            ring.copy_(saved)
+        self._episode_rew_means.copy_(means)
+        for t in (self.last_actions, self.last_dof_vel, self.last_root_vel, self.last_torques_org):
+            t.zero_()
+        self.extras["episode"] = {"rew_" + n: self._episode_rew_means[i] for i, n in enumerate(K.REWARD_NAMES)}
+        if self.cfg.send_timeouts:
+            self.extras["time_outs"] = self._time_outs_latched
         # ... then the reference steps once with zero actions and returns that observation
         obs, priv, *_ = self.step(torch.zeros(self.num_envs, self.num_actions, device=self.device))
+        if dev_counter:
+            self.use_device_step_counter(True)
         return obs, priv
 
 

@@ -196,11 +196,11 @@ class SSInfoGAIL:
             capture_collectives = os.environ.get("QA_CAPTURE_COLLECTIVES", "1") == "1"
         self.capture_collectives = capture_collectives
         self._graph_has_apply = True
-        # north_star's "single NCCL allreduce of PPO gradients": with QA_SINGLE_ALLREDUCE=1 the actor-critic gradients, the
-        # estimator gradients and the KL scalar live in ONE arena reduced by one collective per optimiser step (instead of
-        # three); opt-in until it has run over NCCL (the arithmetic is checked over gloo, tests/test_dist_gloo.py)
+        # north_star's "single NCCL allreduce of PPO gradients": the actor-critic gradients, the estimator gradients and the KL
+        # scalar live in ONE arena reduced by one collective per optimiser step (QA_SINGLE_ALLREDUCE=0: three collectives);
+        # gloo: tests/test_dist_gloo.py, NCCL on 2 x B200: tests/test_dist_nccl_gpu.py
         self._grad_arena = None
-        if self.world_size > 1 and os.environ.get("QA_SINGLE_ALLREDUCE", "0") == "1":
+        if self.world_size > 1 and os.environ.get("QA_SINGLE_ALLREDUCE", "1") == "1":
             self.use_grad_arena()
         # discriminator minibatch step with one shared forward (see update_ss_info_gail); opt-in until it has been measured
         # and re-pinned on the B200 (same values up to the summation order of the weight gradients)

@@ -187,9 +187,9 @@ def _arena_worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     out = {}
     for arena in (False, True):
+        os.environ["QA_SINGLE_ALLREDUCE"] = "1" if arena else "0"          # the arena is the default with > 1 rank
         alg, env, norm = TD._alg(False, "MSELoss")
-        if arena:
-            alg.use_grad_arena()
+        assert (alg._grad_arena is not None) == arena
         g = torch.Generator().manual_seed(100 + rank)
         alg.ac_flat.grad.copy_(torch.randn(alg.ac_flat.numel, generator=g))
         alg.est_flat.grad.copy_(torch.randn(alg.est_flat.numel, generator=g))

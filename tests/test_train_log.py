@@ -85,3 +85,39 @@ def test_log_bbc_emits_the_reference_tags():
     log2 = ScalarLog()
     log_bbc(runner, log2, 4, stats[:6], None, 0.5, 1.5)
     assert "Loss/ss_loss" not in log2.scalars and "Loss/hist_latent_loss" not in log2.scalars
+
+
+def test_episode_rows_start_with_the_first_reset():
+    """`infos['episode']` does not exist before the first reset (legged_robot.py:188-189), so the reference's `ep_infos` has no
+    row for earlier steps (on_policy_runner.py:185-186): the staged per-step means are filtered by a device-side latch."""
+    import torch
+    from qa_b200.rsl_rl.train_log import EpisodeBook
+    book = EpisodeBook(4, 5, ("total",), "cpu", num_episode_keys=3)
+    means = torch.zeros(3)
+    resets = [0, 0, 2, 0, 1]
+    for t, k in enumerate(resets):
+        if k:
+            means = torch.full((3,), float(t))
+        book.record(torch.zeros(4, dtype=torch.uint8), torch.zeros(4, 1), means, num_resets=torch.tensor([k], dtype=torch.int32))
+    book.flush()
+    assert [float(r[0]) for r in book.episode_rows] == [2.0, 2.0, 4.0]
+    # the latch survives the flush: the next iteration's rows are all valid
+    book.record(torch.zeros(4, dtype=torch.uint8), torch.zeros(4, 1), means, num_resets=torch.tensor([0], dtype=torch.int32))
+    book.flush()
+    assert len(book.episode_rows) == 1
+
+
+def test_normalizer_load_moments_keeps_device_tensors():
+    import numpy as np
+    import torch
+    from qa_b200.rsl_rl.utils import Normalizer
+    n = Normalizer(6)
+    mean32, std32 = n.device_moments("cpu")
+    n.update_torch(torch.randn(50, 6))
+    st = n._device_state("cpu")
+    n.load_moments(np.arange(6.0), np.full(6, 4.0), 123.0)
+    assert n._device_state("cpu")[1] is st[1] and n.device_moments("cpu")[0] is st[4]
+    assert torch.allclose(st[4], torch.arange(6.0)) and torch.allclose(st[5], torch.sqrt(torch.full((6,), 4.0 + n.epsilon)))
+    assert float(st[3]) == 123.0 and n.count == 123.0
+    x = torch.randn(3, 6)
+    assert torch.allclose(n.normalize_torch(x, "cpu"), torch.clamp((x - torch.arange(6.0)) / st[5], -n.clip_obs, n.clip_obs))

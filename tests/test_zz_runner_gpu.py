@@ -1,7 +1,6 @@
-"""Device tests written at the end of round 1, after the round's GPU budget was spent: they have not run on a B200 yet (the
-host halves -- deque accounting, tag list, optimiser-dict codec, the runner's learn loop, the batched discriminator step's
-gradients -- are covered on CPU in tests/test_train_log.py, test_checkpoint.py, test_runner_host.py, test_disc_batched.py).
-The file sorts last so that nothing here can mask the verified suite under `pytest -x`.
+"""Device tests of the runner level (all green on the B200 since the round-1 driver run, GPUTEST_r01; host halves -- deque
+accounting, tag list, optimiser-dict codec, the runner's learn loop, the batched discriminator step's gradients -- are covered
+on CPU in tests/test_train_log.py, test_checkpoint.py, test_runner_host.py, test_disc_batched.py).
 
 * `SSInfoGAIL.update_actor_critic(sample)` and one full-size PPO minibatch step (BASELINE config 0) against golden / oracle;
 * `OnPolicyRunner.learn` with a log_dir: episode bookkeeping, the reference's scalar tags, checkpoint round trip
@@ -11,9 +10,7 @@ import numpy as np
 import pytest
 import torch
 
-# not "expected to fail": not yet observed.  strict=False reports a pass as XPASS and keeps a first-run surprise in this file
-# from reading as a regression of the verified suite; the marker goes away after the first device run (tools/gpu_round2_first.sh)
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="written after round 1's GPU budget was spent: first device run pending")]
+pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 

@@ -36,9 +36,11 @@ def show(title, part):
 
 
 show("whole capture", seq)
-idx = [i for i, (k, _) in enumerate(seq) if 'k_gather' in k]
-if len(idx) >= 2:
-    show("one PPO minibatch step", seq[idx[-2]:idx[-1]])
+# one PPO minibatch step = the launches between two consecutive PPO-loss launches (the gathers no longer delimit a step:
+# the static schedule gathers every minibatch once per update)
+idx = [i for i, (k, _) in enumerate(seq) if 'k_ppo_loss' in k and 'tsc' not in k]
+if len(idx) >= 3:
+    show("one PPO minibatch step", seq[idx[-3]:idx[-2]])
 k2 = [i for i, (k, _) in enumerate(seq) if 'k_post_physics' in k]
 if len(k2) >= 2:
     show("one rollout step", seq[k2[-2]:k2[-1]])
