@@ -339,7 +339,7 @@ int qa_gae(const QaGaeArgs* a, void* stream);
  * K6  minibatch gather -- replaces the 9 index ops per minibatch of RolloutStorage.mini_batch_generator,
  *     bbc/rsl_rl/storage/rollout_storage.py:147-155: dst[t][j,:] = src[t][indices[j],:] for every tensor t
  * ------------------------------------------------------------------------------------------ */
-#define QA_GATHER_MAX_TENSORS 12
+#define QA_GATHER_MAX_TENSORS 16
 typedef struct QaGatherArgs {
     int64_t num_rows;                   /* minibatch size (24 576) */
     int32_t num_tensors;
@@ -401,8 +401,8 @@ typedef struct QaLinearArgs {
     float* y;                           /* (M,N) */
     int64_t y_pitch;
     /* column windows inside wider rows (0 = the tensor starts at its base): x[:, x_col0 : x_col0+K] is the input and
-     * y[:, y_col0 : y_col0+N] the output; the bases and pitches, not the windows, carry TMA's 16-byte rule -- e.g. the
-     * privileged-latent lanes 61..89 of the observation row in, the actor-input lanes 61..89 out */
+     * y[:, y_col0 : y_col0+N] the output.  x_col0 must be a multiple of 4 floats (a TMA box starts on a 16-byte boundary);
+     * y_col0 may be any column -- an unaligned output window (the actor-input lanes 61..89) leaves through plain stores */
     int32_t x_col0, y_col0;
 } QaLinearArgs;
 int qa_linear_fwd(const QaLinearArgs* a, void* stream);
@@ -425,8 +425,8 @@ typedef struct QaLinearBwdArgs {
     const float* y_prev; int64_t y_prev_pitch;   /* read through TMA: 16 B aligned base, pitch % 4 == 0 */
     float* db_prev;                     /* (K) or NULL */
     int32_t db_accumulate;              /* 0: db_prev is zeroed first; 1: accumulate (flat gradient buffer zeroed by the caller) */
-    int32_t x_col0;                     /* dw: x[:, x_col0 : x_col0+K] is the layer input */
-    int32_t w_col0;                     /* dx: uses w[:, w_col0 : w_col0+K] (gradient w.r.t. a window of the input row) */
+    int32_t x_col0;                     /* dw: x[:, x_col0 : x_col0+K] is the layer input; multiple of 4 */
+    int32_t w_col0;                     /* dx: uses w[:, w_col0 : w_col0+K] (gradient w.r.t. a window of the input row); multiple of 4 */
 } QaLinearBwdArgs;
 int qa_linear_bwd(const QaLinearBwdArgs* a, void* stream);
 

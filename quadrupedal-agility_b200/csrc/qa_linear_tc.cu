@@ -354,6 +354,22 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                 else tmem_ld16(taddr, r);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 if (EPI == EPI_ACTBWD) mbar_wait(&S.ybar[q][chunk & 1], (chunk >> 1) & 1);
+                if (EPI == EPI_STORE && (g.out_c0 & 3) != 0) {
+                    // output window that does not start on a 16-byte boundary (e.g. the 29 latent lanes at column 61 of the
+                    // actor's input row): TMA needs 16-byte aligned box starts, so these few columns leave through plain stores
+                    const int row = m0 + q * 32 + lane;
+                    if (row < g.Mo) {
+                        float* o = g.out + (size_t)row * g.out_pitch + g.out_c0 + n0 + c0;
+#pragma unroll
+                        for (int j = 0; j < CH; ++j) {
+                            float x = __uint_as_float(r[j]) + bias_s[c0 + j];
+                            if (g.act == 1) x = x > 0.f ? x : __expf(x) - 1.f;
+                            else if (g.act == 2) x = fmaxf(x, 0.f);
+                            if (n0 + c0 + j < g.No) o[j] = x;
+                        }
+                    }
+                    continue;
+                }
 #pragma unroll
                 for (int j4 = 0; j4 < CH / 4; ++j4) {
                     float v[4];
@@ -467,8 +483,11 @@ static int num_sms() {
 
 template <int BN, bool A_MN, bool B_MN, int EPI>
 static int launch_gemm(const TcOperand& A, const TcOperand& B, TcProblem prob, int splits, cudaStream_t stream) {
-    // ring depth: as many 128 x 32 + BN x 32 fp32 stages as fit next to the epilogue buffers (<= 8)
-    constexpr int STAGES = BN >= 256 ? 3 : (BN >= 128 ? 5 : (BN >= 64 ? 6 : 8));
+    // ring depth: as many 128 x 32 + BN x 32 fp32 stages as fit next to the epilogue buffers in 227 KB (<= 8); the
+    // activation-backward epilogue carries 32 KB of y slabs
+    constexpr int STAGES = EPI == EPI_ACTBWD ? (BN >= 256 ? 3 : (BN >= 128 ? 4 : (BN >= 64 ? 6 : 7)))
+                                             : (BN >= 256 ? 3 : (BN >= 128 ? 5 : (BN >= 64 ? 6 : 8)));
+    static_assert(sizeof(TcSmem<BN, STAGES, EPI>) + 1024 <= 227 * 1024, "shared-memory budget");
     CUtensorMap ma, mb;
     int rc = make_map(&ma, A.base, A.rows, A.c0 + A.cols, A.pitch, A_MN ? 32 : TC_BM, A_MN);
     if (rc) return rc;
@@ -546,6 +565,7 @@ extern "C" int qa_linear_fwd(const QaLinearArgs* g, void* stream) {
     QA_CHECK_PTR(g->y);
     if (g->M < 0 || g->N <= 0 || g->K <= 0) return QA_EINVAL;
     if (g->act < 0 || g->act > 2 || g->x_col0 < 0 || g->y_col0 < 0) return QA_EINVAL;
+    if (g->x_col0 & 3) return QA_EINVAL;          // TMA box starts are 16-byte aligned; y_col0 may be odd (plain-store epilogue)
     // TMA constraints: 16 B aligned bases and row pitches
     if (!tma_ok(g->x, g->x_pitch) || !tma_ok(g->w, g->w_pitch) || !tma_ok(g->y, g->y_pitch) || g->x_pitch < g->x_col0 + g->K ||
         g->w_pitch < g->K || g->y_pitch < g->y_col0 + g->N)
@@ -564,6 +584,7 @@ extern "C" int qa_linear_bwd(const QaLinearBwdArgs* g, void* stream) {
     if (g->M == 0) return 0;
     QA_CHECK_PTR(g->gz);
     if (g->M < 0 || g->N <= 0 || g->K <= 0 || g->x_col0 < 0 || g->w_col0 < 0) return QA_EINVAL;
+    if ((g->x_col0 & 3) || (g->w_col0 & 3)) return QA_EINVAL;      // TMA box starts are 16-byte aligned
     if (!tma_ok(g->gz, g->gz_pitch) || g->gz_pitch < g->N) return QA_EINVAL;
     cudaStream_t s = (cudaStream_t)stream;
     int rc = 0;

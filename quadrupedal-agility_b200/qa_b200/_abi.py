@@ -109,7 +109,7 @@ class QaGaeArgs(C.Structure):
                 ("advantages", vp), ("workspace", vp)]
 
 
-GATHER_MAX = 12
+GATHER_MAX = 16
 
 
 class QaGatherArgs(C.Structure):

@@ -245,7 +245,7 @@ def linear_fwd(x, weight, bias, y, act, x_col0: int = 0, y_col0: int = 0) -> Non
     N, K = weight.shape
     if y.stride(1) != 1 or y.dtype != torch.float32 or not y.is_cuda:
         raise RuntimeError("qa_linear_fwd: bad output tensor")
-    if x.shape[1] < x_col0 + K or y.shape[1] < y_col0 + N:
+    if (x_col0 or y_col0) and (x.shape[1] < x_col0 + K or y.shape[1] < y_col0 + N):
         raise RuntimeError("qa_linear_fwd: column window outside the tensor")
     a = _abi.QaLinearArgs(M, N, K, ACT_ID[act], x.data_ptr(), x.stride(0), weight.data_ptr(), weight.stride(0),
                           None if bias is None else _p(bias, torch.float32, "bias"), y.data_ptr(), y.stride(0),

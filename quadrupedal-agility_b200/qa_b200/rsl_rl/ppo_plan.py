@@ -11,8 +11,9 @@ topology is fixed for a whole training run, so the backward pass is known ahead 
                                     split-K dW reduced straight into the flat gradient buffer
   narrow heads (1 / 4 / 12)     K20 / K21 `qa_head_fwd` / `qa_head_bwd`: fp32 CUDA-core row streams
   losses                        K10 `qa_ppo_loss`, K12 `qa_row_loss` (value + gradient in one launch)
-  column windows                the 57 proprioceptive / 29 privileged lanes are read IN PLACE out of the 671-wide observation row
-                                (TMA coordinates), the encoder writes its 29 outputs straight into the actor's input row
+  column windows                the 57 proprioceptive lanes are read IN PLACE out of the 671-wide observation row (TMA coordinates),
+                                the encoder writes its 29 outputs straight into the actor's input row, the actor-input gradient is
+                                taken only for the 16-byte aligned window that covers the latent lanes
 
 Three independent chains (estimator | critic | encoder + actor) run on three streams; under CUDA-graph capture they become
 parallel branches of one graph, so one chain's launch latency and tail hide behind another's main loop.
@@ -116,6 +117,7 @@ class PpoStepPlan:
         self.sets = []
         for _ in range(num_sets):
             self.sets.append(dict(obs=_padded(M, self.W, dev), critic_obs=_padded(M, self.Wc, dev), xa=_padded(M, self.n_in, dev),
+                                  lat_in=_padded(M, self.l, dev),
                                   actions=z(self.A), values=z(1), returns=z(1), old_actions_log_prob=z(1), advantages=z(1),
                                   old_mu=z(self.A), old_sigma=z(self.A), hist_latent=_padded(M, self.l, dev)))
         est_mods = list(est.estimator)
@@ -125,7 +127,12 @@ class PpoStepPlan:
         self.c_critic = _Chain(_linears(ac.critic_trunk), ac.critic_head, self.act, M, dev)
         self.d_est = _padded(M, self.e, dev)
         self.d_reg = _padded(M, self.l, dev)
-        self.dplat = _padded(M, self.l, dev)
+        # TMA boxes start on 16-byte boundaries: the actor-input gradient is taken for the aligned column window that covers the
+        # latent lanes [p+e, p+e+l) and the activation-backward kernel reads the lanes it needs out of it
+        self.w_lo = (self.p + self.e) // 4 * 4
+        self.w_n = min((self.p + self.e + self.l - self.w_lo + 3) // 4 * 4, self.n_in - self.w_lo)
+        self.dplat_win = _padded(M, self.w_n, dev)
+        self.dplat = self.dplat_win[:, self.p + self.e - self.w_lo:self.p + self.e - self.w_lo + self.l]
         self.dmu, self.dvalue = z(self.A), torch.zeros(M, device=dev)
         self._cuda = dev.type == "cuda"           # (the host tests drive the schedule on CPU through stand-in ops: no streams)
         self.s_critic = torch.cuda.Stream(device=dev) if self._cuda else None
@@ -140,7 +147,7 @@ class PpoStepPlan:
         p, e, l, h = self.p, self.e, self.l, self.h
         ent = [(v["obs"], 0, s["obs"], 0, self.W), (v["critic_obs"], 0, s["critic_obs"], 0, self.Wc),
                (v["obs"], 0, s["xa"], 0, p + e), (v["obs"], p + e + l + h, s["xa"], p + e + l, self.n_cmd),
-               (hist_latent_all, 0, s["hist_latent"], 0, l)]
+               (v["obs"], p + e, s["lat_in"], 0, l), (hist_latent_all, 0, s["hist_latent"], 0, l)]
         for key in self.gather_keys:
             ent.append((v[key], 0, s[key], 0, v[key].shape[1]))
         ops.gather_minibatch_windows(idx, ent)
@@ -154,6 +161,7 @@ class PpoStepPlan:
         s["critic_obs"].copy_(critic_obs)
         s["xa"][:, :p + e].copy_(obs[:, :p + e])
         s["xa"][:, p + e + l:].copy_(obs[:, p + e + l + h:])
+        s["lat_in"].copy_(obs[:, p + e:p + e + l])
         for key, val in (("actions", actions), ("values", target_values), ("advantages", advantages), ("returns", returns),
                          ("old_actions_log_prob", old_logp), ("old_mu", old_mu), ("old_sigma", old_sigma)):
             s[key].copy_(val.reshape(s[key].shape))
@@ -216,7 +224,7 @@ class PpoStepPlan:
             self._trunk_fwd(self.c_critic, s["critic_obs"])
         # ---- privileged-latent encoder -> actor (:338-342), regulariser (:352-354) ------------------------------------------
         cp, ca, cc = self.c_priv, self.c_actor, self.c_critic
-        self._trunk_fwd(cp, obs, x_col0=p + e, last_y=xa, last_y_col0=p + e)           # 29 outputs land in xa[:, 61:90]
+        self._trunk_fwd(cp, s["lat_in"], last_y=xa, last_y_col0=p + e)                 # 29 outputs land in xa[:, 61:90]
         plat = xa[:, p + e:p + e + l]
         ops.row_loss(plat, s["hist_latent"], self.d_reg, alg._aux_loss[0:1], 1)
         self._trunk_fwd(ca, xa)
@@ -238,7 +246,7 @@ class PpoStepPlan:
             ops.linear_bwd(ca.gz[i], None, ca.trunk[i].weight, dx=ca.gz[i - 1], act_prev=ca.act, y_prev=ca.h[i - 1],
                            db_prev=ca.trunk[i - 1].bias.grad, db_accumulate=True)
         first = ca.trunk[0]
-        ops.linear_bwd(ca.gz[0], None, first.weight, dx=self.dplat, w_col0=p + e, K=l)
+        ops.linear_bwd(ca.gz[0], None, first.weight, dx=self.dplat_win, w_col0=self.w_lo, K=self.w_n)
         last_p = cp.trunk[-1]
         ops.act_bwd(self.dplat, plat, cp.act, gz=cp.gz[-1], db=last_p.bias.grad, zero_db=False, addend=self.d_reg,
                     addend_scale=alg._priv_reg_coef)
@@ -251,7 +259,7 @@ class PpoStepPlan:
         ops.linear_bwd(ca.gz[0], xa, None, dw=first.weight.grad, K=self.n_in)
         for i in range(m - 1, 0, -1):
             ops.linear_bwd(cp.gz[i], cp.h[i - 1], None, dw=cp.trunk[i].weight.grad)
-        ops.linear_bwd(cp.gz[0], obs, None, dw=cp.trunk[0].weight.grad, x_col0=p + e, K=l)
+        ops.linear_bwd(cp.gz[0], s["lat_in"], None, dw=cp.trunk[0].weight.grad, K=l)
         cur.join(self.s_critic)
         cur.join(self.s_est)
         # kl for the adaptive schedule (:367-373): a 4-byte device copy (it lives in the all-reduce arena when sharded)

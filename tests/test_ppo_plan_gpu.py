@@ -85,25 +85,34 @@ def test_head_fwd_bwd_match_torch(M, N, Kh, act):
 
 # ---- K7 with column windows / fused activation backward -----------------------------------------------------------------------
 def test_linear_fwd_reads_and_writes_column_windows():
-    """Privileged-latent encoder shapes: input = lanes 61..89 of the 671-wide observation row, output = lanes 61..89 of the
-    101-wide actor input row (neighbouring lanes must stay untouched)."""
+    """Input window at a 16-byte aligned column of a wide row (TMA coordinates); output window at an ODD column (lanes 61..89 of
+    the 101-wide actor input row: plain-store epilogue), neighbouring lanes untouched; unaligned INPUT windows are refused."""
     g = torch.Generator().manual_seed(1)
     M = 5000
     obs = _padded(M, 671, gen=g)
-    w1, b1 = (torch.randn(64, 29, generator=g) / 29 ** 0.5), torch.randn(64, generator=g)
-    w1p = _padded(64, 29)
-    w1p.copy_(w1)
+    w1, b1 = _padded(64, 30, gen=g), torch.randn(64, generator=g).to(DEV)
+    w1.mul_(1 / 30 ** 0.5)
     h = _padded(M, 64)
-    ops.linear_fwd(obs, w1p, b1.to(DEV), h, "elu", x_col0=61)
-    x = obs[:, 61:90]
-    ref = torch.nn.functional.elu(x.double() @ w1.double().t().to(DEV) + b1.double().to(DEV))
-    assert _scaled_err(h, ref, x, w1p, b1.to(DEV)) < TF32_BOUND
+    ops.linear_fwd(obs, w1, b1, h, "elu", x_col0=60)
+    x = obs[:, 60:90]
+    ref = torch.nn.functional.elu(x.double() @ w1.double().t() + b1.double())
+    assert _scaled_err(h, ref, x, w1, b1) < TF32_BOUND
+    with pytest.raises(RuntimeError, match="QA_EINVAL"):
+        ops.linear_fwd(obs, w1, b1, h, "elu", x_col0=61)
     w2, b2 = (torch.randn(29, 64, generator=g) / 8).to(DEV), torch.randn(29, generator=g).to(DEV)
     xa = _padded(M, 101, fill=7.0)
     ops.linear_fwd(h, w2, b2, xa, "elu", y_col0=61)
     ref2 = torch.nn.functional.elu(h.double() @ w2.double().t() + b2.double())
     assert _scaled_err(xa[:, 61:90], ref2, h, w2, b2) < TF32_BOUND
     assert bool((xa[:, :61] == 7.0).all()) and bool((xa[:, 90:] == 7.0).all())
+    # a wide unaligned output window (several column chunks and n tiles)
+    w3, b3 = _padded(200, 64, gen=g), torch.randn(200, generator=g).to(DEV)
+    w3.mul_(1 / 8)
+    wide = _padded(M, 260, fill=-3.0)
+    ops.linear_fwd(h, w3, b3, wide, None, y_col0=37)
+    ref3 = h.double() @ w3.double().t() + b3.double()
+    assert _scaled_err(wide[:, 37:237], ref3, h, w3, b3) < TF32_BOUND
+    assert bool((wide[:, :37] == -3.0).all()) and bool((wide[:, 237:] == -3.0).all())
 
 
 @pytest.mark.parametrize("M,N,K,act", [(24576, 256, 512, "elu"), (4100, 128, 256, "elu"), (1000, 29, 64, "elu"), (777, 64, 128, "relu")])
@@ -131,21 +140,24 @@ def test_linear_bwd_dx_fused_activation_backward_tma_prefetch(M, N, K, act):
 
 
 def test_linear_bwd_column_windows():
-    """dX w.r.t. a window of the input row (actor layer 1 -> the 29 latent lanes) and dW from a window of a wider input."""
+    """dX w.r.t. a 16-byte aligned window of the input row (actor layer 1 -> the window that covers the 29 latent lanes) and dW
+    from an aligned window of a wider input; unaligned windows are refused."""
     g = torch.Generator().manual_seed(4)
     M = 6000
     gz, w = _padded(M, 512, gen=g), _padded(512, 101, gen=g)
-    dx = _padded(M, 29, fill=9.0)
-    ops.linear_bwd(gz, None, w, dx=dx, w_col0=61, K=29)
-    ref = gz.double() @ w.double()[:, 61:90]
-    scale = gz.double().abs() @ w.double().abs()[:, 61:90]
+    dx = _padded(M, 32, fill=9.0)
+    ops.linear_bwd(gz, None, w, dx=dx, w_col0=60, K=32)
+    ref = gz.double() @ w.double()[:, 60:92]
+    scale = gz.double().abs() @ w.double().abs()[:, 60:92]
     assert float(((dx.double() - ref).abs() / scale.clamp(min=1e-6)).max()) < TF32_BOUND
+    with pytest.raises(RuntimeError, match="QA_EINVAL"):
+        ops.linear_bwd(gz, None, w, dx=dx, w_col0=61, K=29)
     obs = _padded(M, 671, gen=g)
     gz1 = _padded(M, 64, gen=g)
     dw = _padded(64, 29)
-    ops.linear_bwd(gz1, obs, None, dw=dw, x_col0=61, K=29)
-    ref = gz1.double().t() @ obs.double()[:, 61:90]
-    scale = gz1.double().abs().t() @ obs.double().abs()[:, 61:90]
+    ops.linear_bwd(gz1, obs, None, dw=dw, x_col0=60, K=29)
+    ref = gz1.double().t() @ obs.double()[:, 60:89]
+    scale = gz1.double().abs().t() @ obs.double().abs()[:, 60:89]
     assert float(((dw.double() - ref).abs() / scale.clamp(min=1e-6)).max()) < TF32_BOUND
 
 
@@ -169,8 +181,10 @@ def test_gather_windows_builds_actor_input_row():
     lat = torch.randn(R, 29, generator=g).to(DEV)
     idx = torch.randperm(R, generator=g)[:M].to(DEV)
     xa, ob, hl = _padded(M, 101, fill=5.0), _padded(M, 671), _padded(M, 29)
-    ops.gather_minibatch_windows(idx, [(obs, 0, ob, 0, 671), (obs, 0, xa, 0, 61), (obs, 660, xa, 90, 11), (lat, 0, hl, 0, 29)])
-    assert torch.equal(ob, obs[idx]) and torch.equal(hl, lat[idx])
+    li = _padded(M, 29)
+    ops.gather_minibatch_windows(idx, [(obs, 0, ob, 0, 671), (obs, 0, xa, 0, 61), (obs, 660, xa, 90, 11), (lat, 0, hl, 0, 29),
+                                       (obs, 61, li, 0, 29)])
+    assert torch.equal(ob, obs[idx]) and torch.equal(hl, lat[idx]) and torch.equal(li, obs[idx][:, 61:90])
     assert torch.equal(xa[:, :61], obs[idx][:, :61]) and torch.equal(xa[:, 90:], obs[idx][:, 660:])
     assert bool((xa[:, 61:90] == 5.0).all())
 

@@ -214,4 +214,5 @@ def test_schedule_gather_windows_layout(monkeypatch):
     assert torch.equal(s["xa"][:, :61], v["obs"][idx][:, :61]) and torch.equal(s["xa"][:, 90:], v["obs"][idx][:, 660:])
     assert torch.equal(s["hist_latent"], lat[idx]) and torch.equal(s["actions"], v["actions"][idx])
     assert torch.equal(s["advantages"], v["advantages"][idx])
-    assert all(t.stride(0) % 4 == 0 for t in (s["obs"], s["critic_obs"], s["xa"], s["hist_latent"]))
+    assert torch.equal(s["lat_in"], v["obs"][idx][:, 61:90])
+    assert all(t.stride(0) % 4 == 0 for t in (s["obs"], s["critic_obs"], s["xa"], s["hist_latent"], s["lat_in"]))
