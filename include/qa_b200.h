@@ -51,7 +51,7 @@ int qa_version(void);
 /* human readable build string ("sm_100a, nvcc 12.9, ...") */
 const char* qa_build_info(void);
 /* sizeof() of argument struct number `which` (order of declaration in this header, QaActionPushArgs
- * = 0 ... QaGaeArgs = 9, QaGatherArgs = 10, QaClipAdamArgs = 11, QaLinearArgs = 12, QaActBwdArgs = 13, QaPpoLossArgs = 14, QaLinearBwdArgs = 15, QaHistEncArgs = 16, QaRowLossArgs = 17, QaPpoScalarsArgs = 18, QaDepthArgs = 19, QaPpoLossTscArgs = 20, QaTscConst = 21, QaTscStepArgs = 22, QaDiscInputArgs = 23, QaDiscRewardArgs = 24, QaHeadFwdArgs = 25, QaHeadBwdArgs = 26; -1 if unknown): a layout handshake for FFI mirrors of these structs */
+ * = 0 ... QaGaeArgs = 9, QaGatherArgs = 10, QaClipAdamArgs = 11, QaLinearArgs = 12, QaActBwdArgs = 13, QaPpoLossArgs = 14, QaLinearBwdArgs = 15, QaHistEncArgs = 16, QaRowLossArgs = 17, QaPpoScalarsArgs = 18, QaDepthArgs = 19, QaPpoLossTscArgs = 20, QaTscConst = 21, QaTscStepArgs = 22, QaDiscInputArgs = 23, QaDiscRewardArgs = 24, QaHeadFwdArgs = 25, QaHeadBwdArgs = 26, QaPolicySampleArgs = 27; -1 if unknown): a layout handshake for FFI mirrors of these structs */
 int qa_struct_size(int which);
 /* stream-ordered fill-with-zero / device-to-device copy of `bytes` bytes (cudaMemsetAsync / cudaMemcpyAsync): lets a captured
  * training step zero its flat gradient buffer (optimizer.zero_grad(), gail.py:361, :409) and move device scalars without a
@@ -453,7 +453,8 @@ int qa_act_bwd(const QaActBwdArgs* a, void* stream);
 /* ------------------------------------------------------------------------------------------
  * K20 / K21  narrow output layers (N <= 16 columns) on the CUDA cores, full fp32 -- actor_head Linear(128,12) and critic_head
  *     Linear(128,1) (bbc/rsl_rl/modules/actor_critic.py:118-119, 128-129), the estimator's last Linear(64,4)
- *     (modules/estimator.py:24-33).  Kh in {32, 64, 128}; h: 16 B aligned base, pitch % 4 == 0.
+ *     (modules/estimator.py:24-33), the discriminator's three heads as one (7,256) matrix (algorithms/discriminator.py:42-46).
+ *     Kh in {32, 64, 128} (forward also 256); h: 16 B aligned base, pitch % 4 == 0.
  *     qa_head_fwd:  y = h W^T + b
  *     qa_head_bwd:  gz_prev = ((gz_scale * gz) W) * act'(h)  [act = activation that PRODUCED h: 0 none, 1 ELU, 2 ReLU],
  *                   dw += (gz_scale * gz)^T h, db += colsum(gz_scale * gz), db_prev += colsum(gz_prev)   (all ACCUMULATED)
@@ -482,6 +483,30 @@ typedef struct QaHeadBwdArgs {
     float* db_prev;                     /* (Kh) accumulated, may be NULL */
 } QaHeadBwdArgs;
 int qa_head_bwd(const QaHeadBwdArgs* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K22 policy sample -- Normal(mean, std).sample() + log_prob(actions).sum(-1) + the transition's storage writes of
+ *     SSInfoGAIL.act, bbc/rsl_rl/algorithms/gail.py:186-196 (modules/actor_critic.py:189-197), one launch.
+ *     noise != NULL: actions = mu + std * noise (parity mode, the reference draws from torch's generator);
+ *     noise == NULL: standard normals from Philox4x32-10 keyed by (rng_seed; env, site, step) + Box-Muller, where step =
+ *     *step_state + 1 when step_state != NULL (device-resident env step counter, CUDA-graph replay) else rng_step.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct QaPolicySampleArgs {
+    int64_t M;
+    int32_t A;                          /* action dims (12) */
+    const float* mu; int64_t mu_pitch;  /* (M,A) */
+    const float* std;                   /* (A) */
+    const float* noise;                 /* (M,A) or NULL */
+    uint64_t rng_seed, rng_step;
+    const int64_t* step_state;          /* (1) or NULL */
+    float* actions;                     /* (M,A) out: what env.step() receives */
+    float* logp;                        /* (M) out or NULL */
+    float* actions_st;                  /* (M,A) storage.actions[t] or NULL */
+    float* logp_st;                     /* (M) storage.actions_log_prob[t] or NULL */
+    float* mu_st;                       /* (M,A) storage.mu[t] or NULL */
+    float* sigma_st;                    /* (M,A) storage.sigma[t] or NULL */
+} QaPolicySampleArgs;
+int qa_policy_sample(const QaPolicySampleArgs* a, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * K10 PPO loss forward + backward -- replaces the element-wise graph of SSInfoGAIL.update_actor_critic,

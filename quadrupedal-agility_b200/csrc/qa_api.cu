@@ -42,6 +42,7 @@ extern "C" int qa_struct_size(int which) {
         case 24: return (int)sizeof(QaDiscRewardArgs);
         case 25: return (int)sizeof(QaHeadFwdArgs);
         case 26: return (int)sizeof(QaHeadBwdArgs);
+        case 27: return (int)sizeof(QaPolicySampleArgs);
         default: return -1;
     }
 }

@@ -18,9 +18,12 @@
 
 #define HD_THREADS 256
 #define HD_MAXN 16
-#define HD_MAXK 128
+#define HD_MAXK 256
 
-template <int NT>
+// Forward.  lanes-per-row = min(32, Kh / 4); a lane owns KV = Kh / (4 * lpr) float4 column groups (2 for Kh = 256).  Each warp
+// pass handles 4 * (32 / lpr) rows: the 4 row loads of a lane are issued back to back (memory-level parallelism: the kernel
+// is a pure stream over h), then each row's NT partial dot products are summed across its lanes by xor butterflies.
+template <int NT, int KV>
 __global__ void __launch_bounds__(HD_THREADS) k_head_fwd(const __grid_constant__ QaHeadFwdArgs a) {
     __shared__ __align__(16) float s_w[NT * HD_MAXK];
     __shared__ float s_b[NT];
@@ -31,30 +34,57 @@ __global__ void __launch_bounds__(HD_THREADS) k_head_fwd(const __grid_constant__
     }
     if (threadIdx.x < NT) s_b[threadIdx.x] = (threadIdx.x < N && a.bias != nullptr) ? __ldg(a.bias + threadIdx.x) : 0.f;
     __syncthreads();
-    const int lpr = Kh >> 2;                       // lanes per row: 32 (Kh = 128), 16 (64), 8 (32)
-    const int rpp = 32 / lpr;                      // rows per warp pass
+    const int lpr = (Kh >> 2) / KV;                // lanes per row: 32 (Kh = 128 or 256), 16 (64), 8 (32)
+    const int rpp = 32 / lpr;                      // rows per lane group pass
+    constexpr int U = 4;                           // rows in flight per lane
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane % lpr, rsel = lane / lpr;
     const long long warps_total = (long long)gridDim.x * (HD_THREADS / 32);
-    for (long long r0 = ((long long)blockIdx.x * (HD_THREADS / 32) + warp) * rpp; r0 < a.M; r0 += warps_total * rpp) {
-        const long long r = r0 + rsel;
-        float4 h4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < a.M) h4 = *reinterpret_cast<const float4*>(a.h + r * a.h_pitch + sub * 4);
-        float p[NT];
+    const long long stride = warps_total * rpp * U;
+    for (long long r0 = ((long long)blockIdx.x * (HD_THREADS / 32) + warp) * rpp * U; r0 < a.M; r0 += stride) {
+        float4 h4[U][KV];
 #pragma unroll
-        for (int n = 0; n < NT; ++n) {
-            const float4 w4 = *reinterpret_cast<const float4*>(s_w + n * Kh + sub * 4);
-            p[n] = h4.x * w4.x + h4.y * w4.y + h4.z * w4.z + h4.w * w4.w;
+        for (int u = 0; u < U; ++u) {
+            const long long r = r0 + u * rpp + rsel;
+#pragma unroll
+            for (int v = 0; v < KV; ++v)
+                h4[u][v] = r < a.M ? *reinterpret_cast<const float4*>(a.h + r * a.h_pitch + (v * lpr + sub) * 4)
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
-        for (int n = 0; n < NT; ++n)
-            for (int o = lpr >> 1; o > 0; o >>= 1) p[n] += __shfl_xor_sync(QA_FULL, p[n], o);
-        if (r < a.M) {
+        for (int u = 0; u < U; ++u) {
+            const long long r = r0 + u * rpp + rsel;
+            float p[NT];
+#pragma unroll
+            for (int n = 0; n < NT; ++n) {
+                float acc = 0.f;
+#pragma unroll
+                for (int v = 0; v < KV; ++v) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(s_w + n * Kh + (v * lpr + sub) * 4);
+                    acc += h4[u][v].x * w4.x + h4[u][v].y * w4.y + h4[u][v].z * w4.z + h4[u][v].w * w4.w;
+                }
+                p[n] = acc;
+            }
 #pragma unroll
             for (int n = 0; n < NT; ++n)
-                if (n < N && (n % lpr) == sub) a.y[r * a.y_pitch + n] = p[n] + s_b[n];
+                for (int o = lpr >> 1; o > 0; o >>= 1) p[n] += __shfl_xor_sync(QA_FULL, p[n], o);
+            if (r < a.M) {
+#pragma unroll
+                for (int n = 0; n < NT; ++n)
+                    if (n < N && (n % lpr) == sub) a.y[r * a.y_pitch + n] = p[n] + s_b[n];
+            }
         }
     }
+}
+
+template <int NT>
+static void launch_head_fwd(const QaHeadFwdArgs* a, cudaStream_t s) {
+    const int kv = a->Kh == 256 ? 2 : 1;
+    const int rpp = 32 / ((a->Kh >> 2) / kv);
+    long long blocks = (a->M + 8LL * rpp * 4 - 1) / (8LL * rpp * 4);
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    if (kv == 2) k_head_fwd<NT, 2><<<(unsigned)blocks, HD_THREADS, 0, s>>>(*a);
+    else k_head_fwd<NT, 1><<<(unsigned)blocks, HD_THREADS, 0, s>>>(*a);
 }
 
 extern "C" int qa_head_fwd(const QaHeadFwdArgs* a, void* stream) {
@@ -64,16 +94,14 @@ extern "C" int qa_head_fwd(const QaHeadFwdArgs* a, void* stream) {
     QA_CHECK_PTR(a->w);
     QA_CHECK_PTR(a->y);
     if (a->M < 0 || a->N <= 0 || a->N > HD_MAXN) return QA_EINVAL;
-    if (a->Kh != 32 && a->Kh != 64 && a->Kh != 128) return QA_EINVAL;
+    if (a->Kh != 32 && a->Kh != 64 && a->Kh != 128 && a->Kh != 256) return QA_EINVAL;
     if ((reinterpret_cast<uintptr_t>(a->h) & 15u) || (a->h_pitch & 3) || a->h_pitch < a->Kh || a->w_pitch < a->Kh || a->y_pitch < a->N)
         return QA_EINVAL;
-    const int rpp = 32 / (a->Kh >> 2);
-    long long blocks = (a->M + 8LL * rpp - 1) / (8LL * rpp);
-    if (blocks > 148 * 4) blocks = 148 * 4;
     cudaStream_t s = (cudaStream_t)stream;
-    if (a->N == 1) k_head_fwd<1><<<(unsigned)blocks, HD_THREADS, 0, s>>>(*a);
-    else if (a->N <= 4) k_head_fwd<4><<<(unsigned)blocks, HD_THREADS, 0, s>>>(*a);
-    else k_head_fwd<16><<<(unsigned)blocks, HD_THREADS, 0, s>>>(*a);
+    if (a->N == 1) launch_head_fwd<1>(a, s);
+    else if (a->N <= 4) launch_head_fwd<4>(a, s);
+    else if (a->N <= 8) launch_head_fwd<8>(a, s);
+    else launch_head_fwd<16>(a, s);
     QA_LAUNCH_RET();
 }
 
@@ -81,9 +109,9 @@ extern "C" int qa_head_fwd(const QaHeadFwdArgs* a, void* stream) {
 // (shared atomics) and leaves with one global atomicAdd per element.
 template <int NT>
 __global__ void __launch_bounds__(HD_THREADS) k_head_bwd(const __grid_constant__ QaHeadBwdArgs a) {
-    __shared__ __align__(16) float s_w[NT * HD_MAXK];
-    __shared__ __align__(16) float s_dw[NT * HD_MAXK];
-    __shared__ float s_dbp[HD_MAXK];
+    __shared__ __align__(16) float s_w[NT * 128];
+    __shared__ __align__(16) float s_dw[NT * 128];
+    __shared__ float s_dbp[128];
     __shared__ float s_db[NT];
     const int Kh = a.Kh, N = a.N;
     for (int i = threadIdx.x; i < NT * Kh; i += HD_THREADS) {
@@ -169,5 +197,71 @@ extern "C" int qa_head_bwd(const QaHeadBwdArgs* a, void* stream) {
     if (a->N == 1) k_head_bwd<1><<<(unsigned)blocks, HD_THREADS, 0, s>>>(*a);
     else if (a->N <= 4) k_head_bwd<4><<<(unsigned)blocks, HD_THREADS, 0, s>>>(*a);
     else k_head_bwd<16><<<(unsigned)blocks, HD_THREADS, 0, s>>>(*a);
+    QA_LAUNCH_RET();
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------------
+// K22 qa_policy_sample -- `Normal(mean, std).sample()`, `log_prob(actions).sum(-1)` and the transition's storage writes of
+//     SSInfoGAIL.act (bbc/rsl_rl/algorithms/gail.py:186-196, modules/actor_critic.py:189-197) in one launch:
+//       actions = mu + std * n,  logp = sum_j -(a_j - mu_j)^2 / (2 std_j^2) - log std_j - log sqrt(2 pi)
+//     n is either supplied (parity mode: the reference consumes torch's generator) or drawn in-kernel: Philox4x32-10 keyed by
+//     (seed; env, site, step) + Box-Muller, the same counter layout as the env kernels' production stream.
+// ------------------------------------------------------------------------------------------------------------------------
+#define SITE_ACT0 48
+__global__ void __launch_bounds__(256) k_policy_sample(const __grid_constant__ QaPolicySampleArgs a) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.M) return;
+    const int A = a.A;
+    unsigned long long step = a.rng_step;
+    if (a.step_state != nullptr) step = (unsigned long long)(*reinterpret_cast<const volatile long long*>(a.step_state)) + 1ull;
+    float logp = 0.f;
+    for (int j0 = 0; j0 < A; j0 += 4) {
+        float n4[4];
+        if (a.noise != nullptr) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) n4[e] = j0 + e < A ? a.noise[i * A + j0 + e] : 0.f;
+        } else {
+            const Philox4 r = philox4x32_10((uint32_t)i, SITE_ACT0 + (j0 >> 2), (uint32_t)step, (uint32_t)(step >> 32),
+                                            (uint32_t)a.rng_seed, (uint32_t)(a.rng_seed >> 32));
+            // Box-Muller on (0, 1] uniforms: two pairs -> four standard normals
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const float u1 = ((float)(r.v[2 * e] >> 8) + 1.0f) * (1.0f / 16777216.0f);
+                const float u2 = (float)(r.v[2 * e + 1] >> 8) * (1.0f / 16777216.0f);
+                const float rad = sqrtf(-2.0f * logf(u1));
+                float sn, cs;
+                sincospif(2.0f * u2, &sn, &cs);
+                n4[2 * e] = rad * cs;
+                n4[2 * e + 1] = rad * sn;
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int j = j0 + e;
+            if (j < A) {
+                const float mu = a.mu[i * a.mu_pitch + j], sd = a.std[j];
+                const float act = mu + sd * n4[e];
+                const float d = act - mu;
+                logp += -(d * d) / (2.f * (sd * sd)) - logf(sd) - 0.9189385332046727f;
+                a.actions[i * A + j] = act;
+                if (a.actions_st != nullptr) a.actions_st[i * A + j] = act;
+                if (a.mu_st != nullptr) a.mu_st[i * A + j] = mu;
+                if (a.sigma_st != nullptr) a.sigma_st[i * A + j] = sd;
+            }
+        }
+    }
+    if (a.logp != nullptr) a.logp[i] = logp;
+    if (a.logp_st != nullptr) a.logp_st[i] = logp;
+}
+
+extern "C" int qa_policy_sample(const QaPolicySampleArgs* a, void* stream) {
+    QA_CHECK_PTR(a);
+    if (a->M == 0) return 0;
+    QA_CHECK_PTR(a->mu);
+    QA_CHECK_PTR(a->std);
+    QA_CHECK_PTR(a->actions);
+    if (a->M < 0 || a->A <= 0 || a->A > 64 || a->mu_pitch < a->A) return QA_EINVAL;
+    k_policy_sample<<<(unsigned)((a->M + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*a);
     QA_LAUNCH_RET();
 }

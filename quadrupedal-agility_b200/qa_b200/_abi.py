@@ -142,6 +142,12 @@ class QaHeadFwdArgs(C.Structure):
                 ("w_pitch", C.c_int64), ("bias", vp), ("y", vp), ("y_pitch", C.c_int64)]
 
 
+class QaPolicySampleArgs(C.Structure):
+    _fields_ = [("M", C.c_int64), ("A", C.c_int32), ("mu", vp), ("mu_pitch", C.c_int64), ("std", vp), ("noise", vp),
+                ("rng_seed", C.c_uint64), ("rng_step", C.c_uint64), ("step_state", vp), ("actions", vp), ("logp", vp),
+                ("actions_st", vp), ("logp_st", vp), ("mu_st", vp), ("sigma_st", vp)]
+
+
 class QaHeadBwdArgs(C.Structure):
     _fields_ = [("M", C.c_int64), ("N", C.c_int32), ("Kh", C.c_int32), ("act", C.c_int32), ("gz_scale", C.c_float),
                 ("gz", vp), ("gz_pitch", C.c_int64), ("h", vp), ("h_pitch", C.c_int64), ("w", vp), ("w_pitch", C.c_int64),
@@ -285,12 +291,13 @@ SYMBOLS = {
     "qa_copy_async": (C.c_int, [vp, vp, C.c_uint64, vp]),
     "qa_head_fwd": (C.c_int, [C.POINTER(QaHeadFwdArgs), vp]),
     "qa_head_bwd": (C.c_int, [C.POINTER(QaHeadBwdArgs), vp]),
+    "qa_policy_sample": (C.c_int, [C.POINTER(QaPolicySampleArgs), vp]),
 }
 
 STRUCT_ORDER = [QaActionPushArgs, QaTorqueArgs, QaTerrain, QaHeightScanArgs, QaMocapTable, QaMocapBlendArgs,
                 QaBbcConst, QaBbcStepArgs, QaCompactArgs, QaGaeArgs, QaGatherArgs, QaClipAdamArgs, QaLinearArgs, QaActBwdArgs, QaPpoLossArgs, QaLinearBwdArgs, QaHistEncArgs,
                 QaRowLossArgs, QaPpoScalarsArgs, QaDepthArgs, QaPpoLossTscArgs, QaTscConst, QaTscStepArgs,
-                QaDiscInputArgs, QaDiscRewardArgs, QaHeadFwdArgs, QaHeadBwdArgs]
+                QaDiscInputArgs, QaDiscRewardArgs, QaHeadFwdArgs, QaHeadBwdArgs, QaPolicySampleArgs]
 
 _LIB = None
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libqa_b200.so")

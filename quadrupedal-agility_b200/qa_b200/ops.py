@@ -350,6 +350,22 @@ def head_bwd(gz, h, weight, act, gz_prev=None, dw=None, db=None, db_prev=None, g
     _count(1)
 
 
+# ---- K22 ----------------------------------------------------------------------------------------
+def policy_sample(mu, std, actions, noise=None, rng_seed=0, rng_step=0, step_state=None, logp=None, actions_st=None, logp_st=None,
+                  mu_st=None, sigma_st=None) -> None:
+    """actions = mu + std * n and log_prob(actions).sum(-1) (gail.py:186-196) with the storage writes fused; `noise` = the
+    standard-normal draw in parity mode, else in-kernel Philox (keyed by seed / the device step counter)."""
+    lib = _abi.load()
+    f = torch.float32
+    a = _abi.QaPolicySampleArgs(mu.shape[0], mu.shape[1], _p_strided(mu, f, "mu"), mu.stride(0), _p(std, f, "std"),
+                                _p(noise, f, "noise"), int(rng_seed) & 0xFFFFFFFFFFFFFFFF, int(rng_step),
+                                _p(step_state, torch.int64, "step_state"), _p(actions, f, "actions"), _p(logp, f, "logp"),
+                                _p(actions_st, f, "actions_st"), _p(logp_st, f, "logp_st"), _p(mu_st, f, "mu_st"),
+                                _p(sigma_st, f, "sigma_st"))
+    _abi.check(lib.qa_policy_sample(C.byref(a), _stream()), "qa_policy_sample")
+    _count(1)
+
+
 # ---- K10 --------------------------------------------------------------------------------------
 def ppo_loss(mu, std, value, actions, old_logp, advantages, returns, target_values, old_mu, old_sigma, dmu, dvalue,
              dstd, stats, clip, c_surr, c_value, c_bound, c_entropy, use_clipped_value_loss) -> None:

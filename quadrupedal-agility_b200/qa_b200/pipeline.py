@@ -41,9 +41,11 @@ class BbcIteration:
         # pinned host copies of the simulator tensors (run_host) and device-resident snapshots (run_resident)
         self.host_snaps = [{k: s[k].contiguous().pin_memory() for k in SIM_KEYS} for s in snaps]
         self.dev_snaps = [{k: s[k].to(dev) for k in SIM_KEYS} for s in snaps]
-        self.staging = {k: torch.empty_like(self.dev_snaps[0][k]) for k in SIM_KEYS}
+        # run_host: two staging sets, so that the host->HBM copies of step t+1 (copy stream) overlap the kernels of step t
+        self.staging = [{k: torch.empty_like(self.dev_snaps[0][k]) for k in SIM_KEYS} for _ in range(2)]
         self.phys_resident = RecordedPhysics(self.dev_snaps)
-        self.phys_staged = RecordedPhysics([self.staging])
+        self.phys_staged = RecordedPhysics(self.staging)
+        self._copy_stream = torch.cuda.Stream(device=dev)
         self.env = LeggedRobot(cfg, self.phys_resident, static, table, device=dev, seed=seed, bulk_store=bulk_store, tiled=tiled)
         self.env.global_counter = 1
         torch.manual_seed(seed)
@@ -56,7 +58,7 @@ class BbcIteration:
         self.runner._disc_hist = torch.stack([self.env.get_disc_observations()] * 2, dim=1)
         self.result_host = torch.zeros(8).pin_memory()
         self.k2_traffic_bytes = None
-        self.h2d_bytes_per_iteration = T * sum(self.staging[k].numel() * self.staging[k].element_size() for k in SIM_KEYS)
+        self.h2d_bytes_per_iteration = T * sum(self.staging[0][k].numel() * self.staging[0][k].element_size() for k in SIM_KEYS)
         self.d2h_bytes_per_iteration = 4 * 8
         self._launch0 = ops.launches
         self._iters = 0
@@ -109,11 +111,30 @@ class BbcIteration:
         env, runner = self.env, self.runner
         env.physics = self.phys_staged if host else self.phys_resident
         with torch.no_grad():
+            if not host:
+                for t in range(self.T):
+                    self.obs, self.critic_obs = runner.rollout_step(self.obs, self.critic_obs)
+                return
+            # the physics backend's hand-over: pinned host -> HBM, double buffered on a copy stream (a parallel branch of the
+            # captured graph): step t's kernels wait for copy t, copy t+2 waits for step t's kernels (its staging set is free)
+            main, cs = torch.cuda.current_stream(), self._copy_stream
+            self.phys_staged.cursor = -1
+            cs.wait_stream(main)
+            freed = [None, None]
             for t in range(self.T):
-                if host:
-                    for k in SIM_KEYS:                           # the physics backend's hand-over: pinned host -> HBM
-                        self.staging[k].copy_(self.host_snaps[t][k], non_blocking=True)
+                b = t % 2
+                with torch.cuda.stream(cs):
+                    if freed[b] is not None:
+                        cs.wait_event(freed[b])
+                    for k in SIM_KEYS:
+                        self.staging[b][k].copy_(self.host_snaps[t][k], non_blocking=True)
+                    landed = torch.cuda.Event()
+                    landed.record(cs)
+                main.wait_event(landed)
                 self.obs, self.critic_obs = runner.rollout_step(self.obs, self.critic_obs)
+                freed[b] = torch.cuda.Event()
+                freed[b].record(main)
+            main.wait_stream(cs)
 
     def _capture_rollout(self, host: bool):
         """Captures the whole T-step rollout (every torch op and libqa_b200 launch of `rollout_step`, and in host

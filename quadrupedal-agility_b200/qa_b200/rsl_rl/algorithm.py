@@ -595,6 +595,12 @@ class SSInfoGAIL:
         return (ss_loss.detach(), info_max_loss.detach(), disc_loss.detach(), us_loss.detach(), grad_pen_loss.detach(),
                 disc_logit_loss.detach(), disc_weight_decay.detach(), acc_lb, acc_pi, acc_exp, acc_ulb)
 
+    def notify_disc_changed(self):
+        """Discriminator parameters changed (update / checkpoint load): refresh the derived device copies (rollout_plan's stacked
+        head matrix)."""
+        for cb in getattr(self, "_disc_listeners", ()):
+            cb()
+
     def _disc_optim_step(self, grad_scale: float = 1.0):
         for o in self.optim_d + self.optim_q_eps + self.optim_q_c:               # :519-521
             o.step(grad_scale)
@@ -639,6 +645,7 @@ class SSInfoGAIL:
             qdist.allreduce_mean_scalar_(self._disc_stats)
         if hasattr(self.env, "refresh_prior"):                                  # the steps above moved env.prior_parameters
             self.env.refresh_prior()                                            # (:462-464): next rollout samples from it
+        self.notify_disc_changed()
         return tuple((self._disc_stats / n_mb).tolist())
 
     def _disc_step(self, expert, i_pi, i_lb, i_ulb):
@@ -752,7 +759,7 @@ class SSInfoGAIL:
     def _gather(self, idx):
         v = self.storage.flat_views()
         v["hist_latent"] = self._hist_latent_all
-        ops.gather_minibatch(idx, [v[k] for k in self._mb_keys], [self._mb[k] for k in self._mb_keys])
+        ops.gather_minibatch_windows(idx, [(v[k], 0, self._mb[k], 0, v[k].shape[1]) for k in self._mb_keys])
 
     @torch.no_grad()
     def _encode_history(self):

@@ -75,11 +75,42 @@ class OnPolicyRunner:
         return ExpertData.build(table, ulb, int(r["num_preload_transitions"]), env.dt, env.default_dof_pos, env.obs_scales,
                                 disc_obs_len=self.disc_obs_len, device=device, seed=int(r.get("seed", 0)))
 
+    def _ensure_rollout_plan(self):
+        """The static rollout schedule (rollout_plan) when it applies: CUDA, tcgen05 layers, MSE style reward, QA_ROLLOUT_PLAN != 0."""
+        from . import linear
+        from .rollout_plan import RolloutPlan
+        if getattr(self, "_rollout_plan_off", None) is None:
+            self._rollout_plan_off = os.environ.get("QA_ROLLOUT_PLAN", "1") != "1"
+        if self._rollout_plan_off or linear.get_mode() != "tc" or not hasattr(self.env, "_time_outs_latched"):
+            return None
+        plan = getattr(self, "_rollout_plan", None)
+        if plan is None:
+            if RolloutPlan.supported(self.alg) is not None:
+                self._rollout_plan_off = True
+                return None
+            plan = self._rollout_plan = RolloutPlan(self.alg, self.env, self.disc_obs_len, self.obs_disc_weight_step)
+            self.alg._disc_listeners = list(getattr(self.alg, "_disc_listeners", ())) + [plan.refresh_disc_heads]
+        return plan
+
     # ---- one rollout step (:156-181) ----------------------------------------------------------------------
     def _rollout_step_fused(self, obs, critic_obs, hist_encoding):
         """Same step with the disc-history bookkeeping, the normalisation, the reward tail and the time-out bootstrap in two
         kernels (K18, K19) around the discriminator GEMMs."""
         env, alg = self.env, self.alg
+        plan = self._ensure_rollout_plan()
+        if plan is not None:
+            actions = plan.act(obs, critic_obs, hist_encoding)
+            prev_disc = env.get_disc_observations()
+            next_obs, next_priv, rewards, dones, _ids, _cnt, _term = env.step_device(actions)
+            book = self.book
+            self._disc_hist = plan.reward(obs, rewards, dones, prev_disc, env.get_disc_observations(), self._disc_hist.contiguous(),
+                                          reward_terms=None if book is None else self._terms4)
+            if book is not None:
+                slot = book.term_slot()
+                slot[:, 1:].copy_(self._terms4)
+                slot[:, 0].copy_(self._terms4 @ self._reward_coefs)
+                book.record(dones, episode_means=env._episode_rew_means, num_resets=getattr(env, '_num_resets', None))
+            return next_obs, next_priv
         N, L, W = env.num_envs, self.disc_obs_len, env.num_obs_disc
         if self._hist_pp is None:
             dev = self.device
@@ -206,6 +237,7 @@ class OnPolicyRunner:
             self.alg.disc.reward_i_normalizer = d['reward_i_normalizer']
         if load_optimizer:
             self.alg.load_optimizer_state_dicts(d)
+        self.alg.notify_disc_changed()
         self.current_learning_iteration = d.get('iter', 0)
         return d.get('infos')
 

@@ -31,8 +31,12 @@ class RolloutStorage:
         self.obs_shape, self.privileged_obs_shape, self.actions_shape = obs_shape, privileged_obs_shape, actions_shape
         T, N = num_transitions_per_env, num_envs
         z = lambda *s, **k: torch.zeros(*s, device=device, **k)                # noqa: E731
-        self.observations = z(T, N, *obs_shape)
-        self.privileged_observations = z(T, N, *privileged_obs_shape) if privileged_obs_shape[0] is not None else None
+        # observation rows live at a 16-byte row pitch (671 -> 672 floats): every slot `observations[t]` is then a legal TMA
+        # operand, so the critic reads its input straight out of the storage slot and K6 gathers with a source pitch; the public
+        # tensors keep the reference's shapes (T, N, width) as views
+        rows = lambda shape: z(T, N, (shape[0] + 3) // 4 * 4)[..., :shape[0]] if len(shape) == 1 else z(T, N, *shape)   # noqa: E731
+        self.observations = rows(obs_shape)
+        self.privileged_observations = rows(privileged_obs_shape) if privileged_obs_shape[0] is not None else None
         self.rewards = z(T, N, 1)
         self.actions = z(T, N, *actions_shape)
         self.dones = z(T, N, 1, dtype=torch.uint8)
@@ -67,6 +71,10 @@ class RolloutStorage:
 
     def clear(self):
         self.step = 0
+
+    def advance(self):
+        """Close a transition whose fields were written straight into slot `step` by the producing kernels (rollout_plan)."""
+        self.step += 1
 
     def compute_returns(self, last_values, gamma, lam):
         """GAE + advantage normalisation (rollout_storage.py:97-111) through libqa_b200 (K5)."""

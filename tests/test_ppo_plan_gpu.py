@@ -339,3 +339,94 @@ def test_plan_update_full_size_in_cuda_graph_matches_oracle(tc_mode):
         assert abs(x - y) <= 1e-4 + 1e-3 * abs(y)         # split-K / atomic summation order differs between runs
     assert float((a0 - a1).abs().max()) <= 2.5e-3 and float(((a0 - a1).abs() < 1e-4).float().mean()) > 0.98
     assert float((e0 - e1).abs().max()) <= 2.5e-3
+
+
+# ---- rollout schedule -----------------------------------------------------------------------------------------------------
+def test_head_fwd_wide_input_for_the_discriminator_heads():
+    g = torch.Generator().manual_seed(9)
+    M, N, Kh = 4096, 7, 256
+    h = _padded(M, Kh, gen=g).clamp_(min=0)
+    w, b = (torch.randn(8, Kh, generator=g) / 16).to(DEV), torch.randn(8, generator=g).to(DEV)
+    y = torch.zeros(M, 8, device=DEV)
+    ops.head_fwd(h, w[:N], b[:N], y[:, :N])
+    assert_close("heads", y[:, :N], (h.double() @ w[:N].double().t() + b[:N].double()).float(), rtol=1e-5, atol=1e-5)
+    assert bool((y[:, N:] == 0).all())
+
+
+def test_policy_sample_kernel():
+    """K22 against Normal(mean, std).sample() / log_prob(.).sum(-1) with the draw injected (gail.py:186-196); the in-kernel Philox
+    stream is standard normal, a function of (seed, step, env) only, and advances with the device step counter."""
+    g = torch.Generator().manual_seed(3)
+    M, A = 4096, 12
+    mu, std = _padded(M, A, gen=g), (0.5 + torch.rand(A, generator=g)).to(DEV)
+    noise = torch.randn(M, A, generator=g).to(DEV)
+    out = {k: torch.zeros(M, A, device=DEV) for k in ("a", "a_st", "mu_st", "sg_st")}
+    lp, lp_st = torch.zeros(M, device=DEV), torch.zeros(M, device=DEV)
+    ops.policy_sample(mu, std, out["a"], noise=noise, logp=lp, actions_st=out["a_st"], logp_st=lp_st, mu_st=out["mu_st"], sigma_st=out["sg_st"])
+    dist = torch.distributions.Normal(mu, std.expand_as(mu))
+    want_a = mu + std * noise
+    assert_close("actions", out["a"], want_a, rtol=1e-6, atol=1e-6)
+    assert_close("log_prob", lp, dist.log_prob(want_a).sum(-1), rtol=1e-5, atol=1e-5)
+    assert torch.equal(out["a"], out["a_st"]) and torch.equal(lp, lp_st)
+    assert torch.equal(out["mu_st"], mu.contiguous()) and torch.equal(out["sg_st"], std.expand(M, A).contiguous())
+    state = torch.tensor([41], device=DEV, dtype=torch.int64)
+    draws = []
+    for s_ in (41, 41, 42):
+        state.fill_(s_)
+        a = torch.zeros(M, A, device=DEV)
+        ops.policy_sample(torch.zeros(M, A, device=DEV), torch.ones(A, device=DEV), a, rng_seed=7, step_state=state)
+        draws.append(a)
+    assert torch.equal(draws[0], draws[1]) and not torch.equal(draws[0], draws[2])
+    b = torch.zeros(M, A, device=DEV)
+    ops.policy_sample(torch.zeros(M, A, device=DEV), torch.ones(A, device=DEV), b, rng_seed=7, rng_step=42)     # host counter: same stream
+    assert torch.equal(b, draws[0])
+    z = draws[0].double()
+    assert abs(float(z.mean())) < 0.02 and abs(float(z.std()) - 1.0) < 0.02 and float(z.abs().max()) < 6.5
+    assert abs(float((z ** 3).mean())) < 0.05 and abs(float((z ** 4).mean()) - 3.0) < 0.15
+    cols = torch.corrcoef(z.t())
+    assert float((cols - torch.eye(A, dtype=torch.float64, device=DEV)).abs().max()) < 0.06
+
+
+def test_rollout_schedule_matches_torch_rollout(tc_mode):
+    """A 4-step rollout through `rollout_plan.RolloutPlan` (tcgen05 layers, head kernels, fused sample / storage writes, K18/K19)
+    against the torch restatement of on_policy_runner.py:156-181 on fp32 cuBLAS layers, same action noise (torch generator):
+    masks / replay bookkeeping exact, network-dependent quantities within the TF32 bound of the module docstring."""
+    import bench
+    from qa_b200.pipeline import BbcIteration
+    torch.backends.cuda.matmul.allow_tf32 = False
+    N, T = 256, 4
+    cfg, static, snaps, table = bench.build_workload(0, DEV, n_envs=N, steps=T)
+    out = []
+    for plan in (False, True):
+        linear.set_mode("tc" if plan else "fp32")
+        it = BbcIteration(cfg, static, snaps, table, device=DEV, seed=77, use_cuda_graph=False)
+        it.runner.fused_rollout = plan
+        it.env.task_obs_weight = 0.7
+        if plan:
+            rp = it.runner._ensure_rollout_plan()
+            assert rp is not None
+            rp.use_torch_generator = True
+        torch.manual_seed(5)
+        it._rollout_eager(host=False)
+        torch.cuda.synchronize()
+        st, ds = it.runner.alg.storage, it.runner.alg.disc_storage
+        assert st.step == T
+        out.append({k: getattr(st, k).clone() for k in ("rewards", "dones", "values", "observations", "privileged_observations", "actions",
+                                                        "actions_log_prob", "mu", "sigma")}
+                   | dict(hist=it.runner._disc_hist.clone(), replay=ds.states[:T * N].clone(), replay_eps=ds.latent_eps[:T * N].clone(),
+                          replay_c=ds.latent_c[:T * N].clone(), n=ds.num_samples))
+    a, b = out
+    assert int(a["dones"].sum()) > 0 and a["n"] == b["n"] == T * N
+    assert torch.equal(a["dones"], b["dones"]) and torch.equal(a["sigma"], b["sigma"])
+    for k in ("values", "mu", "actions"):
+        assert_close(k, b[k], a[k], rtol=TC_STAT_RTOL, atol=5e-3)
+    assert_close("log_prob", b["actions_log_prob"], a["actions_log_prob"], rtol=TC_STAT_RTOL, atol=2e-2)
+    assert_close("rewards", b["rewards"], a["rewards"], rtol=TC_STAT_RTOL, atol=1e-3)
+    # observations: only the last-action lanes depend on the policy output
+    assert_close("obs", b["observations"], a["observations"], rtol=TC_STAT_RTOL, atol=5e-3)
+    quiet = [i for i in range(671) if not (29 <= i < 41 or 90 <= i < 660)]
+    assert torch.equal(b["observations"][..., quiet], a["observations"][..., quiet])
+    assert torch.equal(b["observations"], b["privileged_observations"])
+    assert_close("disc history", b["hist"], a["hist"])
+    assert_close("replay states", b["replay"], a["replay"])
+    assert torch.equal(b["replay_eps"], a["replay_eps"]) and torch.equal(b["replay_c"], a["replay_c"])
