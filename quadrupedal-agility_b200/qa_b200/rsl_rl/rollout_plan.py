@@ -46,6 +46,8 @@ class RolloutPlan:
         self.alg, self.env = alg, env
         dev = self.dev = torch.device(alg.device)
         ac, est, st, d = alg.actor_critic, alg.estimator, alg.storage, alg.disc
+        if getattr(alg, "disc_flat", None) is None:
+            alg._init_disc_update()          # flat, 16-byte-pitch discriminator parameters: its trunk is read through TMA
         N = self.N = st.num_envs
         self.act_name = ac.activation_name
         self.p, self.e, self.l = alg.num_prop, alg.num_explicit, alg.num_latent
