@@ -20,58 +20,61 @@
 #define HD_MAXN 16
 #define HD_MAXK 256
 
-// Forward.  lanes-per-row = min(32, Kh / 4); a lane owns KV = Kh / (4 * lpr) float4 column groups (2 for Kh = 256).  Each warp
-// pass handles 4 * (32 / lpr) rows: the 4 row loads of a lane are issued back to back (memory-level parallelism: the kernel
-// is a pure stream over h), then each row's NT partial dot products are summed across its lanes by xor butterflies.
-template <int NT, int KV>
+// Forward.  LPR lanes share a row (LPR = min(32, Kh / 4)); a lane owns KV = Kh / (4 * LPR) float4 column groups (2 for
+// Kh = 256).  Each warp pass handles 4 * (32 / LPR) rows: the 4 row loads of a lane are issued back to back (memory-level
+// parallelism: the kernel is a pure stream over h), then each row's NT partial dot products are summed across its lanes by
+// xor butterflies -- level by level over all NT values, so the NT shuffles of a level are independent and pipeline.
+template <int NT, int KV, int LPR>
 __global__ void __launch_bounds__(HD_THREADS) k_head_fwd(const __grid_constant__ QaHeadFwdArgs a) {
     __shared__ __align__(16) float s_w[NT * HD_MAXK];
     __shared__ float s_b[NT];
-    const int Kh = a.Kh, N = a.N;
+    constexpr int Kh = LPR * KV * 4;
+    const int N = a.N;
     for (int i = threadIdx.x; i < NT * Kh; i += HD_THREADS) {
         const int n = i / Kh, k = i - n * Kh;
         s_w[i] = n < N ? __ldg(a.w + (size_t)n * a.w_pitch + k) : 0.f;
     }
     if (threadIdx.x < NT) s_b[threadIdx.x] = (threadIdx.x < N && a.bias != nullptr) ? __ldg(a.bias + threadIdx.x) : 0.f;
     __syncthreads();
-    const int lpr = (Kh >> 2) / KV;                // lanes per row: 32 (Kh = 128 or 256), 16 (64), 8 (32)
-    const int rpp = 32 / lpr;                      // rows per lane group pass
+    constexpr int RPP = 32 / LPR;                  // rows per lane-group pass
     constexpr int U = 4;                           // rows in flight per lane
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int sub = lane % lpr, rsel = lane / lpr;
+    const int sub = lane % LPR, rsel = lane / LPR;
     const long long warps_total = (long long)gridDim.x * (HD_THREADS / 32);
-    const long long stride = warps_total * rpp * U;
-    for (long long r0 = ((long long)blockIdx.x * (HD_THREADS / 32) + warp) * rpp * U; r0 < a.M; r0 += stride) {
+    const long long stride = warps_total * RPP * U;
+    for (long long r0 = ((long long)blockIdx.x * (HD_THREADS / 32) + warp) * RPP * U; r0 < a.M; r0 += stride) {
         float4 h4[U][KV];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const long long r = r0 + u * rpp + rsel;
+            const long long r = r0 + u * RPP + rsel;
 #pragma unroll
             for (int v = 0; v < KV; ++v)
-                h4[u][v] = r < a.M ? *reinterpret_cast<const float4*>(a.h + r * a.h_pitch + (v * lpr + sub) * 4)
+                h4[u][v] = r < a.M ? *reinterpret_cast<const float4*>(a.h + r * a.h_pitch + (v * LPR + sub) * 4)
                                    : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const long long r = r0 + u * rpp + rsel;
+            const long long r = r0 + u * RPP + rsel;
             float p[NT];
 #pragma unroll
             for (int n = 0; n < NT; ++n) {
                 float acc = 0.f;
 #pragma unroll
                 for (int v = 0; v < KV; ++v) {
-                    const float4 w4 = *reinterpret_cast<const float4*>(s_w + n * Kh + (v * lpr + sub) * 4);
+                    const float4 w4 = *reinterpret_cast<const float4*>(s_w + n * Kh + (v * LPR + sub) * 4);
                     acc += h4[u][v].x * w4.x + h4[u][v].y * w4.y + h4[u][v].z * w4.z + h4[u][v].w * w4.w;
                 }
                 p[n] = acc;
             }
 #pragma unroll
-            for (int n = 0; n < NT; ++n)
-                for (int o = lpr >> 1; o > 0; o >>= 1) p[n] += __shfl_xor_sync(QA_FULL, p[n], o);
+            for (int o = LPR >> 1; o > 0; o >>= 1) {
+#pragma unroll
+                for (int n = 0; n < NT; ++n) p[n] += __shfl_xor_sync(QA_FULL, p[n], o);
+            }
             if (r < a.M) {
 #pragma unroll
                 for (int n = 0; n < NT; ++n)
-                    if (n < N && (n % lpr) == sub) a.y[r * a.y_pitch + n] = p[n] + s_b[n];
+                    if (n < N && (n % LPR) == sub) a.y[r * a.y_pitch + n] = p[n] + s_b[n];
             }
         }
     }
@@ -79,12 +82,17 @@ __global__ void __launch_bounds__(HD_THREADS) k_head_fwd(const __grid_constant__
 
 template <int NT>
 static void launch_head_fwd(const QaHeadFwdArgs* a, cudaStream_t s) {
-    const int kv = a->Kh == 256 ? 2 : 1;
-    const int rpp = 32 / ((a->Kh >> 2) / kv);
+    const int lpr = a->Kh >= 128 ? 32 : a->Kh / 4;
+    const int rpp = 32 / lpr;
     long long blocks = (a->M + 8LL * rpp * 4 - 1) / (8LL * rpp * 4);
     if (blocks > 148 * 4) blocks = 148 * 4;
-    if (kv == 2) k_head_fwd<NT, 2><<<(unsigned)blocks, HD_THREADS, 0, s>>>(*a);
-    else k_head_fwd<NT, 1><<<(unsigned)blocks, HD_THREADS, 0, s>>>(*a);
+    const unsigned g = (unsigned)blocks;
+    switch (a->Kh) {
+        case 256: k_head_fwd<NT, 2, 32><<<g, HD_THREADS, 0, s>>>(*a); break;
+        case 128: k_head_fwd<NT, 1, 32><<<g, HD_THREADS, 0, s>>>(*a); break;
+        case 64: k_head_fwd<NT, 1, 16><<<g, HD_THREADS, 0, s>>>(*a); break;
+        default: k_head_fwd<NT, 1, 8><<<g, HD_THREADS, 0, s>>>(*a); break;
+    }
 }
 
 extern "C" int qa_head_fwd(const QaHeadFwdArgs* a, void* stream) {
@@ -101,6 +109,7 @@ extern "C" int qa_head_fwd(const QaHeadFwdArgs* a, void* stream) {
     if (a->N == 1) launch_head_fwd<1>(a, s);
     else if (a->N <= 4) launch_head_fwd<4>(a, s);
     else if (a->N <= 8) launch_head_fwd<8>(a, s);
+    else if (a->N <= 12) launch_head_fwd<12>(a, s);
     else launch_head_fwd<16>(a, s);
     QA_LAUNCH_RET();
 }
@@ -108,7 +117,7 @@ extern "C" int qa_head_fwd(const QaHeadFwdArgs* a, void* stream) {
 // Backward.  Every lane keeps dW[n][4 columns] partial sums over the rows it visits; the block folds them in shared memory
 // (shared atomics) and leaves with one global atomicAdd per element.
 template <int NT>
-__global__ void __launch_bounds__(HD_THREADS) k_head_bwd(const __grid_constant__ QaHeadBwdArgs a) {
+__global__ void __launch_bounds__(HD_THREADS, 2) k_head_bwd(const __grid_constant__ QaHeadBwdArgs a) {
     __shared__ __align__(16) float s_w[NT * 128];
     __shared__ __align__(16) float s_dw[NT * 128];
     __shared__ float s_dbp[128];
@@ -131,29 +140,41 @@ __global__ void __launch_bounds__(HD_THREADS) k_head_bwd(const __grid_constant__
 #pragma unroll
     for (int n = 0; n < NT; ++n) dw[n] = make_float4(0.f, 0.f, 0.f, 0.f), dbn[n] = 0.f;
     float4 dbp = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (long long r0 = ((long long)blockIdx.x * (HD_THREADS / 32) + warp) * rpp; r0 < a.M; r0 += warps_total * rpp) {
-        const long long r = r0 + rsel;
-        if (r >= a.M) continue;
-        const float4 h4 = *reinterpret_cast<const float4*>(a.h + r * a.h_pitch + sub * 4);
-        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    constexpr int U = NT <= 4 ? 2 : 1;             // rows in flight per lane (register budget: 2 blocks of 256 threads per SM)
+    for (long long r0 = ((long long)blockIdx.x * (HD_THREADS / 32) + warp) * rpp * U; r0 < a.M; r0 += warps_total * rpp * U) {
+        float4 h4[U];
+        float g[U][NT];
+        bool ok[U];
 #pragma unroll
-        for (int n = 0; n < NT; ++n) {
-            if (n < N) {
-                const float g = __ldg(a.gz + r * a.gz_pitch + n) * a.gz_scale;     // same address across the row's lanes: broadcast
+        for (int u = 0; u < U; ++u) {
+            const long long r = r0 + u * rpp + rsel;
+            ok[u] = r < a.M;
+            h4[u] = ok[u] ? *reinterpret_cast<const float4*>(a.h + r * a.h_pitch + sub * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int n = 0; n < NT; ++n)        // same address across the row's lanes: broadcast
+                g[u][n] = (ok[u] && n < N) ? __ldg(a.gz + r * a.gz_pitch + n) * a.gz_scale : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long r = r0 + u * rpp + rsel;
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int n = 0; n < NT; ++n) {
                 const float4 w4 = *reinterpret_cast<const float4*>(s_w + n * Kh + sub * 4);
-                o.x += g * w4.x, o.y += g * w4.y, o.z += g * w4.z, o.w += g * w4.w;
-                dw[n].x += g * h4.x, dw[n].y += g * h4.y, dw[n].z += g * h4.z, dw[n].w += g * h4.w;
-                dbn[n] += g;
+                o.x += g[u][n] * w4.x, o.y += g[u][n] * w4.y, o.z += g[u][n] * w4.z, o.w += g[u][n] * w4.w;
+                dw[n].x += g[u][n] * h4[u].x, dw[n].y += g[u][n] * h4[u].y, dw[n].z += g[u][n] * h4[u].z, dw[n].w += g[u][n] * h4[u].w;
+                dbn[n] += g[u][n];
             }
+            const float4 h = h4[u];
+            if (a.act == 1) {                                                      // ELU'(z) from the output: 1 if h > 0 else h + 1
+                o.x = h.x > 0.f ? o.x : o.x * (h.x + 1.0f), o.y = h.y > 0.f ? o.y : o.y * (h.y + 1.0f);
+                o.z = h.z > 0.f ? o.z : o.z * (h.z + 1.0f), o.w = h.w > 0.f ? o.w : o.w * (h.w + 1.0f);
+            } else if (a.act == 2) {
+                o.x = h.x > 0.f ? o.x : 0.f, o.y = h.y > 0.f ? o.y : 0.f, o.z = h.z > 0.f ? o.z : 0.f, o.w = h.w > 0.f ? o.w : 0.f;
+            }
+            if (ok[u] && a.gz_prev != nullptr) *reinterpret_cast<float4*>(a.gz_prev + r * a.gz_prev_pitch + sub * 4) = o;
+            dbp.x += o.x, dbp.y += o.y, dbp.z += o.z, dbp.w += o.w;
         }
-        if (a.act == 1) {                                                          // ELU'(z) from the output: 1 if h > 0 else h + 1
-            o.x = h4.x > 0.f ? o.x : o.x * (h4.x + 1.0f), o.y = h4.y > 0.f ? o.y : o.y * (h4.y + 1.0f);
-            o.z = h4.z > 0.f ? o.z : o.z * (h4.z + 1.0f), o.w = h4.w > 0.f ? o.w : o.w * (h4.w + 1.0f);
-        } else if (a.act == 2) {
-            o.x = h4.x > 0.f ? o.x : 0.f, o.y = h4.y > 0.f ? o.y : 0.f, o.z = h4.z > 0.f ? o.z : 0.f, o.w = h4.w > 0.f ? o.w : 0.f;
-        }
-        if (a.gz_prev != nullptr) *reinterpret_cast<float4*>(a.gz_prev + r * a.gz_prev_pitch + sub * 4) = o;
-        dbp.x += o.x, dbp.y += o.y, dbp.z += o.z, dbp.w += o.w;
     }
     // fold: lanes that share the columns (the rpp row groups of a warp, the 8 warps) meet in shared memory
 #pragma unroll
@@ -196,6 +217,7 @@ extern "C" int qa_head_bwd(const QaHeadBwdArgs* a, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     if (a->N == 1) k_head_bwd<1><<<(unsigned)blocks, HD_THREADS, 0, s>>>(*a);
     else if (a->N <= 4) k_head_bwd<4><<<(unsigned)blocks, HD_THREADS, 0, s>>>(*a);
+    else if (a->N <= 12) k_head_bwd<12><<<(unsigned)blocks, HD_THREADS, 0, s>>>(*a);
     else k_head_bwd<16><<<(unsigned)blocks, HD_THREADS, 0, s>>>(*a);
     QA_LAUNCH_RET();
 }

@@ -168,13 +168,12 @@ extern "C" int qa_clip_adam(const QaClipAdamArgs* a, void* stream) {
 //     (coalesced 128 B accesses), partial column sums meet in shared memory and leave with one atomicAdd per
 //     column per block.  3 passes over M x N (read gy, y; write gz).
 // ------------------------------------------------------------------------------------------
-#define AB_ROWS 256
-__global__ void __launch_bounds__(256) k_act_bwd(QaActBwdArgs a) {
+__global__ void __launch_bounds__(256) k_act_bwd(QaActBwdArgs a, int rows_per_block) {
     __shared__ float s_part[8][33];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int col = blockIdx.x * 32 + lane;
-    const long long r0 = (long long)blockIdx.y * AB_ROWS;
-    const long long r1 = min((long long)a.M, r0 + AB_ROWS);
+    const long long r0 = (long long)blockIdx.y * rows_per_block;
+    const long long r1 = min((long long)a.M, r0 + rows_per_block);
     float acc = 0.f;
     const float addend_scale = (a.addend != nullptr && a.addend_scale != nullptr) ? __ldg(a.addend_scale) : 1.f;
     if (col < a.N) {
@@ -214,8 +213,13 @@ extern "C" int qa_act_bwd(const QaActBwdArgs* a, void* stream) {
         cudaError_t e = cudaMemsetAsync(a->db, 0, sizeof(float) * a->N, s);
         if (e != cudaSuccess) return (int)e;
     }
-    dim3 grid((a->N + 31) / 32, (unsigned)((a->M + AB_ROWS - 1) / AB_ROWS));
-    k_act_bwd<<<grid, 256, 0, s>>>(*a);
+    // strip height: 256 rows for wide tensors; narrow ones (a few 32-column blocks) get shorter strips so that the grid still
+    // covers the chip several times over (a warp walks its strip row by row: long strips are latency bound)
+    const int col_blocks = (a->N + 31) / 32;
+    int rows = 256;
+    while (rows > 32 && (long long)col_blocks * ((a->M + rows - 1) / rows) < 148 * 6) rows >>= 1;
+    dim3 grid(col_blocks, (unsigned)((a->M + rows - 1) / rows));
+    k_act_bwd<<<grid, 256, 0, s>>>(*a, rows);
     QA_LAUNCH_RET();
 }
 

@@ -25,9 +25,14 @@ if len(sys.argv) > 1 and sys.argv[1] == "--only":            # profiling mode: o
     gz = torch.randn(M, N, device=dev)
     dx = torch.empty(M, kp, device=dev)[:, :K]
     dw = torch.zeros(N, kp, device=dev)[:, :K]
+    db = torch.zeros(K, device=dev)
+    xin = torch.nn.functional.elu(x.clone()) if kp == K else None       # previous layer's output for the fused activation backward
     for _ in range(3):
         ops.linear_fwd(x, w, b, y, "elu")
-        ops.linear_bwd(gz, None, w, dx=dx)
+        if xin is not None:
+            ops.linear_bwd(gz, None, w, dx=dx, act_prev="elu", y_prev=xin, db_prev=db, db_accumulate=True)
+        else:
+            ops.linear_bwd(gz, None, w, dx=dx)
         ops.linear_bwd(gz, x, None, dw=dw)
     torch.cuda.synchronize()
     sys.exit(0)
@@ -91,7 +96,11 @@ for M, N, K in [(24576, 512, 671), (24576, 512, 101), (24576, 256, 512), (24576,
     gz = torch.randn(M, N, device=dev)
     dx = torch.empty(M, kp, device=dev)[:, :K]
     dw = torch.zeros(N, kp, device=dev)[:, :K]
-    t1 = timeit(lambda: ops.linear_bwd(gz, None, w, dx=dx))
+    if kp == K:                                      # hidden layer: dx with the fused activation backward + bias gradient
+        yp, db = torch.nn.functional.elu(x.clone()), torch.zeros(K, device=dev)
+        t1 = timeit(lambda: ops.linear_bwd(gz, None, w, dx=dx, act_prev="elu", y_prev=yp, db_prev=db, db_accumulate=True))
+    else:
+        t1 = timeit(lambda: ops.linear_bwd(gz, None, w, dx=dx))
     t2 = timeit(lambda: ops.linear_bwd(gz, x, None, dw=dw))
     t3 = timeit(lambda: torch.matmul(gz, w))
     t4 = timeit(lambda: torch.matmul(gz.t(), x))
