@@ -229,6 +229,17 @@ def run_ours(args):
         if world == 1:
             line["roofline_gemm"] = gemm_roofline_sample(dev, pk)
             line["roofline_32768"] = k2_roofline_32768(dev, pk)
+            if not args.no_tsc:
+                for key, student in (("tsc_teacher", False), ("tsc_student", True)):
+                    try:                                         # BASELINE configs 3 / 4 beside the headline (guarded like the baselines)
+                        leg = tsc_leg(dev, student, steps=3, warmup=2)
+                        n, T = leg["envs_per_gpu"], leg["steps_per_env"]
+                        leg["value"] = T * n / (leg["ms_per_step"] * 1e-3)
+                        leg["e2e_value"] = T * n / (leg["ms_per_step_host_fed"] * 1e-3)
+                        leg["unit"] = UNIT
+                        line[key] = leg
+                    except Exception as e:                       # noqa: BLE001
+                        line[key] = {"error": f"{type(e).__name__}: {e}"[:300]}
             if not args.no_fp32_value:
                 line["value_fp32_linear"] = fp32_linear_value(args, rank, dev)
         if world == 1 and not args.no_torch_gpu_baseline:
@@ -303,6 +314,139 @@ def time_tsc_env(dev, n_envs=ENVS_PER_GPU, steps=T_STEPS, reps=10):
     return {"workload": f"tsc_go2_agility_teacher_{n_envs}: qa_post_physics_tsc_pre + _post per env step", "us_per_step": us,
             "env_steps_per_sec_env_only": n_envs / (us * 1e-6), "achieved_gbs": achieved, "frac_of_hbm_peak": achieved / pk["hbm_gbs"],
             "algorithmic_bytes_per_env_step": TSC_BYTES_PER_ENV}
+
+
+TSC_KEYS = ("root_states", "dof_state", "contact_forces", "rigid_body_state", "obst_dof_state", "rigid_body_state_post")
+K14_BYTES_PER_ENV = 25440 + 20184 + 40368      # camera image read + depth history read + history written, per env
+
+
+def _cuda_time_ms(fn, steps, flush):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tot = 0.0
+    for _ in range(steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        e0.record()
+        fn()
+        e1.record()
+        e1.synchronize()
+        tot += e0.elapsed_time(e1)
+    return tot / steps
+
+
+class TscWorkload:
+    """BASELINE configs 3 and 4 over synthetic recorded state: the TSC env (K16 / K17 + K0 / K1, K14 for the student) under
+    `OnPolicyRunnerTSC` with the frozen BBC controller.  `host=True` feeds every step's simulator tensors (and camera images)
+    from pinned host memory inside the timed region."""
+
+    def __init__(self, dev, n_envs, T, seed, student):
+        from qa_b200 import synthetic
+        from qa_b200.config import tsc_train_cfg
+        from qa_b200.legged_robot_tsc import LeggedRobotTSC, RecordedPhysicsTSC, TscEnvConfig
+        from qa_b200.rsl_rl.tsc_runner import OnPolicyRunnerTSC
+        self.dev, self.N, self.T, self.student = dev, n_envs, T, student
+        st = synthetic.make_tsc_static(n_envs, seed)
+        n_snaps = 4
+        snaps = [synthetic.make_tsc_snapshot(n_envs, st, seed, step=t) for t in range(n_snaps)]
+        self.host = [{k: v.contiguous().pin_memory() for k, v in s.items() if isinstance(v, torch.Tensor) and k in TSC_KEYS} for s in snaps]
+        self.dsn = [{k: v.to(dev).contiguous() for k, v in s.items() if isinstance(v, torch.Tensor)} for s in snaps]
+        self.env = env = LeggedRobotTSC(TscEnvConfig(num_envs=n_envs), RecordedPhysicsTSC(self.dsn), st, device=dev, seed=seed)
+        env.load_state(snaps[0])
+        self.images_host = None
+        if student:
+            from qa_b200.depth import DepthBuffer
+            depth = DepthBuffer(n_envs, device=dev, seed=seed + 5)
+            g = torch.Generator().manual_seed(seed)
+            self.images_host = [(-(0.1 + 6.0 * torch.rand(n_envs, 60, 106, generator=g))).pin_memory() for _ in range(2)]
+            self.images = self.images_host[0].to(dev)
+            depth.set_batched_images(self.images)
+            env.attach_depth(depth)
+        env.post_physics_step()
+        cfg = tsc_train_cfg(use_camera=student)
+        if student:
+            cfg["depth_encoder"]["num_steps_per_env"] = T
+        else:
+            cfg["runner"]["num_steps_per_env"] = T
+        torch.manual_seed(seed)
+        self.r = r = OnPolicyRunnerTSC(env, cfg, device=dev)
+        self.obs, self.obs_bbc = env.get_observations(), env.get_observations_bbc().clone()
+        r._disc_hist = torch.stack([env.get_observations_disc()] * 2, dim=1)
+        self.critic, self.infos = self.obs, {}
+        self.h2d_bytes = T * (sum(v.numel() * v.element_size() for v in self.host[0].values()) +
+                              (self.images_host[0].numel() * 4 if student else 0))
+        self.result_host = torch.zeros(8).pin_memory()
+        if student:
+            self.hist = torch.zeros(n_envs, env.cfg.action_buf_len, r.num_actions, device=dev)
+            self.sinfos = {"depth": env.depth_buffer.clone()[:, -1], "delta_yaw_ok": torch.ones(n_envs, dtype=torch.bool, device=dev)}
+            r.alg.depth_encoder.train()
+            r.alg.depth_actor.train()
+            self.keys = ("depth", "depth_latent", "scandots_latent", "actions_teacher", "actions_student", "yaw_student", "yaw_teacher",
+                         "obst_student", "obst_teacher", "delta_yaw_ok")
+
+    def _feed(self, t):
+        i = t % len(self.host)
+        for k, v in self.host[i].items():
+            self.dsn[i][k].copy_(v, non_blocking=True)
+        if self.student:
+            self.images.copy_(self.images_host[t % 2], non_blocking=True)
+
+    def iteration(self, host=False):
+        r, env = self.r, self.env
+        if not self.student:
+            with torch.no_grad():
+                for t in range(self.T):
+                    if host:
+                        self._feed(t)
+                    self.obs, self.obs_bbc, self.critic, self.infos = r.rollout_step(self.obs, self.obs_bbc, self.critic, self.infos)
+                r.alg.compute_returns(self.critic)
+            out = r.alg.update()
+            if host:
+                self.result_host[0] = float(out[0])
+            return out
+        buf = {k: [] for k in self.keys}
+        for t in range(self.T):
+            if host:
+                self._feed(t)
+            self.obs, self.obs_bbc, self.sinfos, self.hist, _rew, _dones = r.student_step(self.obs, self.obs_bbc, self.sinfos, self.hist,
+                                                                                          buf, False)
+        cat = {k: torch.cat(v, dim=0) for k, v in buf.items() if k != "delta_yaw_ok"}
+        out = r.alg.update_depth_actor(cat["actions_student"], cat["actions_teacher"], cat["yaw_student"], cat["yaw_teacher"],
+                                       cat["obst_student"], cat["obst_teacher"], cat["depth"])
+        r.alg.depth_encoder.detach_hidden_states()
+        r._student_last = tuple(t.detach() for t in r._student_last)
+        return out
+
+
+def tsc_leg(dev, student, world=1, rank=0, n_envs=None, T=T_STEPS, steps=5, warmup=3):
+    """One TSC workload (config 3: teacher iteration = rollout + GAE + PPO.update, tsc on_policy_runner.py:201-228 + ppo.py:160-282;
+    config 4: student iteration = depth rollout + update_depth_actor, :278-441): device-resident value, host-fed e2e, and the
+    roofline of the workload's own fused kernel(s) -- K16 + K17 (teacher) / K14 (student).  Returns a dict of rank-local numbers."""
+    n_envs = n_envs or (2048 if student else ENVS_PER_GPU)
+    w = TscWorkload(dev, n_envs, T, 1234 + rank, student)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(warmup):
+        w.iteration()
+    from qa_b200 import ops
+    l0 = ops.launches
+    ms = _cuda_time_ms(lambda: w.iteration(), steps, flush)
+    launches = (ops.launches - l0) // max(steps, 1)
+    w.iteration(host=True)
+    ms_host = _cuda_time_ms(lambda: w.iteration(host=True), steps, flush)
+    out = {"envs_per_gpu": n_envs, "steps_per_env": T, "ms_per_step": ms, "ms_per_step_host_fed": ms_host,
+           "h2d_bytes_per_step": w.h2d_bytes, "d2h_bytes_per_step": 32, "gpu_launches": launches}
+    if student:
+        # K14 alone: T launches in a graph
+        depth, env = w.env.depth, w.env
+        g = torch.cuda.CUDAGraph()
+        depth.update_depth_buffer(env.episode_length_buf)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g):
+            for _ in range(T):
+                depth.update_depth_buffer(env.episode_length_buf)
+        us = _cuda_time_ms(g.replay, 10, flush) / T * 1e3
+        out["kernel"] = {"name": "k_depth_update (K14)", "us_per_launch": us, "bytes_per_env": K14_BYTES_PER_ENV}
+        out["kernel"]["achieved_gbs"] = K14_BYTES_PER_ENV * n_envs / (us * 1e-6) / 1e9
+    return out
 
 
 def cpu_reference_sample(n_envs, rollout_steps, minibatch_steps, threads):
@@ -501,6 +645,66 @@ def torch_gpu_baseline_sample(dev, n_envs=ENVS_PER_GPU):
         return {"error": f"{type(e).__name__}: {e}"[:300]}
 
 
+def run_tsc(args):
+    """`--workload tsc_teacher | tsc_student`: the same JSON contract for BASELINE configs 3 / 4 (weak scaling over env shards;
+    the PPO / distillation gradients are all-reduced per optimiser step as in the BBC path)."""
+    rank, local_rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+    from qa_b200.rsl_rl import linear
+    linear.set_mode("tc" if args.linear == "tc" else "fp32")
+    student = args.workload == "tsc_student"
+    sampler = ClockSampler(local_rank)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    if rank == 0:
+        sampler.start()
+    leg = tsc_leg(dev, student, world, rank, steps=args.steps, warmup=args.warmup)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([leg["ms_per_step"], leg["ms_per_step_host_fed"]], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_host = (float(v) for v in t.tolist())
+    n, T = leg["envs_per_gpu"], leg["steps_per_env"]
+    if rank == 0:
+        name = ("tsc_go2_agility_student (--use_camera, depth path)" if student else "tsc_go2_agility_teacher (--exptid base)")
+        line = {"metric": METRIC, "value": T * n * world / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "tf32 GEMM operands / f32 accumulate; conv / GRU of the depth student on cuDNN (tf32)", "data": "synthetic",
+                "config": {"workload": f"{name}: {n} envs per GPU x {T} steps, rollout + update", "envs_per_gpu": n, "steps_per_env": T,
+                           "l2": "256 MiB flush between timed iterations", "parallelism": f"env-sharded dp{world}"},
+                "e2e": {"value": T * n * world / (ms_host * 1e-3), "unit": UNIT, "h2d_bytes_per_step": leg["h2d_bytes_per_step"],
+                        "d2h_bytes_per_step": leg["d2h_bytes_per_step"]},
+                "gpu_launches": leg["gpu_launches"], "clocks": clocks}
+        if "kernel" in leg:
+            pk, _ = peaks()
+            k = leg["kernel"]
+            line["roofline"] = {"bound": "hbm", "kernel": k["name"], "achieved": k["achieved_gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                "frac": k["achieved_gbs"] / pk["hbm_gbs"], "us_per_launch": k["us_per_launch"], "traffic": None}
+        elif world == 1:
+            te = time_tsc_env(dev)
+            pk, _ = peaks()
+            line["roofline"] = {"bound": "hbm", "kernel": "k_post_physics_tsc_pre + _post (K16 + K17)", "achieved": te["achieved_gbs"],
+                                "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": te["frac_of_hbm_peak"], "us_per_launch": te["us_per_step"],
+                                "traffic": None}
+        print(json.dumps(line, default=str), flush=True)
+    if world > 1:
+        import threading
+        dist.barrier()
+        torch.cuda.synchronize()
+        wd = threading.Timer(30.0, lambda: os._exit(0))
+        wd.daemon = True
+        wd.start()
+        dist.destroy_process_group()
+        wd.cancel()
+
+
 def cpu_baseline_sample():
     threads = os.cpu_count() or 1
     rs, ms = 12, 6                                   # ~10-20 s of CPU work
@@ -548,12 +752,18 @@ def main():
     ap.add_argument("--no-torch-gpu-baseline", action="store_true",
                     help="skip the reference's PyTorch path timed on the same GPU (reported beside the metric)")
     ap.add_argument("--no-fp32-value", action="store_true", help="skip the full-fp32 (cuBLAS) run of the same iteration")
+    ap.add_argument("--workload", default="bbc", choices=["bbc", "tsc_teacher", "tsc_student"],
+                    help="bbc = BASELINE configs 1 / 5 (default, the headline metric); tsc_teacher = config 3 (4096 envs per GPU); "
+                         "tsc_student = config 4 (depth path, 2048 envs per GPU: 4096 envs on 2 GPUs)")
+    ap.add_argument("--no-tsc", action="store_true", help="skip the TSC teacher / student sub-legs of the default line")
     ap.add_argument("--k2-bulk", type=int, default=2,
                     help="K2 variant: 2 = 8-env TMA tiles (default), 1 = warp-per-env + TMA row stores, 0 = warp stores")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload != "bbc":
+        run_tsc(args)
     else:
         run_ours(args)
 
