@@ -28,7 +28,11 @@ def _parity_linear_mode():
     """The product default for the dense layers is the tcgen05 TF32 path (tests/test_ppo_plan_gpu.py, test_linear_gpu.py test it
     against derived TF32 bounds); the fp32 parity tests compare against the reference's fp32 results, so EVERY test starts in
     full-fp32 mode -- per test, so that a test that dies in "tc" mode cannot leak the mode into the tests after it."""
+    import torch
     from qa_b200.rsl_rl import linear
     linear.set_mode("fp32")
+    # `import bench` switches the framework's TF32 modes on for the whole process; the parity references are fp32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
     yield
     linear.set_mode("fp32")
