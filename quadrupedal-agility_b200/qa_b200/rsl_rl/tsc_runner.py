@@ -66,7 +66,10 @@ class OnPolicyRunnerTSC:
         self.n_delta_yaw, self.n_obst_type = 2, self.n_auxiliary - 2
         self.n_depth_latent = self.policy_cfg["scan_encoder_dims"][-1]
         if self.if_depth:
-            self.depth_backbone = DepthOnlyFCBackbone58x87(self.n_proprio, self.n_depth_latent, self.depth_encoder_cfg["hidden_dims"])
+            # on the device from the start: the BYOL learner sizes its projector with a dummy forward in its constructor, and
+            # with > 1 rank its batch norms are SyncBatchNorm, which refuses host tensors
+            self.depth_backbone = DepthOnlyFCBackbone58x87(self.n_proprio, self.n_depth_latent,
+                                                           self.depth_encoder_cfg["hidden_dims"]).to(device)
             env_ns = types.SimpleNamespace(n_delta_yaw=self.n_delta_yaw, n_obst_type=self.n_obst_type, n_proprio=self.n_proprio)
             self.depth_encoder = RecurrentDepthBackbone(self.depth_backbone, self.n_depth_latent, env_ns).to(device)
             self.depth_actor = copy.deepcopy(self.actor_critic.actor)

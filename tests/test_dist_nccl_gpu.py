@@ -56,8 +56,10 @@ def _run(rank, world, port, q, arena):
     torch.cuda.synchronize()
     assert alg._plan is not None
     scale = 1.0 / world
-    res = dict(grad_ac=(alg.ac_flat.grad * scale).cpu(), grad_est=(alg.est_flat.grad * scale).cpu(), ac=alg.ac_flat.data.cpu(),
-               est=alg.est_flat.data.cpu(), lr=alg.lr_ac, stats=[float(v) for v in out], arena=alg._grad_arena is not None)
+    # numpy arrays through the queue (tensors would be passed as shared-memory file descriptors of a process that exits)
+    res = dict(grad_ac=(alg.ac_flat.grad * scale).cpu().numpy(), grad_est=(alg.est_flat.grad * scale).cpu().numpy(),
+               ac=alg.ac_flat.data.cpu().numpy(), est=alg.est_flat.data.cpu().numpy(), lr=alg.lr_ac,
+               stats=[float(v) for v in out], arena=alg._grad_arena is not None)
     q.put((rank, res))
     if world > 1:
         dist.barrier()
@@ -74,6 +76,9 @@ def _spawn(world, arena):
     for p in ps:
         p.join(timeout=120)
         assert p.exitcode == 0
+    for r in out.values():
+        for k in ("grad_ac", "grad_est", "ac", "est"):
+            r[k] = torch.from_numpy(r[k])
     return out
 
 
