@@ -212,6 +212,8 @@ typedef struct QaBbcConst {
 } QaBbcConst;
 
 #define QA_K2_BULK_STORE 1u   /* obs/priv rows leave through TMA bulk stores (needs pitch 671, N % 4 == 0) */
+#define QA_K2_PDL 4u          /* launch the tiled kernel with programmatic stream serialization (back-to-back steps overlap
+                               * launch latency with the predecessor's tail; results are identical) */
 #define QA_K2_TILED 2u        /* 8-env CTA tiles, every per-env array staged by TMA bulk copies (needs N % 8 == 0,
                                * 16 B aligned bases, pitch 671); falls back to the warp-per-env kernel otherwise */
 

@@ -9,8 +9,9 @@
 //       8 threads of 8 different warps issue 13 TMA bulk loads (cp.async.bulk + mbarrier complete_tx; every per-env
 //       array's 8-env slice is contiguous and 16 B aligned) -- the 12 small tiles on one mbarrier, the 18 KB history
 //       tile on its own -- and the env warps draw this step's Philox noise while they wait;
-//   P2a (scalar warp A, thread-per-env, starts as soon as ITS loads land): base-frame quantities, euler angles, centre
-//       terrain height, periodic resampling, push;  (scalar warp B, lane = (env, foot)): key-body positions;
+//   P2a (scalar warp A, lane = (env, role), starts as soon as ITS loads land): four roles per env -- base linear velocity |
+//       base angular velocity | projected gravity + euler angles | centre terrain height, periodic resampling, push -- so the
+//       dependent chain is the longest role, not their sum;  (scalar warp B, lane = (env, foot)): key-body positions;
 //   P1  after the small tiles: scalar warp B (lane = (env, leg), 3 DOFs per lane) forms the nine 12-wide reward sums,
 //       the env warps (lanes = bodies) the contact-force norms (ballots) -> per-env scalars; named barrier 1 hands them to
 //   P2b (scalar warp A): contacts, termination, reward total, episode sums, reset decision -- while the env warps run
@@ -153,6 +154,12 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
     const QaBbcStepArgs& r = a_in;
     GSTAMP(16, T_ENV);
     STAMP(0, T_ENV);
+    // Programmatic dependent launch (QA_K2_PDL): this grid may have been scheduled while its predecessor in the stream was
+    // still draining -- nothing global is read before the predecessor has completed and flushed (`wait`); our own dependents
+    // may be scheduled right away (`launch_dependents`): they park in `wait` until this grid is done, so the launch latency of
+    // back-to-back steps overlaps the tail of the previous one.  Both instructions are no-ops under a plain launch.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const long long step_before = k2_load_step(a_in);     // device step counter: in flight before anything else
 
     // ---------------- P0: every load of the tile is put in flight before the first barrier -----------------------
@@ -436,25 +443,37 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
         for (int i = lane; i < HIST_OFF; i += 32) row[i] = clampf(row[i], -c.clip_obs, c.clip_obs);
         STAMP(8, T_ENV);
     } else if (wid == W_SA) {
-        // ---------------- P2a (scalar warp A, thread-per-env): base-frame quantities, euler angles, terrain, resample, push
+        // ---------------- P2a (scalar warp A, lane = (env, role)): the thread-per-env scalar program of round 1 split four ways
+        // so that the dependent chain is the longest ROLE, not their sum (same arithmetic per quantity, bit for bit):
+        //   role 0  base linear velocity            role 2  projected gravity + euler angles
+        //   role 1  base angular velocity           role 3  centre terrain height, periodic resample, push
         if (lane < 26) reinterpret_cast<float4*>(S.root)[lane] = ld0;
         if (st1 != nullptr) *st1 = ld1;
         __syncwarp();
         STAMP(12, T_SA);
-        Vec3 blv = {0.f, 0.f, 0.f}, bav = {0.f, 0.f, 0.f};
-        float center_h = 0.f;
-        long long ep = 0;
-        const int el = lane & (T2_ENVS - 1), e = e0 + el;
+        const int el = lane >> 2, role = lane & 3, e = e0 + el;
         float* R = S.root + el * 13;
         float* sc = S.scal[el];
         float* cmd = S.cmd + el * 5;
-        if (lane < T2_ENVS) {
-            const Quat q = {R[3], R[4], R[5], R[6]};
-            ep = S.ep[el] + 1;                                                         // :133
-            if (c.measure_heights) center_h = terrain_center_height(a.terrain, yaw_quat(q), R[0], R[1], c.center_px, c.center_py);
-            blv = quat_rotate_sgn(q, Vec3{R[7], R[8], R[9]}, -1.f);                     // :138-140
-            bav = quat_rotate_sgn(q, Vec3{R[10], R[11], R[12]}, -1.f);
-            const Vec3 pg = quat_rotate_sgn(q, Vec3{0.f, 0.f, -1.f}, -1.f);
+        float* row = S.obs + el * ROW;
+        float* disc = S.disc + el * QA_NUM_OBS_DISC;
+        const Quat q = {R[3], R[4], R[5], R[6]};
+        long long ep = S.ep[el] + 1;                                                    // :133
+        const float root_z_pre = R[2];                                                 // before any push / reset write
+        Vec3 vec = {0.f, 0.f, 0.f};                                                    // role 0: blv, role 1: bav
+        float center_h = 0.f;
+        if (role == 0) {
+            vec = quat_rotate_sgn(q, Vec3{R[7], R[8], R[9]}, -1.f);                     // :138
+            S.blv[el * 3 + 0] = vec.x, S.blv[el * 3 + 1] = vec.y, S.blv[el * 3 + 2] = vec.z;
+            row[58] = vec.x * c.s_lin_vel, row[59] = vec.y * c.s_lin_vel, row[60] = vec.z * c.s_lin_vel;
+            disc[3] = vec.x * c.s_lin_vel_dist, disc[4] = vec.y * c.s_lin_vel_dist, disc[5] = vec.z * c.s_lin_vel_dist;
+        } else if (role == 1) {
+            vec = quat_rotate_sgn(q, Vec3{R[10], R[11], R[12]}, -1.f);                  // :139
+            S.bav[el * 3 + 0] = vec.x, S.bav[el * 3 + 1] = vec.y, S.bav[el * 3 + 2] = vec.z;
+            row[2] = vec.x * c.s_ang_vel, row[3] = vec.y * c.s_ang_vel, row[4] = vec.z * c.s_ang_vel;
+            disc[6] = vec.x * c.s_ang_vel_dist, disc[7] = vec.y * c.s_ang_vel_dist, disc[8] = vec.z * c.s_ang_vel_dist;
+        } else if (role == 2) {
+            const Vec3 pg = quat_rotate_sgn(q, Vec3{0.f, 0.f, -1.f}, -1.f);             // :140
             float roll, pitch, yaw;
             {
                 const float t0 = 2.0f * (q.w * q.x + q.y * q.z);
@@ -467,23 +486,15 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
                 const float t4 = 1.0f - 2.0f * (q.y * q.y + q.z * q.z);
                 yaw = atan2f(t3, t4);
             }
-            S.blv[el * 3 + 0] = blv.x, S.blv[el * 3 + 1] = blv.y, S.blv[el * 3 + 2] = blv.z;
-            S.bav[el * 3 + 0] = bav.x, S.bav[el * 3 + 1] = bav.y, S.bav[el * 3 + 2] = bav.z;
             S.pg[el * 3 + 0] = pg.x, S.pg[el * 3 + 1] = pg.y, S.pg[el * 3 + 2] = pg.z;
             S.rpy[el * 3 + 0] = roll, S.rpy[el * 3 + 1] = pitch, S.rpy[el * 3 + 2] = yaw;
-            {
-                // this warp's lanes of the observation row and of the disc obs (pre-reset quantities, :263-291)
-                float* row = S.obs + el * ROW;
-                float* disc = S.disc + el * QA_NUM_OBS_DISC;
-                const float root_h_pre = R[2] - center_h;
-                row[0] = roll, row[1] = pitch;
-                row[2] = bav.x * c.s_ang_vel, row[3] = bav.y * c.s_ang_vel, row[4] = bav.z * c.s_ang_vel;
-                row[57] = c.root_height_obs ? root_h_pre : 0.f;
-                row[58] = blv.x * c.s_lin_vel, row[59] = blv.y * c.s_lin_vel, row[60] = blv.z * c.s_lin_vel;
-                disc[0] = roll, disc[1] = pitch, disc[2] = root_h_pre;
-                disc[3] = blv.x * c.s_lin_vel_dist, disc[4] = blv.y * c.s_lin_vel_dist, disc[5] = blv.z * c.s_lin_vel_dist;
-                disc[6] = bav.x * c.s_ang_vel_dist, disc[7] = bav.y * c.s_ang_vel_dist, disc[8] = bav.z * c.s_ang_vel_dist;
-            }
+            row[0] = roll, row[1] = pitch;
+            disc[0] = roll, disc[1] = pitch;
+        } else {
+            if (c.measure_heights) center_h = terrain_center_height(a.terrain, yaw_quat(q), R[0], R[1], c.center_px, c.center_py);
+            const float root_h_pre = root_z_pre - center_h;                             // pre-reset quantities (:263-291)
+            row[57] = c.root_height_obs ? root_h_pre : 0.f;
+            disc[2] = root_h_pre;
             if (divisible_by(ep, c.resample_period)) {                                 // :454-462
                 const K2Draw d = draw_site(c, a, e, SITE_RS0, a.rs_eps_u, a.rs_c_idx, a.rs_cmd_u);
                 resample_thread(c, d, cmd, S.eps + el, S.lc + el * 5);
@@ -504,11 +515,19 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
                 R[8] = span * u1 + (-c.max_push_vel_xy);
             }
         }
+        // role 0 runs P2b and needs the other roles' results: registers through shuffles, commands through shared memory
+        const Vec3 blv = vec;                                                          // valid on role 0
+        Vec3 bav;
+        bav.x = __shfl_down_sync(QA_FULL, vec.x, 1);
+        bav.y = __shfl_down_sync(QA_FULL, vec.y, 1);
+        bav.z = __shfl_down_sync(QA_FULL, vec.z, 1);
+        center_h = __shfl_down_sync(QA_FULL, center_h, 3);
+        __syncwarp();                                                                  // role 3's command / root writes are visible
         STAMP(13, T_SA);
         mbar_wait(&S.bar_small, 0);          // episode sums tile (TMA) visible to this warp
         bar_sync(1, T2_THREADS);             // P1 sums / force norms of the env warps are in S.scal
         STAMP(14, T_SA);
-        if (lane < T2_ENVS) {
+        if (role == 0) {
             // ---------------- P2b: contacts, termination, reward total, episode sums, reset decision --------------------
 #pragma unroll
             for (int j = 0; j < 4; ++j) {                                              // :143-146
@@ -526,7 +545,6 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
                     a.contact_force_buf[((size_t)e * a.contact_ring_len + a.contact_ring_head) * 4 + j] =
                         clampf(f, -c.clip_obs, c.clip_obs);
             }
-            const float root_z_pre = R[2];
             const bool time_out = ((float)ep > c.max_episode_length) || (root_z_pre < -6.0f);   // :168-176
             const bool is_reset = (sc[SC_TERM] != 0.f) || time_out;
             const float root_h_pre = root_z_pre - center_h;
@@ -771,8 +789,19 @@ int qa_k2_try_launch_tiled(const QaBbcConst* c, const QaBbcStepArgs* a, cudaStre
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
-    k_post_physics_bbc_tiled<<<a->num_envs / T2_ENVS, T2_THREADS, sizeof(T2Smem), stream>>>(*c, *a);
     *launched = 1;
+    if (a->flags & QA_K2_PDL) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(a->num_envs / T2_ENVS), cfg.blockDim = dim3(T2_THREADS);
+        cfg.dynamicSmemBytes = sizeof(T2Smem), cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at, cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, k_post_physics_bbc_tiled, *c, *a);
+        return e == cudaSuccess ? 0 : (int)e;
+    }
+    k_post_physics_bbc_tiled<<<a->num_envs / T2_ENVS, T2_THREADS, sizeof(T2Smem), stream>>>(*c, *a);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : (int)e;
 }

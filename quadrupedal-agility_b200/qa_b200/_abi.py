@@ -12,6 +12,7 @@ QA_ABI_VERSION = 1
 NUM_DOF, DIM_C, NUM_REWARDS = 12, 5, 14
 QA_K2_BULK_STORE = 1
 QA_K2_TILED = 2
+QA_K2_PDL = 4
 MAX_NOISE_LANES = 64
 
 f32p = C.POINTER(C.c_float)

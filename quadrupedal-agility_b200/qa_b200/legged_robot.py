@@ -13,6 +13,7 @@ simulate), K2 fused post-physics, reset compaction -- no per-term Python, no hos
 caller asks for the variable-length `reset_env_ids` (`step()` does, `step_device()` does not).
 """
 import ctypes as C
+import os
 import types
 from typing import Dict, Optional
 
@@ -176,6 +177,8 @@ class LeggedRobot:
         self.refresh_prior()
         # kernel variant request; the library falls back to the warp-per-env kernel when a tile constraint fails
         self._flags = (_abi.QA_K2_BULK_STORE if (bulk_store and N % 4 == 0) else 0) | (_abi.QA_K2_TILED if tiled else 0)
+        if os.environ.get("QA_K2_PDL", "1") == "1":         # programmatic dependent launch of the fused step (include/qa_b200.h)
+            self._flags |= _abi.QA_K2_PDL
         self._draws = None
         # device-resident step counter: lets a captured CUDA graph of post_physics_step be replayed (the Philox
         # counter, the push schedule and the contact-ring head advance on the device)
