@@ -51,7 +51,7 @@ int qa_version(void);
 /* human readable build string ("sm_100a, nvcc 12.9, ...") */
 const char* qa_build_info(void);
 /* sizeof() of argument struct number `which` (order of declaration in this header, QaActionPushArgs
- * = 0 ... QaGaeArgs = 9, QaGatherArgs = 10, QaClipAdamArgs = 11, QaLinearArgs = 12, QaActBwdArgs = 13, QaPpoLossArgs = 14, QaLinearBwdArgs = 15, QaHistEncArgs = 16, QaRowLossArgs = 17, QaPpoScalarsArgs = 18, QaDepthArgs = 19, QaPpoLossTscArgs = 20, QaTscConst = 21, QaTscStepArgs = 22, QaDiscInputArgs = 23, QaDiscRewardArgs = 24, QaHeadFwdArgs = 25, QaHeadBwdArgs = 26, QaPolicySampleArgs = 27; -1 if unknown): a layout handshake for FFI mirrors of these structs */
+ * = 0 ... QaGaeArgs = 9, QaGatherArgs = 10, QaClipAdamArgs = 11, QaLinearArgs = 12, QaActBwdArgs = 13, QaPpoLossArgs = 14, QaLinearBwdArgs = 15, QaHistEncArgs = 16, QaRowLossArgs = 17, QaPpoScalarsArgs = 18, QaDepthArgs = 19, QaPpoLossTscArgs = 20, QaTscConst = 21, QaTscStepArgs = 22, QaDiscInputArgs = 23, QaDiscRewardArgs = 24, QaHeadFwdArgs = 25, QaHeadBwdArgs = 26, QaPolicySampleArgs = 27, QaDiscPrepareArgs = 28, QaDiscHeadsArgs = 29, QaDiscGpArgs = 30, QaDiscRegArgs = 31, QaNormMomentsArgs = 32, QaNormMergeArgs = 33; -1 if unknown): a layout handshake for FFI mirrors of these structs */
 int qa_struct_size(int which);
 /* stream-ordered fill-with-zero / device-to-device copy of `bytes` bytes (cudaMemsetAsync / cudaMemcpyAsync): lets a captured
  * training step zero its flat gradient buffer (optimizer.zero_grad(), gail.py:361, :409) and move device scalars without a
@@ -809,6 +809,83 @@ typedef struct QaDiscRewardArgs {
     float* reward_terms;                /* (N,4) reward_i, reward_us, reward_ss, reward_t (already x dt), or NULL */
 } QaDiscRewardArgs;
 int qa_disc_reward(const QaDiscRewardArgs* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K24-K30  discriminator update, SURVEY 8(f)-1 -- the row-wise half of one SSInfoGAIL.update_ss_info_gail minibatch step,
+ *     bbc/rsl_rl/algorithms/gail.py:415-541 (see csrc/qa_disc_update.cu for the line-by-line map).  B = rows per batch; the three
+ *     batches [policy | labelled expert | unlabelled expert] are stacked into one (3B, width) matrix.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct QaDiscPrepareArgs {
+    int64_t B;
+    int32_t width, obs_dim;             /* 98 = disc_obs_len * 49, 49 */
+    const float* replay_states;         /* (R,width) policy replay ring */
+    const float* replay_eps;            /* (R) */
+    const float* replay_c;              /* (R,5) */
+    const float* expert_lb;             /* (n,width) */
+    const int64_t* expert_label;        /* (n) */
+    const float* expert_ulb;            /* (m,width) */
+    const int64_t* idx_pi; const int64_t* idx_lb; const int64_t* idx_ulb;   /* (B) each */
+    int32_t task_obs_weight_decay;
+    const float* task_obs_weight;       /* (1) DEVICE scalar (decays every iteration) or NULL */
+    float obs_disc_weight_step;
+    const float* norm_mean; const float* norm_std; float norm_clip;          /* (width) fp32 */
+    float* x; int64_t x_pitch;          /* (3B,width) out */
+    float* tgt_eps;                     /* (B) out: latent_eps of the policy rows */
+    int32_t* tgt_c;                     /* (B) out: argmax latent_c of the policy rows */
+    int32_t* tgt_label;                 /* (B) out: labels of the labelled expert rows */
+} QaDiscPrepareArgs;
+int qa_disc_prepare(const QaDiscPrepareArgs* a, void* stream);
+
+typedef struct QaDiscHeadsArgs {
+    int64_t B;
+    const float* h2; int64_t h2_pitch;  /* (3B,256) trunk output (post ReLU) */
+    const float* w_d; const float* b_d; /* linear (1,256), (1) */
+    const float* w_eps; const float* b_eps;       /* encoder_eps (1,256), (1) */
+    const float* w_c; int64_t w_c_pitch; const float* b_c;   /* classifier (5,256), (5) */
+    const float* tgt_eps; const int32_t* tgt_c; const int32_t* tgt_label;
+    float ss_coef, disc_coef, us_coef;
+    const float* info_max_coef;         /* (1) device scalar (ramps up during training) or NULL = 0 */
+    float* gz2; int64_t gz2_pitch;      /* (3B,256) out: d loss / d (pre-activation of trunk layer 2) */
+    float* v2; int64_t v2_pitch;        /* (B,256) out: relu'(z2) * w_d for the unlabelled rows, or NULL */
+    float* dw_d; float* db_d; float* dw_eps; float* db_eps; float* dw_c; int64_t dw_c_pitch; float* db_c;   /* accumulated */
+    float* db2;                         /* (256) accumulated: bias gradient of trunk layer 2 */
+    float* stats;                       /* (11) accumulated, the reference's return order (:540-541) */
+    float* prior_batch;                 /* (5) accumulated: mean over the unlabelled rows of the class probabilities */
+} QaDiscHeadsArgs;
+int qa_disc_heads_loss(const QaDiscHeadsArgs* a, void* stream);
+
+typedef struct QaDiscGpArgs {
+    int64_t B; int32_t width;
+    float coef;                         /* disc_grad_penalty */
+    float* g; int64_t g_pitch;          /* (B,width) in: d D / d x; out: d loss / d g */
+    float* stats;
+} QaDiscGpArgs;
+int qa_disc_gp_loss(const QaDiscGpArgs* a, void* stream);
+
+typedef struct QaDiscRegArgs {
+    const float* params; float* grads;  /* flat discriminator parameter / gradient buffers */
+    int64_t seg_off[3], seg_len[3];     /* trunk.0.weight, trunk.2.weight, linear.weight (padded extents) */
+    float logit_reg_coef, weight_decay_coef;
+    float* stats;
+} QaDiscRegArgs;
+int qa_disc_reg(const QaDiscRegArgs* a, void* stream);
+
+typedef struct QaNormMomentsArgs {
+    int64_t B; int32_t width, num_batches;
+    const float* x; int64_t x_pitch;    /* (num_batches*B, width) */
+    double* moments;                    /* (num_batches, 2, width): mean, E[x^2] */
+} QaNormMomentsArgs;
+int qa_norm_moments(const QaNormMomentsArgs* a, void* stream);
+
+typedef struct QaNormMergeArgs {
+    int64_t B; int32_t width, num_batches, world_size;   /* moments hold SUMS over world_size ranks */
+    const double* moments;
+    double* mean; double* var; double* count;             /* running state, (width), (width), (1) */
+    float* mean32; float* std32; double epsilon;          /* what the normalising kernels read */
+    float* prior; const float* prior_batch; float prior_soft_coef;   /* (5) or NULL */
+    float* std; const float* min_std; int32_t num_std;    /* policy std floor or NULL */
+} QaNormMergeArgs;
+int qa_norm_merge(const QaNormMergeArgs* a, void* stream);
 
 #ifdef __cplusplus
 }

@@ -43,6 +43,12 @@ extern "C" int qa_struct_size(int which) {
         case 25: return (int)sizeof(QaHeadFwdArgs);
         case 26: return (int)sizeof(QaHeadBwdArgs);
         case 27: return (int)sizeof(QaPolicySampleArgs);
+        case 28: return (int)sizeof(QaDiscPrepareArgs);
+        case 29: return (int)sizeof(QaDiscHeadsArgs);
+        case 30: return (int)sizeof(QaDiscGpArgs);
+        case 31: return (int)sizeof(QaDiscRegArgs);
+        case 32: return (int)sizeof(QaNormMomentsArgs);
+        case 33: return (int)sizeof(QaNormMergeArgs);
         default: return -1;
     }
 }

@@ -149,6 +149,41 @@ class QaPolicySampleArgs(C.Structure):
                 ("actions_st", vp), ("logp_st", vp), ("mu_st", vp), ("sigma_st", vp)]
 
 
+class QaDiscPrepareArgs(C.Structure):
+    _fields_ = [("B", C.c_int64), ("width", C.c_int32), ("obs_dim", C.c_int32), ("replay_states", vp), ("replay_eps", vp),
+                ("replay_c", vp), ("expert_lb", vp), ("expert_label", vp), ("expert_ulb", vp), ("idx_pi", vp), ("idx_lb", vp),
+                ("idx_ulb", vp), ("task_obs_weight_decay", C.c_int32), ("task_obs_weight", vp), ("obs_disc_weight_step", C.c_float),
+                ("norm_mean", vp), ("norm_std", vp), ("norm_clip", C.c_float), ("x", vp), ("x_pitch", C.c_int64), ("tgt_eps", vp),
+                ("tgt_c", vp), ("tgt_label", vp)]
+
+
+class QaDiscHeadsArgs(C.Structure):
+    _fields_ = [("B", C.c_int64), ("h2", vp), ("h2_pitch", C.c_int64), ("w_d", vp), ("b_d", vp), ("w_eps", vp), ("b_eps", vp),
+                ("w_c", vp), ("w_c_pitch", C.c_int64), ("b_c", vp), ("tgt_eps", vp), ("tgt_c", vp), ("tgt_label", vp),
+                ("ss_coef", C.c_float), ("disc_coef", C.c_float), ("us_coef", C.c_float), ("info_max_coef", vp), ("gz2", vp),
+                ("gz2_pitch", C.c_int64), ("v2", vp), ("v2_pitch", C.c_int64), ("dw_d", vp), ("db_d", vp), ("dw_eps", vp),
+                ("db_eps", vp), ("dw_c", vp), ("dw_c_pitch", C.c_int64), ("db_c", vp), ("db2", vp), ("stats", vp), ("prior_batch", vp)]
+
+
+class QaDiscGpArgs(C.Structure):
+    _fields_ = [("B", C.c_int64), ("width", C.c_int32), ("coef", C.c_float), ("g", vp), ("g_pitch", C.c_int64), ("stats", vp)]
+
+
+class QaDiscRegArgs(C.Structure):
+    _fields_ = [("params", vp), ("grads", vp), ("seg_off", C.c_int64 * 3), ("seg_len", C.c_int64 * 3),
+                ("logit_reg_coef", C.c_float), ("weight_decay_coef", C.c_float), ("stats", vp)]
+
+
+class QaNormMomentsArgs(C.Structure):
+    _fields_ = [("B", C.c_int64), ("width", C.c_int32), ("num_batches", C.c_int32), ("x", vp), ("x_pitch", C.c_int64), ("moments", vp)]
+
+
+class QaNormMergeArgs(C.Structure):
+    _fields_ = [("B", C.c_int64), ("width", C.c_int32), ("num_batches", C.c_int32), ("world_size", C.c_int32), ("moments", vp),
+                ("mean", vp), ("var", vp), ("count", vp), ("mean32", vp), ("std32", vp), ("epsilon", C.c_double), ("prior", vp),
+                ("prior_batch", vp), ("prior_soft_coef", C.c_float), ("std", vp), ("min_std", vp), ("num_std", C.c_int32)]
+
+
 class QaHeadBwdArgs(C.Structure):
     _fields_ = [("M", C.c_int64), ("N", C.c_int32), ("Kh", C.c_int32), ("act", C.c_int32), ("gz_scale", C.c_float),
                 ("gz", vp), ("gz_pitch", C.c_int64), ("h", vp), ("h_pitch", C.c_int64), ("w", vp), ("w_pitch", C.c_int64),
@@ -293,12 +328,19 @@ SYMBOLS = {
     "qa_head_fwd": (C.c_int, [C.POINTER(QaHeadFwdArgs), vp]),
     "qa_head_bwd": (C.c_int, [C.POINTER(QaHeadBwdArgs), vp]),
     "qa_policy_sample": (C.c_int, [C.POINTER(QaPolicySampleArgs), vp]),
+    "qa_disc_prepare": (C.c_int, [C.POINTER(QaDiscPrepareArgs), vp]),
+    "qa_disc_heads_loss": (C.c_int, [C.POINTER(QaDiscHeadsArgs), vp]),
+    "qa_disc_gp_loss": (C.c_int, [C.POINTER(QaDiscGpArgs), vp]),
+    "qa_disc_reg": (C.c_int, [C.POINTER(QaDiscRegArgs), vp]),
+    "qa_norm_moments": (C.c_int, [C.POINTER(QaNormMomentsArgs), vp]),
+    "qa_norm_merge": (C.c_int, [C.POINTER(QaNormMergeArgs), vp]),
 }
 
 STRUCT_ORDER = [QaActionPushArgs, QaTorqueArgs, QaTerrain, QaHeightScanArgs, QaMocapTable, QaMocapBlendArgs,
                 QaBbcConst, QaBbcStepArgs, QaCompactArgs, QaGaeArgs, QaGatherArgs, QaClipAdamArgs, QaLinearArgs, QaActBwdArgs, QaPpoLossArgs, QaLinearBwdArgs, QaHistEncArgs,
                 QaRowLossArgs, QaPpoScalarsArgs, QaDepthArgs, QaPpoLossTscArgs, QaTscConst, QaTscStepArgs,
-                QaDiscInputArgs, QaDiscRewardArgs, QaHeadFwdArgs, QaHeadBwdArgs, QaPolicySampleArgs]
+                QaDiscInputArgs, QaDiscRewardArgs, QaHeadFwdArgs, QaHeadBwdArgs, QaPolicySampleArgs, QaDiscPrepareArgs, QaDiscHeadsArgs,
+                QaDiscGpArgs, QaDiscRegArgs, QaNormMomentsArgs, QaNormMergeArgs]
 
 _LIB = None
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libqa_b200.so")

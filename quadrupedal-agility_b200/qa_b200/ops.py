@@ -585,3 +585,95 @@ def disc_reward(heads, obs, reward_t, dt, coefs, rewards_out, values=None, time_
     a.reward_terms = None if reward_terms is None else _p(reward_terms, f, "reward_terms")
     _abi.check(lib.qa_disc_reward(C.byref(a), _stream()), "qa_disc_reward")
     _count(1)
+
+
+# ---- K24 - K30: discriminator update ---------------------------------------------------------------------------------
+def disc_prepare(B, replay, expert, idx_pi, idx_lb, idx_ulb, task_obs_weight_decay, task_obs_weight, obs_disc_weight_step,
+                 norm_mean, norm_std, norm_clip, x, tgt_eps, tgt_c, tgt_label, obs_dim) -> None:
+    """gail.py:419-452: X = normalise(weight(gather(...))) for [policy | labelled | unlabelled] rows + per-row targets.
+    `replay` = ReplayBuffer (states, latent_eps, latent_c), `expert` = object with preloaded_s_lb / preloaded_label / preloaded_s_ulb."""
+    lib = _abi.load()
+    f, i64, i32 = torch.float32, torch.int64, torch.int32
+    a = _abi.QaDiscPrepareArgs()
+    a.B, a.width, a.obs_dim = int(B), int(replay.states.shape[1]), int(obs_dim)
+    a.replay_states, a.replay_eps, a.replay_c = _p(replay.states, f), _p(replay.latent_eps, f), _p(replay.latent_c, f)
+    a.expert_lb, a.expert_label, a.expert_ulb = _p(expert.preloaded_s_lb, f), _p(expert.preloaded_label, i64), _p(expert.preloaded_s_ulb, f)
+    a.idx_pi, a.idx_lb, a.idx_ulb = _p(idx_pi, i64), _p(idx_lb, i64), _p(idx_ulb, i64)
+    a.task_obs_weight_decay = int(bool(task_obs_weight_decay))
+    a.task_obs_weight = None if task_obs_weight is None else _p(task_obs_weight.reshape(1), f)
+    a.obs_disc_weight_step = float(obs_disc_weight_step)
+    a.norm_mean, a.norm_std, a.norm_clip = _p(norm_mean, f), _p(norm_std, f), float(norm_clip)
+    a.x, a.x_pitch = _p_strided(x, f, "x"), x.stride(0)
+    a.tgt_eps, a.tgt_c, a.tgt_label = _p(tgt_eps, f), _p(tgt_c, i32), _p(tgt_label, i32)
+    _abi.check(lib.qa_disc_prepare(C.byref(a), _stream()), "qa_disc_prepare")
+    _count(1)
+
+
+def disc_heads_loss(B, h2, disc, tgt_eps, tgt_c, tgt_label, ss_coef, disc_coef, us_coef, info_max_coef, gz2, v2, stats,
+                    prior_batch) -> None:
+    """gail.py:454-490 on the trunk output: heads forward, loss terms, gradients, prior estimate, accuracies (K25).
+    `disc` = Discriminator module whose parameters live in a flat buffer (gradients are accumulated into their `.grad`)."""
+    lib = _abi.load()
+    f = torch.float32
+    lin, eps, cls = disc.linear, disc.encoder_eps, disc.classifier
+    a = _abi.QaDiscHeadsArgs()
+    a.B = int(B)
+    a.h2, a.h2_pitch = _p_strided(h2, f, "h2"), h2.stride(0)
+    a.w_d, a.b_d = _p_strided(lin.weight, f, "w_d"), _p(lin.bias, f)
+    a.w_eps, a.b_eps = _p_strided(eps.weight, f, "w_eps"), _p(eps.bias, f)
+    a.w_c, a.w_c_pitch, a.b_c = _p_strided(cls.weight, f, "w_c"), cls.weight.stride(0), _p(cls.bias, f)
+    a.tgt_eps, a.tgt_c, a.tgt_label = _p(tgt_eps, f), _p(tgt_c, torch.int32), _p(tgt_label, torch.int32)
+    a.ss_coef, a.disc_coef, a.us_coef = float(ss_coef), float(disc_coef), float(us_coef)
+    a.info_max_coef = None if info_max_coef is None else _p(info_max_coef.reshape(1), f)
+    a.gz2, a.gz2_pitch = _p_strided(gz2, f, "gz2"), gz2.stride(0)
+    a.v2, a.v2_pitch = (None, 0) if v2 is None else (_p_strided(v2, f, "v2"), v2.stride(0))
+    a.dw_d, a.db_d = _p_strided(lin.weight.grad, f, "dw_d"), _p(lin.bias.grad, f)
+    a.dw_eps, a.db_eps = _p_strided(eps.weight.grad, f, "dw_eps"), _p(eps.bias.grad, f)
+    a.dw_c, a.dw_c_pitch, a.db_c = _p_strided(cls.weight.grad, f, "dw_c"), cls.weight.grad.stride(0), _p(cls.bias.grad, f)
+    a.db2 = _p(disc.trunk[2].bias.grad, f)
+    a.stats, a.prior_batch = _p(stats, f), _p(prior_batch, f)
+    _abi.check(lib.qa_disc_heads_loss(C.byref(a), _stream()), "qa_disc_heads_loss")
+    _count(1)
+
+
+def disc_gp_loss(g, coef, stats) -> None:
+    """Gradient penalty mean_i ||g_i||^2 (gail.py:492-502): value into stats[4], g := d loss / d g in place (K27)."""
+    lib = _abi.load()
+    a = _abi.QaDiscGpArgs(g.shape[0], g.shape[1], float(coef), _p_strided(g, torch.float32, "g"), g.stride(0), _p(stats, torch.float32))
+    _abi.check(lib.qa_disc_gp_loss(C.byref(a), _stream()), "qa_disc_gp_loss")
+    _count(1)
+
+
+def disc_reg(flat, segments, logit_reg_coef, weight_decay_coef, stats) -> None:
+    """Logit regulariser + weight decay (gail.py:488-490, 504-507): values into stats[5:7], gradients into flat.grad (K28).
+    `segments` = [(offset, length)] of trunk.0.weight, trunk.2.weight, linear.weight in the flat buffer."""
+    lib = _abi.load()
+    a = _abi.QaDiscRegArgs()
+    a.params, a.grads = _p(flat.data, torch.float32), _p(flat.grad, torch.float32)
+    for k, (o, n) in enumerate(segments):
+        a.seg_off[k], a.seg_len[k] = int(o), int(n)
+    a.logit_reg_coef, a.weight_decay_coef, a.stats = float(logit_reg_coef), float(weight_decay_coef), _p(stats, torch.float32)
+    _abi.check(lib.qa_disc_reg(C.byref(a), _stream()), "qa_disc_reg")
+    _count(1)
+
+
+def norm_moments(x, B, num_batches, moments) -> None:
+    """Column mean and E[x^2] (fp64) of each of the `num_batches` row blocks of x (K29)."""
+    lib = _abi.load()
+    a = _abi.QaNormMomentsArgs(int(B), x.shape[1], int(num_batches), _p_strided(x, torch.float32, "x"), x.stride(0),
+                               _p(moments, torch.float64))
+    _abi.check(lib.qa_norm_moments(C.byref(a), _stream()), "qa_norm_moments")
+    _count(1)
+
+
+def norm_merge(B, num_batches, world_size, moments, mean, var, count, mean32, std32, epsilon, prior=None, prior_batch=None,
+               prior_soft_coef=0.0, std=None, min_std=None) -> None:
+    """Sequential Chan merge of the batch moments into the running normaliser (utils.py:63-83), prior soft update
+    (gail.py:462-464), policy-std floor (:523-524), all on the device (K30)."""
+    lib = _abi.load()
+    f, f64 = torch.float32, torch.float64
+    a = _abi.QaNormMergeArgs(int(B), mean.shape[0], int(num_batches), int(world_size), _p(moments, f64), _p(mean, f64), _p(var, f64),
+                             _p(count.reshape(1), f64), _p(mean32, f), _p(std32, f), float(epsilon), _p(prior, f), _p(prior_batch, f),
+                             float(prior_soft_coef), _p(std, f), _p(min_std, f), 0 if std is None else int(std.numel()))
+    _abi.check(lib.qa_norm_merge(C.byref(a), _stream()), "qa_norm_merge")
+    _count(1)

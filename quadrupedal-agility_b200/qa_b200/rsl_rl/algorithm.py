@@ -626,7 +626,7 @@ class SSInfoGAIL:
         i_ulb = torch.randint(expert.preloaded_s_ulb.shape[0], (n_mb, mb), device=dev)
         self._disc_stats.zero_()
         if self.use_cuda_graph and (self.world_size == 1 or self.capture_collectives):
-            key = (id(expert), mb, ds.states.data_ptr())
+            key = (id(expert), mb, ds.states.data_ptr(), self._ensure_disc_plan(mb) is not None)
             if getattr(self, "_disc_graph_key", None) != key:
                 self._capture_disc(expert, mb)
                 self._disc_graph_key = key
@@ -648,7 +648,23 @@ class SSInfoGAIL:
         self.notify_disc_changed()
         return tuple((self._disc_stats / n_mb).tolist())
 
+    def _ensure_disc_plan(self, mb):
+        """The static-schedule discriminator step (disc_plan) when it applies: CUDA, tcgen05 layers, MSE loss, QA_DISC_PLAN != 0."""
+        from . import linear
+        from .disc_plan import DiscStepPlan
+        if os.environ.get("QA_DISC_PLAN", "1") != "1" or linear.get_mode() != "tc" or DiscStepPlan.supported(self) is not None:
+            self._disc_plan = None
+            return None
+        plan = getattr(self, "_disc_plan", None)
+        if plan is None or plan.B != mb:
+            plan = self._disc_plan = DiscStepPlan(self, mb)
+        return plan
+
     def _disc_step(self, expert, i_pi, i_lb, i_ulb):
+        plan = self._ensure_disc_plan(i_pi.shape[0])
+        if plan is not None:
+            plan.step(expert, i_pi, i_lb, i_ulb)
+            return
         ds = self.disc_storage
         out = self.update_ss_info_gail((ds.states[i_pi], ds.latent_eps[i_pi], ds.latent_c[i_pi]),
                                        (expert.preloaded_s_lb[i_lb], expert.preloaded_label[i_lb]), expert.preloaded_s_ulb[i_ulb])

@@ -41,7 +41,8 @@ class FakeOps:
     @staticmethod
     def linear_fwd(x, w, b, y, act, x_col0=0, y_col0=0):
         N, K = w.shape
-        y[:, y_col0:y_col0 + N] = _act(x[:, x_col0:x_col0 + K] @ w.t() + b, act)
+        z = x[:, x_col0:x_col0 + K] @ w.t()
+        y[:, y_col0:y_col0 + N] = _act(z if b is None else z + b, act)
 
     @staticmethod
     def head_fwd(h, w, b, y):
