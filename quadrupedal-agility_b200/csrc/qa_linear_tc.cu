@@ -30,6 +30,8 @@
 // is worth 1.5x.  Protocol: every TMA load of the pair completes on the LEADER's full barrier (expect_tx = both CTAs' bytes);
 // the leader's tcgen05.commit multicasts the slot-free and accumulator-ready arrivals to both CTAs; both CTAs' epilogue warps
 // arrive on the leader's accumulator-free barrier.
+// (Tried and dropped: cp.async.bulk.prefetch.tensor of the A stream 12 K blocks ahead -- 3-20 % SLOWER on every layer shape,
+// profiles/r2_k7_microbench_prefetch_on_rejected.txt vs r2_k7_microbench.txt: the prefetches compete with the demand loads for the same L2 request slots.)
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -233,7 +235,6 @@ struct TcSmem {
     // not depend on the accumulator, so their latency hides behind the main loop); the slab is lifted into registers as soon as
     // it lands, which frees the buffer for the next request
     float ybuf[EPI == EPI_ACTBWD ? TC_NEPI : 1][EPI == EPI_ACTBWD ? 32 * 32 : 4];
-    float bias_s[TC_NEPI][BN];              // per-epilogue-warp copy of the tile's bias slice
     uint64_t full[STAGES];
     uint64_t empty[STAGES];
     uint64_t tmem_full[2];
@@ -431,7 +432,6 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         // slab in shared memory -> TMA store (or TMA reduce-add for split-K).  TMA clips rows >= Mo / columns >= No.
         const int e = warp - 2, q = warp & 3, h = e >> 2;
         constexpr int CH = BN >= 32 ? 32 : 16;
-        float* bias_s = S.bias_s[e];
         float* ybuf = S.ybuf[EPI == EPI_ACTBWD ? e : 0];
         unsigned t = 0, chunk = 0;                        // tiles seen / own chunks processed
         auto n_chunks = [&](int w) {                      // chunks of work item w (all warps)
@@ -465,16 +465,12 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             if (w < total_items) y_request(w, h);
         }
         const unsigned te_leader = CG == 2 ? mapa_shared(&S.tmem_empty[0], 0) : 0u;
+        const bool bias_vec = (reinterpret_cast<uintptr_t>(g.bias) & 15u) == 0;      // n0, c0 are multiples of 16 floats
         for (int w = unit; w < total_items; w += units) {
             int m0, n0, kb0, nkb;
             decode(w, m0, n0, kb0, nkb);
             if (nkb <= 0) continue;
             const int nch = n_chunks(w);
-            if (EPI == EPI_STORE && h < nch) {
-                for (int i = lane; i < BN; i += 32)
-                    bias_s[i] = (g.bias != nullptr && n0 + i < g.No) ? __ldg(g.bias + n0 + i) : 0.f;
-                __syncwarp();
-            }
             const unsigned acc = t & 1, aph = (t >> 1) & 1;
             wait(&S.tmem_full[acc], aph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -492,8 +488,22 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                 // stores below): the bias slice while the TMEM load is in flight, the y slab once it has landed
                 float4 bv[CH / 4], yv4[CH / 4];
                 if (EPI == EPI_STORE) {
+                    // bias slice straight from global memory (<= 1 KB per tile: L1 resident after the first touch; every lane
+                    // reads the same address, one broadcast transaction per load)
+                    const float* bp = g.bias + n0 + c0;
+                    if (g.bias != nullptr && bias_vec && n0 + c0 + CH <= g.No) {
 #pragma unroll
-                    for (int j4 = 0; j4 < CH / 4; ++j4) bv[j4] = *reinterpret_cast<const float4*>(bias_s + c0 + j4 * 4);
+                        for (int j4 = 0; j4 < CH / 4; ++j4) bv[j4] = __ldg(reinterpret_cast<const float4*>(bp) + j4);
+                    } else {
+#pragma unroll
+                        for (int j4 = 0; j4 < CH / 4; ++j4) {
+                            float t4[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                t4[k] = (g.bias != nullptr && n0 + c0 + j4 * 4 + k < g.No) ? __ldg(bp + j4 * 4 + k) : 0.f;
+                            bv[j4] = make_float4(t4[0], t4[1], t4[2], t4[3]);
+                        }
+                    }
                 }
                 if (EPI == EPI_ACTBWD) {
                     wait(&S.ybar[e], chunk & 1);
@@ -512,7 +522,8 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
                         float* o = g.out + (size_t)row * g.out_pitch + g.out_c0 + n0 + c0;
 #pragma unroll
                         for (int j = 0; j < CH; ++j) {
-                            float x = __uint_as_float(r[j]) + bias_s[c0 + j];
+                            const float4 b4 = bv[j >> 2];
+                            float x = __uint_as_float(r[j]) + ((j & 3) == 0 ? b4.x : ((j & 3) == 1 ? b4.y : ((j & 3) == 2 ? b4.z : b4.w)));
                             if (g.act == 1) x = x > 0.f ? x : elu_neg(x);
                             else if (g.act == 2) x = fmaxf(x, 0.f);
                             if (n0 + c0 + j < g.No) o[j] = x;

@@ -11,6 +11,10 @@
 //   K21 qa_head_bwd   gz_prev = (gz W) * act'(h)   (the gradient w.r.t. the PREVIOUS layer's pre-activation, ELU'/ReLU'
 //                     recovered from its output h), dW += gz^T h, db += colsum(gz), db_prev += colsum(gz_prev)
 //                     -- what autograd does in 5 kernels (mm, mm, sum, elu_backward, sum) in ONE pass over h.
+// (Round 2 tried a lane = ROW formulation -- 32-row tiles transposed through shared memory, weights broadcast from shared
+// memory, no shuffles: tools/bench_heads.py measured 12.3 / 22.7 us fwd / bwd for the 12-wide actor head at M = 24576 against
+// 20.4 / 25.3 us here, but 23 us against 8.8 us for the 7 x 256 discriminator heads at M = 4096 and 17-19 us for every backward
+// regardless of M: one tile per warp is a serial shared-memory-latency chain that 12 warps per SM cannot hide.  Not kept.)
 // Lane = 4 consecutive hidden columns (float4); a row of 128 columns is one warp-wide 512 B access, a row of 64 columns half
 // a warp (two rows per pass).  W sits in shared memory as [n][Kh].
 #include "qa_b200.h"
