@@ -13,18 +13,16 @@ struct MocapBlendIdx {
 };
 
 // traj_time_sample_batch + the index half of get_full_frame_at_time_batch
-__device__ __forceinline__ MocapBlendIdx mocap_blend_index(const QaMocapTable& tb, int clip, double time_u,
-                                                           double time_between_frames, int disc_obs_len) {
-    const double len_s = tb.clip_len_s[clip];
-    const double subst = time_between_frames * (double)disc_obs_len + tb.clip_frame_dur[clip];
+// operands: the chosen clip's length [s], frame duration [s], frame count and first row
+__device__ __forceinline__ MocapBlendIdx mocap_blend_index_meta(double len_s, double frame_dur, double n, int start, double time_u,
+                                                                double time_between_frames, int disc_obs_len) {
+    const double subst = time_between_frames * (double)disc_obs_len + frame_dur;
     double t = (len_s - subst) * time_u;
     t = fmax(0.0 + 1e-7, t);
     const double p = t / len_s;
-    const double n = tb.clip_nframes[clip];
     const double pn = p * n;
     const double lo = floor(pn), hi = ceil(pn);
     MocapBlendIdx r;
-    const int start = tb.clip_start[clip];
     int ilo = (int)lo, ihi = (int)hi;
     // the reference would raise on an out-of-range row; clamp so that a bad draw cannot fault
     const int last = (int)n - 1;
@@ -34,6 +32,12 @@ __device__ __forceinline__ MocapBlendIdx mocap_blend_index(const QaMocapTable& t
     r.row_hi = start + ihi;
     r.blend = (float)(pn - lo);
     return r;
+}
+
+__device__ __forceinline__ MocapBlendIdx mocap_blend_index(const QaMocapTable& tb, int clip, double time_u,
+                                                           double time_between_frames, int disc_obs_len) {
+    return mocap_blend_index_meta(tb.clip_len_s[clip], tb.clip_frame_dur[clip], tb.clip_nframes[clip], tb.clip_start[clip], time_u,
+                                  time_between_frames, disc_obs_len);
 }
 
 // quaternion_slerp, utils.py:126-159 (spin=0, shortestpath=True).  NB the reference scales by

@@ -46,6 +46,9 @@ enum {
     SC_N = 32
 };
 
+// slots of T2Smem::rst
+enum { RST_MP = 0, RST_MV = 12, RST_Q = 24, RST_LIN = 28, RST_ANG = 31, RST_POS = 34, RST_KEY = 37, RST_N = 52 };
+
 struct __align__(16) T2Smem {
     float obs[T2_ENVS * ROW];
     float hist[T2_ENVS * HIST_W];
@@ -67,6 +70,7 @@ struct __align__(16) T2Smem {
     uint8_t cont_out[T2_ENVS * 4], cfilt_out[T2_ENVS * 4];
     float scal[T2_ENVS][SC_N];
     float rootB[T2_ENVS * 13];           // scalar warp B's private copy of the root tile
+    float rst[T2_ENVS][RST_N];           // a resetting env's precomputed mocap frame (reset_precompute)
     uint64_t bar, bar_small;
     unsigned last;
 };
@@ -89,6 +93,10 @@ __device__ __forceinline__ long long k2_gtime() {
     do {                                                                                   \
         if (threadIdx.x == (who) && blockIdx.x < K2_TRACE_CTAS) g_k2_trace[blockIdx.x][slot] = k2_gtime(); \
     } while (0)
+// attribution experiments (trace build only): bit 0 = the big output tiles (obs, privileged obs, history, disc obs) are NOT stored
+__device__ int g_k2_dbg_mode = 0;
+extern "C" int qa_k2_trace_set_mode(int mode) { return (int)cudaMemcpyToSymbol(g_k2_dbg_mode, &mode, sizeof(int)); }
+#define K2_DBG_NO_TILE_STORES (g_k2_dbg_mode & 1)
 extern "C" int qa_k2_trace_dump(long long* host, int max_ctas) {
     const int n = max_ctas < K2_TRACE_CTAS ? max_ctas : K2_TRACE_CTAS;
     return (int)cudaMemcpyFromSymbol(host, g_k2_trace, sizeof(long long) * 24 * n);
@@ -96,6 +104,7 @@ extern "C" int qa_k2_trace_dump(long long* host, int max_ctas) {
 #else
 #define STAMP(slot, who) do { } while (0)
 #define GSTAMP(slot, who) do { } while (0)
+#define K2_DBG_NO_TILE_STORES 0
 #endif
 #define T_ENV 0                          // first env warp, lane 0
 #define T_SA (W_SA * 32)                 // scalar warp A, lane 0
@@ -143,6 +152,106 @@ __device__ __forceinline__ void copy16(void* gdst, const void* ssrc, int n16, in
     for (int i = lane; i < n16; i += 32) reinterpret_cast<float4*>(gdst)[i] = reinterpret_cast<const float4*>(ssrc)[i];
 }
 
+// Everything of reset_idx (:178-240, :598-612) that does NOT depend on this step's scalar program: the mocap clip / time draw,
+// the blended frame (slerp of the root quaternion, lerps of root position / velocities / DOF state) and the key-body positions
+// on the new root.  The draws are functions of (env, site, step) only and the reset DECISION needs just the contact ballot,
+// the episode counter and the root height, so the env warp runs this ~4 us chain of dependent global loads BEFORE barrier 2,
+// next to the scalar warps' P2a / P2b, instead of after it (profiles/r2_k2_phase_trace_reset_path.txt: the 8.6 us reset path
+// behind barrier 2 set the kernel's tail -- ~11 % of the CTAs hold a resetting env).  Results go to `rst`; P3b commits them.
+// Same arithmetic, op for op, as the in-place version it replaces.
+__device__ __forceinline__ void reset_precompute(const QaBbcConst& c, const K2Step& a, int e, int lane, int B, float* rst,
+                                                 int mode_off) {
+    // `mode_off`: lane 18 + k holds mocap.mode_offset[k] (loaded at kernel entry; production draws only)
+    int clip;
+    double time_u;
+    // clip metadata of the chosen clip (mocap_blend_index's operands)
+    double len_s, frame_dur, nframes;
+    int start;
+    bool have_meta = false;
+    if (a.mocap_clip_idx != nullptr) {
+        clip = a.mocap_clip_idx[e];
+        time_u = a.mocap_time_u[e];
+    } else {
+        Philox4 rr = philox4x32_10((uint32_t)e, SITE_MOCAP, (uint32_t)a.rng_step, (uint32_t)(a.rng_step >> 32),
+                                   (uint32_t)a.rng_seed, (uint32_t)(a.rng_seed >> 32));
+        const double cu = u64_to_unit_f64(rr.v[0], rr.v[1]);
+        time_u = u64_to_unit_f64(rr.v[2], rr.v[3]);
+        // the behaviour mode P2b is going to draw for this reset (same site, same stream)
+        const int m = draw_site(c, a, e, SITE_RT0, a.rt_eps_u, a.rt_c_idx, a.rt_cmd_u).c_idx;
+        const int lo = __shfl_sync(QA_FULL, mode_off, 18 + m), hi = __shfl_sync(QA_FULL, mode_off, 18 + m + 1);
+        // The sequential scan `j = lo; while (j < hi - 1 && cdf[j] <= cu) ++j` ends at the first j in [lo, hi - 1) with
+        // !(cdf[j] <= cu), else at hi - 1.  32 candidates per round, one per lane; every lane also fetches ITS candidate's clip
+        // id and metadata, so the winner's operands arrive with two dependent loads instead of four.
+        clip = -1;
+        for (int base = lo; base <= hi - 1; base += 32) {
+            const int jj = base + lane;
+            const bool in = jj <= hi - 1;
+            const double cj = (in && jj < hi - 1) ? a.mocap.mode_cdf[jj] : 0.0;
+            const int cl = in ? min(max(a.mocap.mode_clips[jj], 0), a.mocap.num_clips - 1) : 0;
+            const double c_len = a.mocap.clip_len_s[cl], c_dur = a.mocap.clip_frame_dur[cl], c_n = a.mocap.clip_nframes[cl];
+            const int c_start = a.mocap.clip_start[cl];
+            const bool stop = in && (jj == hi - 1 || !(cj <= cu));
+            const unsigned hit = __ballot_sync(QA_FULL, stop);
+            if (hit != 0u) {
+                const int w = __ffs((int)hit) - 1;
+                clip = __shfl_sync(QA_FULL, cl, w);
+                len_s = __shfl_sync(QA_FULL, c_len, w), frame_dur = __shfl_sync(QA_FULL, c_dur, w);
+                nframes = __shfl_sync(QA_FULL, c_n, w), start = __shfl_sync(QA_FULL, c_start, w);
+                have_meta = true;
+                break;
+            }
+        }
+        if (clip < 0) clip = a.mocap.mode_clips[max(lo, hi - 1)];             // empty mode: what the scan would read
+    }
+    clip = min(max(clip, 0), a.mocap.num_clips - 1);
+    if (!have_meta) {
+        len_s = a.mocap.clip_len_s[clip], frame_dur = a.mocap.clip_frame_dur[clip], nframes = a.mocap.clip_nframes[clip];
+        start = a.mocap.clip_start[clip];
+    }
+    const MocapBlendIdx bi = mocap_blend_index_meta(len_s, frame_dur, nframes, start, time_u, c.time_between_frames, c.disc_obs_len);
+    const float* f0 = a.mocap.frames + (size_t)bi.row_lo * QA_MOCAP_W;
+    const float* f1 = a.mocap.frames + (size_t)bi.row_hi * QA_MOCAP_W;
+    const float bl = bi.blend;
+    // every global operand of the frame first (independent loads, one latency), then the arithmetic
+    const bool dl = lane < QA_NUM_DOF;
+    const int d_ = dl ? lane : 0;
+    const float p0 = f0[7 + d_], p1 = f1[7 + d_], w0 = f0[37 + d_], w1 = f1[37 + d_];
+    float h0[7], h1[7], u0[6], u1[6];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) h0[k] = f0[k], h1[k] = f1[k];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) u0[k] = f0[31 + k], u1[k] = f1[31 + k];
+    const float ox = a.env_origins[e * 3 + 0], oy = a.env_origins[e * 3 + 1], oz = a.env_origins[e * 3 + 2];
+    float kx = 0.f, ky = 0.f, kz = 0.f;
+    if (lane < 4) {
+        const float* kp = a.rigid_body_state + ((size_t)e * B + c.feet_indices[lane]) * 13;
+        kx = kp[0], ky = kp[1], kz = kp[2];
+    }
+    const Quat qs = slerp_ref(Quat{h0[3], h0[4], h0[5], h0[6]}, Quat{h1[3], h1[4], h1[5], h1[6]}, bl);
+    if (dl) {
+        rst[RST_MP + lane] = mocap_lerp(p0, p1, bl);
+        rst[RST_MV + lane] = mocap_lerp(w0, w1, bl);
+    }
+    // root linear (lane 0) and angular (lane 1) velocity: the same rotation on two lanes
+    const int vo = lane == 1 ? 3 : 0;
+    const Vec3 vel = quat_rotate_sgn(
+        qs, Vec3{mocap_lerp(vo ? u0[3] : u0[0], vo ? u1[3] : u1[0], bl), mocap_lerp(vo ? u0[4] : u0[1], vo ? u1[4] : u1[1], bl),
+                 mocap_lerp(vo ? u0[5] : u0[2], vo ? u1[5] : u1[2], bl)}, 1.f);
+    const float px = mocap_lerp(h0[0], h1[0], bl) + ox, py = mocap_lerp(h0[1], h1[1], bl) + oy, pz = mocap_lerp(h0[2], h1[2], bl) + oz;
+    if (lane == 0) {
+        rst[RST_Q + 0] = qs.x, rst[RST_Q + 1] = qs.y, rst[RST_Q + 2] = qs.z, rst[RST_Q + 3] = qs.w;
+        rst[RST_POS + 0] = px, rst[RST_POS + 1] = py, rst[RST_POS + 2] = pz;
+    }
+    if (lane < 2) rst[RST_LIN + vo + 0] = vel.x, rst[RST_LIN + vo + 1] = vel.y, rst[RST_LIN + vo + 2] = vel.z;   // RST_ANG = RST_LIN + 3
+    if (lane < 4) {                                                         // key-body positions on the mocap root
+        const Quat hq = heading_quat_inv(qs);
+        const Vec3 o = quat_rotate_sgn(hq, Vec3{kx - px, ky - py, kz - pz}, 1.f);
+        rst[RST_KEY + lane * 3 + 0] = o.x * c.s_key_pos, rst[RST_KEY + lane * 3 + 1] = o.y * c.s_key_pos;
+        rst[RST_KEY + lane * 3 + 2] = o.z * c.s_key_pos;
+    }
+    __syncwarp();
+}
+
 __global__ void __launch_bounds__(T2_THREADS, 4)
 k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_constant__ QaBbcStepArgs a_in) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -167,7 +276,9 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
     // as those ~1 KB land, long before the 18 KB history tile); env warps fetch their last action
     float4 ld0 = {0.f, 0.f, 0.f, 0.f}, ld1 = {0.f, 0.f, 0.f, 0.f};
     float4* st1 = nullptr;
-    float k0 = 0.f, k1 = 0.f, k2 = 0.f, alast = 0.f;
+    float k0 = 0.f, k1 = 0.f, k2 = 0.f, alast = 0.f, qc = 0.f;
+    long long ep_pre = 0;
+    int mode_off = 0;
     if (wid == W_SA) {
         if (lane < 26) ld0 = reinterpret_cast<const float4*>(r.root_states + (size_t)e0 * 13)[lane];
         const float4* g = nullptr;
@@ -183,8 +294,16 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
         const int el = lane >> 2, j = lane & 3;
         const float* kp = r.rigid_body_state + ((size_t)(e0 + el) * B + c.feet_indices[j]) * 13;
         k0 = kp[0], k1 = kp[1], k2 = kp[2];
-    } else if (lane < QA_NUM_DOF) {
-        alast = r.action_history_buf[(size_t)(e0 + wid) * QA_ACT_HIST_LEN * QA_NUM_DOF + (QA_ACT_HIST_LEN - 1) * QA_NUM_DOF + lane];
+    } else {
+        if (lane < QA_NUM_DOF)
+            alast = r.action_history_buf[(size_t)(e0 + wid) * QA_ACT_HIST_LEN * QA_NUM_DOF + (QA_ACT_HIST_LEN - 1) * QA_NUM_DOF + lane];
+        // the env's root quaternion, one component per lane 12..15: this warp computes the euler angles while the tiles are in
+        // flight (they were the longest role of scalar warp A's chain: two atan2f + one asinf, ~2 us of dependent issue)
+        else if (lane < QA_NUM_DOF + 4) qc = r.root_states[(size_t)(e0 + wid) * 13 + 3 + (lane - QA_NUM_DOF)];
+        // root height and episode counter: with the contact ballot of P1 they decide the reset (:168-176) before P2b says so
+        else if (lane == 16) qc = r.root_states[(size_t)(e0 + wid) * 13 + 2];
+        else if (lane == 17) ep_pre = r.episode_length_buf[e0 + wid];
+        else if (lane >= 18 && lane < 18 + QA_DIM_C + 1 && r.mocap_clip_idx == nullptr) mode_off = r.mocap.mode_offset[lane - 18];
     }
     if (tid == 0) {
         mbar_init(&S.bar_small, 12);
@@ -253,12 +372,34 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
                 nz[kk] = (2.f * u - 1.f) * c.noise_scale[k];
             }
         }
+        {
+            // euler angles of the pre-reset root (:141, get_euler_xyz): lanes 0 / 2 run the two atan2f side by side, lane 1
+            // the asinf; same expressions, op for op, as the scalar program had
+            const Quat q = {__shfl_sync(QA_FULL, qc, QA_NUM_DOF), __shfl_sync(QA_FULL, qc, QA_NUM_DOF + 1),
+                            __shfl_sync(QA_FULL, qc, QA_NUM_DOF + 2), __shfl_sync(QA_FULL, qc, QA_NUM_DOF + 3)};
+            float ang = 0.f;
+            if (lane == 0 || lane == 2) {
+                const float num = lane == 0 ? 2.0f * (q.w * q.x + q.y * q.z) : 2.0f * (q.w * q.z + q.x * q.y);
+                const float den = lane == 0 ? 1.0f - 2.0f * (q.x * q.x + q.y * q.y) : 1.0f - 2.0f * (q.y * q.y + q.z * q.z);
+                ang = atan2f(num, den);
+            } else if (lane == 1) {
+                float t2 = 2.0f * (q.w * q.y - q.z * q.x);
+                t2 = clampf(t2, -1.f, 1.f);
+                ang = asinf(t2);
+            }
+            if (lane < 3) S.rpy[el * 3 + lane] = ang;
+            if (lane < 2) {
+                S.obs[el * ROW + lane] = ang;
+                S.disc[el * QA_NUM_OBS_DISC + lane] = ang;
+            }
+        }
         STAMP(1, T_ENV);
         mbar_wait(&S.bar_small, 0);
         STAMP(2, T_ENV);
         // ---------------- P1 (env-warp half): contact-force norms, lanes = bodies --------------------------------
         // (the nine 12-wide DOF sums run on scalar warp B with lane = (env, leg): 8x fewer warp instructions)
         const float dof_pos = S.dof[el * 24 + 2 * d_], dof_vel = S.dof[el * 24 + 2 * d_ + 1];
+        bool early_reset = false;
         {
             float nrm = 0.f;
             if (lane < B) {
@@ -266,6 +407,11 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
                 nrm = sqrtf(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]);
             }
             const unsigned hit_term = __ballot_sync(QA_FULL, nrm > 1.f) & c.termination_body_mask;
+            {
+                const long long epn = __shfl_sync(QA_FULL, ep_pre, 17) + 1;                          // :133
+                const float rz = __shfl_sync(QA_FULL, qc, 16);
+                early_reset = (hit_term != 0u) || ((float)epn > c.max_episode_length) || (rz < -6.0f);   // == P2b's is_reset
+            }
             const unsigned hit_col = __ballot_sync(QA_FULL, nrm > 0.1f) & c.penalised_body_mask;
             float ff[4];
 #pragma unroll
@@ -284,6 +430,7 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
             }
         }
         bar_arrive(1, T2_THREADS);          // P1 results are in S.scal: the scalar warp may run P2b while this warp goes on
+        if (early_reset) reset_precompute(c, a, e, lane, B, S.rst[el], mode_off);
         STAMP(3, T_ENV);
         // ---------------- P3a: everything of the row that depends on loaded inputs only ---------------------
         // (the reset path of P3b redoes the DOF lanes for the ~1.5 % reset envs)
@@ -329,6 +476,16 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
             }
         }
         STAMP(6, T_ENV);
+        // Early store of the history tile (29 % of the CTA's output bytes): nine of its ten slots are final now.  The TMA engine
+        // writes the tile out while the scalar chain (P2b) and P3b run; the newest slot -- and the whole history of the ~1.5 %
+        // envs that reset or refill -- are patched with plain stores in P4, after this bulk store has COMPLETED.  What the engine
+        // reads out of the lanes P3b is still going to write does not matter: exactly those lanes are patched.
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        bar_sync(2, T2_ENVS * 32);                                             // the eight env warps: every shifted row is in S.hist
+        if (wid == 2 && lane == 0 && !K2_DBG_NO_TILE_STORES) {
+            bulk_store_bytes(a.obs_history_buf + (size_t)e0 * HIST_W, S.hist, T2_ENVS * HIST_W * 4);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
         any_state_write = __syncthreads_or(any_state_write ? 1 : 0) != 0;      // barrier 2: P2b results are in
         STAMP(7, T_ENV);
 
@@ -338,31 +495,10 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
         const bool is_reset = sc[SC_RESET] != 0.f;
         float dv_out = dof_vel;
         if (is_reset) {
-            int clip;
-            double time_u;
-            if (a.mocap_clip_idx != nullptr) {
-                clip = a.mocap_clip_idx[e];
-                time_u = a.mocap_time_u[e];
-            } else {
-                Philox4 rr = philox4x32_10((uint32_t)e, SITE_MOCAP, (uint32_t)a.rng_step, (uint32_t)(a.rng_step >> 32),
-                                           (uint32_t)a.rng_seed, (uint32_t)(a.rng_seed >> 32));
-                const double cu = u64_to_unit_f64(rr.v[0], rr.v[1]);
-                time_u = u64_to_unit_f64(rr.v[2], rr.v[3]);
-                const int m = __float_as_int(sc[SC_MODE]);
-                const int lo = a.mocap.mode_offset[m], hi = a.mocap.mode_offset[m + 1];
-                int j = lo;
-                while (j < hi - 1 && a.mocap.mode_cdf[j] <= cu) ++j;
-                clip = a.mocap.mode_clips[j];
-            }
-            clip = min(max(clip, 0), a.mocap.num_clips - 1);
-            const MocapBlendIdx bi = mocap_blend_index(a.mocap, clip, time_u, c.time_between_frames, c.disc_obs_len);
-            const float* f0 = a.mocap.frames + (size_t)bi.row_lo * QA_MOCAP_W;
-            const float* f1 = a.mocap.frames + (size_t)bi.row_hi * QA_MOCAP_W;
-            const float bl = bi.blend;
-            const Quat qs = slerp_ref(Quat{f0[3], f0[4], f0[5], f0[6]}, Quat{f1[3], f1[4], f1[5], f1[6]}, bl);
+            float* rs = S.rst[el];
+            if (!early_reset) reset_precompute(c, a, e, lane, B, rs, mode_off);             // (the early decision is P2b's; kept for safety)
             if (dl) {
-                const float mp = mocap_lerp(f0[7 + lane], f1[7 + lane], bl);
-                const float mv = mocap_lerp(f0[37 + lane], f1[37 + lane], bl);
+                const float mp = rs[RST_MP + lane], mv = rs[RST_MV + lane];
                 S.dof[el * 24 + 2 * lane] = mp;
                 S.dof[el * 24 + 2 * lane + 1] = mv;
                 const float dq = (mp - c.default_dof_pos[lane]) * c.s_dof_pos;
@@ -374,31 +510,11 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
                 disc[21 + lane] = dv;
                 dv_out = mv;
             }
-            const Vec3 lin = quat_rotate_sgn(
-                qs, Vec3{mocap_lerp(f0[31], f1[31], bl), mocap_lerp(f0[32], f1[32], bl), mocap_lerp(f0[33], f1[33], bl)}, 1.f);
-            const Vec3 ang = quat_rotate_sgn(
-                qs, Vec3{mocap_lerp(f0[34], f1[34], bl), mocap_lerp(f0[35], f1[35], bl), mocap_lerp(f0[36], f1[36], bl)}, 1.f);
-            __syncwarp();
-            if (lane == 0) {
-                R[0] = mocap_lerp(f0[0], f1[0], bl) + a.env_origins[e * 3 + 0];
-                R[1] = mocap_lerp(f0[1], f1[1], bl) + a.env_origins[e * 3 + 1];
-                R[2] = mocap_lerp(f0[2], f1[2], bl) + a.env_origins[e * 3 + 2];
-                R[3] = qs.x, R[4] = qs.y, R[5] = qs.z, R[6] = qs.w;
-                R[7] = lin.x, R[8] = lin.y, R[9] = lin.z;
-                R[10] = ang.x, R[11] = ang.y, R[12] = ang.z;
-            }
+            if (lane < 13) R[lane] = lane < 3 ? rs[RST_POS + lane] : (lane < 7 ? rs[RST_Q + lane - 3] : rs[RST_LIN + lane - 7]);
             float* gah = a.action_history_buf + (size_t)e * QA_ACT_HIST_LEN * QA_NUM_DOF;
             for (int i = lane; i < QA_ACT_HIST_LEN * QA_NUM_DOF; i += 32) gah[i] = 0.f;
             if (lane < 4) a.feet_air_time[e * 4 + lane] = 0.f;
-            __syncwarp();
-            if (lane < 4) {                                                     // key-body positions on the mocap root
-                const Quat hq = heading_quat_inv(Quat{R[3], R[4], R[5], R[6]});
-                const Vec3 local = {S.key[el * 12 + lane * 3 + 0] - R[0], S.key[el * 12 + lane * 3 + 1] - R[1],
-                                    S.key[el * 12 + lane * 3 + 2] - R[2]};
-                const Vec3 o = quat_rotate_sgn(hq, local, 1.f);
-                disc[33 + lane * 3 + 0] = o.x * c.s_key_pos, disc[33 + lane * 3 + 1] = o.y * c.s_key_pos;
-                disc[33 + lane * 3 + 2] = o.z * c.s_key_pos;
-            }
+            if (lane < 12) disc[33 + lane] = rs[RST_KEY + lane];                // key-body positions on the mocap root
             __syncwarp();
         }
         if (dl) a.last_dof_vel[(size_t)e * 12 + lane] = dv_out;                    // :159 (post-reset dof_vel)
@@ -415,10 +531,13 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
         {
             float* h = S.hist + el * HIST_W;
             if (S.ep[el] <= 1) {                                                   // fill: all 10 slots = current 57-vector
+                int k = lane;                                                      // i % QA_NUM_PROP, carried
                 for (int i = lane; i < HIST_W; i += 32) {
-                    const float v = clampf(row[i % QA_NUM_PROP], -c.clip_obs, c.clip_obs);
+                    const float v = clampf(row[k], -c.clip_obs, c.clip_obs);
                     row[HIST_OFF + i] = v;
                     h[i] = v;
+                    k += 32;
+                    if (k >= QA_NUM_PROP) k -= QA_NUM_PROP;
                 }
             } else {                                                               // newest slot only (shift done in P3a)
                 for (int i = lane; i < QA_NUM_PROP; i += 32) {
@@ -445,7 +564,7 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
     } else if (wid == W_SA) {
         // ---------------- P2a (scalar warp A, lane = (env, role)): the thread-per-env scalar program of round 1 split four ways
         // so that the dependent chain is the longest ROLE, not their sum (same arithmetic per quantity, bit for bit):
-        //   role 0  base linear velocity            role 2  projected gravity + euler angles
+        //   role 0  base linear velocity            role 2  projected gravity (the euler angles run on the env warps)
         //   role 1  base angular velocity           role 3  centre terrain height, periodic resample, push
         if (lane < 26) reinterpret_cast<float4*>(S.root)[lane] = ld0;
         if (st1 != nullptr) *st1 = ld1;
@@ -473,23 +592,8 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
             row[2] = vec.x * c.s_ang_vel, row[3] = vec.y * c.s_ang_vel, row[4] = vec.z * c.s_ang_vel;
             disc[6] = vec.x * c.s_ang_vel_dist, disc[7] = vec.y * c.s_ang_vel_dist, disc[8] = vec.z * c.s_ang_vel_dist;
         } else if (role == 2) {
-            const Vec3 pg = quat_rotate_sgn(q, Vec3{0.f, 0.f, -1.f}, -1.f);             // :140
-            float roll, pitch, yaw;
-            {
-                const float t0 = 2.0f * (q.w * q.x + q.y * q.z);
-                const float t1 = 1.0f - 2.0f * (q.x * q.x + q.y * q.y);
-                roll = atan2f(t0, t1);
-                float t2 = 2.0f * (q.w * q.y - q.z * q.x);
-                t2 = clampf(t2, -1.f, 1.f);
-                pitch = asinf(t2);
-                const float t3 = 2.0f * (q.w * q.z + q.x * q.y);
-                const float t4 = 1.0f - 2.0f * (q.y * q.y + q.z * q.z);
-                yaw = atan2f(t3, t4);
-            }
+            const Vec3 pg = quat_rotate_sgn(q, Vec3{0.f, 0.f, -1.f}, -1.f);             // :140 (euler angles: env warps)
             S.pg[el * 3 + 0] = pg.x, S.pg[el * 3 + 1] = pg.y, S.pg[el * 3 + 2] = pg.z;
-            S.rpy[el * 3 + 0] = roll, S.rpy[el * 3 + 1] = pitch, S.rpy[el * 3 + 2] = yaw;
-            row[0] = roll, row[1] = pitch;
-            disc[0] = roll, disc[1] = pitch;
         } else {
             if (c.measure_heights) center_h = terrain_center_height(a.terrain, yaw_quat(q), R[0], R[1], c.center_px, c.center_py);
             const float root_h_pre = root_z_pre - center_h;                             // pre-reset quantities (:263-291)
@@ -698,15 +802,28 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     STAMP(9, T_ENV);
-    if (lane == 0 && wid < 6) {
+    if (wid == 2 && !K2_DBG_NO_TILE_STORES) {
+        // history: the early bulk store has to be complete before its stale lanes are overwritten (write-after-write on the
+        // same addresses from two proxies); then the newest slot of every env, everything of a reset / refilled env
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        __syncwarp();
+#pragma unroll 1
+        for (int el = 0; el < T2_ENVS; ++el) {
+            float* gh = a.obs_history_buf + (size_t)(e0 + el) * HIST_W;
+            const float* h = S.hist + el * HIST_W;
+            const int lo = (S.ep[el] <= 1) ? 0 : HIST_W - QA_NUM_PROP;
+            for (int i = lo + lane; i < HIST_W; i += 32) gh[i] = h[i];
+        }
+    }
+    if (lane == 0 && wid < 6 && wid != 2) {
         bool issued = true;
-        switch (wid) {
+        switch (K2_DBG_NO_TILE_STORES && wid < 4 ? 99 : wid) {
+            case 99: issued = false; break;
             case 0: bulk_store_bytes(a.obs_buf + (size_t)e0 * ROW, S.obs, T2_ENVS * ROW * 4); break;
             case 1:
                 if (a.privileged_obs_buf != a.obs_buf) bulk_store_bytes(a.privileged_obs_buf + (size_t)e0 * ROW, S.obs, T2_ENVS * ROW * 4);
                 else issued = false;
                 break;
-            case 2: bulk_store_bytes(a.obs_history_buf + (size_t)e0 * HIST_W, S.hist, T2_ENVS * HIST_W * 4); break;
             case 3: bulk_store_bytes(a.obs_disc_buf + (size_t)e0 * QA_NUM_OBS_DISC, S.disc, T2_ENVS * QA_NUM_OBS_DISC * 4); break;
             case 4:                                     // simulator memory is only written on reset / push
                 if (any_state_write) bulk_store_bytes(a.root_states + (size_t)e0 * 13, S.root, T2_ENVS * 13 * 4);

@@ -28,8 +28,12 @@ SEGMENTS = [  # (name, stamp_from, stamp_to); stamps 0-11 env warp 0, 12-15/18 s
     ("env: history shift", 5, 6),
     ("env: barrier 2 wait (P2b)", 6, 7),
     ("env: P3b", 7, 8),
-    ("env: barrier 3", 8, 9),
-    ("P4 issue store", 9, 10),
+    ("env: P3b end -> barrier 3 stamp (the clock read is hoisted ABOVE the barrier)", 8, 9),
+    ("barrier 3 wait (slowest env warp of the CTA, e.g. a reset) + store issue", 9, 10),
+    ("reset env: barrier 2 -> clip chosen (draw + CDF search)", 7, 21),
+    ("reset env: clip chosen -> blend rows known (clip metadata, fp64 index math)", 21, 22),
+    ("reset env: slerp of the root quaternion (first touch of the frame rows)", 22, 23),
+    ("reset env: slerp done -> end of P3b", 23, 8),
     ("P4 wait_group.read", 10, 11),
     ("scalar A: entry -> own loads landed", 0, 12),
     ("scalar A: P2a", 12, 13),
@@ -65,7 +69,7 @@ def build():
     print("built", os.path.join(OUT, "libqa_b200.so"))
 
 
-def run(n_envs, reps):
+def run(n_envs, reps, mode=0):
     import numpy as np
     import torch
     from qa_b200 import _abi
@@ -73,6 +77,8 @@ def run(n_envs, reps):
     lib = _abi.load()
     lib.qa_k2_trace_dump.restype = ctypes.c_int
     lib.qa_k2_trace_dump.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    lib.qa_k2_trace_set_mode.restype = ctypes.c_int
+    lib.qa_k2_trace_set_mode.argtypes = [ctypes.c_int]
     import bench
     from qa_b200.legged_robot import LeggedRobot, RecordedPhysics
     dev = torch.device("cuda:0")
@@ -85,6 +91,9 @@ def run(n_envs, reps):
     env.global_counter = 1
     env.use_device_step_counter(True)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    assert lib.qa_k2_trace_set_mode(mode) == 0
+    if mode:
+        print(f"#### attribution mode {mode}: bit 0 = the four big output tiles are not stored")
     n_cta = min(n_envs // 8, 1024)
     host = np.zeros((n_cta, 24), dtype=np.int64)
     seg = {name: [] for name, _, _ in SEGMENTS}
@@ -107,13 +116,18 @@ def run(n_envs, reps):
         skews.append(float(g0.max() - g0.min()) / 1e3)
         cyc_per_ns = np.median((host[:, 11] - host[:, 0]) / np.maximum(g1 - g0, 1))
         for name, a, b in SEGMENTS:
-            seg[name].append((host[:, b] - host[:, a]) / cyc_per_ns / 1e3)
+            d = (host[:, b] - host[:, a]) / cyc_per_ns / 1e3
+            if name.startswith("reset env"):                    # only the CTAs whose env 0 reset in THIS launch
+                d = d[(host[:, 21] > host[:, 7]) & (host[:, 21] < host[:, 8])]
+            seg[name].append(d)
     print(f"== K2 tiled phase trace: {n_envs} envs, {n_envs // 8} CTAs (first {n_cta} traced), {reps} launches, L2 flushed; "
           f"clock {cyc_per_ns:.3f} cycles/ns")
     print(f"event time per launch (eager, incl. finalize kernel): median {np.median(times):.2f} us")
     print(f"kernel span, first CTA entry -> last CTA exit: median {np.median(spans):.2f} us;  CTA start skew {np.median(skews):.2f} us")
     for name, _, _ in SEGMENTS:
         v = np.concatenate(seg[name])
+        if v.size == 0:
+            continue
         print(f"  {name:55s} median {np.median(v):6.2f} us   p90 {np.percentile(v, 90):6.2f}   max {v.max():6.2f}")
 
 
@@ -122,9 +136,11 @@ if __name__ == "__main__":
     ap.add_argument("--build", action="store_true")
     ap.add_argument("--envs", type=int, nargs="*", default=[4096, 32768])
     ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--mode", type=int, nargs="*", default=[0], help="attribution modes to run (trace build only), e.g. 0 1")
     args = ap.parse_args()
     if args.build:
         build()
     else:
         for n in args.envs:
-            run(n, args.reps)
+            for m in args.mode:
+                run(n, args.reps, m)
