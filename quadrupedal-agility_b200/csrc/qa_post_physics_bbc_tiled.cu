@@ -204,6 +204,7 @@ __device__ __forceinline__ void reset_precompute(const QaBbcConst& c, const K2St
         if (clip < 0) clip = a.mocap.mode_clips[max(lo, hi - 1)];             // empty mode: what the scan would read
     }
     clip = min(max(clip, 0), a.mocap.num_clips - 1);
+    STAMP(21, T_ENV);
     if (!have_meta) {
         len_s = a.mocap.clip_len_s[clip], frame_dur = a.mocap.clip_frame_dur[clip], nframes = a.mocap.clip_nframes[clip];
         start = a.mocap.clip_start[clip];
@@ -227,7 +228,9 @@ __device__ __forceinline__ void reset_precompute(const QaBbcConst& c, const K2St
         const float* kp = a.rigid_body_state + ((size_t)e * B + c.feet_indices[lane]) * 13;
         kx = kp[0], ky = kp[1], kz = kp[2];
     }
+    STAMP(22, T_ENV);
     const Quat qs = slerp_ref(Quat{h0[3], h0[4], h0[5], h0[6]}, Quat{h1[3], h1[4], h1[5], h1[6]}, bl);
+    STAMP(23, T_ENV);
     if (dl) {
         rst[RST_MP + lane] = mocap_lerp(p0, p1, bl);
         rst[RST_MV + lane] = mocap_lerp(w0, w1, bl);
@@ -297,9 +300,6 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
     } else {
         if (lane < QA_NUM_DOF)
             alast = r.action_history_buf[(size_t)(e0 + wid) * QA_ACT_HIST_LEN * QA_NUM_DOF + (QA_ACT_HIST_LEN - 1) * QA_NUM_DOF + lane];
-        // the env's root quaternion, one component per lane 12..15: this warp computes the euler angles while the tiles are in
-        // flight (they were the longest role of scalar warp A's chain: two atan2f + one asinf, ~2 us of dependent issue)
-        else if (lane < QA_NUM_DOF + 4) qc = r.root_states[(size_t)(e0 + wid) * 13 + 3 + (lane - QA_NUM_DOF)];
         // root height and episode counter: with the contact ballot of P1 they decide the reset (:168-176) before P2b says so
         else if (lane == 16) qc = r.root_states[(size_t)(e0 + wid) * 13 + 2];
         else if (lane == 17) ep_pre = r.episode_length_buf[e0 + wid];
@@ -370,27 +370,6 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
                     u = u32_to_unit_f32(rr.v[i & 3]);
                 }
                 nz[kk] = (2.f * u - 1.f) * c.noise_scale[k];
-            }
-        }
-        {
-            // euler angles of the pre-reset root (:141, get_euler_xyz): lanes 0 / 2 run the two atan2f side by side, lane 1
-            // the asinf; same expressions, op for op, as the scalar program had
-            const Quat q = {__shfl_sync(QA_FULL, qc, QA_NUM_DOF), __shfl_sync(QA_FULL, qc, QA_NUM_DOF + 1),
-                            __shfl_sync(QA_FULL, qc, QA_NUM_DOF + 2), __shfl_sync(QA_FULL, qc, QA_NUM_DOF + 3)};
-            float ang = 0.f;
-            if (lane == 0 || lane == 2) {
-                const float num = lane == 0 ? 2.0f * (q.w * q.x + q.y * q.z) : 2.0f * (q.w * q.z + q.x * q.y);
-                const float den = lane == 0 ? 1.0f - 2.0f * (q.x * q.x + q.y * q.y) : 1.0f - 2.0f * (q.y * q.y + q.z * q.z);
-                ang = atan2f(num, den);
-            } else if (lane == 1) {
-                float t2 = 2.0f * (q.w * q.y - q.z * q.x);
-                t2 = clampf(t2, -1.f, 1.f);
-                ang = asinf(t2);
-            }
-            if (lane < 3) S.rpy[el * 3 + lane] = ang;
-            if (lane < 2) {
-                S.obs[el * ROW + lane] = ang;
-                S.disc[el * QA_NUM_OBS_DISC + lane] = ang;
             }
         }
         STAMP(1, T_ENV);
@@ -564,7 +543,7 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
     } else if (wid == W_SA) {
         // ---------------- P2a (scalar warp A, lane = (env, role)): the thread-per-env scalar program of round 1 split four ways
         // so that the dependent chain is the longest ROLE, not their sum (same arithmetic per quantity, bit for bit):
-        //   role 0  base linear velocity            role 2  projected gravity (the euler angles run on the env warps)
+        //   role 0  base linear velocity            role 2  projected gravity (the euler angles run on scalar warp B)
         //   role 1  base angular velocity           role 3  centre terrain height, periodic resample, push
         if (lane < 26) reinterpret_cast<float4*>(S.root)[lane] = ld0;
         if (st1 != nullptr) *st1 = ld1;
@@ -795,6 +774,29 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
         }
         STAMP(15 + 5, T_SB);
         bar_arrive(1, T2_THREADS);
+        {
+            // euler angles of the pre-reset root (:141, get_euler_xyz), lane = (env, j): j = 0 roll and j = 2 yaw run the two
+            // atan2f side by side, j = 1 the asinf -- in this warp's slack before barrier 2 (they were the longest role of scalar
+            // warp A's chain: ~2 us of dependent issue).  Same expressions, op for op, as the scalar program had.
+            const int el = lane >> 2, j = lane & 3;
+            const float* R = S.rootB + el * 13;
+            const Quat q = {R[3], R[4], R[5], R[6]};
+            float ang = 0.f;
+            if (j == 0 || j == 2) {
+                const float num = j == 0 ? 2.0f * (q.w * q.x + q.y * q.z) : 2.0f * (q.w * q.z + q.x * q.y);
+                const float den = j == 0 ? 1.0f - 2.0f * (q.x * q.x + q.y * q.y) : 1.0f - 2.0f * (q.y * q.y + q.z * q.z);
+                ang = atan2f(num, den);
+            } else if (j == 1) {
+                float t2 = 2.0f * (q.w * q.y - q.z * q.x);
+                t2 = clampf(t2, -1.f, 1.f);
+                ang = asinf(t2);
+            }
+            if (j < 3) S.rpy[el * 3 + j] = ang;
+            if (j < 2) {
+                S.obs[el * ROW + j] = ang;
+                S.disc[el * QA_NUM_OBS_DISC + j] = ang;
+            }
+        }
         any_state_write = __syncthreads_or(any_state_write ? 1 : 0) != 0;      // barrier 2
     }
 

@@ -30,10 +30,10 @@ SEGMENTS = [  # (name, stamp_from, stamp_to); stamps 0-11 env warp 0, 12-15/18 s
     ("env: P3b", 7, 8),
     ("env: P3b end -> barrier 3 stamp (the clock read is hoisted ABOVE the barrier)", 8, 9),
     ("barrier 3 wait (slowest env warp of the CTA, e.g. a reset) + store issue", 9, 10),
-    ("reset env: barrier 2 -> clip chosen (draw + CDF search)", 7, 21),
-    ("reset env: clip chosen -> blend rows known (clip metadata, fp64 index math)", 21, 22),
-    ("reset env: slerp of the root quaternion (first touch of the frame rows)", 22, 23),
-    ("reset env: slerp done -> end of P3b", 23, 8),
+    ("reset env: P1 start -> clip chosen (contact ballot, 3 Philox draws, lane-parallel CDF search)", 2, 21),
+    ("reset env: clip chosen -> frame operands requested (fp64 index math)", 21, 22),
+    ("reset env: operands landed + slerp of the root quaternion", 22, 23),
+    ("reset env: lerps, velocity rotation, key-body positions -> end of the precompute", 23, 3),
     ("P4 wait_group.read", 10, 11),
     ("scalar A: entry -> own loads landed", 0, 12),
     ("scalar A: P2a", 12, 13),
@@ -118,7 +118,7 @@ def run(n_envs, reps, mode=0):
         for name, a, b in SEGMENTS:
             d = (host[:, b] - host[:, a]) / cyc_per_ns / 1e3
             if name.startswith("reset env"):                    # only the CTAs whose env 0 reset in THIS launch
-                d = d[(host[:, 21] > host[:, 7]) & (host[:, 21] < host[:, 8])]
+                d = d[(host[:, 21] > host[:, 2]) & (host[:, 21] < host[:, 3])]
             seg[name].append(d)
     print(f"== K2 tiled phase trace: {n_envs} envs, {n_envs // 8} CTAs (first {n_cta} traced), {reps} launches, L2 flushed; "
           f"clock {cyc_per_ns:.3f} cycles/ns")
