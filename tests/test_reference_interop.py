@@ -21,3 +21,11 @@ def test_reference_tsc_ppo_runs_over_this_packages_actor_critic_tsc():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "check_interop.py"), "tsc"], capture_output=True, text=True,
                          timeout=600)
     assert out.returncode == 0 and "interop OK (tsc)" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/bbc"), reason="the reference tree only exists in the build container")
+def test_dropin_construction_extracts_config_and_constants_from_the_reference_env():
+    """`qa_b200.dropin`: BbcEnvConfig + per-env constants out of an env the UNMODIFIED reference class built; the registrable
+    task class has the reference constructor's signature (bbc/legged_gym/utils/task_registry.py:66-70)."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "check_dropin.py")], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "dropin OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
