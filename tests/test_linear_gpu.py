@@ -18,6 +18,10 @@ SHAPES = [  # (M, N, K, x_pitch, w_pitch)
     (24576, 512, 671, 672, 672), (4096, 512, 101, 104, 104), (4096, 256, 512, 512, 512), (4096, 128, 256, 256, 256),
     (4096, 12, 128, 128, 128), (4096, 1, 128, 128, 128), (300, 64, 57, 672, 60), (128, 29, 64, 64, 64),
     (1, 16, 32, 32, 32), (1000, 512, 98, 100, 100), (129, 5, 256, 256, 256), (4096, 4, 64, 64, 64),
+    # tall problems run on CTA pairs (cta_group::2, M >= 8192): ragged last pair (second CTA partly / wholly out of range),
+    # N that is not a multiple of the tile, every pair tile width
+    (10000, 512, 671, 672, 672), (8200, 200, 300, 300, 300), (9001, 64, 128, 128, 128), (8192 + 130, 100, 57, 60, 60),
+    (24576, 256, 512, 512, 512), (24576, 128, 256, 256, 256),
 ]
 
 
@@ -89,6 +93,9 @@ def test_actor_critic_tc_mode_matches_fp32_mode_and_grads():
 BWD_SHAPES = [  # (M, N, K, x_pitch, w_pitch)
     (24576, 512, 671, 672, 672), (24576, 256, 512, 512, 512), (24576, 128, 256, 256, 256), (24576, 12, 128, 128, 128),
     (4096, 512, 101, 104, 104), (1000, 64, 57, 672, 60), (300, 4, 64, 64, 64), (129, 128, 32, 32, 32), (4096, 64, 128, 128, 128),
+    # CTA pairs: ragged M (dX: last pair partly out of range; dW: the reduction's last K block partly out of range), N = 300
+    # output features (dW: second CTA of the second pair partly out of range), K not a multiple of the n tile
+    (10000, 512, 671, 672, 672), (8200, 300, 200, 200, 300), (9001, 256, 100, 100, 256), (24576, 512, 101, 104, 104),
 ]
 
 
@@ -127,7 +134,7 @@ def test_linear_bwd_matches_fp32_reference(shape):
 def test_linear_bwd_fused_activation_backward(act):
     """dx epilogue fused with the previous layer's activation derivative and bias gradient (EPI_ACTBWD)."""
     g = torch.Generator().manual_seed(11)
-    for M, N, K in ((24576, 256, 512), (1000, 128, 256), (4096, 12, 128), (130, 64, 100)):
+    for M, N, K in ((24576, 256, 512), (1000, 128, 256), (4096, 12, 128), (130, 64, 100), (10001, 300, 200), (9000, 64, 128)):
         kp = (K + 3) // 4 * 4
         z_prev = torch.randn(M, kp, generator=g).to(DEV)[:, :K]
         y_prev = F.elu(z_prev) if act == "elu" else F.relu(z_prev)
