@@ -785,6 +785,14 @@ typedef struct QaDiscInputArgs {
     float norm_clip;                    /* 10 */
     int32_t task_obs_weight_decay; float task_obs_weight;
     float obs_disc_weight_step;
+    /* optional (all may be NULL).  task_obs_weight_dev: (1) device scalar that overrides task_obs_weight (the weight decays
+     * every iteration, on_policy_runner.py:224-225: a captured rollout graph must not freeze it).  Snapshots for a reward tail
+     * that runs concurrently with the NEXT env step (which overwrites rew_buf / reset_buf / time_outs): copied here, by the
+     * launch that already reads `dones` */
+    const float* task_obs_weight_dev;
+    const float* rewards_in; float* rewards_snap;               /* (N) */
+    uint8_t* dones_snap;                                        /* (N) */
+    const uint8_t* time_outs_in; uint8_t* time_outs_snap;       /* (N) */
 } QaDiscInputArgs;
 int qa_disc_input(const QaDiscInputArgs* a, void* stream);
 

@@ -22,6 +22,12 @@ __global__ void __launch_bounds__(256) k_disc_input(const __grid_constant__ QaDi
     float* hn = a.hist_new + (size_t)e * 2 * DI_W;
     float* hx = a.hist_next + (size_t)e * 2 * DI_W;
     float* x = a.x_norm + (size_t)e * a.x_pitch;
+    const float tow = a.task_obs_weight_dev != nullptr ? __ldg(a.task_obs_weight_dev) : a.task_obs_weight;
+    if (lane == 0) {
+        if (a.rewards_snap != nullptr) a.rewards_snap[e] = a.rewards_in[e];
+        if (a.dones_snap != nullptr) a.dones_snap[e] = a.dones[e];
+        if (a.time_outs_snap != nullptr) a.time_outs_snap[e] = a.time_outs_in[e];
+    }
     for (int i = lane; i < 2 * DI_W; i += 32) {
         const int slot = i >= DI_W ? 1 : 0, k = i - slot * DI_W;
         const float nx = next[k];
@@ -30,7 +36,7 @@ __global__ void __launch_bounds__(256) k_disc_input(const __grid_constant__ QaDi
         hn[i] = v;
         hx[i] = done ? nx : v;                                               // fresh episodes restart their history (:180-181)
         float o = v;
-        if (a.task_obs_weight_decay && ((k >= 3 && k < 9) || k >= 33)) o = o * a.task_obs_weight;   // discriminator.py:76-78
+        if (a.task_obs_weight_decay && ((k >= 3 && k < 9) || k >= 33)) o = o * tow;   // discriminator.py:76-78
         if (a.obs_disc_weight_step != 0.f) o = o * ((float)slot * a.obs_disc_weight_step + 1.f);    // :80-84
         o = (o - a.norm_mean[i]) / a.norm_std[i];                            // Normalizer.normalize_torch, utils.py:97-103
         x[i] = fminf(fmaxf(o, -a.norm_clip), a.norm_clip);
@@ -45,6 +51,8 @@ extern "C" int qa_disc_input(const QaDiscInputArgs* a, void* stream) {
                           a->norm_mean, a->norm_std};
     for (const void* p : need) QA_CHECK_PTR(p);
     if (a->x_pitch < 2 * DI_W) return QA_EINVAL;
+    if (a->rewards_snap != nullptr) QA_CHECK_PTR(a->rewards_in);
+    if (a->time_outs_snap != nullptr) QA_CHECK_PTR(a->time_outs_in);
     k_disc_input<<<(a->num_envs + 7) / 8, 256, 0, (cudaStream_t)stream>>>(*a);
     QA_LAUNCH_RET();
 }

@@ -548,16 +548,26 @@ def post_physics_tsc(const, args, which: str) -> None:
 
 # ---- K18 / K19 ------------------------------------------------------------------------------------
 def disc_input(dones, prev_disc, next_disc, hist_prev, hist_new, hist_next, x_norm, norm_mean, norm_std, norm_clip,
-               task_obs_weight_decay, task_obs_weight, obs_disc_weight_step) -> None:
+               task_obs_weight_decay, task_obs_weight, obs_disc_weight_step, snapshots=None) -> None:
     """Disc-history bookkeeping of the rollout step + the normalised discriminator input (on_policy_runner.py:163-181,
-    discriminator.py:74-88)."""
+    discriminator.py:74-88).  `task_obs_weight`: float or 0-d / (1,) device tensor (read at run time: a captured graph sees the
+    decayed value).  `snapshots` = (rewards_in, rewards_snap, dones_snap, time_outs_in or None, time_outs_snap or None): copies
+    of the env buffers the NEXT env step overwrites, for a reward tail that runs concurrently with it."""
     lib = _abi.load()
     f = torch.float32
+    tow_dev = task_obs_weight if torch.is_tensor(task_obs_weight) else None
     a = _abi.QaDiscInputArgs(dones.shape[0], _bytep(dones, "dones"), _p(prev_disc, f, "prev_disc"), _p(next_disc, f, "next_disc"),
                              _p(hist_prev, f, "hist_prev"), _p(hist_new, f, "hist_new"), _p(hist_next, f, "hist_next"),
                              _p_strided(x_norm, f, "x_norm"), x_norm.stride(0), _p(norm_mean, f, "norm_mean"),
                              _p(norm_std, f, "norm_std"), float(norm_clip), int(bool(task_obs_weight_decay)),
-                             float(task_obs_weight), float(obs_disc_weight_step))
+                             1.0 if tow_dev is not None else float(task_obs_weight), float(obs_disc_weight_step))
+    if tow_dev is not None:
+        a.task_obs_weight_dev = _p(tow_dev.reshape(1), f, "task_obs_weight")
+    if snapshots is not None:
+        r_in, r_snap, d_snap, t_in, t_snap = snapshots
+        a.rewards_in, a.rewards_snap, a.dones_snap = _p(r_in, f, "rewards_in"), _p(r_snap, f, "rewards_snap"), _bytep(d_snap, "dones_snap")
+        if t_in is not None:
+            a.time_outs_in, a.time_outs_snap = _bytep(t_in, "time_outs_in"), _bytep(t_snap, "time_outs_snap")
     _abi.check(lib.qa_disc_input(C.byref(a), _stream()), "qa_disc_input")
     _count(1)
 

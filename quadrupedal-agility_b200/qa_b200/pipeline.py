@@ -52,6 +52,7 @@ class BbcIteration:
         train_cfg = bbc_train_cfg()
         train_cfg["algorithm"]["use_cuda_graph"] = use_cuda_graph
         self.runner = OnPolicyRunner(self.env, train_cfg, log_dir=None, device=dev)
+        self.runner.full_rollouts = True                   # every rollout here runs all T steps: deferred reward tails are legal
         self.env.load_state({k: v.to(dev) for k, v in snaps[0].items() if k in CARRIED})
         self.phys_resident.cursor = -1
         self.obs, self.critic_obs = self.env.get_observations(), self.env.get_privileged_observations()
@@ -114,6 +115,7 @@ class BbcIteration:
             if not host:
                 for t in range(self.T):
                     self.obs, self.critic_obs = runner.rollout_step(self.obs, self.critic_obs)
+                runner.finish_rollout()
                 return
             # the physics backend's hand-over: pinned host -> HBM, double buffered on a copy stream (a parallel branch of the
             # captured graph): step t's kernels wait for copy t, copy t+2 waits for step t's kernels (its staging set is free)
@@ -134,6 +136,7 @@ class BbcIteration:
                 self.obs, self.critic_obs = runner.rollout_step(self.obs, self.critic_obs)
                 freed[b] = torch.cuda.Event()
                 freed[b].record(main)
+            runner.finish_rollout()
             main.wait_stream(cs)
 
     def _capture_rollout(self, host: bool):

@@ -78,6 +78,14 @@ class RolloutPlan:
         self.heads_out = torch.zeros(N, self.heads_w.shape[0], device=dev)
         self.refresh_disc_heads()
         self.s_est, self.s_priv, self.s_critic = (torch.cuda.Stream(device=dev) for _ in range(3))
+        # reward tail (discriminator trunk, heads, K19) of step t on its own stream, next to the policy chain and the env kernels
+        # of step t+1 (`defer_reward_tail`): what the tail reads and the next env step overwrites is snapshotted by K18
+        self.s_rew = torch.cuda.Stream(device=dev)
+        self.defer_reward_tail = False                  # set by callers that run WHOLE rollouts (runner.learn, BbcIteration)
+        self._tail_pending = False
+        self.rew_snap = torch.zeros(N, device=dev)
+        self.dones_snap = torch.zeros(N, device=dev, dtype=torch.uint8)
+        self.tout_snap = torch.zeros(N, device=dev, dtype=torch.uint8)
         # action noise: in-kernel Philox by default; True = draw it from torch's CUDA generator like the reference's
         # Normal.sample() (one extra framework kernel per step; what the torch-path comparison tests use)
         self.use_torch_generator = False
@@ -152,6 +160,12 @@ class RolloutPlan:
         tr.observations, tr.critic_observations = obs, critic_obs
         return self.actions
 
+    def finish_rewards(self):
+        """Joins a reward tail that is still running on its side stream (end of a rollout that does not fill the storage)."""
+        if self._tail_pending:
+            _Cur(True).join(self.s_rew)
+            self._tail_pending = False
+
     # ---- reward + process_env_step ----------------------------------------------------------------------------------------------
     @torch.no_grad()
     def reward(self, obs, rewards, dones, prev_disc, next_disc, disc_hist, reward_terms=None):
@@ -162,19 +176,46 @@ class RolloutPlan:
         hist_new = alg._disc_stage[0][t] if staged else self.hist_new
         dst = self.hist_pp[0] if disc_hist is not self.hist_pp[0] else self.hist_pp[1]
         mean, std = alg.disc_normalizer.device_moments(self.dev)
-        ops.disc_input(dones, prev_disc, next_disc, disc_hist, hist_new, dst, self.x_norm, mean, std, alg.disc_normalizer.clip_obs,
-                       env.task_obs_weight_decay, env.task_obs_weight, self.obs_disc_weight_step)
-        self._trunk(self.c_disc, self.x_norm)
-        ops.head_fwd(self.c_disc.h[-1], self.heads_w, self.heads_b, self.heads_out)
         time_outs = env._time_outs_latched if env.cfg.send_timeouts else None
-        ops.disc_reward(self.heads_out, obs, rewards, d.dt, (d.reward_i_coef, d.reward_us_coef, d.reward_ss_coef, d.reward_t_coef),
-                        st.rewards[t].view(-1), values=st.values[t], time_outs=time_outs, gamma=alg.gamma, dones=dones,
-                        dones_out=st.dones[t].view(-1), reward_terms=reward_terms)
+        # Deferred tail: the trunk / heads / K19 of this step run on `s_rew` while the main stream goes on with the next step's
+        # policy and env kernels.  Hazards: (1) x_norm / heads_out / the snapshots are single buffers -> the previous tail is
+        # joined first (it has had a whole env step to finish); (2) rew_buf, reset_buf and the latched time-outs are overwritten
+        # by the next K2 -> K18, which runs here on the main stream, copies them; (3) the observation row the policy saw (the
+        # labels K19 reads) lives in a ping-pong buffer the step after next overwrites -> read from its storage slot;
+        # (4) latent_eps / latent_c may be resampled by the next K2 -> the replay-buffer staging stays on the main stream.
+        defer = self.defer_reward_tail and reward_terms is None
+        cur = _Cur(True)
+        if self._tail_pending:
+            cur.join(self.s_rew)
+            self._tail_pending = False
+        weight = alg._task_obs_weight_dev() if (env.task_obs_weight_decay and hasattr(alg, "_task_obs_weight_dev")) else env.task_obs_weight
+        snaps = (rewards, self.rew_snap, self.dones_snap, time_outs, None if time_outs is None else self.tout_snap) if defer else None
+        ops.disc_input(dones, prev_disc, next_disc, disc_hist, hist_new, dst, self.x_norm, mean, std, alg.disc_normalizer.clip_obs,
+                       env.task_obs_weight_decay, weight, self.obs_disc_weight_step, snapshots=snaps)
         if staged:
             ops.gather_minibatch_windows(self.rows, [(env.latent_eps, 0, alg._disc_stage[1][t], 0, env.latent_eps.shape[1]),
                                                      (env.latent_c, 0, alg._disc_stage[2][t], 0, env.latent_c.shape[1])])
         else:
             alg.disc_storage.insert(hist_new, env.latent_eps, env.latent_c)
+        coefs = (d.reward_i_coef, d.reward_us_coef, d.reward_ss_coef, d.reward_t_coef)
+        if defer:
+            cur.fork(self.s_rew)
+            with torch.cuda.stream(self.s_rew):
+                self._trunk(self.c_disc, self.x_norm)
+                ops.head_fwd(self.c_disc.h[-1], self.heads_w, self.heads_b, self.heads_out)
+                ops.disc_reward(self.heads_out, st.observations[t], self.rew_snap, d.dt, coefs, st.rewards[t].view(-1),
+                                values=st.values[t], time_outs=None if time_outs is None else self.tout_snap, gamma=alg.gamma,
+                                dones=self.dones_snap, dones_out=st.dones[t].view(-1))
+            self._tail_pending = True
+            if t + 1 >= st.num_transitions_per_env:          # last step of the rollout: GAE reads rewards / dones next
+                cur.join(self.s_rew)
+                self._tail_pending = False
+        else:
+            self._trunk(self.c_disc, self.x_norm)
+            ops.head_fwd(self.c_disc.h[-1], self.heads_w, self.heads_b, self.heads_out)
+            ops.disc_reward(self.heads_out, obs, rewards, d.dt, coefs, st.rewards[t].view(-1), values=st.values[t],
+                            time_outs=time_outs, gamma=alg.gamma, dones=dones, dones_out=st.dones[t].view(-1),
+                            reward_terms=reward_terms)
         alg.transition.dones = dones
         st.step += 1
         alg.actor_critic.reset(dones)

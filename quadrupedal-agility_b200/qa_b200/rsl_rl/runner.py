@@ -90,7 +90,15 @@ class OnPolicyRunner:
                 return None
             plan = self._rollout_plan = RolloutPlan(self.alg, self.env, self.disc_obs_len, self.obs_disc_weight_step)
             self.alg._disc_listeners = list(getattr(self.alg, "_disc_listeners", ())) + [plan.refresh_disc_heads]
+        # whole-rollout callers (learn(), pipeline.BbcIteration) let the reward tail of step t run next to step t+1
+        plan.defer_reward_tail = bool(getattr(self, "full_rollouts", False)) and os.environ.get("QA_DEFER_REWARD_TAIL", "1") == "1"
         return plan
+
+    def finish_rollout(self):
+        """After the last step of a rollout: a deferred reward tail (rollout_plan) is joined into the current stream."""
+        plan = getattr(self, "_rollout_plan", None)
+        if plan is not None:
+            plan.finish_rewards()
 
     # ---- one rollout step (:156-181) ----------------------------------------------------------------------
     def _rollout_step_fused(self, obs, critic_obs, hist_encoding):
@@ -178,12 +186,14 @@ class OnPolicyRunner:
             self._reward_coefs = torch.tensor([d.reward_i_coef, d.reward_us_coef, d.reward_ss_coef, d.reward_t_coef],
                                               device=self.device)
         hist_latent_loss = None
+        self.full_rollouts = True                                           # every rollout below runs all num_steps_per_env steps
         for it in range(self.current_learning_iteration, self.current_learning_iteration + num_learning_iterations):
             start = time.time()
             hist_encoding = it % self.dagger_update_freq == 0
             with torch.inference_mode(False), torch.no_grad():
                 for _ in range(self.num_steps_per_env):
                     obs, critic_obs = self.rollout_step(obs, critic_obs, hist_encoding)
+                self.finish_rollout()
                 torch.cuda.synchronize() if torch.device(self.device).type == "cuda" else None
                 stop = time.time()
                 collection_time = stop - start

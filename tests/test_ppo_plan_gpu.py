@@ -430,3 +430,31 @@ def test_rollout_schedule_matches_torch_rollout(tc_mode):
     assert_close("disc history", b["hist"], a["hist"])
     assert_close("replay states", b["replay"], a["replay"])
     assert torch.equal(b["replay_eps"], a["replay_eps"]) and torch.equal(b["replay_c"], a["replay_c"])
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_rollout_deferred_reward_tail_equals_in_order_tail(tc_mode, graph):
+    """The reward tail of step t (discriminator trunk, heads, K19) on its own stream next to step t+1 -- with K18's snapshots of
+    rew_buf / reset_buf / latched time-outs and the labels read from the storage slot -- fills the storage with exactly what
+    the in-order schedule does (same kernels on the same values: bit-equal), eagerly and as one captured rollout graph."""
+    import bench
+    from qa_b200.pipeline import BbcIteration
+    N, T = 512, 8
+    cfg, static, snaps, table = bench.build_workload(0, DEV, n_envs=N, steps=T)
+    out = []
+    for defer in (False, True):
+        it = BbcIteration(cfg, static, snaps, table, device=DEV, seed=77, use_cuda_graph=graph)
+        it.runner.full_rollouts = defer
+        rp = it.runner._ensure_rollout_plan()
+        assert rp is not None and rp.defer_reward_tail == defer
+        for _ in range(2):                                        # two rollouts: the second starts from carried state
+            it.runner.alg.storage.clear()
+            it._rollout(host=False)
+        torch.cuda.synchronize()
+        st = it.runner.alg.storage
+        out.append({k: getattr(st, k).clone() for k in ("rewards", "dones", "values", "observations", "actions")}
+                   | dict(hist=it.runner._disc_hist.clone()))
+    a, b = out
+    assert int(a["dones"].sum()) > 0 and float(a["rewards"].abs().sum()) > 0
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
