@@ -793,6 +793,10 @@ typedef struct QaDiscInputArgs {
     const float* rewards_in; float* rewards_snap;               /* (N) */
     uint8_t* dones_snap;                                        /* (N) */
     const uint8_t* time_outs_in; uint8_t* time_outs_snap;       /* (N) */
+    /* optional: the env's latent_eps (N,1) / latent_c (N,dim_c) of this step into the replay-buffer rows that go with hist_new
+     * (storage/replay_buffer.py insert; saves the separate copy launch of the rollout step) */
+    const float* latent_eps_in; float* latent_eps_out;
+    const float* latent_c_in; float* latent_c_out;
 } QaDiscInputArgs;
 int qa_disc_input(const QaDiscInputArgs* a, void* stream);
 

@@ -27,7 +27,9 @@ __global__ void __launch_bounds__(256) k_disc_input(const __grid_constant__ QaDi
         if (a.rewards_snap != nullptr) a.rewards_snap[e] = a.rewards_in[e];
         if (a.dones_snap != nullptr) a.dones_snap[e] = a.dones[e];
         if (a.time_outs_snap != nullptr) a.time_outs_snap[e] = a.time_outs_in[e];
+        if (a.latent_eps_out != nullptr) a.latent_eps_out[e] = a.latent_eps_in[e];
     }
+    if (a.latent_c_out != nullptr && lane < QA_DIM_C) a.latent_c_out[(size_t)e * QA_DIM_C + lane] = a.latent_c_in[(size_t)e * QA_DIM_C + lane];
     for (int i = lane; i < 2 * DI_W; i += 32) {
         const int slot = i >= DI_W ? 1 : 0, k = i - slot * DI_W;
         const float nx = next[k];
@@ -53,6 +55,8 @@ extern "C" int qa_disc_input(const QaDiscInputArgs* a, void* stream) {
     if (a->x_pitch < 2 * DI_W) return QA_EINVAL;
     if (a->rewards_snap != nullptr) QA_CHECK_PTR(a->rewards_in);
     if (a->time_outs_snap != nullptr) QA_CHECK_PTR(a->time_outs_in);
+    if (a->latent_eps_out != nullptr) QA_CHECK_PTR(a->latent_eps_in);
+    if (a->latent_c_out != nullptr) QA_CHECK_PTR(a->latent_c_in);
     k_disc_input<<<(a->num_envs + 7) / 8, 256, 0, (cudaStream_t)stream>>>(*a);
     QA_LAUNCH_RET();
 }

@@ -287,7 +287,8 @@ class QaDiscInputArgs(C.Structure):
                 ("hist_new", vp), ("hist_next", vp), ("x_norm", vp), ("x_pitch", C.c_int64), ("norm_mean", vp),
                 ("norm_std", vp), ("norm_clip", C.c_float), ("task_obs_weight_decay", C.c_int32),
                 ("task_obs_weight", C.c_float), ("obs_disc_weight_step", C.c_float), ("task_obs_weight_dev", vp),
-                ("rewards_in", vp), ("rewards_snap", vp), ("dones_snap", vp), ("time_outs_in", vp), ("time_outs_snap", vp)]
+                ("rewards_in", vp), ("rewards_snap", vp), ("dones_snap", vp), ("time_outs_in", vp), ("time_outs_snap", vp),
+                ("latent_eps_in", vp), ("latent_eps_out", vp), ("latent_c_in", vp), ("latent_c_out", vp)]
 
 
 class QaDiscRewardArgs(C.Structure):

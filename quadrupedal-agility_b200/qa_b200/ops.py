@@ -548,11 +548,12 @@ def post_physics_tsc(const, args, which: str) -> None:
 
 # ---- K18 / K19 ------------------------------------------------------------------------------------
 def disc_input(dones, prev_disc, next_disc, hist_prev, hist_new, hist_next, x_norm, norm_mean, norm_std, norm_clip,
-               task_obs_weight_decay, task_obs_weight, obs_disc_weight_step, snapshots=None) -> None:
+               task_obs_weight_decay, task_obs_weight, obs_disc_weight_step, snapshots=None, latents=None) -> None:
     """Disc-history bookkeeping of the rollout step + the normalised discriminator input (on_policy_runner.py:163-181,
     discriminator.py:74-88).  `task_obs_weight`: float or 0-d / (1,) device tensor (read at run time: a captured graph sees the
     decayed value).  `snapshots` = (rewards_in, rewards_snap, dones_snap, time_outs_in or None, time_outs_snap or None): copies
-    of the env buffers the NEXT env step overwrites, for a reward tail that runs concurrently with it."""
+    of the env buffers the NEXT env step overwrites, for a reward tail that runs concurrently with it.  `latents` =
+    (latent_eps (N,1), latent_eps_out, latent_c (N,dim_c), latent_c_out): the replay-buffer rows that go with hist_new."""
     lib = _abi.load()
     f = torch.float32
     tow_dev = task_obs_weight if torch.is_tensor(task_obs_weight) else None
@@ -568,6 +569,12 @@ def disc_input(dones, prev_disc, next_disc, hist_prev, hist_new, hist_next, x_no
         a.rewards_in, a.rewards_snap, a.dones_snap = _p(r_in, f, "rewards_in"), _p(r_snap, f, "rewards_snap"), _bytep(d_snap, "dones_snap")
         if t_in is not None:
             a.time_outs_in, a.time_outs_snap = _bytep(t_in, "time_outs_in"), _bytep(t_snap, "time_outs_snap")
+    if latents is not None:
+        e_in, e_out, c_in, c_out = latents
+        if c_in.shape[-1] != 5 or not (e_out.is_contiguous() and c_out.is_contiguous()):
+            raise RuntimeError("qa_b200: disc_input latents must be (N,1) / (N,5) contiguous rows")
+        a.latent_eps_in, a.latent_eps_out = _p(e_in, f, "latent_eps"), _p(e_out, f, "latent_eps_out")
+        a.latent_c_in, a.latent_c_out = _p(c_in, f, "latent_c"), _p(c_out, f, "latent_c_out")
     _abi.check(lib.qa_disc_input(C.byref(a), _stream()), "qa_disc_input")
     _count(1)
 

@@ -190,12 +190,10 @@ class RolloutPlan:
             self._tail_pending = False
         weight = alg._task_obs_weight_dev() if (env.task_obs_weight_decay and hasattr(alg, "_task_obs_weight_dev")) else env.task_obs_weight
         snaps = (rewards, self.rew_snap, self.dones_snap, time_outs, None if time_outs is None else self.tout_snap) if defer else None
+        lat = (env.latent_eps, alg._disc_stage[1][t], env.latent_c, alg._disc_stage[2][t]) if staged else None
         ops.disc_input(dones, prev_disc, next_disc, disc_hist, hist_new, dst, self.x_norm, mean, std, alg.disc_normalizer.clip_obs,
-                       env.task_obs_weight_decay, weight, self.obs_disc_weight_step, snapshots=snaps)
-        if staged:
-            ops.gather_minibatch_windows(self.rows, [(env.latent_eps, 0, alg._disc_stage[1][t], 0, env.latent_eps.shape[1]),
-                                                     (env.latent_c, 0, alg._disc_stage[2][t], 0, env.latent_c.shape[1])])
-        else:
+                       env.task_obs_weight_decay, weight, self.obs_disc_weight_step, snapshots=snaps, latents=lat)
+        if not staged:
             alg.disc_storage.insert(hist_new, env.latent_eps, env.latent_c)
         coefs = (d.reward_i_coef, d.reward_us_coef, d.reward_ss_coef, d.reward_t_coef)
         if defer:
