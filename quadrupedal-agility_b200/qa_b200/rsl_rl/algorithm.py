@@ -854,7 +854,8 @@ class SSInfoGAIL:
         scale = 1.0
         if self.world_size > 1:
             scale = self._allreduce_grads()
-        self.optim_estimator.step(scale)
+        if not getattr(getattr(self, "_plan", None), "est_stepped_in_chain", False):
+            self.optim_estimator.step(scale)
         adaptive = self.desired_kl is not None and self.schedule == 'adaptive'
         if torch.device(self.device).type == "cuda":
             # K13: adaptive LR + the seven running statistics, one launch
@@ -874,6 +875,8 @@ class SSInfoGAIL:
 
     def _minibatch_step(self):
         self._forward_backward()
+        if getattr(self, "_plan", None) is not None:
+            self._plan.est_stepped_in_chain = False        # autograd variant: the estimator's optimiser steps in _apply
         self._apply()
 
     def _capture(self):
@@ -886,7 +889,7 @@ class SSInfoGAIL:
                                     self.optim_ac.step_count, self.optim_estimator.step_count, self._stats)]
         plan = self._plan
         sets = range(plan.num_sets) if plan is not None else (None,)
-        fb = (lambda k: plan.forward_backward(k)) if plan is not None else (lambda k: self._forward_backward())
+        fb = (lambda k: plan.forward_backward(k, step_estimator=True)) if plan is not None else (lambda k: self._forward_backward())
         with torch.cuda.stream(s):
             for _ in range(3):
                 fb(sets[0])

@@ -196,9 +196,10 @@ class PpoStepPlan:
         ops.head_bwd(gz_out, c.h[-1], c.head.weight, c.act, gz_prev=c.gz[-1], dw=c.head.weight.grad, db=c.head.bias.grad,
                      db_prev=last.bias.grad, gz_scale=scale)
 
-    def forward_backward(self, k: int) -> None:
+    def forward_backward(self, k: int, step_estimator: bool = False) -> None:
         """Forward + backward of minibatch set `k`; leaves the gradients in the flat buffers, the PPO statistics in
-        `alg._ppo_stats` (surrogate, value, bound, kl) and `alg._aux_loss` (priv_reg, estimator)."""
+        `alg._ppo_stats` (surrogate, value, bound, kl) and `alg._aux_loss` (priv_reg, estimator).  `step_estimator`: on a single
+        rank the estimator's optimiser step (gail.py:361-365) is issued inside the estimator's chain (`_apply` then skips it)."""
         alg, s = self.alg, self.sets[k]
         ac = alg.actor_critic
         p, e, l = self.p, self.e, self.l
@@ -219,6 +220,11 @@ class PpoStepPlan:
             ops.row_loss(ce.out, obs[:, p:p + e], self.d_est, alg._aux_loss[1:2], 0)
             self._head_bwd(ce, self.d_est)
             self._trunk_bwd(ce, obs, 0, p)
+            # single rank: the estimator's own optimiser step (gail.py:361-365) needs nothing from the other chains -- it runs
+            # here, behind the estimator's backward, instead of at the end of the step where nothing else is left to overlap it
+            self.est_stepped_in_chain = step_estimator and self._cuda and alg.world_size == 1
+            if self.est_stepped_in_chain:
+                alg.optim_estimator.step(1.0)
         # ---- critic forward (:343) ----------------------------------------------------------------------------------------
         with on(self.s_critic):
             self._trunk_fwd(self.c_critic, s["critic_obs"])
@@ -271,5 +277,5 @@ class PpoStepPlan:
                     c_entropy=a.entropy_coef, clipped_value=a.use_clipped_value_loss)
 
     def step(self, k: int) -> None:
-        self.forward_backward(k)
+        self.forward_backward(k, step_estimator=True)
         self.alg._apply()
