@@ -51,7 +51,7 @@ int qa_version(void);
 /* human readable build string ("sm_100a, nvcc 12.9, ...") */
 const char* qa_build_info(void);
 /* sizeof() of argument struct number `which` (order of declaration in this header, QaActionPushArgs
- * = 0 ... QaGaeArgs = 9, QaGatherArgs = 10, QaClipAdamArgs = 11, QaLinearArgs = 12, QaActBwdArgs = 13, QaPpoLossArgs = 14, QaLinearBwdArgs = 15, QaHistEncArgs = 16, QaRowLossArgs = 17, QaPpoScalarsArgs = 18, QaDepthArgs = 19, QaPpoLossTscArgs = 20, QaTscConst = 21, QaTscStepArgs = 22, QaDiscInputArgs = 23, QaDiscRewardArgs = 24, QaHeadFwdArgs = 25, QaHeadBwdArgs = 26, QaPolicySampleArgs = 27, QaDiscPrepareArgs = 28, QaDiscHeadsArgs = 29, QaDiscGpArgs = 30, QaDiscRegArgs = 31, QaNormMomentsArgs = 32, QaNormMergeArgs = 33; -1 if unknown): a layout handshake for FFI mirrors of these structs */
+ * = 0 ... QaGaeArgs = 9, QaGatherArgs = 10, QaClipAdamArgs = 11, QaLinearArgs = 12, QaActBwdArgs = 13, QaPpoLossArgs = 14, QaLinearBwdArgs = 15, QaHistEncArgs = 16, QaRowLossArgs = 17, QaPpoScalarsArgs = 18, QaDepthArgs = 19, QaPpoLossTscArgs = 20, QaTscConst = 21, QaTscStepArgs = 22, QaDiscInputArgs = 23, QaDiscRewardArgs = 24, QaHeadFwdArgs = 25, QaHeadBwdArgs = 26, QaPolicySampleArgs = 27, QaDiscPrepareArgs = 28, QaDiscHeadsArgs = 29, QaDiscGpArgs = 30, QaDiscRegArgs = 31, QaNormMomentsArgs = 32, QaNormMergeArgs = 33, QaPeerAllreduceArgs = 34; -1 if unknown): a layout handshake for FFI mirrors of these structs */
 int qa_struct_size(int which);
 /* stream-ordered fill-with-zero / device-to-device copy of `bytes` bytes (cudaMemsetAsync / cudaMemcpyAsync): lets a captured
  * training step zero its flat gradient buffer (optimizer.zero_grad(), gail.py:361, :409) and move device scalars without a
@@ -898,6 +898,41 @@ typedef struct QaNormMergeArgs {
     float* std; const float* min_std; int32_t num_std;    /* policy std floor or NULL */
 } QaNormMergeArgs;
 int qa_norm_merge(const QaNormMergeArgs* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K31  peer-memory all-reduce of the PPO gradient arena fused with K8's gradient-norm pass (ONE all-reduce of the
+ *      PPO gradients per optimiser step).  Every rank maps every other rank's arena and control block (cudaIpc, same node,
+ *      NVLink peers); see csrc/qa_peer.cu for the protocol.  In place: afterwards every rank's arena holds the bit-identical
+ *      SUM over ranks.  sumsq_out[0] / [1] (fp64, may be NULL) receive sum(g^2) of arena[0 : seg_split) and of
+ *      arena[seg_split : norm_end) -- the actor-critic and the estimator gradients of the arena layout
+ *      [actor-critic | estimator | kl, pad] -- i.e. what K8's own norm kernel would compute on the reduced gradients.
+ * ------------------------------------------------------------------------------------------ */
+#define QA_PEER_MAX_RANKS 8
+typedef struct QaPeerAllreduceArgs {
+    int32_t world_size, rank;
+    int64_t n;                              /* floats in the arena, multiple of 4 */
+    int64_t seg_split, norm_end;            /* 0 <= seg_split <= norm_end <= n */
+    float* arena[QA_PEER_MAX_RANKS];        /* arena[p] = rank p's arena as mapped in THIS process (arena[rank] = own) */
+    uint32_t* ctrl[QA_PEER_MAX_RANKS];      /* control blocks (qa_peer_ctrl_bytes() each, zero-initialised once), same mapping */
+    double* sumsq_out[2];
+    /* so that K8 can run as its update pass alone (qa_adam_apply): the norms are stored multiplied by grad_scale^2 (K8 squares
+     * grad * grad_scale), step_inc[k] (may be NULL) is incremented by one like K8's own norm pass does, and
+     * arena[scale_index] (the KL scalar of the arena layout; -1 = none) is multiplied by grad_scale (rank mean) */
+    float grad_scale;
+    int32_t* step_inc[2];
+    int64_t scale_index;
+} QaPeerAllreduceArgs;
+int qa_peer_ctrl_bytes(void);
+/* K8's update pass alone: workspace (sum of squares of grad * grad_scale, fp64) and *step are taken as they are */
+int qa_adam_apply(const QaClipAdamArgs* a, void* stream);
+int qa_peer_allreduce(const QaPeerAllreduceArgs* a, void* stream);
+/* exportable device buffers for the above: cudaMalloc + zero fill / cudaFree / cudaIpcGetMemHandle (64 bytes) /
+ * cudaIpcOpenMemHandle (lazy peer access) / cudaIpcCloseMemHandle */
+int qa_ipc_alloc(void** ptr, uint64_t bytes);
+int qa_ipc_free(void* ptr);
+int qa_ipc_get_handle(const void* ptr, uint8_t* handle64);
+int qa_ipc_open_handle(const uint8_t* handle64, void** ptr);
+int qa_ipc_close_handle(void* ptr);
 
 #ifdef __cplusplus
 }

@@ -49,6 +49,7 @@ extern "C" int qa_struct_size(int which) {
         case 31: return (int)sizeof(QaDiscRegArgs);
         case 32: return (int)sizeof(QaNormMomentsArgs);
         case 33: return (int)sizeof(QaNormMergeArgs);
+        case 34: return (int)sizeof(QaPeerAllreduceArgs);
         default: return -1;
     }
 }

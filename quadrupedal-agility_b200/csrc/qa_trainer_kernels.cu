@@ -160,6 +160,21 @@ extern "C" int qa_clip_adam(const QaClipAdamArgs* a, void* stream) {
     QA_LAUNCH_RET();
 }
 
+// K8's update pass alone: the norm (and the step increment) were produced by K31 while it reduced the gradients
+extern "C" int qa_adam_apply(const QaClipAdamArgs* a, void* stream) {
+    QA_CHECK_PTR(a);
+    if (a->numel == 0) return 0;
+    const void* need[] = {a->params, a->grads, a->exp_avg, a->exp_avg_sq, a->lr, a->step, a->workspace};
+    for (const void* p : need) QA_CHECK_PTR(p);
+    if (a->numel < 0) return QA_EINVAL;
+    if ((((uintptr_t)a->params | (uintptr_t)a->grads | (uintptr_t)a->exp_avg | (uintptr_t)a->exp_avg_sq) & 15u) != 0) return QA_EINVAL;
+    long long blocks = ((a->numel >> 2) + 255) / 256;
+    if (blocks < 1) blocks = 1;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_clip_adam<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*a);
+    QA_LAUNCH_RET();
+}
+
 // ------------------------------------------------------------------------------------------
 // K9: activation backward fused with the bias gradient:  gz = gy * act'(y),  db[c] = sum_r gz[r,c]
 //     (the element-wise half of the backward of every Linear+ELU/ReLU, actor_critic.py:113-129).  The ELU

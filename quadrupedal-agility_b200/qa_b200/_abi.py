@@ -184,6 +184,15 @@ class QaNormMergeArgs(C.Structure):
                 ("prior_batch", vp), ("prior_soft_coef", C.c_float), ("std", vp), ("min_std", vp), ("num_std", C.c_int32)]
 
 
+QA_PEER_MAX_RANKS = 8
+
+
+class QaPeerAllreduceArgs(C.Structure):
+    _fields_ = [("world_size", C.c_int32), ("rank", C.c_int32), ("n", C.c_int64), ("seg_split", C.c_int64), ("norm_end", C.c_int64),
+                ("arena", vp * QA_PEER_MAX_RANKS), ("ctrl", vp * QA_PEER_MAX_RANKS), ("sumsq_out", vp * 2),
+                ("grad_scale", C.c_float), ("step_inc", vp * 2), ("scale_index", C.c_int64)]
+
+
 class QaHeadBwdArgs(C.Structure):
     _fields_ = [("M", C.c_int64), ("N", C.c_int32), ("Kh", C.c_int32), ("act", C.c_int32), ("gz_scale", C.c_float),
                 ("gz", vp), ("gz_pitch", C.c_int64), ("h", vp), ("h_pitch", C.c_int64), ("w", vp), ("w_pitch", C.c_int64),
@@ -312,6 +321,14 @@ SYMBOLS = {
     "qa_gae": (C.c_int, [C.POINTER(QaGaeArgs), vp]),
     "qa_gather_minibatch": (C.c_int, [C.POINTER(QaGatherArgs), vp]),
     "qa_clip_adam": (C.c_int, [C.POINTER(QaClipAdamArgs), vp]),
+    "qa_adam_apply": (C.c_int, [C.POINTER(QaClipAdamArgs), vp]),
+    "qa_peer_allreduce": (C.c_int, [C.POINTER(QaPeerAllreduceArgs), vp]),
+    "qa_peer_ctrl_bytes": (C.c_int, []),
+    "qa_ipc_alloc": (C.c_int, [C.POINTER(vp), C.c_uint64]),
+    "qa_ipc_free": (C.c_int, [vp]),
+    "qa_ipc_get_handle": (C.c_int, [vp, C.c_char_p]),
+    "qa_ipc_open_handle": (C.c_int, [C.c_char_p, C.POINTER(vp)]),
+    "qa_ipc_close_handle": (C.c_int, [vp]),
     "qa_linear_fwd": (C.c_int, [C.POINTER(QaLinearArgs), vp]),
     "qa_linear_bwd": (C.c_int, [C.POINTER(QaLinearBwdArgs), vp]),
     "qa_act_bwd": (C.c_int, [C.POINTER(QaActBwdArgs), vp]),
@@ -342,7 +359,7 @@ STRUCT_ORDER = [QaActionPushArgs, QaTorqueArgs, QaTerrain, QaHeightScanArgs, QaM
                 QaBbcConst, QaBbcStepArgs, QaCompactArgs, QaGaeArgs, QaGatherArgs, QaClipAdamArgs, QaLinearArgs, QaActBwdArgs, QaPpoLossArgs, QaLinearBwdArgs, QaHistEncArgs,
                 QaRowLossArgs, QaPpoScalarsArgs, QaDepthArgs, QaPpoLossTscArgs, QaTscConst, QaTscStepArgs,
                 QaDiscInputArgs, QaDiscRewardArgs, QaHeadFwdArgs, QaHeadBwdArgs, QaPolicySampleArgs, QaDiscPrepareArgs, QaDiscHeadsArgs,
-                QaDiscGpArgs, QaDiscRegArgs, QaNormMomentsArgs, QaNormMergeArgs]
+                QaDiscGpArgs, QaDiscRegArgs, QaNormMomentsArgs, QaNormMergeArgs, QaPeerAllreduceArgs]
 
 _LIB = None
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libqa_b200.so")

@@ -65,3 +65,82 @@ def allreduce_mean_grads_(params) -> None:
         n = g.numel()
         g.copy_(flat[off:off + n].view_as(g))
         off += n
+
+
+class _CudaBlob:
+    """A cudaMalloc'ed buffer exposed to torch through __cuda_array_interface__ (zero copy)."""
+
+    def __init__(self, ptr: int, nbytes: int, typestr: str, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2,
+                                         "strides": None}
+        self.nbytes = nbytes
+
+
+class PeerArena:
+    """The PPO gradient arena of every rank of ONE node, mapped into every process (cudaIpc over NVLink peers), for K31
+    (`ops.peer_allreduce`): `tensor` = this rank's arena (fp32, n floats, zero-filled), `arena_ptrs[p]` / `ctrl_ptrs[p]` = rank
+    p's arena / control block as mapped here.  Handles travel through `dist.all_gather_object`.  `available()` says whether the
+    process group qualifies (NCCL backend, all ranks on this node, <= 8 ranks, QA_PEER_ALLREDUCE != 0)."""
+
+    @staticmethod
+    def available() -> bool:
+        import os
+        if os.environ.get("QA_PEER_ALLREDUCE", "1") != "1" or not (dist.is_available() and dist.is_initialized()):
+            return False
+        w = dist.get_world_size()
+        if w < 2 or w > 8 or dist.get_backend() != "nccl":
+            return False
+        local = int(os.environ.get("LOCAL_WORLD_SIZE", w))
+        return local == w
+
+    def __init__(self, n: int, device):
+        import ctypes as C
+        from . import _abi
+        lib = _abi.load()
+        self._lib, self.n = lib, int(n)
+        self.rank, self.world_size = dist.get_rank(), dist.get_world_size()
+        dev = torch.device(device)
+        torch.cuda.set_device(dev)
+        ctrl_bytes = int(lib.qa_peer_ctrl_bytes())
+        self._own = []
+        handles = []
+        for nbytes in (self.n * 4, ctrl_bytes):
+            p = C.c_void_p()
+            _abi.check(lib.qa_ipc_alloc(C.byref(p), nbytes), "qa_ipc_alloc")
+            h = C.create_string_buffer(64)
+            _abi.check(lib.qa_ipc_get_handle(p, h), "qa_ipc_get_handle")
+            self._own.append(int(p.value))
+            handles.append(bytes(h.raw))
+        gathered = [None] * self.world_size
+        dist.all_gather_object(gathered, handles)
+        self.arena_ptrs, self.ctrl_ptrs, self._opened = [], [], []
+        for r, (ha, hc) in enumerate(gathered):
+            if r == self.rank:
+                self.arena_ptrs.append(self._own[0])
+                self.ctrl_ptrs.append(self._own[1])
+                continue
+            ptrs = []
+            for h in (ha, hc):
+                q = C.c_void_p()
+                _abi.check(lib.qa_ipc_open_handle(C.c_char_p(h), C.byref(q)), "qa_ipc_open_handle")
+                ptrs.append(int(q.value))
+                self._opened.append(int(q.value))
+            self.arena_ptrs.append(ptrs[0])
+            self.ctrl_ptrs.append(ptrs[1])
+        self.tensor = torch.as_tensor(_CudaBlob(self._own[0], self.n * 4, "<f4", (self.n,)), device=dev)
+        dist.barrier()                                   # every rank has mapped every arena before the first kernel touches one
+
+    def close(self):
+        """Unmap the peers' buffers and free this rank's (after a barrier: nobody may still be reading them)."""
+        import ctypes as C
+        if getattr(self, "_lib", None) is None:
+            return
+        torch.cuda.synchronize()
+        if dist.is_initialized():
+            dist.barrier()
+        for q in self._opened:
+            self._lib.qa_ipc_close_handle(C.c_void_p(q))
+        self.tensor = None
+        for p in self._own:
+            self._lib.qa_ipc_free(C.c_void_p(p))
+        self._lib = None

@@ -225,6 +225,37 @@ def clip_adam(params, grads, exp_avg, exp_avg_sq, lr, step, workspace, beta1=0.9
     _count(2)
 
 
+def adam_apply(params, grads, exp_avg, exp_avg_sq, lr, step, workspace, beta1=0.9, beta2=0.999, eps=1e-8, max_grad_norm=1.0,
+               grad_scale=1.0, grad_norm_out=None, weight_decay=0.0) -> None:
+    """K8's update pass alone: `workspace` already holds sum((grad * grad_scale)^2) and `step` is already incremented (K31)."""
+    lib = _abi.load()
+    f = torch.float32
+    a = _abi.QaClipAdamArgs(params.numel(), _p(params, f, "params"), _p(grads, f, "grads"), _p(exp_avg, f, "exp_avg"),
+                            _p(exp_avg_sq, f, "exp_avg_sq"), _p(lr, f, "lr"), _p(step, torch.int32, "step"),
+                            float(beta1), float(beta2), float(eps), float(max_grad_norm), float(grad_scale),
+                            _p(grad_norm_out, f, "grad_norm_out"), _p(workspace, torch.float64, "workspace"),
+                            float(weight_decay))
+    _abi.check(lib.qa_adam_apply(C.byref(a), _stream()), "qa_adam_apply")
+    _count(1)
+
+
+def peer_allreduce(world_size, rank, n, arena_ptrs, ctrl_ptrs, seg_split=0, norm_end=0, sumsq_out=(None, None), grad_scale=1.0,
+                   step_inc=(None, None), scale_index=-1) -> None:
+    """K31: in-place all-reduce(SUM) of every rank's arena over NVLink peer memory (+ the gradient norms K8 needs).
+    `arena_ptrs[p]` / `ctrl_ptrs[p]`: device addresses of rank p's arena / control block as mapped in this process."""
+    lib = _abi.load()
+    a = _abi.QaPeerAllreduceArgs()
+    a.world_size, a.rank, a.n, a.seg_split, a.norm_end = int(world_size), int(rank), int(n), int(seg_split), int(norm_end)
+    for p in range(world_size):
+        a.arena[p], a.ctrl[p] = int(arena_ptrs[p]), int(ctrl_ptrs[p])
+    for k in range(2):
+        a.sumsq_out[k] = None if sumsq_out[k] is None else _p(sumsq_out[k], torch.float64, "sumsq_out")
+        a.step_inc[k] = None if step_inc[k] is None else _p(step_inc[k], torch.int32, "step_inc")
+    a.grad_scale, a.scale_index = float(grad_scale), int(scale_index)
+    _abi.check(lib.qa_peer_allreduce(C.byref(a), _stream()), "qa_peer_allreduce")
+    _count(1)
+
+
 # ---- K7 ---------------------------------------------------------------------------------------
 ACT_ID = {None: 0, "none": 0, "elu": 1, "relu": 2}
 

@@ -76,10 +76,12 @@ class FlatAdam:
         self.ws = torch.zeros(2, device=dev, dtype=torch.float64)
         self.betas, self.eps, self.max_grad_norm, self.weight_decay = betas, eps, max_grad_norm, weight_decay
 
-    def step(self, grad_scale: float = 1.0):
-        ops.clip_adam(self.flat.data[self.lo:self.hi], self.flat.grad[self.lo:self.hi], self.exp_avg, self.exp_avg_sq, self.lr,
-                      self.step_count, self.ws, self.betas[0], self.betas[1], self.eps, self.max_grad_norm, grad_scale,
-                      self.grad_norm, self.weight_decay)
+    def step(self, grad_scale: float = 1.0, presummed: bool = False):
+        """`presummed`: K31 has already left sum((grad * grad_scale)^2) in `ws` and incremented `step_count`."""
+        fn = ops.adam_apply if presummed else ops.clip_adam
+        fn(self.flat.data[self.lo:self.hi], self.flat.grad[self.lo:self.hi], self.exp_avg, self.exp_avg_sq, self.lr,
+           self.step_count, self.ws, self.betas[0], self.betas[1], self.eps, self.max_grad_norm, grad_scale,
+           self.grad_norm, self.weight_decay)
 
     # torch.optim-compatible state for checkpoints
     def state_dict(self):
@@ -222,7 +224,15 @@ class SSInfoGAIL:
     def use_grad_arena(self):
         """[actor-critic grads | estimator grads | kl, pad] in one contiguous buffer; `_allreduce_grads` then needs one collective."""
         n_ac, n_est = self.ac_flat.numel, self.est_flat.numel
-        arena = torch.zeros(n_ac + n_est + 4, device=self.device)
+        n = (n_ac + n_est + 4 + 3) // 4 * 4
+        self._peer = None
+        if torch.device(self.device).type == "cuda" and qdist.PeerArena.available():
+            # every rank's arena mapped into every process (cudaIpc, NVLink peers): the all-reduce is K31, one kernel that also
+            # leaves the gradient norms for K8 -- no NCCL collective on the optimiser step (QA_PEER_ALLREDUCE=0: NCCL)
+            self._peer = qdist.PeerArena(n, self.device)
+            arena = self._peer.tensor
+        else:
+            arena = torch.zeros(n, device=self.device)
         self.ac_flat.rebind_grad(arena[:n_ac])
         self.est_flat.rebind_grad(arena[n_ac:n_ac + n_est])
         self._kl = arena[n_ac + n_est]
@@ -231,6 +241,14 @@ class SSInfoGAIL:
     def _allreduce_grads(self) -> float:
         """SUM of the flat gradients over the ranks (the 1/W goes into K8's grad_scale) and the rank-mean of the KL."""
         if self._grad_arena is not None:
+            peer = getattr(self, "_peer", None)
+            if peer is not None:
+                n_ac, n_est = self.ac_flat.numel, self.est_flat.numel
+                scale = 1.0 / self.world_size
+                ops.peer_allreduce(peer.world_size, peer.rank, peer.n, peer.arena_ptrs, peer.ctrl_ptrs, seg_split=n_ac,
+                                   norm_end=n_ac + n_est, sumsq_out=(self.optim_ac.ws, self.optim_estimator.ws), grad_scale=scale,
+                                   step_inc=(self.optim_ac.step_count, self.optim_estimator.step_count), scale_index=n_ac + n_est)
+                return scale
             scale = qdist.allreduce_flat_(self._grad_arena)
             self._kl.mul_(scale)
             return scale
@@ -854,8 +872,9 @@ class SSInfoGAIL:
         scale = 1.0
         if self.world_size > 1:
             scale = self._allreduce_grads()
+        pre = self.world_size > 1 and getattr(self, "_peer", None) is not None
         if not getattr(getattr(self, "_plan", None), "est_stepped_in_chain", False):
-            self.optim_estimator.step(scale)
+            self.optim_estimator.step(scale, presummed=pre)
         adaptive = self.desired_kl is not None and self.schedule == 'adaptive'
         if torch.device(self.device).type == "cuda":
             # K13: adaptive LR + the seven running statistics, one launch
@@ -871,7 +890,7 @@ class SSInfoGAIL:
                 hi = kl > self.desired_kl * 2.0
                 lo = (kl < self.desired_kl / 2.0) & (kl > 0.0)
                 lr.copy_(torch.where(hi, torch.clamp(lr / 1.5, min=1e-5), torch.where(lo, torch.clamp(lr * 1.5, max=1e-2), lr)))
-        self.optim_ac.step(scale)
+        self.optim_ac.step(scale, presummed=pre)
 
     def _minibatch_step(self):
         self._forward_backward()
