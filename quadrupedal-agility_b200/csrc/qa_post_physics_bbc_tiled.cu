@@ -177,7 +177,15 @@ __device__ __forceinline__ void reset_precompute(const QaBbcConst& c, const K2St
         const double cu = u64_to_unit_f64(rr.v[0], rr.v[1]);
         time_u = u64_to_unit_f64(rr.v[2], rr.v[3]);
         // the behaviour mode P2b is going to draw for this reset (same site, same stream)
-        const int m = draw_site(c, a, e, SITE_RT0, a.rt_eps_u, a.rt_c_idx, a.rt_cmd_u).c_idx;
+        int m;                                                          // == draw_site(..., SITE_RT0, ...).c_idx
+        if (a.rt_eps_u != nullptr) {
+            m = a.rt_c_idx[e];
+        } else {
+            Philox4 r0 = philox4x32_10((uint32_t)e, SITE_RT0, (uint32_t)a.rng_step, (uint32_t)(a.rng_step >> 32),
+                                       (uint32_t)a.rng_seed, (uint32_t)(a.rng_seed >> 32));
+            m = pick_mode(c, a.prior_cdf, u32_to_unit_f32(r0.v[2]));
+        }
+        m = min(max(m, 0), QA_DIM_C - 1);
         const int lo = __shfl_sync(QA_FULL, mode_off, 18 + m), hi = __shfl_sync(QA_FULL, mode_off, 18 + m + 1);
         // The sequential scan `j = lo; while (j < hi - 1 && cdf[j] <= cu) ++j` ends at the first j in [lo, hi - 1) with
         // !(cdf[j] <= cu), else at hi - 1.  32 candidates per round, one per lane; every lane also fetches ITS candidate's clip
@@ -353,25 +361,6 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
         const int el = wid, e = e0 + el;
         const bool dl = lane < QA_NUM_DOF;
         const int d_ = dl ? lane : 0;
-        // noise of this step (:318-319) needs nothing but (env, lane, step): drawn while the tiles are in flight
-        float nz[QA_MAX_NOISE_LANES / 32];
-#pragma unroll
-        for (int kk = 0; kk < QA_MAX_NOISE_LANES / 32; ++kk) {
-            const int k = kk * 32 + lane;
-            nz[kk] = 0.f;
-            if (k < c.num_noise) {
-                const int i = c.noise_idx[k];
-                float u;
-                if (a.noise_u != nullptr) {
-                    u = a.noise_u[(size_t)e * ROW + i];
-                } else {
-                    Philox4 rr = philox4x32_10((uint32_t)e, SITE_NOISE0 + (i >> 2), (uint32_t)a.rng_step,
-                                               (uint32_t)(a.rng_step >> 32), (uint32_t)a.rng_seed, (uint32_t)(a.rng_seed >> 32));
-                    u = u32_to_unit_f32(rr.v[i & 3]);
-                }
-                nz[kk] = (2.f * u - 1.f) * c.noise_scale[k];
-            }
-        }
         STAMP(1, T_ENV);
         mbar_wait(&S.bar_small, 0);
         STAMP(2, T_ENV);
@@ -410,6 +399,26 @@ k_post_physics_bbc_tiled(const __grid_constant__ QaBbcConst c, const __grid_cons
         }
         bar_arrive(1, T2_THREADS);          // P1 results are in S.scal: the scalar warp may run P2b while this warp goes on
         if (early_reset) reset_precompute(c, a, e, lane, B, S.rst[el], mode_off);
+        // noise of this step (:318-319) needs nothing but (env, lane, step): drawn after P1, in this warp's slack before
+        // barrier 2 (a resetting env starts its precompute that much earlier)
+        float nz[QA_MAX_NOISE_LANES / 32];
+#pragma unroll
+        for (int kk = 0; kk < QA_MAX_NOISE_LANES / 32; ++kk) {
+            const int k = kk * 32 + lane;
+            nz[kk] = 0.f;
+            if (k < c.num_noise) {
+                const int i = c.noise_idx[k];
+                float u;
+                if (a.noise_u != nullptr) {
+                    u = a.noise_u[(size_t)e * ROW + i];
+                } else {
+                    Philox4 rr = philox4x32_10((uint32_t)e, SITE_NOISE0 + (i >> 2), (uint32_t)a.rng_step,
+                                               (uint32_t)(a.rng_step >> 32), (uint32_t)a.rng_seed, (uint32_t)(a.rng_seed >> 32));
+                    u = u32_to_unit_f32(rr.v[i & 3]);
+                }
+                nz[kk] = (2.f * u - 1.f) * c.noise_scale[k];
+            }
+        }
         STAMP(3, T_ENV);
         // ---------------- P3a: everything of the row that depends on loaded inputs only ---------------------
         // (the reset path of P3b redoes the DOF lanes for the ~1.5 % reset envs)

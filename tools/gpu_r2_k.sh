@@ -2,7 +2,7 @@
 # K2 after moving the euler angles to the env warps + early history store: parity, phase trace, roofline legs
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_env_gpu.py tests/test_advice_gpu.py tests/test_zz_runner_gpu.py -q > gpurun_out/pytest_env.log 2>&1; echo "env tests rc=$?"; grep -E "^FAILED|^ERROR|passed|failed" gpurun_out/pytest_env.log | tail -8
-timeout 300 python tools/k2_trace.py --envs 4096 --reps 20 > gpurun_out/k2_trace_r2f.txt 2>&1; echo "trace rc=$?"; tail -26 gpurun_out/k2_trace_r2f.txt
+timeout 300 python tools/k2_trace.py --envs 4096 --reps 20 > gpurun_out/k2_trace_r2h.txt 2>&1; echo "trace rc=$?"; tail -26 gpurun_out/k2_trace_r2h.txt
 timeout 900 python bench.py --steps 10 --warmup 3 --no-tsc --no-cpu-baseline --no-torch-gpu-baseline --no-fp32-value > gpurun_out/bench_k.json 2> gpurun_out/bench_k.err; echo "bench rc=$?"; python - <<'PY'
 import json
 d = [json.loads(l) for l in open("gpurun_out/bench_k.json") if l.startswith("{")][-1]
