@@ -51,7 +51,7 @@ int qa_version(void);
 /* human readable build string ("sm_100a, nvcc 12.9, ...") */
 const char* qa_build_info(void);
 /* sizeof() of argument struct number `which` (order of declaration in this header, QaActionPushArgs
- * = 0 ... QaGaeArgs = 9, QaGatherArgs = 10, QaClipAdamArgs = 11, QaLinearArgs = 12, QaActBwdArgs = 13, QaPpoLossArgs = 14, QaLinearBwdArgs = 15, QaHistEncArgs = 16, QaRowLossArgs = 17, QaPpoScalarsArgs = 18, QaDepthArgs = 19, QaPpoLossTscArgs = 20, QaTscConst = 21, QaTscStepArgs = 22, QaDiscInputArgs = 23, QaDiscRewardArgs = 24, QaHeadFwdArgs = 25, QaHeadBwdArgs = 26, QaPolicySampleArgs = 27, QaDiscPrepareArgs = 28, QaDiscHeadsArgs = 29, QaDiscGpArgs = 30, QaDiscRegArgs = 31, QaNormMomentsArgs = 32, QaNormMergeArgs = 33, QaPeerAllreduceArgs = 34; -1 if unknown): a layout handshake for FFI mirrors of these structs */
+ * = 0 ... QaGaeArgs = 9, QaGatherArgs = 10, QaClipAdamArgs = 11, QaLinearArgs = 12, QaActBwdArgs = 13, QaPpoLossArgs = 14, QaLinearBwdArgs = 15, QaHistEncArgs = 16, QaRowLossArgs = 17, QaPpoScalarsArgs = 18, QaDepthArgs = 19, QaPpoLossTscArgs = 20, QaTscConst = 21, QaTscStepArgs = 22, QaDiscInputArgs = 23, QaDiscRewardArgs = 24, QaHeadFwdArgs = 25, QaHeadBwdArgs = 26, QaPolicySampleArgs = 27, QaDiscPrepareArgs = 28, QaDiscHeadsArgs = 29, QaDiscGpArgs = 30, QaDiscRegArgs = 31, QaNormMomentsArgs = 32, QaNormMergeArgs = 33, QaPeerAllreduceArgs = 34, QaAdamChainArgs = 35; -1 if unknown): a layout handshake for FFI mirrors of these structs */
 int qa_struct_size(int which);
 /* stream-ordered fill-with-zero / device-to-device copy of `bytes` bytes (cudaMemsetAsync / cudaMemcpyAsync): lets a captured
  * training step zero its flat gradient buffer (optimizer.zero_grad(), gail.py:361, :409) and move device scalars without a
@@ -898,6 +898,30 @@ typedef struct QaNormMergeArgs {
     float* std; const float* min_std; int32_t num_std;    /* policy std floor or NULL */
 } QaNormMergeArgs;
 int qa_norm_merge(const QaNormMergeArgs* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K8c  a CHAIN of Adam steps (torch.optim.Adam semantics, weight decay added to the gradient, no clipping) over one flat
+ *      parameter buffer in ONE launch: op k updates params[lo_k, hi_k) with its own moments / learning rate / step counter;
+ *      an element covered by several ops receives their updates in op order, each seeing the parameter the previous one
+ *      left -- the discriminator's three optimisers, which all step the shared trunk (bbc/rsl_rl/algorithms/gail.py:107-128,
+ *      :519-521), as one kernel instead of fifteen graph nodes.  Every step counter is incremented by one.
+ * ------------------------------------------------------------------------------------------ */
+#define QA_ADAM_CHAIN_MAX 8
+typedef struct QaAdamChainOp {
+    int64_t lo, hi;                     /* element range in the flat buffer, multiples of 4 */
+    float* exp_avg; float* exp_avg_sq;  /* (hi - lo), 16-byte aligned */
+    const float* lr;                    /* (1) device scalar */
+    int32_t* step;                      /* (1) device counter: value BEFORE this step */
+    float weight_decay;
+} QaAdamChainOp;
+typedef struct QaAdamChainArgs {
+    float* params; const float* grads;  /* flat buffers, 16-byte aligned */
+    int32_t num_ops;
+    QaAdamChainOp ops[QA_ADAM_CHAIN_MAX];
+    float beta1, beta2, eps, grad_scale;
+    uint32_t* ticket;                   /* (1) zero-initialised once */
+} QaAdamChainArgs;
+int qa_adam_chain(const QaAdamChainArgs* a, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * K31  peer-memory all-reduce of the PPO gradient arena fused with K8's gradient-norm pass (ONE all-reduce of the

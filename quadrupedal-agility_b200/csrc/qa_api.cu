@@ -50,6 +50,7 @@ extern "C" int qa_struct_size(int which) {
         case 32: return (int)sizeof(QaNormMomentsArgs);
         case 33: return (int)sizeof(QaNormMergeArgs);
         case 34: return (int)sizeof(QaPeerAllreduceArgs);
+        case 35: return (int)sizeof(QaAdamChainArgs);
         default: return -1;
     }
 }

@@ -160,6 +160,75 @@ extern "C" int qa_clip_adam(const QaClipAdamArgs* a, void* stream) {
     QA_LAUNCH_RET();
 }
 
+// K8c: a chain of Adam steps over one flat buffer (see qa_b200.h).  Thread = one float4 of the union range; the ops are applied
+// to it in order, in registers.
+__global__ void __launch_bounds__(256) k_adam_chain(const __grid_constant__ QaAdamChainArgs a, long long first4, long long last4) {
+    __shared__ float s_step_size[QA_ADAM_CHAIN_MAX], s_bc2_sqrt[QA_ADAM_CHAIN_MAX];
+    __shared__ unsigned s_last;
+    if (threadIdx.x < a.num_ops) {
+        const QaAdamChainOp& o = a.ops[threadIdx.x];
+        const int step = *o.step + 1;
+        const float bc1 = 1.f - powf(a.beta1, (float)step);
+        s_bc2_sqrt[threadIdx.x] = sqrtf(1.f - powf(a.beta2, (float)step));
+        s_step_size[threadIdx.x] = *o.lr / bc1;
+    }
+    __syncthreads();
+    for (long long i = first4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < last4; i += (long long)gridDim.x * blockDim.x) {
+        float4 p = reinterpret_cast<float4*>(a.params)[i];
+        const float4 g = reinterpret_cast<const float4*>(a.grads)[i];
+        bool touched = false;
+        for (int k = 0; k < a.num_ops; ++k) {
+            const QaAdamChainOp& o = a.ops[k];
+            if (i * 4 < o.lo || i * 4 >= o.hi) continue;
+            const long long j = i - (o.lo >> 2);
+            float4 m = reinterpret_cast<float4*>(o.exp_avg)[j], v = reinterpret_cast<float4*>(o.exp_avg_sq)[j];
+            const float wd = o.weight_decay, ss = s_step_size[k], bq = s_bc2_sqrt[k];
+            p.x = adam_one(p.x, g.x * a.grad_scale + wd * p.x, m.x, v.x, a.beta1, a.beta2, a.eps, ss, bq);
+            p.y = adam_one(p.y, g.y * a.grad_scale + wd * p.y, m.y, v.y, a.beta1, a.beta2, a.eps, ss, bq);
+            p.z = adam_one(p.z, g.z * a.grad_scale + wd * p.z, m.z, v.z, a.beta1, a.beta2, a.eps, ss, bq);
+            p.w = adam_one(p.w, g.w * a.grad_scale + wd * p.w, m.w, v.w, a.beta1, a.beta2, a.eps, ss, bq);
+            reinterpret_cast<float4*>(o.exp_avg)[j] = m;
+            reinterpret_cast<float4*>(o.exp_avg_sq)[j] = v;
+            touched = true;
+        }
+        if (touched) reinterpret_cast<float4*>(a.params)[i] = p;
+    }
+    // every block has read the step counters before it takes its ticket: the last one increments them
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_last) {
+        if (threadIdx.x < a.num_ops) *a.ops[threadIdx.x].step += 1;
+        if (threadIdx.x == 0) *a.ticket = 0u;
+    }
+}
+
+extern "C" int qa_adam_chain(const QaAdamChainArgs* a, void* stream) {
+    QA_CHECK_PTR(a);
+    QA_CHECK_PTR(a->params);
+    QA_CHECK_PTR(a->grads);
+    QA_CHECK_PTR(a->ticket);
+    if (a->num_ops <= 0 || a->num_ops > QA_ADAM_CHAIN_MAX) return QA_EINVAL;
+    if ((((uintptr_t)a->params | (uintptr_t)a->grads) & 15u) != 0) return QA_EINVAL;
+    long long lo = -1, hi = -1;
+    for (int k = 0; k < a->num_ops; ++k) {
+        const QaAdamChainOp& o = a->ops[k];
+        const void* need[] = {o.exp_avg, o.exp_avg_sq, o.lr, o.step};
+        for (const void* p : need) QA_CHECK_PTR(p);
+        if (o.lo < 0 || o.hi <= o.lo || (o.lo & 3) || (o.hi & 3) || (((uintptr_t)o.exp_avg | (uintptr_t)o.exp_avg_sq) & 15u)) return QA_EINVAL;
+        lo = lo < 0 || o.lo < lo ? o.lo : lo;
+        hi = o.hi > hi ? o.hi : hi;
+    }
+    const long long n4 = (hi - lo) >> 2;
+    long long blocks = (n4 + 255) / 256;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    k_adam_chain<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(*a, lo >> 2, hi >> 2);
+    QA_LAUNCH_RET();
+}
+
 // K8's update pass alone: the norm (and the step increment) were produced by K31 while it reduced the gradients
 extern "C" int qa_adam_apply(const QaClipAdamArgs* a, void* stream) {
     QA_CHECK_PTR(a);

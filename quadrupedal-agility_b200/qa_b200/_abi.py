@@ -185,6 +185,17 @@ class QaNormMergeArgs(C.Structure):
 
 
 QA_PEER_MAX_RANKS = 8
+QA_ADAM_CHAIN_MAX = 8
+
+
+class QaAdamChainOp(C.Structure):
+    _fields_ = [("lo", C.c_int64), ("hi", C.c_int64), ("exp_avg", vp), ("exp_avg_sq", vp), ("lr", vp), ("step", vp),
+                ("weight_decay", C.c_float)]
+
+
+class QaAdamChainArgs(C.Structure):
+    _fields_ = [("params", vp), ("grads", vp), ("num_ops", C.c_int32), ("ops", QaAdamChainOp * QA_ADAM_CHAIN_MAX),
+                ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("grad_scale", C.c_float), ("ticket", vp)]
 
 
 class QaPeerAllreduceArgs(C.Structure):
@@ -322,6 +333,7 @@ SYMBOLS = {
     "qa_gather_minibatch": (C.c_int, [C.POINTER(QaGatherArgs), vp]),
     "qa_clip_adam": (C.c_int, [C.POINTER(QaClipAdamArgs), vp]),
     "qa_adam_apply": (C.c_int, [C.POINTER(QaClipAdamArgs), vp]),
+    "qa_adam_chain": (C.c_int, [C.POINTER(QaAdamChainArgs), vp]),
     "qa_peer_allreduce": (C.c_int, [C.POINTER(QaPeerAllreduceArgs), vp]),
     "qa_peer_ctrl_bytes": (C.c_int, []),
     "qa_ipc_alloc": (C.c_int, [C.POINTER(vp), C.c_uint64]),
@@ -359,7 +371,7 @@ STRUCT_ORDER = [QaActionPushArgs, QaTorqueArgs, QaTerrain, QaHeightScanArgs, QaM
                 QaBbcConst, QaBbcStepArgs, QaCompactArgs, QaGaeArgs, QaGatherArgs, QaClipAdamArgs, QaLinearArgs, QaActBwdArgs, QaPpoLossArgs, QaLinearBwdArgs, QaHistEncArgs,
                 QaRowLossArgs, QaPpoScalarsArgs, QaDepthArgs, QaPpoLossTscArgs, QaTscConst, QaTscStepArgs,
                 QaDiscInputArgs, QaDiscRewardArgs, QaHeadFwdArgs, QaHeadBwdArgs, QaPolicySampleArgs, QaDiscPrepareArgs, QaDiscHeadsArgs,
-                QaDiscGpArgs, QaDiscRegArgs, QaNormMomentsArgs, QaNormMergeArgs, QaPeerAllreduceArgs]
+                QaDiscGpArgs, QaDiscRegArgs, QaNormMomentsArgs, QaNormMergeArgs, QaPeerAllreduceArgs, QaAdamChainArgs]
 
 _LIB = None
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libqa_b200.so")

@@ -239,6 +239,23 @@ def adam_apply(params, grads, exp_avg, exp_avg_sq, lr, step, workspace, beta1=0.
     _count(1)
 
 
+def adam_chain(params, grads, chain, ticket, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0) -> None:
+    """K8c: the Adam steps of `chain` = [(lo, hi, exp_avg, exp_avg_sq, lr, step, weight_decay), ...] on the flat buffer
+    `params` / `grads`, applied per element in chain order, in ONE launch (no clipping); every `step` is incremented."""
+    lib = _abi.load()
+    f = torch.float32
+    a = _abi.QaAdamChainArgs()
+    a.params, a.grads, a.num_ops = _p(params, f, "params"), _p(grads, f, "grads"), len(chain)
+    for k, (lo, hi, m, v, lr, step, wd) in enumerate(chain):
+        o = a.ops[k]
+        o.lo, o.hi, o.exp_avg, o.exp_avg_sq = int(lo), int(hi), _p(m, f, "exp_avg"), _p(v, f, "exp_avg_sq")
+        o.lr, o.step, o.weight_decay = _p(lr, f, "lr"), _p(step, torch.int32, "step"), float(wd)
+    a.beta1, a.beta2, a.eps, a.grad_scale = float(beta1), float(beta2), float(eps), float(grad_scale)
+    a.ticket = _p(ticket, torch.int32, "ticket")
+    _abi.check(lib.qa_adam_chain(C.byref(a), _stream()), "qa_adam_chain")
+    _count(1)
+
+
 def peer_allreduce(world_size, rank, n, arena_ptrs, ctrl_ptrs, seg_split=0, norm_end=0, sumsq_out=(None, None), grad_scale=1.0,
                    step_inc=(None, None), scale_index=-1) -> None:
     """K31: in-place all-reduce(SUM) of every rank's arena over NVLink peer memory (+ the gradient norms K8 needs).

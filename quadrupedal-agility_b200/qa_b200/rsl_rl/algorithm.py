@@ -620,8 +620,21 @@ class SSInfoGAIL:
             cb()
 
     def _disc_optim_step(self, grad_scale: float = 1.0):
-        for o in self.optim_d + self.optim_q_eps + self.optim_q_c:               # :519-521
-            o.step(grad_scale)
+        opts = self.optim_d + self.optim_q_eps + self.optim_q_c                   # :519-521, in the reference's order
+        flat = self.disc_flat
+        chainable = (flat.data.is_cuda and len(opts) <= 8 and os.environ.get("QA_ADAM_CHAIN", "1") == "1" and
+                     all(o.max_grad_norm <= 0 and o.lo % 4 == 0 and o.hi % 4 == 0 and o.betas == opts[0].betas and o.eps == opts[0].eps
+                         for o in opts))
+        if not chainable:
+            for o in opts:
+                o.step(grad_scale)
+            return
+        # K8c: the three optimisers' five parameter groups as ONE launch (an element of the shared trunk receives its three
+        # updates in order, in registers) instead of 5 x (memset, norm / step kernel, update kernel)
+        if getattr(self, "_adam_chain_ticket", None) is None:
+            self._adam_chain_ticket = torch.zeros(1, device=flat.data.device, dtype=torch.int32)
+        ops.adam_chain(flat.data, flat.grad, [(o.lo, o.hi, o.exp_avg, o.exp_avg_sq, o.lr, o.step_count, o.weight_decay) for o in opts],
+                       self._adam_chain_ticket, opts[0].betas[0], opts[0].betas[1], opts[0].eps, grad_scale)
 
     def update_disc(self, expert, num_updates=None):
         """The discriminator half of SSInfoGAIL.update (gail.py:258-300): `4 * epochs * minibatches` minibatch steps of

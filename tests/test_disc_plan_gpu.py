@@ -266,3 +266,29 @@ def test_update_disc_plan_graph_matches_plan_eager(tc_mode):
     assert float((a[1] - b[1]).abs().max()) < 1e-2
     np.testing.assert_allclose(a[2], b[2], rtol=1e-6, atol=1e-8)
     assert_close("prior", a[3], b[3], rtol=1e-3, atol=1e-6)
+
+
+def test_k8c_adam_chain_equals_the_five_sequential_adam_steps():
+    """The discriminator's three optimisers (five parameter groups, the shared trunk stepped three times with separate
+    moments, weight decay 1e-3) as ONE launch: parameters, moments and step counters bit-equal to five K8 calls, three steps."""
+    import os
+    res = []
+    for chain in ("0", "1"):
+        os.environ["QA_ADAM_CHAIN"] = chain
+        try:
+            alg, _, _ = _disc()
+            g = torch.Generator().manual_seed(8)
+            for _ in range(3):
+                alg.disc_flat.grad.copy_(torch.randn(alg.disc_flat.grad.shape, generator=g) * 0.05)
+                alg._disc_optim_step(0.5)
+            torch.cuda.synchronize()
+            opts = alg.optim_d + alg.optim_q_eps + alg.optim_q_c
+            res.append((alg.disc_flat.data.clone(), [o.exp_avg.clone() for o in opts], [o.exp_avg_sq.clone() for o in opts],
+                        [int(o.step_count) for o in opts]))
+        finally:
+            os.environ.pop("QA_ADAM_CHAIN", None)
+    a, b = res
+    assert a[3] == b[3] == [3] * 5
+    assert torch.equal(a[0], b[0])
+    for x, y in zip(a[1] + a[2], b[1] + b[2]):
+        assert torch.equal(x, y)
