@@ -69,6 +69,7 @@ class DiscStepPlan:
         self.prior_batch = torch.zeros(8, device=dev)
         self._cuda = dev.type == "cuda"            # (the host tests drive the schedule on CPU through stand-in ops: no streams)
         self.s_gp = torch.cuda.Stream(device=dev) if self._cuda else None
+        self.s_gw = torch.cuda.Stream(device=dev) if self._cuda else None      # the penalty's two weight-gradient GEMMs
         sl = alg.disc_flat.slices
         self.reg_segments = [sl["trunk.0.weight"], sl["trunk.2.weight"], sl["linear.weight"]]
         self.obs_dim = alg.num_disc_obs
@@ -101,12 +102,20 @@ class DiscStepPlan:
             ops.linear_bwd(self.v2, None, l2.weight, dx=self.v1, act_prev="relu", y_prev=h1u)          # v1 = m1 (v2 W2)
             ops.linear_bwd(self.v1, None, l1.weight, dx=self.g)                                        # g = v1 W1
             ops.disc_gp_loss(self.g, alg.disc_grad_penalty, stats)                                     # g := d loss / d g
-            ops.linear_bwd(self.v1, self.g, None, dw=l1.weight.grad)                                   # dW1 += v1^T dg
+            gp = _Cur(self._cuda)                                                                      # (current stream = s_gp)
+            # the two weight-gradient GEMMs are leaves of the chain (split-K reduce-adds into the flat gradient buffer): they
+            # run on a third stream next to the dv1 -> dt1 -> dv2 chain, which is the critical path of the whole step
+            gp.fork(self.s_gw)
+            with on(self.s_gw):
+                ops.linear_bwd(self.v1, self.g, None, dw=l1.weight.grad)                               # dW1 += v1^T dg
             ops.linear_fwd(self.g, l1.weight, None, self.dv1, None)                                    # dv1 = dg W1^T
             ops.act_bwd(self.dv1, h1u, "relu", gz=self.dt1)                                            # dt1 = m1 dv1
-            ops.linear_bwd(self.v2, self.dt1, None, dw=l2.weight.grad)                                 # dW2 += v2^T dt1
+            gp.fork(self.s_gw)
+            with on(self.s_gw):
+                ops.linear_bwd(self.v2, self.dt1, None, dw=l2.weight.grad)                             # dW2 += v2^T dt1
             ops.linear_fwd(self.dt1, l2.weight, None, self.dv2, None)                                  # dv2 = dt1 W2^T
             ops.act_bwd(self.dv2, h2u, "relu", gz=None, db=d.linear.weight.grad.view(-1), zero_db=False)   # dw_d += sum m2 dv2
+            gp.join(self.s_gw)
         # ---- main backward -----------------------------------------------------------------------------------------------------
         ops.linear_bwd(self.gz2, None, l2.weight, dx=self.gz1, act_prev="relu", y_prev=self.h1, db_prev=l1.bias.grad,
                        db_accumulate=True)
