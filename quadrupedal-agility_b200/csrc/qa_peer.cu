@@ -34,6 +34,23 @@
 #define PA_TICKET (PA_CTAS * QA_PEER_MAX_RANKS * 3 + PA_CTAS)
 #define PA_CTRL_WORDS (PA_CTAS * QA_PEER_MAX_RANKS * 3 + PA_CTAS + 4)
 
+// optional phase trace (tools/k2_trace.py --build compiles with -DQA_PEER_TRACE; never in the product build): %globaltimer
+// stamps of CTA 0 / thread 0
+#ifdef QA_PEER_TRACE
+__device__ long long g_peer_trace[8];
+extern "C" int qa_peer_trace_dump(long long* host) { return (int)cudaMemcpyFromSymbol(host, g_peer_trace, sizeof(long long) * 8); }
+#define PSTAMP(k)                                                          \
+    do {                                                                   \
+        if (blockIdx.x == 0 && threadIdx.x == 0) {                         \
+            long long t_;                                                  \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));         \
+            g_peer_trace[k] = t_;                                          \
+        }                                                                  \
+    } while (0)
+#else
+#define PSTAMP(k) do { } while (0)
+#endif
+
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
     unsigned v;
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -43,13 +60,21 @@ __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+__device__ __forceinline__ void st_relaxed_sys(unsigned* p, unsigned v) {
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 // CTA-wide barrier with the same CTA of every other rank.  Thread q < W signals rank q and waits for rank q's signal.
-__device__ __forceinline__ void peer_barrier(const QaPeerAllreduceArgs& a, unsigned value) {
-    __syncthreads();                                                    // every thread's prior stores are issued
+// `publish`: this CTA has written peer memory that the other side reads after the barrier.  Then EVERY thread fences its own
+// stores at system scope first (in parallel: one NVLink round trip; a single thread's fence after the __syncthreads measured
+// 8 us, profiles/r2_k31_phase_trace.txt) and the flag goes out relaxed behind the CTA barrier.  Without `publish` (barrier 1:
+// what the peers read was written by earlier kernels of this stream) no fence is needed at all.
+__device__ __forceinline__ void peer_barrier(const QaPeerAllreduceArgs& a, unsigned value, bool publish) {
+    if (publish) asm volatile("fence.acq_rel.sys;" ::: "memory");     // release is all that is needed (not membar.sys = fence.sc.sys)
+    __syncthreads();
     const int q = threadIdx.x;
     if (q < a.world_size) {
-        __threadfence_system();
-        st_release_sys(a.ctrl[q] + PA_FLAG(blockIdx.x, a.rank), value);
+        st_relaxed_sys(a.ctrl[q] + PA_FLAG(blockIdx.x, a.rank), value);
         const unsigned* mine = a.ctrl[a.rank] + PA_FLAG(blockIdx.x, q);
         long long t0 = 0;
         unsigned spins = 0;
@@ -70,7 +95,9 @@ __global__ void __launch_bounds__(PA_THREADS) k_peer_allreduce(const __grid_cons
     const int W = a.world_size, r = a.rank;
     unsigned* my_ctrl = a.ctrl[r];
     const unsigned epoch = my_ctrl[PA_EPOCH(blockIdx.x)];               // written only by this CTA (thread 0, at the end)
-    peer_barrier(a, epoch + 1u);
+    PSTAMP(0);
+    peer_barrier(a, epoch + 1u, false);
+    PSTAMP(1);
     // slice r, in float4 units; this CTA's share of it
     const long long n4 = a.n / 4;                                       // n % 4 == 0 (checked at launch)
     const long long per = (n4 + W - 1) / W;
@@ -110,6 +137,7 @@ __global__ void __launch_bounds__(PA_THREADS) k_peer_allreduce(const __grid_cons
             }
         }
     }
+    PSTAMP(2);
     // CTA partial norms -> every rank's control block (row of this CTA, column of this rank)
     sq0 = warp_sum(sq0), sq1 = warp_sum(sq1);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -121,7 +149,9 @@ __global__ void __launch_bounds__(PA_THREADS) k_peer_allreduce(const __grid_cons
         for (int k = 0; k < PA_THREADS / 32; ++k) t += s_red[threadIdx.x][k];
         for (int p = 0; p < W; ++p) reinterpret_cast<float*>(a.ctrl[p])[PA_NORM(blockIdx.x, r, threadIdx.x)] = t;
     }
-    peer_barrier(a, epoch + 2u);
+    PSTAMP(3);
+    peer_barrier(a, epoch + 2u, true);
+    PSTAMP(4);
     __shared__ unsigned s_last;
     if (threadIdx.x == 0) {
         my_ctrl[PA_EPOCH(blockIdx.x)] = epoch + 2u;

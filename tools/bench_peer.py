@@ -13,7 +13,10 @@ rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int
 torch.cuda.set_device(local)
 dev = torch.device(f"cuda:{local}")
 dist.init_process_group("nccl", device_id=dev)
-from qa_b200 import ops  # noqa: E402
+from qa_b200 import _abi, ops  # noqa: E402
+TRACE = os.environ.get("QA_PEER_TRACE") == "1"
+if TRACE:                                                   # the -DQA_PEER_TRACE build of tools/k2_trace.py --build
+    _abi.LIB_PATH = os.path.join(ROOT, "tools", "_k2trace", "libqa_b200.so")
 from qa_b200.dist import PeerArena  # noqa: E402
 
 N_AC, N_EST = 722_000, 16_000
@@ -66,6 +69,23 @@ def timed(fn, name):
 
 
 timed(peer, "K31 peer all-reduce + norms")
+if TRACE:
+    import ctypes
+    import numpy as np
+    lib = _abi.load()
+    lib.qa_peer_trace_dump.restype = ctypes.c_int
+    lib.qa_peer_trace_dump.argtypes = [ctypes.c_void_p]
+    acc = []
+    for _ in range(20):
+        dist.barrier()
+        peer()
+        torch.cuda.synchronize()
+        h = np.zeros(8, dtype=np.int64)
+        assert lib.qa_peer_trace_dump(h.ctypes.data) == 0
+        acc.append(np.diff(h[:5]) / 1e3)
+    m = np.median(np.array(acc), axis=0)
+    print(f"rank {rank} CTA 0 phases [us]: barrier 1 {m[0]:.2f} | loads + sum + write-back issued {m[1]:.2f} | partial norms + "
+          f"__syncthreads {m[2]:.2f} | barrier 2 (fence.sys waits for the peer stores) {m[3]:.2f}", flush=True)
 x.mul_(0)
 timed(nccl, "ncclAllReduce (same bytes)")
 dist.barrier()

@@ -57,7 +57,7 @@ def build():
         objs.append(o)
         procs.append(subprocess.Popen(
             ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
-             "-DQA_K2_TRACE", "-I" + os.path.join(ROOT, "include"), "-I" + csrc] + (["-fmad=false"] if exact else []) +
+             "-DQA_K2_TRACE", "-DQA_PEER_TRACE", "-I" + os.path.join(ROOT, "include"), "-I" + csrc] + (["-fmad=false"] if exact else []) +
             ["-c", os.path.join(csrc, f), "-o", o]))
     for p in procs:
         if p.wait() != 0:
