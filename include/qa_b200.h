@@ -937,7 +937,7 @@ typedef struct QaPeerAllreduceArgs {
     int64_t n;                              /* floats in the arena, multiple of 4 */
     int64_t seg_split, norm_end;            /* 0 <= seg_split <= norm_end <= n */
     float* arena[QA_PEER_MAX_RANKS];        /* arena[p] = rank p's arena as mapped in THIS process (arena[rank] = own) */
-    uint32_t* ctrl[QA_PEER_MAX_RANKS];      /* control blocks (qa_peer_ctrl_bytes() each, zero-initialised once), same mapping */
+    uint32_t* ctrl[QA_PEER_MAX_RANKS];      /* control blocks (qa_peer_ctrl_bytes(n) each, zero-initialised once), same mapping */
     double* sumsq_out[2];
     /* so that K8 can run as its update pass alone (qa_adam_apply): the norms are stored multiplied by grad_scale^2 (K8 squares
      * grad * grad_scale), step_inc[k] (may be NULL) is incremented by one like K8's own norm pass does, and
@@ -946,7 +946,7 @@ typedef struct QaPeerAllreduceArgs {
     int32_t* step_inc[2];
     int64_t scale_index;
 } QaPeerAllreduceArgs;
-int qa_peer_ctrl_bytes(void);
+long long qa_peer_ctrl_bytes(long long n);   /* bytes of a control block (incl. the staging area) for an arena of n floats */
 /* K8's update pass alone: workspace (sum of squares of grad * grad_scale, fp64) and *step are taken as they are */
 int qa_adam_apply(const QaClipAdamArgs* a, void* stream);
 int qa_peer_allreduce(const QaPeerAllreduceArgs* a, void* stream);

@@ -1,23 +1,29 @@
 // K31: in-place all-reduce(SUM) of the PPO gradient arena over NVLink peer memory, fused with the gradient-norm pass of K8.
 //
 // env shards, ONE all-reduce of the PPO gradients per optimiser step (2.96 MB: actor-critic + estimator gradients +
-// the KL scalar).  Over NCCL that collective costs ~55 us per step at 2 ranks -- launch and protocol latency, not bandwidth -- in
-// a 570 us minibatch step, and the fused clip + Adam (K8) that consumes it then needs a separate sum-of-squares launch per
-// optimiser.  Here every rank maps the other ranks' arenas (cudaIpc) and one kernel does, per rank r of W:
+// the KL scalar).  Over NCCL that collective costs 33 us (2 ranks) to 56 us (8 ranks) per step -- launch and protocol latency,
+// not bandwidth -- in a 570 us minibatch step, and the fused clip + Adam (K8) that consumes it then needs a separate
+// sum-of-squares launch per optimiser.  Here every rank maps the other ranks' arenas and control blocks (cudaIpc) and one kernel
+// does, per rank r of W:
 //
-//   barrier 1   (flag exchange over peer memory) every rank's backward pass has finished -- this kernel is stream ordered
-//               behind it, so a rank that has ENTERED the kernel has complete gradients;
-//   reduce      rank r owns slice r (n / W elements): it reads that slice from all W arenas in rank order 0..W-1, sums in
-//               fp32, and writes the sum back into slice r of ALL W arenas (peer stores).  Slices are disjoint, so one rank's
-//               write-back never touches what another rank is reading; every element is summed by exactly one rank in one
-//               order => all ranks hold bit-identical sums;
+//   barrier     (flag exchange over peer memory, no fence) every rank's backward pass has finished -- this kernel is stream
+//               ordered behind it, so a rank that has ENTERED the kernel has complete gradients;
+//   reduce      rank r owns slice r (n / W elements): it reads that slice from all W arenas in rank order 0..W-1 (peer loads,
+//               every load of the pass in flight), sums in fp32, stores the sum into its own arena and PUSHES it to every
+//               peer as flagged words -- {value, epoch, value, epoch} per 16-byte store into the peer's staging area (the
+//               scheme of NCCL's LL protocol: the 8-byte halves are written atomically, so a reader that sees the epoch sees
+//               the value).  Every element is summed by exactly one rank in one order => bit-identical replicas;
+//   poll        every rank spins on ITS staging words of the other W - 1 slices and unpacks them into its arena.  The data is
+//               its own synchronisation: no second barrier and no system-scope fence (which costs ~7 us on this platform
+//               whatever it has to drain: profiles/r2_k31_phase_trace.txt).  Receiving slice q also proves that rank q has
+//               finished reading this rank's raw gradients, so the arena may be overwritten as soon as the kernel ends;
 //   norm        while it holds the sums, the owner accumulates sum(g^2) per optimiser segment (K8's clip_grad_norm_ input);
-//               the partial norms are exchanged through the control blocks and added in one fixed order by the CTA that takes
-//               the last ticket (bit-identical on every rank again);
-//   barrier 2   all write-backs are visible everywhere before anything downstream (K13, K8, next step's memset) runs.
+//               the CTA partials travel as flagged words too and are added in one fixed order by the CTA that takes the last
+//               ticket (bit-identical on every rank again).
 //
-// Flags are monotonic epochs (no reset, safe under CUDA-graph replay); one flag row per CTA, so CTA b of rank r pairs with
-// CTA b of the other ranks.  Spins are bounded: a protocol error traps after ~2 s instead of hanging the box.
+// Epochs are monotonic call counts (no reset, safe under CUDA-graph replay; a rank cannot enter call e + 1, and overwrite
+// staging words of call e, before every peer has signalled the barrier of call e + 1, i.e. has left call e).  One flag row per
+// CTA, so CTA b of rank r pairs with CTA b of the other ranks.  Spins are bounded: a protocol error traps after ~2 s.
 #include <stdint.h>
 
 #include "qa_b200.h"
@@ -27,12 +33,13 @@
 #define PA_THREADS 512
 
 // layout of one rank's control block (uint32 words): [PA_CTAS][QA_PEER_MAX_RANKS] barrier flags, then
-// [PA_CTAS][QA_PEER_MAX_RANKS][2] float partial norms, then [PA_CTAS] local epochs, then the local last-CTA ticket
+// [PA_CTAS][QA_PEER_MAX_RANKS][2] flagged partial norms {float, epoch}, then [PA_CTAS] local epochs, the local last-CTA ticket,
+// and from PA_STAGE_WORD on the staging area: one {value, epoch} pair per arena element
 #define PA_FLAG(b, r) ((b) * QA_PEER_MAX_RANKS + (r))
-#define PA_NORM(b, r, k) (PA_CTAS * QA_PEER_MAX_RANKS + ((b) * QA_PEER_MAX_RANKS + (r)) * 2 + (k))
-#define PA_EPOCH(b) (PA_CTAS * QA_PEER_MAX_RANKS * 3 + (b))
-#define PA_TICKET (PA_CTAS * QA_PEER_MAX_RANKS * 3 + PA_CTAS)
-#define PA_CTRL_WORDS (PA_CTAS * QA_PEER_MAX_RANKS * 3 + PA_CTAS + 4)
+#define PA_NORM(b, r, k) (PA_CTAS * QA_PEER_MAX_RANKS + (((b) * QA_PEER_MAX_RANKS + (r)) * 2 + (k)) * 2)
+#define PA_EPOCH(b) (PA_CTAS * QA_PEER_MAX_RANKS * 5 + (b))
+#define PA_TICKET (PA_CTAS * QA_PEER_MAX_RANKS * 5 + PA_CTAS)
+#define PA_STAGE_WORD (((PA_CTAS * QA_PEER_MAX_RANKS * 5 + PA_CTAS + 4) + 3) / 4 * 4)
 
 // optional phase trace (tools/k2_trace.py --build compiles with -DQA_PEER_TRACE; never in the product build): %globaltimer
 // stamps of CTA 0 / thread 0
@@ -63,14 +70,26 @@ __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
 __device__ __forceinline__ void st_relaxed_sys(unsigned* p, unsigned v) {
     asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ void st_volatile_v4(uint4* p, uint4 v) {
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 ld_volatile_v4(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void spin_guard(unsigned& spins, long long& t0) {
+    if ((++spins & 4095u) == 0u) {
+        long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t0 == 0) t0 = t;
+        else if (t - t0 > 2000000000LL) __trap();
+    }
+}
 
-// CTA-wide barrier with the same CTA of every other rank.  Thread q < W signals rank q and waits for rank q's signal.
-// `publish`: this CTA has written peer memory that the other side reads after the barrier.  Then EVERY thread fences its own
-// stores at system scope first (in parallel: one NVLink round trip; a single thread's fence after the __syncthreads measured
-// 8 us, profiles/r2_k31_phase_trace.txt) and the flag goes out relaxed behind the CTA barrier.  Without `publish` (barrier 1:
-// what the peers read was written by earlier kernels of this stream) no fence is needed at all.
-__device__ __forceinline__ void peer_barrier(const QaPeerAllreduceArgs& a, unsigned value, bool publish) {
-    if (publish) asm volatile("fence.acq_rel.sys;" ::: "memory");     // release is all that is needed (not membar.sys = fence.sc.sys)
+// CTA-wide barrier with the same CTA of every other rank: thread q < W signals rank q and waits for rank q's signal.  Nothing is
+// published through it (what the peers read afterwards was written by earlier kernels of this stream): no fence.
+__device__ __forceinline__ void peer_barrier(const QaPeerAllreduceArgs& a, unsigned value) {
     __syncthreads();
     const int q = threadIdx.x;
     if (q < a.world_size) {
@@ -78,25 +97,19 @@ __device__ __forceinline__ void peer_barrier(const QaPeerAllreduceArgs& a, unsig
         const unsigned* mine = a.ctrl[a.rank] + PA_FLAG(blockIdx.x, q);
         long long t0 = 0;
         unsigned spins = 0;
-        while ((int)(ld_acquire_sys(mine) - value) < 0) {               // monotonic epochs, wrap safe
-            if ((++spins & 4095u) == 0u) {
-                long long t;
-                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-                if (t0 == 0) t0 = t;
-                else if (t - t0 > 2000000000LL) __trap();
-            }
-        }
+        while ((int)(ld_acquire_sys(mine) - value) < 0) spin_guard(spins, t0);   // monotonic epochs, wrap safe
     }
     __syncthreads();
 }
 
 __global__ void __launch_bounds__(PA_THREADS) k_peer_allreduce(const __grid_constant__ QaPeerAllreduceArgs a) {
     __shared__ float s_red[2][PA_THREADS / 32];
+    __shared__ unsigned s_last;
     const int W = a.world_size, r = a.rank;
     unsigned* my_ctrl = a.ctrl[r];
-    const unsigned epoch = my_ctrl[PA_EPOCH(blockIdx.x)];               // written only by this CTA (thread 0, at the end)
+    const unsigned e = my_ctrl[PA_EPOCH(blockIdx.x)] + 1u;              // this call's epoch (the word is written only by this CTA)
     PSTAMP(0);
-    peer_barrier(a, epoch + 1u, false);
+    peer_barrier(a, e);
     PSTAMP(1);
     // slice r, in float4 units; this CTA's share of it
     const long long n4 = a.n / 4;                                       // n % 4 == 0 (checked at launch)
@@ -127,7 +140,15 @@ __global__ void __launch_bounds__(PA_THREADS) k_peer_allreduce(const __grid_cons
         for (int u = 0; u < U; ++u) {
             const long long i = i0 + u * stride;
             if (i >= hi) continue;
-            for (int p = 0; p < W; ++p) reinterpret_cast<float4*>(a.arena[p])[i] = s[u];
+            reinterpret_cast<float4*>(a.arena[r])[i] = s[u];
+            const uint4 w0 = make_uint4(__float_as_uint(s[u].x), e, __float_as_uint(s[u].y), e);
+            const uint4 w1 = make_uint4(__float_as_uint(s[u].z), e, __float_as_uint(s[u].w), e);
+            for (int dp = 1; dp < W; ++dp) {
+                const int p = (r + dp) % W;
+                uint4* st = reinterpret_cast<uint4*>(a.ctrl[p] + PA_STAGE_WORD) + i * 2;
+                st_volatile_v4(st, w0);
+                st_volatile_v4(st + 1, w1);
+            }
             const float c4[4] = {s[u].x, s[u].y, s[u].z, s[u].w};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -137,8 +158,7 @@ __global__ void __launch_bounds__(PA_THREADS) k_peer_allreduce(const __grid_cons
             }
         }
     }
-    PSTAMP(2);
-    // CTA partial norms -> every rank's control block (row of this CTA, column of this rank)
+    // CTA partial norms -> every rank's control block (row of this CTA, column of this rank) as flagged words
     sq0 = warp_sum(sq0), sq1 = warp_sum(sq1);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) s_red[0][warp] = sq0, s_red[1][warp] = sq1;
@@ -147,28 +167,53 @@ __global__ void __launch_bounds__(PA_THREADS) k_peer_allreduce(const __grid_cons
         float t = 0.f;
 #pragma unroll
         for (int k = 0; k < PA_THREADS / 32; ++k) t += s_red[threadIdx.x][k];
-        for (int p = 0; p < W; ++p) reinterpret_cast<float*>(a.ctrl[p])[PA_NORM(blockIdx.x, r, threadIdx.x)] = t;
+        const unsigned long long word = ((unsigned long long)e << 32) | (unsigned long long)__float_as_uint(t);
+        for (int p = 0; p < W; ++p)
+            *reinterpret_cast<volatile unsigned long long*>(a.ctrl[p] + PA_NORM(blockIdx.x, r, threadIdx.x)) = word;
+    }
+    PSTAMP(2);
+    // poll: the reduced slices of the other ranks arrive in this rank's staging area
+    const uint4* stage = reinterpret_cast<const uint4*>(my_ctrl + PA_STAGE_WORD);
+    for (int dq = 1; dq < W; ++dq) {
+        const int q = (r + W - dq) % W;                                 // the peer whose first target this rank was comes first
+        const long long qlo = (long long)q * per, qhi = min(n4, qlo + per);
+        for (long long i = qlo + (long long)blockIdx.x * PA_THREADS + threadIdx.x; i < qhi; i += stride) {
+            uint4 w0, w1;
+            long long t0 = 0;
+            unsigned spins = 0;
+            while (true) {
+                w0 = ld_volatile_v4(stage + i * 2);
+                w1 = ld_volatile_v4(stage + i * 2 + 1);
+                if (w0.y == e && w0.w == e && w1.y == e && w1.w == e) break;
+                spin_guard(spins, t0);
+            }
+            reinterpret_cast<float4*>(a.arena[r])[i] =
+                make_float4(__uint_as_float(w0.x), __uint_as_float(w0.z), __uint_as_float(w1.x), __uint_as_float(w1.z));
+        }
     }
     PSTAMP(3);
-    peer_barrier(a, epoch + 2u, true);
-    PSTAMP(4);
-    __shared__ unsigned s_last;
+    __syncthreads();
     if (threadIdx.x == 0) {
-        my_ctrl[PA_EPOCH(blockIdx.x)] = epoch + 2u;
+        my_ctrl[PA_EPOCH(blockIdx.x)] = e;
         __threadfence();
         s_last = (atomicAdd(my_ctrl + PA_TICKET, 1u) == PA_CTAS - 1) ? 1u : 0u;
     }
     __syncthreads();
     if (s_last && threadIdx.x < 64) {
-        // every CTA of this rank has passed barrier 2, i.e. the partial norms of all CTAs of all ranks have landed: warp k adds
-        // the PA_CTAS x W partials of segment k -- lane = CTA rows lane, lane + 32, ..., ranks in order, then a fixed xor
-        // butterfly: the same order on every rank, fp64 like K8's own norm pass
+        // warp k adds the PA_CTAS x W partials of segment k as they arrive -- lane = CTA rows lane, lane + 32, ..., ranks in
+        // order, then a fixed xor butterfly: the same order on every rank, fp64 like K8's own norm pass
         __threadfence();
-        const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        const volatile float* c = reinterpret_cast<const volatile float*>(my_ctrl);
+        const int k = threadIdx.x >> 5;
         double t = 0.0;
         for (int b = lane; b < PA_CTAS; b += 32)
-            for (int p = 0; p < W; ++p) t += (double)c[PA_NORM(b, p, k)];
+            for (int p = 0; p < W; ++p) {
+                const volatile unsigned long long* slot = reinterpret_cast<const volatile unsigned long long*>(my_ctrl + PA_NORM(b, p, k));
+                unsigned long long word;
+                long long t0 = 0;
+                unsigned spins = 0;
+                while ((unsigned)((word = *slot) >> 32) != e) spin_guard(spins, t0);
+                t += (double)__uint_as_float((unsigned)word);
+            }
         t = warp_sum_d(t);
         if (lane == 0 && a.sumsq_out[k] != nullptr) {
             *a.sumsq_out[k] = t * (double)a.grad_scale * (double)a.grad_scale;
@@ -177,9 +222,11 @@ __global__ void __launch_bounds__(PA_THREADS) k_peer_allreduce(const __grid_cons
         if (threadIdx.x == 1 && a.scale_index >= 0) a.arena[r][a.scale_index] *= a.grad_scale;
         if (threadIdx.x == 0) my_ctrl[PA_TICKET] = 0u;
     }
+    PSTAMP(4);
 }
 
-extern "C" int qa_peer_ctrl_bytes(void) { return (int)(PA_CTRL_WORDS * sizeof(unsigned)); }
+// bytes of one rank's control block for an arena of n floats: flags + flagged norms + epochs + ticket + staging (8 B per element)
+extern "C" long long qa_peer_ctrl_bytes(long long n) { return (long long)PA_STAGE_WORD * 4 + (n > 0 ? n : 0) * 8; }
 
 extern "C" int qa_peer_allreduce(const QaPeerAllreduceArgs* a, void* stream) {
     QA_CHECK_PTR(a);

@@ -335,7 +335,7 @@ SYMBOLS = {
     "qa_adam_apply": (C.c_int, [C.POINTER(QaClipAdamArgs), vp]),
     "qa_adam_chain": (C.c_int, [C.POINTER(QaAdamChainArgs), vp]),
     "qa_peer_allreduce": (C.c_int, [C.POINTER(QaPeerAllreduceArgs), vp]),
-    "qa_peer_ctrl_bytes": (C.c_int, []),
+    "qa_peer_ctrl_bytes": (C.c_longlong, [C.c_longlong]),
     "qa_ipc_alloc": (C.c_int, [C.POINTER(vp), C.c_uint64]),
     "qa_ipc_free": (C.c_int, [vp]),
     "qa_ipc_get_handle": (C.c_int, [vp, C.c_char_p]),

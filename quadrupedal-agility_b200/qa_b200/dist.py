@@ -101,7 +101,7 @@ class PeerArena:
         self.rank, self.world_size = dist.get_rank(), dist.get_world_size()
         dev = torch.device(device)
         torch.cuda.set_device(dev)
-        ctrl_bytes = int(lib.qa_peer_ctrl_bytes())
+        ctrl_bytes = int(lib.qa_peer_ctrl_bytes(self.n))
         self._own = []
         handles = []
         for nbytes in (self.n * 4, ctrl_bytes):

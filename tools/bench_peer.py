@@ -84,8 +84,8 @@ if TRACE:
         assert lib.qa_peer_trace_dump(h.ctypes.data) == 0
         acc.append(np.diff(h[:5]) / 1e3)
     m = np.median(np.array(acc), axis=0)
-    print(f"rank {rank} CTA 0 phases [us]: barrier 1 {m[0]:.2f} | loads + sum + write-back issued {m[1]:.2f} | partial norms + "
-          f"__syncthreads {m[2]:.2f} | barrier 2 (fence.sys waits for the peer stores) {m[3]:.2f}", flush=True)
+    print(f"rank {rank} CTA 0 phases [us]: barrier {m[0]:.2f} | reduce own slice + push flagged words {m[1]:.2f} | poll + unpack the "
+          f"peers' slices {m[2]:.2f} | ticket + norms {m[3]:.2f}", flush=True)
 x.mul_(0)
 timed(nccl, "ncclAllReduce (same bytes)")
 dist.barrier()
