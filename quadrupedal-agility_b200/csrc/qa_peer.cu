@@ -25,6 +25,7 @@
 // staging words of call e, before every peer has signalled the barrier of call e + 1, i.e. has left call e).  One flag row per
 // CTA, so CTA b of rank r pairs with CTA b of the other ranks.  Spins are bounded: a protocol error traps after ~2 s.
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "qa_b200.h"
 #include "qa_common.cuh"
@@ -225,6 +226,122 @@ __global__ void __launch_bounds__(PA_THREADS) k_peer_allreduce(const __grid_cons
     PSTAMP(4);
 }
 
+// ------------------------------------------------------------------------------------------------------------------------------
+// Variant for more than two ranks: the owner writes the plain sums into slice r of ALL arenas and a second flag barrier behind a
+// system-scope release publishes them.  The flagged-word version above doubles the write-back bytes and pushes them to W - 1
+// peers: at 8 ranks it measured 43.1 us per call against 34.1 us for this one (profiles/r2_k31_phase_trace.txt); at 2 ranks
+// 17.0 against 20.8.  Epochs advance by two per call here.
+// ------------------------------------------------------------------------------------------------------------------------------
+// CTA-wide barrier with the same CTA of every other rank.  Thread q < W signals rank q and waits for rank q's signal.
+// `publish`: this CTA has written peer memory that the other side reads after the barrier.  Then EVERY thread fences its own
+// stores at system scope first (in parallel: one NVLink round trip; a single thread's fence after the __syncthreads measured
+// 8 us, profiles/r2_k31_phase_trace.txt) and the flag goes out relaxed behind the CTA barrier.  Without `publish` (barrier 1:
+// what the peers read was written by earlier kernels of this stream) no fence is needed at all.
+__device__ __forceinline__ void peer_barrier_fence(const QaPeerAllreduceArgs& a, unsigned value, bool publish) {
+    if (publish) asm volatile("fence.acq_rel.sys;" ::: "memory");     // release is all that is needed (not membar.sys = fence.sc.sys)
+    __syncthreads();
+    const int q = threadIdx.x;
+    if (q < a.world_size) {
+        st_relaxed_sys(a.ctrl[q] + PA_FLAG(blockIdx.x, a.rank), value);
+        const unsigned* mine = a.ctrl[a.rank] + PA_FLAG(blockIdx.x, q);
+        long long t0 = 0;
+        unsigned spins = 0;
+        while ((int)(ld_acquire_sys(mine) - value) < 0) {               // monotonic epochs, wrap safe
+            if ((++spins & 4095u) == 0u) {
+                long long t;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                if (t0 == 0) t0 = t;
+                else if (t - t0 > 2000000000LL) __trap();
+            }
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(PA_THREADS) k_peer_allreduce_fence(const __grid_constant__ QaPeerAllreduceArgs a) {
+    __shared__ float s_red[2][PA_THREADS / 32];
+    const int W = a.world_size, r = a.rank;
+    unsigned* my_ctrl = a.ctrl[r];
+    const unsigned epoch = my_ctrl[PA_EPOCH(blockIdx.x)];               // written only by this CTA (thread 0, at the end)
+    peer_barrier_fence(a, epoch + 1u, false);
+    // slice r, in float4 units; this CTA's share of it
+    const long long n4 = a.n / 4;                                       // n % 4 == 0 (checked at launch)
+    const long long per = (n4 + W - 1) / W;
+    const long long lo = (long long)r * per, hi = min(n4, lo + per);
+    float sq0 = 0.f, sq1 = 0.f;
+    constexpr int U = 2;                                                // float4s per thread in flight per peer: NVLink round trips are
+    const long long stride = (long long)PA_CTAS * PA_THREADS;           // ~2-3 us, so the loads of a whole pass are issued before any use
+    for (long long i0 = lo + (long long)blockIdx.x * PA_THREADS + threadIdx.x; i0 < hi; i0 += stride * U) {
+        float4 s[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long i = i0 + u * stride;
+            // .cg: peer lines must not be served from this SM's L1 (a previous step's copy of the same addresses)
+            s[u] = i < hi ? __ldcg(reinterpret_cast<const float4*>(a.arena[0]) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        for (int p = 1; p < W; ++p) {
+            float4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const long long i = i0 + u * stride;
+                v[u] = i < hi ? __ldcg(reinterpret_cast<const float4*>(a.arena[p]) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) s[u].x += v[u].x, s[u].y += v[u].y, s[u].z += v[u].z, s[u].w += v[u].w;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long i = i0 + u * stride;
+            if (i >= hi) continue;
+            for (int p = 0; p < W; ++p) reinterpret_cast<float4*>(a.arena[p])[i] = s[u];
+            const float c4[4] = {s[u].x, s[u].y, s[u].z, s[u].w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const long long idx = i * 4 + k;
+                if (idx < a.seg_split) sq0 += c4[k] * c4[k];
+                else if (idx < a.norm_end) sq1 += c4[k] * c4[k];
+            }
+        }
+    }
+    // CTA partial norms -> every rank's control block (row of this CTA, column of this rank)
+    sq0 = warp_sum(sq0), sq1 = warp_sum(sq1);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) s_red[0][warp] = sq0, s_red[1][warp] = sq1;
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < PA_THREADS / 32; ++k) t += s_red[threadIdx.x][k];
+        for (int p = 0; p < W; ++p) reinterpret_cast<float*>(a.ctrl[p])[PA_NORM(blockIdx.x, r, threadIdx.x)] = t;      // (low word of the slot)
+    }
+    peer_barrier_fence(a, epoch + 2u, true);
+    __shared__ unsigned s_last;
+    if (threadIdx.x == 0) {
+        my_ctrl[PA_EPOCH(blockIdx.x)] = epoch + 2u;
+        __threadfence();
+        s_last = (atomicAdd(my_ctrl + PA_TICKET, 1u) == PA_CTAS - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x < 64) {
+        // every CTA of this rank has passed barrier 2, i.e. the partial norms of all CTAs of all ranks have landed: warp k adds
+        // the PA_CTAS x W partials of segment k -- lane = CTA rows lane, lane + 32, ..., ranks in order, then a fixed xor
+        // butterfly: the same order on every rank, fp64 like K8's own norm pass
+        __threadfence();
+        const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const volatile float* c = reinterpret_cast<const volatile float*>(my_ctrl);
+        double t = 0.0;
+        for (int b = lane; b < PA_CTAS; b += 32)
+            for (int p = 0; p < W; ++p) t += (double)c[PA_NORM(b, p, k)];
+        t = warp_sum_d(t);
+        if (lane == 0 && a.sumsq_out[k] != nullptr) {
+            *a.sumsq_out[k] = t * (double)a.grad_scale * (double)a.grad_scale;
+            if (a.step_inc[k] != nullptr) *a.step_inc[k] += 1;
+        }
+        if (threadIdx.x == 1 && a.scale_index >= 0) a.arena[r][a.scale_index] *= a.grad_scale;
+        if (threadIdx.x == 0) my_ctrl[PA_TICKET] = 0u;
+    }
+}
+
 // bytes of one rank's control block for an arena of n floats: flags + flagged norms + epochs + ticket + staging (8 B per element)
 extern "C" long long qa_peer_ctrl_bytes(long long n) { return (long long)PA_STAGE_WORD * 4 + (n > 0 ? n : 0) * 8; }
 
@@ -239,7 +356,13 @@ extern "C" int qa_peer_allreduce(const QaPeerAllreduceArgs* a, void* stream) {
         if (reinterpret_cast<uintptr_t>(a->arena[p]) & 15u) return QA_EINVAL;
     }
     if (a->scale_index >= a->n) return QA_EINVAL;
-    k_peer_allreduce<<<PA_CTAS, PA_THREADS, 0, (cudaStream_t)stream>>>(*a);
+    static int ll_max = -1;                                          // QA_PEER_LL_MAX: largest world size served by the flagged-word version
+    if (ll_max < 0) {
+        const char* e = getenv("QA_PEER_LL_MAX");
+        ll_max = e != nullptr ? atoi(e) : 2;
+    }
+    if (a->world_size <= ll_max) k_peer_allreduce<<<PA_CTAS, PA_THREADS, 0, (cudaStream_t)stream>>>(*a);
+    else k_peer_allreduce_fence<<<PA_CTAS, PA_THREADS, 0, (cudaStream_t)stream>>>(*a);
     QA_LAUNCH_RET();
 }
 
