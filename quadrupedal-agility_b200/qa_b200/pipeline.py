@@ -181,6 +181,9 @@ class BbcIteration:
         if key not in self._rollout_graphs:
             self._rollout_graphs[key] = self._capture_rollout(host)
         g, n = self._rollout_graphs[key]
+        alg = self.runner.alg
+        if self.env.task_obs_weight_decay and hasattr(alg, "_task_obs_weight_dev"):
+            alg._task_obs_weight_dev(refresh=True)       # K18 reads the (decaying) weight from this device scalar: a replay sees today's
         g.replay()
         ops._count(n)
         self.runner.alg.flush_disc_stage()
