@@ -190,6 +190,9 @@ def _arena_worker(rank, world, port, q):
         os.environ["QA_SINGLE_ALLREDUCE"] = "1" if arena else "0"          # the arena is the default with > 1 rank
         alg, env, norm = TD._alg(False, "MSELoss")
         assert (alg._grad_arena is not None) == arena
+        # the peer-memory all-reduce (K31) is for NCCL groups on CUDA devices of one node; here the arena falls back to the
+        # process group's all-reduce
+        assert not qdist.PeerArena.available() and getattr(alg, "_peer", None) is None
         g = torch.Generator().manual_seed(100 + rank)
         alg.ac_flat.grad.copy_(torch.randn(alg.ac_flat.numel, generator=g))
         alg.est_flat.grad.copy_(torch.randn(alg.est_flat.numel, generator=g))
