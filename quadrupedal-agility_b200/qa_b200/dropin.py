@@ -111,7 +111,7 @@ def mocap_from_reference(ref_env):
     from .mocap import MocapTable
     ml = ref_env.motion_loader
     files = list(getattr(ml, "motion_files_lb", None) or ref_env.cfg.env.motion_files_lb)
-    return MocapTable.from_json_files(sorted(files))
+    return MocapTable.from_json_files(files)          # the loader's own clip order (motion_loader.py:111): clip ids stay the same
 
 
 def from_reference_env(ref_env, device: Optional[str] = None, physics=None, mocap=None, seed: Optional[int] = None, **kw):
