@@ -16,7 +16,7 @@ the hot path to this package:
     from qa_b200.dropin import make_task_class
     task_registry.register("go2_locomotion", make_task_class(RefLeggedRobot), Go2LocomotionCfg(), Go2LocomotionCfgAlgo())
 
-`oracle/check_interop.py dropin` (build container) runs the extraction over the reference env the parity harness builds and
+`oracle/check_dropin.py` (build container) runs the extraction over the reference env the parity harness builds and
 checks the round trip against the values that were injected.
 """
 from typing import Dict, Optional
